@@ -1,0 +1,115 @@
+"""Pins the CPU oracle against the reference's own known-answer tests."""
+import numpy as np
+import pytest
+
+from momentum_b200 import character as mc
+from oracle.binding import OracleFunction
+
+
+def _dummy_pos(ch, B=1):
+    return mc.PositionErrorFunction(np.array([2], np.int32), np.array([[0, 1, 0]], np.float64), np.array([1.0]), np.zeros((B, 1, 3)))
+
+
+@pytest.mark.parametrize("dtype,tol", [("float32", 1e-6), ("float64", 5e-7)])
+@pytest.mark.parametrize("J", [3, 4, 22, 129, 512])
+def test_ka1_fk_golden_vector(dtype, tol, J):
+    # momentum/test/character/forward_kinematics_test.cpp:78-87
+    ch = mc.create_test_character(J)
+    fn = OracleFunction(ch, [_dummy_pos(ch)], dtype)
+    theta = np.zeros(ch.num_params)
+    theta[:10] = [1.0, 1.0, 1.0, np.pi, 0.0, -np.pi, 0.1, np.pi, np.pi, -np.pi]
+    if dtype == "float32":
+        theta = theta.astype(np.float32).astype(np.float64)
+    xf, _, _ = fn.fk(theta)
+    t, q, s = xf[2, :3], xf[2, 3:7], xf[2, 7]
+    p = mc._qrot(q, s * np.ones(3)) + t
+    assert np.linalg.norm(p - np.array([-1.14354682, 3.14354706, -0.0717732906])) <= tol
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_ka2_rest_pose_identities(dtype):
+    # forward_kinematics_test.cpp:60-76
+    ch = mc.create_test_character(7)
+    fn = OracleFunction(ch, [_dummy_pos(ch)], dtype)
+    xf, ra, ta = fn.fk(np.zeros(ch.num_params))
+    for j in range(7):
+        assert np.array_equal(xf[j, 3:7], [0, 0, 0, 1])
+        assert xf[j, 7] == 1.0
+        assert np.array_equal(ra[j], np.eye(3)) and np.array_equal(ta[j], np.eye(3))
+        assert np.allclose(xf[j, :3], [0, j, 0], atol=1e-6)
+
+
+def _quat_axis(k, a):
+    q = np.zeros(4); q[k] = np.sin(a / 2); q[3] = np.cos(a / 2)
+    return q
+
+
+def test_ka3_rotation_order_and_derivative_axes():
+    # joint_state_test.cpp:566-594 (rz*ry*rx), :101-155 (translationAxis == parent.toLinear()), :597-623 (ln2)
+    ch = mc.create_test_character(3)
+    # give joint 1 all of rx ry rz by editing the transform: use root rx,ry,rz instead (params 3,4,5)
+    fn = OracleFunction(ch, [_dummy_pos(ch)], "float64")
+    theta = np.zeros(ch.num_params)
+    rx, ry, rz = np.pi / 4, np.pi / 3, np.pi / 6
+    theta[3:6] = [rx, ry, rz]
+    theta[6] = 0.5
+    xf, ra, ta = fn.fk(theta)
+    expect = mc._qmul(mc._qmul(_quat_axis(2, rz), _quat_axis(1, ry)), _quat_axis(0, rx))
+    assert np.allclose(xf[0, 3:7], expect, atol=1e-14)
+    assert np.isclose(xf[0, 7], 2 ** 0.5)
+    # child's translationAxis is parent's linear part s*R
+    R = np.stack([mc._qrot(expect, e) for e in np.eye(3)], 1)
+    assert np.allclose(ta[1], (2 ** 0.5) * R, atol=1e-13)
+    # rotation axes of the root: z axis is world z; y axis = Rz * y; x axis = Rz*Ry * x
+    assert np.allclose(ra[0][:, 2], [0, 0, 1])
+    assert np.allclose(ra[0][:, 1], mc._qrot(_quat_axis(2, rz), np.array([0, 1.0, 0])))
+    assert np.allclose(ra[0][:, 0], mc._qrot(mc._qmul(_quat_axis(2, rz), _quat_axis(1, ry)), np.array([1.0, 0, 0])))
+
+
+@pytest.mark.parametrize("dtype,e_rest,e_tgt,d_tgt", [("float32", 1e-7, 5e-7, 5e-5), ("float64", 1e-15, 1e-8, 1e-5)])
+def test_ka4_three_joint_ik(dtype, e_rest, e_tgt, d_tgt):
+    # momentum/test/character_solver/inverse_kinematics_test.cpp:38-123
+    ch = mc.create_test_character(3)
+    rest_target = np.array([[[0.0, 3.0, 0.0]]])
+    pos = mc.PositionErrorFunction(np.array([2], np.int32), np.array([[0.0, 1.0, 0.0]]), np.array([1.0]), rest_target)
+    fn = OracleFunction(ch, [pos], dtype)
+    kw = dict(min_iterations=6, max_iterations=6, threshold=1.0, regularization=1e-7, use_block_jtj=True)
+    err, p, it, hist = fn.solve(np.zeros(ch.num_params), **kw)
+    assert err <= e_rest and np.linalg.norm(p) <= e_rest
+    rng = np.random.default_rng(12345)
+    params = np.zeros(ch.num_params)
+    for _ in range(10):
+        tgt = rng.uniform(-1, 1, 3) * 3
+        if dtype == "float32":
+            tgt = tgt.astype(np.float32).astype(np.float64)
+        pos.targets = tgt[None, None]
+        fn.select_instance(0)
+        err, params, it, hist = fn.solve(params, **kw)
+        assert it == 6
+        assert err <= e_tgt
+        assert np.linalg.norm(params) >= e_rest
+        p = mc.world_points(ch, params[None], [2], [[0, 1.0, 0]])[0, 0]
+        assert np.linalg.norm(p - tgt) <= d_tgt
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+@pytest.mark.parametrize("use_block", [False, True])
+def test_ka5_block_jtj_equivalence_with_noncontiguous_enabled_subset(dtype, use_block):
+    # gauss_newton_solver_test.cpp:757-880: useBlockJtJ on/off must agree (1e-6 error / 1e-4 params)
+    ch = mc.create_test_character(8)
+    rng = np.random.default_rng(7)
+    theta_star = rng.uniform(-0.4, 0.4, (1, ch.num_params)); theta_star[0, 6] = 0
+    parents = np.array([3, 5, 7], np.int32)
+    offs = rng.uniform(-1, 1, (3, 3))
+    tg = mc.world_points(ch, theta_star, parents, offs)
+    pos = mc.PositionErrorFunction(parents, offs, np.ones(3), tg)
+    results = []
+    for ub in (False, True):
+        fn = OracleFunction(ch, [pos], dtype)
+        en = np.ones(ch.num_params, bool); en[[1, 6, 9, 12]] = False
+        fn.set_enabled_parameters(en)
+        err, p, it, hist = fn.solve(np.zeros(ch.num_params), min_iterations=4, max_iterations=8, regularization=0.05, use_block_jtj=ub)
+        assert np.all(p[[1, 6, 9, 12]] == 0)
+        results.append((err, p))
+    assert abs(results[0][0] - results[1][0]) <= 1e-6
+    assert np.max(np.abs(results[0][1] - results[1][1])) <= 1e-4
