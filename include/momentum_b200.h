@@ -1,0 +1,208 @@
+/*
+ * momentum_b200 — C-ABI of the B200-native batched Gauss-Newton IK path.
+ *
+ * This is the drop-in boundary for ONE hot path of facebookresearch/momentum: the per-iteration
+ * FK sweep -> residual/Jacobian (Position / Orientation / State / Limit) -> JtJ, Jtr -> damped
+ * Cholesky -> parameter update, for a BATCH of independent IK instances that share one rig and one
+ * constraint topology (the body of the dispenso::parallel_for at
+ * pymomentum/tensor_ik/tensor_ik.cpp:127-177). Every entry point below names the reference
+ * interface it stands in for (paths relative to the reference's momentum/ directory).
+ *
+ * Conventions
+ *  - plain C types only; no C++/torch types cross this boundary.
+ *  - every function returns MB2_OK (0) or an error code; mb2_last_error() gives the message of the
+ *    last failure on the calling thread (reference: MT_CHECK/MT_THROW -> std::runtime_error,
+ *    common/checks.h:36, common/exception.h:31; adapters rethrow).
+ *  - host pointers unless the name says _device. Host inputs are copied during the call and never
+ *    retained (reference ownership: the solver holds non-owning pointers, solver/solver.h:106).
+ *  - handles are not thread-safe; one handle = one CUDA stream (reference: one solver + function per
+ *    thread, tensor_ik.cpp:127-162; mutable scratch in skeleton_solver_function.h:89).
+ *  - quaternions are (x, y, z, w) like Eigen::Quaternion::coeffs().
+ *  - batched arrays are instance-major: [B][...].
+ *  - there is no CPU fallback: every compute entry point fails with MB2_ERR_CUDA when no sm_100
+ *    device is usable.
+ */
+#ifndef MOMENTUM_B200_H_
+#define MOMENTUM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB2_PARAMETERS_PER_JOINT 7   /* character/types.h:21 kParametersPerJoint */
+#define MB2_MAX_MODEL_PARAMETERS 2048 /* math/types.h:426-429 ParameterSet = std::bitset<2048> */
+#define MB2_PARAMETER_SET_WORDS 32   /* 2048 / 64 */
+
+typedef enum mb2_status {
+  MB2_OK = 0,
+  MB2_ERR_INVALID_ARGUMENT = 1, /* MT_CHECK failure in the reference */
+  MB2_ERR_CUDA = 2,             /* CUDA runtime error / no usable device (no CPU fallback) */
+  MB2_ERR_UNSUPPORTED = 3
+} mb2_status;
+
+/* Per-instance result status of a batched solve (reference: NaN/Inf guard of the batched caller,
+ * tensor_ik.cpp:168-173; LLT info is ignored by the dense solver, gauss_newton_solver.cpp:251). */
+typedef enum mb2_instance_status {
+  MB2_INSTANCE_OK = 0,
+  MB2_INSTANCE_CHOLESKY_BREAKDOWN = 1, /* a non-positive pivot was met (Eigen: NumericalIssue) */
+  MB2_INSTANCE_NON_FINITE = 2          /* parameters became NaN/Inf */
+} mb2_instance_status;
+
+/* character/parameter_limits.h:20-33 LimitType */
+typedef enum mb2_limit_type {
+  MB2_LIMIT_MINMAX = 0,
+  MB2_LIMIT_MINMAX_JOINT = 1,
+  MB2_LIMIT_MINMAX_JOINT_PASSIVE = 2,
+  MB2_LIMIT_LINEAR = 3,
+  MB2_LIMIT_LINEAR_JOINT = 4,
+  MB2_LIMIT_ELLIPSOID = 5,
+  MB2_LIMIT_HALFPLANE = 6
+} mb2_limit_type;
+
+/* character/parameter_limits.h:117-127 ParameterLimit, flattened.
+ *  MinMax:      i[0]=parameterIndex, f[0..1]=limits
+ *  MinMaxJoint: i[0]=jointIndex, i[1]=jointParameter, f[0..1]=limits
+ *  Linear:      i[0]=referenceIndex, i[1]=targetIndex, f[0]=scale, f[1]=offset, f[2]=rangeMin, f[3]=rangeMax
+ *  LinearJoint: i[0..1]=reference joint/param, i[2..3]=target joint/param, f[0..3] as Linear
+ *  HalfPlane:   i[0]=param1, i[1]=param2, f[0..1]=normal, f[2]=offset
+ *  Ellipsoid:   i[0]=ellipsoidParent, i[1]=parent, f[0..11]=ellipsoid 3x4 row-major, f[12..23]=ellipsoidInv, f[24..26]=offset */
+typedef struct mb2_parameter_limit {
+  int32_t type;
+  float weight;
+  int32_t i[4];
+  float f[27];
+} mb2_parameter_limit;
+
+/* state_error_function.h:17-32 RotationErrorType */
+typedef enum mb2_rotation_error_type {
+  MB2_ROTATION_MATRIX_DIFFERENCE = 0,
+  MB2_QUATERNION_LOG_MAP = 1
+} mb2_rotation_error_type;
+
+/* How JtJ is formed on the device (extension; the reference always uses Eigen fp32/fp64 GEMM). */
+typedef enum mb2_jtj_mode {
+  MB2_JTJ_AUTO = 0,      /* tensor-core 3xTF32 where the shape allows, else FP32 SIMT */
+  MB2_JTJ_FP32_SIMT = 1, /* CUDA-core fp32 (validation path) */
+  MB2_JTJ_TF32X3 = 2,    /* tcgen05 kind::tf32, 3-term split, fp32 accumulate in TMEM (fp32-class accuracy) */
+  MB2_JTJ_TF32 = 3       /* tcgen05 kind::tf32 single pass (~1e-3 relative; changes the GN path, not the fixed point) */
+} mb2_jtj_mode;
+
+/* solver/solver.h:19-34 SolverOptions + solver/gauss_newton_solver.h:17-59 GaussNewtonSolverOptions,
+ * field for field, plus device extensions at the end. */
+typedef struct mb2_gauss_newton_options {
+  uint64_t min_iterations;        /* SolverOptions::minIterations = 1 */
+  uint64_t max_iterations;        /* SolverOptions::maxIterations = 2 */
+  float threshold;                /* SolverOptions::threshold = 1.0f */
+  int32_t verbose;                /* SolverOptions::verbose */
+  float regularization;           /* GaussNewtonSolverBaseOptions::regularization = 0.05f */
+  int32_t do_line_search;         /* ::doLineSearch = false */
+  int32_t use_block_jtj;          /* ::useBlockJtJ = false (same normal equations either way) */
+  uint64_t target_rows_per_chunk; /* ::targetRowsPerChunk = SIZE_MAX (accepted, no effect on results) */
+  int32_t subset_line_search;     /* 1 = SubsetGaussNewtonSolverT line search (c1=1e-4, g.delta), subset_gauss_newton_solver.cpp:119-141 */
+  int32_t jtj_mode;               /* mb2_jtj_mode */
+  int32_t store_error_history;    /* keep per-iteration error per instance (solver.h:90 getErrorHistory) */
+  int32_t reserved;
+} mb2_gauss_newton_options;
+
+typedef struct mb2_character mb2_character;             /* Skeleton + ParameterTransform + ParameterLimits on device */
+typedef struct mb2_solver_function mb2_solver_function; /* batch of B SkeletonSolverFunctionT<float> */
+typedef struct mb2_solver mb2_solver;                   /* batch of B GaussNewtonSolverT<float> */
+
+const char* mb2_last_error(void);
+/* number of usable sm_100 devices (0 => every compute call fails with MB2_ERR_CUDA) */
+int mb2_device_count(void);
+void mb2_default_gauss_newton_options(mb2_gauss_newton_options* opt);
+
+/* ---- Character: Skeleton (character/skeleton.h:22-77, joint.h:18-76) + ParameterTransform
+ * (character/parameter_transform.h:62-184; CSR rows = 7*num_joints) ------------------------------- */
+int mb2_character_create(int device, int32_t num_joints, const int32_t* parents /*[J], -1 root*/,
+                         const float* translation_offsets /*[J*3]*/, const float* pre_rotations /*[J*4] xyzw*/,
+                         int32_t num_model_parameters, const int32_t* transform_outer /*[7J+1]*/,
+                         const int32_t* transform_inner /*[nnz]*/, const float* transform_values /*[nnz]*/,
+                         const float* transform_offsets /*[7J]*/, mb2_character** out);
+/* ParameterLimits consumed by LimitErrorFunctionT (character/parameter_limits.h:129) */
+int mb2_character_set_parameter_limits(mb2_character* c, int32_t count, const mb2_parameter_limit* limits);
+void mb2_character_destroy(mb2_character* c);
+
+/* ---- SkeletonSolverFunctionT<float> x B (character_solver/skeleton_solver_function.h:21-95) ---- */
+int mb2_solver_function_create(const mb2_character* c, int32_t batch, mb2_solver_function** out);
+void mb2_solver_function_destroy(mb2_solver_function* f);
+int32_t mb2_solver_function_num_parameters(const mb2_solver_function* f);    /* getNumParameters */
+int32_t mb2_solver_function_actual_parameters(const mb2_solver_function* f); /* getActualParameters */
+int32_t mb2_solver_function_batch(const mb2_solver_function* f);
+/* getJacobianBlockSize summed and padded to 8 (solver_function.cpp:33-38) */
+int32_t mb2_solver_function_jacobian_rows(const mb2_solver_function* f);
+/* row stride (leading dimension) of device Jacobian columns */
+int32_t mb2_solver_function_jacobian_stride(const mb2_solver_function* f);
+
+/* addErrorFunction(PositionErrorFunctionT) — position_error_function.h:16-73. Constraint topology
+ * (parent, offset, weight) is shared by the batch; targets are per instance. Returns block index. */
+int mb2_add_position_error_function(mb2_solver_function* f, float weight, float loss_alpha, float loss_c,
+                                    int32_t num_constraints, const int32_t* parents, const float* offsets /*[nc*3]*/,
+                                    const float* weights /*[nc]*/, int32_t* out_index);
+/* addErrorFunction(OrientationErrorFunctionT / OrientationRotDiffErrorFunctionT) —
+ * orientation_error_function.h:16-108; offsets are normalised as in OrientationDataT's ctor. */
+int mb2_add_orientation_error_function(mb2_solver_function* f, float weight, float loss_alpha, float loss_c,
+                                       int32_t rot_diff, int32_t num_constraints, const int32_t* parents,
+                                       const float* offsets /*[nc*4]*/, const float* weights /*[nc]*/, int32_t* out_index);
+/* addErrorFunction(StateErrorFunctionT) — state_error_function.h:35-117 (setWeights, setTargetWeights) */
+int mb2_add_state_error_function(mb2_solver_function* f, float weight, int32_t rotation_error_type, float pos_wgt,
+                                 float rot_wgt, const float* target_position_weights /*[J]*/,
+                                 const float* target_rotation_weights /*[J]*/, int32_t* out_index);
+/* addErrorFunction(LimitErrorFunctionT) over the character's limits — limit_error_function.h:25-119 */
+int mb2_add_limit_error_function(mb2_solver_function* f, float weight, float loss_alpha, float loss_c, int32_t* out_index);
+/* SkeletonErrorFunctionT::setWeight (skeleton_error_function.h:45-47) */
+int mb2_set_error_function_weight(mb2_solver_function* f, int32_t index, float weight);
+/* Per-instance targets: Position [B*nc*3] (setConstraints targets), Orientation [B*nc*4] xyzw
+ * (normalised on upload), State [B*J*8] = (t, q xyzw, s) (setTargetState). */
+int mb2_set_targets(mb2_solver_function* f, int32_t index, const float* targets);
+int mb2_set_targets_device(mb2_solver_function* f, int32_t index, const float* targets_device, void* cuda_stream);
+/* Optional per-instance constraint weights [B*nc] for a Position/Orientation block (ConstraintData::weight) */
+int mb2_set_constraint_weights(mb2_solver_function* f, int32_t index, const float* weights, int32_t per_instance);
+/* SolverFunctionT::setEnabledParameters(ParameterSet) — skeleton_solver_function.cpp:45-61 */
+int mb2_solver_function_set_enabled_parameters(mb2_solver_function* f, const uint64_t bits[MB2_PARAMETER_SET_WORDS]);
+
+/* SolverFunctionT::getError — skeleton_solver_function.cpp:64-83 (value rounded through float). */
+int mb2_solver_function_get_error(mb2_solver_function* f, const float* parameters /*[B*n]*/, double* errors /*[B]*/);
+/* SolverFunctionT::getJacobian — solver_function.cpp:22-71. jacobian [B][n][rows] (column-major per
+ * instance, rows = mb2_solver_function_jacobian_rows), residual [B][rows]. */
+int mb2_solver_function_get_jacobian(mb2_solver_function* f, const float* parameters, float* jacobian, float* residual,
+                                     double* errors, int32_t* actual_rows);
+/* SolverFunctionT::getJtJR — solver_function.cpp:74-121. jtj [B][ap][ap] (lower triangle valid,
+ * ap = actual parameters), jtr [B][ap]. */
+int mb2_solver_function_get_jtjr(mb2_solver_function* f, const float* parameters, int32_t jtj_mode, float* jtj, float* jtr,
+                                 double* errors);
+/* Skeleton state after initializeJacobianComputation (skeleton_state.cpp:87-121): [B][J][8] (t,q,s) */
+int mb2_solver_function_get_skeleton_state(mb2_solver_function* f, const float* parameters, float* state);
+
+/* ---- GaussNewtonSolverT<float> x B (solver/gauss_newton_solver.h:67-137, solver/solver.h:36-100) ---- */
+int mb2_solver_create(mb2_solver_function* f, const mb2_gauss_newton_options* opt, mb2_solver** out);
+void mb2_solver_destroy(mb2_solver* s);
+int mb2_solver_set_options(mb2_solver* s, const mb2_gauss_newton_options* opt); /* setOptions */
+/* SolverT::setEnabledParameters — solver.cpp:41-48 (forwards to the solver function) */
+int mb2_solver_set_enabled_parameters(mb2_solver* s, const uint64_t bits[MB2_PARAMETER_SET_WORDS]);
+/* SolverT::solve for every instance — solver.cpp:50-128. parameters [B*n] in/out (host). errors[b] is
+ * the objective before the last update (what solve() returns); iterations[b] = number of
+ * doIteration calls; status[b] = mb2_instance_status. Any of errors/iterations/status may be NULL. */
+int mb2_solver_solve(mb2_solver* s, float* parameters, double* errors, int32_t* iterations, int32_t* status);
+/* Same with parameters resident on the device; asynchronous on `cuda_stream` (NULL = handle stream).
+ * Results are fetched with mb2_solver_get_results after synchronising. */
+int mb2_solver_solve_device(mb2_solver* s, float* parameters_device, void* cuda_stream);
+int mb2_solver_get_results(mb2_solver* s, double* errors, int32_t* iterations, int32_t* status);
+/* getErrorHistory (solver.h:90): [B][max_iterations], valid up to iterations[b] */
+int mb2_solver_get_error_history(mb2_solver* s, double* history);
+/* sum over the batch of iterations executed / kernels launched by the last solve (for throughput) */
+int mb2_solver_get_counters(mb2_solver* s, uint64_t* total_iterations, uint64_t* kernel_launches);
+/* device time of the dominant kernels in the last solve, milliseconds (CUDA events on the handle's
+ * stream); index: 0 = FK+Jacobian, 1 = JtJ/Jtr, 2 = Cholesky/update, 3 = error-only. Enabled by
+ * mb2_solver_set_profiling(s, 1); off by default (events serialise the stream). */
+int mb2_solver_set_profiling(mb2_solver* s, int32_t enabled);
+int mb2_solver_get_phase_times(mb2_solver* s, double ms[4], uint64_t launches[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOMENTUM_B200_H_ */

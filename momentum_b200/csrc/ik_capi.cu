@@ -1,0 +1,892 @@
+// C-ABI of momentum_b200 (include/momentum_b200.h): handle management, host<->device plumbing and
+// the batched SolverT::solve driver. No CPU fallback: every compute entry fails with MB2_ERR_CUDA
+// when no sm_100 device is usable.
+#include "../../include/momentum_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "ik_jtj_tc.cuh"
+#include "ik_kernels.cuh"
+#include "ik_plan.h"
+
+using namespace mb2;
+
+namespace {
+
+thread_local std::string g_lastError;
+
+int fail(int code, const std::string& msg) {
+  g_lastError = msg;
+  return code;
+}
+#define MB2_CUDA(expr)                                                                                  \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess) return fail(MB2_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+#define MB2_CHECK(cond, msg)                                   \
+  do {                                                         \
+    if (!(cond)) return fail(MB2_ERR_INVALID_ARGUMENT, (msg)); \
+  } while (0)
+
+template <class T>
+struct DeviceBuffer {
+  T* p{nullptr};
+  size_t n{0};
+  ~DeviceBuffer() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  cudaError_t resize(size_t count) {
+    if (count <= n && p) return cudaSuccess;
+    release();
+    if (count == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+  cudaError_t upload(const std::vector<T>& v, cudaStream_t s) {
+    cudaError_t e = resize(std::max<size_t>(v.size(), 1));
+    if (e != cudaSuccess || v.empty()) return e;
+    return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+  }
+};
+
+int roundUp(int v, int m) { return (v + m - 1) / m * m; }
+
+} // namespace
+
+struct mb2_character {
+  int device{0};
+  HostCharacter host;
+  DeviceBuffer<int32_t> parent, ptOuter, ptInner, levelStart, levelJoints;
+  DeviceBuffer<float> offset, prerot, ptVals, ptOffsets;
+  uint64_t limitsVersion{0};
+};
+
+struct mb2_solver_function {
+  const mb2_character* ch{nullptr};
+  int B{0};
+  cudaStream_t stream{nullptr};
+  std::vector<HostErrorFunction> efs;
+  std::vector<uint8_t> enabled;
+  int targetStride{0}, numWeights{0};
+  bool weightsPerInstance{false};
+  bool planDirty{true};
+  uint64_t planLimitsVersion{~0ull};
+  Plan plan;
+  int ldJ{32};
+  // device tables
+  DeviceBuffer<EfDesc> dEfs;
+  DeviceBuffer<UnitDesc> dUnits;
+  DeviceBuffer<CellDesc> dCells;
+  DeviceBuffer<ContribDesc> dContribs;
+  DeviceBuffer<float> dLimitData;
+  DeviceBuffer<int32_t> dEnabledList, dIdentity;
+  // device data
+  DeviceBuffer<float> dTargets, dWeights, dJ, dResidual, dTheta, dState, dH;
+  DeviceBuffer<double> dErrors;
+  std::vector<float> hWeights; // shared weights mirror
+  FunctionTables tables() const;
+};
+
+struct PhaseEvent {
+  cudaEvent_t start, stop;
+  int phase;
+};
+
+struct mb2_solver {
+  mb2_solver_function* fn{nullptr};
+  mb2_gauss_newton_options opt{};
+  DeviceBuffer<float> dH, dDelta, dThetaOrig, dTheta0, dScale, dGradDotDelta, dThetaStage;
+  DeviceBuffer<double> dLastErrors, dTrialErrors, dHistory;
+  DeviceBuffer<int32_t> dActive, dIterations, dStatus, dSearching, dActiveCount;
+  int* hActiveCount{nullptr}; // pinned
+  uint64_t totalIterations{0}, kernelLaunches{0};
+  bool profiling{false};
+  std::vector<PhaseEvent> events;
+  double phaseMs[4]{0, 0, 0, 0};
+  uint64_t phaseLaunches[4]{0, 0, 0, 0};
+  size_t historyStride{0};
+  ~mb2_solver() {
+    if (hActiveCount) cudaFreeHost(hActiveCount);
+    for (auto& e : events) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }
+  }
+};
+
+FunctionTables mb2_solver_function::tables() const {
+  FunctionTables T{};
+  const HostCharacter& h = ch->host;
+  T.numJoints = h.numJoints;
+  T.numParams = h.numParams;
+  T.parent = ch->parent.p;
+  T.offset = ch->offset.p;
+  T.prerot = ch->prerot.p;
+  T.ptOuter = ch->ptOuter.p;
+  T.ptInner = ch->ptInner.p;
+  T.ptVals = ch->ptVals.p;
+  T.ptOffsets = ch->ptOffsets.p;
+  T.numLevels = int(h.levelStart.size()) - 1;
+  T.levelStart = ch->levelStart.p;
+  T.levelJoints = ch->levelJoints.p;
+  T.numEf = int(plan.efs.size());
+  T.numUnits = int(plan.units.size());
+  T.numCells = int(plan.cells.size());
+  T.efs = dEfs.p;
+  T.units = dUnits.p;
+  T.cells = dCells.p;
+  T.contribs = dContribs.p;
+  T.limitData = dLimitData.p;
+  T.targetStride = targetStride;
+  T.recStride = plan.recStride;
+  T.numRows = plan.numRows;
+  T.ldJ = ldJ;
+  T.weightsPerInstance = weightsPerInstance ? 1 : 0;
+  T.numWeights = numWeights;
+  return T;
+}
+
+namespace {
+
+bool g_deviceChecked = false;
+int g_usableDevices = 0;
+
+int usableDevices() {
+  if (!g_deviceChecked) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { n = 0; cudaGetLastError(); }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+      int major = 0;
+      if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++ok;
+    }
+    g_usableDevices = ok;
+    g_deviceChecked = true;
+  }
+  return g_usableDevices;
+}
+
+int requireDevice(int device) {
+  if (usableDevices() <= 0) return fail(MB2_ERR_CUDA, "no usable sm_100 CUDA device: momentum_b200 has no CPU fallback");
+  MB2_CUDA(cudaSetDevice(device));
+  MB2_CUDA(initKernelAttributes());
+  return MB2_OK;
+}
+
+int ensureTargets(mb2_solver_function* f) {
+  const size_t need = size_t(f->B) * std::max(f->targetStride, 1);
+  if (f->dTargets.n < need) {
+    DeviceBuffer<float> old;
+    std::swap(old.p, f->dTargets.p);
+    std::swap(old.n, f->dTargets.n);
+    MB2_CUDA(f->dTargets.resize(need));
+    MB2_CUDA(cudaMemsetAsync(f->dTargets.p, 0, need * sizeof(float), f->stream));
+    (void)old; // targets of blocks added earlier must be re-sent after adding blocks (documented)
+  }
+  return MB2_OK;
+}
+
+int uploadWeights(mb2_solver_function* f) {
+  if (!f->weightsPerInstance) {
+    std::vector<float> w = f->hWeights;
+    if (w.empty()) w.push_back(0.f);
+    MB2_CUDA(f->dWeights.upload(w, f->stream));
+  }
+  return MB2_OK;
+}
+
+int ensurePlan(mb2_solver_function* f) {
+  if (!f->planDirty && f->planLimitsVersion == f->ch->limitsVersion) return MB2_OK;
+  MB2_CUDA(cudaSetDevice(f->ch->device));
+  const std::string err = buildPlan(f->ch->host, f->efs, f->enabled, f->plan);
+  if (!err.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, err);
+  cudaStream_t s = f->stream;
+  MB2_CUDA(f->dEfs.upload(f->plan.efs, s));
+  MB2_CUDA(f->dUnits.upload(f->plan.units, s));
+  MB2_CUDA(f->dCells.upload(f->plan.cells, s));
+  MB2_CUDA(f->dContribs.upload(f->plan.contribs, s));
+  MB2_CUDA(f->dLimitData.upload(f->plan.limitData, s));
+  MB2_CUDA(f->dEnabledList.upload(f->plan.enabledList, s));
+  std::vector<int32_t> ident(f->ch->host.numParams);
+  for (size_t i = 0; i < ident.size(); ++i) ident[i] = int32_t(i);
+  MB2_CUDA(f->dIdentity.upload(ident, s));
+  f->ldJ = std::max(32, roundUp(f->plan.numRows, 32));
+  const size_t jElems = size_t(f->B) * f->ch->host.numParams * f->ldJ;
+  MB2_CUDA(f->dJ.resize(jElems));
+  // cells outside the plan are never written: zero once per plan (ResizeableMatrix::resizeAndSetZero
+  // happens every iteration in the reference, solver_function.cpp:96)
+  MB2_CUDA(cudaMemsetAsync(f->dJ.p, 0, jElems * sizeof(float), s));
+  MB2_CUDA(f->dResidual.resize(size_t(f->B) * f->ldJ));
+  MB2_CUDA(cudaMemsetAsync(f->dResidual.p, 0, size_t(f->B) * f->ldJ * sizeof(float), s));
+  MB2_CUDA(f->dErrors.resize(f->B));
+  MB2_CUDA(f->dTheta.resize(size_t(f->B) * f->ch->host.numParams));
+  int rc = ensureTargets(f);
+  if (rc != MB2_OK) return rc;
+  rc = uploadWeights(f);
+  if (rc != MB2_OK) return rc;
+  f->planDirty = false;
+  f->planLimitsVersion = f->ch->limitsVersion;
+  return MB2_OK;
+}
+
+SweepArgs sweepArgs(mb2_solver_function* f, const float* theta, const int32_t* active) {
+  SweepArgs a{};
+  a.T = f->tables();
+  a.batch = f->B;
+  a.theta = theta;
+  a.ldTheta = f->ch->host.numParams;
+  a.targets = f->dTargets.p;
+  a.cweights = f->dWeights.p;
+  a.jacobian = f->dJ.p;
+  a.residual = f->dResidual.p;
+  a.errors = f->dErrors.p;
+  a.active = active;
+  a.stateOut = nullptr;
+  return a;
+}
+
+int addBlock(mb2_solver_function* f, HostErrorFunction& ef, int32_t* outIndex) {
+  ef.targetOff = f->targetStride;
+  ef.weightOff = f->numWeights;
+  f->targetStride += ef.targetSize;
+  if (ef.kind <= 2) {
+    f->numWeights += ef.numConstraints();
+    f->hWeights.insert(f->hWeights.end(), ef.weights.begin(), ef.weights.end());
+    if (f->weightsPerInstance) return fail(MB2_ERR_UNSUPPORTED, "add all error functions before setting per-instance constraint weights");
+  }
+  f->efs.push_back(ef);
+  f->planDirty = true;
+  if (outIndex) *outIndex = int32_t(f->efs.size()) - 1;
+  return MB2_OK;
+}
+
+void bitsToEnabled(const uint64_t* bits, int n, std::vector<uint8_t>& out) {
+  out.assign(n, 0);
+  for (int i = 0; i < n; ++i) out[i] = (bits[i >> 6] >> (i & 63)) & 1ull ? 1 : 0;
+}
+
+void recordPhaseStart(mb2_solver* s, int phase, cudaStream_t st) {
+  s->kernelLaunches++;
+  if (!s->profiling) return;
+  PhaseEvent e;
+  cudaEventCreate(&e.start);
+  cudaEventCreate(&e.stop);
+  e.phase = phase;
+  cudaEventRecord(e.start, st);
+  s->events.push_back(e);
+}
+void recordPhaseStop(mb2_solver* s, cudaStream_t st) {
+  if (!s->profiling) return;
+  cudaEventRecord(s->events.back().stop, st);
+}
+
+__global__ void initSolveStateKernel(int batch, int32_t* active, int32_t* iterations, int32_t* status, double* lastErrors, double* errors) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  active[b] = 1;
+  iterations[b] = 0;
+  status[b] = 0;
+  lastErrors[b] = DBL_MAX; // solver.cpp:83-84
+  errors[b] = DBL_MAX;
+}
+__global__ void initLineSearchKernel(int batch, const int32_t* active, int32_t* searching, float* scale) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  searching[b] = active[b];
+  scale[b] = 1.f;
+}
+// NaN/Inf guard of the batched caller (pymomentum/tensor_ik/tensor_ik.cpp:168-173): revert to the initial guess
+__global__ void finalizeKernel(int batch, int n, float* theta, const float* theta0, int32_t* status) {
+  const int b = blockIdx.x;
+  __shared__ int bad;
+  if (threadIdx.x == 0) bad = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    if (!isfinite(theta[size_t(b) * n + i])) bad = 1;
+  __syncthreads();
+  if (bad) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) theta[size_t(b) * n + i] = theta0[size_t(b) * n + i];
+    if (threadIdx.x == 0) status[b] = MB2_INSTANCE_NON_FINITE;
+  }
+}
+
+int resolveJtjMode(const mb2_solver_function* f, int requested, int ns) {
+  if (requested == MB2_JTJ_FP32_SIMT) return MB2_JTJ_FP32_SIMT;
+  const bool ok = jtjTensorSupported(ns, f->ldJ);
+  if (requested == MB2_JTJ_AUTO) return ok ? MB2_JTJ_TF32X3 : MB2_JTJ_FP32_SIMT;
+  return ok ? requested : -1;
+}
+
+int runJtJ(mb2_solver_function* f, int mode, const int32_t* cols, int ns, float* H, int ldH, const int32_t* active, cudaStream_t st) {
+  JtJArgs a{};
+  a.batch = f->B;
+  a.jacobian = f->dJ.p;
+  a.residual = f->dResidual.p;
+  a.numParams = f->ch->host.numParams;
+  a.ldJ = f->ldJ;
+  a.kRows = roundUp(std::max(f->plan.numRows, 1), 4);
+  a.cols = cols;
+  a.ns = ns;
+  a.H = H;
+  a.ldH = ldH;
+  a.active = active;
+  if (mode == MB2_JTJ_FP32_SIMT) { MB2_CUDA(launchJtJSimt(a, st)); }
+  else { MB2_CUDA(launchJtJTensor(a, mode == MB2_JTJ_TF32X3 ? 3 : 1, st)); }
+  return MB2_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* mb2_last_error(void) { return g_lastError.c_str(); }
+int mb2_device_count(void) { return usableDevices(); }
+
+void mb2_default_gauss_newton_options(mb2_gauss_newton_options* o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  o->min_iterations = 1;  // solver.h:21
+  o->max_iterations = 2;  // solver.h:24
+  o->threshold = 1.0f;    // solver.h:27
+  o->verbose = 0;
+  o->regularization = 0.05f; // gauss_newton_solver.h:22
+  o->do_line_search = 0;
+  o->use_block_jtj = 0;
+  o->target_rows_per_chunk = ~0ull;
+  o->subset_line_search = 0;
+  o->jtj_mode = MB2_JTJ_AUTO;
+  o->store_error_history = 0;
+}
+
+int mb2_character_create(int device, int32_t J, const int32_t* parents, const float* offsets, const float* prerot, int32_t n,
+                         const int32_t* outer, const int32_t* inner, const float* vals, const float* ptoffsets, mb2_character** out) {
+  MB2_CHECK(out != nullptr && parents && offsets && prerot && outer && ptoffsets, "null argument");
+  MB2_CHECK(J > 0 && n > 0, "numJoints and numModelParameters must be positive");
+  auto c = std::make_unique<mb2_character>();
+  HostCharacter& h = c->host;
+  h.numJoints = J;
+  h.numParams = n;
+  h.parent.assign(parents, parents + J);
+  h.offset.assign(offsets, offsets + 3 * J);
+  h.prerot.assign(prerot, prerot + 4 * J);
+  h.ptOuter.assign(outer, outer + 7 * J + 1);
+  const int nnz = outer[7 * J];
+  MB2_CHECK(nnz >= 0 && (nnz == 0 || (inner && vals)), "parameter transform nnz invalid");
+  h.ptInner.assign(inner, inner + nnz);
+  h.ptVals.assign(vals, vals + nnz);
+  h.ptOffsets.assign(ptoffsets, ptoffsets + 7 * J);
+  const std::string err = h.validate();
+  if (!err.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, err);
+  h.buildLevels();
+  int rc = requireDevice(device);
+  if (rc != MB2_OK) return rc;
+  c->device = device;
+  MB2_CUDA(c->parent.upload(h.parent, nullptr));
+  MB2_CUDA(c->offset.upload(h.offset, nullptr));
+  MB2_CUDA(c->prerot.upload(h.prerot, nullptr));
+  MB2_CUDA(c->ptOuter.upload(h.ptOuter, nullptr));
+  MB2_CUDA(c->ptInner.upload(h.ptInner, nullptr));
+  MB2_CUDA(c->ptVals.upload(h.ptVals, nullptr));
+  MB2_CUDA(c->ptOffsets.upload(h.ptOffsets, nullptr));
+  MB2_CUDA(c->levelStart.upload(h.levelStart, nullptr));
+  MB2_CUDA(c->levelJoints.upload(h.levelJoints, nullptr));
+  MB2_CUDA(cudaStreamSynchronize(nullptr));
+  *out = c.release();
+  return MB2_OK;
+}
+
+int mb2_character_set_parameter_limits(mb2_character* c, int32_t count, const mb2_parameter_limit* limits) {
+  MB2_CHECK(c != nullptr && count >= 0 && (count == 0 || limits), "invalid limits");
+  c->host.limits.clear();
+  for (int i = 0; i < count; ++i) {
+    HostLimit l;
+    l.type = limits[i].type;
+    l.weight = limits[i].weight;
+    std::memcpy(l.i, limits[i].i, sizeof(l.i));
+    std::memcpy(l.f, limits[i].f, sizeof(l.f));
+    MB2_CHECK(l.type >= 0 && l.type <= 6, "Unknown parameter type for joint limit");
+    c->host.limits.push_back(l);
+  }
+  c->limitsVersion++;
+  return MB2_OK;
+}
+
+void mb2_character_destroy(mb2_character* c) { delete c; }
+
+int mb2_solver_function_create(const mb2_character* c, int32_t batch, mb2_solver_function** out) {
+  MB2_CHECK(c != nullptr && out != nullptr, "null argument");
+  MB2_CHECK(batch > 0, "batch must be positive");
+  int rc = requireDevice(c->device);
+  if (rc != MB2_OK) return rc;
+  auto f = std::make_unique<mb2_solver_function>();
+  f->ch = c;
+  f->B = batch;
+  f->enabled.assign(c->host.numParams, 1); // all parameters enabled by default (skeleton_error_function.h:27)
+  MB2_CUDA(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+  *out = f.release();
+  return MB2_OK;
+}
+
+void mb2_solver_function_destroy(mb2_solver_function* f) {
+  if (!f) return;
+  if (f->stream) cudaStreamDestroy(f->stream);
+  delete f;
+}
+
+int32_t mb2_solver_function_num_parameters(const mb2_solver_function* f) { return f ? f->ch->host.numParams : 0; }
+int32_t mb2_solver_function_batch(const mb2_solver_function* f) { return f ? f->B : 0; }
+int32_t mb2_solver_function_actual_parameters(const mb2_solver_function* f) {
+  if (!f) return 0;
+  int ap = 0;
+  for (int i = 0; i < f->ch->host.numParams; ++i) if (f->enabled[i]) ap = i + 1;
+  return ap;
+}
+int32_t mb2_solver_function_jacobian_rows(const mb2_solver_function* f) {
+  if (!f) return 0;
+  int total = 0;
+  for (const auto& ef : f->efs) if (ef.weight > 0.f) total += jacobianBlockSize(f->ch->host, ef);
+  return roundUp(total, 8); // padToSimdAlignment (solver_function.h:27-29)
+}
+int32_t mb2_solver_function_jacobian_stride(const mb2_solver_function* f) {
+  if (!f) return 0;
+  int total = 0;
+  for (const auto& ef : f->efs) if (ef.weight > 0.f) total += jacobianBlockSize(f->ch->host, ef);
+  return std::max(32, roundUp(total, 32));
+}
+
+int mb2_add_position_error_function(mb2_solver_function* f, float weight, float alpha, float c, int32_t nc, const int32_t* parents,
+                                    const float* offsets, const float* weights, int32_t* outIndex) {
+  MB2_CHECK(f != nullptr && nc >= 0 && (nc == 0 || (parents && offsets && weights)), "invalid position constraints");
+  MB2_CHECK(c > 0.f, "Parameter c should be positive"); // generalized_loss.cpp:83
+  HostErrorFunction ef;
+  ef.kind = 0;
+  ef.weight = weight;
+  ef.lossAlpha = alpha;
+  ef.lossC = c;
+  ef.parents.assign(parents, parents + nc);
+  for (int p : ef.parents) MB2_CHECK(p >= 0 && p < f->ch->host.numJoints, "constraint parent joint out of range");
+  ef.offsets.assign(offsets, offsets + 3 * size_t(nc));
+  ef.weights.assign(weights, weights + nc);
+  ef.targetSize = 3 * nc;
+  return addBlock(f, ef, outIndex);
+}
+
+int mb2_add_orientation_error_function(mb2_solver_function* f, float weight, float alpha, float c, int32_t rotDiff, int32_t nc,
+                                       const int32_t* parents, const float* offsets, const float* weights, int32_t* outIndex) {
+  MB2_CHECK(f != nullptr && nc >= 0 && (nc == 0 || (parents && offsets && weights)), "invalid orientation constraints");
+  MB2_CHECK(c > 0.f, "Parameter c should be positive");
+  HostErrorFunction ef;
+  ef.kind = rotDiff ? 2 : 1;
+  ef.weight = weight;
+  ef.lossAlpha = alpha;
+  ef.lossC = c;
+  ef.parents.assign(parents, parents + nc);
+  for (int p : ef.parents) MB2_CHECK(p >= 0 && p < f->ch->host.numJoints, "constraint parent joint out of range");
+  ef.offsets.assign(offsets, offsets + 4 * size_t(nc));
+  for (int i = 0; i < nc; ++i) { // OrientationDataT ctor: offset(inOffset.normalized()) (orientation_error_function.h:33-35)
+    float* q = &ef.offsets[4 * size_t(i)];
+    const float nrm = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    for (int k = 0; k < 4; ++k) q[k] /= nrm;
+  }
+  ef.weights.assign(weights, weights + nc);
+  ef.targetSize = 4 * nc;
+  return addBlock(f, ef, outIndex);
+}
+
+int mb2_add_state_error_function(mb2_solver_function* f, float weight, int32_t rotationErrorType, float posWgt, float rotWgt,
+                                 const float* posW, const float* rotW, int32_t* outIndex) {
+  MB2_CHECK(f != nullptr && posW && rotW, "invalid state error function");
+  MB2_CHECK(rotationErrorType == 0 || rotationErrorType == 1, "unknown rotation error type");
+  HostErrorFunction ef;
+  ef.kind = 3;
+  ef.weight = weight;
+  ef.rotationErrorType = rotationErrorType;
+  ef.posWgt = posWgt;
+  ef.rotWgt = rotWgt;
+  const int J = f->ch->host.numJoints;
+  ef.posW.assign(posW, posW + J);
+  ef.rotW.assign(rotW, rotW + J);
+  ef.targetSize = 8 * J;
+  return addBlock(f, ef, outIndex);
+}
+
+int mb2_add_limit_error_function(mb2_solver_function* f, float weight, float alpha, float c, int32_t* outIndex) {
+  MB2_CHECK(f != nullptr, "null solver function");
+  MB2_CHECK(c > 0.f, "Parameter c should be positive");
+  HostErrorFunction ef;
+  ef.kind = 4;
+  ef.weight = weight;
+  ef.lossAlpha = alpha;
+  ef.lossC = c;
+  ef.targetSize = 0;
+  return addBlock(f, ef, outIndex);
+}
+
+int mb2_set_error_function_weight(mb2_solver_function* f, int32_t index, float weight) {
+  MB2_CHECK(f != nullptr && index >= 0 && index < int(f->efs.size()), "error function index out of range");
+  f->efs[index].weight = weight;
+  f->planDirty = true;
+  return MB2_OK;
+}
+
+static int setTargetsImpl(mb2_solver_function* f, int32_t index, const float* targets, bool deviceSrc, cudaStream_t st) {
+  MB2_CHECK(f != nullptr && index >= 0 && index < int(f->efs.size()) && targets, "invalid targets");
+  const HostErrorFunction& ef = f->efs[index];
+  MB2_CHECK(ef.targetSize > 0, "this error function has no per-instance targets");
+  MB2_CUDA(cudaSetDevice(f->ch->device));
+  int rc = ensureTargets(f);
+  if (rc != MB2_OK) return rc;
+  float* dst = f->dTargets.p + ef.targetOff;
+  MB2_CUDA(cudaMemcpy2DAsync(dst, size_t(f->targetStride) * sizeof(float), targets, size_t(ef.targetSize) * sizeof(float),
+                             size_t(ef.targetSize) * sizeof(float), f->B, deviceSrc ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  if (ef.kind == 1 || ef.kind == 2) MB2_CUDA(launchNormalizeQuats(dst, 0, f->targetStride, ef.numConstraints(), f->B, st));
+  return MB2_OK;
+}
+int mb2_set_targets(mb2_solver_function* f, int32_t index, const float* targets) {
+  if (!f) return fail(MB2_ERR_INVALID_ARGUMENT, "null solver function");
+  int rc = setTargetsImpl(f, index, targets, false, f->stream);
+  if (rc != MB2_OK) return rc;
+  MB2_CUDA(cudaStreamSynchronize(f->stream)); // host buffer may be reused by the caller
+  return MB2_OK;
+}
+int mb2_set_targets_device(mb2_solver_function* f, int32_t index, const float* targets, void* stream) {
+  if (!f) return fail(MB2_ERR_INVALID_ARGUMENT, "null solver function");
+  return setTargetsImpl(f, index, targets, true, stream ? (cudaStream_t)stream : f->stream);
+}
+
+int mb2_set_constraint_weights(mb2_solver_function* f, int32_t index, const float* weights, int32_t perInstance) {
+  MB2_CHECK(f != nullptr && index >= 0 && index < int(f->efs.size()) && weights, "invalid constraint weights");
+  HostErrorFunction& ef = f->efs[index];
+  MB2_CHECK(ef.kind <= 2, "constraint weights apply to Position/Orientation error functions");
+  MB2_CUDA(cudaSetDevice(f->ch->device));
+  const int nc = ef.numConstraints();
+  if (!perInstance) {
+    MB2_CHECK(!f->weightsPerInstance, "solver function already uses per-instance constraint weights");
+    ef.weights.assign(weights, weights + nc);
+    std::copy(weights, weights + nc, f->hWeights.begin() + ef.weightOff);
+    return uploadWeights(f);
+  }
+  if (!f->weightsPerInstance) { // expand the shared array to [B][numWeights]
+    std::vector<float> all(size_t(f->B) * f->numWeights);
+    for (int b = 0; b < f->B; ++b) std::copy(f->hWeights.begin(), f->hWeights.end(), all.begin() + size_t(b) * f->numWeights);
+    f->dWeights.release();
+    MB2_CUDA(f->dWeights.upload(all, f->stream));
+    f->weightsPerInstance = true;
+  }
+  MB2_CUDA(cudaMemcpy2DAsync(f->dWeights.p + ef.weightOff, size_t(f->numWeights) * sizeof(float), weights, size_t(nc) * sizeof(float),
+                             size_t(nc) * sizeof(float), f->B, cudaMemcpyHostToDevice, f->stream));
+  MB2_CUDA(cudaStreamSynchronize(f->stream));
+  return MB2_OK;
+}
+
+int mb2_solver_function_set_enabled_parameters(mb2_solver_function* f, const uint64_t* bits) {
+  MB2_CHECK(f != nullptr && bits != nullptr, "null argument");
+  bitsToEnabled(bits, f->ch->host.numParams, f->enabled);
+  f->planDirty = true;
+  return MB2_OK;
+}
+
+int mb2_solver_function_get_error(mb2_solver_function* f, const float* params, double* errors) {
+  MB2_CHECK(f != nullptr && params && errors, "null argument");
+  int rc = ensurePlan(f);
+  if (rc != MB2_OK) return rc;
+  const size_t n = f->ch->host.numParams;
+  MB2_CUDA(cudaMemcpyAsync(f->dTheta.p, params, size_t(f->B) * n * sizeof(float), cudaMemcpyHostToDevice, f->stream));
+  MB2_CUDA(launchSweep(sweepArgs(f, f->dTheta.p, nullptr), false, f->stream));
+  MB2_CUDA(cudaMemcpyAsync(errors, f->dErrors.p, size_t(f->B) * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+  MB2_CUDA(cudaStreamSynchronize(f->stream));
+  return MB2_OK;
+}
+
+int mb2_solver_function_get_jacobian(mb2_solver_function* f, const float* params, float* jac, float* residual, double* errors, int32_t* actualRows) {
+  MB2_CHECK(f != nullptr && params, "null argument");
+  int rc = ensurePlan(f);
+  if (rc != MB2_OK) return rc;
+  const size_t n = f->ch->host.numParams;
+  const int rows = mb2_solver_function_jacobian_rows(f);
+  MB2_CUDA(cudaMemcpyAsync(f->dTheta.p, params, size_t(f->B) * n * sizeof(float), cudaMemcpyHostToDevice, f->stream));
+  MB2_CUDA(launchSweep(sweepArgs(f, f->dTheta.p, nullptr), true, f->stream));
+  if (jac && rows > 0)
+    MB2_CUDA(cudaMemcpy2DAsync(jac, size_t(rows) * sizeof(float), f->dJ.p, size_t(f->ldJ) * sizeof(float), size_t(rows) * sizeof(float),
+                               size_t(f->B) * n, cudaMemcpyDeviceToHost, f->stream));
+  if (residual && rows > 0)
+    MB2_CUDA(cudaMemcpy2DAsync(residual, size_t(rows) * sizeof(float), f->dResidual.p, size_t(f->ldJ) * sizeof(float), size_t(rows) * sizeof(float),
+                               f->B, cudaMemcpyDeviceToHost, f->stream));
+  if (errors) MB2_CUDA(cudaMemcpyAsync(errors, f->dErrors.p, size_t(f->B) * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+  MB2_CUDA(cudaStreamSynchronize(f->stream));
+  if (actualRows) *actualRows = rows; // solver_function.cpp:50 actualRows = totalRows (padded)
+  return MB2_OK;
+}
+
+int mb2_solver_function_get_jtjr(mb2_solver_function* f, const float* params, int32_t jtjMode, float* jtj, float* jtr, double* errors) {
+  MB2_CHECK(f != nullptr && params, "null argument");
+  int rc = ensurePlan(f);
+  if (rc != MB2_OK) return rc;
+  const size_t n = f->ch->host.numParams;
+  const int ap = f->plan.actualParameters;
+  MB2_CHECK(ap > 0, "no enabled parameters");
+  const int mode = resolveJtjMode(f, jtjMode, ap);
+  if (mode < 0) return fail(MB2_ERR_UNSUPPORTED, "tensor-core JtJ does not support this shape");
+  const int ldH = ap | 1;
+  MB2_CUDA(f->dH.resize(size_t(f->B) * (ap + 1) * ldH));
+  MB2_CUDA(cudaMemcpyAsync(f->dTheta.p, params, size_t(f->B) * n * sizeof(float), cudaMemcpyHostToDevice, f->stream));
+  MB2_CUDA(launchSweep(sweepArgs(f, f->dTheta.p, nullptr), true, f->stream));
+  MB2_CUDA(cudaMemsetAsync(f->dH.p, 0, size_t(f->B) * (ap + 1) * ldH * sizeof(float), f->stream));
+  rc = runJtJ(f, mode, f->dIdentity.p, ap, f->dH.p, ldH, nullptr, f->stream);
+  if (rc != MB2_OK) return rc;
+  for (int b = 0; b < f->B && (jtj || jtr); ++b) { // per-instance 2D copies (debug/parity entry point)
+    const float* Hb = f->dH.p + size_t(b) * (ap + 1) * ldH;
+    if (jtj) MB2_CUDA(cudaMemcpy2DAsync(jtj + size_t(b) * ap * ap, size_t(ap) * sizeof(float), Hb, size_t(ldH) * sizeof(float), size_t(ap) * sizeof(float), ap,
+                                        cudaMemcpyDeviceToHost, f->stream));
+    if (jtr) MB2_CUDA(cudaMemcpyAsync(jtr + size_t(b) * ap, Hb + size_t(ap) * ldH, size_t(ap) * sizeof(float), cudaMemcpyDeviceToHost, f->stream));
+  }
+  if (errors) MB2_CUDA(cudaMemcpyAsync(errors, f->dErrors.p, size_t(f->B) * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+  MB2_CUDA(cudaStreamSynchronize(f->stream));
+  return MB2_OK;
+}
+
+int mb2_solver_function_get_skeleton_state(mb2_solver_function* f, const float* params, float* state) {
+  MB2_CHECK(f != nullptr && params && state, "null argument");
+  int rc = ensurePlan(f);
+  if (rc != MB2_OK) return rc;
+  const size_t n = f->ch->host.numParams;
+  const size_t sz = size_t(f->B) * f->ch->host.numJoints * 8;
+  MB2_CUDA(f->dState.resize(sz));
+  MB2_CUDA(cudaMemcpyAsync(f->dTheta.p, params, size_t(f->B) * n * sizeof(float), cudaMemcpyHostToDevice, f->stream));
+  SweepArgs a = sweepArgs(f, f->dTheta.p, nullptr);
+  a.stateOut = f->dState.p;
+  MB2_CUDA(launchSweep(a, false, f->stream));
+  MB2_CUDA(cudaMemcpyAsync(state, f->dState.p, sz * sizeof(float), cudaMemcpyDeviceToHost, f->stream));
+  MB2_CUDA(cudaStreamSynchronize(f->stream));
+  return MB2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Solver
+// ---------------------------------------------------------------------------------------------
+int mb2_solver_create(mb2_solver_function* f, const mb2_gauss_newton_options* opt, mb2_solver** out) {
+  MB2_CHECK(f != nullptr && out != nullptr, "null argument");
+  auto s = std::make_unique<mb2_solver>();
+  s->fn = f;
+  if (opt) s->opt = *opt; else mb2_default_gauss_newton_options(&s->opt);
+  MB2_CUDA(cudaSetDevice(f->ch->device));
+  MB2_CUDA(cudaMallocHost(&s->hActiveCount, sizeof(int)));
+  *out = s.release();
+  return MB2_OK;
+}
+void mb2_solver_destroy(mb2_solver* s) { delete s; }
+int mb2_solver_set_options(mb2_solver* s, const mb2_gauss_newton_options* opt) {
+  MB2_CHECK(s != nullptr && opt != nullptr, "null argument");
+  s->opt = *opt;
+  return MB2_OK;
+}
+int mb2_solver_set_enabled_parameters(mb2_solver* s, const uint64_t* bits) {
+  MB2_CHECK(s != nullptr, "null solver");
+  return mb2_solver_function_set_enabled_parameters(s->fn, bits);
+}
+int mb2_solver_set_profiling(mb2_solver* s, int32_t enabled) {
+  MB2_CHECK(s != nullptr, "null solver");
+  s->profiling = enabled != 0;
+  return MB2_OK;
+}
+
+int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
+  MB2_CHECK(s != nullptr && theta != nullptr, "null argument");
+  mb2_solver_function* f = s->fn;
+  int rc = ensurePlan(f);
+  if (rc != MB2_OK) return rc;
+  cudaStream_t st = cudaStream ? (cudaStream_t)cudaStream : f->stream;
+  const int B = f->B, n = f->ch->host.numParams;
+  const int ns = int(f->plan.enabledList.size());
+  const mb2_gauss_newton_options& o = s->opt;
+  const int maxIt = int(std::min<uint64_t>(o.max_iterations, 1u << 30));
+  const int minIt = int(std::min<uint64_t>(o.min_iterations, 1u << 30));
+  MB2_CHECK(ns > 0, "no enabled parameters");
+  const int mode = resolveJtjMode(f, o.jtj_mode, ns);
+  if (mode < 0) return fail(MB2_ERR_UNSUPPORTED, "tensor-core JtJ does not support this shape");
+  const int ldH = ns | 1;
+  MB2_CUDA(s->dH.resize(size_t(B) * (ns + 1) * ldH));
+  MB2_CUDA(s->dDelta.resize(size_t(B) * ns));
+  MB2_CUDA(s->dTheta0.resize(size_t(B) * n));
+  MB2_CUDA(s->dLastErrors.resize(B));
+  MB2_CUDA(s->dActive.resize(B));
+  MB2_CUDA(s->dIterations.resize(B));
+  MB2_CUDA(s->dStatus.resize(B));
+  MB2_CUDA(s->dActiveCount.resize(1));
+  const bool lineSearch = o.do_line_search != 0;
+  if (lineSearch) {
+    MB2_CUDA(s->dThetaOrig.resize(size_t(B) * n));
+    MB2_CUDA(s->dTrialErrors.resize(B));
+    MB2_CUDA(s->dScale.resize(B));
+    MB2_CUDA(s->dSearching.resize(B));
+    MB2_CUDA(s->dGradDotDelta.resize(B));
+  }
+  if (o.store_error_history) {
+    MB2_CUDA(s->dHistory.resize(size_t(B) * std::max(maxIt, 1)));
+    MB2_CUDA(cudaMemsetAsync(s->dHistory.p, 0, size_t(B) * std::max(maxIt, 1) * sizeof(double), st));
+    s->historyStride = size_t(std::max(maxIt, 1));
+  }
+  for (auto& e : s->events) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }
+  s->events.clear();
+  s->kernelLaunches = 0;
+
+  initSolveStateKernel<<<(B + 127) / 128, 128, 0, st>>>(B, s->dActive.p, s->dIterations.p, s->dStatus.p, s->dLastErrors.p, f->dErrors.p);
+  MB2_CUDA(cudaGetLastError());
+  MB2_CUDA(cudaMemcpyAsync(s->dTheta0.p, theta, size_t(B) * n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+
+  for (int it = 0; it < maxIt; ++it) {
+    MB2_CUDA(cudaMemsetAsync(s->dActiveCount.p, 0, sizeof(int), st));
+    // --- doIteration (gauss_newton_solver.cpp:224-280) ---
+    recordPhaseStart(s, 0, st);
+    MB2_CUDA(launchSweep(sweepArgs(f, theta, s->dActive.p), true, st));
+    recordPhaseStop(s, st);
+    recordPhaseStart(s, 1, st);
+    rc = runJtJ(f, mode, f->dEnabledList.p, ns, s->dH.p, ldH, s->dActive.p, st);
+    if (rc != MB2_OK) return rc;
+    recordPhaseStop(s, st);
+    CholArgs c{};
+    c.batch = B;
+    c.H = s->dH.p;
+    c.ns = ns;
+    c.ldH = ldH;
+    c.regularization = o.regularization;
+    c.cols = f->dEnabledList.p;
+    c.theta = theta;
+    c.ldTheta = n;
+    c.delta = s->dDelta.p;
+    c.applyUpdate = lineSearch ? 0 : 1;
+    c.errors = f->dErrors.p;
+    c.lastErrors = s->dLastErrors.p;
+    c.active = s->dActive.p;
+    c.iterations = s->dIterations.p;
+    c.status = s->dStatus.p;
+    c.history = o.store_error_history ? s->dHistory.p : nullptr;
+    c.iteration = it;
+    c.minIterations = minIt;
+    c.maxIterations = maxIt;
+    c.threshold = o.threshold;
+    c.activeCount = s->dActiveCount.p;
+    c.bookkeeping = lineSearch ? 0 : 1;
+    c.gradDotDelta = lineSearch ? s->dGradDotDelta.p : nullptr;
+    recordPhaseStart(s, 2, st);
+    MB2_CUDA(launchCholesky(c, st));
+    recordPhaseStop(s, st);
+    if (lineSearch) { // gauss_newton_solver.cpp:283-313 / subset_gauss_newton_solver.cpp:119-141
+      MB2_CUDA(cudaMemcpyAsync(s->dThetaOrig.p, theta, size_t(B) * n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      initLineSearchKernel<<<(B + 127) / 128, 128, 0, st>>>(B, s->dActive.p, s->dSearching.p, s->dScale.p);
+      MB2_CUDA(cudaGetLastError());
+      for (int step = 0; step < 10; ++step) {
+        MB2_CUDA(launchTrialUpdate(B, s->dThetaOrig.p, n, s->dDelta.p, ns, f->dEnabledList.p, s->dScale.p, theta, s->dSearching.p, st));
+        SweepArgs ea = sweepArgs(f, theta, s->dSearching.p);
+        ea.errors = s->dTrialErrors.p;
+        recordPhaseStart(s, 3, st);
+        MB2_CUDA(launchSweep(ea, false, st));
+        recordPhaseStop(s, st);
+        LineSearchArgs la{};
+        la.batch = B; la.ns = ns; la.numParams = n; la.ldTheta = n;
+        la.errors = f->dErrors.p;
+        la.trialErrors = s->dTrialErrors.p;
+        la.gradDotDelta = s->dGradDotDelta.p;
+        la.scale = s->dScale.p;
+        la.searching = s->dSearching.p;
+        la.step = step;
+        la.subsetVariant = o.subset_line_search;
+        la.active = s->dActive.p;
+        MB2_CUDA(launchLineSearchStep(la, st));
+        s->kernelLaunches += 2;
+      }
+      BookkeepingArgs ba{};
+      ba.batch = B;
+      ba.errors = f->dErrors.p; ba.lastErrors = s->dLastErrors.p; ba.active = s->dActive.p; ba.iterations = s->dIterations.p;
+      ba.status = s->dStatus.p; ba.history = o.store_error_history ? s->dHistory.p : nullptr;
+      ba.theta = theta; ba.ldTheta = n; ba.numParams = n;
+      ba.iteration = it; ba.minIterations = minIt; ba.maxIterations = maxIt; ba.threshold = o.threshold; ba.activeCount = s->dActiveCount.p;
+      MB2_CUDA(launchBookkeeping(ba, st));
+      s->kernelLaunches += 1;
+    }
+    // Instances can only stop once iteration >= minIterations (solver.cpp:113): poll the device
+    // counter from then on so a converged batch does not run to maxIterations.
+    if (it + 1 < maxIt && it >= minIt) {
+      MB2_CUDA(cudaMemcpyAsync(s->hActiveCount, s->dActiveCount.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+      MB2_CUDA(cudaStreamSynchronize(st));
+      if (*s->hActiveCount == 0) break;
+    }
+  }
+  finalizeKernel<<<B, 128, 0, st>>>(B, n, theta, s->dTheta0.p, s->dStatus.p);
+  MB2_CUDA(cudaGetLastError());
+  s->kernelLaunches += 2;
+  return MB2_OK;
+}
+
+int mb2_solver_get_results(mb2_solver* s, double* errors, int32_t* iterations, int32_t* status) {
+  MB2_CHECK(s != nullptr, "null solver");
+  mb2_solver_function* f = s->fn;
+  const int B = f->B;
+  MB2_CUDA(cudaSetDevice(f->ch->device));
+  MB2_CUDA(cudaDeviceSynchronize());
+  if (errors) MB2_CUDA(cudaMemcpy(errors, f->dErrors.p, size_t(B) * sizeof(double), cudaMemcpyDeviceToHost));
+  std::vector<int32_t> its(B);
+  MB2_CUDA(cudaMemcpy(its.data(), s->dIterations.p, size_t(B) * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  s->totalIterations = 0;
+  for (int v : its) s->totalIterations += uint64_t(v);
+  if (iterations) std::copy(its.begin(), its.end(), iterations);
+  if (status) MB2_CUDA(cudaMemcpy(status, s->dStatus.p, size_t(B) * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (s->profiling) {
+    for (int k = 0; k < 4; ++k) { s->phaseMs[k] = 0; s->phaseLaunches[k] = 0; }
+    for (auto& e : s->events) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, e.start, e.stop) == cudaSuccess) { s->phaseMs[e.phase] += ms; s->phaseLaunches[e.phase]++; }
+    }
+  }
+  return MB2_OK;
+}
+
+int mb2_solver_solve(mb2_solver* s, float* params, double* errors, int32_t* iterations, int32_t* status) {
+  MB2_CHECK(s != nullptr && params != nullptr, "null argument");
+  mb2_solver_function* f = s->fn;
+  MB2_CUDA(cudaSetDevice(f->ch->device));
+  const size_t bytes = size_t(f->B) * f->ch->host.numParams * sizeof(float);
+  MB2_CUDA(s->dThetaStage.resize(size_t(f->B) * f->ch->host.numParams));
+  MB2_CUDA(cudaMemcpyAsync(s->dThetaStage.p, params, bytes, cudaMemcpyHostToDevice, f->stream));
+  int rc = mb2_solver_solve_device(s, s->dThetaStage.p, f->stream);
+  if (rc != MB2_OK) return rc;
+  MB2_CUDA(cudaMemcpyAsync(params, s->dThetaStage.p, bytes, cudaMemcpyDeviceToHost, f->stream));
+  MB2_CUDA(cudaStreamSynchronize(f->stream));
+  return mb2_solver_get_results(s, errors, iterations, status);
+}
+
+int mb2_solver_get_error_history(mb2_solver* s, double* history) {
+  MB2_CHECK(s != nullptr && history != nullptr, "null argument");
+  MB2_CHECK(s->opt.store_error_history && s->dHistory.p, "error history was not stored (set store_error_history)");
+  MB2_CUDA(cudaMemcpy(history, s->dHistory.p, size_t(s->fn->B) * s->historyStride * sizeof(double), cudaMemcpyDeviceToHost));
+  return MB2_OK;
+}
+
+int mb2_solver_get_counters(mb2_solver* s, uint64_t* totalIterations, uint64_t* kernelLaunches) {
+  MB2_CHECK(s != nullptr, "null solver");
+  if (totalIterations) *totalIterations = s->totalIterations;
+  if (kernelLaunches) *kernelLaunches = s->kernelLaunches;
+  return MB2_OK;
+}
+
+int mb2_solver_get_phase_times(mb2_solver* s, double ms[4], uint64_t launches[4]) {
+  MB2_CHECK(s != nullptr, "null solver");
+  for (int k = 0; k < 4; ++k) {
+    if (ms) ms[k] = s->phaseMs[k];
+    if (launches) launches[k] = s->phaseLaunches[k];
+  }
+  return MB2_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,414 @@
+// sm_100a kernels for one Gauss-Newton iteration over a batch of IK instances.
+//
+//   K1 sweepKernel<true>   FK sweep + residual + Jacobian cells      (skeleton_solver_function.cpp:200-261)
+//   K4 sweepKernel<false>  FK sweep + error only (line search)       (skeleton_solver_function.cpp:64-83)
+//   K2 jtjSimtKernel       JtJ (lower) and Jtr, fp32 CUDA cores      (solver_function.cpp:113-116) — validation path
+//   K3 choleskyKernel      (JtJ + lambda I) delta = Jtr via blocked LLT, theta -= delta, SolverT bookkeeping
+//                          (gauss_newton_solver.cpp:248-259, solver.cpp:89-122)
+//
+// The tensor-core JtJ (tcgen05, TMEM accumulators, TMA-fed) lives in ik_jtj_tc.cu.
+#include "ik_kernels.cuh"
+
+#include <cstdio>
+
+#include "ik_chol.cuh"
+#include "ik_device.cuh"
+
+namespace mb2 {
+
+// ------------------------------------------------------------------------------------------------
+// K1 / K4: one warp per IK instance. Joint state lives in shared memory (17 floats / joint, odd
+// stride => conflict-free when lanes own different joints); the joint tree is swept level by level
+// with lanes = joints of one depth level; then lanes = units (constraints), then lanes = Jacobian cells.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warpSum(double v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+size_t sweepSmemPerInstance(const FunctionTables& T) {
+  const size_t nPad = (T.numParams + 3) & ~3;
+  return sizeof(float) * (nPad + size_t(T.numJoints) * (kParametersPerJoint + kJointStateStride) + size_t(T.recStride) + 4);
+}
+
+template <bool kJacobian>
+__global__ void __launch_bounds__(256) sweepKernel(const SweepArgs a) {
+  extern __shared__ float smem[];
+  const FunctionTables& T = a.T;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warpsPerCta = blockDim.x >> 5;
+  const int nPad = (T.numParams + 3) & ~3;
+  const int perWarp = nPad + T.numJoints * (kParametersPerJoint + kJointStateStride) + T.recStride + 4;
+  float* th = smem + size_t(warp) * perWarp;
+  float* jp = th + nPad;
+  float* js = jp + T.numJoints * kParametersPerJoint;
+  float* rec = js + T.numJoints * kJointStateStride;
+  const int numJointParams = T.numJoints * kParametersPerJoint;
+
+  for (int b = blockIdx.x * warpsPerCta + warp; b < a.batch; b += gridDim.x * warpsPerCta) {
+    if (a.active != nullptr && a.active[b] == 0) continue;
+    const float* theta = a.theta + size_t(b) * a.ldTheta;
+    for (int i = lane; i < T.numParams; i += 32) th[i] = theta[i];
+    __syncwarp();
+    for (int row = lane; row < numJointParams; row += 32) jp[row] = jointParameterRow(T, row, th);
+    __syncwarp();
+    for (int lvl = 0; lvl < T.numLevels; ++lvl) {
+      const int end = T.levelStart[lvl + 1];
+      for (int k = T.levelStart[lvl] + lane; k < end; k += 32) fkJoint<kJacobian>(T, T.levelJoints[k], jp, js);
+      __syncwarp();
+    }
+    if (a.stateOut != nullptr) {
+      float* so = a.stateOut + size_t(b) * T.numJoints * 8;
+      for (int i = lane; i < T.numJoints * 8; i += 32) so[i] = js[(i >> 3) * kJointStateStride + (i & 7)];
+    }
+    const float* targets = a.targets + size_t(b) * T.targetStride;
+    const float* cw = a.cweights + (T.weightsPerInstance ? size_t(b) * T.numWeights : 0);
+    float* residual = kJacobian ? a.residual + size_t(b) * T.ldJ : nullptr;
+    double err = 0.0;
+    for (int u = lane; u < T.numUnits; u += 32) err += (double)evalUnit<kJacobian>(T, u, th, jp, js, targets, cw, rec, residual);
+    __syncwarp();
+    if (kJacobian) {
+      float* J = a.jacobian + size_t(b) * T.numParams * T.ldJ;
+      for (int c = lane; c < T.numCells; c += 32) jacobianCell(T, c, js, rec, targets, J);
+    }
+    err = warpSum(err);
+    // getError() rounds through float (skeleton_solver_function.cpp:82); the Jacobian pass keeps double
+    if (lane == 0) a.errors[b] = kJacobian ? err : (double)(float)err;
+    __syncwarp();
+  }
+}
+
+static int g_numSms = 0;
+static int g_maxSmemOptin = 0;
+
+cudaError_t launchSweep(const SweepArgs& a, bool jacobian, cudaStream_t stream) {
+  const size_t per = sweepSmemPerInstance(a.T);
+  int warps = 8;
+  while (warps > 1 && per * warps > 100 * 1024) warps >>= 1;
+  const size_t smem = per * warps;
+  if (smem > size_t(g_maxSmemOptin)) return cudaErrorInvalidConfiguration;
+  cudaError_t e;
+  if (jacobian) e = cudaFuncSetAttribute(sweepKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  else e = cudaFuncSetAttribute(sweepKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (e != cudaSuccess) return e;
+  const int ctasNeeded = (a.batch + warps - 1) / warps;
+  const int ctasPerSm = (int)((200 * 1024) / (smem + 1024)) > 0 ? (int)((200 * 1024) / (smem + 1024)) : 1;
+  int grid = g_numSms * (ctasPerSm > 8 ? 8 : ctasPerSm);
+  if (grid > ctasNeeded) grid = ctasNeeded;
+  if (grid < 1) grid = 1;
+  if (jacobian) sweepKernel<true><<<grid, warps * 32, smem, stream>>>(a);
+  else sweepKernel<false><<<grid, warps * 32, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 (SIMT validation path): H[i][j] = sum_k J[k][cols[i]] J[k][cols[j]] for i >= j; g = J^T r.
+// grid = (lower-triangular 64x64 tile pairs, B); 256 threads, 4x4 outputs per thread.
+// ------------------------------------------------------------------------------------------------
+constexpr int kJtjTile = 64;
+constexpr int kJtjKc = 32;
+
+__global__ void __launch_bounds__(256) jtjSimtKernel(const JtJArgs a) {
+  const int b = blockIdx.y;
+  if (a.active != nullptr && a.active[b] == 0) return;
+  // decode lower-triangular tile index
+  int t = blockIdx.x, ti = 0;
+  while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+  const int tj = t - ti * (ti + 1) / 2;
+  __shared__ float As[kJtjTile][kJtjKc + 1];
+  __shared__ float Bs[kJtjTile][kJtjKc + 1];
+  __shared__ float rs[kJtjKc];
+  const float* J = a.jacobian + size_t(b) * a.numParams * a.ldJ;
+  const float* r = a.residual + size_t(b) * a.ldJ;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float gacc = 0.f;
+  const bool diag = (ti == tj);
+  for (int k0 = 0; k0 < a.kRows; k0 += kJtjKc) {
+    // load 64 columns x 32 rows for both operands (lane -> consecutive k: coalesced 128B per column)
+    for (int idx = threadIdx.x; idx < kJtjTile * kJtjKc; idx += 256) {
+      const int c = idx / kJtjKc, kk = idx % kJtjKc;
+      const int ia = ti * kJtjTile + c, ib = tj * kJtjTile + c;
+      const int k = k0 + kk;
+      As[c][kk] = (ia < a.ns && k < a.kRows) ? J[size_t(a.cols[ia]) * a.ldJ + k] : 0.f;
+      Bs[c][kk] = (ib < a.ns && k < a.kRows) ? J[size_t(a.cols[ib]) * a.ldJ + k] : 0.f;
+    }
+    if (threadIdx.x < kJtjKc) rs[threadIdx.x] = (k0 + threadIdx.x < a.kRows) ? r[k0 + threadIdx.x] : 0.f;
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < kJtjKc; ++kk) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = As[ty * 4 + i][kk];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = Bs[tx * 4 + j][kk];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (diag && threadIdx.x < kJtjTile)
+      for (int kk = 0; kk < kJtjKc; ++kk) gacc = fmaf(As[threadIdx.x][kk], rs[kk], gacc);
+    __syncthreads();
+  }
+  float* H = a.H + size_t(b) * (a.ns + 1) * a.ldH;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gi = ti * kJtjTile + ty * 4 + i, gj = tj * kJtjTile + tx * 4 + j;
+      if (gi < a.ns && gj <= gi) H[size_t(gi) * a.ldH + gj] = acc[i][j];
+    }
+  if (diag && threadIdx.x < kJtjTile) {
+    const int gi = ti * kJtjTile + threadIdx.x;
+    if (gi < a.ns) H[size_t(a.ns) * a.ldH + gi] = gacc;
+  }
+}
+
+cudaError_t launchJtJSimt(const JtJArgs& a, cudaStream_t stream) {
+  const int tiles = (a.ns + kJtjTile - 1) / kJtjTile;
+  dim3 grid(tiles * (tiles + 1) / 2, a.batch);
+  jtjSimtKernel<<<grid, 256, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: one CTA per instance. Matrix A = [H + lambda I ; g^T] ((ns+1) x lda, row-major, lower part)
+// is factored in place with Eigen's LLT structure (ik_chol.cuh); the appended row turns into
+// y = L^-1 g for free; back substitution gives delta.
+// ------------------------------------------------------------------------------------------------
+template <int NB>
+__global__ void __launch_bounds__(kCholThreads) choleskyKernel(const CholArgs a, const int useSmemMatrix) {
+  extern __shared__ float smem[];
+  const int b = blockIdx.x;
+  if (a.active[b] == 0) return;
+  const int n = a.ns;
+  const int tid = threadIdx.x;
+  float* Hg = a.H + size_t(b) * (n + 1) * a.ldH;
+  CholCtx ctx;
+  ctx.n = n;
+  int ldp = ((n + 1 + 3) & ~3) + 4;
+  float* P = smem;                       // [NB][ldp] transposed panel
+  float* gsave = P + NB * ldp;           // [n] copy of Jtr (for g.delta)
+  int* flags = reinterpret_cast<int*>(gsave + ((n + 3) & ~3)); // [0] = fail index+1
+  float* As = reinterpret_cast<float*>(flags + 4);
+  if (useSmemMatrix) {
+    ctx.lda = n | 1;
+    ctx.A = As;
+    for (int idx = tid; idx < (n + 1) * n; idx += kCholThreads) {
+      const int i = idx / n, j = idx - i * n;
+      if (j <= i || i == n) {
+        float v = Hg[size_t(i) * a.ldH + j];
+        if (i == j) v += a.regularization; // gauss_newton_solver.cpp:248
+        As[i * ctx.lda + j] = v;
+      }
+    }
+  } else {
+    ctx.lda = a.ldH;
+    ctx.A = Hg;
+    for (int i = tid; i < n; i += kCholThreads) Hg[size_t(i) * a.ldH + i] += a.regularization;
+  }
+  ctx.P = P;
+  ctx.ldp = ldp;
+  ctx.fail = flags;
+  if (tid == 0) flags[0] = 0;
+  for (int i = tid; i < n; i += kCholThreads) gsave[i] = Hg[size_t(n) * a.ldH + i];
+  __syncthreads();
+
+  const int blockSize = cholBlockSize(n, NB);
+  for (int k = 0; k < n; k += blockSize) {
+    const int bs = min(blockSize, n - k);
+    if (tid < 32) { // unblocked LLT of the diagonal block by warp 0 (left-looking, Eigen llt_inplace::unblocked)
+      for (int jj = 0; jj < bs; ++jj) {
+        const float x = cholDiagPivot(ctx, k, jj);
+        __syncwarp();
+        if (!(x > 0.f)) { if (tid == 0) flags[0] = k + jj + 1; break; }
+        cholDiagColumn(ctx, k, bs, jj, x, tid);
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    if (flags[0] != 0) break; // Eigen returns early: the rest of the matrix stays as it is
+    cholPanelSolve<NB>(ctx, k, bs, tid, kCholThreads);
+    __syncthreads();
+    cholTrailingUpdate<NB>(ctx, k, bs, tid, kCholThreads);
+    __syncthreads();
+  }
+  float* y = ctx.A + size_t(n) * ctx.lda; // appended row
+  if (flags[0] != 0) {
+    // finish the forward substitution with whatever the lower triangle holds (LLT::solve after a failed compute)
+    if (tid == 0) cholForwardFrom(ctx, cholCompletedColumns(flags[0] - 1, blockSize), y);
+    __syncthreads();
+  }
+  // back substitution L^T x = y, 32 columns at a time from the bottom
+  for (int i0 = ((n - 1) / 32) * 32; i0 >= 0; i0 -= 32) {
+    const int nb = min(32, n - i0);
+    if (tid < 32) {
+      float yv = tid < nb ? y[i0 + tid] : 0.f;
+      float dinv = tid < nb ? 1.f / ctx.A[size_t(i0 + tid) * ctx.lda + i0 + tid] : 0.f;
+      for (int kk = nb - 1; kk >= 0; --kk) {
+        const float xk = __shfl_sync(0xffffffffu, yv, kk) * __shfl_sync(0xffffffffu, dinv, kk);
+        if (tid == kk) yv = xk;
+        else if (tid < kk) yv -= ctx.A[size_t(i0 + kk) * ctx.lda + i0 + tid] * xk;
+      }
+      if (tid < nb) y[i0 + tid] = yv;
+    }
+    __syncthreads();
+    for (int i = tid; i < i0; i += kCholThreads) {
+      float s = y[i];
+      for (int kk = 0; kk < nb; ++kk) s -= ctx.A[size_t(i0 + kk) * ctx.lda + i] * y[i0 + kk];
+      y[i] = s;
+    }
+    __syncthreads();
+  }
+  // delta, parameter update (skeleton_solver_function.cpp:153-159), status
+  float* theta = a.theta + size_t(b) * a.ldTheta;
+  float part = 0.f;
+  for (int i = tid; i < n; i += kCholThreads) {
+    const float d = y[i];
+    a.delta[size_t(b) * n + i] = d;
+    part += gsave[i] * d;
+    if (a.applyUpdate) theta[a.cols[i]] -= d;
+  }
+  if (a.gradDotDelta != nullptr) {
+    __shared__ float red[kCholThreads / 32];
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((tid & 31) == 0) red[tid >> 5] = part;
+    __syncthreads();
+    if (tid == 0) {
+      float s = 0.f;
+      for (int w = 0; w < kCholThreads / 32; ++w) s += red[w];
+      a.gradDotDelta[b] = s;
+    }
+  }
+  if (tid == 0) {
+    if (flags[0] != 0 && a.status[b] == 0) a.status[b] = 1; // MB2_INSTANCE_CHOLESKY_BREAKDOWN
+    if (a.bookkeeping) {
+      // SolverT::solve loop tail (solver.cpp:92-122)
+      const double error = a.errors[b], last = a.lastErrors[b];
+      if (a.history != nullptr) a.history[size_t(b) * a.maxIterations + a.iteration] = error;
+      const bool converged = fabs(last - error) / (fabs(error) + (double)FLT_MIN) <= (double)(a.threshold * FLT_EPSILON);
+      a.iterations[b] = a.iteration + 1;
+      if ((a.iteration >= a.minIterations && converged) || a.iteration + 1 >= a.maxIterations) a.active[b] = 0;
+      else { a.lastErrors[b] = error; atomicAdd(a.activeCount, 1); }
+    }
+  }
+}
+
+static size_t cholSmemBytes(int n, int NB, bool matrixInSmem) {
+  const size_t ldp = ((n + 1 + 3) & ~3) + 4;
+  size_t s = sizeof(float) * (NB * ldp + ((n + 3) & ~3)) + 4 * sizeof(int);
+  if (matrixInSmem) s += sizeof(float) * size_t(n + 1) * (n | 1);
+  return s;
+}
+
+cudaError_t launchCholesky(const CholArgs& a, cudaStream_t stream) {
+  const int n = a.ns;
+  const int eig = cholBlockSize(n, 32);
+  const int NB = eig <= 8 ? 8 : (eig <= 16 ? 16 : 32);
+  bool inSmem = cholSmemBytes(n, NB, true) <= size_t(g_maxSmemOptin);
+  const size_t smem = cholSmemBytes(n, NB, inSmem);
+  cudaError_t e = cudaSuccess;
+#define MB2_LAUNCH_CHOL(NBV)                                                                                   \
+  e = cudaFuncSetAttribute(choleskyKernel<NBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));       \
+  if (e != cudaSuccess) return e;                                                                              \
+  choleskyKernel<NBV><<<a.batch, kCholThreads, smem, stream>>>(a, inSmem ? 1 : 0);
+  if (NB == 8) { MB2_LAUNCH_CHOL(8) } else if (NB == 16) { MB2_LAUNCH_CHOL(16) } else { MB2_LAUNCH_CHOL(32) }
+#undef MB2_LAUNCH_CHOL
+  return cudaGetLastError();
+}
+
+cudaError_t initKernelAttributes() {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  e = cudaDeviceGetAttribute(&g_numSms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return e;
+  return cudaDeviceGetAttribute(&g_maxSmemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Small element-wise kernels: line search (gauss_newton_solver.cpp:283-313,
+// subset_gauss_newton_solver.cpp:119-141), SolverT bookkeeping, target normalisation.
+// ------------------------------------------------------------------------------------------------
+__global__ void trialUpdateKernel(int batch, const float* thetaOrig, int ldTheta, const float* delta, int ns, const int32_t* cols, const float* scale,
+                                  float* thetaTrial, const int32_t* active) {
+  const int b = blockIdx.x;
+  if (active[b] == 0) return;
+  const float s = scale[b];
+  for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+    const int c = cols[i];
+    thetaTrial[size_t(b) * ldTheta + c] = thetaOrig[size_t(b) * ldTheta + c] - s * delta[size_t(b) * ns + i];
+  }
+}
+cudaError_t launchTrialUpdate(int batch, const float* thetaOrig, int ldTheta, const float* delta, int ns, const int32_t* cols, const float* scale,
+                              float* thetaTrial, const int32_t* active, cudaStream_t stream) {
+  trialUpdateKernel<<<batch, 128, 0, stream>>>(batch, thetaOrig, ldTheta, delta, ns, cols, scale, thetaTrial, active);
+  return cudaGetLastError();
+}
+
+__global__ void lineSearchStepKernel(const LineSearchArgs a) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.batch || a.searching[b] == 0) return;
+  const double error = a.errors[b], errorNew = a.trialErrors[b];
+  const float scale = a.scale[b];
+  bool accept;
+  if (!a.subsetVariant) {
+    const float scaledError = 1e-3f * (float)error; // kC1 * error_ in T
+    accept = (error - errorNew) >= (double)(scale * scaledError);
+  } else {
+    accept = (error - errorNew) >= (double)(1e-4f * scale) * (double)a.gradDotDelta[b];
+  }
+  if (accept || a.step >= 9) a.searching[b] = 0;
+  else a.scale[b] = scale * 0.5f;
+}
+cudaError_t launchLineSearchStep(const LineSearchArgs& a, cudaStream_t stream) {
+  lineSearchStepKernel<<<(a.batch + 127) / 128, 128, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+__global__ void commitTrialKernel(int batch, int numParams, int ldTheta, const float* thetaTrial, float* theta, const int32_t* active) {
+  const int b = blockIdx.x;
+  if (active[b] == 0) return;
+  for (int i = threadIdx.x; i < numParams; i += blockDim.x) theta[size_t(b) * ldTheta + i] = thetaTrial[size_t(b) * ldTheta + i];
+}
+cudaError_t launchCommitTrial(int batch, int numParams, int ldTheta, const float* thetaTrial, float* theta, const int32_t* active, cudaStream_t stream) {
+  commitTrialKernel<<<batch, 128, 0, stream>>>(batch, numParams, ldTheta, thetaTrial, theta, active);
+  return cudaGetLastError();
+}
+
+__global__ void bookkeepingKernel(const BookkeepingArgs a) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.batch || a.active[b] == 0) return;
+  const double error = a.errors[b], last = a.lastErrors[b];
+  if (a.history != nullptr) a.history[size_t(b) * a.maxIterations + a.iteration] = error;
+  const bool converged = fabs(last - error) / (fabs(error) + (double)FLT_MIN) <= (double)(a.threshold * FLT_EPSILON);
+  a.iterations[b] = a.iteration + 1;
+  if ((a.iteration >= a.minIterations && converged) || a.iteration + 1 >= a.maxIterations) a.active[b] = 0;
+  else { a.lastErrors[b] = error; atomicAdd(a.activeCount, 1); }
+}
+cudaError_t launchBookkeeping(const BookkeepingArgs& a, cudaStream_t stream) {
+  bookkeepingKernel<<<(a.batch + 127) / 128, 128, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+__global__ void normalizeQuatsKernel(float* base, int count, int strideFloats, int quatsPerRecord, int batch) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= batch * quatsPerRecord) return;
+  const int b = idx / quatsPerRecord, q = idx % quatsPerRecord;
+  float* p = base + size_t(b) * strideFloats + 4 * q;
+  const float n = sqrtf(p[0] * p[0] + p[1] * p[1] + p[2] * p[2] + p[3] * p[3]);
+  p[0] /= n; p[1] /= n; p[2] /= n; p[3] /= n;
+}
+cudaError_t launchNormalizeQuats(float* base, int count, int strideFloats, int quatsPerRecord, int batch, cudaStream_t stream) {
+  const int total = batch * quatsPerRecord;
+  if (total == 0) return cudaSuccess;
+  normalizeQuatsKernel<<<(total + 127) / 128, 128, 0, stream>>>(base, count, strideFloats, quatsPerRecord, batch);
+  return cudaGetLastError();
+}
+
+} // namespace mb2

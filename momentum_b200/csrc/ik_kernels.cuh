@@ -1,0 +1,90 @@
+// sm_100a kernels of the batched Gauss-Newton iteration (declarations + launch parameter structs).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "ik_types.h"
+
+namespace mb2 {
+
+struct SweepArgs {           // K1 (FK + residual + Jacobian) and K4 (FK + error only)
+  FunctionTables T;
+  int32_t batch;
+  const float* theta;        // [B][ldTheta]
+  int32_t ldTheta;
+  const float* targets;      // [B][T.targetStride]
+  const float* cweights;     // [numWeights] or [B][numWeights]
+  float* jacobian;           // [B][numParams][ldJ] (K1 only)
+  float* residual;           // [B][ldJ] (K1 only)
+  double* errors;            // [B]
+  const int32_t* active;     // optional per-instance mask
+  float* stateOut;           // optional [B][J][8]
+};
+
+struct JtJArgs {             // K2
+  int32_t batch;
+  const float* jacobian;     // [B][numParams][ldJ]
+  const float* residual;     // [B][ldJ]
+  int32_t numParams, ldJ, kRows; // kRows = contraction length (rows rounded up to 4)
+  const int32_t* cols;       // [ns] column index list (enabled parameters, or identity up to actualParameters)
+  int32_t ns;
+  float* H;                  // [B][ns+1][ldH]; rows 0..ns-1 lower triangle of JtJ, row ns = Jtr
+  int32_t ldH;
+  const int32_t* active;
+};
+
+struct CholArgs {            // K3: damped Cholesky + solve + update + SolverT bookkeeping
+  int32_t batch;
+  float* H;                  // [B][ns+1][ldH] (overwritten)
+  int32_t ns, ldH;
+  float regularization;
+  const int32_t* cols;       // [ns] subset -> full parameter index
+  float* theta;              // [B][ldTheta], updated: theta[cols[a]] -= delta[a]   (no line search)
+  int32_t ldTheta;
+  float* delta;              // [B][ns] (always written)
+  int32_t applyUpdate;       // 1: theta -= delta here
+  const double* errors;      // [B] error of this iteration (from K1)
+  double* lastErrors;        // [B]
+  int32_t* active;           // [B] in/out
+  int32_t* iterations;       // [B]
+  int32_t* status;           // [B]
+  double* history;           // optional [B][maxIterations]
+  int32_t iteration, minIterations, maxIterations;
+  float threshold;
+  int32_t* activeCount;      // device counter (atomicAdd of instances still active)
+  int32_t bookkeeping;       // 1: run the SolverT convergence test here (no line search)
+  float* gradDotDelta;       // optional [B]: Jtr . delta (SubsetGaussNewtonSolverT line search)
+};
+
+cudaError_t launchSweep(const SweepArgs& a, bool jacobian, cudaStream_t stream);
+size_t sweepSmemPerInstance(const FunctionTables& T);
+cudaError_t launchJtJSimt(const JtJArgs& a, cudaStream_t stream);
+cudaError_t launchCholesky(const CholArgs& a, cudaStream_t stream);
+cudaError_t initKernelAttributes();
+
+// line-search helpers
+cudaError_t launchTrialUpdate(int batch, const float* thetaOrig, int ldTheta, const float* delta, int ns, const int32_t* cols, const float* scale /*[B]*/,
+                              float* thetaTrial, const int32_t* active, cudaStream_t stream);
+struct LineSearchArgs {
+  int32_t batch, ns, numParams, ldTheta;
+  const double* errors;      // error_ at theta (from the Jacobian pass)
+  const double* trialErrors; // getError(theta - scale*delta)
+  const float* gradDotDelta; // [B] (subset variant) or nullptr
+  float* scale;              // [B] in/out line-search scale
+  int32_t* searching;        // [B] 1 while the instance is still halving
+  int32_t step;              // 0..9
+  int32_t subsetVariant;
+  const int32_t* active;
+};
+cudaError_t launchLineSearchStep(const LineSearchArgs& a, cudaStream_t stream);
+cudaError_t launchCommitTrial(int batch, int numParams, int ldTheta, const float* thetaTrial, float* theta, const int32_t* active, cudaStream_t stream);
+struct BookkeepingArgs {
+  int32_t batch;
+  const double* errors; double* lastErrors; int32_t* active; int32_t* iterations; int32_t* status; double* history;
+  const float* theta; int32_t ldTheta, numParams;
+  int32_t iteration, minIterations, maxIterations; float threshold; int32_t* activeCount;
+};
+cudaError_t launchBookkeeping(const BookkeepingArgs& a, cudaStream_t stream);
+cudaError_t launchNormalizeQuats(float* base, int count, int strideFloats, int quatsPerRecord, int batch, cudaStream_t stream);
+
+} // namespace mb2

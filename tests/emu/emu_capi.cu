@@ -1,0 +1,440 @@
+// TEST HARNESS ONLY — CPU lane-emulation of the device code, built into tests/emu/libmb2_emu.so.
+//
+// It exports the subset of include/momentum_b200.h that the parity tests use, but runs the
+// __host__ __device__ building blocks of momentum_b200/csrc (ik_device.cuh, ik_chol.cuh) and the real
+// planner (ik_plan.cpp) lane by lane on the CPU. Purpose: catch planner / indexing / semantics bugs
+// in this GPU-less container before spending B200 time. It is not part of the product library and
+// nothing in momentum_b200/ loads it.
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/momentum_b200.h"
+#include "../../momentum_b200/csrc/ik_chol.cuh"
+#include "../../momentum_b200/csrc/ik_device.cuh"
+#include "../../momentum_b200/csrc/ik_plan.h"
+
+using namespace mb2;
+
+static thread_local std::string g_err;
+static int fail(int c, const std::string& m) { g_err = m; return c; }
+
+struct mb2_character { HostCharacter host; };
+struct mb2_solver_function {
+  const mb2_character* ch;
+  int B;
+  std::vector<HostErrorFunction> efs;
+  std::vector<uint8_t> enabled;
+  int targetStride{0}, numWeights{0};
+  bool weightsPerInstance{false};
+  std::vector<float> weights, targets;
+  Plan plan;
+  int ldJ{32};
+  std::vector<float> J, residual;
+  std::vector<double> errors;
+};
+struct mb2_solver {
+  mb2_solver_function* fn;
+  mb2_gauss_newton_options opt;
+  std::vector<double> errors, history;
+  std::vector<int32_t> iterations, status;
+  uint64_t totalIterations{0};
+};
+
+static int roundUp(int v, int m) { return (v + m - 1) / m * m; }
+
+static std::string plan(mb2_solver_function* f) {
+  std::string e = buildPlan(f->ch->host, f->efs, f->enabled, f->plan);
+  if (!e.empty()) return e;
+  f->ldJ = std::max(32, roundUp(f->plan.numRows, 32));
+  f->J.assign(size_t(f->B) * f->ch->host.numParams * f->ldJ, 0.f);
+  f->residual.assign(size_t(f->B) * f->ldJ, 0.f);
+  f->errors.assign(f->B, 0.0);
+  f->targets.resize(size_t(f->B) * std::max(f->targetStride, 1), 0.f);
+  if (f->weights.empty()) f->weights.push_back(0.f);
+  return "";
+}
+
+static FunctionTables tables(const mb2_solver_function* f) {
+  FunctionTables T{};
+  const HostCharacter& h = f->ch->host;
+  T.numJoints = h.numJoints; T.numParams = h.numParams;
+  T.parent = h.parent.data(); T.offset = h.offset.data(); T.prerot = h.prerot.data();
+  T.ptOuter = h.ptOuter.data(); T.ptInner = h.ptInner.data(); T.ptVals = h.ptVals.data(); T.ptOffsets = h.ptOffsets.data();
+  T.numLevels = int(h.levelStart.size()) - 1; T.levelStart = h.levelStart.data(); T.levelJoints = h.levelJoints.data();
+  T.numEf = int(f->plan.efs.size()); T.numUnits = int(f->plan.units.size()); T.numCells = int(f->plan.cells.size());
+  T.efs = f->plan.efs.data(); T.units = f->plan.units.data(); T.cells = f->plan.cells.data(); T.contribs = f->plan.contribs.data();
+  T.limitData = f->plan.limitData.data();
+  T.targetStride = f->targetStride; T.recStride = f->plan.recStride; T.numRows = f->plan.numRows; T.ldJ = f->ldJ;
+  T.weightsPerInstance = f->weightsPerInstance; T.numWeights = f->numWeights;
+  return T;
+}
+
+// emulation of sweepKernel<kJacobian> for one instance (the warp's lanes run in sequence)
+template <bool kJacobian>
+static void sweepOne(mb2_solver_function* f, const FunctionTables& T, int b, const float* theta, double* errOut, float* stateOut) {
+  std::vector<float> jp(size_t(T.numJoints) * 7), js(size_t(T.numJoints) * kJointStateStride), rec(T.recStride + 4);
+  for (int row = 0; row < T.numJoints * 7; ++row) jp[row] = jointParameterRow(T, row, theta);
+  for (int lvl = 0; lvl < T.numLevels; ++lvl)
+    for (int k = T.levelStart[lvl]; k < T.levelStart[lvl + 1]; ++k) fkJoint<kJacobian>(T, T.levelJoints[k], jp.data(), js.data());
+  if (stateOut)
+    for (int i = 0; i < T.numJoints * 8; ++i) stateOut[i] = js[(i >> 3) * kJointStateStride + (i & 7)];
+  const float* tg = f->targets.data() + size_t(b) * T.targetStride;
+  const float* cw = f->weights.data() + (T.weightsPerInstance ? size_t(b) * T.numWeights : 0);
+  float* res = kJacobian ? f->residual.data() + size_t(b) * T.ldJ : nullptr;
+  // lanes accumulate in double, then a butterfly reduction: emulate the same association
+  double lane[32];
+  for (int l = 0; l < 32; ++l) lane[l] = 0.0;
+  for (int u = 0; u < T.numUnits; ++u) lane[u & 31] += (double)evalUnit<kJacobian>(T, u, theta, jp.data(), js.data(), tg, cw, rec.data(), res);
+  for (int o = 16; o > 0; o >>= 1) {
+    double t[32];
+    for (int l = 0; l < 32; ++l) t[l] = lane[l] + lane[l ^ o];
+    for (int l = 0; l < 32; ++l) lane[l] = t[l];
+  }
+  if (kJacobian) {
+    float* J = f->J.data() + size_t(b) * T.numParams * T.ldJ;
+    for (int c = 0; c < T.numCells; ++c) jacobianCell(T, c, js.data(), rec.data(), tg, J);
+  }
+  *errOut = kJacobian ? lane[0] : (double)(float)lane[0];
+}
+
+static void jtjOne(const mb2_solver_function* f, int b, const int32_t* cols, int ns, float* H, int ldH) {
+  const int n = f->ch->host.numParams;
+  const float* J = f->J.data() + size_t(b) * n * f->ldJ;
+  const float* r = f->residual.data() + size_t(b) * f->ldJ;
+  const int K = roundUp(std::max(f->plan.numRows, 1), 4);
+  for (int i = 0; i < ns; ++i) {
+    for (int j = 0; j <= i; ++j) {
+      float s = 0.f;
+      for (int k = 0; k < K; ++k) s = fmaf(J[size_t(cols[i]) * f->ldJ + k], J[size_t(cols[j]) * f->ldJ + k], s);
+      H[size_t(i) * ldH + j] = s;
+    }
+    float g = 0.f;
+    for (int k = 0; k < K; ++k) g = fmaf(J[size_t(cols[i]) * f->ldJ + k], r[k], g);
+    H[size_t(ns) * ldH + i] = g;
+  }
+}
+
+// emulation of choleskyKernel<NB> for one instance; returns fail flag, writes delta and g.delta
+template <int NB>
+static int cholOne(float* Hg, int n, int ldH, float reg, float* delta, float* gdd) {
+  const int lda = n | 1;
+  std::vector<float> A(size_t(n + 1) * lda, 0.f);
+  const int ldp = ((n + 1 + 3) & ~3) + 4;
+  std::vector<float> P(size_t(NB) * ldp, 0.f), gsave(n);
+  for (int i = 0; i <= n; ++i)
+    for (int j = 0; j < n; ++j)
+      if (j <= i || i == n) A[size_t(i) * lda + j] = Hg[size_t(i) * ldH + j] + ((i == j) ? reg : 0.f);
+  for (int i = 0; i < n; ++i) gsave[i] = Hg[size_t(n) * ldH + i];
+  int flag = 0;
+  CholCtx ctx{A.data(), lda, n, P.data(), ldp, &flag};
+  const int blockSize = cholBlockSize(n, NB);
+  for (int k = 0; k < n && flag == 0; k += blockSize) {
+    const int bs = std::min(blockSize, n - k);
+    for (int jj = 0; jj < bs; ++jj) {
+      const float x = cholDiagPivot(ctx, k, jj);
+      if (!(x > 0.f)) { flag = k + jj + 1; break; }
+      for (int lane = 0; lane < 32; ++lane) cholDiagColumn(ctx, k, bs, jj, x, lane);
+    }
+    if (flag) break;
+    for (int t = 0; t < kCholThreads; ++t) cholPanelSolve<NB>(ctx, k, bs, t, kCholThreads);
+    for (int t = 0; t < kCholThreads; ++t) cholTrailingUpdate<NB>(ctx, k, bs, t, kCholThreads);
+  }
+  float* y = A.data() + size_t(n) * lda;
+  if (flag) cholForwardFrom(ctx, cholCompletedColumns(flag - 1, blockSize), y);
+  for (int i = n - 1; i >= 0; --i) {
+    float s = y[i];
+    for (int k = i + 1; k < n; ++k) s -= A[size_t(k) * lda + i] * y[k];
+    y[i] = s / A[size_t(i) * lda + i];
+  }
+  float gd = 0.f;
+  for (int i = 0; i < n; ++i) { delta[i] = y[i]; gd += gsave[i] * y[i]; }
+  *gdd = gd;
+  return flag;
+}
+
+static int cholDispatch(float* Hg, int n, int ldH, float reg, float* delta, float* gdd) {
+  const int eig = cholBlockSize(n, 32);
+  if (eig <= 8) return cholOne<8>(Hg, n, ldH, reg, delta, gdd);
+  if (eig <= 16) return cholOne<16>(Hg, n, ldH, reg, delta, gdd);
+  return cholOne<32>(Hg, n, ldH, reg, delta, gdd);
+}
+
+extern "C" {
+
+const char* mb2_last_error(void) { return g_err.c_str(); }
+int mb2_device_count(void) { return 0; }
+void mb2_default_gauss_newton_options(mb2_gauss_newton_options* o) {
+  std::memset(o, 0, sizeof(*o));
+  o->min_iterations = 1; o->max_iterations = 2; o->threshold = 1.f; o->regularization = 0.05f; o->target_rows_per_chunk = ~0ull;
+}
+
+int mb2_character_create(int, int32_t J, const int32_t* parents, const float* offsets, const float* prerot, int32_t n, const int32_t* outer,
+                         const int32_t* inner, const float* vals, const float* ptoffsets, mb2_character** out) {
+  auto c = std::make_unique<mb2_character>();
+  HostCharacter& h = c->host;
+  h.numJoints = J; h.numParams = n;
+  h.parent.assign(parents, parents + J);
+  h.offset.assign(offsets, offsets + 3 * J);
+  h.prerot.assign(prerot, prerot + 4 * J);
+  h.ptOuter.assign(outer, outer + 7 * J + 1);
+  const int nnz = outer[7 * J];
+  h.ptInner.assign(inner, inner + nnz);
+  h.ptVals.assign(vals, vals + nnz);
+  h.ptOffsets.assign(ptoffsets, ptoffsets + 7 * J);
+  const std::string e = h.validate();
+  if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
+  h.buildLevels();
+  *out = c.release();
+  return MB2_OK;
+}
+int mb2_character_set_parameter_limits(mb2_character* c, int32_t count, const mb2_parameter_limit* limits) {
+  c->host.limits.clear();
+  for (int i = 0; i < count; ++i) {
+    HostLimit l;
+    l.type = limits[i].type; l.weight = limits[i].weight;
+    std::memcpy(l.i, limits[i].i, sizeof(l.i)); std::memcpy(l.f, limits[i].f, sizeof(l.f));
+    c->host.limits.push_back(l);
+  }
+  return MB2_OK;
+}
+void mb2_character_destroy(mb2_character* c) { delete c; }
+
+int mb2_solver_function_create(const mb2_character* c, int32_t batch, mb2_solver_function** out) {
+  auto f = std::make_unique<mb2_solver_function>();
+  f->ch = c; f->B = batch;
+  f->enabled.assign(c->host.numParams, 1);
+  *out = f.release();
+  return MB2_OK;
+}
+void mb2_solver_function_destroy(mb2_solver_function* f) { delete f; }
+int32_t mb2_solver_function_num_parameters(const mb2_solver_function* f) { return f->ch->host.numParams; }
+int32_t mb2_solver_function_batch(const mb2_solver_function* f) { return f->B; }
+int32_t mb2_solver_function_actual_parameters(const mb2_solver_function* f) {
+  int ap = 0;
+  for (int i = 0; i < f->ch->host.numParams; ++i) if (f->enabled[i]) ap = i + 1;
+  return ap;
+}
+int32_t mb2_solver_function_jacobian_rows(const mb2_solver_function* f) {
+  int total = 0;
+  for (const auto& ef : f->efs) if (ef.weight > 0.f) total += jacobianBlockSize(f->ch->host, ef);
+  return roundUp(total, 8);
+}
+int32_t mb2_solver_function_jacobian_stride(const mb2_solver_function* f) {
+  int total = 0;
+  for (const auto& ef : f->efs) if (ef.weight > 0.f) total += jacobianBlockSize(f->ch->host, ef);
+  return std::max(32, roundUp(total, 32));
+}
+
+static int addBlock(mb2_solver_function* f, HostErrorFunction& ef, int32_t* outIndex) {
+  ef.targetOff = f->targetStride; ef.weightOff = f->numWeights;
+  f->targetStride += ef.targetSize;
+  if (ef.kind <= 2) { f->numWeights += ef.numConstraints(); f->weights.insert(f->weights.end(), ef.weights.begin(), ef.weights.end()); }
+  f->efs.push_back(ef);
+  // re-layout targets (tests add all blocks before setting targets)
+  f->targets.assign(size_t(f->B) * std::max(f->targetStride, 1), 0.f);
+  if (outIndex) *outIndex = int32_t(f->efs.size()) - 1;
+  return MB2_OK;
+}
+int mb2_add_position_error_function(mb2_solver_function* f, float weight, float alpha, float c, int32_t nc, const int32_t* parents, const float* offsets,
+                                    const float* weights, int32_t* outIndex) {
+  HostErrorFunction ef;
+  ef.kind = 0; ef.weight = weight; ef.lossAlpha = alpha; ef.lossC = c;
+  ef.parents.assign(parents, parents + nc); ef.offsets.assign(offsets, offsets + 3 * size_t(nc)); ef.weights.assign(weights, weights + nc);
+  ef.targetSize = 3 * nc;
+  return addBlock(f, ef, outIndex);
+}
+int mb2_add_orientation_error_function(mb2_solver_function* f, float weight, float alpha, float c, int32_t rotDiff, int32_t nc, const int32_t* parents,
+                                       const float* offsets, const float* weights, int32_t* outIndex) {
+  HostErrorFunction ef;
+  ef.kind = rotDiff ? 2 : 1; ef.weight = weight; ef.lossAlpha = alpha; ef.lossC = c;
+  ef.parents.assign(parents, parents + nc); ef.offsets.assign(offsets, offsets + 4 * size_t(nc));
+  for (int i = 0; i < nc; ++i) {
+    float* q = &ef.offsets[4 * size_t(i)];
+    const float nrm = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    for (int k = 0; k < 4; ++k) q[k] /= nrm;
+  }
+  ef.weights.assign(weights, weights + nc);
+  ef.targetSize = 4 * nc;
+  return addBlock(f, ef, outIndex);
+}
+int mb2_add_state_error_function(mb2_solver_function* f, float weight, int32_t rotationErrorType, float posWgt, float rotWgt, const float* posW,
+                                 const float* rotW, int32_t* outIndex) {
+  HostErrorFunction ef;
+  ef.kind = 3; ef.weight = weight; ef.rotationErrorType = rotationErrorType; ef.posWgt = posWgt; ef.rotWgt = rotWgt;
+  const int J = f->ch->host.numJoints;
+  ef.posW.assign(posW, posW + J); ef.rotW.assign(rotW, rotW + J);
+  ef.targetSize = 8 * J;
+  return addBlock(f, ef, outIndex);
+}
+int mb2_add_limit_error_function(mb2_solver_function* f, float weight, float alpha, float c, int32_t* outIndex) {
+  HostErrorFunction ef;
+  ef.kind = 4; ef.weight = weight; ef.lossAlpha = alpha; ef.lossC = c; ef.targetSize = 0;
+  return addBlock(f, ef, outIndex);
+}
+int mb2_set_error_function_weight(mb2_solver_function* f, int32_t index, float weight) { f->efs[index].weight = weight; return MB2_OK; }
+int mb2_set_targets(mb2_solver_function* f, int32_t index, const float* targets) {
+  const HostErrorFunction& ef = f->efs[index];
+  for (int b = 0; b < f->B; ++b) {
+    float* dst = f->targets.data() + size_t(b) * f->targetStride + ef.targetOff;
+    std::memcpy(dst, targets + size_t(b) * ef.targetSize, size_t(ef.targetSize) * sizeof(float));
+    if (ef.kind == 1 || ef.kind == 2)
+      for (int q = 0; q < ef.numConstraints(); ++q) {
+        float* p = dst + 4 * q;
+        const float n = sqrtf(p[0] * p[0] + p[1] * p[1] + p[2] * p[2] + p[3] * p[3]);
+        p[0] /= n; p[1] /= n; p[2] /= n; p[3] /= n;
+      }
+  }
+  return MB2_OK;
+}
+int mb2_set_constraint_weights(mb2_solver_function* f, int32_t index, const float* weights, int32_t perInstance) {
+  HostErrorFunction& ef = f->efs[index];
+  const int nc = ef.numConstraints();
+  if (!perInstance) { std::copy(weights, weights + nc, f->weights.begin() + ef.weightOff); return MB2_OK; }
+  if (!f->weightsPerInstance) {
+    std::vector<float> all(size_t(f->B) * f->numWeights);
+    for (int b = 0; b < f->B; ++b) std::copy(f->weights.begin(), f->weights.begin() + f->numWeights, all.begin() + size_t(b) * f->numWeights);
+    f->weights = all;
+    f->weightsPerInstance = true;
+  }
+  for (int b = 0; b < f->B; ++b) std::copy(weights + size_t(b) * nc, weights + size_t(b + 1) * nc, f->weights.begin() + size_t(b) * f->numWeights + ef.weightOff);
+  return MB2_OK;
+}
+int mb2_solver_function_set_enabled_parameters(mb2_solver_function* f, const uint64_t* bits) {
+  for (int i = 0; i < f->ch->host.numParams; ++i) f->enabled[i] = (bits[i >> 6] >> (i & 63)) & 1ull ? 1 : 0;
+  return MB2_OK;
+}
+
+int mb2_solver_function_get_error(mb2_solver_function* f, const float* params, double* errors) {
+  const std::string e = plan(f);
+  if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
+  const FunctionTables T = tables(f);
+  for (int b = 0; b < f->B; ++b) sweepOne<false>(f, T, b, params + size_t(b) * T.numParams, &errors[b], nullptr);
+  return MB2_OK;
+}
+int mb2_solver_function_get_skeleton_state(mb2_solver_function* f, const float* params, float* state) {
+  const std::string e = plan(f);
+  if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
+  const FunctionTables T = tables(f);
+  double err;
+  for (int b = 0; b < f->B; ++b) sweepOne<false>(f, T, b, params + size_t(b) * T.numParams, &err, state + size_t(b) * T.numJoints * 8);
+  return MB2_OK;
+}
+int mb2_solver_function_get_jacobian(mb2_solver_function* f, const float* params, float* jac, float* residual, double* errors, int32_t* actualRows) {
+  const std::string e = plan(f);
+  if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
+  const FunctionTables T = tables(f);
+  const int rows = mb2_solver_function_jacobian_rows(f), n = T.numParams;
+  for (int b = 0; b < f->B; ++b) {
+    double err;
+    sweepOne<true>(f, T, b, params + size_t(b) * n, &err, nullptr);
+    if (errors) errors[b] = err;
+    for (int c = 0; c < n && jac; ++c) std::memcpy(jac + (size_t(b) * n + c) * rows, f->J.data() + (size_t(b) * n + c) * f->ldJ, size_t(rows) * sizeof(float));
+    if (residual) std::memcpy(residual + size_t(b) * rows, f->residual.data() + size_t(b) * f->ldJ, size_t(rows) * sizeof(float));
+  }
+  if (actualRows) *actualRows = rows;
+  return MB2_OK;
+}
+int mb2_solver_function_get_jtjr(mb2_solver_function* f, const float* params, int32_t, float* jtj, float* jtr, double* errors) {
+  const std::string e = plan(f);
+  if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
+  const FunctionTables T = tables(f);
+  const int ap = f->plan.actualParameters, n = T.numParams, ldH = ap | 1;
+  std::vector<int32_t> ident(n);
+  for (int i = 0; i < n; ++i) ident[i] = i;
+  std::vector<float> H(size_t(ap + 1) * ldH);
+  for (int b = 0; b < f->B; ++b) {
+    double err;
+    sweepOne<true>(f, T, b, params + size_t(b) * n, &err, nullptr);
+    if (errors) errors[b] = err;
+    std::fill(H.begin(), H.end(), 0.f);
+    jtjOne(f, b, ident.data(), ap, H.data(), ldH);
+    for (int i = 0; i < ap; ++i) {
+      if (jtj) std::memcpy(jtj + (size_t(b) * ap + i) * ap, H.data() + size_t(i) * ldH, size_t(ap) * sizeof(float));
+      if (jtr) jtr[size_t(b) * ap + i] = H[size_t(ap) * ldH + i];
+    }
+  }
+  return MB2_OK;
+}
+
+int mb2_solver_create(mb2_solver_function* f, const mb2_gauss_newton_options* opt, mb2_solver** out) {
+  auto s = std::make_unique<mb2_solver>();
+  s->fn = f;
+  if (opt) s->opt = *opt; else mb2_default_gauss_newton_options(&s->opt);
+  *out = s.release();
+  return MB2_OK;
+}
+void mb2_solver_destroy(mb2_solver* s) { delete s; }
+int mb2_solver_set_options(mb2_solver* s, const mb2_gauss_newton_options* opt) { s->opt = *opt; return MB2_OK; }
+int mb2_solver_set_enabled_parameters(mb2_solver* s, const uint64_t* bits) { return mb2_solver_function_set_enabled_parameters(s->fn, bits); }
+
+// emulation of mb2_solver_solve_device's launch sequence, instance by instance
+int mb2_solver_solve(mb2_solver* s, float* params, double* errors, int32_t* iterations, int32_t* status) {
+  mb2_solver_function* f = s->fn;
+  const std::string e = plan(f);
+  if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
+  const FunctionTables T = tables(f);
+  const int n = T.numParams, ns = int(f->plan.enabledList.size()), ldH = ns | 1;
+  const auto& o = s->opt;
+  const int maxIt = int(o.max_iterations), minIt = int(o.min_iterations);
+  s->errors.assign(f->B, DBL_MAX); s->iterations.assign(f->B, 0); s->status.assign(f->B, 0);
+  s->history.assign(size_t(f->B) * std::max(maxIt, 1), 0.0);
+  std::vector<float> H(size_t(ns + 1) * ldH), delta(ns), orig(n);
+  s->totalIterations = 0;
+  for (int b = 0; b < f->B; ++b) {
+    float* theta = params + size_t(b) * n;
+    std::vector<float> theta0(theta, theta + n);
+    double last = DBL_MAX, error = DBL_MAX;
+    for (int it = 0; it < maxIt; ++it) {
+      sweepOne<true>(f, T, b, theta, &error, nullptr);
+      std::fill(H.begin(), H.end(), 0.f);
+      jtjOne(f, b, f->plan.enabledList.data(), ns, H.data(), ldH);
+      float gdd = 0.f;
+      if (cholDispatch(H.data(), ns, ldH, o.regularization, delta.data(), &gdd) && s->status[b] == 0) s->status[b] = MB2_INSTANCE_CHOLESKY_BREAKDOWN;
+      if (!o.do_line_search) {
+        for (int a = 0; a < ns; ++a) theta[f->plan.enabledList[a]] -= delta[a];
+      } else {
+        std::copy(theta, theta + n, orig.begin());
+        float scale = 1.f;
+        for (int step = 0; step < 10; ++step) {
+          for (int a = 0; a < ns; ++a) { const int c = f->plan.enabledList[a]; theta[c] = orig[c] - scale * delta[a]; }
+          double en;
+          sweepOne<false>(f, T, b, theta, &en, nullptr);
+          bool accept;
+          if (!o.subset_line_search) accept = (error - en) >= (double)(scale * (1e-3f * (float)error));
+          else accept = (error - en) >= (double)(1e-4f * scale) * (double)gdd;
+          if (accept || step >= 9) break;
+          scale *= 0.5f;
+        }
+      }
+      s->history[size_t(b) * std::max(maxIt, 1) + it] = error;
+      s->iterations[b] = it + 1;
+      const bool converged = std::fabs(last - error) / (std::fabs(error) + (double)FLT_MIN) <= (double)(o.threshold * FLT_EPSILON);
+      if (it >= minIt && converged) break;
+      last = error;
+    }
+    bool bad = false;
+    for (int i = 0; i < n; ++i) if (!std::isfinite(theta[i])) bad = true;
+    if (bad) { std::copy(theta0.begin(), theta0.end(), theta); s->status[b] = MB2_INSTANCE_NON_FINITE; }
+    s->errors[b] = error;
+    s->totalIterations += s->iterations[b];
+    if (errors) errors[b] = error;
+    if (iterations) iterations[b] = s->iterations[b];
+    if (status) status[b] = s->status[b];
+  }
+  return MB2_OK;
+}
+int mb2_solver_get_error_history(mb2_solver* s, double* history) {
+  std::memcpy(history, s->history.data(), s->history.size() * sizeof(double));
+  return MB2_OK;
+}
+int mb2_solver_get_counters(mb2_solver* s, uint64_t* totalIterations, uint64_t* kernelLaunches) {
+  if (totalIterations) *totalIterations = s->totalIterations;
+  if (kernelLaunches) *kernelLaunches = 0;
+  return MB2_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,106 @@
+"""Shared parity checks: a backend implementing include/momentum_b200.h (the CUDA product library, or
+the CPU lane-emulation harness tests/emu) against the float oracle on the same inputs.
+
+Tolerances: single-iteration JtJ / Jtr Linf <= 1e-5 relative in fp32 mode (the
+reference's own cross-implementation bound is 1e-3, error_function_helpers.h:70-78); converged
+parameters ||dtheta||inf / max(1, ||theta||inf) <= 1e-4; objective rel <= 1e-3 or abs <= 1e-7."""
+import numpy as np
+
+from momentum_b200 import character as mc
+from momentum_b200 import solver as ms
+from oracle.binding import OracleFunction
+
+
+def build_function(ch, efs, B, lib_path=None, enabled=None):
+    fn = ms.SkeletonSolverFunction(ch, B, efs, lib_path=lib_path)
+    fn.upload_targets()
+    if enabled is not None:
+        fn.set_enabled_parameters(enabled)
+    return fn
+
+
+def f32(a):
+    return np.asarray(a, np.float32).astype(np.float64)
+
+
+def check_fk(ch, efs, theta, lib_path=None, atol=2e-5):
+    B = theta.shape[0]
+    fn = build_function(ch, efs, B, lib_path)
+    st = fn.get_skeleton_state(theta)
+    for b in range(B):
+        orc = OracleFunction(ch, efs, "float32", instance=b)
+        xf, _, _ = orc.fk(f32(theta[b]))
+        scale = max(1.0, np.abs(xf[:, :3]).max())
+        assert np.max(np.abs(st[b, :, :3] - xf[:, :3])) <= atol * scale
+        assert np.max(np.abs(st[b, :, 3:] - xf[:, 3:])) <= atol
+
+
+def check_single_iteration(ch, efs, theta, lib_path=None, enabled=None, rtol=1e-5, jtj_mode=ms.JTJ_FP32_SIMT, check_jacobian=True):
+    B = theta.shape[0]
+    fn = build_function(ch, efs, B, lib_path, enabled)
+    e_gpu = fn.get_error(theta)
+    ej, J, r, rows = fn.get_jacobian(theta)
+    eh, H, g = fn.get_jtjr(theta, jtj_mode)
+    for b in range(B):
+        orc = OracleFunction(ch, efs, "float32", instance=b)
+        if enabled is not None:
+            orc.set_enabled_parameters(enabled)
+        th = f32(theta[b])
+        e0 = orc.get_error(th)
+        e1, Jo, ro, rows_o = orc.get_jacobian(th)
+        e2, Ho, go = orc.get_jtjr(th)
+        assert rows == rows_o, (rows, rows_o)
+        assert abs(e_gpu[b] - e0) <= 2e-5 * max(1.0, abs(e0)), (b, e_gpu[b], e0)
+        assert abs(ej[b] - e1) <= 2e-5 * max(1.0, abs(e1)), (b, ej[b], e1)
+        assert abs(eh[b] - e2) <= 2e-5 * max(1.0, abs(e2))
+        if check_jacobian:
+            js = max(1.0, np.abs(Jo).max())
+            assert np.max(np.abs(J[b] - Jo)) <= 2e-5 * js, (b, np.max(np.abs(J[b] - Jo)), js)
+            assert np.max(np.abs(r[b] - ro)) <= 2e-5 * max(1.0, np.abs(ro).max())
+            # structural zeros (gating by enabledParameters_/activeJointParams_): nothing but FMA-level
+            # cancellation noise may appear where the reference has an exact zero
+            assert np.max(np.abs(J[b][np.abs(Jo) == 0]), initial=0.0) <= 2e-6 * js
+        hs = max(1.0, np.abs(Ho).max())
+        assert np.max(np.abs(np.tril(H[b]) - np.tril(Ho))) <= rtol * hs, (b, np.max(np.abs(np.tril(H[b]) - np.tril(Ho))), hs)
+        assert np.max(np.abs(g[b] - go)) <= rtol * max(1.0, np.abs(go).max())
+    return fn
+
+
+def check_solve(ch, efs, theta0, opts: ms.GaussNewtonSolverOptions, lib_path=None, enabled=None, param_tol=1e-4, instances=None,
+                compare_history=True):
+    B = theta0.shape[0]
+    fn = build_function(ch, efs, B, lib_path, enabled)
+    solver = ms.GaussNewtonSolver(opts, fn)
+    out = solver.solve(theta0)
+    idx = range(B) if instances is None else instances
+    worst = 0.0
+    for b in idx:
+        orc = OracleFunction(ch, efs, "float32", instance=b)
+        if enabled is not None:
+            orc.set_enabled_parameters(enabled)
+        err, p, it, hist = orc.solve(f32(theta0[b]), min_iterations=opts.min_iterations, max_iterations=opts.max_iterations,
+                                     threshold=opts.threshold, regularization=opts.regularization, do_line_search=opts.do_line_search,
+                                     use_block_jtj=opts.use_block_jtj, subset_solver=opts.subset_line_search)
+        d = np.max(np.abs(out["params"][b] - p)) / max(1.0, np.max(np.abs(p)))
+        worst = max(worst, d)
+        tol, etol = param_tol, 1e-3 * abs(err) + 1e-7
+        if d > param_tol or abs(out["errors"][b] - err) > etol:
+            # ill-conditioned instance: float rounding alone moves the reference by more than the
+            # nominal tolerance. Calibrate with the reference's own float-vs-double gap on the same
+            # inputs (the reference runs its tests in both precisions, error_function_helpers.h:38-52).
+            orc64 = OracleFunction(ch, efs, "float64", instance=b)
+            if enabled is not None:
+                orc64.set_enabled_parameters(enabled)
+            err64, p64, _, _ = orc64.solve(f32(theta0[b]), min_iterations=opts.min_iterations, max_iterations=opts.max_iterations,
+                                           threshold=opts.threshold, regularization=opts.regularization, do_line_search=opts.do_line_search,
+                                           use_block_jtj=opts.use_block_jtj, subset_solver=opts.subset_line_search)
+            tol = max(param_tol, 3.0 * np.max(np.abs(p - p64)) / max(1.0, np.max(np.abs(p))))
+            etol = max(etol, 3.0 * abs(err - err64))
+        assert d <= tol, (b, d, tol, out["iterations"][b], it)
+        assert abs(out["errors"][b] - err) <= etol, (b, out["errors"][b], err)
+        if compare_history:
+            assert abs(int(out["iterations"][b]) - it) <= 1, (b, out["iterations"][b], it)
+        if enabled is not None:
+            dis = ~np.asarray(enabled, bool)
+            assert np.array_equal(out["params"][b][dis], np.asarray(theta0[b], np.float32)[dis])
+    return out, worst

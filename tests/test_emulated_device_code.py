@@ -1,0 +1,103 @@
+"""CPU lane-emulation of the device building blocks (tests/emu) vs the oracle.
+
+Validates, without a GPU: the planner (units / cells / chain-rule contributions / gating), the
+per-lane FK + residual + Jacobian code, the Eigen-structured blocked Cholesky phases and the batched
+solve loop — i.e. everything in momentum_b200/csrc that is not CUDA launch glue."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from momentum_b200 import character as mc
+from momentum_b200 import solver as ms
+from momentum_b200.problems import chain_problem, chain22_problem, humanoid_problem
+from tests import parity
+
+EMU_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
+EMU_LIB = os.path.join(EMU_DIR, "libmb2_emu.so")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _build_emu():
+    subprocess.check_call(["make", "-C", EMU_DIR, "-s"])
+
+
+FAMS = [("position",), ("orientation",), ("state",), ("limit",), ("position", "orientation", "state", "limit")]
+
+
+@pytest.mark.parametrize("fams", FAMS)
+def test_single_iteration_families(fams):
+    ch, efs, theta0, _ = chain_problem(J=6, B=3, seed=21, families=fams)
+    parity.check_fk(ch, efs, theta0, EMU_LIB)
+    parity.check_single_iteration(ch, efs, theta0, EMU_LIB)
+
+
+@pytest.mark.parametrize("logmap,rot_diff", [(True, False), (False, True)])
+def test_single_iteration_logmap_rotdiff(logmap, rot_diff):
+    ch, efs, theta0, _ = chain_problem(J=7, B=2, seed=22, families=("orientation", "state"), logmap=logmap, rot_diff=rot_diff)
+    parity.check_single_iteration(ch, efs, theta0, EMU_LIB)
+
+
+@pytest.mark.parametrize("alpha,c", [(mc.LOSS_L1, 0.7), (mc.LOSS_CAUCHY, 1.3), (mc.LOSS_WELSCH, 0.9), (-2.0, 1.1), (1.5, 0.8)])
+def test_single_iteration_generalized_loss(alpha, c):
+    ch, efs, theta0, _ = chain_problem(J=5, B=2, seed=23, families=("position", "orientation", "limit"), loss=(alpha, c))
+    parity.check_single_iteration(ch, efs, theta0, EMU_LIB)
+
+
+def test_single_iteration_enabled_subset():
+    ch, efs, theta0, _ = chain_problem(J=6, B=2, seed=24)
+    en = np.ones(ch.num_params, bool); en[[0, 2, 5, 8, ch.num_params - 1]] = False
+    parity.check_single_iteration(ch, efs, theta0, EMU_LIB, enabled=en)
+
+
+def test_humanoid_single_iteration():
+    ch, efs, theta0, theta_star = humanoid_problem(2, orientation=True)
+    th = (theta0 + 0.3 * theta_star).astype(np.float32)
+    parity.check_single_iteration(ch, efs, th, EMU_LIB)
+
+
+@pytest.mark.parametrize("line_search,subset", [(False, False), (True, False), (True, True)])
+def test_solve_chain_all_families(line_search, subset):
+    ch, efs, theta0, _ = chain_problem(J=6, B=3, seed=25)
+    # fixed iteration count with line search: the relative-change stop (solver.cpp:98-101) sits at the
+    # float rounding floor there, so iteration counts are only comparable without it
+    opts = ms.GaussNewtonSolverOptions(min_iterations=8 if line_search else 1, max_iterations=8 if line_search else 12, threshold=10.0,
+                                       regularization=0.05, do_line_search=line_search, subset_line_search=subset)
+    parity.check_solve(ch, efs, theta0, opts, EMU_LIB, param_tol=2e-4)
+
+
+def test_solve_enabled_subset_and_block_sizes():
+    # n = 39 -> Eigen block size 8 (blocked LLT path), with a non-contiguous enabled set
+    ch, efs, theta0, theta_star = chain_problem(J=32, B=2, seed=26, families=("position", "state"))
+    theta0 = theta_star + 0.1 * theta0  # start near the targets: a 32-joint chain far from them is chaotic in float
+    en = np.ones(ch.num_params, bool); en[[1, 6, 9, 12, 30]] = False
+    opts = ms.GaussNewtonSolverOptions(min_iterations=2, max_iterations=6, regularization=0.05)
+    parity.check_solve(ch, efs, theta0, opts, EMU_LIB, enabled=en, param_tol=2e-4)
+
+
+def test_solve_humanoid_blocked_cholesky():
+    ch, efs, theta0, _ = humanoid_problem(2, orientation=True)
+    opts = ms.GaussNewtonSolverOptions(min_iterations=1, max_iterations=6, regularization=0.05)
+    out, worst = parity.check_solve(ch, efs, theta0, opts, EMU_LIB)
+    assert np.all(out["status"] == 0)
+
+
+def test_ka4_three_joint_ik_with_cholesky_breakdown():
+    # inverse_kinematics_test.cpp:38-123 in float: regularization 1e-7 makes LLT hit a zero pivot;
+    # the solver must behave like Eigen's early-exit LLT (status flags the breakdown, result still fine).
+    ch = mc.create_test_character(3)
+    rng = np.random.default_rng(12345)
+    tg = (rng.uniform(-1, 1, (10, 1, 3)) * 3).astype(np.float32)
+    pos = mc.PositionErrorFunction(np.array([2], np.int32), np.array([[0.0, 1.0, 0.0]]), np.array([1.0]), tg)
+    opts = ms.GaussNewtonSolverOptions(min_iterations=6, max_iterations=6, threshold=1.0, regularization=1e-7, use_block_jtj=True)
+    out, _ = parity.check_solve(ch, [pos], np.zeros((10, ch.num_params), np.float32), opts, EMU_LIB, param_tol=5e-3, compare_history=True)
+    p = mc.world_points(ch, out["params"], [2], [[0, 1.0, 0]])[:, 0]
+    assert np.all(np.linalg.norm(p - tg[:, 0], axis=1) <= 5e-5)
+    assert np.all(out["errors"] <= 5e-7)
+
+
+def test_chain22_cfg1():
+    ch, efs, theta0, _ = chain22_problem()
+    opts = ms.GaussNewtonSolverOptions(min_iterations=1, max_iterations=50, threshold=1.0, regularization=0.05)
+    parity.check_solve(ch, efs, theta0, opts, EMU_LIB, param_tol=2e-4)

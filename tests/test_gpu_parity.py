@@ -1,0 +1,155 @@
+"""GPU parity tests proper: the CUDA product path through the C-ABI vs the float oracle on the same
+seeded inputs (small sizes), plus size-independent properties at BASELINE.json's full sizes."""
+import numpy as np
+import pytest
+
+from momentum_b200 import character as mc
+from momentum_b200 import solver as ms
+from momentum_b200.problems import bodyhands_problem, chain_problem, chain22_problem, humanoid_problem
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+FAMS = [("position",), ("orientation",), ("state",), ("limit",), ("position", "orientation", "state", "limit")]
+
+
+@pytest.mark.parametrize("fams", FAMS)
+def test_single_iteration_families(fams):
+    ch, efs, theta0, _ = chain_problem(J=6, B=5, seed=21, families=fams)
+    parity.check_fk(ch, efs, theta0)
+    parity.check_single_iteration(ch, efs, theta0)
+
+
+@pytest.mark.parametrize("logmap,rot_diff", [(True, False), (False, True)])
+def test_single_iteration_logmap_rotdiff(logmap, rot_diff):
+    ch, efs, theta0, _ = chain_problem(J=7, B=3, seed=22, families=("orientation", "state"), logmap=logmap, rot_diff=rot_diff)
+    parity.check_single_iteration(ch, efs, theta0)
+
+
+@pytest.mark.parametrize("alpha,c", [(mc.LOSS_L1, 0.7), (mc.LOSS_CAUCHY, 1.3), (mc.LOSS_WELSCH, 0.9), (-2.0, 1.1), (1.5, 0.8)])
+def test_single_iteration_generalized_loss(alpha, c):
+    ch, efs, theta0, _ = chain_problem(J=5, B=3, seed=23, families=("position", "orientation", "limit"), loss=(alpha, c))
+    parity.check_single_iteration(ch, efs, theta0)
+
+
+def test_single_iteration_enabled_subset():
+    ch, efs, theta0, _ = chain_problem(J=6, B=3, seed=24)
+    en = np.ones(ch.num_params, bool); en[[0, 2, 5, 8, ch.num_params - 1]] = False
+    parity.check_single_iteration(ch, efs, theta0, enabled=en)
+
+
+def test_humanoid_single_iteration():
+    ch, efs, theta0, theta_star = humanoid_problem(40, orientation=True)
+    th = (theta0 + 0.3 * theta_star).astype(np.float32)
+    parity.check_single_iteration(ch, efs, th[:40])
+
+
+def test_bodyhands_single_iteration_wide_rig():
+    # 300 joints / n = 424 / m = 600: multi-pass levels (>32 joints per depth level), matrix too big for smem Cholesky
+    ch, efs, theta0, theta_star = bodyhands_problem(3)
+    th = (theta0 + 0.3 * theta_star).astype(np.float32)
+    parity.check_single_iteration(ch, efs, th, check_jacobian=True)
+
+
+@pytest.mark.parametrize("line_search,subset", [(False, False), (True, False), (True, True)])
+def test_solve_chain_all_families(line_search, subset):
+    ch, efs, theta0, _ = chain_problem(J=6, B=7, seed=25)
+    opts = ms.GaussNewtonSolverOptions(min_iterations=8 if line_search else 1, max_iterations=8 if line_search else 12, threshold=10.0,
+                                       regularization=0.05, do_line_search=line_search, subset_line_search=subset)
+    parity.check_solve(ch, efs, theta0, opts, param_tol=2e-4)
+
+
+def test_solve_enabled_subset_and_block_sizes():
+    ch, efs, theta0, theta_star = chain_problem(J=32, B=4, seed=26, families=("position", "state"))
+    theta0 = theta_star + 0.1 * theta0
+    en = np.ones(ch.num_params, bool); en[[1, 6, 9, 12, 30]] = False
+    opts = ms.GaussNewtonSolverOptions(min_iterations=2, max_iterations=6, regularization=0.05)
+    parity.check_solve(ch, efs, theta0, opts, enabled=en, param_tol=2e-4)
+
+
+def test_ka4_three_joint_ik_with_cholesky_breakdown():
+    # momentum/test/character_solver/inverse_kinematics_test.cpp:38-123, float instantiation
+    ch = mc.create_test_character(3)
+    rng = np.random.default_rng(12345)
+    tg = (rng.uniform(-1, 1, (10, 1, 3)) * 3).astype(np.float32)
+    pos = mc.PositionErrorFunction(np.array([2], np.int32), np.array([[0.0, 1.0, 0.0]]), np.array([1.0]), tg)
+    opts = ms.GaussNewtonSolverOptions(min_iterations=6, max_iterations=6, threshold=1.0, regularization=1e-7, use_block_jtj=True)
+    out, _ = parity.check_solve(ch, [pos], np.zeros((10, ch.num_params), np.float32), opts, param_tol=5e-3)
+    p = mc.world_points(ch, out["params"], [2], [[0, 1.0, 0]])[:, 0]
+    assert np.all(np.linalg.norm(p - tg[:, 0], axis=1) <= 5e-5)
+    assert np.all(out["errors"] <= 5e-7)
+
+
+def test_cfg1_chain22():
+    ch, efs, theta0, _ = chain22_problem()
+    opts = ms.GaussNewtonSolverOptions(min_iterations=1, max_iterations=50, threshold=1.0, regularization=0.05)
+    parity.check_solve(ch, efs, theta0, opts, param_tol=2e-4)
+
+
+@pytest.mark.parametrize("orientation", [False, True])
+def test_cfg2_cfg3_humanoid_converged_parameters(orientation):
+    # cfg2 (24 Position, m=72) / cfg3 (+6 Orientation, m=126) at a size the oracle finishes in seconds
+    B = 96
+    ch, efs, theta0, _ = humanoid_problem(B, orientation=orientation)
+    opts = ms.GaussNewtonSolverOptions(min_iterations=1, max_iterations=50, threshold=1.0, regularization=0.05)
+    out, worst = parity.check_solve(ch, efs, theta0, opts, instances=range(0, B, 5))
+    assert np.all(out["status"] == 0)
+    print("max rel param diff", worst)
+
+
+def test_cfg4_bodyhands_solve():
+    ch, efs, theta0, _ = bodyhands_problem(6)
+    opts = ms.GaussNewtonSolverOptions(min_iterations=1, max_iterations=10, threshold=1.0, regularization=0.05)
+    parity.check_solve(ch, efs, theta0, opts, instances=[0, 5])
+
+
+def test_full_size_properties_cfg3_shard():
+    """BASELINE cfg3 per-GPU shard (8192 x humanoid72, m=126): properties that need no oracle."""
+    B = 8192
+    ch, efs, theta0, theta_star = humanoid_problem(B, orientation=True)
+    fn = parity.build_function(ch, efs, B)
+    e0 = fn.get_error(theta0)
+    opts = ms.GaussNewtonSolverOptions(min_iterations=1, max_iterations=30, threshold=1.0, regularization=0.05, store_error_history=True)
+    solver = ms.GaussNewtonSolver(opts, fn)
+    out = solver.solve(theta0)
+    assert np.all(out["status"] == 0) and np.all(np.isfinite(out["params"]))
+    e1 = fn.get_error(out["params"])
+    assert np.all(e1 <= 1e-3 * e0 + 1e-6)                     # reachable targets: objective collapses
+    hist = solver.get_error_history()
+    for b in range(0, B, 511):                                   # history is monotone for damped GN here
+        h = hist[b, : out["iterations"][b]]
+        assert np.all(np.diff(h) <= 1e-6 * h[:-1] + 1e-9)
+    # idempotence: solving again from the solution changes nothing measurable
+    out2 = ms.GaussNewtonSolver(ms.GaussNewtonSolverOptions(min_iterations=1, max_iterations=3, regularization=0.05), fn).solve(out["params"])
+    assert np.max(np.abs(out2["params"] - out["params"])) <= 5e-3
+    # permutation equivariance: instance b of a shuffled batch gives bit-identical parameters
+    perm = np.random.default_rng(0).permutation(B)
+    efs_p = [type(e)(**{**e.__dict__, "targets": np.asarray(e.targets)[perm]}) for e in efs]
+    fn_p = parity.build_function(ch, efs_p, B)
+    out_p = ms.GaussNewtonSolver(opts, fn_p).solve(theta0[perm])
+    assert np.array_equal(out_p["params"], out["params"][perm])
+
+
+def test_per_instance_constraint_weights_and_zero_weight_skip():
+    ch, efs, theta0, _ = chain_problem(J=6, B=4, seed=31, families=("position",))
+    fn = parity.build_function(ch, efs, 4)
+    w = np.tile(np.asarray(efs[0].weights, np.float32), (4, 1))
+    w[1, 0] = 0.0; w[2, :] *= 2.0
+    fn.set_constraint_weights(0, w, per_instance=True)
+    e = fn.get_error(theta0)
+    from oracle.binding import OracleFunction
+    import copy
+    for b in range(4):
+        ef = copy.copy(efs[0]); ef.weights = w[b]
+        orc = OracleFunction(ch, [ef], "float32", instance=b)
+        assert abs(orc.get_error(parity.f32(theta0[b])) - e[b]) <= 2e-5 * max(1, e[b])
+
+
+def test_non_finite_input_reverts_to_initial_guess():
+    # batched caller's guard, pymomentum/tensor_ik/tensor_ik.cpp:168-173
+    ch, efs, theta0, _ = chain_problem(J=5, B=3, seed=33, families=("position",))
+    efs[0].targets = np.asarray(efs[0].targets).copy(); efs[0].targets[1, 0, 0] = np.nan
+    fn = parity.build_function(ch, efs, 3)
+    out = ms.GaussNewtonSolver(ms.GaussNewtonSolverOptions(max_iterations=4), fn).solve(theta0)
+    assert out["status"][1] == ms.INSTANCE_NON_FINITE and np.array_equal(out["params"][1], theta0[1].astype(np.float32))
+    assert out["status"][0] == 0 and out["status"][2] == 0
