@@ -157,7 +157,9 @@ def main():
     solver = ms.GaussNewtonSolver(opts, fn)
     m_rows = sum(3 * len(e.parents) if e.kind == 0 else 9 * len(e.parents) for e in efs)
 
-    stream = torch.cuda.current_stream().cuda_stream
+    work_stream = torch.cuda.Stream()  # a real (non-NULL) stream: NULL means "the handle's own stream" in the C-ABI
+    torch.cuda.set_stream(work_stream)
+    stream = work_stream.cuda_stream
     theta0_dev = torch.from_numpy(theta0.astype(np.float32)).cuda()
     theta_dev = torch.empty_like(theta0_dev)
     # pinned host buffers for the e2e leg

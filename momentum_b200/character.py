@@ -249,6 +249,11 @@ def bodyhands300(seed: int = 12348) -> "tuple[Character, dict]":
     n_body = len(tb.parents)
     assert n_body == 60
     attach += [head] * 4 + spine * 4
+    body_all = list(range(1, n_body))
+    k = 0
+    while len(attach) < 60:  # remaining helper chains hang off body joints round-robin
+        attach.append(body_all[(7 * k) % len(body_all)])
+        k += 1
     chain_parents = attach[:60]
     assert len(chain_parents) == 60
     helper_ids = []

@@ -84,6 +84,7 @@ struct mb2_solver_function {
   int targetStride{0}, numWeights{0};
   bool weightsPerInstance{false};
   bool planDirty{true};
+  bool planCompact{false};
   uint64_t planLimitsVersion{~0ull};
   Plan plan;
   int ldJ{32};
@@ -95,7 +96,7 @@ struct mb2_solver_function {
   DeviceBuffer<float> dLimitData;
   DeviceBuffer<int32_t> dEnabledList, dIdentity;
   // device data
-  DeviceBuffer<float> dTargets, dWeights, dJ, dResidual, dTheta, dState, dH;
+  DeviceBuffer<float> dTargets, dWeights, dJ, dTheta, dState, dH;
   DeviceBuffer<double> dErrors;
   std::vector<float> hWeights; // shared weights mirror
   FunctionTables tables() const;
@@ -152,6 +153,7 @@ FunctionTables mb2_solver_function::tables() const {
   T.recStride = plan.recStride;
   T.numRows = plan.numRows;
   T.ldJ = ldJ;
+  T.numCols = plan.numCols;
   T.weightsPerInstance = weightsPerInstance ? 1 : 0;
   T.numWeights = numWeights;
   return T;
@@ -206,10 +208,17 @@ int uploadWeights(mb2_solver_function* f) {
   return MB2_OK;
 }
 
-int ensurePlan(mb2_solver_function* f) {
-  if (!f->planDirty && f->planLimitsVersion == f->ch->limitsVersion) return MB2_OK;
+// compact = true: device Jacobian holds only the enabled columns, packed (solver path);
+// compact = false: every column at its model-parameter index (getJacobian / getJtJR parity).
+// Both coincide when every parameter is enabled.
+int ensurePlan(mb2_solver_function* f, bool compact) {
+  bool allEnabled = true;
+  for (uint8_t e : f->enabled) allEnabled = allEnabled && e;
+  if (allEnabled) compact = false;
+  if (!f->planDirty && f->planLimitsVersion == f->ch->limitsVersion && f->planCompact == compact) return MB2_OK;
   MB2_CUDA(cudaSetDevice(f->ch->device));
-  const std::string err = buildPlan(f->ch->host, f->efs, f->enabled, f->plan);
+  f->planCompact = compact;
+  const std::string err = buildPlan(f->ch->host, f->efs, f->enabled, compact, f->plan);
   if (!err.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, err);
   cudaStream_t s = f->stream;
   MB2_CUDA(f->dEfs.upload(f->plan.efs, s));
@@ -222,13 +231,11 @@ int ensurePlan(mb2_solver_function* f) {
   for (size_t i = 0; i < ident.size(); ++i) ident[i] = int32_t(i);
   MB2_CUDA(f->dIdentity.upload(ident, s));
   f->ldJ = std::max(32, roundUp(f->plan.numRows, 32));
-  const size_t jElems = size_t(f->B) * f->ch->host.numParams * f->ldJ;
+  const size_t jElems = size_t(f->B) * (f->plan.numCols + 1) * f->ldJ;
   MB2_CUDA(f->dJ.resize(jElems));
   // cells outside the plan are never written: zero once per plan (ResizeableMatrix::resizeAndSetZero
   // happens every iteration in the reference, solver_function.cpp:96)
   MB2_CUDA(cudaMemsetAsync(f->dJ.p, 0, jElems * sizeof(float), s));
-  MB2_CUDA(f->dResidual.resize(size_t(f->B) * f->ldJ));
-  MB2_CUDA(cudaMemsetAsync(f->dResidual.p, 0, size_t(f->B) * f->ldJ * sizeof(float), s));
   MB2_CUDA(f->dErrors.resize(f->B));
   MB2_CUDA(f->dTheta.resize(size_t(f->B) * f->ch->host.numParams));
   int rc = ensureTargets(f);
@@ -249,7 +256,6 @@ SweepArgs sweepArgs(mb2_solver_function* f, const float* theta, const int32_t* a
   a.targets = f->dTargets.p;
   a.cweights = f->dWeights.p;
   a.jacobian = f->dJ.p;
-  a.residual = f->dResidual.p;
   a.errors = f->dErrors.p;
   a.active = active;
   a.stateOut = nullptr;
@@ -323,20 +329,18 @@ __global__ void finalizeKernel(int batch, int n, float* theta, const float* thet
 
 int resolveJtjMode(const mb2_solver_function* f, int requested, int ns) {
   if (requested == MB2_JTJ_FP32_SIMT) return MB2_JTJ_FP32_SIMT;
-  const bool ok = jtjTensorSupported(ns, f->ldJ);
+  const bool ok = jtjTensorSupported(ns, f->plan.numCols, f->ldJ);
   if (requested == MB2_JTJ_AUTO) return ok ? MB2_JTJ_TF32X3 : MB2_JTJ_FP32_SIMT;
   return ok ? requested : -1;
 }
 
-int runJtJ(mb2_solver_function* f, int mode, const int32_t* cols, int ns, float* H, int ldH, const int32_t* active, cudaStream_t st) {
+int runJtJ(mb2_solver_function* f, int mode, int ns, float* H, int ldH, const int32_t* active, cudaStream_t st) {
   JtJArgs a{};
   a.batch = f->B;
   a.jacobian = f->dJ.p;
-  a.residual = f->dResidual.p;
-  a.numParams = f->ch->host.numParams;
+  a.numCols = f->plan.numCols;
   a.ldJ = f->ldJ;
   a.kRows = roundUp(std::max(f->plan.numRows, 1), 4);
-  a.cols = cols;
   a.ns = ns;
   a.H = H;
   a.ldH = ldH;
@@ -599,7 +603,7 @@ int mb2_solver_function_set_enabled_parameters(mb2_solver_function* f, const uin
 
 int mb2_solver_function_get_error(mb2_solver_function* f, const float* params, double* errors) {
   MB2_CHECK(f != nullptr && params && errors, "null argument");
-  int rc = ensurePlan(f);
+  int rc = ensurePlan(f, f->planCompact);
   if (rc != MB2_OK) return rc;
   const size_t n = f->ch->host.numParams;
   MB2_CUDA(cudaMemcpyAsync(f->dTheta.p, params, size_t(f->B) * n * sizeof(float), cudaMemcpyHostToDevice, f->stream));
@@ -611,18 +615,20 @@ int mb2_solver_function_get_error(mb2_solver_function* f, const float* params, d
 
 int mb2_solver_function_get_jacobian(mb2_solver_function* f, const float* params, float* jac, float* residual, double* errors, int32_t* actualRows) {
   MB2_CHECK(f != nullptr && params, "null argument");
-  int rc = ensurePlan(f);
+  int rc = ensurePlan(f, false);
   if (rc != MB2_OK) return rc;
   const size_t n = f->ch->host.numParams;
   const int rows = mb2_solver_function_jacobian_rows(f);
   MB2_CUDA(cudaMemcpyAsync(f->dTheta.p, params, size_t(f->B) * n * sizeof(float), cudaMemcpyHostToDevice, f->stream));
   MB2_CUDA(launchSweep(sweepArgs(f, f->dTheta.p, nullptr), true, f->stream));
-  if (jac && rows > 0)
-    MB2_CUDA(cudaMemcpy2DAsync(jac, size_t(rows) * sizeof(float), f->dJ.p, size_t(f->ldJ) * sizeof(float), size_t(rows) * sizeof(float),
-                               size_t(f->B) * n, cudaMemcpyDeviceToHost, f->stream));
-  if (residual && rows > 0)
-    MB2_CUDA(cudaMemcpy2DAsync(residual, size_t(rows) * sizeof(float), f->dResidual.p, size_t(f->ldJ) * sizeof(float), size_t(rows) * sizeof(float),
-                               f->B, cudaMemcpyDeviceToHost, f->stream));
+  for (int b = 0; b < f->B && rows > 0; ++b) { // parity/debug entry point: one strided copy per instance
+    const float* Jb = f->dJ.p + size_t(b) * (n + 1) * f->ldJ;
+    if (jac)
+      MB2_CUDA(cudaMemcpy2DAsync(jac + size_t(b) * n * rows, size_t(rows) * sizeof(float), Jb, size_t(f->ldJ) * sizeof(float), size_t(rows) * sizeof(float), n,
+                                 cudaMemcpyDeviceToHost, f->stream));
+    if (residual)
+      MB2_CUDA(cudaMemcpyAsync(residual + size_t(b) * rows, Jb + n * f->ldJ, size_t(rows) * sizeof(float), cudaMemcpyDeviceToHost, f->stream));
+  }
   if (errors) MB2_CUDA(cudaMemcpyAsync(errors, f->dErrors.p, size_t(f->B) * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
   MB2_CUDA(cudaStreamSynchronize(f->stream));
   if (actualRows) *actualRows = rows; // solver_function.cpp:50 actualRows = totalRows (padded)
@@ -631,34 +637,38 @@ int mb2_solver_function_get_jacobian(mb2_solver_function* f, const float* params
 
 int mb2_solver_function_get_jtjr(mb2_solver_function* f, const float* params, int32_t jtjMode, float* jtj, float* jtr, double* errors) {
   MB2_CHECK(f != nullptr && params, "null argument");
-  int rc = ensurePlan(f);
+  int rc = ensurePlan(f, false);
   if (rc != MB2_OK) return rc;
   const size_t n = f->ch->host.numParams;
   const int ap = f->plan.actualParameters;
   MB2_CHECK(ap > 0, "no enabled parameters");
   const int mode = resolveJtjMode(f, jtjMode, ap);
   if (mode < 0) return fail(MB2_ERR_UNSUPPORTED, "tensor-core JtJ does not support this shape");
-  const int ldH = ap | 1;
-  MB2_CUDA(f->dH.resize(size_t(f->B) * (ap + 1) * ldH));
+  const int ldH = (ap + 1) | 1;
+  const size_t hElems = size_t(f->B) * (ap + 1) * ldH;
+  MB2_CUDA(f->dH.resize(hElems));
   MB2_CUDA(cudaMemcpyAsync(f->dTheta.p, params, size_t(f->B) * n * sizeof(float), cudaMemcpyHostToDevice, f->stream));
   MB2_CUDA(launchSweep(sweepArgs(f, f->dTheta.p, nullptr), true, f->stream));
-  MB2_CUDA(cudaMemsetAsync(f->dH.p, 0, size_t(f->B) * (ap + 1) * ldH * sizeof(float), f->stream));
-  rc = runJtJ(f, mode, f->dIdentity.p, ap, f->dH.p, ldH, nullptr, f->stream);
+  MB2_CUDA(cudaMemsetAsync(f->dH.p, 0, hElems * sizeof(float), f->stream));
+  rc = runJtJ(f, mode, ap, f->dH.p, ldH, nullptr, f->stream);
   if (rc != MB2_OK) return rc;
-  for (int b = 0; b < f->B && (jtj || jtr); ++b) { // per-instance 2D copies (debug/parity entry point)
-    const float* Hb = f->dH.p + size_t(b) * (ap + 1) * ldH;
-    if (jtj) MB2_CUDA(cudaMemcpy2DAsync(jtj + size_t(b) * ap * ap, size_t(ap) * sizeof(float), Hb, size_t(ldH) * sizeof(float), size_t(ap) * sizeof(float), ap,
-                                        cudaMemcpyDeviceToHost, f->stream));
-    if (jtr) MB2_CUDA(cudaMemcpyAsync(jtr + size_t(b) * ap, Hb + size_t(ap) * ldH, size_t(ap) * sizeof(float), cudaMemcpyDeviceToHost, f->stream));
-  }
+  std::vector<float> h(hElems);
+  MB2_CUDA(cudaMemcpyAsync(h.data(), f->dH.p, hElems * sizeof(float), cudaMemcpyDeviceToHost, f->stream));
   if (errors) MB2_CUDA(cudaMemcpyAsync(errors, f->dErrors.p, size_t(f->B) * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
   MB2_CUDA(cudaStreamSynchronize(f->stream));
+  for (int b = 0; b < f->B; ++b) { // device layout is column-major lower [JtJ; Jtr]; the ABI returns row-major lower + Jtr
+    const float* Hb = h.data() + size_t(b) * (ap + 1) * ldH;
+    for (int j = 0; j < ap; ++j) {
+      if (jtj) for (int i = j; i < ap; ++i) jtj[(size_t(b) * ap + i) * ap + j] = Hb[size_t(j) * ldH + i];
+      if (jtr) jtr[size_t(b) * ap + j] = Hb[size_t(j) * ldH + ap];
+    }
+  }
   return MB2_OK;
 }
 
 int mb2_solver_function_get_skeleton_state(mb2_solver_function* f, const float* params, float* state) {
   MB2_CHECK(f != nullptr && params && state, "null argument");
-  int rc = ensurePlan(f);
+  int rc = ensurePlan(f, f->planCompact);
   if (rc != MB2_OK) return rc;
   const size_t n = f->ch->host.numParams;
   const size_t sz = size_t(f->B) * f->ch->host.numJoints * 8;
@@ -704,7 +714,7 @@ int mb2_solver_set_profiling(mb2_solver* s, int32_t enabled) {
 int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
   MB2_CHECK(s != nullptr && theta != nullptr, "null argument");
   mb2_solver_function* f = s->fn;
-  int rc = ensurePlan(f);
+  int rc = ensurePlan(f, true);
   if (rc != MB2_OK) return rc;
   cudaStream_t st = cudaStream ? (cudaStream_t)cudaStream : f->stream;
   const int B = f->B, n = f->ch->host.numParams;
@@ -715,7 +725,7 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
   MB2_CHECK(ns > 0, "no enabled parameters");
   const int mode = resolveJtjMode(f, o.jtj_mode, ns);
   if (mode < 0) return fail(MB2_ERR_UNSUPPORTED, "tensor-core JtJ does not support this shape");
-  const int ldH = ns | 1;
+  const int ldH = (ns + 1) | 1;
   MB2_CUDA(s->dH.resize(size_t(B) * (ns + 1) * ldH));
   MB2_CUDA(s->dDelta.resize(size_t(B) * ns));
   MB2_CUDA(s->dTheta0.resize(size_t(B) * n));
@@ -752,7 +762,7 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
     MB2_CUDA(launchSweep(sweepArgs(f, theta, s->dActive.p), true, st));
     recordPhaseStop(s, st);
     recordPhaseStart(s, 1, st);
-    rc = runJtJ(f, mode, f->dEnabledList.p, ns, s->dH.p, ldH, s->dActive.p, st);
+    rc = runJtJ(f, mode, ns, s->dH.p, ldH, s->dActive.p, st);
     if (rc != MB2_OK) return rc;
     recordPhaseStop(s, st);
     CholArgs c{};

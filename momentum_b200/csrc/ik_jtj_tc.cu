@@ -1,8 +1,369 @@
+// K2 on the 5th-generation tensor cores: per-instance [J r]^T [J r] (lower triangle) with
+// tcgen05.mma kind::tf32, fp32 accumulators in TMEM, operands staged global -> shared by TMA.
+//
+//   reference computation: jtj.selfadjointView<Lower>().rankUpdate(J^T); jtr += J^T r
+//   (momentum/solver/solver_function.cpp:113-116, gauss_newton_solver.cpp:215-216)
+//
+// Data layout. The device Jacobian of an instance is R = numCols + 1 "column vectors" of ldJ floats
+// (column c of J at J + c*ldJ, the residual r as vector numCols): a K-major [R x K] operand, which is
+// exactly what both UMMA operands want for D = X X^T with X = [J r]^T. D's last row is J^T r, so Jtr
+// costs nothing extra. One TMA box (boxRows x 32 floats, SWIZZLE_128B) per 32-row K block lands the
+// whole K slab of an instance; out-of-range rows are zero-filled by TMA.
+//
+// Precision. kind::tf32 keeps 10 mantissa bits, so a single pass gives ~1e-3 relative error, which
+// would change the Gauss-Newton path of the under-determined IK problems (m < n). The default is the
+// 3xTF32 split: x = hi + lo with hi = tf32(x), lo = tf32(x - hi); D += hi*hi + hi*lo + lo*hi. A group of
+// converter warps derives hi (in place) and lo (second buffer, same swizzled positions) from the raw
+// fp32 slab that TMA delivered.
+//
+// Roles in one persistent CTA (1 CTA / SM, 320 threads):
+//   warp 0        TMA producer (one elected lane)
+//   warp 1        TMEM allocator + MMA issuer (one elected lane)
+//   warps 2..5    hi/lo converters
+//   warps 6..9    epilogue: TMEM -> registers -> global (column-major lower H, coalesced along rows)
+// Pipelines: smem ring full -> converted -> (MMA) -> empty; TMEM full/empty between MMA and epilogue.
 #include "ik_jtj_tc.cuh"
+
+#include <cuda.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <mutex>
+#include <tuple>
 
 namespace mb2 {
 
-bool jtjTensorSupported(int, int) { return false; }
-cudaError_t launchJtJTensor(const JtJArgs&, int, cudaStream_t) { return cudaErrorNotSupported; }
+namespace {
+
+constexpr int kTcThreads = 320;
+constexpr int kKBlock = 32;         // floats per K block = one 128-byte swizzle row
+constexpr int kRowBytes = 128;
+constexpr int kUmmaK = 8;           // tf32: 32 bytes of K per instruction
+constexpr uint64_t kSpinLimit = 4000000000ull; // cycles before a stuck barrier traps instead of hanging the box
+
+struct TcParams {
+  int batch;
+  int ns, numCols, ldJ, kBlocks;
+  float* H;
+  int ldH;
+  const int32_t* active;
+  int passes;     // 3 or 1
+  int mTiles;     // 1 or 2
+  int boxRows;    // 128 or 256
+  int n0, n1;     // UMMA N of tile 0 / tile 1 (multiples of 16)
+  int tmemCols;   // power of two >= n0 + n1
+  int stages;
+};
+
+__device__ __forceinline__ uint32_t smemAddr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbarInit(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarArrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if ((uint64_t)(clock64() - t0) > kSpinLimit) {
+      printf("momentum_b200: JtJ tensor kernel barrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tmaLoad3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void ummaTf32(uint32_t tmemD, uint64_t descA, uint64_t descB, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmemD),
+      "l"(descA), "l"(descB), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void ummaCommit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tcFenceBefore() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcFenceAfter() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ uint32_t toTf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void tmemLoad16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) (8 rows * 128 B)
+// | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64)
+__device__ __forceinline__ uint64_t makeSmemDesc(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// cute::UMMA::InstrDescriptor: c_format F32 (1) [4,6) | a_format TF32 (2) [7,10) | b_format TF32 (2) [10,13)
+// | a_major K (0) [15] | b_major K (0) [16] | N>>3 [17,23) | M>>4 [24,29)
+__device__ __forceinline__ uint32_t makeInstrDesc(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smemRaw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t base = (smemAddr(smemRaw) + 1023u) & ~1023u;
+  const uint32_t slabBytes = (uint32_t)p.boxRows * kRowBytes;          // one K block of all rows
+  const uint32_t stageBytes = slabBytes * (p.passes == 3 ? 2u : 1u);   // hi [+ lo]
+  const uint32_t barBase = base + stageBytes * p.stages;
+  auto fullBar = [&](int s) { return barBase + 8u * s; };
+  auto convBar = [&](int s) { return barBase + 8u * (p.stages + s); };
+  auto emptyBar = [&](int s) { return barBase + 8u * (2 * p.stages + s); };
+  const uint32_t tmemFullBar = barBase + 8u * (3 * p.stages);
+  const uint32_t tmemEmptyBar = tmemFullBar + 8u;
+  const uint32_t tmemSlot = tmemEmptyBar + 8u;
+  uint8_t* gen = smemRaw + (base - smemAddr(smemRaw)); // generic pointer to the aligned base
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbarInit(fullBar(s), 1); mbarInit(convBar(s), 128); mbarInit(emptyBar(s), 1); }
+    mbarInit(tmemFullBar, 1);
+    mbarInit(tmemEmptyBar, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmemSlot), "r"((uint32_t)p.tmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcFenceBefore();
+  __syncthreads();
+  tcFenceAfter();
+  const uint32_t tmemBase = *reinterpret_cast<volatile uint32_t*>(gen + (tmemSlot - base));
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
+        if (p.active != nullptr && p.active[b] == 0) continue;
+        for (int kb = 0; kb < p.kBlocks; ++kb) {
+          mbarWait(emptyBar(s), ph ^ 1u);
+          mbarExpectTx(fullBar(s), slabBytes);
+          tmaLoad3d(base + stageBytes * s, &tmap, kb * kKBlock, 0, b, fullBar(s));
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0, tph = 0;
+      const uint32_t idesc0 = makeInstrDesc(128, p.n0), idesc1 = makeInstrDesc(128, p.n1);
+      for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
+        if (p.active != nullptr && p.active[b] == 0) continue;
+        mbarWait(tmemEmptyBar, tph ^ 1u); // epilogue has drained the previous instance's accumulators
+        tcFenceAfter();
+        for (int kb = 0; kb < p.kBlocks; ++kb) {
+          mbarWait(convBar(s), ph);
+          tcFenceAfter();
+          const uint32_t hi = base + stageBytes * s, lo = hi + slabBytes;
+          for (int t = 0; t < p.mTiles; ++t) {
+            const uint32_t dcol = tmemBase + (t == 0 ? 0u : (uint32_t)p.n0);
+            const uint32_t idesc = t == 0 ? idesc0 : idesc1;
+            const uint32_t aOff = (uint32_t)t * 128u * kRowBytes;
+            for (int pass = 0; pass < p.passes; ++pass) {
+              const uint32_t aBase = (pass == 2 ? lo : hi) + aOff; // hi*hi, hi*lo, lo*hi
+              const uint32_t bBase = (pass == 1 ? lo : hi);
+#pragma unroll
+              for (int k4 = 0; k4 < kKBlock / kUmmaK; ++k4) {
+                const uint32_t acc = (kb == 0 && pass == 0 && k4 == 0) ? 0u : 1u;
+                ummaTf32(dcol, makeSmemDesc(aBase + k4 * 32u), makeSmemDesc(bBase + k4 * 32u), idesc, acc);
+              }
+            }
+          }
+          ummaCommit(emptyBar(s)); // smem slab reusable once these MMAs have read it
+          if (kb == p.kBlocks - 1) ummaCommit(tmemFullBar);
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
+        }
+        tph ^= 1u;
+      }
+    }
+  } else if (warp < 6) {
+    // ---------------- converters: raw fp32 -> tf32 hi (in place) and lo ----------------
+    const int ct = threadIdx.x - 64; // 0..127
+    int s = 0;
+    uint32_t ph = 0;
+    const int vecs = (int)(slabBytes / 16u);
+    for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
+      if (p.active != nullptr && p.active[b] == 0) continue;
+      for (int kb = 0; kb < p.kBlocks; ++kb) {
+        mbarWait(fullBar(s), ph);
+        float4* hi = reinterpret_cast<float4*>(gen + stageBytes * s);
+        float4* lo = reinterpret_cast<float4*>(gen + stageBytes * s + slabBytes);
+        for (int i = ct; i < vecs; i += 128) {
+          const float4 x = hi[i];
+          uint4 h;
+          h.x = toTf32(x.x); h.y = toTf32(x.y); h.z = toTf32(x.z); h.w = toTf32(x.w);
+          reinterpret_cast<uint4*>(hi)[i] = h;
+          if (p.passes == 3) {
+            uint4 l;
+            l.x = toTf32(x.x - __uint_as_float(h.x)); l.y = toTf32(x.y - __uint_as_float(h.y));
+            l.z = toTf32(x.z - __uint_as_float(h.z)); l.w = toTf32(x.w - __uint_as_float(h.w));
+            reinterpret_cast<uint4*>(lo)[i] = l;
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy stores -> visible to the tensor core (async proxy)
+        mbarArrive(convBar(s));
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    // ---------------- epilogue: TMEM -> global, column-major lower triangle of [JtJ; Jtr] ----------------
+    const int q = warp & 3; // TMEM lane quarter this warp may access
+    uint32_t eph = 0;
+    for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
+      if (p.active != nullptr && p.active[b] == 0) continue;
+      float* H = p.H + (size_t)b * (p.ns + 1) * p.ldH;
+      mbarWait(tmemFullBar, eph);
+      tcFenceAfter();
+      for (int t = 0; t < p.mTiles; ++t) {
+        const int row = t * 128 + q * 32 + lane;                 // row of [J r]^T [J r]
+        const int i = row < p.ns ? row : (row == p.numCols ? p.ns : -1); // index in the (ns+1) system; -1: not wanted
+        const int maxI = __reduce_max_sync(0xffffffffu, i);
+        const int nT = t == 0 ? p.n0 : p.n1;
+        const uint32_t colBase = tmemBase + ((uint32_t)(q * 32) << 16) + (t == 0 ? 0u : (uint32_t)p.n0);
+        for (int c0 = 0; c0 < nT; c0 += 16) {
+          if (c0 > maxI || c0 >= p.ns) break; // warp-uniform: the rest lies above the diagonal / outside the system
+          float v[16];
+          tmemLoad16(colBase + (uint32_t)c0, v);
+#pragma unroll
+          for (int cc = 0; cc < 16; ++cc) {
+            const int c = c0 + cc;
+            if (c < p.ns && c <= i) H[(size_t)c * p.ldH + i] = v[cc];
+          }
+        }
+      }
+      tcFenceBefore();
+      mbarArrive(tmemEmptyBar);
+      eph ^= 1u;
+    }
+  }
+  tcFenceBefore();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"((uint32_t)p.tmemCols) : "memory");
+  }
+}
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encodeTiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int roundUpI(int v, int m) { return (v + m - 1) / m * m; }
+
+struct Shape {
+  int rows, mTiles, boxRows, n0, n1, tmemCols;
+};
+Shape shapeFor(int numCols) {
+  Shape s{};
+  s.rows = numCols + 1;
+  s.mTiles = s.rows > 128 ? 2 : 1;
+  s.boxRows = s.mTiles * 128;
+  const int r16 = roundUpI(s.rows, 16);
+  s.n0 = r16 < 128 ? r16 : 128;
+  s.n1 = s.mTiles == 2 ? r16 : 0;
+  int need = s.n0 + s.n1, c = 32;
+  while (c < need) c <<= 1;
+  s.tmemCols = c;
+  return s;
+}
+
+} // namespace
+
+bool jtjTensorSupported(int ns, int numCols, int ldJ) {
+  if (encodeTiled() == nullptr) return false;
+  return ns >= 1 && ns <= numCols && numCols + 1 <= 256 && (ldJ % kKBlock) == 0;
+}
+
+cudaError_t launchJtJTensor(const JtJArgs& a, int passes, cudaStream_t stream) {
+  if (!jtjTensorSupported(a.ns, a.numCols, a.ldJ)) return cudaErrorNotSupported;
+  const Shape sh = shapeFor(a.numCols);
+  // TMA descriptor over the device Jacobian [batch][numCols + 1][ldJ] (innermost first)
+  CUtensorMap map;
+  const cuuint64_t dims[3] = {(cuuint64_t)a.ldJ, (cuuint64_t)(a.numCols + 1), (cuuint64_t)a.batch};
+  const cuuint64_t strides[2] = {(cuuint64_t)a.ldJ * sizeof(float), (cuuint64_t)(a.numCols + 1) * a.ldJ * sizeof(float)};
+  const cuuint32_t box[3] = {(cuuint32_t)kKBlock, (cuuint32_t)sh.boxRows, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  const CUresult r = encodeTiled()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(a.jacobian), dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+  TcParams p{};
+  p.batch = a.batch;
+  p.ns = a.ns;
+  p.numCols = a.numCols;
+  p.ldJ = a.ldJ;
+  p.kBlocks = (a.kRows + kKBlock - 1) / kKBlock;
+  p.H = a.H;
+  p.ldH = a.ldH;
+  p.active = a.active;
+  p.passes = passes == 3 ? 3 : 1;
+  p.mTiles = sh.mTiles;
+  p.boxRows = sh.boxRows;
+  p.n0 = sh.n0;
+  p.n1 = sh.n1;
+  p.tmemCols = sh.tmemCols;
+  const size_t stageBytes = size_t(sh.boxRows) * kRowBytes * (p.passes == 3 ? 2 : 1);
+  int stages = int((200 * 1024) / stageBytes);
+  if (stages > 6) stages = 6;
+  if (stages < 2) return cudaErrorInvalidConfiguration;
+  p.stages = stages;
+  const size_t smem = stageBytes * stages + 1024 /*alignment slack*/ + 8 * (3 * stages + 2) + 16;
+  cudaError_t e = cudaFuncSetAttribute(jtjTensorKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (e != cudaSuccess) return e;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = a.batch < sms ? a.batch : sms;
+  jtjTensorKernel<<<grid, kTcThreads, smem, stream>>>(map, p);
+  return cudaGetLastError();
+}
 
 } // namespace mb2

@@ -63,14 +63,13 @@ __global__ void __launch_bounds__(256) sweepKernel(const SweepArgs a) {
     }
     const float* targets = a.targets + size_t(b) * T.targetStride;
     const float* cw = a.cweights + (T.weightsPerInstance ? size_t(b) * T.numWeights : 0);
-    float* residual = kJacobian ? a.residual + size_t(b) * T.ldJ : nullptr;
+    float* J = kJacobian ? a.jacobian + size_t(b) * (T.numCols + 1) * T.ldJ : nullptr;
+    float* residual = kJacobian ? J + size_t(T.numCols) * T.ldJ : nullptr; // the residual is the last column of the device matrix
     double err = 0.0;
     for (int u = lane; u < T.numUnits; u += 32) err += (double)evalUnit<kJacobian>(T, u, th, jp, js, targets, cw, rec, residual);
     __syncwarp();
-    if (kJacobian) {
-      float* J = a.jacobian + size_t(b) * T.numParams * T.ldJ;
+    if (kJacobian)
       for (int c = lane; c < T.numCells; c += 32) jacobianCell(T, c, js, rec, targets, J);
-    }
     err = warpSum(err);
     // getError() rounds through float (skeleton_solver_function.cpp:82); the Jacobian pass keeps double
     if (lane == 0) a.errors[b] = kJacobian ? err : (double)(float)err;
@@ -118,8 +117,8 @@ __global__ void __launch_bounds__(256) jtjSimtKernel(const JtJArgs a) {
   __shared__ float As[kJtjTile][kJtjKc + 1];
   __shared__ float Bs[kJtjTile][kJtjKc + 1];
   __shared__ float rs[kJtjKc];
-  const float* J = a.jacobian + size_t(b) * a.numParams * a.ldJ;
-  const float* r = a.residual + size_t(b) * a.ldJ;
+  const float* J = a.jacobian + size_t(b) * (a.numCols + 1) * a.ldJ;
+  const float* r = J + size_t(a.numCols) * a.ldJ;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   float acc[4][4];
 #pragma unroll
@@ -134,8 +133,8 @@ __global__ void __launch_bounds__(256) jtjSimtKernel(const JtJArgs a) {
       const int c = idx / kJtjKc, kk = idx % kJtjKc;
       const int ia = ti * kJtjTile + c, ib = tj * kJtjTile + c;
       const int k = k0 + kk;
-      As[c][kk] = (ia < a.ns && k < a.kRows) ? J[size_t(a.cols[ia]) * a.ldJ + k] : 0.f;
-      Bs[c][kk] = (ib < a.ns && k < a.kRows) ? J[size_t(a.cols[ib]) * a.ldJ + k] : 0.f;
+      As[c][kk] = (ia < a.ns && k < a.kRows) ? J[size_t(ia) * a.ldJ + k] : 0.f;
+      Bs[c][kk] = (ib < a.ns && k < a.kRows) ? J[size_t(ib) * a.ldJ + k] : 0.f;
     }
     if (threadIdx.x < kJtjKc) rs[threadIdx.x] = (k0 + threadIdx.x < a.kRows) ? r[k0 + threadIdx.x] : 0.f;
     __syncthreads();
@@ -161,11 +160,11 @@ __global__ void __launch_bounds__(256) jtjSimtKernel(const JtJArgs a) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int gi = ti * kJtjTile + ty * 4 + i, gj = tj * kJtjTile + tx * 4 + j;
-      if (gi < a.ns && gj <= gi) H[size_t(gi) * a.ldH + gj] = acc[i][j];
+      if (gi < a.ns && gj <= gi) H[size_t(gj) * a.ldH + gi] = acc[i][j];
     }
   if (diag && threadIdx.x < kJtjTile) {
     const int gi = ti * kJtjTile + threadIdx.x;
-    if (gi < a.ns) H[size_t(a.ns) * a.ldH + gi] = gacc;
+    if (gi < a.ns) H[size_t(gi) * a.ldH + a.ns] = gacc;
   }
 }
 
@@ -199,24 +198,31 @@ __global__ void __launch_bounds__(kCholThreads) choleskyKernel(const CholArgs a,
   if (useSmemMatrix) {
     ctx.lda = n | 1;
     ctx.A = As;
+    // source is column-major (coalesced along i); smem target is row-major with odd stride
     for (int idx = tid; idx < (n + 1) * n; idx += kCholThreads) {
-      const int i = idx / n, j = idx - i * n;
-      if (j <= i || i == n) {
-        float v = Hg[size_t(i) * a.ldH + j];
+      const int j = idx / (n + 1), i = idx - j * (n + 1);
+      if (i >= j) {
+        float v = Hg[size_t(j) * a.ldH + i];
         if (i == j) v += a.regularization; // gauss_newton_solver.cpp:248
         As[i * ctx.lda + j] = v;
       }
     }
   } else {
+    // matrix too large for shared memory: factor in place in global memory (L2-resident). K2 wrote the lower
+    // triangle column-major (element (i,j) at [j*ldH + i]); mirror it so that A(i,j) = Hg[i*ldH + j] reads row-major.
     ctx.lda = a.ldH;
     ctx.A = Hg;
+    for (int idx = tid; idx < (n + 1) * n; idx += kCholThreads) {
+      const int j = idx / (n + 1), i = idx - j * (n + 1);
+      if (i > j) Hg[size_t(i) * a.ldH + j] = Hg[size_t(j) * a.ldH + i];
+    }
     for (int i = tid; i < n; i += kCholThreads) Hg[size_t(i) * a.ldH + i] += a.regularization;
   }
   ctx.P = P;
   ctx.ldp = ldp;
   ctx.fail = flags;
   if (tid == 0) flags[0] = 0;
-  for (int i = tid; i < n; i += kCholThreads) gsave[i] = Hg[size_t(n) * a.ldH + i];
+  for (int i = tid; i < n; i += kCholThreads) gsave[i] = Hg[size_t(i) * a.ldH + n];
   __syncthreads();
 
   const int blockSize = cholBlockSize(n, NB);

@@ -14,8 +14,7 @@ struct SweepArgs {           // K1 (FK + residual + Jacobian) and K4 (FK + error
   int32_t ldTheta;
   const float* targets;      // [B][T.targetStride]
   const float* cweights;     // [numWeights] or [B][numWeights]
-  float* jacobian;           // [B][numParams][ldJ] (K1 only)
-  float* residual;           // [B][ldJ] (K1 only)
+  float* jacobian;           // [B][numCols + 1][ldJ] (K1 only); column numCols is the residual vector
   double* errors;            // [B]
   const int32_t* active;     // optional per-instance mask
   float* stateOut;           // optional [B][J][8]
@@ -23,19 +22,18 @@ struct SweepArgs {           // K1 (FK + residual + Jacobian) and K4 (FK + error
 
 struct JtJArgs {             // K2
   int32_t batch;
-  const float* jacobian;     // [B][numParams][ldJ]
-  const float* residual;     // [B][ldJ]
-  int32_t numParams, ldJ, kRows; // kRows = contraction length (rows rounded up to 4)
-  const int32_t* cols;       // [ns] column index list (enabled parameters, or identity up to actualParameters)
-  int32_t ns;
-  float* H;                  // [B][ns+1][ldH]; rows 0..ns-1 lower triangle of JtJ, row ns = Jtr
-  int32_t ldH;
+  const float* jacobian;     // [B][numCols + 1][ldJ]; column numCols = residual
+  int32_t numCols, ldJ, kRows; // kRows = contraction length (rows rounded up to 4)
+  int32_t ns;                // leading ns columns enter the normal equations (ns <= numCols)
+  float* H;                  // [B][ns+1][ldH] column-major lower triangle of [JtJ, Jtr]: element (i,j), i>=j, at H[j*ldH + i];
+                             // row index ns holds Jtr (H[j*ldH + ns] = (J^T r)_j)
+  int32_t ldH;               // >= ns + 1
   const int32_t* active;
 };
 
 struct CholArgs {            // K3: damped Cholesky + solve + update + SolverT bookkeeping
   int32_t batch;
-  float* H;                  // [B][ns+1][ldH] (overwritten)
+  float* H;                  // [B][ns+1][ldH] column-major lower [JtJ; Jtr] (as written by K2)
   int32_t ns, ldH;
   float regularization;
   const int32_t* cols;       // [ns] subset -> full parameter index

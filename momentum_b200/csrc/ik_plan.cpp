@@ -107,20 +107,25 @@ struct CellBuilder {
 };
 } // namespace
 
-std::string buildPlan(const HostCharacter& ch, const std::vector<HostErrorFunction>& efs, const std::vector<uint8_t>& enabled, Plan& out) {
+std::string buildPlan(const HostCharacter& ch, const std::vector<HostErrorFunction>& efs, const std::vector<uint8_t>& enabled, bool compact, Plan& out) {
   out = Plan();
+  out.compact = compact;
   const int n = ch.numParams;
   if (int(enabled.size()) != n) return "enabled parameter set size mismatch";
   for (int i = 0; i < n; ++i)
     if (enabled[i]) { out.actualParameters = i + 1; out.enabledList.push_back(i); }
   const std::vector<uint8_t> active = ch.computeActiveJointParams(enabled);
+  std::vector<int> colMap(n, -1); // model parameter -> device column
+  if (compact) { for (size_t a = 0; a < out.enabledList.size(); ++a) colMap[out.enabledList[a]] = int(a); out.numCols = int(out.enabledList.size()); }
+  else { for (int i = 0; i < n; ++i) colMap[i] = i; out.numCols = n; }
 
   int row = 0, rec = 0;
   auto flushCells = [&](int unitIndex, CellBuilder& cb) {
     for (auto& kv : cb.m) {
+      if (colMap[kv.first] < 0) continue; // column of a disabled parameter: not held on the device
       CellDesc c{};
       c.unit = uint16_t(unitIndex);
-      c.col = uint16_t(kv.first);
+      c.col = uint16_t(colMap[kv.first]);
       c.contribBegin = uint32_t(out.contribs.size());
       c.contribCount = uint16_t(kv.second.size());
       c.coef = 0.f;
@@ -129,9 +134,10 @@ std::string buildPlan(const HostCharacter& ch, const std::vector<HostErrorFuncti
     }
   };
   auto staticCell = [&](int unitIndex, int col, float coef) {
+    if (colMap[col] < 0) return;
     CellDesc c{};
     c.unit = uint16_t(unitIndex);
-    c.col = uint16_t(col);
+    c.col = uint16_t(colMap[col]);
     c.contribBegin = 0;
     c.contribCount = 0;
     c.coef = coef;

@@ -68,7 +68,7 @@ struct UnitDesc {
 // One Jacobian cell: rows [unit.row0, +numRows) x column `col`
 struct CellDesc {
   uint16_t unit;
-  uint16_t col;           // model parameter index (column of J)
+  uint16_t col;           // device column of J (model parameter index, or its rank in the enabled list when compacted)
   uint32_t contribBegin;  // into ContribDesc table
   uint16_t contribCount;  // 0 for limit cells that only scale by coef
   uint16_t pad;
@@ -106,7 +106,9 @@ struct FunctionTables {
   int32_t targetStride; // floats per instance
   int32_t recStride;    // floats per instance of evaluation records
   int32_t numRows;      // active residual rows m (unpadded)
-  int32_t ldJ;          // row stride of a Jacobian column (m padded)
+  int32_t ldJ;          // row stride of a Jacobian column (m padded to 32)
+  int32_t numCols;      // Jacobian columns held on the device (all n, or only the enabled ones when compacted);
+                        // the device matrix has numCols + 1 columns: the last one is the residual vector
   int32_t weightsPerInstance; // 0: cweights [numWeights] shared, 1: [B][numWeights]
   int32_t numWeights;
 };

@@ -33,7 +33,8 @@ struct mb2_solver_function {
   std::vector<float> weights, targets;
   Plan plan;
   int ldJ{32};
-  std::vector<float> J, residual;
+  std::vector<float> J;
+  bool planCompact{false};
   std::vector<double> errors;
 };
 struct mb2_solver {
@@ -46,12 +47,12 @@ struct mb2_solver {
 
 static int roundUp(int v, int m) { return (v + m - 1) / m * m; }
 
-static std::string plan(mb2_solver_function* f) {
-  std::string e = buildPlan(f->ch->host, f->efs, f->enabled, f->plan);
+static std::string plan(mb2_solver_function* f, bool compact) {
+  std::string e = buildPlan(f->ch->host, f->efs, f->enabled, compact, f->plan);
   if (!e.empty()) return e;
+  f->planCompact = compact;
   f->ldJ = std::max(32, roundUp(f->plan.numRows, 32));
-  f->J.assign(size_t(f->B) * f->ch->host.numParams * f->ldJ, 0.f);
-  f->residual.assign(size_t(f->B) * f->ldJ, 0.f);
+  f->J.assign(size_t(f->B) * (f->plan.numCols + 1) * f->ldJ, 0.f);
   f->errors.assign(f->B, 0.0);
   f->targets.resize(size_t(f->B) * std::max(f->targetStride, 1), 0.f);
   if (f->weights.empty()) f->weights.push_back(0.f);
@@ -68,7 +69,7 @@ static FunctionTables tables(const mb2_solver_function* f) {
   T.numEf = int(f->plan.efs.size()); T.numUnits = int(f->plan.units.size()); T.numCells = int(f->plan.cells.size());
   T.efs = f->plan.efs.data(); T.units = f->plan.units.data(); T.cells = f->plan.cells.data(); T.contribs = f->plan.contribs.data();
   T.limitData = f->plan.limitData.data();
-  T.targetStride = f->targetStride; T.recStride = f->plan.recStride; T.numRows = f->plan.numRows; T.ldJ = f->ldJ;
+  T.targetStride = f->targetStride; T.recStride = f->plan.recStride; T.numRows = f->plan.numRows; T.ldJ = f->ldJ; T.numCols = f->plan.numCols;
   T.weightsPerInstance = f->weightsPerInstance; T.numWeights = f->numWeights;
   return T;
 }
@@ -84,7 +85,8 @@ static void sweepOne(mb2_solver_function* f, const FunctionTables& T, int b, con
     for (int i = 0; i < T.numJoints * 8; ++i) stateOut[i] = js[(i >> 3) * kJointStateStride + (i & 7)];
   const float* tg = f->targets.data() + size_t(b) * T.targetStride;
   const float* cw = f->weights.data() + (T.weightsPerInstance ? size_t(b) * T.numWeights : 0);
-  float* res = kJacobian ? f->residual.data() + size_t(b) * T.ldJ : nullptr;
+  float* Jb = f->J.data() + size_t(b) * (T.numCols + 1) * T.ldJ;
+  float* res = kJacobian ? Jb + size_t(T.numCols) * T.ldJ : nullptr;
   // lanes accumulate in double, then a butterfly reduction: emulate the same association
   double lane[32];
   for (int l = 0; l < 32; ++l) lane[l] = 0.0;
@@ -94,27 +96,25 @@ static void sweepOne(mb2_solver_function* f, const FunctionTables& T, int b, con
     for (int l = 0; l < 32; ++l) t[l] = lane[l] + lane[l ^ o];
     for (int l = 0; l < 32; ++l) lane[l] = t[l];
   }
-  if (kJacobian) {
-    float* J = f->J.data() + size_t(b) * T.numParams * T.ldJ;
-    for (int c = 0; c < T.numCells; ++c) jacobianCell(T, c, js.data(), rec.data(), tg, J);
-  }
+  if (kJacobian)
+    for (int c = 0; c < T.numCells; ++c) jacobianCell(T, c, js.data(), rec.data(), tg, Jb);
   *errOut = kJacobian ? lane[0] : (double)(float)lane[0];
 }
 
-static void jtjOne(const mb2_solver_function* f, int b, const int32_t* cols, int ns, float* H, int ldH) {
-  const int n = f->ch->host.numParams;
-  const float* J = f->J.data() + size_t(b) * n * f->ldJ;
-  const float* r = f->residual.data() + size_t(b) * f->ldJ;
+static void jtjOne(const mb2_solver_function* f, int b, int ns, float* H, int ldH) {
+  const int nc = f->plan.numCols;
+  const float* J = f->J.data() + size_t(b) * (nc + 1) * f->ldJ;
+  const float* r = J + size_t(nc) * f->ldJ;
   const int K = roundUp(std::max(f->plan.numRows, 1), 4);
   for (int i = 0; i < ns; ++i) {
     for (int j = 0; j <= i; ++j) {
       float s = 0.f;
-      for (int k = 0; k < K; ++k) s = fmaf(J[size_t(cols[i]) * f->ldJ + k], J[size_t(cols[j]) * f->ldJ + k], s);
-      H[size_t(i) * ldH + j] = s;
+      for (int k = 0; k < K; ++k) s = fmaf(J[size_t(i) * f->ldJ + k], J[size_t(j) * f->ldJ + k], s);
+      H[size_t(j) * ldH + i] = s; // column-major lower
     }
     float g = 0.f;
-    for (int k = 0; k < K; ++k) g = fmaf(J[size_t(cols[i]) * f->ldJ + k], r[k], g);
-    H[size_t(ns) * ldH + i] = g;
+    for (int k = 0; k < K; ++k) g = fmaf(J[size_t(i) * f->ldJ + k], r[k], g);
+    H[size_t(i) * ldH + ns] = g;
   }
 }
 
@@ -127,8 +127,8 @@ static int cholOne(float* Hg, int n, int ldH, float reg, float* delta, float* gd
   std::vector<float> P(size_t(NB) * ldp, 0.f), gsave(n);
   for (int i = 0; i <= n; ++i)
     for (int j = 0; j < n; ++j)
-      if (j <= i || i == n) A[size_t(i) * lda + j] = Hg[size_t(i) * ldH + j] + ((i == j) ? reg : 0.f);
-  for (int i = 0; i < n; ++i) gsave[i] = Hg[size_t(n) * ldH + i];
+      if (j <= i) A[size_t(i) * lda + j] = Hg[size_t(j) * ldH + i] + ((i == j) ? reg : 0.f);
+  for (int i = 0; i < n; ++i) gsave[i] = Hg[size_t(i) * ldH + n];
   int flag = 0;
   CholCtx ctx{A.data(), lda, n, P.data(), ldp, &flag};
   const int blockSize = cholBlockSize(n, NB);
@@ -309,14 +309,14 @@ int mb2_solver_function_set_enabled_parameters(mb2_solver_function* f, const uin
 }
 
 int mb2_solver_function_get_error(mb2_solver_function* f, const float* params, double* errors) {
-  const std::string e = plan(f);
+  const std::string e = plan(f, f->planCompact);
   if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
   const FunctionTables T = tables(f);
   for (int b = 0; b < f->B; ++b) sweepOne<false>(f, T, b, params + size_t(b) * T.numParams, &errors[b], nullptr);
   return MB2_OK;
 }
 int mb2_solver_function_get_skeleton_state(mb2_solver_function* f, const float* params, float* state) {
-  const std::string e = plan(f);
+  const std::string e = plan(f, f->planCompact);
   if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
   const FunctionTables T = tables(f);
   double err;
@@ -324,7 +324,7 @@ int mb2_solver_function_get_skeleton_state(mb2_solver_function* f, const float* 
   return MB2_OK;
 }
 int mb2_solver_function_get_jacobian(mb2_solver_function* f, const float* params, float* jac, float* residual, double* errors, int32_t* actualRows) {
-  const std::string e = plan(f);
+  const std::string e = plan(f, false);
   if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
   const FunctionTables T = tables(f);
   const int rows = mb2_solver_function_jacobian_rows(f), n = T.numParams;
@@ -332,29 +332,27 @@ int mb2_solver_function_get_jacobian(mb2_solver_function* f, const float* params
     double err;
     sweepOne<true>(f, T, b, params + size_t(b) * n, &err, nullptr);
     if (errors) errors[b] = err;
-    for (int c = 0; c < n && jac; ++c) std::memcpy(jac + (size_t(b) * n + c) * rows, f->J.data() + (size_t(b) * n + c) * f->ldJ, size_t(rows) * sizeof(float));
-    if (residual) std::memcpy(residual + size_t(b) * rows, f->residual.data() + size_t(b) * f->ldJ, size_t(rows) * sizeof(float));
+    for (int c = 0; c < n && jac; ++c) std::memcpy(jac + (size_t(b) * n + c) * rows, f->J.data() + (size_t(b) * (n + 1) + c) * f->ldJ, size_t(rows) * sizeof(float));
+    if (residual) std::memcpy(residual + size_t(b) * rows, f->J.data() + (size_t(b) * (n + 1) + n) * f->ldJ, size_t(rows) * sizeof(float));
   }
   if (actualRows) *actualRows = rows;
   return MB2_OK;
 }
 int mb2_solver_function_get_jtjr(mb2_solver_function* f, const float* params, int32_t, float* jtj, float* jtr, double* errors) {
-  const std::string e = plan(f);
+  const std::string e = plan(f, false);
   if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
   const FunctionTables T = tables(f);
-  const int ap = f->plan.actualParameters, n = T.numParams, ldH = ap | 1;
-  std::vector<int32_t> ident(n);
-  for (int i = 0; i < n; ++i) ident[i] = i;
+  const int ap = f->plan.actualParameters, n = T.numParams, ldH = (ap + 1) | 1;
   std::vector<float> H(size_t(ap + 1) * ldH);
   for (int b = 0; b < f->B; ++b) {
     double err;
     sweepOne<true>(f, T, b, params + size_t(b) * n, &err, nullptr);
     if (errors) errors[b] = err;
     std::fill(H.begin(), H.end(), 0.f);
-    jtjOne(f, b, ident.data(), ap, H.data(), ldH);
-    for (int i = 0; i < ap; ++i) {
-      if (jtj) std::memcpy(jtj + (size_t(b) * ap + i) * ap, H.data() + size_t(i) * ldH, size_t(ap) * sizeof(float));
-      if (jtr) jtr[size_t(b) * ap + i] = H[size_t(ap) * ldH + i];
+    jtjOne(f, b, ap, H.data(), ldH);
+    for (int j = 0; j < ap; ++j) {
+      if (jtj) for (int i = j; i < ap; ++i) jtj[(size_t(b) * ap + i) * ap + j] = H[size_t(j) * ldH + i];
+      if (jtr) jtr[size_t(b) * ap + j] = H[size_t(j) * ldH + ap];
     }
   }
   return MB2_OK;
@@ -374,10 +372,10 @@ int mb2_solver_set_enabled_parameters(mb2_solver* s, const uint64_t* bits) { ret
 // emulation of mb2_solver_solve_device's launch sequence, instance by instance
 int mb2_solver_solve(mb2_solver* s, float* params, double* errors, int32_t* iterations, int32_t* status) {
   mb2_solver_function* f = s->fn;
-  const std::string e = plan(f);
+  const std::string e = plan(f, true);
   if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
   const FunctionTables T = tables(f);
-  const int n = T.numParams, ns = int(f->plan.enabledList.size()), ldH = ns | 1;
+  const int n = T.numParams, ns = int(f->plan.enabledList.size()), ldH = (ns + 1) | 1;
   const auto& o = s->opt;
   const int maxIt = int(o.max_iterations), minIt = int(o.min_iterations);
   s->errors.assign(f->B, DBL_MAX); s->iterations.assign(f->B, 0); s->status.assign(f->B, 0);
@@ -391,7 +389,7 @@ int mb2_solver_solve(mb2_solver* s, float* params, double* errors, int32_t* iter
     for (int it = 0; it < maxIt; ++it) {
       sweepOne<true>(f, T, b, theta, &error, nullptr);
       std::fill(H.begin(), H.end(), 0.f);
-      jtjOne(f, b, f->plan.enabledList.data(), ns, H.data(), ldH);
+      jtjOne(f, b, ns, H.data(), ldH);
       float gdd = 0.f;
       if (cholDispatch(H.data(), ns, ldH, o.regularization, delta.data(), &gdd) && s->status[b] == 0) s->status[b] = MB2_INSTANCE_CHOLESKY_BREAKDOWN;
       if (!o.do_line_search) {
