@@ -130,6 +130,7 @@ def main():
     ap.add_argument("--workload", default="cfg3-shard", choices=sorted(WORKLOADS))
     ap.add_argument("--batch-per-gpu", type=int, default=0)
     ap.add_argument("--jtj-mode", type=int, default=0)
+    ap.add_argument("--cholesky-mode", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -153,7 +154,7 @@ def main():
     n = ch.num_params
     fn = ms.SkeletonSolverFunction(ch, B, efs, device=local_rank)
     fn.upload_targets()
-    opts = ms.GaussNewtonSolverOptions(min_iterations=ITERS, max_iterations=ITERS, threshold=1.0, regularization=0.05, jtj_mode=args.jtj_mode)
+    opts = ms.GaussNewtonSolverOptions(min_iterations=ITERS, max_iterations=ITERS, threshold=1.0, regularization=0.05, jtj_mode=args.jtj_mode, cholesky_mode=args.cholesky_mode)
     solver = ms.GaussNewtonSolver(opts, fn)
     m_rows = sum(3 * len(e.parents) if e.kind == 0 else 9 * len(e.parents) for e in efs)
 
@@ -255,7 +256,7 @@ def main():
         "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "desc": WORKLOADS[args.workload]["desc"], "batch_per_gpu": B, "global_batch": B * world, "iterations_per_solve": ITERS,
                    "rows_m": m_rows, "params_n": n, "parallelism": f"dp{world} (instances sharded, no data-path collective)",
-                   "jtj_mode": args.jtj_mode, "l2": "256 MB buffer written between timed steps (L2 flush)"},
+                   "jtj_mode": args.jtj_mode, "cholesky_mode": args.cholesky_mode, "l2": "256 MB buffer written between timed steps (L2 flush)"},
         "solves_per_sec": value / ITERS,
         "e2e": {"value": e2e_value, "unit": "GN it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),

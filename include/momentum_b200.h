@@ -90,6 +90,18 @@ typedef enum mb2_jtj_mode {
   MB2_JTJ_TF32 = 3       /* tcgen05 kind::tf32 single pass (~1e-3 relative; changes the GN path, not the fixed point) */
 } mb2_jtj_mode;
 
+/* How (JtJ + lambda I) delta = Jtr is solved on the device (extension; the reference always runs a dense
+ * Eigen::LLT, gauss_newton_solver.cpp:251). All modes solve the same system; they differ in elimination
+ * order (rounding) and in what happens on a non-positive pivot: the dense Eigen-structured kernel
+ * reproduces Eigen's early exit, the tile schedules substitute the damping for the pivot; both flag the
+ * instance MB2_INSTANCE_CHOLESKY_BREAKDOWN. */
+typedef enum mb2_cholesky_mode {
+  MB2_CHOLESKY_AUTO = 0,            /* tile schedule on the sparsity pattern for >= 48 unknowns, else dense Eigen-structured */
+  MB2_CHOLESKY_DENSE_EIGEN = 1,     /* blocked LLT with Eigen's block structure and failure semantics */
+  MB2_CHOLESKY_TILES_DENSE = 2,     /* level-scheduled 16x16 tiles, every tile present */
+  MB2_CHOLESKY_TILES_SPARSE = 3     /* level-scheduled tiles over the kinematic-tree sparsity of JtJ (min-degree order) */
+} mb2_cholesky_mode;
+
 /* solver/solver.h:19-34 SolverOptions + solver/gauss_newton_solver.h:17-59 GaussNewtonSolverOptions,
  * field for field, plus device extensions at the end. */
 typedef struct mb2_gauss_newton_options {
@@ -104,7 +116,7 @@ typedef struct mb2_gauss_newton_options {
   int32_t subset_line_search;     /* 1 = SubsetGaussNewtonSolverT line search (c1=1e-4, g.delta), subset_gauss_newton_solver.cpp:119-141 */
   int32_t jtj_mode;               /* mb2_jtj_mode */
   int32_t store_error_history;    /* keep per-iteration error per instance (solver.h:90 getErrorHistory) */
-  int32_t reserved;
+  int32_t cholesky_mode;          /* mb2_cholesky_mode */
 } mb2_gauss_newton_options;
 
 typedef struct mb2_character mb2_character;             /* Skeleton + ParameterTransform + ParameterLimits on device */

@@ -14,6 +14,7 @@
 #include <string>
 #include <vector>
 
+#include "ik_chol_sched.h"
 #include "ik_jtj_tc.cuh"
 #include "ik_kernels.cuh"
 #include "ik_plan.h"
@@ -75,6 +76,16 @@ struct mb2_character {
   uint64_t limitsVersion{0};
 };
 
+struct DeviceSchedule {
+  CholSchedule host;
+  CholSchedDev dev{};
+  bool valid{false};
+  bool dense{false};
+  DeviceBuffer<int16_t> perm, tileRow, tileCol;
+  DeviceBuffer<int32_t> diagTile, levelColStart, levelCols, levelPanelStart, panelTile, panelDiag, levelTaskStart, taskDst, taskPairStart, pairA, pairB,
+      levelVTaskStart, vtaskRow, vtaskSrcStart, vsrcTile, vsrcCol, colPanelStart, colPanelTile, colPanelRow;
+};
+
 struct mb2_solver_function {
   const mb2_character* ch{nullptr};
   int B{0};
@@ -99,6 +110,7 @@ struct mb2_solver_function {
   DeviceBuffer<float> dTargets, dWeights, dJ, dTheta, dState, dH;
   DeviceBuffer<double> dErrors;
   std::vector<float> hWeights; // shared weights mirror
+  std::unique_ptr<DeviceSchedule> sched; // Cholesky schedule of the current (compact) plan
   FunctionTables tables() const;
 };
 
@@ -208,6 +220,28 @@ int uploadWeights(mb2_solver_function* f) {
   return MB2_OK;
 }
 
+int ensureSchedule(mb2_solver_function* f, bool dense) {
+  if (f->sched && f->sched->valid && f->sched->dense == dense) return MB2_OK;
+  auto ds = std::make_unique<DeviceSchedule>();
+  const int ns = f->plan.numCols;
+  std::vector<std::vector<int>> cliques(f->plan.units.size());
+  for (const CellDesc& c : f->plan.cells) cliques[c.unit].push_back(int(c.col));
+  const std::string err = buildCholSchedule(ns, cliques, dense, ds->host);
+  if (!err.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, err);
+  cudaStream_t s = f->stream;
+  const CholSchedule& h = ds->host;
+#define MB2_UP(field) MB2_CUDA(ds->field.upload(h.field, s)); ds->dev.field = ds->field.p;
+  MB2_UP(perm) MB2_UP(tileRow) MB2_UP(tileCol) MB2_UP(diagTile) MB2_UP(levelColStart) MB2_UP(levelCols) MB2_UP(levelPanelStart) MB2_UP(panelTile)
+  MB2_UP(panelDiag) MB2_UP(levelTaskStart) MB2_UP(taskDst) MB2_UP(taskPairStart) MB2_UP(pairA) MB2_UP(pairB) MB2_UP(levelVTaskStart) MB2_UP(vtaskRow)
+  MB2_UP(vtaskSrcStart) MB2_UP(vsrcTile) MB2_UP(vsrcCol) MB2_UP(colPanelStart) MB2_UP(colPanelTile) MB2_UP(colPanelRow)
+#undef MB2_UP
+  ds->dev.n = h.n; ds->dev.nPad = h.nPad; ds->dev.numTileCols = h.numTileCols; ds->dev.numTiles = h.numTiles; ds->dev.numLevels = h.numLevels;
+  ds->valid = true;
+  ds->dense = dense;
+  f->sched = std::move(ds);
+  return MB2_OK;
+}
+
 // compact = true: device Jacobian holds only the enabled columns, packed (solver path);
 // compact = false: every column at its model-parameter index (getJacobian / getJtJR parity).
 // Both coincide when every parameter is enabled.
@@ -242,6 +276,7 @@ int ensurePlan(mb2_solver_function* f, bool compact) {
   if (rc != MB2_OK) return rc;
   rc = uploadWeights(f);
   if (rc != MB2_OK) return rc;
+  f->sched.reset();
   f->planDirty = false;
   f->planLimitsVersion = f->ch->limitsVersion;
   return MB2_OK;
@@ -735,6 +770,16 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
   MB2_CUDA(s->dStatus.resize(B));
   MB2_CUDA(s->dActiveCount.resize(1));
   const bool lineSearch = o.do_line_search != 0;
+  // Cholesky path: 0 auto, 1 dense Eigen-structured kernel, 2 tile schedule on the dense pattern, 3 tile schedule on the sparse pattern
+  int cholMode = o.cholesky_mode;
+  if (cholMode == 0) cholMode = ns >= 48 ? 3 : 1;
+  bool useSchedule = false;
+  if (cholMode >= 2) {
+    rc = ensureSchedule(f, cholMode == 2);
+    if (rc != MB2_OK) return rc;
+    useSchedule = choleskyScheduledSmemBytes(ns, f->sched->host.nPad, f->sched->host.numTiles) <= size_t(200 * 1024);
+    if (!useSchedule && o.cholesky_mode >= 2) return fail(MB2_ERR_UNSUPPORTED, "tile schedule does not fit in shared memory for this system");
+  }
   if (lineSearch) {
     MB2_CUDA(s->dThetaOrig.resize(size_t(B) * n));
     MB2_CUDA(s->dTrialErrors.resize(B));
@@ -790,7 +835,8 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
     c.bookkeeping = lineSearch ? 0 : 1;
     c.gradDotDelta = lineSearch ? s->dGradDotDelta.p : nullptr;
     recordPhaseStart(s, 2, st);
-    MB2_CUDA(launchCholesky(c, st));
+    if (useSchedule) MB2_CUDA(launchCholeskyScheduled(c, f->sched->dev, st));
+    else MB2_CUDA(launchCholesky(c, st));
     recordPhaseStop(s, st);
     if (lineSearch) { // gauss_newton_solver.cpp:283-313 / subset_gauss_newton_solver.cpp:119-141
       MB2_CUDA(cudaMemcpyAsync(s->dThetaOrig.p, theta, size_t(B) * n * sizeof(float), cudaMemcpyDeviceToDevice, st));

@@ -1,0 +1,232 @@
+#include "ik_chol_sched.h"
+
+#include <algorithm>
+#include <map>
+
+namespace mb2 {
+
+namespace {
+
+struct BitRows {
+  int n, words;
+  std::vector<uint64_t> b;
+  BitRows(int n_) : n(n_), words((n_ + 63) / 64), b(size_t(n_) * ((n_ + 63) / 64), 0) {}
+  uint64_t* row(int i) { return b.data() + size_t(i) * words; }
+  const uint64_t* row(int i) const { return b.data() + size_t(i) * words; }
+  void set(int i, int j) { row(i)[j >> 6] |= 1ull << (j & 63); }
+  void clear(int i, int j) { row(i)[j >> 6] &= ~(1ull << (j & 63)); }
+  bool test(int i, int j) const { return (row(i)[j >> 6] >> (j & 63)) & 1ull; }
+  int count(int i) const {
+    int c = 0;
+    for (int w = 0; w < words; ++w) c += __builtin_popcountll(row(i)[w]);
+    return c;
+  }
+};
+
+// Minimum-degree ordering on the symmetric pattern; ties go to a neighbour of the vertex eliminated
+// last (keeps the parameters of one kinematic chain contiguous), then to the lowest index.
+std::vector<int> minimumDegreeOrder(BitRows& adj) {
+  const int n = adj.n;
+  std::vector<int> order;
+  order.reserve(n);
+  std::vector<uint8_t> done(n, 0);
+  std::vector<int> degree(n);
+  for (int i = 0; i < n; ++i) degree[i] = adj.count(i);
+  int last = -1;
+  for (int step = 0; step < n; ++step) {
+    int best = -1;
+    for (int i = 0; i < n; ++i) {
+      if (done[i]) continue;
+      if (best < 0 || degree[i] < degree[best]) best = i;
+      else if (degree[i] == degree[best] && last >= 0 && adj.test(last, i) && !adj.test(last, best)) best = i;
+    }
+    // eliminate `best`: its remaining neighbours become a clique
+    std::vector<int> nb;
+    for (int j = 0; j < n; ++j)
+      if (!done[j] && j != best && adj.test(best, j)) nb.push_back(j);
+    for (int u : nb) {
+      uint64_t* ru = adj.row(u);
+      const uint64_t* rv = adj.row(best);
+      for (int w = 0; w < adj.words; ++w) ru[w] |= rv[w];
+      adj.clear(u, u);
+      adj.clear(u, best);
+    }
+    for (int u : nb) {
+      int c = 0;
+      for (int j : nb) c += (j != u) ? 1 : 0; // lower bound; exact count below
+      (void)c;
+      // exact remaining degree: neighbours that are not eliminated
+      int d = 0;
+      const uint64_t* ru = adj.row(u);
+      for (int j = 0; j < n; ++j)
+        if (!done[j] && j != best && ((ru[j >> 6] >> (j & 63)) & 1ull)) ++d;
+      degree[u] = d;
+    }
+    done[best] = 1;
+    order.push_back(best);
+    last = best;
+  }
+  return order;
+}
+
+} // namespace
+
+std::string buildCholSchedule(int n, const std::vector<std::vector<int>>& cliques, bool forceDense, CholSchedule& out) {
+  out = CholSchedule();
+  if (n <= 0) return "empty system";
+  out.n = n;
+
+  // 1. ordering
+  std::vector<int> order(n);
+  BitRows pattern(n);
+  for (int i = 0; i < n; ++i) pattern.set(i, i);
+  if (forceDense) {
+    for (int i = 0; i < n; ++i) order[i] = i;
+  } else {
+    for (const auto& c : cliques)
+      for (int a : c) {
+        if (a < 0 || a >= n) continue;
+        for (int b : c)
+          if (b >= 0 && b < n) pattern.set(a, b);
+      }
+    BitRows work = pattern;
+    for (int i = 0; i < n; ++i) work.clear(i, i);
+    order = minimumDegreeOrder(work);
+  }
+  // 1b. supernodes of the element-level factor (columns with nested structure) decide where tiles may
+  //     break: a supernode that fits in one tile is never split across two (padding instead), because a
+  //     split chain would make consecutive tile columns depend on each other and serialise the levels.
+  std::vector<int> slot(n); // padded position of the i-th eliminated parameter
+  {
+    std::vector<int> rank(n);
+    for (int i = 0; i < n; ++i) rank[order[i]] = i;
+    BitRows F(n); // filled lower pattern in elimination order: F[i][j], i > j
+    for (int a = 0; a < n; ++a)
+      for (int b = 0; b < n; ++b)
+        if (a != b && (forceDense || pattern.test(a, b))) { const int i = rank[a], j = rank[b]; if (i > j) F.set(i, j); }
+    std::vector<int> parent(n, -1), cnt(n, 0);
+    // column structures via row-merge: struct(j) = {i > j : F[i][j]}; fill: struct(parent(j)) |= struct(j) \ {parent(j)}
+    std::vector<std::vector<int>> col(n);
+    for (int j = 0; j < n; ++j) {
+      for (int i = j + 1; i < n; ++i) if (F.test(i, j)) col[j].push_back(i);
+      cnt[j] = int(col[j].size());
+      if (!col[j].empty()) {
+        const int pj = col[j][0];
+        parent[j] = pj;
+        for (size_t k = 1; k < col[j].size(); ++k) F.set(col[j][k], pj);
+      }
+    }
+    int fill = 0, start = 0; // greedy packing of supernodes into tiles
+    int padded = 0;
+    auto flushSupernode = [&](int first, int lastExcl) {
+      const int sz = lastExcl - first;
+      if (sz <= kCholTile && fill + sz > kCholTile) { padded += kCholTile - fill; fill = 0; } // do not split: pad to the tile boundary
+      for (int j = first; j < lastExcl; ++j) { slot[j] = padded++; fill = (fill + 1) % kCholTile; }
+    };
+    for (int j = 1; j <= n; ++j) {
+      const bool joins = j < n && parent[j - 1] == j && cnt[j - 1] == cnt[j] + 1;
+      if (!joins) { flushSupernode(start, j); start = j; }
+    }
+    (void)fill;
+    const int T0 = (padded + kCholTile - 1) / kCholTile;
+    out.numTileCols = T0;
+    out.nPad = T0 * kCholTile;
+  }
+  const int T = out.numTileCols;
+  if (T > 512) return "system too large for the tile schedule";
+  out.perm.assign(out.nPad, int16_t(-1));
+  std::vector<int> pos(n);
+  for (int i = 0; i < n; ++i) { out.perm[slot[i]] = int16_t(order[i]); pos[order[i]] = slot[i]; }
+
+  // 2. tile-level pattern (lower) + symbolic factorisation
+  std::vector<std::vector<uint8_t>> S(T, std::vector<uint8_t>(T, 0));
+  for (int I = 0; I < T; ++I) S[I][I] = 1;
+  if (forceDense) {
+    for (int I = 0; I < T; ++I) for (int J = 0; J <= I; ++J) S[I][J] = 1;
+  } else {
+    for (int a = 0; a < n; ++a)
+      for (int b = 0; b < n; ++b)
+        if (pattern.test(a, b)) {
+          const int I = pos[a] / kCholTile, J = pos[b] / kCholTile;
+          if (I >= J) S[I][J] = 1;
+        }
+    for (int K = 0; K < T; ++K) {
+      std::vector<int> st;
+      for (int I = K + 1; I < T; ++I) if (S[I][K]) st.push_back(I);
+      for (size_t a = 0; a < st.size(); ++a)
+        for (size_t b = 0; b <= a; ++b) S[st[a]][st[b]] = 1;
+    }
+  }
+  // 3. tiles, elimination tree, levels
+  std::vector<std::vector<int>> tileId(T, std::vector<int>(T, -1));
+  out.diagTile.assign(T, -1);
+  for (int J = 0; J < T; ++J)
+    for (int I = J; I < T; ++I)
+      if (S[I][J]) {
+        tileId[I][J] = int(out.tileRow.size());
+        out.tileRow.push_back(int16_t(I));
+        out.tileCol.push_back(int16_t(J));
+        if (I == J) out.diagTile[J] = tileId[I][J];
+      }
+  out.numTiles = int(out.tileRow.size());
+  std::vector<int> level(T, 0);
+  std::vector<std::vector<int>> st(T);
+  for (int K = 0; K < T; ++K) {
+    for (int I = K + 1; I < T; ++I) if (S[I][K]) st[K].push_back(I);
+    if (!st[K].empty()) level[st[K][0]] = std::max(level[st[K][0]], level[K] + 1);
+  }
+  int numLevels = 0;
+  for (int K = 0; K < T; ++K) numLevels = std::max(numLevels, level[K] + 1);
+  out.numLevels = numLevels;
+
+  // 4. per-level work lists
+  out.levelColStart.assign(1, 0);
+  out.levelPanelStart.assign(1, 0);
+  out.levelTaskStart.assign(1, 0);
+  out.levelVTaskStart.assign(1, 0);
+  out.taskPairStart.assign(1, 0);
+  out.vtaskSrcStart.assign(1, 0);
+  for (int L = 0; L < numLevels; ++L) {
+    std::map<int, std::vector<std::pair<int, int>>> tasks; // dst tile -> (A,B) pairs
+    std::map<int, std::vector<std::pair<int, int>>> vtasks; // block row -> (tile, K)
+    for (int K = 0; K < T; ++K) {
+      if (level[K] != L) continue;
+      out.levelCols.push_back(K);
+      for (int I : st[K]) {
+        out.panelTile.push_back(tileId[I][K]);
+        out.panelDiag.push_back(out.diagTile[K]);
+        out.panelRow.push_back(I);
+        vtasks[I].push_back({tileId[I][K], K});
+      }
+      for (size_t a = 0; a < st[K].size(); ++a)
+        for (size_t b = 0; b <= a; ++b) {
+          const int I = st[K][a], J = st[K][b];
+          tasks[tileId[I][J]].push_back({tileId[I][K], tileId[J][K]});
+          out.tileOps++;
+        }
+    }
+    for (auto& kv : tasks) {
+      out.taskDst.push_back(kv.first);
+      for (auto& pr : kv.second) { out.pairA.push_back(pr.first); out.pairB.push_back(pr.second); }
+      out.taskPairStart.push_back(int(out.pairA.size()));
+    }
+    for (auto& kv : vtasks) {
+      out.vtaskRow.push_back(kv.first);
+      for (auto& pr : kv.second) { out.vsrcTile.push_back(pr.first); out.vsrcCol.push_back(pr.second); }
+      out.vtaskSrcStart.push_back(int(out.vsrcTile.size()));
+    }
+    out.levelColStart.push_back(int(out.levelCols.size()));
+    out.levelPanelStart.push_back(int(out.panelTile.size()));
+    out.levelTaskStart.push_back(int(out.taskDst.size()));
+    out.levelVTaskStart.push_back(int(out.vtaskRow.size()));
+  }
+  out.colPanelStart.assign(1, 0);
+  for (int K = 0; K < T; ++K) {
+    for (int I : st[K]) { out.colPanelTile.push_back(tileId[I][K]); out.colPanelRow.push_back(I); }
+    out.colPanelStart.push_back(int(out.colPanelTile.size()));
+  }
+  for (int K = 0; K < T; ++K) { const int64_t r = T - 1 - K; out.denseTileOps += r * (r + 1) / 2; }
+  return "";
+}
+
+} // namespace mb2

@@ -1,0 +1,209 @@
+// Device building blocks of the level-scheduled tile-sparse Cholesky (see ik_chol_sched.h).
+//
+// Storage: every structurally non-zero lower tile is a 16x16 fp32 block in shared memory. Rows are
+// 64 bytes; the four float4 groups of a row are XOR-swizzled with ((row >> 1) & 3) so that the two
+// access shapes used everywhere — "16 lanes read 16 consecutive floats of one row" and "lane r reads
+// float4 group g of row r" — are both bank-conflict free.
+// Panel tiles L(I,K) are stored TRANSPOSED once solved (T[c][r] = L[r][c]): update tasks then read
+// both operands along rows (float2 / float4), and the substitution phases read along rows too.
+//
+// Work is mapped to half-warps (one 16-row tile each) except the 16x16x16 update tasks (one warp,
+// each lane a 2x4 register block). Cross-lane steps (diagonal tile factorisation, the two 16x16
+// triangular solves) use width-16 shuffles on the device; the host build (tests/emu) runs the same
+// arithmetic serially so that the schedule and the tile algebra are validated without a GPU.
+#pragma once
+
+#include <cmath>
+
+#include "ik_types.h"
+
+#if defined(__CUDACC__)
+#include <vector_types.h>
+#endif
+
+namespace mb2 {
+
+struct CholSchedDev {
+  int32_t n, nPad, numTileCols, numTiles, numLevels;
+  const int16_t* perm;
+  const int16_t* tileRow;
+  const int16_t* tileCol;
+  const int32_t* diagTile;
+  const int32_t* levelColStart;
+  const int32_t* levelCols;
+  const int32_t* levelPanelStart;
+  const int32_t* panelTile;
+  const int32_t* panelDiag;
+  const int32_t* levelTaskStart;
+  const int32_t* taskDst;
+  const int32_t* taskPairStart;
+  const int32_t* pairA;
+  const int32_t* pairB;
+  const int32_t* levelVTaskStart;
+  const int32_t* vtaskRow;
+  const int32_t* vtaskSrcStart;
+  const int32_t* vsrcTile;
+  const int32_t* vsrcCol;
+  const int32_t* colPanelStart;
+  const int32_t* colPanelTile;
+  const int32_t* colPanelRow;
+};
+
+MB2_HD int tileIdx(int r, int c) { return r * 16 + ((((c >> 2) ^ ((r >> 1) & 3)) << 2) | (c & 3)); }
+MB2_HD int tileGrp(int r, int g) { return r * 16 + ((g ^ ((r >> 1) & 3)) << 2); }
+
+MB2_HD void tileLoadRow(const float* tile, int r, float* a) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const float4 v = *reinterpret_cast<const float4*>(tile + tileGrp(r, g));
+    a[4 * g] = v.x; a[4 * g + 1] = v.y; a[4 * g + 2] = v.z; a[4 * g + 3] = v.w;
+  }
+}
+MB2_HD void tileStoreRow(float* tile, int r, const float* a) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float4 v;
+    v.x = a[4 * g]; v.y = a[4 * g + 1]; v.z = a[4 * g + 2]; v.w = a[4 * g + 3];
+    *reinterpret_cast<float4*>(tile + tileGrp(r, g)) = v;
+  }
+}
+
+// ---- phase A: Cholesky of a diagonal tile + forward solve of its 16 right-hand-side entries ----
+// hl = lane within the half-warp (0..15), hmask = shuffle mask of the half-warp.
+// A non-positive pivot is replaced by `fallback` (the damping) and reported through *fail.
+MB2_HD void cholDiagTile(float* tile, float* y16, int hl, unsigned hmask, float fallback, int* fail) {
+#if defined(__CUDA_ARCH__)
+  float a[16];
+  tileLoadRow(tile, hl, a);
+  float yv = y16[hl];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    float piv = __shfl_sync(hmask, a[k], k, 16);
+    if (!(piv > 0.f)) { piv = fallback; if (hl == k) *fail = 1; }
+    const float d = sqrtf(piv);
+    const float rd = 1.f / d;
+    const float lk = a[k] * rd; // L[r][k] for r > k
+    const float xk = __shfl_sync(hmask, yv, k, 16) * rd;
+#pragma unroll
+    for (int j = k + 1; j < 16; ++j) {
+      const float ljk = __shfl_sync(hmask, lk, j, 16);
+      a[j] -= lk * ljk;
+    }
+    if (hl > k) yv -= lk * xk;
+    else if (hl == k) yv = xk;
+    a[k] = (hl == k) ? d : lk;
+  }
+  tileStoreRow(tile, hl, a);
+  y16[hl] = yv;
+#else
+  if (hl != 0) return; // host emulation: one caller does the whole tile with the same operation order
+  for (int k = 0; k < 16; ++k) {
+    float piv = tile[tileIdx(k, k)];
+    if (!(piv > 0.f)) { piv = fallback; *fail = 1; }
+    const float d = sqrtf(piv);
+    const float rd = 1.f / d;
+    float lk[16];
+    for (int r = 0; r < 16; ++r) lk[r] = tile[tileIdx(r, k)] * rd;
+    const float xk = y16[k] * rd;
+    for (int r = k + 1; r < 16; ++r)
+      for (int j = k + 1; j <= r; ++j) tile[tileIdx(r, j)] -= lk[r] * lk[j];
+    for (int r = k + 1; r < 16; ++r) { y16[r] -= lk[r] * xk; tile[tileIdx(r, k)] = lk[r]; }
+    y16[k] = xk;
+    tile[tileIdx(k, k)] = d;
+  }
+#endif
+}
+
+// ---- phase B: X = A(I,K) L(K,K)^-T for one panel tile; lane hl owns row hl. Two steps so that the
+// transposed write-back cannot race with other lanes still reading their rows. ----
+MB2_HD void cholPanelLoad(const float* tile, int hl, float* a) { tileLoadRow(tile, hl, a); }
+MB2_HD void cholPanelSolveStore(float* tile, const float* diag, int hl, float* a) {
+  float x[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    float d[16];
+    tileLoadRow(diag, c, d); // row c of L(K,K): broadcast reads
+    float s0 = a[c], s1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (j < c) { if (j & 1) s1 += x[j] * d[j]; else s0 -= x[j] * d[j]; }
+    }
+    x[c] = (s0 - s1) / d[c];
+  }
+#pragma unroll
+  for (int c = 0; c < 16; ++c) tile[tileIdx(c, hl)] = x[c]; // transposed: T[c][r]
+}
+
+// ---- phase C: one update task, D(I,J) -= sum_pairs L(I,K) L(J,K)^T; a warp, lane = 2x4 block ----
+MB2_HD void cholUpdateTask(float* tiles, const CholSchedDev& S, int task, int lane) {
+  const int lr = lane >> 2, lc = lane & 3;
+  float acc[2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int p = S.taskPairStart[task]; p < S.taskPairStart[task + 1]; ++p) {
+    const float* A = tiles + size_t(S.pairA[p]) * 256;
+    const float* B = tiles + size_t(S.pairB[p]) * 256;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float2 av = *reinterpret_cast<const float2*>(A + tileGrp(k, lr >> 1) + 2 * (lr & 1));
+      const float4 bv = *reinterpret_cast<const float4*>(B + tileGrp(k, lc));
+      acc[0][0] += av.x * bv.x; acc[0][1] += av.x * bv.y; acc[0][2] += av.x * bv.z; acc[0][3] += av.x * bv.w;
+      acc[1][0] += av.y * bv.x; acc[1][1] += av.y * bv.y; acc[1][2] += av.y * bv.z; acc[1][3] += av.y * bv.w;
+    }
+  }
+  float* D = tiles + size_t(S.taskDst[task]) * 256;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    float4* dp = reinterpret_cast<float4*>(D + tileGrp(2 * lr + i, lc));
+    float4 v = *dp;
+    v.x -= acc[i][0]; v.y -= acc[i][1]; v.z -= acc[i][2]; v.w -= acc[i][3];
+    *dp = v;
+  }
+}
+
+// ---- phase C (vector part): y_I -= sum L(I,K) y_K over this level's columns; lane hl = row ----
+MB2_HD void cholVectorTask(const float* tiles, float* y, const CholSchedDev& S, int vtask, int hl) {
+  float s = 0.f;
+  for (int p = S.vtaskSrcStart[vtask]; p < S.vtaskSrcStart[vtask + 1]; ++p) {
+    const float* T = tiles + size_t(S.vsrcTile[p]) * 256;
+    const float* yk = y + S.vsrcCol[p] * 16;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) s += T[tileIdx(c, hl)] * yk[c];
+  }
+  y[S.vtaskRow[vtask] * 16 + hl] -= s;
+}
+
+// ---- backward substitution for one tile column K: y_K <- L(K,K)^-T (y_K - sum_I L(I,K)^T y_I) ----
+MB2_HD void cholBackwardColumn(const float* tiles, float* y, const CholSchedDev& S, int K, int hl, unsigned hmask) {
+  float s = y[K * 16 + hl];
+  for (int p = S.colPanelStart[K]; p < S.colPanelStart[K + 1]; ++p) {
+    float t[16];
+    tileLoadRow(tiles + size_t(S.colPanelTile[p]) * 256, hl, t); // row c = hl of the transposed tile: L[r][c], r = 0..15
+    const float* yi = y + S.colPanelRow[p] * 16;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) s -= t[r] * yi[r];
+  }
+  const float* D = tiles + size_t(S.diagTile[K]) * 256;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+  for (int k = 15; k >= 0; --k) {
+    const float xk = __shfl_sync(hmask, s, k, 16) / D[tileIdx(k, k)];
+    if (hl < k) s -= D[tileIdx(k, hl)] * xk;
+    else if (hl == k) s = xk;
+  }
+  y[K * 16 + hl] = s;
+#else
+  // host emulation: lanes run one after the other, so stage the sums, then lane 15 (last) solves
+  y[K * 16 + hl] = s;
+  if (hl != 15) return;
+  for (int k = 15; k >= 0; --k) {
+    const float xk = y[K * 16 + k] / D[tileIdx(k, k)];
+    for (int c = 0; c < k; ++c) y[K * 16 + c] -= D[tileIdx(k, c)] * xk;
+    y[K * 16 + k] = xk;
+  }
+#endif
+}
+
+} // namespace mb2

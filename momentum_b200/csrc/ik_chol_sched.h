@@ -1,0 +1,48 @@
+// Level-scheduled, tile-sparse Cholesky: host-side symbolic analysis.
+//
+// The reference factors the dense normal matrix with Eigen::LLT (gauss_newton_solver.cpp:251). For a
+// skeleton, (J^T J)(p,q) is structurally non-zero only when some residual row depends on both p and q,
+// i.e. when their joints lie on one root-to-constraint path (joint_error_function-inl.h:229-294 walks
+// exactly that path) — so the matrix of a branching rig is mostly zero blocks (the two arms never
+// couple), and eliminating children before parents creates no fill outside that structure.
+// This analysis (once per plan) turns the sparsity pattern into a static schedule for the device:
+//   1. minimum-degree ordering of the enabled parameters (pattern = cliques of the Jacobian row groups),
+//   2. 16x16 tiles over the permuted order, tile-level symbolic factorisation (fill included),
+//   3. the tile elimination tree and its levels: all tile columns of one level are independent, so
+//      a level costs three block-wide phases no matter how many columns it holds,
+//   4. per level: diagonal tiles, panel tiles, and one update task per destination tile listing every
+//      (L(I,K), L(J,K)) pair that contributes to it (deterministic summation order, no atomics).
+// A dense matrix is the special case "every tile non-zero, elimination tree = chain".
+// The solution of (H + lambda I) x = g is the same as Eigen's up to rounding.
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace mb2 {
+
+constexpr int kCholTile = 16;
+
+struct CholSchedule {
+  int32_t n{0}, nPad{0}, numTileCols{0}, numTiles{0}, numLevels{0};
+  std::vector<int16_t> perm;            // [nPad] permuted position -> device column, -1 = padding
+  std::vector<int16_t> tileRow, tileCol; // [numTiles] block coordinates (I >= J)
+  std::vector<int32_t> diagTile;        // [numTileCols]
+  // per level
+  std::vector<int32_t> levelColStart, levelCols;       // tile columns K of each level
+  std::vector<int32_t> levelPanelStart, panelTile, panelDiag, panelRow; // panel tiles (I,K) of the level's columns; diag tile of K; block row I
+  std::vector<int32_t> levelTaskStart, taskDst, taskPairStart, pairA, pairB; // matrix update tasks
+  std::vector<int32_t> levelVTaskStart, vtaskRow, vtaskSrcStart, vsrcTile, vsrcCol; // forward-substitution updates y_I -= L(I,K) y_K
+  // per tile column (backward substitution): its panel tiles
+  std::vector<int32_t> colPanelStart, colPanelTile, colPanelRow;
+  // statistics
+  int64_t tileOps{0};      // 16x16x16 multiply-accumulate blocks executed by update tasks
+  int64_t denseTileOps{0}; // what a dense factorisation of the same size would execute
+};
+
+// `cliques`: for every Jacobian row group, the device columns it touches (each list is a clique of the
+// pattern). n = number of device columns that enter the normal equations.
+std::string buildCholSchedule(int n, const std::vector<std::vector<int>>& cliques, bool forceDense, CholSchedule& out);
+
+} // namespace mb2

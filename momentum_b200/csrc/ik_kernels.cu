@@ -180,6 +180,43 @@ cudaError_t launchJtJSimt(const JtJArgs& a, cudaStream_t stream) {
 // is factored in place with Eigen's LLT structure (ik_chol.cuh); the appended row turns into
 // y = L^-1 g for free; back substitution gives delta.
 // ------------------------------------------------------------------------------------------------
+// Common tail of both Cholesky kernels: delta, parameter update (skeleton_solver_function.cpp:153-159),
+// g.delta for the subset line search, status and the SolverT bookkeeping (solver.cpp:92-122).
+// dsub / gsub are indexed by subset position. Every thread of the CTA must call it.
+__device__ void cholFinish(const CholArgs& a, int b, int n, const float* dsub, const float* gsub, bool failed) {
+  const int tid = threadIdx.x;
+  float* theta = a.theta + size_t(b) * a.ldTheta;
+  float part = 0.f;
+  for (int i = tid; i < n; i += blockDim.x) {
+    const float d = dsub[i];
+    a.delta[size_t(b) * n + i] = d;
+    part += gsub[i] * d;
+    if (a.applyUpdate) theta[a.cols[i]] -= d;
+  }
+  if (a.gradDotDelta != nullptr) {
+    __shared__ float red[32];
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((tid & 31) == 0) red[tid >> 5] = part;
+    __syncthreads();
+    if (tid == 0) {
+      float s = 0.f;
+      for (int w = 0; w < int(blockDim.x >> 5); ++w) s += red[w];
+      a.gradDotDelta[b] = s;
+    }
+  }
+  if (tid == 0) {
+    if (failed && a.status[b] == 0) a.status[b] = 1; // MB2_INSTANCE_CHOLESKY_BREAKDOWN
+    if (a.bookkeeping) {
+      const double error = a.errors[b], last = a.lastErrors[b];
+      if (a.history != nullptr) a.history[size_t(b) * a.maxIterations + a.iteration] = error;
+      const bool converged = fabs(last - error) / (fabs(error) + (double)FLT_MIN) <= (double)(a.threshold * FLT_EPSILON);
+      a.iterations[b] = a.iteration + 1;
+      if ((a.iteration >= a.minIterations && converged) || a.iteration + 1 >= a.maxIterations) a.active[b] = 0;
+      else { a.lastErrors[b] = error; atomicAdd(a.activeCount, 1); }
+    }
+  }
+}
+
 template <int NB>
 __global__ void __launch_bounds__(kCholThreads) choleskyKernel(const CholArgs a, const int useSmemMatrix) {
   extern __shared__ float smem[];
@@ -271,38 +308,7 @@ __global__ void __launch_bounds__(kCholThreads) choleskyKernel(const CholArgs a,
     }
     __syncthreads();
   }
-  // delta, parameter update (skeleton_solver_function.cpp:153-159), status
-  float* theta = a.theta + size_t(b) * a.ldTheta;
-  float part = 0.f;
-  for (int i = tid; i < n; i += kCholThreads) {
-    const float d = y[i];
-    a.delta[size_t(b) * n + i] = d;
-    part += gsave[i] * d;
-    if (a.applyUpdate) theta[a.cols[i]] -= d;
-  }
-  if (a.gradDotDelta != nullptr) {
-    __shared__ float red[kCholThreads / 32];
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if ((tid & 31) == 0) red[tid >> 5] = part;
-    __syncthreads();
-    if (tid == 0) {
-      float s = 0.f;
-      for (int w = 0; w < kCholThreads / 32; ++w) s += red[w];
-      a.gradDotDelta[b] = s;
-    }
-  }
-  if (tid == 0) {
-    if (flags[0] != 0 && a.status[b] == 0) a.status[b] = 1; // MB2_INSTANCE_CHOLESKY_BREAKDOWN
-    if (a.bookkeeping) {
-      // SolverT::solve loop tail (solver.cpp:92-122)
-      const double error = a.errors[b], last = a.lastErrors[b];
-      if (a.history != nullptr) a.history[size_t(b) * a.maxIterations + a.iteration] = error;
-      const bool converged = fabs(last - error) / (fabs(error) + (double)FLT_MIN) <= (double)(a.threshold * FLT_EPSILON);
-      a.iterations[b] = a.iteration + 1;
-      if ((a.iteration >= a.minIterations && converged) || a.iteration + 1 >= a.maxIterations) a.active[b] = 0;
-      else { a.lastErrors[b] = error; atomicAdd(a.activeCount, 1); }
-    }
-  }
+  cholFinish(a, b, n, y, gsave, flags[0] != 0);
 }
 
 static size_t cholSmemBytes(int n, int NB, bool matrixInSmem) {
@@ -325,6 +331,88 @@ cudaError_t launchCholesky(const CholArgs& a, cudaStream_t stream) {
   choleskyKernel<NBV><<<a.batch, kCholThreads, smem, stream>>>(a, inSmem ? 1 : 0);
   if (NB == 8) { MB2_LAUNCH_CHOL(8) } else if (NB == 16) { MB2_LAUNCH_CHOL(16) } else { MB2_LAUNCH_CHOL(32) }
 #undef MB2_LAUNCH_CHOL
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 (scheduled): level-scheduled tile-sparse Cholesky of the permuted system (ik_chol_sched.h).
+// One CTA per instance; tiles, right-hand side and scratch live in shared memory (<= ~64 KB for the
+// humanoid rig => several CTAs per SM hide each other's latencies).
+// ------------------------------------------------------------------------------------------------
+constexpr int kSchedThreads = 256;
+
+size_t choleskyScheduledSmemBytes(int n, int nPad, int numTiles) {
+  return sizeof(float) * (size_t(numTiles) * 256 + size_t(nPad) + 2 * size_t((n + 3) & ~3)) + 16;
+}
+
+__global__ void __launch_bounds__(kSchedThreads, 2) choleskyScheduledKernel(const CholArgs a, const CholSchedDev S) {
+  extern __shared__ __align__(16) float smemS[];
+  const int b = blockIdx.x;
+  if (a.active[b] == 0) return;
+  const int n = a.ns, tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31, hw = tid >> 4, hl = tid & 15;
+  const unsigned hmask = 0xFFFFu << (16 * ((tid >> 4) & 1));
+  float* tiles = smemS;
+  float* y = tiles + size_t(S.numTiles) * 256;
+  float* gsub = y + S.nPad;
+  float* dsub = gsub + ((n + 3) & ~3);
+  int* flags = reinterpret_cast<int*>(dsub + ((n + 3) & ~3));
+  const float* Hg = a.H + size_t(b) * (n + 1) * a.ldH;
+  if (tid == 0) flags[0] = 0;
+  // gather the permuted tiles: element (i,j), i >= j, of [JtJ; Jtr] sits at Hg[j*ldH + i]
+  for (int idx = tid; idx < S.numTiles * 256; idx += kSchedThreads) {
+    const int t = idx >> 8, e = idx & 255, c = e >> 4, r = e & 15;
+    const int I = S.tileRow[t], J = S.tileCol[t];
+    const int gi = S.perm[16 * I + r], gj = S.perm[16 * J + c];
+    float v;
+    if (gi < 0 || gj < 0) v = (I == J && r == c) ? 1.f : 0.f; // padding variable: identity
+    else {
+      const int hi = gi > gj ? gi : gj, lo = gi > gj ? gj : gi;
+      v = Hg[size_t(lo) * a.ldH + hi];
+      if (gi == gj) v += a.regularization; // gauss_newton_solver.cpp:248
+    }
+    tiles[size_t(t) * 256 + tileIdx(r, c)] = v;
+  }
+  for (int i = tid; i < S.nPad; i += kSchedThreads) { const int p = S.perm[i]; y[i] = p >= 0 ? Hg[size_t(p) * a.ldH + n] : 0.f; }
+  for (int i = tid; i < n; i += kSchedThreads) gsub[i] = Hg[size_t(i) * a.ldH + n];
+  __syncthreads();
+
+  for (int L = 0; L < S.numLevels; ++L) {
+    // A: diagonal tiles of this level (one half-warp each) + forward solve of their rhs block
+    for (int ci = S.levelColStart[L] + hw; ci < S.levelColStart[L + 1]; ci += kSchedThreads / 16) {
+      const int K = S.levelCols[ci];
+      cholDiagTile(tiles + size_t(S.diagTile[K]) * 256, y + 16 * K, hl, hmask, a.regularization, flags);
+    }
+    __syncthreads();
+    // B: panel tiles
+    for (int pi = S.levelPanelStart[L] + hw; pi < S.levelPanelStart[L + 1]; pi += kSchedThreads / 16) {
+      float* P = tiles + size_t(S.panelTile[pi]) * 256;
+      float arow[16];
+      cholPanelLoad(P, hl, arow);
+      __syncwarp(hmask);
+      cholPanelSolveStore(P, tiles + size_t(S.panelDiag[pi]) * 256, hl, arow);
+    }
+    __syncthreads();
+    // C: update tasks (warp each) and rhs updates (half-warp each)
+    for (int ti = S.levelTaskStart[L] + warp; ti < S.levelTaskStart[L + 1]; ti += kSchedThreads / 32) cholUpdateTask(tiles, S, ti, lane);
+    for (int vi = S.levelVTaskStart[L] + hw; vi < S.levelVTaskStart[L + 1]; vi += kSchedThreads / 16) cholVectorTask(tiles, y, S, vi, hl);
+    __syncthreads();
+  }
+  for (int L = S.numLevels - 1; L >= 0; --L) {
+    for (int ci = S.levelColStart[L] + hw; ci < S.levelColStart[L + 1]; ci += kSchedThreads / 16) cholBackwardColumn(tiles, y, S, S.levelCols[ci], hl, hmask);
+    __syncthreads();
+  }
+  for (int i = tid; i < S.nPad; i += kSchedThreads) { const int p = S.perm[i]; if (p >= 0) dsub[p] = y[i]; }
+  __syncthreads();
+  cholFinish(a, b, n, dsub, gsub, flags[0] != 0);
+}
+
+cudaError_t launchCholeskyScheduled(const CholArgs& a, const CholSchedDev& sched, cudaStream_t stream) {
+  const size_t smem = choleskyScheduledSmemBytes(a.ns, sched.nPad, sched.numTiles);
+  if (smem > size_t(g_maxSmemOptin)) return cudaErrorInvalidConfiguration;
+  cudaError_t e = cudaFuncSetAttribute(choleskyScheduledKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (e != cudaSuccess) return e;
+  choleskyScheduledKernel<<<a.batch, kSchedThreads, smem, stream>>>(a, sched);
   return cudaGetLastError();
 }
 

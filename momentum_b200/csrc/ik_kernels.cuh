@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 
+#include "ik_chol_sched.cuh"
 #include "ik_types.h"
 
 namespace mb2 {
@@ -58,6 +59,9 @@ cudaError_t launchSweep(const SweepArgs& a, bool jacobian, cudaStream_t stream);
 size_t sweepSmemPerInstance(const FunctionTables& T);
 cudaError_t launchJtJSimt(const JtJArgs& a, cudaStream_t stream);
 cudaError_t launchCholesky(const CholArgs& a, cudaStream_t stream);
+// level-scheduled tile-sparse variant (ik_chol_sched.h); returns cudaErrorInvalidConfiguration when the tiles do not fit in shared memory
+cudaError_t launchCholeskyScheduled(const CholArgs& a, const CholSchedDev& sched, cudaStream_t stream);
+size_t choleskyScheduledSmemBytes(int n, int nPad, int numTiles);
 cudaError_t initKernelAttributes();
 
 // line-search helpers

@@ -26,6 +26,7 @@ SIZE_MAX = 2 ** 64 - 1
 
 JTJ_AUTO, JTJ_FP32_SIMT, JTJ_TF32X3, JTJ_TF32 = 0, 1, 2, 3
 INSTANCE_OK, INSTANCE_CHOLESKY_BREAKDOWN, INSTANCE_NON_FINITE = 0, 1, 2
+CHOLESKY_AUTO, CHOLESKY_DENSE_EIGEN, CHOLESKY_TILES_DENSE, CHOLESKY_TILES_SPARSE = 0, 1, 2, 3
 
 
 class MomentumB200Error(RuntimeError):
@@ -40,7 +41,7 @@ class _Options(C.Structure):
     _fields_ = [("min_iterations", C.c_uint64), ("max_iterations", C.c_uint64), ("threshold", C.c_float), ("verbose", C.c_int32),
                 ("regularization", C.c_float), ("do_line_search", C.c_int32), ("use_block_jtj", C.c_int32),
                 ("target_rows_per_chunk", C.c_uint64), ("subset_line_search", C.c_int32), ("jtj_mode", C.c_int32),
-                ("store_error_history", C.c_int32), ("reserved", C.c_int32)]
+                ("store_error_history", C.c_int32), ("cholesky_mode", C.c_int32)]
 
 
 _fp = C.POINTER(C.c_float)
@@ -151,11 +152,12 @@ class GaussNewtonSolverOptions(SolverOptions):
     subset_line_search: bool = False
     jtj_mode: int = JTJ_AUTO
     store_error_history: bool = False
+    cholesky_mode: int = 0  # CHOLESKY_AUTO
 
     def _c(self) -> _Options:
         return _Options(self.min_iterations, self.max_iterations, self.threshold, int(self.verbose), self.regularization,
                         int(self.do_line_search), int(self.use_block_jtj), self.target_rows_per_chunk, int(self.subset_line_search),
-                        int(self.jtj_mode), int(self.store_error_history), 0)
+                        int(self.jtj_mode), int(self.store_error_history), int(self.cholesky_mode))
 
 
 class _Base:

@@ -14,6 +14,8 @@
 
 #include "../../include/momentum_b200.h"
 #include "../../momentum_b200/csrc/ik_chol.cuh"
+#include "../../momentum_b200/csrc/ik_chol_sched.cuh"
+#include "../../momentum_b200/csrc/ik_chol_sched.h"
 #include "../../momentum_b200/csrc/ik_device.cuh"
 #include "../../momentum_b200/csrc/ik_plan.h"
 
@@ -161,6 +163,59 @@ static int cholDispatch(float* Hg, int n, int ldH, float reg, float* delta, floa
   if (eig <= 8) return cholOne<8>(Hg, n, ldH, reg, delta, gdd);
   if (eig <= 16) return cholOne<16>(Hg, n, ldH, reg, delta, gdd);
   return cholOne<32>(Hg, n, ldH, reg, delta, gdd);
+}
+
+// emulation of choleskyScheduledKernel for one instance: phases in the same order, half-warps/warps in sequence
+static CholSchedDev devView(const CholSchedule& h) {
+  CholSchedDev d{};
+  d.n = h.n; d.nPad = h.nPad; d.numTileCols = h.numTileCols; d.numTiles = h.numTiles; d.numLevels = h.numLevels;
+  d.perm = h.perm.data(); d.tileRow = h.tileRow.data(); d.tileCol = h.tileCol.data(); d.diagTile = h.diagTile.data();
+  d.levelColStart = h.levelColStart.data(); d.levelCols = h.levelCols.data(); d.levelPanelStart = h.levelPanelStart.data();
+  d.panelTile = h.panelTile.data(); d.panelDiag = h.panelDiag.data(); d.levelTaskStart = h.levelTaskStart.data(); d.taskDst = h.taskDst.data();
+  d.taskPairStart = h.taskPairStart.data(); d.pairA = h.pairA.data(); d.pairB = h.pairB.data(); d.levelVTaskStart = h.levelVTaskStart.data();
+  d.vtaskRow = h.vtaskRow.data(); d.vtaskSrcStart = h.vtaskSrcStart.data(); d.vsrcTile = h.vsrcTile.data(); d.vsrcCol = h.vsrcCol.data();
+  d.colPanelStart = h.colPanelStart.data(); d.colPanelTile = h.colPanelTile.data(); d.colPanelRow = h.colPanelRow.data();
+  return d;
+}
+static int cholScheduledOne(const CholSchedule& h, const float* Hg, int n, int ldH, float reg, float* delta, float* gdd) {
+  const CholSchedDev S = devView(h);
+  std::vector<float> tiles(size_t(S.numTiles) * 256 + 16, 0.f), y(S.nPad, 0.f);
+  float* tl = tiles.data();
+  while ((reinterpret_cast<uintptr_t>(tl) & 15) != 0) ++tl; // float4 alignment
+  for (int t = 0; t < S.numTiles; ++t)
+    for (int e = 0; e < 256; ++e) {
+      const int c = e >> 4, r = e & 15, I = S.tileRow[t], J = S.tileCol[t];
+      const int gi = S.perm[16 * I + r], gj = S.perm[16 * J + c];
+      float v;
+      if (gi < 0 || gj < 0) v = (I == J && r == c) ? 1.f : 0.f;
+      else { const int hi = std::max(gi, gj), lo = std::min(gi, gj); v = Hg[size_t(lo) * ldH + hi]; if (gi == gj) v += reg; }
+      tl[size_t(t) * 256 + tileIdx(r, c)] = v;
+    }
+  for (int i = 0; i < S.nPad; ++i) { const int p = S.perm[i]; y[i] = p >= 0 ? Hg[size_t(p) * ldH + n] : 0.f; }
+  int flag = 0;
+  for (int L = 0; L < S.numLevels; ++L) {
+    for (int ci = S.levelColStart[L]; ci < S.levelColStart[L + 1]; ++ci) {
+      const int K = S.levelCols[ci];
+      for (int hl = 0; hl < 16; ++hl) cholDiagTile(tl + size_t(S.diagTile[K]) * 256, y.data() + 16 * K, hl, 0xFFFFu, reg, &flag);
+    }
+    for (int pi = S.levelPanelStart[L]; pi < S.levelPanelStart[L + 1]; ++pi) {
+      float* P = tl + size_t(S.panelTile[pi]) * 256;
+      float rows[16][16];
+      for (int hl = 0; hl < 16; ++hl) cholPanelLoad(P, hl, rows[hl]);
+      for (int hl = 0; hl < 16; ++hl) cholPanelSolveStore(P, tl + size_t(S.panelDiag[pi]) * 256, hl, rows[hl]);
+    }
+    for (int ti = S.levelTaskStart[L]; ti < S.levelTaskStart[L + 1]; ++ti)
+      for (int lane = 0; lane < 32; ++lane) cholUpdateTask(tl, S, ti, lane);
+    for (int vi = S.levelVTaskStart[L]; vi < S.levelVTaskStart[L + 1]; ++vi)
+      for (int hl = 0; hl < 16; ++hl) cholVectorTask(tl, y.data(), S, vi, hl);
+  }
+  for (int L = S.numLevels - 1; L >= 0; --L)
+    for (int ci = S.levelColStart[L]; ci < S.levelColStart[L + 1]; ++ci)
+      for (int hl = 0; hl < 16; ++hl) cholBackwardColumn(tl, y.data(), S, S.levelCols[ci], hl, 0xFFFFu);
+  float gd = 0.f;
+  for (int i = 0; i < S.nPad; ++i) { const int p = S.perm[i]; if (p >= 0) { delta[p] = y[i]; gd += Hg[size_t(p) * ldH + n] * y[i]; } }
+  *gdd = gd;
+  return flag;
 }
 
 extern "C" {
@@ -382,6 +437,15 @@ int mb2_solver_solve(mb2_solver* s, float* params, double* errors, int32_t* iter
   s->history.assign(size_t(f->B) * std::max(maxIt, 1), 0.0);
   std::vector<float> H(size_t(ns + 1) * ldH), delta(ns), orig(n);
   s->totalIterations = 0;
+  int cholMode = o.cholesky_mode;
+  if (cholMode == 0) cholMode = ns >= 48 ? 3 : 1;
+  CholSchedule sched;
+  if (cholMode >= 2) {
+    std::vector<std::vector<int>> cliques(f->plan.units.size());
+    for (const CellDesc& c : f->plan.cells) cliques[c.unit].push_back(int(c.col));
+    const std::string se = buildCholSchedule(ns, cliques, cholMode == 2, sched);
+    if (!se.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, se);
+  }
   for (int b = 0; b < f->B; ++b) {
     float* theta = params + size_t(b) * n;
     std::vector<float> theta0(theta, theta + n);
@@ -391,7 +455,9 @@ int mb2_solver_solve(mb2_solver* s, float* params, double* errors, int32_t* iter
       std::fill(H.begin(), H.end(), 0.f);
       jtjOne(f, b, ns, H.data(), ldH);
       float gdd = 0.f;
-      if (cholDispatch(H.data(), ns, ldH, o.regularization, delta.data(), &gdd) && s->status[b] == 0) s->status[b] = MB2_INSTANCE_CHOLESKY_BREAKDOWN;
+      const int failed = cholMode >= 2 ? cholScheduledOne(sched, H.data(), ns, ldH, o.regularization, delta.data(), &gdd)
+                                        : cholDispatch(H.data(), ns, ldH, o.regularization, delta.data(), &gdd);
+      if (failed && s->status[b] == 0) s->status[b] = MB2_INSTANCE_CHOLESKY_BREAKDOWN;
       if (!o.do_line_search) {
         for (int a = 0; a < ns; ++a) theta[f->plan.enabledList[a]] -= delta[a];
       } else {
@@ -436,3 +502,16 @@ int mb2_solver_get_counters(mb2_solver* s, uint64_t* totalIterations, uint64_t* 
 }
 
 } // extern "C"
+
+// ---- scheduler statistics (test/debug helper) ----
+#include "../../momentum_b200/csrc/ik_chol_sched.h"
+extern "C" int emu_chol_schedule_stats(int n, int numCliques, const int* cliqueStart, const int* cliqueCols, int forceDense, long long* stats) {
+  std::vector<std::vector<int>> cl(numCliques);
+  for (int c = 0; c < numCliques; ++c) cl[c].assign(cliqueCols + cliqueStart[c], cliqueCols + cliqueStart[c + 1]);
+  CholSchedule s;
+  const std::string e = buildCholSchedule(n, cl, forceDense != 0, s);
+  if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
+  stats[0] = s.numTileCols; stats[1] = s.numTiles; stats[2] = s.numLevels; stats[3] = s.tileOps; stats[4] = s.denseTileOps;
+  stats[5] = (long long)s.taskDst.size(); stats[6] = (long long)s.panelTile.size();
+  return MB2_OK;
+}

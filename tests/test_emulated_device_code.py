@@ -83,6 +83,26 @@ def test_solve_humanoid_blocked_cholesky():
     assert np.all(out["status"] == 0)
 
 
+@pytest.mark.parametrize("mode", [ms.CHOLESKY_TILES_DENSE, ms.CHOLESKY_TILES_SPARSE])
+@pytest.mark.parametrize("case", ["humanoid", "chain_state", "subset"])
+def test_solve_tile_scheduled_cholesky(case, mode):
+    """Level-scheduled tile Cholesky (dense pattern and min-degree sparse pattern) vs the oracle's Eigen-style LLT."""
+    enabled = None
+    if case == "humanoid":
+        ch, efs, theta0, _ = humanoid_problem(2, orientation=True)
+        opts = ms.GaussNewtonSolverOptions(min_iterations=1, max_iterations=6, regularization=0.05, cholesky_mode=mode)
+    elif case == "chain_state":  # n = 71: dense-ish pattern (state terms couple every ancestor pair), 5 tile columns
+        ch, efs, theta0, theta_star = chain_problem(J=64, B=2, seed=51, families=("position", "state", "limit"))
+        theta0 = theta_star + 0.1 * theta0
+        opts = ms.GaussNewtonSolverOptions(min_iterations=2, max_iterations=5, regularization=0.05, cholesky_mode=mode)
+    else:
+        ch, efs, theta0, _ = humanoid_problem(2, orientation=True)
+        enabled = np.ones(ch.num_params, bool); enabled[[0, 5, 6, 40, 41, 42, 100, 219]] = False
+        opts = ms.GaussNewtonSolverOptions(min_iterations=1, max_iterations=6, regularization=0.05, cholesky_mode=mode)
+    out, worst = parity.check_solve(ch, efs, theta0, opts, EMU_LIB, enabled=enabled, param_tol=1e-4)
+    assert np.all(out["status"] == 0)
+
+
 def test_ka4_three_joint_ik_with_cholesky_breakdown():
     # inverse_kinematics_test.cpp:38-123 in float: regularization 1e-7 makes LLT hit a zero pivot;
     # the solver must behave like Eigen's early-exit LLT (status flags the breakdown, result still fine).
