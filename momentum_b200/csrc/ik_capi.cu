@@ -81,7 +81,7 @@ struct DeviceSchedule {
   CholSchedDev dev{};
   bool valid{false};
   bool dense{false};
-  DeviceBuffer<int16_t> perm, tileRow, tileCol;
+  DeviceBuffer<int16_t> perm, pos, tileIdTable, tileRow, tileCol;
   DeviceBuffer<int32_t> diagTile, levelColStart, levelCols, levelPanelStart, panelTile, panelDiag, levelTaskStart, taskDst, taskPairStart, pairA, pairB,
       levelVTaskStart, vtaskRow, vtaskSrcStart, vsrcTile, vsrcCol, colPanelStart, colPanelTile, colPanelRow;
 };
@@ -95,7 +95,8 @@ struct mb2_solver_function {
   int targetStride{0}, numWeights{0};
   bool weightsPerInstance{false};
   bool planDirty{true};
-  bool planCompact{false};
+  int planMode{0};        // 0 full columns (API parity), 1 solver: enabled columns in natural order, 2 solver: elimination order + tile schedule
+  bool planSchedDense{false};
   uint64_t planLimitsVersion{~0ull};
   Plan plan;
   int ldJ{32};
@@ -105,9 +106,9 @@ struct mb2_solver_function {
   DeviceBuffer<CellDesc> dCells;
   DeviceBuffer<ContribDesc> dContribs;
   DeviceBuffer<float> dLimitData;
-  DeviceBuffer<int32_t> dEnabledList, dIdentity;
+  DeviceBuffer<int32_t> dEnabledList, dIdentity, dDeviceCols;
   // device data
-  DeviceBuffer<float> dTargets, dWeights, dJ, dTheta, dState, dH;
+  DeviceBuffer<float> dTargets, dWeights, dJ, dTheta, dState, dH, dPacked;
   DeviceBuffer<double> dErrors;
   std::vector<float> hWeights; // shared weights mirror
   std::unique_ptr<DeviceSchedule> sched; // Cholesky schedule of the current (compact) plan
@@ -220,47 +221,63 @@ int uploadWeights(mb2_solver_function* f) {
   return MB2_OK;
 }
 
-int ensureSchedule(mb2_solver_function* f, bool dense) {
-  if (f->sched && f->sched->valid && f->sched->dense == dense) return MB2_OK;
-  auto ds = std::make_unique<DeviceSchedule>();
-  const int ns = f->plan.numCols;
-  std::vector<std::vector<int>> cliques(f->plan.units.size());
-  for (const CellDesc& c : f->plan.cells) cliques[c.unit].push_back(int(c.col));
-  const std::string err = buildCholSchedule(ns, cliques, dense, ds->host);
-  if (!err.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, err);
+int uploadSchedule(mb2_solver_function* f, std::unique_ptr<DeviceSchedule>& ds) {
   cudaStream_t s = f->stream;
   const CholSchedule& h = ds->host;
 #define MB2_UP(field) MB2_CUDA(ds->field.upload(h.field, s)); ds->dev.field = ds->field.p;
-  MB2_UP(perm) MB2_UP(tileRow) MB2_UP(tileCol) MB2_UP(diagTile) MB2_UP(levelColStart) MB2_UP(levelCols) MB2_UP(levelPanelStart) MB2_UP(panelTile)
-  MB2_UP(panelDiag) MB2_UP(levelTaskStart) MB2_UP(taskDst) MB2_UP(taskPairStart) MB2_UP(pairA) MB2_UP(pairB) MB2_UP(levelVTaskStart) MB2_UP(vtaskRow)
-  MB2_UP(vtaskSrcStart) MB2_UP(vsrcTile) MB2_UP(vsrcCol) MB2_UP(colPanelStart) MB2_UP(colPanelTile) MB2_UP(colPanelRow)
+  MB2_UP(perm) MB2_UP(pos) MB2_UP(tileIdTable) MB2_UP(tileRow) MB2_UP(tileCol) MB2_UP(diagTile) MB2_UP(levelColStart) MB2_UP(levelCols)
+  MB2_UP(levelPanelStart) MB2_UP(panelTile) MB2_UP(panelDiag) MB2_UP(levelTaskStart) MB2_UP(taskDst) MB2_UP(taskPairStart) MB2_UP(pairA) MB2_UP(pairB)
+  MB2_UP(levelVTaskStart) MB2_UP(vtaskRow) MB2_UP(vtaskSrcStart) MB2_UP(vsrcTile) MB2_UP(vsrcCol) MB2_UP(colPanelStart) MB2_UP(colPanelTile) MB2_UP(colPanelRow)
 #undef MB2_UP
   ds->dev.n = h.n; ds->dev.nPad = h.nPad; ds->dev.numTileCols = h.numTileCols; ds->dev.numTiles = h.numTiles; ds->dev.numLevels = h.numLevels;
   ds->valid = true;
-  ds->dense = dense;
-  f->sched = std::move(ds);
   return MB2_OK;
 }
 
-// compact = true: device Jacobian holds only the enabled columns, packed (solver path);
-// compact = false: every column at its model-parameter index (getJacobian / getJtJR parity).
-// Both coincide when every parameter is enabled.
-int ensurePlan(mb2_solver_function* f, bool compact) {
+// mode 0: every column at its model-parameter index (getJacobian / getJtJR parity);
+// mode 1: solver, only the enabled columns, ascending (dense Eigen-structured Cholesky);
+// mode 2: solver, enabled columns in the Cholesky elimination order + tile schedule (schedDense: dense pattern).
+// Modes 0 and 1 coincide when every parameter is enabled.
+int ensurePlan(mb2_solver_function* f, int mode, bool schedDense = false) {
   bool allEnabled = true;
   for (uint8_t e : f->enabled) allEnabled = allEnabled && e;
-  if (allEnabled) compact = false;
-  if (!f->planDirty && f->planLimitsVersion == f->ch->limitsVersion && f->planCompact == compact) return MB2_OK;
+  if (allEnabled && mode == 1) mode = 0;
+  if (!f->planDirty && f->planLimitsVersion == f->ch->limitsVersion && f->planMode == mode && (mode != 2 || f->planSchedDense == schedDense)) return MB2_OK;
   MB2_CUDA(cudaSetDevice(f->ch->device));
-  f->planCompact = compact;
-  const std::string err = buildPlan(f->ch->host, f->efs, f->enabled, compact, f->plan);
-  if (!err.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, err);
   cudaStream_t s = f->stream;
+  f->sched.reset();
+  std::string err = buildPlan(f->ch->host, f->efs, f->enabled, mode != 0, f->plan);
+  if (!err.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, err);
+  if (mode == 2) {
+    auto ds = std::make_unique<DeviceSchedule>();
+    const int ns = f->plan.numCols;
+    std::vector<std::vector<int>> cliques(f->plan.units.size());
+    for (const CellDesc& c : f->plan.cells) cliques[c.unit].push_back(int(c.col));
+    err = buildCholSchedule(ns, cliques, schedDense, ds->host);
+    if (!err.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, err);
+    // re-plan with the device columns in elimination order, then express the schedule in those columns
+    std::vector<int32_t> colOrder(ns);
+    for (int i = 0; i < ns; ++i) colOrder[i] = f->plan.enabledList[ds->host.order[i]];
+    err = buildPlan(f->ch->host, f->efs, f->enabled, true, f->plan, &colOrder);
+    if (!err.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, err);
+    relabelScheduleToEliminationOrder(ds->host);
+    ds->dense = schedDense;
+    int rc = uploadSchedule(f, ds);
+    if (rc != MB2_OK) return rc;
+    f->sched = std::move(ds);
+    const size_t stride = packedStride(f->sched->host.numTiles, f->sched->host.nPad);
+    MB2_CUDA(f->dPacked.resize(size_t(f->B) * stride));
+    MB2_CUDA(cudaMemsetAsync(f->dPacked.p, 0, size_t(f->B) * stride * sizeof(float), s)); // structural zeros / fill tiles stay zero
+  }
+  f->planMode = mode;
+  f->planSchedDense = schedDense;
   MB2_CUDA(f->dEfs.upload(f->plan.efs, s));
   MB2_CUDA(f->dUnits.upload(f->plan.units, s));
   MB2_CUDA(f->dCells.upload(f->plan.cells, s));
   MB2_CUDA(f->dContribs.upload(f->plan.contribs, s));
   MB2_CUDA(f->dLimitData.upload(f->plan.limitData, s));
   MB2_CUDA(f->dEnabledList.upload(f->plan.enabledList, s));
+  MB2_CUDA(f->dDeviceCols.upload(f->plan.deviceCols, s));
   std::vector<int32_t> ident(f->ch->host.numParams);
   for (size_t i = 0; i < ident.size(); ++i) ident[i] = int32_t(i);
   MB2_CUDA(f->dIdentity.upload(ident, s));
@@ -276,7 +293,6 @@ int ensurePlan(mb2_solver_function* f, bool compact) {
   if (rc != MB2_OK) return rc;
   rc = uploadWeights(f);
   if (rc != MB2_OK) return rc;
-  f->sched.reset();
   f->planDirty = false;
   f->planLimitsVersion = f->ch->limitsVersion;
   return MB2_OK;
@@ -369,7 +385,7 @@ int resolveJtjMode(const mb2_solver_function* f, int requested, int ns) {
   return ok ? requested : -1;
 }
 
-int runJtJ(mb2_solver_function* f, int mode, int ns, float* H, int ldH, const int32_t* active, cudaStream_t st) {
+int runJtJ(mb2_solver_function* f, int mode, int ns, float* H, int ldH, const int32_t* active, cudaStream_t st, const PackedTarget* packed = nullptr) {
   JtJArgs a{};
   a.batch = f->B;
   a.jacobian = f->dJ.p;
@@ -380,8 +396,13 @@ int runJtJ(mb2_solver_function* f, int mode, int ns, float* H, int ldH, const in
   a.H = H;
   a.ldH = ldH;
   a.active = active;
-  if (mode == MB2_JTJ_FP32_SIMT) { MB2_CUDA(launchJtJSimt(a, st)); }
-  else { MB2_CUDA(launchJtJTensor(a, mode == MB2_JTJ_TF32X3 ? 3 : 1, st)); }
+  if (mode == MB2_JTJ_FP32_SIMT) {
+    MB2_CUDA(launchJtJSimt(a, st));
+    if (packed != nullptr) MB2_CUDA(launchPackNormalEquations(f->B, H, ns, ldH, *packed, active, st));
+  } else {
+    if (packed != nullptr) a.packed = *packed;
+    MB2_CUDA(launchJtJTensor(a, mode == MB2_JTJ_TF32X3 ? 3 : 1, st));
+  }
   return MB2_OK;
 }
 
@@ -638,7 +659,7 @@ int mb2_solver_function_set_enabled_parameters(mb2_solver_function* f, const uin
 
 int mb2_solver_function_get_error(mb2_solver_function* f, const float* params, double* errors) {
   MB2_CHECK(f != nullptr && params && errors, "null argument");
-  int rc = ensurePlan(f, f->planCompact);
+  int rc = ensurePlan(f, f->planMode, f->planSchedDense);
   if (rc != MB2_OK) return rc;
   const size_t n = f->ch->host.numParams;
   MB2_CUDA(cudaMemcpyAsync(f->dTheta.p, params, size_t(f->B) * n * sizeof(float), cudaMemcpyHostToDevice, f->stream));
@@ -650,7 +671,7 @@ int mb2_solver_function_get_error(mb2_solver_function* f, const float* params, d
 
 int mb2_solver_function_get_jacobian(mb2_solver_function* f, const float* params, float* jac, float* residual, double* errors, int32_t* actualRows) {
   MB2_CHECK(f != nullptr && params, "null argument");
-  int rc = ensurePlan(f, false);
+  int rc = ensurePlan(f, 0);
   if (rc != MB2_OK) return rc;
   const size_t n = f->ch->host.numParams;
   const int rows = mb2_solver_function_jacobian_rows(f);
@@ -672,7 +693,7 @@ int mb2_solver_function_get_jacobian(mb2_solver_function* f, const float* params
 
 int mb2_solver_function_get_jtjr(mb2_solver_function* f, const float* params, int32_t jtjMode, float* jtj, float* jtr, double* errors) {
   MB2_CHECK(f != nullptr && params, "null argument");
-  int rc = ensurePlan(f, false);
+  int rc = ensurePlan(f, 0);
   if (rc != MB2_OK) return rc;
   const size_t n = f->ch->host.numParams;
   const int ap = f->plan.actualParameters;
@@ -703,7 +724,7 @@ int mb2_solver_function_get_jtjr(mb2_solver_function* f, const float* params, in
 
 int mb2_solver_function_get_skeleton_state(mb2_solver_function* f, const float* params, float* state) {
   MB2_CHECK(f != nullptr && params && state, "null argument");
-  int rc = ensurePlan(f, f->planCompact);
+  int rc = ensurePlan(f, f->planMode, f->planSchedDense);
   if (rc != MB2_OK) return rc;
   const size_t n = f->ch->host.numParams;
   const size_t sz = size_t(f->B) * f->ch->host.numJoints * 8;
@@ -749,17 +770,35 @@ int mb2_solver_set_profiling(mb2_solver* s, int32_t enabled) {
 int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
   MB2_CHECK(s != nullptr && theta != nullptr, "null argument");
   mb2_solver_function* f = s->fn;
-  int rc = ensurePlan(f, true);
+  const mb2_gauss_newton_options& o = s->opt;
+  // Cholesky path: 0 auto, 1 dense Eigen-structured kernel, 2 tile schedule on the dense pattern, 3 tile schedule on the sparse pattern
+  int numEnabled = 0;
+  for (uint8_t e : f->enabled) numEnabled += e ? 1 : 0;
+  int cholMode = o.cholesky_mode;
+  if (cholMode == 0) cholMode = numEnabled >= 48 ? 3 : 1;
+  int rc = ensurePlan(f, cholMode >= 2 ? 2 : 1, cholMode == 2);
   if (rc != MB2_OK) return rc;
+  bool useSchedule = cholMode >= 2;
+  if (useSchedule && choleskyScheduledSmemBytes(f->plan.numCols, f->sched->host.nPad, f->sched->host.numTiles) > size_t(200 * 1024)) {
+    if (o.cholesky_mode >= 2) return fail(MB2_ERR_UNSUPPORTED, "tile schedule does not fit in shared memory for this system");
+    useSchedule = false; // fall back to the dense kernel (matrix in global memory)
+    rc = ensurePlan(f, 1);
+    if (rc != MB2_OK) return rc;
+  }
   cudaStream_t st = cudaStream ? (cudaStream_t)cudaStream : f->stream;
   const int B = f->B, n = f->ch->host.numParams;
-  const int ns = int(f->plan.enabledList.size());
-  const mb2_gauss_newton_options& o = s->opt;
+  const int ns = f->plan.numCols;
   const int maxIt = int(std::min<uint64_t>(o.max_iterations, 1u << 30));
   const int minIt = int(std::min<uint64_t>(o.min_iterations, 1u << 30));
   MB2_CHECK(ns > 0, "no enabled parameters");
   const int mode = resolveJtjMode(f, o.jtj_mode, ns);
   if (mode < 0) return fail(MB2_ERR_UNSUPPORTED, "tensor-core JtJ does not support this shape");
+  PackedTarget packed{};
+  if (useSchedule) {
+    packed.packed = f->dPacked.p;
+    packed.stride = packedStride(f->sched->host.numTiles, f->sched->host.nPad);
+    packed.sched = f->sched->dev;
+  }
   const int ldH = (ns + 1) | 1;
   MB2_CUDA(s->dH.resize(size_t(B) * (ns + 1) * ldH));
   MB2_CUDA(s->dDelta.resize(size_t(B) * ns));
@@ -770,16 +809,6 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
   MB2_CUDA(s->dStatus.resize(B));
   MB2_CUDA(s->dActiveCount.resize(1));
   const bool lineSearch = o.do_line_search != 0;
-  // Cholesky path: 0 auto, 1 dense Eigen-structured kernel, 2 tile schedule on the dense pattern, 3 tile schedule on the sparse pattern
-  int cholMode = o.cholesky_mode;
-  if (cholMode == 0) cholMode = ns >= 48 ? 3 : 1;
-  bool useSchedule = false;
-  if (cholMode >= 2) {
-    rc = ensureSchedule(f, cholMode == 2);
-    if (rc != MB2_OK) return rc;
-    useSchedule = choleskyScheduledSmemBytes(ns, f->sched->host.nPad, f->sched->host.numTiles) <= size_t(200 * 1024);
-    if (!useSchedule && o.cholesky_mode >= 2) return fail(MB2_ERR_UNSUPPORTED, "tile schedule does not fit in shared memory for this system");
-  }
   if (lineSearch) {
     MB2_CUDA(s->dThetaOrig.resize(size_t(B) * n));
     MB2_CUDA(s->dTrialErrors.resize(B));
@@ -807,7 +836,7 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
     MB2_CUDA(launchSweep(sweepArgs(f, theta, s->dActive.p), true, st));
     recordPhaseStop(s, st);
     recordPhaseStart(s, 1, st);
-    rc = runJtJ(f, mode, ns, s->dH.p, ldH, s->dActive.p, st);
+    rc = runJtJ(f, mode, ns, s->dH.p, ldH, s->dActive.p, st, useSchedule ? &packed : nullptr);
     if (rc != MB2_OK) return rc;
     recordPhaseStop(s, st);
     CholArgs c{};
@@ -816,7 +845,7 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
     c.ns = ns;
     c.ldH = ldH;
     c.regularization = o.regularization;
-    c.cols = f->dEnabledList.p;
+    c.cols = f->dDeviceCols.p;
     c.theta = theta;
     c.ldTheta = n;
     c.delta = s->dDelta.p;
@@ -835,7 +864,7 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
     c.bookkeeping = lineSearch ? 0 : 1;
     c.gradDotDelta = lineSearch ? s->dGradDotDelta.p : nullptr;
     recordPhaseStart(s, 2, st);
-    if (useSchedule) MB2_CUDA(launchCholeskyScheduled(c, f->sched->dev, st));
+    if (useSchedule) MB2_CUDA(launchCholeskyScheduled(c, packed, st));
     else MB2_CUDA(launchCholesky(c, st));
     recordPhaseStop(s, st);
     if (lineSearch) { // gauss_newton_solver.cpp:283-313 / subset_gauss_newton_solver.cpp:119-141
@@ -843,7 +872,7 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
       initLineSearchKernel<<<(B + 127) / 128, 128, 0, st>>>(B, s->dActive.p, s->dSearching.p, s->dScale.p);
       MB2_CUDA(cudaGetLastError());
       for (int step = 0; step < 10; ++step) {
-        MB2_CUDA(launchTrialUpdate(B, s->dThetaOrig.p, n, s->dDelta.p, ns, f->dEnabledList.p, s->dScale.p, theta, s->dSearching.p, st));
+        MB2_CUDA(launchTrialUpdate(B, s->dThetaOrig.p, n, s->dDelta.p, ns, f->dDeviceCols.p, s->dScale.p, theta, s->dSearching.p, st));
         SweepArgs ea = sweepArgs(f, theta, s->dSearching.p);
         ea.errors = s->dTrialErrors.p;
         recordPhaseStart(s, 3, st);

@@ -169,6 +169,10 @@ std::string buildCholSchedule(int n, const std::vector<std::vector<int>>& clique
         if (I == J) out.diagTile[J] = tileId[I][J];
       }
   out.numTiles = int(out.tileRow.size());
+  out.tileIdTable.assign(size_t(T) * T, int16_t(-1));
+  for (int I = 0; I < T; ++I) for (int J = 0; J <= I; ++J) out.tileIdTable[size_t(I) * T + J] = int16_t(tileId[I][J]);
+  out.pos.resize(n);
+  for (int i = 0; i < n; ++i) out.pos[i] = int16_t(pos[i]);
   std::vector<int> level(T, 0);
   std::vector<std::vector<int>> st(T);
   for (int K = 0; K < T; ++K) {
@@ -201,7 +205,9 @@ std::string buildCholSchedule(int n, const std::vector<std::vector<int>>& clique
       for (size_t a = 0; a < st[K].size(); ++a)
         for (size_t b = 0; b <= a; ++b) {
           const int I = st[K][a], J = st[K][b];
-          tasks[tileId[I][J]].push_back({tileId[I][K], tileId[J][K]});
+          // off-diagonal destinations are stored transposed: compute dst^T = L(J,K) L(I,K)^T instead
+          if (I == J) tasks[tileId[I][J]].push_back({tileId[I][K], tileId[J][K]});
+          else tasks[tileId[I][J]].push_back({tileId[J][K], tileId[I][K]});
           out.tileOps++;
         }
     }
@@ -226,7 +232,19 @@ std::string buildCholSchedule(int n, const std::vector<std::vector<int>>& clique
     out.colPanelStart.push_back(int(out.colPanelTile.size()));
   }
   for (int K = 0; K < T; ++K) { const int64_t r = T - 1 - K; out.denseTileOps += r * (r + 1) / 2; }
+  out.order = order;
   return "";
+}
+
+void relabelScheduleToEliminationOrder(CholSchedule& s) {
+  // device column of the i-th eliminated parameter becomes i: perm[slot] = rank, pos[rank] = slot (monotone)
+  std::vector<int> rank(s.n);
+  for (int i = 0; i < s.n; ++i) rank[s.order[i]] = i;
+  for (auto& p : s.perm) if (p >= 0) p = int16_t(rank[p]);
+  std::vector<int16_t> pos(s.n);
+  for (int slot = 0; slot < s.nPad; ++slot) if (s.perm[slot] >= 0) pos[s.perm[slot]] = int16_t(slot);
+  s.pos = pos;
+  for (int i = 0; i < s.n; ++i) s.order[i] = i;
 }
 
 } // namespace mb2

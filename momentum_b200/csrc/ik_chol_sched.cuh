@@ -26,6 +26,8 @@ namespace mb2 {
 struct CholSchedDev {
   int32_t n, nPad, numTileCols, numTiles, numLevels;
   const int16_t* perm;
+  const int16_t* pos;         // [n] device column -> permuted position
+  const int16_t* tileIdTable; // [numTileCols^2]
   const int16_t* tileRow;
   const int16_t* tileCol;
   const int32_t* diagTile;
@@ -51,6 +53,22 @@ struct CholSchedDev {
 
 MB2_HD int tileIdx(int r, int c) { return r * 16 + ((((c >> 2) ^ ((r >> 1) & 3)) << 2) | (c & 3)); }
 MB2_HD int tileGrp(int r, int g) { return r * 16 + ((g ^ ((r >> 1) & 3)) << 2); }
+
+// Tile-packed normal matrix ("packed H"): [numTiles][256] floats in exactly the shared-memory tile layout,
+// followed by the permuted right-hand side [nPad]. Off-diagonal tiles are stored transposed (T[c][r] = H(r,c));
+// diagonal tiles are stored symmetric (both triangles). Structural zeros and padding are written once per plan.
+MB2_HD size_t packedStride(int numTiles, int nPad) { return size_t(numTiles) * 256 + size_t(nPad); }
+// offset of element (pi, pc) (permuted positions, any order) in the packed matrix; -1 if its tile is absent.
+// For a diagonal tile the mirrored twin is returned through *mirror (else -1).
+MB2_HD int packedOffset(const CholSchedDev& S, int pi, int pc, int* mirror) {
+  const int R = pi > pc ? pi : pc, C = pi > pc ? pc : pi;
+  const int I = R >> 4, J = C >> 4, r = R & 15, c = C & 15;
+  const int t = S.tileIdTable[I * S.numTileCols + J];
+  *mirror = -1;
+  if (t < 0) return -1;
+  if (I == J) { if (r != c) *mirror = t * 256 + tileIdx(c, r); return t * 256 + tileIdx(r, c); }
+  return t * 256 + tileIdx(c, r); // transposed storage
+}
 
 MB2_HD void tileLoadRow(const float* tile, int r, float* a) {
 #pragma unroll
@@ -114,11 +132,12 @@ MB2_HD void cholDiagTile(float* tile, float* y16, int hl, unsigned hmask, float 
 #endif
 }
 
-// ---- phase B: X = A(I,K) L(K,K)^-T for one panel tile; lane hl owns row hl. Two steps so that the
-// transposed write-back cannot race with other lanes still reading their rows. ----
-MB2_HD void cholPanelLoad(const float* tile, int hl, float* a) { tileLoadRow(tile, hl, a); }
-MB2_HD void cholPanelSolveStore(float* tile, const float* diag, int hl, float* a) {
-  float x[16];
+// ---- phase B: X = A(I,K) L(K,K)^-T for one panel tile; lane hl owns matrix row hl ----
+// (panel tiles are stored transposed from the start, so a lane reads and writes only its own column)
+MB2_HD void cholPanelSolve(float* tile, const float* diag, int hl) {
+  float a[16], x[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) a[c] = tile[tileIdx(c, hl)];
 #pragma unroll
   for (int c = 0; c < 16; ++c) {
     float d[16];

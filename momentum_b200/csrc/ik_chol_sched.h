@@ -27,6 +27,8 @@ constexpr int kCholTile = 16;
 struct CholSchedule {
   int32_t n{0}, nPad{0}, numTileCols{0}, numTiles{0}, numLevels{0};
   std::vector<int16_t> perm;            // [nPad] permuted position -> device column, -1 = padding
+  std::vector<int16_t> pos;             // [n] device column -> permuted position (inverse of perm)
+  std::vector<int16_t> tileIdTable;     // [numTileCols * numTileCols] tile id of (I,J), I >= J, or -1
   std::vector<int16_t> tileRow, tileCol; // [numTiles] block coordinates (I >= J)
   std::vector<int32_t> diagTile;        // [numTileCols]
   // per level
@@ -36,6 +38,7 @@ struct CholSchedule {
   std::vector<int32_t> levelVTaskStart, vtaskRow, vtaskSrcStart, vsrcTile, vsrcCol; // forward-substitution updates y_I -= L(I,K) y_K
   // per tile column (backward substitution): its panel tiles
   std::vector<int32_t> colPanelStart, colPanelTile, colPanelRow;
+  std::vector<int> order;               // elimination order: order[i] = input column eliminated i-th
   // statistics
   int64_t tileOps{0};      // 16x16x16 multiply-accumulate blocks executed by update tasks
   int64_t denseTileOps{0}; // what a dense factorisation of the same size would execute
@@ -44,5 +47,8 @@ struct CholSchedule {
 // `cliques`: for every Jacobian row group, the device columns it touches (each list is a clique of the
 // pattern). n = number of device columns that enter the normal equations.
 std::string buildCholSchedule(int n, const std::vector<std::vector<int>>& cliques, bool forceDense, CholSchedule& out);
+// After the caller has re-ordered the device columns into elimination order (column i = i-th eliminated parameter),
+// rewrite perm/pos accordingly (pos becomes monotone: lower triangle of JtJ == lower triangle of the permuted system).
+void relabelScheduleToEliminationOrder(CholSchedule& s);
 
 } // namespace mb2

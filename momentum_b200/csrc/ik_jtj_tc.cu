@@ -54,6 +54,7 @@ struct TcParams {
   int n0, n1;     // UMMA N of tile 0 / tile 1 (multiples of 16)
   int tmemCols;   // power of two >= n0 + n1
   int stages;
+  PackedTarget packed; // optional tile-packed output
 };
 
 __device__ __forceinline__ uint32_t smemAddr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -261,10 +262,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
           if (c0 > maxI || c0 >= p.ns) break; // warp-uniform: the rest lies above the diagonal / outside the system
           float v[16];
           tmemLoad16(colBase + (uint32_t)c0, v);
+          if (p.packed.packed == nullptr) {
 #pragma unroll
-          for (int cc = 0; cc < 16; ++cc) {
-            const int c = c0 + cc;
-            if (c < p.ns && c <= i) H[(size_t)c * p.ldH + i] = v[cc];
+            for (int cc = 0; cc < 16; ++cc) {
+              const int c = c0 + cc;
+              if (c < p.ns && c <= i) H[(size_t)c * p.ldH + i] = v[cc];
+            }
+          } else if (i >= 0) {
+            // tile-packed layout for the scheduled Cholesky: device columns are in elimination order, so (i, c), c <= i,
+            // is a lower-triangle element of the permuted system and consecutive lanes fill consecutive floats of a tile row
+            const CholSchedDev& S = p.packed.sched;
+            float* P = p.packed.packed + (size_t)b * p.packed.stride;
+            const int pi = i < p.ns ? S.pos[i] : -1;
+#pragma unroll
+            for (int cc = 0; cc < 16; ++cc) {
+              const int c = c0 + cc;
+              if (c < p.ns && c <= i) {
+                const int pc = S.pos[c];
+                if (pi < 0) P[(size_t)S.numTiles * 256 + pc] = v[cc]; // Jtr row -> permuted right-hand side
+                else {
+                  int mirror;
+                  const int off = packedOffset(S, pi, pc, &mirror);
+                  if (off >= 0) { P[off] = v[cc]; if (mirror >= 0) P[mirror] = v[cc]; }
+                }
+              }
+            }
           }
         }
       }
@@ -350,6 +372,7 @@ cudaError_t launchJtJTensor(const JtJArgs& a, int passes, cudaStream_t stream) {
   p.n0 = sh.n0;
   p.n1 = sh.n1;
   p.tmemCols = sh.tmemCols;
+  p.packed = a.packed;
   const size_t stageBytes = size_t(sh.boxRows) * kRowBytes * (p.passes == 3 ? 2 : 1);
   int stages = int((200 * 1024) / stageBytes);
   if (stages > 6) stages = 6;

@@ -345,7 +345,8 @@ size_t choleskyScheduledSmemBytes(int n, int nPad, int numTiles) {
   return sizeof(float) * (size_t(numTiles) * 256 + size_t(nPad) + 2 * size_t((n + 3) & ~3)) + 16;
 }
 
-__global__ void __launch_bounds__(kSchedThreads, 2) choleskyScheduledKernel(const CholArgs a, const CholSchedDev S) {
+__global__ void __launch_bounds__(kSchedThreads, 2) choleskyScheduledKernel(const CholArgs a, const CholSchedDev S, const float* __restrict__ packedAll,
+                                                                             const size_t packedStrideFloats) {
   extern __shared__ __align__(16) float smemS[];
   const int b = blockIdx.x;
   if (a.active[b] == 0) return;
@@ -357,24 +358,21 @@ __global__ void __launch_bounds__(kSchedThreads, 2) choleskyScheduledKernel(cons
   float* gsub = y + S.nPad;
   float* dsub = gsub + ((n + 3) & ~3);
   int* flags = reinterpret_cast<int*>(dsub + ((n + 3) & ~3));
-  const float* Hg = a.H + size_t(b) * (n + 1) * a.ldH;
   if (tid == 0) flags[0] = 0;
-  // gather the permuted tiles: element (i,j), i >= j, of [JtJ; Jtr] sits at Hg[j*ldH + i]
-  for (int idx = tid; idx < S.numTiles * 256; idx += kSchedThreads) {
-    const int t = idx >> 8, e = idx & 255, c = e >> 4, r = e & 15;
-    const int I = S.tileRow[t], J = S.tileCol[t];
-    const int gi = S.perm[16 * I + r], gj = S.perm[16 * J + c];
-    float v;
-    if (gi < 0 || gj < 0) v = (I == J && r == c) ? 1.f : 0.f; // padding variable: identity
-    else {
-      const int hi = gi > gj ? gi : gj, lo = gi > gj ? gj : gi;
-      v = Hg[size_t(lo) * a.ldH + hi];
-      if (gi == gj) v += a.regularization; // gauss_newton_solver.cpp:248
-    }
-    tiles[size_t(t) * 256 + tileIdx(r, c)] = v;
+  // the tile-packed system is already in shared-memory layout: one linear, fully coalesced copy
+  {
+    const float4* src = reinterpret_cast<const float4*>(packedAll + size_t(b) * packedStrideFloats);
+    float4* dst = reinterpret_cast<float4*>(smemS);
+    const int vecs = (S.numTiles * 256 + S.nPad) >> 2;
+    for (int i = tid; i < vecs; i += kSchedThreads) dst[i] = src[i];
   }
-  for (int i = tid; i < S.nPad; i += kSchedThreads) { const int p = S.perm[i]; y[i] = p >= 0 ? Hg[size_t(p) * a.ldH + n] : 0.f; }
-  for (int i = tid; i < n; i += kSchedThreads) gsub[i] = Hg[size_t(i) * a.ldH + n];
+  __syncthreads();
+  for (int s = tid; s < S.nPad; s += kSchedThreads) {
+    const int K = s >> 4, r = s & 15, p = S.perm[s];
+    float* D = tiles + size_t(S.diagTile[K]) * 256 + tileIdx(r, r);
+    if (p >= 0) { *D += a.regularization; gsub[p] = y[s]; } // gauss_newton_solver.cpp:248
+    else *D = 1.f;                                           // padding variable: identity row/column
+  }
   __syncthreads();
 
   for (int L = 0; L < S.numLevels; ++L) {
@@ -386,11 +384,7 @@ __global__ void __launch_bounds__(kSchedThreads, 2) choleskyScheduledKernel(cons
     __syncthreads();
     // B: panel tiles
     for (int pi = S.levelPanelStart[L] + hw; pi < S.levelPanelStart[L + 1]; pi += kSchedThreads / 16) {
-      float* P = tiles + size_t(S.panelTile[pi]) * 256;
-      float arow[16];
-      cholPanelLoad(P, hl, arow);
-      __syncwarp(hmask);
-      cholPanelSolveStore(P, tiles + size_t(S.panelDiag[pi]) * 256, hl, arow);
+      cholPanelSolve(tiles + size_t(S.panelTile[pi]) * 256, tiles + size_t(S.panelDiag[pi]) * 256, hl);
     }
     __syncthreads();
     // C: update tasks (warp each) and rhs updates (half-warp each)
@@ -407,12 +401,35 @@ __global__ void __launch_bounds__(kSchedThreads, 2) choleskyScheduledKernel(cons
   cholFinish(a, b, n, dsub, gsub, flags[0] != 0);
 }
 
-cudaError_t launchCholeskyScheduled(const CholArgs& a, const CholSchedDev& sched, cudaStream_t stream) {
+// dense column-major lower [JtJ; Jtr] -> tile-packed (element (i,c), i >= c, of the device-column order)
+__global__ void packNormalEquationsKernel(int batch, const float* H, int ns, int ldH, const PackedTarget P, const int32_t* active) {
+  const int b = blockIdx.x;
+  if (active != nullptr && active[b] == 0) return;
+  const float* Hg = H + size_t(b) * (ns + 1) * ldH;
+  float* out = P.packed + size_t(b) * P.stride;
+  const CholSchedDev& S = P.sched;
+  for (int idx = threadIdx.x; idx < ns * (ns + 1); idx += blockDim.x) {
+    const int c = idx / (ns + 1), i = idx - c * (ns + 1);
+    if (i < c) continue;
+    const float v = Hg[size_t(c) * ldH + i];
+    if (i == ns) { out[size_t(S.numTiles) * 256 + S.pos[c]] = v; continue; }
+    int mirror;
+    const int off = packedOffset(S, S.pos[i], S.pos[c], &mirror);
+    if (off >= 0) { out[off] = v; if (mirror >= 0) out[mirror] = v; }
+  }
+}
+cudaError_t launchPackNormalEquations(int batch, const float* H, int ns, int ldH, const PackedTarget& packed, const int32_t* active, cudaStream_t stream) {
+  packNormalEquationsKernel<<<batch, 256, 0, stream>>>(batch, H, ns, ldH, packed, active);
+  return cudaGetLastError();
+}
+
+cudaError_t launchCholeskyScheduled(const CholArgs& a, const PackedTarget& packed, cudaStream_t stream) {
+  const CholSchedDev& sched = packed.sched;
   const size_t smem = choleskyScheduledSmemBytes(a.ns, sched.nPad, sched.numTiles);
   if (smem > size_t(g_maxSmemOptin)) return cudaErrorInvalidConfiguration;
   cudaError_t e = cudaFuncSetAttribute(choleskyScheduledKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
-  choleskyScheduledKernel<<<a.batch, kSchedThreads, smem, stream>>>(a, sched);
+  choleskyScheduledKernel<<<a.batch, kSchedThreads, smem, stream>>>(a, sched, packed.packed, packed.stride);
   return cudaGetLastError();
 }
 

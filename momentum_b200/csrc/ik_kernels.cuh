@@ -21,6 +21,13 @@ struct SweepArgs {           // K1 (FK + residual + Jacobian) and K4 (FK + error
   float* stateOut;           // optional [B][J][8]
 };
 
+// Optional tile-packed form of the normal equations (ik_chol_sched.cuh): produced by K2, consumed by the scheduled K3.
+struct PackedTarget {
+  float* packed;     // [B][stride], nullptr = not requested
+  size_t stride;     // packedStride(numTiles, nPad)
+  CholSchedDev sched;
+};
+
 struct JtJArgs {             // K2
   int32_t batch;
   const float* jacobian;     // [B][numCols + 1][ldJ]; column numCols = residual
@@ -29,6 +36,7 @@ struct JtJArgs {             // K2
   float* H;                  // [B][ns+1][ldH] column-major lower triangle of [JtJ, Jtr]: element (i,j), i>=j, at H[j*ldH + i];
                              // row index ns holds Jtr (H[j*ldH + ns] = (J^T r)_j)
   int32_t ldH;               // >= ns + 1
+  PackedTarget packed;       // when packed.packed != nullptr the tensor kernel writes this layout instead of H
   const int32_t* active;
 };
 
@@ -60,7 +68,9 @@ size_t sweepSmemPerInstance(const FunctionTables& T);
 cudaError_t launchJtJSimt(const JtJArgs& a, cudaStream_t stream);
 cudaError_t launchCholesky(const CholArgs& a, cudaStream_t stream);
 // level-scheduled tile-sparse variant (ik_chol_sched.h); returns cudaErrorInvalidConfiguration when the tiles do not fit in shared memory
-cudaError_t launchCholeskyScheduled(const CholArgs& a, const CholSchedDev& sched, cudaStream_t stream);
+cudaError_t launchCholeskyScheduled(const CholArgs& a, const PackedTarget& packed, cudaStream_t stream);
+// dense column-major H -> tile-packed (used after the SIMT JtJ)
+cudaError_t launchPackNormalEquations(int batch, const float* H, int ns, int ldH, const PackedTarget& packed, const int32_t* active, cudaStream_t stream);
 size_t choleskyScheduledSmemBytes(int n, int nPad, int numTiles);
 cudaError_t initKernelAttributes();
 

@@ -107,7 +107,8 @@ struct CellBuilder {
 };
 } // namespace
 
-std::string buildPlan(const HostCharacter& ch, const std::vector<HostErrorFunction>& efs, const std::vector<uint8_t>& enabled, bool compact, Plan& out) {
+std::string buildPlan(const HostCharacter& ch, const std::vector<HostErrorFunction>& efs, const std::vector<uint8_t>& enabled, bool compact, Plan& out,
+                      const std::vector<int32_t>* columnOrder) {
   out = Plan();
   out.compact = compact;
   const int n = ch.numParams;
@@ -116,8 +117,24 @@ std::string buildPlan(const HostCharacter& ch, const std::vector<HostErrorFuncti
     if (enabled[i]) { out.actualParameters = i + 1; out.enabledList.push_back(i); }
   const std::vector<uint8_t> active = ch.computeActiveJointParams(enabled);
   std::vector<int> colMap(n, -1); // model parameter -> device column
-  if (compact) { for (size_t a = 0; a < out.enabledList.size(); ++a) colMap[out.enabledList[a]] = int(a); out.numCols = int(out.enabledList.size()); }
-  else { for (int i = 0; i < n; ++i) colMap[i] = i; out.numCols = n; }
+  if (compact) {
+    out.deviceCols = out.enabledList;
+    if (columnOrder != nullptr) {
+      if (columnOrder->size() != out.enabledList.size()) return "column order must list every enabled parameter once";
+      out.deviceCols = *columnOrder;
+    }
+    for (size_t a = 0; a < out.deviceCols.size(); ++a) {
+      const int p = out.deviceCols[a];
+      if (p < 0 || p >= n || !enabled[p] || colMap[p] >= 0) return "column order must list every enabled parameter once";
+      colMap[p] = int(a);
+    }
+    out.numCols = int(out.deviceCols.size());
+  } else {
+    for (int i = 0; i < n; ++i) colMap[i] = i;
+    out.numCols = n;
+    out.deviceCols.resize(n);
+    for (int i = 0; i < n; ++i) out.deviceCols[i] = i;
+  }
 
   int row = 0, rec = 0;
   auto flushCells = [&](int unitIndex, CellBuilder& cb) {

@@ -65,13 +65,17 @@ struct Plan {
   std::vector<int32_t> enabledList; // gauss_newton_solver.cpp:57-66
   int32_t numCols{0};   // device Jacobian columns: numParams (full) or enabledList.size() (compact)
   bool compact{false};
+  std::vector<int32_t> deviceCols; // [numCols] model parameter held by each device column
 };
 
 // Builds the plan. `enabled` has numParams entries.
 // compact = true drops the columns of disabled parameters and packs the enabled ones in order (what the solver
 // needs: gauss_newton_solver.cpp:204-209 discards the others anyway); compact = false keeps the reference's
 // full column positions (getJacobian / getJtJR parity).
-std::string buildPlan(const HostCharacter& ch, const std::vector<HostErrorFunction>& efs, const std::vector<uint8_t>& enabled, bool compact, Plan& out);
+// columnOrder (optional, compact only): model parameters in the order the device columns should take (a permutation
+// of the enabled parameters, e.g. the Cholesky elimination order); default = ascending enabled parameters.
+std::string buildPlan(const HostCharacter& ch, const std::vector<HostErrorFunction>& efs, const std::vector<uint8_t>& enabled, bool compact, Plan& out,
+                      const std::vector<int32_t>* columnOrder = nullptr);
 
 // getJacobianSize() of a block (joint_error_function-inl.h:300-302, state_error_function.cpp:394-404,
 // limit_error_function.cpp:1138-1161)

@@ -917,7 +917,7 @@ struct SkeletonSolverFunction {
   SkeletonState<T> state;
   std::vector<T> jpScratch;
   Mat<T> tJacobian;
-  std::vector<T> tResidual;
+  std::vector<T> tResidual, jt_;
 
   explicit SkeletonSolverFunction(const Rig* r) : rig(r) { // skeleton_solver_function.cpp:25-39
     numParameters = actualParameters = r->numParams;
@@ -1002,15 +1002,21 @@ struct SkeletonSolverFunction {
       int rows = 0;
       error += computeJacobianBlock(params, b, tJacobian, 0, tResidual.data(), rows);
       if (rows == 0) continue;
-      for (int j = 0; j < ap; ++j) {
-        for (int i = j; i < ap; ++i) { // lower triangle (selfadjointView<Lower>().rankUpdate)
-          T s = 0;
-          for (int k = 0; k < rows; ++k) s += tJacobian(k, i) * tJacobian(k, j);
-          jtj(i, j) += s;
+      // lower triangle (selfadjointView<Lower>().rankUpdate) as a sequence of rank-1 updates over a
+      // transposed copy of the block: every (i,j) still sums its products in row order k = 0..rows-1,
+      // but the inner loop runs over contiguous memory like Eigen's kernels do (SIMD-friendly baseline).
+      jt_.assign(size_t(rows) * ap, T(0));
+      for (int c = 0; c < ap; ++c) for (int k = 0; k < rows; ++k) jt_[size_t(k) * ap + c] = tJacobian(k, c);
+      for (int k = 0; k < rows; ++k) {
+        const T* row = &jt_[size_t(k) * ap];
+        const T rk = tResidual[k];
+        for (int j = 0; j < ap; ++j) {
+          const T t = row[j];
+          if (t == T(0)) { continue; }
+          T* hcol = &jtj.a[size_t(j) * ap];
+          for (int i = j; i < ap; ++i) hcol[i] += row[i] * t;
+          jtr[j] += t * rk;
         }
-        T s = 0;
-        for (int k = 0; k < rows; ++k) s += tJacobian(k, j) * tResidual[k];
-        jtr[j] += s;
       }
     }
     return error;
@@ -1114,7 +1120,7 @@ struct GaussNewtonSolver {
   double error{0}, lastError{0};
   size_t iteration{0};
   Mat<T> hessian, jacobian;
-  std::vector<T> jtr, residual;
+  std::vector<T> jtr, residual, jt_;
 
   GaussNewtonSolver(const GaussNewtonOptions& o, SkeletonSolverFunction<T>* f) : opt(o), fn(f) {
     activeParameters.assign(f->numParameters, 1); // solver.cpp:27 activeParameters_.flip()
@@ -1142,17 +1148,18 @@ struct GaussNewtonSolver {
       error = fn->getJacobian(parameters.data(), jacobian, residual, rows);
       hessian.resizeAndSetZero(ns, ns);
       jtr.assign(ns, T(0));
-      for (int a = 0; a < ns; ++a) {
-        const int ca = enabled[a];
-        for (int b = 0; b <= a; ++b) {
-          const int cb = enabled[b];
-          T s = 0;
-          for (int k = 0; k < rows; ++k) s += jacobian(k, ca) * jacobian(k, cb);
-          hessian(a, b) = s;
+      jt_.assign(size_t(rows) * ns, T(0)); // transposed, column-compacted copy (see getJtJR)
+      for (int a = 0; a < ns; ++a) for (int k = 0; k < rows; ++k) jt_[size_t(k) * ns + a] = jacobian(k, enabled[a]);
+      for (int k = 0; k < rows; ++k) {
+        const T* row = &jt_[size_t(k) * ns];
+        const T rk = residual[k];
+        for (int b = 0; b < ns; ++b) {
+          const T t = row[b];
+          if (t == T(0)) { continue; }
+          T* hcol = &hessian.a[size_t(b) * ns];
+          for (int a = b; a < ns; ++a) hcol[a] += row[a] * t;
+          jtr[b] += t * rk;
         }
-        T s = 0;
-        for (int k = 0; k < rows; ++k) s += jacobian(k, ca) * residual[k];
-        jtr[a] = s;
       }
     }
     const std::vector<T> gradSubset = jtr;

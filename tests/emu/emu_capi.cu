@@ -169,7 +169,7 @@ static int cholDispatch(float* Hg, int n, int ldH, float reg, float* delta, floa
 static CholSchedDev devView(const CholSchedule& h) {
   CholSchedDev d{};
   d.n = h.n; d.nPad = h.nPad; d.numTileCols = h.numTileCols; d.numTiles = h.numTiles; d.numLevels = h.numLevels;
-  d.perm = h.perm.data(); d.tileRow = h.tileRow.data(); d.tileCol = h.tileCol.data(); d.diagTile = h.diagTile.data();
+  d.perm = h.perm.data(); d.pos = h.pos.data(); d.tileIdTable = h.tileIdTable.data(); d.tileRow = h.tileRow.data(); d.tileCol = h.tileCol.data(); d.diagTile = h.diagTile.data();
   d.levelColStart = h.levelColStart.data(); d.levelCols = h.levelCols.data(); d.levelPanelStart = h.levelPanelStart.data();
   d.panelTile = h.panelTile.data(); d.panelDiag = h.panelDiag.data(); d.levelTaskStart = h.levelTaskStart.data(); d.taskDst = h.taskDst.data();
   d.taskPairStart = h.taskPairStart.data(); d.pairA = h.pairA.data(); d.pairB = h.pairB.data(); d.levelVTaskStart = h.levelVTaskStart.data();
@@ -177,43 +177,50 @@ static CholSchedDev devView(const CholSchedule& h) {
   d.colPanelStart = h.colPanelStart.data(); d.colPanelTile = h.colPanelTile.data(); d.colPanelRow = h.colPanelRow.data();
   return d;
 }
-static int cholScheduledOne(const CholSchedule& h, const float* Hg, int n, int ldH, float reg, float* delta, float* gdd) {
+// dense column-major lower [JtJ; Jtr] (device-column order = elimination order) -> tile-packed; mirrors packNormalEquationsKernel
+static void packOne(const CholSchedule& h, const float* Hg, int ns, int ldH, float* out) {
   const CholSchedDev S = devView(h);
-  std::vector<float> tiles(size_t(S.numTiles) * 256 + 16, 0.f), y(S.nPad, 0.f);
-  float* tl = tiles.data();
-  while ((reinterpret_cast<uintptr_t>(tl) & 15) != 0) ++tl; // float4 alignment
-  for (int t = 0; t < S.numTiles; ++t)
-    for (int e = 0; e < 256; ++e) {
-      const int c = e >> 4, r = e & 15, I = S.tileRow[t], J = S.tileCol[t];
-      const int gi = S.perm[16 * I + r], gj = S.perm[16 * J + c];
-      float v;
-      if (gi < 0 || gj < 0) v = (I == J && r == c) ? 1.f : 0.f;
-      else { const int hi = std::max(gi, gj), lo = std::min(gi, gj); v = Hg[size_t(lo) * ldH + hi]; if (gi == gj) v += reg; }
-      tl[size_t(t) * 256 + tileIdx(r, c)] = v;
+  for (int c = 0; c < ns; ++c)
+    for (int i = c; i <= ns; ++i) {
+      const float v = Hg[size_t(c) * ldH + i];
+      if (i == ns) { out[size_t(S.numTiles) * 256 + S.pos[c]] = v; continue; }
+      int mirror;
+      const int off = packedOffset(S, S.pos[i], S.pos[c], &mirror);
+      if (off >= 0) { out[off] = v; if (mirror >= 0) out[mirror] = v; }
     }
-  for (int i = 0; i < S.nPad; ++i) { const int p = S.perm[i]; y[i] = p >= 0 ? Hg[size_t(p) * ldH + n] : 0.f; }
+}
+// mirrors choleskyScheduledKernel
+static int cholScheduledOne(const CholSchedule& h, const float* packed, int n, float reg, float* delta, float* gdd) {
+  const CholSchedDev S = devView(h);
+  std::vector<float> store(size_t(S.numTiles) * 256 + S.nPad + 16, 0.f);
+  float* tl = store.data();
+  while ((reinterpret_cast<uintptr_t>(tl) & 15) != 0) ++tl; // float4 alignment
+  std::copy(packed, packed + size_t(S.numTiles) * 256 + S.nPad, tl);
+  float* y = tl + size_t(S.numTiles) * 256;
+  std::vector<float> gsub(n, 0.f);
+  for (int s2 = 0; s2 < S.nPad; ++s2) {
+    const int K = s2 >> 4, r = s2 & 15, p = S.perm[s2];
+    float* D = tl + size_t(S.diagTile[K]) * 256 + tileIdx(r, r);
+    if (p >= 0) { *D += reg; gsub[p] = y[s2]; } else *D = 1.f;
+  }
   int flag = 0;
   for (int L = 0; L < S.numLevels; ++L) {
     for (int ci = S.levelColStart[L]; ci < S.levelColStart[L + 1]; ++ci) {
       const int K = S.levelCols[ci];
-      for (int hl = 0; hl < 16; ++hl) cholDiagTile(tl + size_t(S.diagTile[K]) * 256, y.data() + 16 * K, hl, 0xFFFFu, reg, &flag);
+      for (int hl = 0; hl < 16; ++hl) cholDiagTile(tl + size_t(S.diagTile[K]) * 256, y + 16 * K, hl, 0xFFFFu, reg, &flag);
     }
-    for (int pi = S.levelPanelStart[L]; pi < S.levelPanelStart[L + 1]; ++pi) {
-      float* P = tl + size_t(S.panelTile[pi]) * 256;
-      float rows[16][16];
-      for (int hl = 0; hl < 16; ++hl) cholPanelLoad(P, hl, rows[hl]);
-      for (int hl = 0; hl < 16; ++hl) cholPanelSolveStore(P, tl + size_t(S.panelDiag[pi]) * 256, hl, rows[hl]);
-    }
+    for (int pi = S.levelPanelStart[L]; pi < S.levelPanelStart[L + 1]; ++pi)
+      for (int hl = 0; hl < 16; ++hl) cholPanelSolve(tl + size_t(S.panelTile[pi]) * 256, tl + size_t(S.panelDiag[pi]) * 256, hl);
     for (int ti = S.levelTaskStart[L]; ti < S.levelTaskStart[L + 1]; ++ti)
       for (int lane = 0; lane < 32; ++lane) cholUpdateTask(tl, S, ti, lane);
     for (int vi = S.levelVTaskStart[L]; vi < S.levelVTaskStart[L + 1]; ++vi)
-      for (int hl = 0; hl < 16; ++hl) cholVectorTask(tl, y.data(), S, vi, hl);
+      for (int hl = 0; hl < 16; ++hl) cholVectorTask(tl, y, S, vi, hl);
   }
   for (int L = S.numLevels - 1; L >= 0; --L)
     for (int ci = S.levelColStart[L]; ci < S.levelColStart[L + 1]; ++ci)
-      for (int hl = 0; hl < 16; ++hl) cholBackwardColumn(tl, y.data(), S, S.levelCols[ci], hl, 0xFFFFu);
+      for (int hl = 0; hl < 16; ++hl) cholBackwardColumn(tl, y, S, S.levelCols[ci], hl, 0xFFFFu);
   float gd = 0.f;
-  for (int i = 0; i < S.nPad; ++i) { const int p = S.perm[i]; if (p >= 0) { delta[p] = y[i]; gd += Hg[size_t(p) * ldH + n] * y[i]; } }
+  for (int i = 0; i < S.nPad; ++i) { const int p = S.perm[i]; if (p >= 0) { delta[p] = y[i]; gd += gsub[p] * y[i]; } }
   *gdd = gd;
   return flag;
 }
@@ -427,25 +434,35 @@ int mb2_solver_set_enabled_parameters(mb2_solver* s, const uint64_t* bits) { ret
 // emulation of mb2_solver_solve_device's launch sequence, instance by instance
 int mb2_solver_solve(mb2_solver* s, float* params, double* errors, int32_t* iterations, int32_t* status) {
   mb2_solver_function* f = s->fn;
-  const std::string e = plan(f, true);
-  if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
-  const FunctionTables T = tables(f);
-  const int n = T.numParams, ns = int(f->plan.enabledList.size()), ldH = (ns + 1) | 1;
   const auto& o = s->opt;
+  int numEnabled = 0;
+  for (uint8_t e : f->enabled) numEnabled += e ? 1 : 0;
+  int cholMode = o.cholesky_mode;
+  if (cholMode == 0) cholMode = numEnabled >= 48 ? 3 : 1;
+  std::string e = plan(f, true);
+  if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
+  CholSchedule sched;
+  if (cholMode >= 2) { // same two-pass planning as ensurePlan(mode 2) in ik_capi.cu
+    const int ns0 = f->plan.numCols;
+    std::vector<std::vector<int>> cliques(f->plan.units.size());
+    for (const CellDesc& c : f->plan.cells) cliques[c.unit].push_back(int(c.col));
+    e = buildCholSchedule(ns0, cliques, cholMode == 2, sched);
+    if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
+    std::vector<int32_t> colOrder(ns0);
+    for (int i = 0; i < ns0; ++i) colOrder[i] = f->plan.enabledList[sched.order[i]];
+    e = buildPlan(f->ch->host, f->efs, f->enabled, true, f->plan, &colOrder);
+    if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
+    f->J.assign(size_t(f->B) * (f->plan.numCols + 1) * f->ldJ, 0.f);
+    relabelScheduleToEliminationOrder(sched);
+  }
+  const FunctionTables T = tables(f);
+  const int n = T.numParams, ns = f->plan.numCols, ldH = (ns + 1) | 1;
   const int maxIt = int(o.max_iterations), minIt = int(o.min_iterations);
   s->errors.assign(f->B, DBL_MAX); s->iterations.assign(f->B, 0); s->status.assign(f->B, 0);
   s->history.assign(size_t(f->B) * std::max(maxIt, 1), 0.0);
   std::vector<float> H(size_t(ns + 1) * ldH), delta(ns), orig(n);
+  std::vector<float> packed(cholMode >= 2 ? packedStride(sched.numTiles, sched.nPad) : 1, 0.f);
   s->totalIterations = 0;
-  int cholMode = o.cholesky_mode;
-  if (cholMode == 0) cholMode = ns >= 48 ? 3 : 1;
-  CholSchedule sched;
-  if (cholMode >= 2) {
-    std::vector<std::vector<int>> cliques(f->plan.units.size());
-    for (const CellDesc& c : f->plan.cells) cliques[c.unit].push_back(int(c.col));
-    const std::string se = buildCholSchedule(ns, cliques, cholMode == 2, sched);
-    if (!se.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, se);
-  }
   for (int b = 0; b < f->B; ++b) {
     float* theta = params + size_t(b) * n;
     std::vector<float> theta0(theta, theta + n);
@@ -455,16 +472,21 @@ int mb2_solver_solve(mb2_solver* s, float* params, double* errors, int32_t* iter
       std::fill(H.begin(), H.end(), 0.f);
       jtjOne(f, b, ns, H.data(), ldH);
       float gdd = 0.f;
-      const int failed = cholMode >= 2 ? cholScheduledOne(sched, H.data(), ns, ldH, o.regularization, delta.data(), &gdd)
-                                        : cholDispatch(H.data(), ns, ldH, o.regularization, delta.data(), &gdd);
+      int failed;
+      if (cholMode >= 2) {
+        packOne(sched, H.data(), ns, ldH, packed.data()); // structural zeros of `packed` are never written: stay zero across iterations
+        failed = cholScheduledOne(sched, packed.data(), ns, o.regularization, delta.data(), &gdd);
+      } else {
+        failed = cholDispatch(H.data(), ns, ldH, o.regularization, delta.data(), &gdd);
+      }
       if (failed && s->status[b] == 0) s->status[b] = MB2_INSTANCE_CHOLESKY_BREAKDOWN;
       if (!o.do_line_search) {
-        for (int a = 0; a < ns; ++a) theta[f->plan.enabledList[a]] -= delta[a];
+        for (int a = 0; a < ns; ++a) theta[f->plan.deviceCols[a]] -= delta[a];
       } else {
         std::copy(theta, theta + n, orig.begin());
         float scale = 1.f;
         for (int step = 0; step < 10; ++step) {
-          for (int a = 0; a < ns; ++a) { const int c = f->plan.enabledList[a]; theta[c] = orig[c] - scale * delta[a]; }
+          for (int a = 0; a < ns; ++a) { const int c = f->plan.deviceCols[a]; theta[c] = orig[c] - scale * delta[a]; }
           double en;
           sweepOne<false>(f, T, b, theta, &en, nullptr);
           bool accept;

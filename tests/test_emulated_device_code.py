@@ -93,7 +93,7 @@ def test_solve_tile_scheduled_cholesky(case, mode):
         opts = ms.GaussNewtonSolverOptions(min_iterations=1, max_iterations=6, regularization=0.05, cholesky_mode=mode)
     elif case == "chain_state":  # n = 71: dense-ish pattern (state terms couple every ancestor pair), 5 tile columns
         ch, efs, theta0, theta_star = chain_problem(J=64, B=2, seed=51, families=("position", "state", "limit"))
-        theta0 = theta_star + 0.1 * theta0
+        theta0 = theta_star + 0.02 * theta0  # a 64-joint chain is chaotic in float unless started near the targets
         opts = ms.GaussNewtonSolverOptions(min_iterations=2, max_iterations=5, regularization=0.05, cholesky_mode=mode)
     else:
         ch, efs, theta0, _ = humanoid_problem(2, orientation=True)
