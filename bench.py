@@ -207,14 +207,11 @@ def main():
     res = solver.get_results()
     its_per_step = int(res["iterations"].sum())
     total_iter, launches = solver.get_counters()
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    max_ms = float(t.item())
-    its_all = torch.tensor([float(its_per_step), float(res["errors"].sum())], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(its_all, op=dist.ReduceOp.SUM)  # the one collective of the path: aggregate iterations / residual norm
-    value = its_all[0].item() * args.steps / (max_ms * 1e-3)
+    # the one collective of the path: aggregate iterations / residual norm (SUM) and elapsed device time (MAX over ranks)
+    from momentum_b200.distributed import aggregate_solve_stats
+
+    its_total, err_total, max_ms = aggregate_solve_stats(float(its_per_step), float(res["errors"].sum()), total_ms, device="cuda")
+    value = its_total * args.steps / (max_ms * 1e-3)
 
     # ---- per-kernel times for the roofline (profiling mode: events around every launch) ----
     solver.set_profiling(True)
@@ -236,7 +233,7 @@ def main():
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = its_all[0].item() * args.steps / te.item()
+    e2e_value = its_total * args.steps / te.item()
     h2d = int(theta0_pin.numel() * 4 + sum(tp.numel() * 4 for tp in target_pins))
     d2h = int(theta_pin.numel() * 4 + B * (8 + 4 + 4))
 
@@ -257,7 +254,7 @@ def main():
         "config": {"workload": args.workload, "desc": WORKLOADS[args.workload]["desc"], "batch_per_gpu": B, "global_batch": B * world, "iterations_per_solve": ITERS,
                    "rows_m": m_rows, "params_n": n, "parallelism": f"dp{world} (instances sharded, no data-path collective)",
                    "jtj_mode": args.jtj_mode, "cholesky_mode": args.cholesky_mode, "l2": "256 MB buffer written between timed steps (L2 flush)"},
-        "solves_per_sec": value / ITERS,
+        "solves_per_sec": value / ITERS, "aggregate_final_error": err_total,
         "e2e": {"value": e2e_value, "unit": "GN it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -137,7 +137,7 @@ class BatchedSkeletonSolverFunction {
   }
   // getError for every instance (skeleton_solver_function.cpp:64-83)
   std::vector<double> getError(const std::vector<float>& parameters) {
-    std::vector<double> e(size_t(batch()));
+    std::vector<double> e(static_cast<size_t>(batch()), 0.0);
     check(mb2_solver_function_get_error(h_, parameters.data(), e.data()));
     return e;
   }

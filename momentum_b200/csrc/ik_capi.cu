@@ -81,9 +81,7 @@ struct DeviceSchedule {
   CholSchedDev dev{};
   bool valid{false};
   bool dense{false};
-  DeviceBuffer<int16_t> perm, pos, tileIdTable, tileRow, tileCol;
-  DeviceBuffer<int32_t> diagTile, levelColStart, levelCols, levelPanelStart, panelTile, panelDiag, levelTaskStart, taskDst, taskPairStart, pairA, pairB,
-      levelVTaskStart, vtaskRow, vtaskSrcStart, vsrcTile, vsrcCol, colPanelStart, colPanelTile, colPanelRow;
+  DeviceBuffer<int32_t> blob;
 };
 
 struct mb2_solver_function {
@@ -222,14 +220,11 @@ int uploadWeights(mb2_solver_function* f) {
 }
 
 int uploadSchedule(mb2_solver_function* f, std::unique_ptr<DeviceSchedule>& ds) {
-  cudaStream_t s = f->stream;
-  const CholSchedule& h = ds->host;
-#define MB2_UP(field) MB2_CUDA(ds->field.upload(h.field, s)); ds->dev.field = ds->field.p;
-  MB2_UP(perm) MB2_UP(pos) MB2_UP(tileIdTable) MB2_UP(tileRow) MB2_UP(tileCol) MB2_UP(diagTile) MB2_UP(levelColStart) MB2_UP(levelCols)
-  MB2_UP(levelPanelStart) MB2_UP(panelTile) MB2_UP(panelDiag) MB2_UP(levelTaskStart) MB2_UP(taskDst) MB2_UP(taskPairStart) MB2_UP(pairA) MB2_UP(pairB)
-  MB2_UP(levelVTaskStart) MB2_UP(vtaskRow) MB2_UP(vtaskSrcStart) MB2_UP(vsrcTile) MB2_UP(vsrcCol) MB2_UP(colPanelStart) MB2_UP(colPanelTile) MB2_UP(colPanelRow)
-#undef MB2_UP
-  ds->dev.n = h.n; ds->dev.nPad = h.nPad; ds->dev.numTileCols = h.numTileCols; ds->dev.numTiles = h.numTiles; ds->dev.numLevels = h.numLevels;
+  std::vector<int32_t> blob;
+  CholSchedDev hostView;
+  makeScheduleBlob(ds->host, blob, hostView);
+  MB2_CUDA(ds->blob.upload(blob, f->stream));
+  ds->dev = rebaseSchedule(hostView, ds->blob.p);
   ds->valid = true;
   return MB2_OK;
 }
@@ -265,9 +260,9 @@ int ensurePlan(mb2_solver_function* f, int mode, bool schedDense = false) {
     int rc = uploadSchedule(f, ds);
     if (rc != MB2_OK) return rc;
     f->sched = std::move(ds);
-    const size_t stride = packedStride(f->sched->host.numTiles, f->sched->host.nPad);
+    const size_t stride = size_t(f->sched->host.nPad) * slotLd(f->sched->host.nPad);
     MB2_CUDA(f->dPacked.resize(size_t(f->B) * stride));
-    MB2_CUDA(cudaMemsetAsync(f->dPacked.p, 0, size_t(f->B) * stride * sizeof(float), s)); // structural zeros / fill tiles stay zero
+    MB2_CUDA(cudaMemsetAsync(f->dPacked.p, 0, size_t(f->B) * stride * sizeof(float), s)); // padding rows/columns and fill tiles stay zero
   }
   f->planMode = mode;
   f->planSchedDense = schedDense;
@@ -385,7 +380,7 @@ int resolveJtjMode(const mb2_solver_function* f, int requested, int ns) {
   return ok ? requested : -1;
 }
 
-int runJtJ(mb2_solver_function* f, int mode, int ns, float* H, int ldH, const int32_t* active, cudaStream_t st, const PackedTarget* packed = nullptr) {
+int runJtJ(mb2_solver_function* f, int mode, int ns, float* H, int ldH, size_t hStride, const int32_t* active, cudaStream_t st, bool slots = false) {
   JtJArgs a{};
   a.batch = f->B;
   a.jacobian = f->dJ.p;
@@ -395,14 +390,12 @@ int runJtJ(mb2_solver_function* f, int mode, int ns, float* H, int ldH, const in
   a.ns = ns;
   a.H = H;
   a.ldH = ldH;
+  a.hStride = hStride;
+  a.slotOf = slots ? f->sched->dev.pos : nullptr;
+  a.rhsRow = slots ? f->sched->host.nPad : ns;
   a.active = active;
-  if (mode == MB2_JTJ_FP32_SIMT) {
-    MB2_CUDA(launchJtJSimt(a, st));
-    if (packed != nullptr) MB2_CUDA(launchPackNormalEquations(f->B, H, ns, ldH, *packed, active, st));
-  } else {
-    if (packed != nullptr) a.packed = *packed;
-    MB2_CUDA(launchJtJTensor(a, mode == MB2_JTJ_TF32X3 ? 3 : 1, st));
-  }
+  if (mode == MB2_JTJ_FP32_SIMT) { MB2_CUDA(launchJtJSimt(a, st)); }
+  else { MB2_CUDA(launchJtJTensor(a, mode == MB2_JTJ_TF32X3 ? 3 : 1, st)); }
   return MB2_OK;
 }
 
@@ -706,7 +699,7 @@ int mb2_solver_function_get_jtjr(mb2_solver_function* f, const float* params, in
   MB2_CUDA(cudaMemcpyAsync(f->dTheta.p, params, size_t(f->B) * n * sizeof(float), cudaMemcpyHostToDevice, f->stream));
   MB2_CUDA(launchSweep(sweepArgs(f, f->dTheta.p, nullptr), true, f->stream));
   MB2_CUDA(cudaMemsetAsync(f->dH.p, 0, hElems * sizeof(float), f->stream));
-  rc = runJtJ(f, mode, ap, f->dH.p, ldH, nullptr, f->stream);
+  rc = runJtJ(f, mode, ap, f->dH.p, ldH, size_t(ap + 1) * ldH, nullptr, f->stream);
   if (rc != MB2_OK) return rc;
   std::vector<float> h(hElems);
   MB2_CUDA(cudaMemcpyAsync(h.data(), f->dH.p, hElems * sizeof(float), cudaMemcpyDeviceToHost, f->stream));
@@ -779,7 +772,7 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
   int rc = ensurePlan(f, cholMode >= 2 ? 2 : 1, cholMode == 2);
   if (rc != MB2_OK) return rc;
   bool useSchedule = cholMode >= 2;
-  if (useSchedule && choleskyScheduledSmemBytes(f->plan.numCols, f->sched->host.nPad, f->sched->host.numTiles) > size_t(200 * 1024)) {
+  if (useSchedule && choleskyScheduledSmemBytes(f->plan.numCols, f->sched->host.nPad, f->sched->host.numTiles, f->sched->dev.blobInts) > size_t(200 * 1024)) {
     if (o.cholesky_mode >= 2) return fail(MB2_ERR_UNSUPPORTED, "tile schedule does not fit in shared memory for this system");
     useSchedule = false; // fall back to the dense kernel (matrix in global memory)
     rc = ensurePlan(f, 1);
@@ -793,14 +786,12 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
   MB2_CHECK(ns > 0, "no enabled parameters");
   const int mode = resolveJtjMode(f, o.jtj_mode, ns);
   if (mode < 0) return fail(MB2_ERR_UNSUPPORTED, "tensor-core JtJ does not support this shape");
-  PackedTarget packed{};
-  if (useSchedule) {
-    packed.packed = f->dPacked.p;
-    packed.stride = packedStride(f->sched->host.numTiles, f->sched->host.nPad);
-    packed.sched = f->sched->dev;
-  }
-  const int ldH = (ns + 1) | 1;
-  MB2_CUDA(s->dH.resize(size_t(B) * (ns + 1) * ldH));
+  // normal equations: dense column-major [ns+1][ldH] for the dense kernel, or the slot-ordered padded system for the tile schedule
+  const int ldH = useSchedule ? slotLd(f->sched->host.nPad) : ((ns + 1) | 1);
+  const size_t hStride = useSchedule ? size_t(f->sched->host.nPad) * ldH : size_t(ns + 1) * ldH;
+  float* Hbuf = nullptr;
+  if (useSchedule) Hbuf = f->dPacked.p; // zeroed once per plan in ensurePlan
+  else { MB2_CUDA(s->dH.resize(size_t(B) * hStride)); Hbuf = s->dH.p; }
   MB2_CUDA(s->dDelta.resize(size_t(B) * ns));
   MB2_CUDA(s->dTheta0.resize(size_t(B) * n));
   MB2_CUDA(s->dLastErrors.resize(B));
@@ -836,14 +827,15 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
     MB2_CUDA(launchSweep(sweepArgs(f, theta, s->dActive.p), true, st));
     recordPhaseStop(s, st);
     recordPhaseStart(s, 1, st);
-    rc = runJtJ(f, mode, ns, s->dH.p, ldH, s->dActive.p, st, useSchedule ? &packed : nullptr);
+    rc = runJtJ(f, mode, ns, Hbuf, ldH, hStride, s->dActive.p, st, useSchedule);
     if (rc != MB2_OK) return rc;
     recordPhaseStop(s, st);
     CholArgs c{};
     c.batch = B;
-    c.H = s->dH.p;
+    c.H = Hbuf;
     c.ns = ns;
     c.ldH = ldH;
+    c.hStride = hStride;
     c.regularization = o.regularization;
     c.cols = f->dDeviceCols.p;
     c.theta = theta;
@@ -864,7 +856,7 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
     c.bookkeeping = lineSearch ? 0 : 1;
     c.gradDotDelta = lineSearch ? s->dGradDotDelta.p : nullptr;
     recordPhaseStart(s, 2, st);
-    if (useSchedule) MB2_CUDA(launchCholeskyScheduled(c, packed, st));
+    if (useSchedule) MB2_CUDA(launchCholeskyScheduled(c, f->sched->dev, st));
     else MB2_CUDA(launchCholesky(c, st));
     recordPhaseStop(s, st);
     if (lineSearch) { // gauss_newton_solver.cpp:283-313 / subset_gauss_newton_solver.cpp:119-141

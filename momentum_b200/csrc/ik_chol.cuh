@@ -17,9 +17,7 @@
 
 #include "ik_types.h"
 
-#if defined(__CUDACC__)
-#include <vector_types.h>
-#endif
+#include <vector_types.h> // float2 / float4 (CUDA toolkit header, usable from plain C++ too)
 
 namespace mb2 {
 

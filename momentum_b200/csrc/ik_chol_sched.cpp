@@ -1,5 +1,7 @@
 #include "ik_chol_sched.h"
 
+#include "ik_chol_sched.cuh"
+
 #include <algorithm>
 #include <map>
 
@@ -245,6 +247,34 @@ void relabelScheduleToEliminationOrder(CholSchedule& s) {
   for (int slot = 0; slot < s.nPad; ++slot) if (s.perm[slot] >= 0) pos[s.perm[slot]] = int16_t(slot);
   s.pos = pos;
   for (int i = 0; i < s.n; ++i) s.order[i] = i;
+}
+
+} // namespace mb2
+
+namespace mb2 {
+
+void makeScheduleBlob(const CholSchedule& s, std::vector<int32_t>& blob, CholSchedDev& dev) {
+  blob.clear();
+  std::vector<size_t> offs;
+  auto add16 = [&](const std::vector<int16_t>& v) { offs.push_back(blob.size()); for (int16_t x : v) blob.push_back(int32_t(x)); while (blob.size() % 4) blob.push_back(0); };
+  auto add32 = [&](const std::vector<int32_t>& v) { offs.push_back(blob.size()); blob.insert(blob.end(), v.begin(), v.end()); while (blob.size() % 4) blob.push_back(0); };
+  add16(s.perm); add16(s.pos); add16(s.tileIdTable); add16(s.tileRow); add16(s.tileCol);
+  add32(s.diagTile); add32(s.levelColStart); add32(s.levelCols); add32(s.levelPanelStart); add32(s.panelTile); add32(s.panelDiag);
+  add32(s.levelTaskStart); add32(s.taskDst); add32(s.taskPairStart); add32(s.pairA); add32(s.pairB); add32(s.levelVTaskStart); add32(s.vtaskRow);
+  add32(s.vtaskSrcStart); add32(s.vsrcTile); add32(s.vsrcCol); add32(s.colPanelStart); add32(s.colPanelTile); add32(s.colPanelRow);
+  if (blob.empty()) blob.push_back(0);
+  dev = CholSchedDev();
+  dev.n = s.n; dev.nPad = s.nPad; dev.numTileCols = s.numTileCols; dev.numTiles = s.numTiles; dev.numLevels = s.numLevels;
+  const int32_t* b = blob.data();
+  dev.blob = b;
+  dev.blobInts = int32_t(blob.size());
+  int k = 0;
+  dev.perm = b + offs[k++]; dev.pos = b + offs[k++]; dev.tileIdTable = b + offs[k++]; dev.tileRow = b + offs[k++]; dev.tileCol = b + offs[k++];
+  dev.diagTile = b + offs[k++]; dev.levelColStart = b + offs[k++]; dev.levelCols = b + offs[k++]; dev.levelPanelStart = b + offs[k++];
+  dev.panelTile = b + offs[k++]; dev.panelDiag = b + offs[k++]; dev.levelTaskStart = b + offs[k++]; dev.taskDst = b + offs[k++];
+  dev.taskPairStart = b + offs[k++]; dev.pairA = b + offs[k++]; dev.pairB = b + offs[k++]; dev.levelVTaskStart = b + offs[k++]; dev.vtaskRow = b + offs[k++];
+  dev.vtaskSrcStart = b + offs[k++]; dev.vsrcTile = b + offs[k++]; dev.vsrcCol = b + offs[k++]; dev.colPanelStart = b + offs[k++];
+  dev.colPanelTile = b + offs[k++]; dev.colPanelRow = b + offs[k++];
 }
 
 } // namespace mb2

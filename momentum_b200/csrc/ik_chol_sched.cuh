@@ -17,19 +17,20 @@
 
 #include "ik_types.h"
 
-#if defined(__CUDACC__)
-#include <vector_types.h>
-#endif
+#include <vector_types.h> // float2 / float4 (CUDA toolkit header, usable from plain C++ too)
 
 namespace mb2 {
 
 struct CholSchedDev {
   int32_t n, nPad, numTileCols, numTiles, numLevels;
-  const int16_t* perm;
-  const int16_t* pos;         // [n] device column -> permuted position
-  const int16_t* tileIdTable; // [numTileCols^2]
-  const int16_t* tileRow;
-  const int16_t* tileCol;
+  // every table below lives in one contiguous int32 blob (copied to shared memory by the kernels)
+  const int32_t* blob;
+  int32_t blobInts;
+  const int32_t* perm;        // [nPad] slot -> device column, -1 = padding
+  const int32_t* pos;         // [n] device column -> slot (monotone: device columns are in elimination order)
+  const int32_t* tileIdTable; // [numTileCols^2]
+  const int32_t* tileRow;
+  const int32_t* tileCol;
   const int32_t* diagTile;
   const int32_t* levelColStart;
   const int32_t* levelCols;
@@ -50,25 +51,26 @@ struct CholSchedDev {
   const int32_t* colPanelTile;
   const int32_t* colPanelRow;
 };
+// view of the same schedule with every table pointer moved to a copy of the blob at `newBlob`
+MB2_HD CholSchedDev rebaseSchedule(const CholSchedDev& S, const int32_t* newBlob) {
+  CholSchedDev R = S;
+  const long d = newBlob - S.blob;
+  R.blob = newBlob;
+  R.perm += d; R.pos += d; R.tileIdTable += d; R.tileRow += d; R.tileCol += d; R.diagTile += d; R.levelColStart += d; R.levelCols += d;
+  R.levelPanelStart += d; R.panelTile += d; R.panelDiag += d; R.levelTaskStart += d; R.taskDst += d; R.taskPairStart += d; R.pairA += d; R.pairB += d;
+  R.levelVTaskStart += d; R.vtaskRow += d; R.vtaskSrcStart += d; R.vsrcTile += d; R.vsrcCol += d; R.colPanelStart += d; R.colPanelTile += d;
+  R.colPanelRow += d;
+  return R;
+}
+
+// Slot-ordered normal equations ("Hs"): column-major, (nPad + 1) rows x nPad columns with leading dimension ldHs (a
+// multiple of 16 floats): element (si, sc), si >= sc, of the permuted+padded system at Hs[sc*ldHs + si]; row nPad holds the
+// permuted J^T r. Only structurally non-zero entries are ever written (the buffer is zeroed once per plan), so a tile
+// (I,J) is sixteen 64-byte segments that the scheduled Cholesky copies with coalesced loads.
+MB2_HD int slotLd(int nPad) { return nPad + 16; }
 
 MB2_HD int tileIdx(int r, int c) { return r * 16 + ((((c >> 2) ^ ((r >> 1) & 3)) << 2) | (c & 3)); }
 MB2_HD int tileGrp(int r, int g) { return r * 16 + ((g ^ ((r >> 1) & 3)) << 2); }
-
-// Tile-packed normal matrix ("packed H"): [numTiles][256] floats in exactly the shared-memory tile layout,
-// followed by the permuted right-hand side [nPad]. Off-diagonal tiles are stored transposed (T[c][r] = H(r,c));
-// diagonal tiles are stored symmetric (both triangles). Structural zeros and padding are written once per plan.
-MB2_HD size_t packedStride(int numTiles, int nPad) { return size_t(numTiles) * 256 + size_t(nPad); }
-// offset of element (pi, pc) (permuted positions, any order) in the packed matrix; -1 if its tile is absent.
-// For a diagonal tile the mirrored twin is returned through *mirror (else -1).
-MB2_HD int packedOffset(const CholSchedDev& S, int pi, int pc, int* mirror) {
-  const int R = pi > pc ? pi : pc, C = pi > pc ? pc : pi;
-  const int I = R >> 4, J = C >> 4, r = R & 15, c = C & 15;
-  const int t = S.tileIdTable[I * S.numTileCols + J];
-  *mirror = -1;
-  if (t < 0) return -1;
-  if (I == J) { if (r != c) *mirror = t * 256 + tileIdx(c, r); return t * 256 + tileIdx(r, c); }
-  return t * 256 + tileIdx(c, r); // transposed storage
-}
 
 MB2_HD void tileLoadRow(const float* tile, int r, float* a) {
 #pragma unroll

@@ -51,4 +51,8 @@ std::string buildCholSchedule(int n, const std::vector<std::vector<int>>& clique
 // rewrite perm/pos accordingly (pos becomes monotone: lower triangle of JtJ == lower triangle of the permuted system).
 void relabelScheduleToEliminationOrder(CholSchedule& s);
 
+struct CholSchedDev;
+// Concatenates every table into one int32 blob; `dev` gets pointers into blob.data() (rebase them after uploading).
+void makeScheduleBlob(const CholSchedule& s, std::vector<int32_t>& blob, CholSchedDev& dev);
+
 } // namespace mb2

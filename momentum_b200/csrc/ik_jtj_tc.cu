@@ -54,7 +54,9 @@ struct TcParams {
   int n0, n1;     // UMMA N of tile 0 / tile 1 (multiples of 16)
   int tmemCols;   // power of two >= n0 + n1
   int stages;
-  PackedTarget packed; // optional tile-packed output
+  size_t hStride;
+  const int32_t* slotOf; // optional slot mapping (see JtJArgs)
+  int rhsRow;
 };
 
 __device__ __forceinline__ uint32_t smemAddr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -249,43 +251,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
     uint32_t eph = 0;
     for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
       if (p.active != nullptr && p.active[b] == 0) continue;
-      float* H = p.H + (size_t)b * (p.ns + 1) * p.ldH;
+      float* H = p.H + (size_t)b * p.hStride;
       mbarWait(tmemFullBar, eph);
       tcFenceAfter();
       for (int t = 0; t < p.mTiles; ++t) {
         const int row = t * 128 + q * 32 + lane;                 // row of [J r]^T [J r]
         const int i = row < p.ns ? row : (row == p.numCols ? p.ns : -1); // index in the (ns+1) system; -1: not wanted
         const int maxI = __reduce_max_sync(0xffffffffu, i);
+        const int si = (p.slotOf != nullptr && i >= 0) ? (i < p.ns ? p.slotOf[i] : p.rhsRow) : 0; // slot of this lane's row
         const int nT = t == 0 ? p.n0 : p.n1;
         const uint32_t colBase = tmemBase + ((uint32_t)(q * 32) << 16) + (t == 0 ? 0u : (uint32_t)p.n0);
         for (int c0 = 0; c0 < nT; c0 += 16) {
           if (c0 > maxI || c0 >= p.ns) break; // warp-uniform: the rest lies above the diagonal / outside the system
           float v[16];
           tmemLoad16(colBase + (uint32_t)c0, v);
-          if (p.packed.packed == nullptr) {
+          if (p.slotOf == nullptr) {
 #pragma unroll
             for (int cc = 0; cc < 16; ++cc) {
               const int c = c0 + cc;
               if (c < p.ns && c <= i) H[(size_t)c * p.ldH + i] = v[cc];
             }
-          } else if (i >= 0) {
-            // tile-packed layout for the scheduled Cholesky: device columns are in elimination order, so (i, c), c <= i,
-            // is a lower-triangle element of the permuted system and consecutive lanes fill consecutive floats of a tile row
-            const CholSchedDev& S = p.packed.sched;
-            float* P = p.packed.packed + (size_t)b * p.packed.stride;
-            const int pi = i < p.ns ? S.pos[i] : -1;
+          } else {
+            // (every lane takes part in the shuffles; rows that are not wanted have i = -1 and never pass c <= i)
+            // slot-ordered output: device columns are in elimination order, so (i, c), c <= i, stays in the lower triangle and
+            // consecutive lanes (rows) write consecutive floats except across padding gaps
+            const int myCol = c0 + lane < p.ns ? p.slotOf[c0 + lane] : 0; // lane l fetches the slot of column c0 + l once
 #pragma unroll
             for (int cc = 0; cc < 16; ++cc) {
               const int c = c0 + cc;
-              if (c < p.ns && c <= i) {
-                const int pc = S.pos[c];
-                if (pi < 0) P[(size_t)S.numTiles * 256 + pc] = v[cc]; // Jtr row -> permuted right-hand side
-                else {
-                  int mirror;
-                  const int off = packedOffset(S, pi, pc, &mirror);
-                  if (off >= 0) { P[off] = v[cc]; if (mirror >= 0) P[mirror] = v[cc]; }
-                }
-              }
+              const int sc = __shfl_sync(0xffffffffu, myCol, cc);
+              if (c < p.ns && c <= i) H[(size_t)sc * p.ldH + si] = v[cc];
             }
           }
         }
@@ -372,7 +367,9 @@ cudaError_t launchJtJTensor(const JtJArgs& a, int passes, cudaStream_t stream) {
   p.n0 = sh.n0;
   p.n1 = sh.n1;
   p.tmemCols = sh.tmemCols;
-  p.packed = a.packed;
+  p.hStride = a.hStride;
+  p.slotOf = a.slotOf;
+  p.rhsRow = a.rhsRow;
   const size_t stageBytes = size_t(sh.boxRows) * kRowBytes * (p.passes == 3 ? 2 : 1);
   int stages = int((200 * 1024) / stageBytes);
   if (stages > 6) stages = 6;

@@ -154,17 +154,23 @@ __global__ void __launch_bounds__(256) jtjSimtKernel(const JtJArgs a) {
       for (int kk = 0; kk < kJtjKc; ++kk) gacc = fmaf(As[threadIdx.x][kk], rs[kk], gacc);
     __syncthreads();
   }
-  float* H = a.H + size_t(b) * (a.ns + 1) * a.ldH;
+  float* H = a.H + size_t(b) * a.hStride;
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int gi = ti * kJtjTile + ty * 4 + i, gj = tj * kJtjTile + tx * 4 + j;
-      if (gi < a.ns && gj <= gi) H[size_t(gj) * a.ldH + gi] = acc[i][j];
+      if (gi < a.ns && gj <= gi) {
+        if (a.slotOf == nullptr) H[size_t(gj) * a.ldH + gi] = acc[i][j];
+        else H[size_t(a.slotOf[gj]) * a.ldH + a.slotOf[gi]] = acc[i][j];
+      }
     }
   if (diag && threadIdx.x < kJtjTile) {
     const int gi = ti * kJtjTile + threadIdx.x;
-    if (gi < a.ns) H[size_t(gi) * a.ldH + a.ns] = gacc;
+    if (gi < a.ns) {
+      if (a.slotOf == nullptr) H[size_t(gi) * a.ldH + a.ns] = gacc;
+      else H[size_t(a.slotOf[gi]) * a.ldH + a.rhsRow] = gacc;
+    }
   }
 }
 
@@ -224,7 +230,7 @@ __global__ void __launch_bounds__(kCholThreads) choleskyKernel(const CholArgs a,
   if (a.active[b] == 0) return;
   const int n = a.ns;
   const int tid = threadIdx.x;
-  float* Hg = a.H + size_t(b) * (n + 1) * a.ldH;
+  float* Hg = a.H + size_t(b) * a.hStride;
   CholCtx ctx;
   ctx.n = n;
   int ldp = ((n + 1 + 3) & ~3) + 4;
@@ -341,12 +347,11 @@ cudaError_t launchCholesky(const CholArgs& a, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------------
 constexpr int kSchedThreads = 256;
 
-size_t choleskyScheduledSmemBytes(int n, int nPad, int numTiles) {
-  return sizeof(float) * (size_t(numTiles) * 256 + size_t(nPad) + 2 * size_t((n + 3) & ~3)) + 16;
+size_t choleskyScheduledSmemBytes(int n, int nPad, int numTiles, int blobInts) {
+  return sizeof(float) * (size_t(numTiles) * 256 + size_t(nPad) + 2 * size_t((n + 3) & ~3)) + sizeof(int32_t) * size_t((blobInts + 3) & ~3) + 16;
 }
 
-__global__ void __launch_bounds__(kSchedThreads, 2) choleskyScheduledKernel(const CholArgs a, const CholSchedDev S, const float* __restrict__ packedAll,
-                                                                             const size_t packedStrideFloats) {
+__global__ void __launch_bounds__(kSchedThreads, 2) choleskyScheduledKernel(const CholArgs a, const CholSchedDev Sg) {
   extern __shared__ __align__(16) float smemS[];
   const int b = blockIdx.x;
   if (a.active[b] == 0) return;
@@ -354,24 +359,34 @@ __global__ void __launch_bounds__(kSchedThreads, 2) choleskyScheduledKernel(cons
   const int warp = tid >> 5, lane = tid & 31, hw = tid >> 4, hl = tid & 15;
   const unsigned hmask = 0xFFFFu << (16 * ((tid >> 4) & 1));
   float* tiles = smemS;
-  float* y = tiles + size_t(S.numTiles) * 256;
-  float* gsub = y + S.nPad;
+  float* y = tiles + size_t(Sg.numTiles) * 256;
+  float* gsub = y + Sg.nPad;
   float* dsub = gsub + ((n + 3) & ~3);
-  int* flags = reinterpret_cast<int*>(dsub + ((n + 3) & ~3));
+  int32_t* blob = reinterpret_cast<int32_t*>(dsub + ((n + 3) & ~3));
+  int* flags = reinterpret_cast<int*>(blob + ((Sg.blobInts + 3) & ~3));
+  // the schedule (a few KB of int32 tables) is read many times per level: stage it in shared memory once
+  for (int i = tid; i < Sg.blobInts; i += kSchedThreads) blob[i] = Sg.blob[i];
   if (tid == 0) flags[0] = 0;
-  // the tile-packed system is already in shared-memory layout: one linear, fully coalesced copy
-  {
-    const float4* src = reinterpret_cast<const float4*>(packedAll + size_t(b) * packedStrideFloats);
-    float4* dst = reinterpret_cast<float4*>(smemS);
-    const int vecs = (S.numTiles * 256 + S.nPad) >> 2;
-    for (int i = tid; i < vecs; i += kSchedThreads) dst[i] = src[i];
-  }
   __syncthreads();
+  const CholSchedDev S = rebaseSchedule(Sg, blob);
+  // gather the stored tiles from the slot-ordered system: tile (I,J) = 16 segments of 64 bytes
+  const float* Hs = a.H + size_t(b) * a.hStride;
+  for (int idx = tid; idx < S.numTiles * 256; idx += kSchedThreads) {
+    const int t = idx >> 8, e = idx & 255, c = e >> 4, r = e & 15;
+    const int I = S.tileRow[t], J = S.tileCol[t];
+    if (I != J) tiles[idx - e + tileIdx(c, r)] = Hs[size_t(16 * J + c) * a.ldH + 16 * I + r]; // stored transposed: T[c][r] = H(r,c)
+    else {
+      const int lo = r < c ? r : c, hi = r < c ? c : r;
+      float v = Hs[size_t(16 * J + lo) * a.ldH + 16 * I + hi];                                 // symmetric fill of the diagonal tile
+      if (r == c) { const int p = S.perm[16 * I + r]; v = p >= 0 ? v + a.regularization : 1.f; } // damping (gauss_newton_solver.cpp:248) / padding
+      tiles[idx - e + tileIdx(c, r)] = v;
+    }
+  }
   for (int s = tid; s < S.nPad; s += kSchedThreads) {
-    const int K = s >> 4, r = s & 15, p = S.perm[s];
-    float* D = tiles + size_t(S.diagTile[K]) * 256 + tileIdx(r, r);
-    if (p >= 0) { *D += a.regularization; gsub[p] = y[s]; } // gauss_newton_solver.cpp:248
-    else *D = 1.f;                                           // padding variable: identity row/column
+    const int p = S.perm[s];
+    const float g = p >= 0 ? Hs[size_t(s) * a.ldH + S.nPad] : 0.f;
+    y[s] = g;
+    if (p >= 0) gsub[p] = g;
   }
   __syncthreads();
 
@@ -401,35 +416,12 @@ __global__ void __launch_bounds__(kSchedThreads, 2) choleskyScheduledKernel(cons
   cholFinish(a, b, n, dsub, gsub, flags[0] != 0);
 }
 
-// dense column-major lower [JtJ; Jtr] -> tile-packed (element (i,c), i >= c, of the device-column order)
-__global__ void packNormalEquationsKernel(int batch, const float* H, int ns, int ldH, const PackedTarget P, const int32_t* active) {
-  const int b = blockIdx.x;
-  if (active != nullptr && active[b] == 0) return;
-  const float* Hg = H + size_t(b) * (ns + 1) * ldH;
-  float* out = P.packed + size_t(b) * P.stride;
-  const CholSchedDev& S = P.sched;
-  for (int idx = threadIdx.x; idx < ns * (ns + 1); idx += blockDim.x) {
-    const int c = idx / (ns + 1), i = idx - c * (ns + 1);
-    if (i < c) continue;
-    const float v = Hg[size_t(c) * ldH + i];
-    if (i == ns) { out[size_t(S.numTiles) * 256 + S.pos[c]] = v; continue; }
-    int mirror;
-    const int off = packedOffset(S, S.pos[i], S.pos[c], &mirror);
-    if (off >= 0) { out[off] = v; if (mirror >= 0) out[mirror] = v; }
-  }
-}
-cudaError_t launchPackNormalEquations(int batch, const float* H, int ns, int ldH, const PackedTarget& packed, const int32_t* active, cudaStream_t stream) {
-  packNormalEquationsKernel<<<batch, 256, 0, stream>>>(batch, H, ns, ldH, packed, active);
-  return cudaGetLastError();
-}
-
-cudaError_t launchCholeskyScheduled(const CholArgs& a, const PackedTarget& packed, cudaStream_t stream) {
-  const CholSchedDev& sched = packed.sched;
-  const size_t smem = choleskyScheduledSmemBytes(a.ns, sched.nPad, sched.numTiles);
+cudaError_t launchCholeskyScheduled(const CholArgs& a, const CholSchedDev& sched, cudaStream_t stream) {
+  const size_t smem = choleskyScheduledSmemBytes(a.ns, sched.nPad, sched.numTiles, sched.blobInts);
   if (smem > size_t(g_maxSmemOptin)) return cudaErrorInvalidConfiguration;
   cudaError_t e = cudaFuncSetAttribute(choleskyScheduledKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
-  choleskyScheduledKernel<<<a.batch, kSchedThreads, smem, stream>>>(a, sched, packed.packed, packed.stride);
+  choleskyScheduledKernel<<<a.batch, kSchedThreads, smem, stream>>>(a, sched);
   return cudaGetLastError();
 }
 

@@ -21,13 +21,6 @@ struct SweepArgs {           // K1 (FK + residual + Jacobian) and K4 (FK + error
   float* stateOut;           // optional [B][J][8]
 };
 
-// Optional tile-packed form of the normal equations (ik_chol_sched.cuh): produced by K2, consumed by the scheduled K3.
-struct PackedTarget {
-  float* packed;     // [B][stride], nullptr = not requested
-  size_t stride;     // packedStride(numTiles, nPad)
-  CholSchedDev sched;
-};
-
 struct JtJArgs {             // K2
   int32_t batch;
   const float* jacobian;     // [B][numCols + 1][ldJ]; column numCols = residual
@@ -36,13 +29,17 @@ struct JtJArgs {             // K2
   float* H;                  // [B][ns+1][ldH] column-major lower triangle of [JtJ, Jtr]: element (i,j), i>=j, at H[j*ldH + i];
                              // row index ns holds Jtr (H[j*ldH + ns] = (J^T r)_j)
   int32_t ldH;               // >= ns + 1
-  PackedTarget packed;       // when packed.packed != nullptr the tensor kernel writes this layout instead of H
+  size_t hStride;            // floats per instance in H
+  const int32_t* slotOf;     // optional [ns]: write element (i,j) at the slots (slotOf[i], slotOf[j]) of the padded, elimination-ordered
+                             // system instead (ik_chol_sched.cuh "Hs"); Jtr then goes to row rhsRow
+  int32_t rhsRow;
   const int32_t* active;
 };
 
 struct CholArgs {            // K3: damped Cholesky + solve + update + SolverT bookkeeping
   int32_t batch;
   float* H;                  // [B][ns+1][ldH] column-major lower [JtJ; Jtr] (as written by K2)
+  size_t hStride;            // floats per instance in H
   int32_t ns, ldH;
   float regularization;
   const int32_t* cols;       // [ns] subset -> full parameter index
@@ -68,10 +65,9 @@ size_t sweepSmemPerInstance(const FunctionTables& T);
 cudaError_t launchJtJSimt(const JtJArgs& a, cudaStream_t stream);
 cudaError_t launchCholesky(const CholArgs& a, cudaStream_t stream);
 // level-scheduled tile-sparse variant (ik_chol_sched.h); returns cudaErrorInvalidConfiguration when the tiles do not fit in shared memory
-cudaError_t launchCholeskyScheduled(const CholArgs& a, const PackedTarget& packed, cudaStream_t stream);
-// dense column-major H -> tile-packed (used after the SIMT JtJ)
-cudaError_t launchPackNormalEquations(int batch, const float* H, int ns, int ldH, const PackedTarget& packed, const int32_t* active, cudaStream_t stream);
-size_t choleskyScheduledSmemBytes(int n, int nPad, int numTiles);
+// `a.H` is the slot-ordered system Hs (ld = a.ldH, a.hStride floats per instance)
+cudaError_t launchCholeskyScheduled(const CholArgs& a, const CholSchedDev& sched, cudaStream_t stream);
+size_t choleskyScheduledSmemBytes(int n, int nPad, int numTiles, int blobInts);
 cudaError_t initKernelAttributes();
 
 // line-search helpers

@@ -103,7 +103,7 @@ static void sweepOne(mb2_solver_function* f, const FunctionTables& T, int b, con
   *errOut = kJacobian ? lane[0] : (double)(float)lane[0];
 }
 
-static void jtjOne(const mb2_solver_function* f, int b, int ns, float* H, int ldH) {
+static void jtjOne(const mb2_solver_function* f, int b, int ns, float* H, int ldH, const int32_t* slotOf = nullptr, int rhsRow = 0) {
   const int nc = f->plan.numCols;
   const float* J = f->J.data() + size_t(b) * (nc + 1) * f->ldJ;
   const float* r = J + size_t(nc) * f->ldJ;
@@ -112,11 +112,11 @@ static void jtjOne(const mb2_solver_function* f, int b, int ns, float* H, int ld
     for (int j = 0; j <= i; ++j) {
       float s = 0.f;
       for (int k = 0; k < K; ++k) s = fmaf(J[size_t(i) * f->ldJ + k], J[size_t(j) * f->ldJ + k], s);
-      H[size_t(j) * ldH + i] = s; // column-major lower
+      if (slotOf) H[size_t(slotOf[j]) * ldH + slotOf[i]] = s; else H[size_t(j) * ldH + i] = s; // column-major lower
     }
     float g = 0.f;
     for (int k = 0; k < K; ++k) g = fmaf(J[size_t(i) * f->ldJ + k], r[k], g);
-    H[size_t(i) * ldH + ns] = g;
+    if (slotOf) H[size_t(slotOf[i]) * ldH + rhsRow] = g; else H[size_t(i) * ldH + ns] = g;
   }
 }
 
@@ -166,42 +166,28 @@ static int cholDispatch(float* Hg, int n, int ldH, float reg, float* delta, floa
 }
 
 // emulation of choleskyScheduledKernel for one instance: phases in the same order, half-warps/warps in sequence
-static CholSchedDev devView(const CholSchedule& h) {
-  CholSchedDev d{};
-  d.n = h.n; d.nPad = h.nPad; d.numTileCols = h.numTileCols; d.numTiles = h.numTiles; d.numLevels = h.numLevels;
-  d.perm = h.perm.data(); d.pos = h.pos.data(); d.tileIdTable = h.tileIdTable.data(); d.tileRow = h.tileRow.data(); d.tileCol = h.tileCol.data(); d.diagTile = h.diagTile.data();
-  d.levelColStart = h.levelColStart.data(); d.levelCols = h.levelCols.data(); d.levelPanelStart = h.levelPanelStart.data();
-  d.panelTile = h.panelTile.data(); d.panelDiag = h.panelDiag.data(); d.levelTaskStart = h.levelTaskStart.data(); d.taskDst = h.taskDst.data();
-  d.taskPairStart = h.taskPairStart.data(); d.pairA = h.pairA.data(); d.pairB = h.pairB.data(); d.levelVTaskStart = h.levelVTaskStart.data();
-  d.vtaskRow = h.vtaskRow.data(); d.vtaskSrcStart = h.vtaskSrcStart.data(); d.vsrcTile = h.vsrcTile.data(); d.vsrcCol = h.vsrcCol.data();
-  d.colPanelStart = h.colPanelStart.data(); d.colPanelTile = h.colPanelTile.data(); d.colPanelRow = h.colPanelRow.data();
-  return d;
-}
-// dense column-major lower [JtJ; Jtr] (device-column order = elimination order) -> tile-packed; mirrors packNormalEquationsKernel
-static void packOne(const CholSchedule& h, const float* Hg, int ns, int ldH, float* out) {
-  const CholSchedDev S = devView(h);
-  for (int c = 0; c < ns; ++c)
-    for (int i = c; i <= ns; ++i) {
-      const float v = Hg[size_t(c) * ldH + i];
-      if (i == ns) { out[size_t(S.numTiles) * 256 + S.pos[c]] = v; continue; }
-      int mirror;
-      const int off = packedOffset(S, S.pos[i], S.pos[c], &mirror);
-      if (off >= 0) { out[off] = v; if (mirror >= 0) out[mirror] = v; }
-    }
-}
-// mirrors choleskyScheduledKernel
-static int cholScheduledOne(const CholSchedule& h, const float* packed, int n, float reg, float* delta, float* gdd) {
-  const CholSchedDev S = devView(h);
+static int cholScheduledOne(const CholSchedDev& S, const float* Hs, int ldH, int n, float reg, float* delta, float* gdd) {
   std::vector<float> store(size_t(S.numTiles) * 256 + S.nPad + 16, 0.f);
   float* tl = store.data();
   while ((reinterpret_cast<uintptr_t>(tl) & 15) != 0) ++tl; // float4 alignment
-  std::copy(packed, packed + size_t(S.numTiles) * 256 + S.nPad, tl);
   float* y = tl + size_t(S.numTiles) * 256;
   std::vector<float> gsub(n, 0.f);
+  for (int idx = 0; idx < S.numTiles * 256; ++idx) {
+    const int t = idx >> 8, e = idx & 255, c = e >> 4, r = e & 15;
+    const int I = S.tileRow[t], J = S.tileCol[t];
+    if (I != J) tl[idx - e + tileIdx(c, r)] = Hs[size_t(16 * J + c) * ldH + 16 * I + r];
+    else {
+      const int lo = r < c ? r : c, hi = r < c ? c : r;
+      float v = Hs[size_t(16 * J + lo) * ldH + 16 * I + hi];
+      if (r == c) { const int p = S.perm[16 * I + r]; v = p >= 0 ? v + reg : 1.f; }
+      tl[idx - e + tileIdx(c, r)] = v;
+    }
+  }
   for (int s2 = 0; s2 < S.nPad; ++s2) {
-    const int K = s2 >> 4, r = s2 & 15, p = S.perm[s2];
-    float* D = tl + size_t(S.diagTile[K]) * 256 + tileIdx(r, r);
-    if (p >= 0) { *D += reg; gsub[p] = y[s2]; } else *D = 1.f;
+    const int p = S.perm[s2];
+    const float g = p >= 0 ? Hs[size_t(s2) * ldH + S.nPad] : 0.f;
+    y[s2] = g;
+    if (p >= 0) gsub[p] = g;
   }
   int flag = 0;
   for (int L = 0; L < S.numLevels; ++L) {
@@ -455,13 +441,15 @@ int mb2_solver_solve(mb2_solver* s, float* params, double* errors, int32_t* iter
     f->J.assign(size_t(f->B) * (f->plan.numCols + 1) * f->ldJ, 0.f);
     relabelScheduleToEliminationOrder(sched);
   }
+  std::vector<int32_t> blob;
+  CholSchedDev S{};
+  if (cholMode >= 2) makeScheduleBlob(sched, blob, S);
   const FunctionTables T = tables(f);
-  const int n = T.numParams, ns = f->plan.numCols, ldH = (ns + 1) | 1;
+  const int n = T.numParams, ns = f->plan.numCols, ldH = cholMode >= 2 ? slotLd(sched.nPad) : ((ns + 1) | 1);
   const int maxIt = int(o.max_iterations), minIt = int(o.min_iterations);
   s->errors.assign(f->B, DBL_MAX); s->iterations.assign(f->B, 0); s->status.assign(f->B, 0);
   s->history.assign(size_t(f->B) * std::max(maxIt, 1), 0.0);
-  std::vector<float> H(size_t(ns + 1) * ldH), delta(ns), orig(n);
-  std::vector<float> packed(cholMode >= 2 ? packedStride(sched.numTiles, sched.nPad) : 1, 0.f);
+  std::vector<float> H(cholMode >= 2 ? size_t(sched.nPad) * ldH : size_t(ns + 1) * ldH, 0.f), delta(ns), orig(n);
   s->totalIterations = 0;
   for (int b = 0; b < f->B; ++b) {
     float* theta = params + size_t(b) * n;
@@ -469,14 +457,15 @@ int mb2_solver_solve(mb2_solver* s, float* params, double* errors, int32_t* iter
     double last = DBL_MAX, error = DBL_MAX;
     for (int it = 0; it < maxIt; ++it) {
       sweepOne<true>(f, T, b, theta, &error, nullptr);
-      std::fill(H.begin(), H.end(), 0.f);
-      jtjOne(f, b, ns, H.data(), ldH);
       float gdd = 0.f;
       int failed;
       if (cholMode >= 2) {
-        packOne(sched, H.data(), ns, ldH, packed.data()); // structural zeros of `packed` are never written: stay zero across iterations
-        failed = cholScheduledOne(sched, packed.data(), ns, o.regularization, delta.data(), &gdd);
+        // slot-ordered system: padding rows/columns are never written and stay zero across iterations (zeroed once, like the device buffer)
+        jtjOne(f, b, ns, H.data(), ldH, S.pos, S.nPad);
+        failed = cholScheduledOne(S, H.data(), ldH, ns, o.regularization, delta.data(), &gdd);
       } else {
+        std::fill(H.begin(), H.end(), 0.f);
+        jtjOne(f, b, ns, H.data(), ldH);
         failed = cholDispatch(H.data(), ns, ldH, o.regularization, delta.data(), &gdd);
       }
       if (failed && s->status[b] == 0) s->status[b] = MB2_INSTANCE_CHOLESKY_BREAKDOWN;
