@@ -52,14 +52,18 @@ struct CholSchedDev {
   const int32_t* colPanelRow;
 };
 // view of the same schedule with every table pointer moved to a copy of the blob at `newBlob`
+// Every pointer is re-derived FROM newBlob (newBlob + element offset): nvcc assumes kernel-parameter pointers address
+// global memory, so "old pointer + delta" would still be loaded with ld.global even when the copy lives in shared memory.
 MB2_HD CholSchedDev rebaseSchedule(const CholSchedDev& S, const int32_t* newBlob) {
   CholSchedDev R = S;
-  const long d = newBlob - S.blob;
+  const int32_t* o = S.blob;
   R.blob = newBlob;
-  R.perm += d; R.pos += d; R.tileIdTable += d; R.tileRow += d; R.tileCol += d; R.diagTile += d; R.levelColStart += d; R.levelCols += d;
-  R.levelPanelStart += d; R.panelTile += d; R.panelDiag += d; R.levelTaskStart += d; R.taskDst += d; R.taskPairStart += d; R.pairA += d; R.pairB += d;
-  R.levelVTaskStart += d; R.vtaskRow += d; R.vtaskSrcStart += d; R.vsrcTile += d; R.vsrcCol += d; R.colPanelStart += d; R.colPanelTile += d;
-  R.colPanelRow += d;
+#define MB2_RB(f) R.f = newBlob + (S.f - o);
+  MB2_RB(perm) MB2_RB(pos) MB2_RB(tileIdTable) MB2_RB(tileRow) MB2_RB(tileCol) MB2_RB(diagTile) MB2_RB(levelColStart) MB2_RB(levelCols)
+  MB2_RB(levelPanelStart) MB2_RB(panelTile) MB2_RB(panelDiag) MB2_RB(levelTaskStart) MB2_RB(taskDst) MB2_RB(taskPairStart) MB2_RB(pairA) MB2_RB(pairB)
+  MB2_RB(levelVTaskStart) MB2_RB(vtaskRow) MB2_RB(vtaskSrcStart) MB2_RB(vsrcTile) MB2_RB(vsrcCol) MB2_RB(colPanelStart) MB2_RB(colPanelTile)
+  MB2_RB(colPanelRow)
+#undef MB2_RB
   return R;
 }
 

@@ -28,6 +28,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -57,6 +58,7 @@ struct TcParams {
   size_t hStride;
   const int32_t* slotOf; // optional slot mapping (see JtJArgs)
   int rhsRow;
+  int profile;    // MB2_TC_PROFILE=1: block 0 prints per-role wait/busy cycles (debug aid, off by default)
 };
 
 __device__ __forceinline__ uint32_t smemAddr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -171,15 +173,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
+      long long wEmpty = 0, tStart = clock64();
       for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
         if (p.active != nullptr && p.active[b] == 0) continue;
         for (int kb = 0; kb < p.kBlocks; ++kb) {
+          long long t0 = clock64();
           mbarWait(emptyBar(s), ph ^ 1u);
+          wEmpty += clock64() - t0;
           mbarExpectTx(fullBar(s), slabBytes);
           tmaLoad3d(base + stageBytes * s, &tmap, kb * kKBlock, 0, b, fullBar(s));
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
       }
+      if (p.profile && blockIdx.x == 0) printf("tc-profile producer: total %lld waitEmpty %lld\n", clock64() - tStart, wEmpty);
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
@@ -187,12 +193,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
       int s = 0;
       uint32_t ph = 0, tph = 0;
       const uint32_t idesc0 = makeInstrDesc(128, p.n0), idesc1 = makeInstrDesc(128, p.n1);
+      long long wTmem = 0, wConv = 0, tStart = clock64();
       for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
         if (p.active != nullptr && p.active[b] == 0) continue;
+        long long t0 = clock64();
         mbarWait(tmemEmptyBar, tph ^ 1u); // epilogue has drained the previous instance's accumulators
+        wTmem += clock64() - t0;
         tcFenceAfter();
         for (int kb = 0; kb < p.kBlocks; ++kb) {
+          t0 = clock64();
           mbarWait(convBar(s), ph);
+          wConv += clock64() - t0;
           tcFenceAfter();
           const uint32_t hi = base + stageBytes * s, lo = hi + slabBytes;
           for (int t = 0; t < p.mTiles; ++t) {
@@ -215,6 +226,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
         }
         tph ^= 1u;
       }
+      if (p.profile && blockIdx.x == 0) printf("tc-profile mma: total %lld waitTmemEmpty %lld waitConverted %lld\n", clock64() - tStart, wTmem, wConv);
     }
   } else if (warp < 6) {
     // ---------------- converters: raw fp32 -> tf32 hi (in place) and lo ----------------
@@ -222,10 +234,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
     int s = 0;
     uint32_t ph = 0;
     const int vecs = (int)(slabBytes / 16u);
+    long long wFull = 0, tStart = clock64();
     for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
       if (p.active != nullptr && p.active[b] == 0) continue;
       for (int kb = 0; kb < p.kBlocks; ++kb) {
+        long long t0 = clock64();
         mbarWait(fullBar(s), ph);
+        wFull += clock64() - t0;
         float4* hi = reinterpret_cast<float4*>(gen + stageBytes * s);
         float4* lo = reinterpret_cast<float4*>(gen + stageBytes * s + slabBytes);
         for (int i = ct; i < vecs; i += 128) {
@@ -245,14 +260,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
         if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
     }
+    if (p.profile && blockIdx.x == 0 && ct == 0) printf("tc-profile converter: total %lld waitFull %lld\n", clock64() - tStart, wFull);
   } else {
     // ---------------- epilogue: TMEM -> global, column-major lower triangle of [JtJ; Jtr] ----------------
     const int q = warp & 3; // TMEM lane quarter this warp may access
     uint32_t eph = 0;
+    long long wFullT = 0, tStart = clock64();
     for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
       if (p.active != nullptr && p.active[b] == 0) continue;
       float* H = p.H + (size_t)b * p.hStride;
+      long long t0 = clock64();
       mbarWait(tmemFullBar, eph);
+      wFullT += clock64() - t0;
       tcFenceAfter();
       for (int t = 0; t < p.mTiles; ++t) {
         const int row = t * 128 + q * 32 + lane;                 // row of [J r]^T [J r]
@@ -289,6 +308,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
       mbarArrive(tmemEmptyBar);
       eph ^= 1u;
     }
+    if (p.profile && blockIdx.x == 0 && threadIdx.x == 6 * 32) printf("tc-profile epilogue: total %lld waitTmemFull %lld\n", clock64() - tStart, wFullT);
   }
   tcFenceBefore();
   __syncthreads();
@@ -370,6 +390,7 @@ cudaError_t launchJtJTensor(const JtJArgs& a, int passes, cudaStream_t stream) {
   p.hStride = a.hStride;
   p.slotOf = a.slotOf;
   p.rhsRow = a.rhsRow;
+  p.profile = getenv("MB2_TC_PROFILE") != nullptr ? 1 : 0;
   const size_t stageBytes = size_t(sh.boxRows) * kRowBytes * (p.passes == 3 ? 2 : 1);
   int stages = int((200 * 1024) / stageBytes);
   if (stages > 6) stages = 6;
