@@ -9,6 +9,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -260,9 +261,6 @@ int ensurePlan(mb2_solver_function* f, int mode, bool schedDense = false) {
     int rc = uploadSchedule(f, ds);
     if (rc != MB2_OK) return rc;
     f->sched = std::move(ds);
-    const size_t stride = size_t(f->sched->host.nPad) * slotLd(f->sched->host.nPad);
-    MB2_CUDA(f->dPacked.resize(size_t(f->B) * stride));
-    MB2_CUDA(cudaMemsetAsync(f->dPacked.p, 0, size_t(f->B) * stride * sizeof(float), s)); // padding rows/columns and fill tiles stay zero
   }
   f->planMode = mode;
   f->planSchedDense = schedDense;
@@ -380,7 +378,7 @@ int resolveJtjMode(const mb2_solver_function* f, int requested, int ns) {
   return ok ? requested : -1;
 }
 
-int runJtJ(mb2_solver_function* f, int mode, int ns, float* H, int ldH, size_t hStride, const int32_t* active, cudaStream_t st, bool slots = false) {
+int runJtJ(mb2_solver_function* f, int mode, int ns, float* H, int ldH, size_t hStride, const int32_t* active, cudaStream_t st) {
   JtJArgs a{};
   a.batch = f->B;
   a.jacobian = f->dJ.p;
@@ -391,8 +389,6 @@ int runJtJ(mb2_solver_function* f, int mode, int ns, float* H, int ldH, size_t h
   a.H = H;
   a.ldH = ldH;
   a.hStride = hStride;
-  a.slotOf = slots ? f->sched->dev.pos : nullptr;
-  a.rhsRow = slots ? f->sched->host.nPad : ns;
   a.active = active;
   if (mode == MB2_JTJ_FP32_SIMT) { MB2_CUDA(launchJtJSimt(a, st)); }
   else { MB2_CUDA(launchJtJTensor(a, mode == MB2_JTJ_TF32X3 ? 3 : 1, st)); }
@@ -693,7 +689,7 @@ int mb2_solver_function_get_jtjr(mb2_solver_function* f, const float* params, in
   MB2_CHECK(ap > 0, "no enabled parameters");
   const int mode = resolveJtjMode(f, jtjMode, ap);
   if (mode < 0) return fail(MB2_ERR_UNSUPPORTED, "tensor-core JtJ does not support this shape");
-  const int ldH = (ap + 1) | 1;
+  const int ldH = roundUp(ap + 1, 16);
   const size_t hElems = size_t(f->B) * (ap + 1) * ldH;
   MB2_CUDA(f->dH.resize(hElems));
   MB2_CUDA(cudaMemcpyAsync(f->dTheta.p, params, size_t(f->B) * n * sizeof(float), cudaMemcpyHostToDevice, f->stream));
@@ -705,7 +701,7 @@ int mb2_solver_function_get_jtjr(mb2_solver_function* f, const float* params, in
   MB2_CUDA(cudaMemcpyAsync(h.data(), f->dH.p, hElems * sizeof(float), cudaMemcpyDeviceToHost, f->stream));
   if (errors) MB2_CUDA(cudaMemcpyAsync(errors, f->dErrors.p, size_t(f->B) * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
   MB2_CUDA(cudaStreamSynchronize(f->stream));
-  for (int b = 0; b < f->B; ++b) { // device layout is column-major lower [JtJ; Jtr]; the ABI returns row-major lower + Jtr
+  for (int b = 0; b < f->B; ++b) { // device layout is the full symmetric [JtJ, Jtr]; the ABI returns the lower triangle + Jtr
     const float* Hb = h.data() + size_t(b) * (ap + 1) * ldH;
     for (int j = 0; j < ap; ++j) {
       if (jtj) for (int i = j; i < ap; ++i) jtj[(size_t(b) * ap + i) * ap + j] = Hb[size_t(j) * ldH + i];
@@ -786,12 +782,11 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
   MB2_CHECK(ns > 0, "no enabled parameters");
   const int mode = resolveJtjMode(f, o.jtj_mode, ns);
   if (mode < 0) return fail(MB2_ERR_UNSUPPORTED, "tensor-core JtJ does not support this shape");
-  // normal equations: dense column-major [ns+1][ldH] for the dense kernel, or the slot-ordered padded system for the tile schedule
-  const int ldH = useSchedule ? slotLd(f->sched->host.nPad) : ((ns + 1) | 1);
-  const size_t hStride = useSchedule ? size_t(f->sched->host.nPad) * ldH : size_t(ns + 1) * ldH;
-  float* Hbuf = nullptr;
-  if (useSchedule) Hbuf = f->dPacked.p; // zeroed once per plan in ensurePlan
-  else { MB2_CUDA(s->dH.resize(size_t(B) * hStride)); Hbuf = s->dH.p; }
+  // normal equations: full symmetric [ns+1][ldH] in device-column order (row/column ns = J^T r)
+  const int ldH = roundUp(ns + 1, 16);
+  const size_t hStride = size_t(ns + 1) * ldH;
+  MB2_CUDA(s->dH.resize(size_t(B) * hStride));
+  float* Hbuf = s->dH.p;
   MB2_CUDA(s->dDelta.resize(size_t(B) * ns));
   MB2_CUDA(s->dTheta0.resize(size_t(B) * n));
   MB2_CUDA(s->dLastErrors.resize(B));
@@ -827,7 +822,7 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
     MB2_CUDA(launchSweep(sweepArgs(f, theta, s->dActive.p), true, st));
     recordPhaseStop(s, st);
     recordPhaseStart(s, 1, st);
-    rc = runJtJ(f, mode, ns, Hbuf, ldH, hStride, s->dActive.p, st, useSchedule);
+    rc = runJtJ(f, mode, ns, Hbuf, ldH, hStride, s->dActive.p, st);
     if (rc != MB2_OK) return rc;
     recordPhaseStop(s, st);
     CholArgs c{};
@@ -855,6 +850,7 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
     c.activeCount = s->dActiveCount.p;
     c.bookkeeping = lineSearch ? 0 : 1;
     c.gradDotDelta = lineSearch ? s->dGradDotDelta.p : nullptr;
+    c.profile = (it == 0 && getenv("MB2_CHOL_PROFILE") != nullptr) ? 1 : 0;
     recordPhaseStart(s, 2, st);
     if (useSchedule) MB2_CUDA(launchCholeskyScheduled(c, f->sched->dev, st));
     else MB2_CUDA(launchCholesky(c, st));

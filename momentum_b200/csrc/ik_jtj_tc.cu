@@ -56,8 +56,6 @@ struct TcParams {
   int tmemCols;   // power of two >= n0 + n1
   int stages;
   size_t hStride;
-  const int32_t* slotOf; // optional slot mapping (see JtJArgs)
-  int rhsRow;
   int profile;    // MB2_TC_PROFILE=1: block 0 prints per-role wait/busy cycles (debug aid, off by default)
 };
 
@@ -265,7 +263,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
     // ---------------- epilogue: TMEM -> global, column-major lower triangle of [JtJ; Jtr] ----------------
     const int q = warp & 3; // TMEM lane quarter this warp may access
     uint32_t eph = 0;
-    long long wFullT = 0, tStart = clock64();
+    long long wFullT = 0, tStart = clock64(), tLd = 0, nChunks = 0;
     for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
       if (p.active != nullptr && p.active[b] == 0) continue;
       float* H = p.H + (size_t)b * p.hStride;
@@ -275,31 +273,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
       tcFenceAfter();
       for (int t = 0; t < p.mTiles; ++t) {
         const int row = t * 128 + q * 32 + lane;                 // row of [J r]^T [J r]
-        const int i = row < p.ns ? row : (row == p.numCols ? p.ns : -1); // index in the (ns+1) system; -1: not wanted
-        const int maxI = __reduce_max_sync(0xffffffffu, i);
-        const int si = (p.slotOf != nullptr && i >= 0) ? (i < p.ns ? p.slotOf[i] : p.rhsRow) : 0; // slot of this lane's row
+        const int i = row < p.ns ? row : (row == p.numCols ? p.ns : -1); // row of the (ns+1) system; -1: not wanted
+        const int anyRow = __reduce_max_sync(0xffffffffu, i);
+        if (anyRow < 0) continue;                                 // warp-uniform: nothing to write from these 32 rows
         const int nT = t == 0 ? p.n0 : p.n1;
         const uint32_t colBase = tmemBase + ((uint32_t)(q * 32) << 16) + (t == 0 ? 0u : (uint32_t)p.n0);
+        float* Hrow = H + (size_t)(i < 0 ? 0 : i) * p.ldH;
         for (int c0 = 0; c0 < nT; c0 += 16) {
-          if (c0 > maxI || c0 >= p.ns) break; // warp-uniform: the rest lies above the diagonal / outside the system
           float v[16];
+          const long long tl0 = p.profile ? clock64() : 0;
           tmemLoad16(colBase + (uint32_t)c0, v);
-          if (p.slotOf == nullptr) {
+          if (p.profile) { tLd += clock64() - tl0; ++nChunks; }
+          if (i < 0) continue;
+          if (p.ns == p.numCols || c0 + 16 <= p.ns) {
+            // every thread owns one full row of the symmetric matrix: 64 contiguous bytes per chunk
+            // (columns >= ns + 1 of the last chunk are zero products of zero-filled TMA rows; ldH is a multiple of 16)
+            if (c0 <= p.ns) {
 #pragma unroll
-            for (int cc = 0; cc < 16; ++cc) {
-              const int c = c0 + cc;
-              if (c < p.ns && c <= i) H[(size_t)c * p.ldH + i] = v[cc];
+              for (int g4 = 0; g4 < 4; ++g4)
+                *reinterpret_cast<float4*>(Hrow + c0 + 4 * g4) = make_float4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
             }
           } else {
-            // (every lane takes part in the shuffles; rows that are not wanted have i = -1 and never pass c <= i)
-            // slot-ordered output: device columns are in elimination order, so (i, c), c <= i, stays in the lower triangle and
-            // consecutive lanes (rows) write consecutive floats except across padding gaps
-            const int myCol = c0 + lane < p.ns ? p.slotOf[c0 + lane] : 0; // lane l fetches the slot of column c0 + l once
+            // leading-block request (ns < numCols, getJtJR parity entry): columns ns.. are skipped except the residual column
 #pragma unroll
             for (int cc = 0; cc < 16; ++cc) {
               const int c = c0 + cc;
-              const int sc = __shfl_sync(0xffffffffu, myCol, cc);
-              if (c < p.ns && c <= i) H[(size_t)sc * p.ldH + si] = v[cc];
+              if (c < p.ns) Hrow[c] = v[cc];
+              else if (c == p.numCols) Hrow[p.ns] = v[cc];
             }
           }
         }
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
       mbarArrive(tmemEmptyBar);
       eph ^= 1u;
     }
-    if (p.profile && blockIdx.x == 0 && threadIdx.x == 6 * 32) printf("tc-profile epilogue: total %lld waitTmemFull %lld\n", clock64() - tStart, wFullT);
+    if (p.profile && blockIdx.x == 0 && threadIdx.x == 6 * 32) printf("tc-profile epilogue: total %lld waitTmemFull %lld tmemLoad %lld chunks %lld\n", clock64() - tStart, wFullT, tLd, nChunks);
   }
   tcFenceBefore();
   __syncthreads();
@@ -344,7 +344,7 @@ Shape shapeFor(int numCols) {
   s.mTiles = s.rows > 128 ? 2 : 1;
   s.boxRows = s.mTiles * 128;
   const int r16 = roundUpI(s.rows, 16);
-  s.n0 = r16 < 128 ? r16 : 128;
+  s.n0 = r16;                      // both row tiles span every column: the epilogue writes full rows of the symmetric matrix
   s.n1 = s.mTiles == 2 ? r16 : 0;
   int need = s.n0 + s.n1, c = 32;
   while (c < need) c <<= 1;
@@ -388,8 +388,6 @@ cudaError_t launchJtJTensor(const JtJArgs& a, int passes, cudaStream_t stream) {
   p.n1 = sh.n1;
   p.tmemCols = sh.tmemCols;
   p.hStride = a.hStride;
-  p.slotOf = a.slotOf;
-  p.rhsRow = a.rhsRow;
   p.profile = getenv("MB2_TC_PROFILE") != nullptr ? 1 : 0;
   const size_t stageBytes = size_t(sh.boxRows) * kRowBytes * (p.passes == 3 ? 2 : 1);
   int stages = int((200 * 1024) / stageBytes);

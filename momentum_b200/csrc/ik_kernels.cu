@@ -160,17 +160,11 @@ __global__ void __launch_bounds__(256) jtjSimtKernel(const JtJArgs a) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int gi = ti * kJtjTile + ty * 4 + i, gj = tj * kJtjTile + tx * 4 + j;
-      if (gi < a.ns && gj <= gi) {
-        if (a.slotOf == nullptr) H[size_t(gj) * a.ldH + gi] = acc[i][j];
-        else H[size_t(a.slotOf[gj]) * a.ldH + a.slotOf[gi]] = acc[i][j];
-      }
+      if (gi < a.ns && gj <= gi) { H[size_t(gj) * a.ldH + gi] = acc[i][j]; H[size_t(gi) * a.ldH + gj] = acc[i][j]; }
     }
   if (diag && threadIdx.x < kJtjTile) {
     const int gi = ti * kJtjTile + threadIdx.x;
-    if (gi < a.ns) {
-      if (a.slotOf == nullptr) H[size_t(gi) * a.ldH + a.ns] = gacc;
-      else H[size_t(a.slotOf[gi]) * a.ldH + a.rhsRow] = gacc;
-    }
+    if (gi < a.ns) { H[size_t(gi) * a.ldH + a.ns] = gacc; H[size_t(a.ns) * a.ldH + gi] = gacc; }
   }
 }
 
@@ -365,30 +359,42 @@ __global__ void __launch_bounds__(kSchedThreads, 2) choleskyScheduledKernel(cons
   int32_t* blob = reinterpret_cast<int32_t*>(dsub + ((n + 3) & ~3));
   int* flags = reinterpret_cast<int*>(blob + ((Sg.blobInts + 3) & ~3));
   // the schedule (a few KB of int32 tables) is read many times per level: stage it in shared memory once
+  long long pc[6] = {0, 0, 0, 0, 0, 0}, pt = clock64();
+#define MB2_PROF(k) if (a.profile) { const long long now = clock64(); pc[k] += now - pt; pt = now; }
   for (int i = tid; i < Sg.blobInts; i += kSchedThreads) blob[i] = Sg.blob[i];
   if (tid == 0) flags[0] = 0;
   __syncthreads();
   const CholSchedDev S = rebaseSchedule(Sg, blob);
-  // gather the stored tiles from the slot-ordered system: tile (I,J) = 16 segments of 64 bytes
+  // Gather the stored tiles from the symmetric matrix. Device columns are in elimination order and padding only closes a
+  // tile, so block row I covers device columns tileBase(I) .. tileBase(I) + valid(I) - 1: the transposed tile
+  // T[c][r] = H(r,c) = H(c,r) is sixteen contiguous runs of row (tileBase(J)+c) of H. All copies are 4-byte cp.async
+  // (LDGSTS) so that every thread has its ~60 loads in flight at once.
   const float* Hs = a.H + size_t(b) * a.hStride;
   for (int idx = tid; idx < S.numTiles * 256; idx += kSchedThreads) {
     const int t = idx >> 8, e = idx & 255, c = e >> 4, r = e & 15;
     const int I = S.tileRow[t], J = S.tileCol[t];
-    if (I != J) tiles[idx - e + tileIdx(c, r)] = Hs[size_t(16 * J + c) * a.ldH + 16 * I + r]; // stored transposed: T[c][r] = H(r,c)
-    else {
-      const int lo = r < c ? r : c, hi = r < c ? c : r;
-      float v = Hs[size_t(16 * J + lo) * a.ldH + 16 * I + hi];                                 // symmetric fill of the diagonal tile
-      if (r == c) { const int p = S.perm[16 * I + r]; v = p >= 0 ? v + a.regularization : 1.f; } // damping (gauss_newton_solver.cpp:248) / padding
-      tiles[idx - e + tileIdx(c, r)] = v;
+    const int gi = S.perm[16 * I + r], gj = S.perm[16 * J + c];
+    float* dst = tiles + (idx - e + tileIdx(c, r));
+    if (gi >= 0 && gj >= 0) {
+      const unsigned sdst = static_cast<unsigned>(__cvta_generic_to_shared(dst));
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst), "l"(Hs + size_t(gj) * a.ldH + gi) : "memory");
+    } else {
+      *dst = (I == J && r == c) ? 1.f : 0.f; // padding variable: identity row/column
     }
   }
   for (int s = tid; s < S.nPad; s += kSchedThreads) {
     const int p = S.perm[s];
-    const float g = p >= 0 ? Hs[size_t(s) * a.ldH + S.nPad] : 0.f;
+    const float g = p >= 0 ? Hs[size_t(n) * a.ldH + p] : 0.f;
     y[s] = g;
     if (p >= 0) gsub[p] = g;
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
+  for (int s = tid; s < S.nPad; s += kSchedThreads)
+    if (S.perm[s] >= 0) tiles[size_t(S.diagTile[s >> 4]) * 256 + tileIdx(s & 15, s & 15)] += a.regularization; // gauss_newton_solver.cpp:248
+  __syncthreads();
+  MB2_PROF(0)
 
   for (int L = 0; L < S.numLevels; ++L) {
     // A: diagonal tiles of this level (one half-warp each) + forward solve of their rhs block
@@ -397,23 +403,32 @@ __global__ void __launch_bounds__(kSchedThreads, 2) choleskyScheduledKernel(cons
       cholDiagTile(tiles + size_t(S.diagTile[K]) * 256, y + 16 * K, hl, hmask, a.regularization, flags);
     }
     __syncthreads();
+    MB2_PROF(1)
     // B: panel tiles
     for (int pi = S.levelPanelStart[L] + hw; pi < S.levelPanelStart[L + 1]; pi += kSchedThreads / 16) {
       cholPanelSolve(tiles + size_t(S.panelTile[pi]) * 256, tiles + size_t(S.panelDiag[pi]) * 256, hl);
     }
     __syncthreads();
+    MB2_PROF(2)
     // C: update tasks (warp each) and rhs updates (half-warp each)
     for (int ti = S.levelTaskStart[L] + warp; ti < S.levelTaskStart[L + 1]; ti += kSchedThreads / 32) cholUpdateTask(tiles, S, ti, lane);
     for (int vi = S.levelVTaskStart[L] + hw; vi < S.levelVTaskStart[L + 1]; vi += kSchedThreads / 16) cholVectorTask(tiles, y, S, vi, hl);
     __syncthreads();
+    MB2_PROF(3)
   }
   for (int L = S.numLevels - 1; L >= 0; --L) {
     for (int ci = S.levelColStart[L] + hw; ci < S.levelColStart[L + 1]; ci += kSchedThreads / 16) cholBackwardColumn(tiles, y, S, S.levelCols[ci], hl, hmask);
     __syncthreads();
   }
+  MB2_PROF(4)
   for (int i = tid; i < S.nPad; i += kSchedThreads) { const int p = S.perm[i]; if (p >= 0) dsub[p] = y[i]; }
   __syncthreads();
   cholFinish(a, b, n, dsub, gsub, flags[0] != 0);
+  MB2_PROF(5)
+  if (a.profile && b == 0 && tid == 0)
+    printf("chol-profile (cycles, block 0): load %lld diag %lld panel %lld update %lld backward %lld finish %lld | levels %d tiles %d\n", pc[0], pc[1], pc[2], pc[3],
+           pc[4], pc[5], S.numLevels, S.numTiles);
+#undef MB2_PROF
 }
 
 cudaError_t launchCholeskyScheduled(const CholArgs& a, const CholSchedDev& sched, cudaStream_t stream) {

@@ -26,19 +26,16 @@ struct JtJArgs {             // K2
   const float* jacobian;     // [B][numCols + 1][ldJ]; column numCols = residual
   int32_t numCols, ldJ, kRows; // kRows = contraction length (rows rounded up to 4)
   int32_t ns;                // leading ns columns enter the normal equations (ns <= numCols)
-  float* H;                  // [B][ns+1][ldH] column-major lower triangle of [JtJ, Jtr]: element (i,j), i>=j, at H[j*ldH + i];
-                             // row index ns holds Jtr (H[j*ldH + ns] = (J^T r)_j)
-  int32_t ldH;               // >= ns + 1
+  float* H;                  // [B][ns+1][ldH] FULL symmetric matrix [J r]^T [J r] restricted to the leading ns columns + r:
+                             // H[i*ldH + j] = H[j*ldH + i]; row/column ns holds J^T r (H[i*ldH + ns] = (J^T r)_i)
+  int32_t ldH;               // multiple of 16, >= ns + 1
   size_t hStride;            // floats per instance in H
-  const int32_t* slotOf;     // optional [ns]: write element (i,j) at the slots (slotOf[i], slotOf[j]) of the padded, elimination-ordered
-                             // system instead (ik_chol_sched.cuh "Hs"); Jtr then goes to row rhsRow
-  int32_t rhsRow;
   const int32_t* active;
 };
 
 struct CholArgs {            // K3: damped Cholesky + solve + update + SolverT bookkeeping
   int32_t batch;
-  float* H;                  // [B][ns+1][ldH] column-major lower [JtJ; Jtr] (as written by K2)
+  float* H;                  // [B][ns+1][ldH] full symmetric [JtJ, Jtr] (as written by K2); K3 never writes it unless it factors in place
   size_t hStride;            // floats per instance in H
   int32_t ns, ldH;
   float regularization;
@@ -58,6 +55,7 @@ struct CholArgs {            // K3: damped Cholesky + solve + update + SolverT b
   int32_t* activeCount;      // device counter (atomicAdd of instances still active)
   int32_t bookkeeping;       // 1: run the SolverT convergence test here (no line search)
   float* gradDotDelta;       // optional [B]: Jtr . delta (SubsetGaussNewtonSolverT line search)
+  int32_t profile;           // MB2_CHOL_PROFILE=1: block 0 prints per-phase cycles (debug aid)
 };
 
 cudaError_t launchSweep(const SweepArgs& a, bool jacobian, cudaStream_t stream);
@@ -65,7 +63,7 @@ size_t sweepSmemPerInstance(const FunctionTables& T);
 cudaError_t launchJtJSimt(const JtJArgs& a, cudaStream_t stream);
 cudaError_t launchCholesky(const CholArgs& a, cudaStream_t stream);
 // level-scheduled tile-sparse variant (ik_chol_sched.h); returns cudaErrorInvalidConfiguration when the tiles do not fit in shared memory
-// `a.H` is the slot-ordered system Hs (ld = a.ldH, a.hStride floats per instance)
+// `a.H` is the full symmetric system in device-column (= elimination) order
 cudaError_t launchCholeskyScheduled(const CholArgs& a, const CholSchedDev& sched, cudaStream_t stream);
 size_t choleskyScheduledSmemBytes(int n, int nPad, int numTiles, int blobInts);
 cudaError_t initKernelAttributes();

@@ -103,7 +103,7 @@ static void sweepOne(mb2_solver_function* f, const FunctionTables& T, int b, con
   *errOut = kJacobian ? lane[0] : (double)(float)lane[0];
 }
 
-static void jtjOne(const mb2_solver_function* f, int b, int ns, float* H, int ldH, const int32_t* slotOf = nullptr, int rhsRow = 0) {
+static void jtjOne(const mb2_solver_function* f, int b, int ns, float* H, int ldH) {
   const int nc = f->plan.numCols;
   const float* J = f->J.data() + size_t(b) * (nc + 1) * f->ldJ;
   const float* r = J + size_t(nc) * f->ldJ;
@@ -112,11 +112,11 @@ static void jtjOne(const mb2_solver_function* f, int b, int ns, float* H, int ld
     for (int j = 0; j <= i; ++j) {
       float s = 0.f;
       for (int k = 0; k < K; ++k) s = fmaf(J[size_t(i) * f->ldJ + k], J[size_t(j) * f->ldJ + k], s);
-      if (slotOf) H[size_t(slotOf[j]) * ldH + slotOf[i]] = s; else H[size_t(j) * ldH + i] = s; // column-major lower
+      H[size_t(j) * ldH + i] = s; H[size_t(i) * ldH + j] = s; // full symmetric
     }
     float g = 0.f;
     for (int k = 0; k < K; ++k) g = fmaf(J[size_t(i) * f->ldJ + k], r[k], g);
-    if (slotOf) H[size_t(slotOf[i]) * ldH + rhsRow] = g; else H[size_t(i) * ldH + ns] = g;
+    H[size_t(i) * ldH + ns] = g; H[size_t(ns) * ldH + i] = g;
   }
 }
 
@@ -175,19 +175,14 @@ static int cholScheduledOne(const CholSchedDev& S, const float* Hs, int ldH, int
   for (int idx = 0; idx < S.numTiles * 256; ++idx) {
     const int t = idx >> 8, e = idx & 255, c = e >> 4, r = e & 15;
     const int I = S.tileRow[t], J = S.tileCol[t];
-    if (I != J) tl[idx - e + tileIdx(c, r)] = Hs[size_t(16 * J + c) * ldH + 16 * I + r];
-    else {
-      const int lo = r < c ? r : c, hi = r < c ? c : r;
-      float v = Hs[size_t(16 * J + lo) * ldH + 16 * I + hi];
-      if (r == c) { const int p = S.perm[16 * I + r]; v = p >= 0 ? v + reg : 1.f; }
-      tl[idx - e + tileIdx(c, r)] = v;
-    }
+    const int gi = S.perm[16 * I + r], gj = S.perm[16 * J + c];
+    tl[idx - e + tileIdx(c, r)] = (gi >= 0 && gj >= 0) ? Hs[size_t(gj) * ldH + gi] : ((I == J && r == c) ? 1.f : 0.f);
   }
   for (int s2 = 0; s2 < S.nPad; ++s2) {
     const int p = S.perm[s2];
-    const float g = p >= 0 ? Hs[size_t(s2) * ldH + S.nPad] : 0.f;
+    const float g = p >= 0 ? Hs[size_t(n) * ldH + p] : 0.f;
     y[s2] = g;
-    if (p >= 0) gsub[p] = g;
+    if (p >= 0) { gsub[p] = g; tl[size_t(S.diagTile[s2 >> 4]) * 256 + tileIdx(s2 & 15, s2 & 15)] += reg; }
   }
   int flag = 0;
   for (int L = 0; L < S.numLevels; ++L) {
@@ -390,7 +385,7 @@ int mb2_solver_function_get_jtjr(mb2_solver_function* f, const float* params, in
   const std::string e = plan(f, false);
   if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
   const FunctionTables T = tables(f);
-  const int ap = f->plan.actualParameters, n = T.numParams, ldH = (ap + 1) | 1;
+  const int ap = f->plan.actualParameters, n = T.numParams, ldH = roundUp(ap + 1, 16);
   std::vector<float> H(size_t(ap + 1) * ldH);
   for (int b = 0; b < f->B; ++b) {
     double err;
@@ -445,11 +440,11 @@ int mb2_solver_solve(mb2_solver* s, float* params, double* errors, int32_t* iter
   CholSchedDev S{};
   if (cholMode >= 2) makeScheduleBlob(sched, blob, S);
   const FunctionTables T = tables(f);
-  const int n = T.numParams, ns = f->plan.numCols, ldH = cholMode >= 2 ? slotLd(sched.nPad) : ((ns + 1) | 1);
+  const int n = T.numParams, ns = f->plan.numCols, ldH = roundUp(ns + 1, 16);
   const int maxIt = int(o.max_iterations), minIt = int(o.min_iterations);
   s->errors.assign(f->B, DBL_MAX); s->iterations.assign(f->B, 0); s->status.assign(f->B, 0);
   s->history.assign(size_t(f->B) * std::max(maxIt, 1), 0.0);
-  std::vector<float> H(cholMode >= 2 ? size_t(sched.nPad) * ldH : size_t(ns + 1) * ldH, 0.f), delta(ns), orig(n);
+  std::vector<float> H(size_t(ns + 1) * ldH, 0.f), delta(ns), orig(n);
   s->totalIterations = 0;
   for (int b = 0; b < f->B; ++b) {
     float* theta = params + size_t(b) * n;
@@ -459,13 +454,11 @@ int mb2_solver_solve(mb2_solver* s, float* params, double* errors, int32_t* iter
       sweepOne<true>(f, T, b, theta, &error, nullptr);
       float gdd = 0.f;
       int failed;
+      std::fill(H.begin(), H.end(), 0.f);
+      jtjOne(f, b, ns, H.data(), ldH);
       if (cholMode >= 2) {
-        // slot-ordered system: padding rows/columns are never written and stay zero across iterations (zeroed once, like the device buffer)
-        jtjOne(f, b, ns, H.data(), ldH, S.pos, S.nPad);
         failed = cholScheduledOne(S, H.data(), ldH, ns, o.regularization, delta.data(), &gdd);
       } else {
-        std::fill(H.begin(), H.end(), 0.f);
-        jtjOne(f, b, ns, H.data(), ldH);
         failed = cholDispatch(H.data(), ns, ldH, o.regularization, delta.data(), &gdd);
       }
       if (failed && s->status[b] == 0) s->status[b] = MB2_INSTANCE_CHOLESKY_BREAKDOWN;
