@@ -92,20 +92,24 @@ MB2_HD void tileStoreRow(float* tile, int r, const float* a) {
   }
 }
 
-// ---- phase A: Cholesky of a diagonal tile + forward solve of its 16 right-hand-side entries ----
+// ---- phase A: Cholesky of a diagonal tile, forward solve of its 16 right-hand-side entries, and W = L^-1 ----
 // hl = lane within the half-warp (0..15), hmask = shuffle mask of the half-warp.
 // A non-positive pivot is replaced by `fallback` (the damping) and reported through *fail.
+// On return the tile holds W = L(K,K)^-1 (lower triangular, zeros above the diagonal): every later use of the diagonal
+// block (panel solve, backward substitution) is then a 16x16 product with W — no dependent 16-step chain on the
+// critical path of a level. L(K,K) itself is not needed again.
 MB2_HD void cholDiagTile(float* tile, float* y16, int hl, unsigned hmask, float fallback, int* fail) {
 #if defined(__CUDA_ARCH__)
   float a[16];
   tileLoadRow(tile, hl, a);
   float yv = y16[hl];
+  float rdSelf = 0.f;
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
     float piv = __shfl_sync(hmask, a[k], k, 16);
     if (!(piv > 0.f)) { piv = fallback; if (hl == k) *fail = 1; }
-    const float d = sqrtf(piv);
-    const float rd = 1.f / d;
+    const float rd = rsqrtf(piv);
+    const float d = piv * rd;
     const float lk = a[k] * rd; // L[r][k] for r > k
     const float xk = __shfl_sync(hmask, yv, k, 16) * rd;
 #pragma unroll
@@ -114,18 +118,37 @@ MB2_HD void cholDiagTile(float* tile, float* y16, int hl, unsigned hmask, float 
       a[j] -= lk * ljk;
     }
     if (hl > k) yv -= lk * xk;
-    else if (hl == k) yv = xk;
+    else if (hl == k) { yv = xk; rdSelf = rd; }
     a[k] = (hl == k) ? d : lk;
   }
-  tileStoreRow(tile, hl, a);
+  tileStoreRow(tile, hl, a); // L (lower part valid)
   y16[hl] = yv;
+  __syncwarp(hmask);
+  // column hl of W = L^-1 by forward substitution against e_hl (rows of L are broadcast reads)
+  float w[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float rdi = __shfl_sync(hmask, rdSelf, i, 16);
+    float Lrow[16];
+    tileLoadRow(tile, i, Lrow);
+    float s0 = (i == hl) ? 1.f : 0.f, s1 = 0.f;
+#pragma unroll
+    for (int m = 0; m < 16; ++m)
+      if (m < i) { if (m & 1) s1 += Lrow[m] * w[m]; else s0 -= Lrow[m] * w[m]; }
+    w[i] = (s0 - s1) * rdi;
+  }
+  __syncwarp(hmask);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) tile[tileIdx(i, hl)] = w[i]; // W[i][hl]; zero above the diagonal
 #else
   if (hl != 0) return; // host emulation: one caller does the whole tile with the same operation order
+  float rdv[16];
   for (int k = 0; k < 16; ++k) {
     float piv = tile[tileIdx(k, k)];
     if (!(piv > 0.f)) { piv = fallback; *fail = 1; }
-    const float d = sqrtf(piv);
-    const float rd = 1.f / d;
+    const float rd = 1.f / sqrtf(piv);
+    const float d = piv * rd;
+    rdv[k] = rd;
     float lk[16];
     for (int r = 0; r < 16; ++r) lk[r] = tile[tileIdx(r, k)] * rd;
     const float xk = y16[k] * rd;
@@ -135,25 +158,31 @@ MB2_HD void cholDiagTile(float* tile, float* y16, int hl, unsigned hmask, float 
     y16[k] = xk;
     tile[tileIdx(k, k)] = d;
   }
+  float W[16][16];
+  for (int j = 0; j < 16; ++j)
+    for (int i = 0; i < 16; ++i) {
+      float s0 = (i == j) ? 1.f : 0.f, s1 = 0.f;
+      for (int m = 0; m < i; ++m) { if (m & 1) s1 += tile[tileIdx(i, m)] * W[m][j]; else s0 -= tile[tileIdx(i, m)] * W[m][j]; }
+      W[i][j] = (s0 - s1) * rdv[i];
+    }
+  for (int i = 0; i < 16; ++i) for (int j = 0; j < 16; ++j) tile[tileIdx(i, j)] = W[i][j];
 #endif
 }
 
-// ---- phase B: X = A(I,K) L(K,K)^-T for one panel tile; lane hl owns matrix row hl ----
+// ---- phase B: X = A(I,K) L(K,K)^-T = A W^T for one panel tile; lane hl owns matrix row hl ----
 // (panel tiles are stored transposed from the start, so a lane reads and writes only its own column)
-MB2_HD void cholPanelSolve(float* tile, const float* diag, int hl) {
+MB2_HD void cholPanelSolve(float* tile, const float* diagW, int hl) {
   float a[16], x[16];
 #pragma unroll
   for (int c = 0; c < 16; ++c) a[c] = tile[tileIdx(c, hl)];
 #pragma unroll
   for (int c = 0; c < 16; ++c) {
-    float d[16];
-    tileLoadRow(diag, c, d); // row c of L(K,K): broadcast reads
-    float s0 = a[c], s1 = 0.f;
+    float wr[16];
+    tileLoadRow(diagW, c, wr); // row c of W: broadcast reads; entries beyond the diagonal are zero
+    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      if (j < c) { if (j & 1) s1 += x[j] * d[j]; else s0 -= x[j] * d[j]; }
-    }
-    x[c] = (s0 - s1) / d[c];
+    for (int j = 0; j < 16; ++j) { if (j & 1) s1 += a[j] * wr[j]; else s0 += a[j] * wr[j]; }
+    x[c] = s0 + s1;
   }
 #pragma unroll
   for (int c = 0; c < 16; ++c) tile[tileIdx(c, hl)] = x[c]; // transposed: T[c][r]
@@ -210,23 +239,23 @@ MB2_HD void cholBackwardColumn(const float* tiles, float* y, const CholSchedDev&
 #pragma unroll
     for (int r = 0; r < 16; ++r) s -= t[r] * yi[r];
   }
-  const float* D = tiles + size_t(S.diagTile[K]) * 256;
+  // x_K = W^T s with W = L(K,K)^-1 stored by phase A: stage s, then lane c accumulates column c of W
+  const float* W = tiles + size_t(S.diagTile[K]) * 256;
 #if defined(__CUDA_ARCH__)
+  float x = 0.f;
 #pragma unroll
-  for (int k = 15; k >= 0; --k) {
-    const float xk = __shfl_sync(hmask, s, k, 16) / D[tileIdx(k, k)];
-    if (hl < k) s -= D[tileIdx(k, hl)] * xk;
-    else if (hl == k) s = xk;
-  }
-  y[K * 16 + hl] = s;
+  for (int r = 0; r < 16; ++r) x += W[tileIdx(r, hl)] * __shfl_sync(hmask, s, r, 16);
+  y[K * 16 + hl] = x;
 #else
-  // host emulation: lanes run one after the other, so stage the sums, then lane 15 (last) solves
+  // host emulation: lanes run one after the other, so stage the sums, then lane 15 (last) finishes the block
   y[K * 16 + hl] = s;
   if (hl != 15) return;
-  for (int k = 15; k >= 0; --k) {
-    const float xk = y[K * 16 + k] / D[tileIdx(k, k)];
-    for (int c = 0; c < k; ++c) y[K * 16 + c] -= D[tileIdx(k, c)] * xk;
-    y[K * 16 + k] = xk;
+  float sv[16];
+  for (int r = 0; r < 16; ++r) sv[r] = y[K * 16 + r];
+  for (int c = 0; c < 16; ++c) {
+    float x = 0.f;
+    for (int r = 0; r < 16; ++r) x += W[tileIdx(r, c)] * sv[r];
+    y[K * 16 + c] = x;
   }
 #endif
 }

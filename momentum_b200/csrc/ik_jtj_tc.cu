@@ -16,11 +16,12 @@
 // converter warps derives hi (in place) and lo (second buffer, same swizzled positions) from the raw
 // fp32 slab that TMA delivered.
 //
-// Roles in one persistent CTA (1 CTA / SM, 320 threads):
+// Roles in one persistent CTA (1 CTA / SM, 448 threads):
 //   warp 0        TMA producer (one elected lane)
 //   warp 1        TMEM allocator + MMA issuer (one elected lane)
-//   warps 2..5    hi/lo converters
-//   warps 6..9    epilogue: TMEM -> registers -> global (column-major lower H, coalesced along rows)
+//   warps 2..9    hi/lo converters
+//   warps 10..13  epilogue: TMEM -> registers -> shared (32x32 transpose stage) -> global rows of the symmetric matrix,
+//                 every store instruction covering four full 128-byte lines
 // Pipelines: smem ring full -> converted -> (MMA) -> empty; TMEM full/empty between MMA and epilogue.
 #include "ik_jtj_tc.cuh"
 
@@ -37,7 +38,9 @@ namespace mb2 {
 
 namespace {
 
-constexpr int kTcThreads = 320;
+constexpr int kTcThreads = 448;      // warp 0 TMA, warp 1 MMA, warps 2-9 converters, warps 10-13 epilogue
+constexpr int kConvThreads = 256;
+constexpr int kStageRowFloats = 36;  // epilogue staging row: 32 floats + 4 pad (16-byte aligned, conflict-free float4 rows)
 constexpr int kKBlock = 32;         // floats per K block = one 128-byte swizzle row
 constexpr int kRowBytes = 128;
 constexpr int kUmmaK = 8;           // tf32: 32 bytes of K per instruction
@@ -124,6 +127,22 @@ __device__ __forceinline__ void tmemLoad16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmemLoad32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, "
+      "%23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+        "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 // start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) (8 rows * 128 B)
 // | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64)
@@ -149,10 +168,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
   const uint32_t tmemFullBar = barBase + 8u * (3 * p.stages);
   const uint32_t tmemEmptyBar = tmemFullBar + 8u;
   const uint32_t tmemSlot = tmemEmptyBar + 8u;
+  const uint32_t stageOff = ((tmemSlot + 16u - base) + 15u) & ~15u; // epilogue transpose stages: 4 warps x 32 rows x 36 floats
   uint8_t* gen = smemRaw + (base - smemAddr(smemRaw)); // generic pointer to the aligned base
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbarInit(fullBar(s), 1); mbarInit(convBar(s), 128); mbarInit(emptyBar(s), 1); }
+    for (int s = 0; s < p.stages; ++s) { mbarInit(fullBar(s), 1); mbarInit(convBar(s), kConvThreads); mbarInit(emptyBar(s), 1); }
     mbarInit(tmemFullBar, 1);
     mbarInit(tmemEmptyBar, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -226,9 +246,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
       }
       if (p.profile && blockIdx.x == 0) printf("tc-profile mma: total %lld waitTmemEmpty %lld waitConverted %lld\n", clock64() - tStart, wTmem, wConv);
     }
-  } else if (warp < 6) {
+  } else if (warp < 10) {
     // ---------------- converters: raw fp32 -> tf32 hi (in place) and lo ----------------
-    const int ct = threadIdx.x - 64; // 0..127
+    const int ct = threadIdx.x - 64; // 0..255
     int s = 0;
     uint32_t ph = 0;
     const int vecs = (int)(slabBytes / 16u);
@@ -241,7 +261,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
         wFull += clock64() - t0;
         float4* hi = reinterpret_cast<float4*>(gen + stageBytes * s);
         float4* lo = reinterpret_cast<float4*>(gen + stageBytes * s + slabBytes);
-        for (int i = ct; i < vecs; i += 128) {
+#pragma unroll 4
+        for (int i = ct; i < vecs; i += kConvThreads) {
           const float4 x = hi[i];
           uint4 h;
           h.x = toTf32(x.x); h.y = toTf32(x.y); h.z = toTf32(x.z); h.w = toTf32(x.w);
@@ -262,6 +283,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
   } else {
     // ---------------- epilogue: TMEM -> global, column-major lower triangle of [JtJ; Jtr] ----------------
     const int q = warp & 3; // TMEM lane quarter this warp may access
+    float* stage = reinterpret_cast<float*>(gen + stageOff) + (warp - 10) * 32 * kStageRowFloats;
     uint32_t eph = 0;
     long long wFullT = 0, tStart = clock64(), tLd = 0, nChunks = 0;
     for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
@@ -272,29 +294,43 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
       wFullT += clock64() - t0;
       tcFenceAfter();
       for (int t = 0; t < p.mTiles; ++t) {
-        const int row = t * 128 + q * 32 + lane;                 // row of [J r]^T [J r]
+        const int rowBase = t * 128 + q * 32;                     // first of this warp's 32 rows of [J r]^T [J r]
+        const int row = rowBase + lane;
         const int i = row < p.ns ? row : (row == p.numCols ? p.ns : -1); // row of the (ns+1) system; -1: not wanted
-        const int anyRow = __reduce_max_sync(0xffffffffu, i);
-        if (anyRow < 0) continue;                                 // warp-uniform: nothing to write from these 32 rows
+        if (__reduce_max_sync(0xffffffffu, i) < 0) continue;       // warp-uniform: nothing to write from these 32 rows
         const int nT = t == 0 ? p.n0 : p.n1;
         const uint32_t colBase = tmemBase + ((uint32_t)(q * 32) << 16) + (t == 0 ? 0u : (uint32_t)p.n0);
-        float* Hrow = H + (size_t)(i < 0 ? 0 : i) * p.ldH;
-        for (int c0 = 0; c0 < nT; c0 += 16) {
-          float v[16];
-          const long long tl0 = p.profile ? clock64() : 0;
-          tmemLoad16(colBase + (uint32_t)c0, v);
-          if (p.profile) { tLd += clock64() - tl0; ++nChunks; }
-          if (i < 0) continue;
-          if (p.ns == p.numCols || c0 + 16 <= p.ns) {
-            // every thread owns one full row of the symmetric matrix: 64 contiguous bytes per chunk
-            // (columns >= ns + 1 of the last chunk are zero products of zero-filled TMA rows; ldH is a multiple of 16)
-            if (c0 <= p.ns) {
+        if (p.ns == p.numCols) {
+          // solver path: full rows. 32x32 blocks go TMEM -> registers -> shared (row = TMEM lane) -> global, re-mapped so
+          // that one store instruction writes four rows x 128 contiguous bytes.
+          for (int c0 = 0; c0 < nT; c0 += 32) {
+            float v[32];
+            const long long tl0 = p.profile ? clock64() : 0;
+            if (c0 + 32 <= nT) tmemLoad32(colBase + (uint32_t)c0, v);
+            else { tmemLoad16(colBase + (uint32_t)c0, v); for (int k = 16; k < 32; ++k) v[k] = 0.f; }
+            if (p.profile) { tLd += clock64() - tl0; ++nChunks; }
 #pragma unroll
-              for (int g4 = 0; g4 < 4; ++g4)
-                *reinterpret_cast<float4*>(Hrow + c0 + 4 * g4) = make_float4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
+            for (int g4 = 0; g4 < 8; ++g4)
+              *reinterpret_cast<float4*>(stage + lane * kStageRowFloats + 4 * g4) = make_float4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
+            __syncwarp();
+            const int c = c0 + 4 * (lane & 7);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int rr = 4 * k + (lane >> 3);
+              const int rowAbs = rowBase + rr;
+              const int io = rowAbs < p.ns ? rowAbs : (rowAbs == p.numCols ? p.ns : -1);
+              if (io >= 0 && c < p.ldH)
+                *reinterpret_cast<float4*>(H + (size_t)io * p.ldH + c) = *reinterpret_cast<const float4*>(stage + rr * kStageRowFloats + 4 * (lane & 7));
             }
-          } else {
-            // leading-block request (ns < numCols, getJtJR parity entry): columns ns.. are skipped except the residual column
+            __syncwarp();
+          }
+        } else {
+          // leading-block request (ns < numCols, getJtJR parity entry): columns ns.. are skipped except the residual column
+          float* Hrow = H + (size_t)(i < 0 ? 0 : i) * p.ldH;
+          for (int c0 = 0; c0 < nT; c0 += 16) {
+            float v[16];
+            tmemLoad16(colBase + (uint32_t)c0, v);
+            if (i < 0) continue;
 #pragma unroll
             for (int cc = 0; cc < 16; ++cc) {
               const int c = c0 + cc;
@@ -308,7 +344,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
       mbarArrive(tmemEmptyBar);
       eph ^= 1u;
     }
-    if (p.profile && blockIdx.x == 0 && threadIdx.x == 6 * 32) printf("tc-profile epilogue: total %lld waitTmemFull %lld tmemLoad %lld chunks %lld\n", clock64() - tStart, wFullT, tLd, nChunks);
+    if (p.profile && blockIdx.x == 0 && threadIdx.x == 10 * 32) printf("tc-profile epilogue: total %lld waitTmemFull %lld tmemLoad %lld chunks %lld\n", clock64() - tStart, wFullT, tLd, nChunks);
   }
   tcFenceBefore();
   __syncthreads();
@@ -390,11 +426,11 @@ cudaError_t launchJtJTensor(const JtJArgs& a, int passes, cudaStream_t stream) {
   p.hStride = a.hStride;
   p.profile = getenv("MB2_TC_PROFILE") != nullptr ? 1 : 0;
   const size_t stageBytes = size_t(sh.boxRows) * kRowBytes * (p.passes == 3 ? 2 : 1);
-  int stages = int((200 * 1024) / stageBytes);
+  int stages = int((196 * 1024) / stageBytes);
   if (stages > 6) stages = 6;
   if (stages < 2) return cudaErrorInvalidConfiguration;
   p.stages = stages;
-  const size_t smem = stageBytes * stages + 1024 /*alignment slack*/ + 8 * (3 * stages + 2) + 16;
+  const size_t smem = stageBytes * stages + 1024 /*alignment slack*/ + 8 * (3 * stages + 2) + 48 + 4 * 32 * kStageRowFloats * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(jtjTensorKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
   int dev = 0, sms = 0;

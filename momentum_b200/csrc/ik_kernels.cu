@@ -370,6 +370,7 @@ __global__ void __launch_bounds__(kSchedThreads, 2) choleskyScheduledKernel(cons
   // T[c][r] = H(r,c) = H(c,r) is sixteen contiguous runs of row (tileBase(J)+c) of H. All copies are 4-byte cp.async
   // (LDGSTS) so that every thread has its ~60 loads in flight at once.
   const float* Hs = a.H + size_t(b) * a.hStride;
+#pragma unroll 4
   for (int idx = tid; idx < S.numTiles * 256; idx += kSchedThreads) {
     const int t = idx >> 8, e = idx & 255, c = e >> 4, r = e & 15;
     const int I = S.tileRow[t], J = S.tileCol[t];
