@@ -100,10 +100,14 @@ MB2_HD void tileStoreRow(float* tile, int r, const float* a) {
 // critical path of a level. L(K,K) itself is not needed again.
 MB2_HD void cholDiagTile(float* tile, float* y16, int hl, unsigned hmask, float fallback, int* fail) {
 #if defined(__CUDA_ARCH__)
+  // the gather fills the diagonal tile as S[c][r] = H(r, c) for r >= c only (contiguous runs of the upper triangle of H):
+  // matrix row hl, columns k <= hl, is therefore storage column hl
   float a[16];
-  tileLoadRow(tile, hl, a);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) a[k] = tile[tileIdx(k, hl)];
   float yv = y16[hl];
   float rdSelf = 0.f;
+  __syncwarp(hmask); // every lane has read its column before any lane overwrites the tile with rows of L
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
     float piv = __shfl_sync(hmask, a[k], k, 16);
@@ -143,6 +147,9 @@ MB2_HD void cholDiagTile(float* tile, float* y16, int hl, unsigned hmask, float 
 #else
   if (hl != 0) return; // host emulation: one caller does the whole tile with the same operation order
   float rdv[16];
+  { // same convention as the device path: the valid half of the tile is S[c][r], r >= c; mirror it first
+    for (int r = 0; r < 16; ++r) for (int c = 0; c < r; ++c) tile[tileIdx(r, c)] = tile[tileIdx(c, r)];
+  }
   for (int k = 0; k < 16; ++k) {
     float piv = tile[tileIdx(k, k)];
     if (!(piv > 0.f)) { piv = fallback; *fail = 1; }

@@ -20,7 +20,7 @@
 //   warp 0        TMA producer (one elected lane)
 //   warp 1        TMEM allocator + MMA issuer (one elected lane)
 //   warps 2..9    hi/lo converters
-//   warps 10..13  epilogue: TMEM -> registers -> shared (32x32 transpose stage) -> global rows of the symmetric matrix,
+//   warps 10..13  epilogue: TMEM -> registers -> shared (32x32 transpose stage) -> global rows (upper triangle) of the symmetric matrix,
 //                 every store instruction covering four full 128-byte lines
 // Pipelines: smem ring full -> converted -> (MMA) -> empty; TMEM full/empty between MMA and epilogue.
 #include "ik_jtj_tc.cuh"
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
             const uint32_t aOff = (uint32_t)t * 128u * kRowBytes;
             for (int pass = 0; pass < p.passes; ++pass) {
               const uint32_t aBase = (pass == 2 ? lo : hi) + aOff; // hi*hi, hi*lo, lo*hi
-              const uint32_t bBase = (pass == 1 ? lo : hi);
+              const uint32_t bBase = (pass == 1 ? lo : hi) + aOff; // tile 1 multiplies against rows 128.. only (upper triangle)
 #pragma unroll
               for (int k4 = 0; k4 < kKBlock / kUmmaK; ++k4) {
                 const uint32_t acc = (kb == 0 && pass == 0 && k4 == 0) ? 0u : 1u;
@@ -313,13 +313,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
             for (int g4 = 0; g4 < 8; ++g4)
               *reinterpret_cast<float4*>(stage + lane * kStageRowFloats + 4 * g4) = make_float4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
             __syncwarp();
-            const int c = c0 + 4 * (lane & 7);
+            const int c = t * 128 + c0 + 4 * (lane & 7); // matrix column of this lane's float4
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
               const int rr = 4 * k + (lane >> 3);
               const int rowAbs = rowBase + rr;
               const int io = rowAbs < p.ns ? rowAbs : (rowAbs == p.numCols ? p.ns : -1);
-              if (io >= 0 && c < p.ldH)
+              if (io >= 0 && c < p.ldH && c + 3 >= io) // upper triangle (col >= row) only: everything downstream reads H(min, max)
                 *reinterpret_cast<float4*>(H + (size_t)io * p.ldH + c) = *reinterpret_cast<const float4*>(stage + rr * kStageRowFloats + 4 * (lane & 7));
             }
             __syncwarp();
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
             if (i < 0) continue;
 #pragma unroll
             for (int cc = 0; cc < 16; ++cc) {
-              const int c = c0 + cc;
+              const int c = t * 128 + c0 + cc;
               if (c < p.ns) Hrow[c] = v[cc];
               else if (c == p.numCols) Hrow[p.ns] = v[cc];
             }
@@ -380,8 +380,8 @@ Shape shapeFor(int numCols) {
   s.mTiles = s.rows > 128 ? 2 : 1;
   s.boxRows = s.mTiles * 128;
   const int r16 = roundUpI(s.rows, 16);
-  s.n0 = r16;                      // both row tiles span every column: the epilogue writes full rows of the symmetric matrix
-  s.n1 = s.mTiles == 2 ? r16 : 0;
+  s.n0 = r16;                      // rows 0..127 against every column
+  s.n1 = s.mTiles == 2 ? r16 - 128 : 0; // rows 128.. against columns 128.. only: consumers read the upper triangle (col >= row)
   int need = s.n0 + s.n1, c = 32;
   while (c < need) c <<= 1;
   s.tmemCols = c;

@@ -345,7 +345,7 @@ size_t choleskyScheduledSmemBytes(int n, int nPad, int numTiles, int blobInts) {
   return sizeof(float) * (size_t(numTiles) * 256 + size_t(nPad) + 2 * size_t((n + 3) & ~3)) + sizeof(int32_t) * size_t((blobInts + 3) & ~3) + 16;
 }
 
-__global__ void __launch_bounds__(kSchedThreads, 2) choleskyScheduledKernel(const CholArgs a, const CholSchedDev Sg) {
+__global__ void __launch_bounds__(kSchedThreads, 3) choleskyScheduledKernel(const CholArgs a, const CholSchedDev Sg) {
   extern __shared__ __align__(16) float smemS[];
   const int b = blockIdx.x;
   if (a.active[b] == 0) return;
@@ -370,22 +370,34 @@ __global__ void __launch_bounds__(kSchedThreads, 2) choleskyScheduledKernel(cons
   // T[c][r] = H(r,c) = H(c,r) is sixteen contiguous runs of row (tileBase(J)+c) of H. All copies are 4-byte cp.async
   // (LDGSTS) so that every thread has its ~60 loads in flight at once.
   const float* Hs = a.H + size_t(b) * a.hStride;
-#pragma unroll 4
-  for (int idx = tid; idx < S.numTiles * 256; idx += kSchedThreads) {
-    const int t = idx >> 8, e = idx & 255, c = e >> 4, r = e & 15;
+  // one work item = four consecutive matrix rows r4..r4+3 of one tile column c (16 bytes of the transposed tile row c)
+#pragma unroll 2
+  for (int idx = tid; idx < S.numTiles * 64; idx += kSchedThreads) {
+    const int t = idx >> 6, e = idx & 63, c = e >> 2, r4 = (e & 3) << 2;
     const int I = S.tileRow[t], J = S.tileCol[t];
-    const int gi = S.perm[16 * I + r], gj = S.perm[16 * J + c];
-    float* dst = tiles + (idx - e + tileIdx(c, r));
-    if (gi >= 0 && gj >= 0) {
-      const unsigned sdst = static_cast<unsigned>(__cvta_generic_to_shared(dst));
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst), "l"(Hs + size_t(gj) * a.ldH + gi) : "memory");
+    if (I == J && r4 + 3 < c) continue; // diagonal tiles are only read at (row >= col), see cholDiagTile
+    const int gj = S.perm[16 * J + c];
+    const int gi0 = S.perm[16 * I + r4], gi3 = S.perm[16 * I + r4 + 3];
+    float* dst = tiles + (size_t(t) * 256 + tileGrp(c, r4 >> 2));
+    const unsigned sdst = static_cast<unsigned>(__cvta_generic_to_shared(dst));
+    if (gj >= 0 && gi3 >= 0 && (gi0 & 3) == 0 && gi0 >= gj) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(Hs + size_t(gj) * a.ldH + gi0) : "memory");
     } else {
-      *dst = (I == J && r == c) ? 1.f : 0.f; // padding variable: identity row/column
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int gi = S.perm[16 * I + r4 + q];
+        if (gi >= 0 && gj >= 0) {
+          const int lo = gi < gj ? gi : gj, hi = gi < gj ? gj : gi;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst + 4u * q), "l"(Hs + size_t(lo) * a.ldH + hi) : "memory");
+        } else {
+          dst[q] = (I == J && r4 + q == c) ? 1.f : 0.f; // padding variable: identity row/column
+        }
+      }
     }
   }
   for (int s = tid; s < S.nPad; s += kSchedThreads) {
     const int p = S.perm[s];
-    const float g = p >= 0 ? Hs[size_t(n) * a.ldH + p] : 0.f;
+    const float g = p >= 0 ? Hs[size_t(p) * a.ldH + n] : 0.f; // J^T r sits in column n of every row
     y[s] = g;
     if (p >= 0) gsub[p] = g;
   }

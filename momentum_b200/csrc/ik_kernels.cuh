@@ -26,8 +26,8 @@ struct JtJArgs {             // K2
   const float* jacobian;     // [B][numCols + 1][ldJ]; column numCols = residual
   int32_t numCols, ldJ, kRows; // kRows = contraction length (rows rounded up to 4)
   int32_t ns;                // leading ns columns enter the normal equations (ns <= numCols)
-  float* H;                  // [B][ns+1][ldH] FULL symmetric matrix [J r]^T [J r] restricted to the leading ns columns + r:
-                             // H[i*ldH + j] = H[j*ldH + i]; row/column ns holds J^T r (H[i*ldH + ns] = (J^T r)_i)
+  float* H;                  // [B][ns+1][ldH] symmetric matrix [J r]^T [J r] restricted to the leading ns columns + r, row-major;
+                             // only the UPPER triangle H[i*ldH + j], j >= i, is guaranteed (column ns = J^T r: H[i*ldH + ns] = (J^T r)_i)
   int32_t ldH;               // multiple of 16, >= ns + 1
   size_t hStride;            // floats per instance in H
   const int32_t* active;

@@ -112,11 +112,11 @@ static void jtjOne(const mb2_solver_function* f, int b, int ns, float* H, int ld
     for (int j = 0; j <= i; ++j) {
       float s = 0.f;
       for (int k = 0; k < K; ++k) s = fmaf(J[size_t(i) * f->ldJ + k], J[size_t(j) * f->ldJ + k], s);
-      H[size_t(j) * ldH + i] = s; H[size_t(i) * ldH + j] = s; // full symmetric
+      H[size_t(j) * ldH + i] = s; // upper triangle only (row j, column i >= j), like the tensor-core epilogue
     }
     float g = 0.f;
     for (int k = 0; k < K; ++k) g = fmaf(J[size_t(i) * f->ldJ + k], r[k], g);
-    H[size_t(i) * ldH + ns] = g; H[size_t(ns) * ldH + i] = g;
+    H[size_t(i) * ldH + ns] = g;
   }
 }
 
@@ -176,11 +176,12 @@ static int cholScheduledOne(const CholSchedDev& S, const float* Hs, int ldH, int
     const int t = idx >> 8, e = idx & 255, c = e >> 4, r = e & 15;
     const int I = S.tileRow[t], J = S.tileCol[t];
     const int gi = S.perm[16 * I + r], gj = S.perm[16 * J + c];
-    tl[idx - e + tileIdx(c, r)] = (gi >= 0 && gj >= 0) ? Hs[size_t(gj) * ldH + gi] : ((I == J && r == c) ? 1.f : 0.f);
+    if (I == J && r < c) { tl[idx - e + tileIdx(c, r)] = -12345.f; continue; } // not gathered on the device either (must never be read)
+    tl[idx - e + tileIdx(c, r)] = (gi >= 0 && gj >= 0) ? Hs[size_t(std::min(gi, gj)) * ldH + std::max(gi, gj)] : ((I == J && r == c) ? 1.f : 0.f);
   }
   for (int s2 = 0; s2 < S.nPad; ++s2) {
     const int p = S.perm[s2];
-    const float g = p >= 0 ? Hs[size_t(n) * ldH + p] : 0.f;
+    const float g = p >= 0 ? Hs[size_t(p) * ldH + n] : 0.f;
     y[s2] = g;
     if (p >= 0) { gsub[p] = g; tl[size_t(S.diagTile[s2 >> 4]) * 256 + tileIdx(s2 & 15, s2 & 15)] += reg; }
   }
