@@ -168,6 +168,9 @@ FunctionTables mb2_solver_function::tables() const {
   T.numCols = plan.numCols;
   T.weightsPerInstance = weightsPerInstance ? 1 : 0;
   T.numWeights = numWeights;
+  T.ptNnz = int(h.ptInner.size());
+  T.numContribs = int(plan.contribs.size());
+  T.numLimitData = int(plan.limitData.size());
   return T;
 }
 

@@ -31,10 +31,34 @@ size_t sweepSmemPerInstance(const FunctionTables& T) {
   return sizeof(float) * (nPad + size_t(T.numJoints) * (kParametersPerJoint + kJointStateStride) + size_t(T.recStride) + 4);
 }
 
+// The read-only tables (character + plan) are walked by dependent loads (cell -> unit -> contributions -> joint);
+// from L2 each hop costs several hundred cycles, so a persistent CTA copies them into shared memory once.
+MB2_HD size_t tableWords(size_t count, size_t elemBytes) { return (count * elemBytes + 15) / 16 * 4; }
+size_t sweepTableBytes(const FunctionTables& T) {
+  const size_t J = T.numJoints;
+  size_t w = 0;
+  w += tableWords(J, 4) + tableWords(3 * J, 4) + tableWords(4 * J, 4);                       // parent, offset, prerot
+  w += tableWords(7 * J + 1, 4) + tableWords(T.ptNnz, 4) * 2 + tableWords(7 * J, 4);         // ptOuter, ptInner, ptVals, ptOffsets
+  w += tableWords(T.numLevels + 1, 4) + tableWords(J, 4);                                    // levelStart, levelJoints
+  w += tableWords(T.numEf, sizeof(EfDesc)) + tableWords(T.numUnits, sizeof(UnitDesc)) + tableWords(T.numCells, sizeof(CellDesc));
+  w += tableWords(T.numContribs, sizeof(ContribDesc)) + tableWords(T.numLimitData, 4);
+  return w * 4;
+}
+
+template <class E>
+__device__ __forceinline__ void stageTable(const E*& table, size_t count, uint32_t*& cursor) {
+  static_assert(sizeof(E) % 4 == 0, "tables are staged word by word");
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(table);
+  const size_t words = count * (sizeof(E) / 4);
+  for (size_t i = threadIdx.x; i < words; i += blockDim.x) cursor[i] = src[i];
+  table = reinterpret_cast<const E*>(cursor);
+  cursor += tableWords(count, sizeof(E));
+}
+
 template <bool kJacobian>
-__global__ void __launch_bounds__(256) sweepKernel(const SweepArgs a) {
-  extern __shared__ float smem[];
-  const FunctionTables& T = a.T;
+__global__ void __launch_bounds__(512) sweepKernel(const SweepArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  FunctionTables T = a.T;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warpsPerCta = blockDim.x >> 5;
   const int nPad = (T.numParams + 3) & ~3;
@@ -44,6 +68,17 @@ __global__ void __launch_bounds__(256) sweepKernel(const SweepArgs a) {
   float* js = jp + T.numJoints * kParametersPerJoint;
   float* rec = js + T.numJoints * kJointStateStride;
   const int numJointParams = T.numJoints * kParametersPerJoint;
+  if (a.stageTables) {
+    uint32_t* cursor = reinterpret_cast<uint32_t*>(smem + ((size_t(warpsPerCta) * perWarp + 3) & ~size_t(3)));
+    const size_t J = T.numJoints;
+    stageTable(T.parent, J, cursor); stageTable(T.offset, 3 * J, cursor); stageTable(T.prerot, 4 * J, cursor);
+    stageTable(T.ptOuter, 7 * J + 1, cursor); stageTable(T.ptInner, T.ptNnz, cursor); stageTable(T.ptVals, T.ptNnz, cursor);
+    stageTable(T.ptOffsets, 7 * J, cursor);
+    stageTable(T.levelStart, T.numLevels + 1, cursor); stageTable(T.levelJoints, J, cursor);
+    stageTable(T.efs, T.numEf, cursor); stageTable(T.units, T.numUnits, cursor); stageTable(T.cells, T.numCells, cursor);
+    stageTable(T.contribs, T.numContribs, cursor); stageTable(T.limitData, T.numLimitData, cursor);
+    __syncthreads();
+  }
 
   for (int b = blockIdx.x * warpsPerCta + warp; b < a.batch; b += gridDim.x * warpsPerCta) {
     if (a.active != nullptr && a.active[b] == 0) continue;
@@ -79,20 +114,33 @@ __global__ void __launch_bounds__(256) sweepKernel(const SweepArgs a) {
 
 static int g_numSms = 0;
 static int g_maxSmemOptin = 0;
+static int g_maxSmemPerSm = 0;
 
-cudaError_t launchSweep(const SweepArgs& a, bool jacobian, cudaStream_t stream) {
+cudaError_t launchSweep(const SweepArgs& a0, bool jacobian, cudaStream_t stream) {
+  SweepArgs a = a0;
   const size_t per = sweepSmemPerInstance(a.T);
-  int warps = 8;
-  while (warps > 1 && per * warps > 100 * 1024) warps >>= 1;
-  const size_t smem = per * warps;
-  if (smem > size_t(g_maxSmemOptin)) return cudaErrorInvalidConfiguration;
+  const size_t tableBytes = sweepTableBytes(a.T) + 16;
+  const size_t budget = size_t(g_maxSmemOptin);
+  // persistent CTAs: 16 warps (instances in flight) + the staged tables when they fit, else the tables stay in L2
+  int warps = 16;
+  a.stageTables = 1;
+  while (warps > 4 && per * warps + tableBytes > budget) warps >>= 1;
+  if (per * warps + tableBytes > budget) {
+    a.stageTables = 0;
+    warps = 8;
+    while (warps > 1 && per * warps > 100 * 1024) warps >>= 1;
+  }
+  const size_t smem = per * warps + (a.stageTables ? tableBytes : 0);
+  if (smem > budget) return cudaErrorInvalidConfiguration;
   cudaError_t e;
   if (jacobian) e = cudaFuncSetAttribute(sweepKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   else e = cudaFuncSetAttribute(sweepKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
   const int ctasNeeded = (a.batch + warps - 1) / warps;
-  const int ctasPerSm = (int)((200 * 1024) / (smem + 1024)) > 0 ? (int)((200 * 1024) / (smem + 1024)) : 1;
-  int grid = g_numSms * (ctasPerSm > 8 ? 8 : ctasPerSm);
+  int ctasPerSm = (int)((size_t(g_maxSmemPerSm)) / (smem + 1024));
+  if (ctasPerSm < 1) ctasPerSm = 1;
+  if (ctasPerSm * warps > 32) ctasPerSm = 32 / warps > 0 ? 32 / warps : 1;
+  int grid = g_numSms * ctasPerSm;
   if (grid > ctasNeeded) grid = ctasNeeded;
   if (grid < 1) grid = 1;
   if (jacobian) sweepKernel<true><<<grid, warps * 32, smem, stream>>>(a);
@@ -458,6 +506,8 @@ cudaError_t initKernelAttributes() {
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   e = cudaDeviceGetAttribute(&g_numSms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return e;
+  e = cudaDeviceGetAttribute(&g_maxSmemPerSm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
   if (e != cudaSuccess) return e;
   return cudaDeviceGetAttribute(&g_maxSmemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
 }

@@ -19,6 +19,7 @@ struct SweepArgs {           // K1 (FK + residual + Jacobian) and K4 (FK + error
   double* errors;            // [B]
   const int32_t* active;     // optional per-instance mask
   float* stateOut;           // optional [B][J][8]
+  int32_t stageTables;       // set by launchSweep: copy the read-only tables into shared memory
 };
 
 struct JtJArgs {             // K2

@@ -111,6 +111,8 @@ struct FunctionTables {
                         // the device matrix has numCols + 1 columns: the last one is the residual vector
   int32_t weightsPerInstance; // 0: cweights [numWeights] shared, 1: [B][numWeights]
   int32_t numWeights;
+  // table sizes (the sweep kernel stages every table in shared memory when they fit)
+  int32_t ptNnz, numContribs, numLimitData;
 };
 
 } // namespace mb2

@@ -1,0 +1,14 @@
+#!/bin/bash
+# Runs on the GPU box (gpurun): launch list + one full ncu capture of each hot kernel of the default bench workload.
+# Usage: scripts/profile_gpu.sh <tag>     -> gpurun_out/<tag>_launches.csv, gpurun_out/<tag>_{k1,k2,k3}.ncu-rep
+set -u
+TAG=${1:-r01}
+OUT=gpurun_out
+mkdir -p $OUT
+BENCH="python bench.py --steps 1 --warmup 1 --no-cpu-baseline"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv $BENCH > $OUT/${TAG}_launches.log 2>&1
+for spec in "k1:sweepKernel" "k2:jtjTensorKernel" "k3:choleskyScheduledKernel"; do
+  name=${spec%%:*}; regex=${spec##*:}
+  ncu --set full --clock-control none --import-source on -k regex:$regex --launch-skip 12 -c 1 -f -o $OUT/${TAG}_${name} $BENCH > $OUT/${TAG}_${name}.log 2>&1
+done
+ls -la $OUT

@@ -7,6 +7,7 @@
 // nothing in momentum_b200/ loads it.
 #include <cfloat>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -518,5 +519,28 @@ extern "C" int emu_chol_schedule_stats(int n, int numCliques, const int* cliqueS
   if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
   stats[0] = s.numTileCols; stats[1] = s.numTiles; stats[2] = s.numLevels; stats[3] = s.tileOps; stats[4] = s.denseTileOps;
   stats[5] = (long long)s.taskDst.size(); stats[6] = (long long)s.panelTile.size();
+  return MB2_OK;
+}
+
+extern "C" int emu_chol_schedule_dump(int n, int numCliques, const int* cliqueStart, const int* cliqueCols, int forceDense) {
+  std::vector<std::vector<int>> cl(numCliques);
+  for (int c = 0; c < numCliques; ++c) cl[c].assign(cliqueCols + cliqueStart[c], cliqueCols + cliqueStart[c + 1]);
+  CholSchedule s;
+  const std::string e = buildCholSchedule(n, cl, forceDense != 0, s);
+  if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
+  std::printf("n %d nPad %d tilecols %d tiles %d levels %d\n", s.n, s.nPad, s.numTileCols, s.numTiles, s.numLevels);
+  for (int L = 0; L < s.numLevels; ++L) {
+    int maxPairs = 0, totPairs = 0;
+    for (int t = s.levelTaskStart[L]; t < s.levelTaskStart[L + 1]; ++t) { const int p = s.taskPairStart[t + 1] - s.taskPairStart[t]; maxPairs = std::max(maxPairs, p); totPairs += p; }
+    std::printf(" level %d: cols %d panels %d tasks %d pairs %d maxPairsPerTask %d vtasks %d | cols:", L, s.levelColStart[L + 1] - s.levelColStart[L],
+                s.levelPanelStart[L + 1] - s.levelPanelStart[L], s.levelTaskStart[L + 1] - s.levelTaskStart[L], totPairs, maxPairs,
+                s.levelVTaskStart[L + 1] - s.levelVTaskStart[L]);
+    for (int c = s.levelColStart[L]; c < s.levelColStart[L + 1]; ++c) {
+      int valid = 0;
+      for (int r = 0; r < 16; ++r) valid += s.perm[16 * s.levelCols[c] + r] >= 0;
+      std::printf(" %d(%d)", s.levelCols[c], valid);
+    }
+    std::printf("\n");
+  }
   return MB2_OK;
 }
