@@ -57,39 +57,66 @@ def measured_peaks():
     return dict(hbm_gbs=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")
 
 
+def measured_traffic(workload, batch):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/ncu_traffic.json);
+    only valid for the exact workload / batch they were captured on."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return {}
+    d = json.load(open(p))
+    return d.get(f"{workload}:{batch}", {}).get("dram_bytes_per_launch", {})
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / clock-event reasons sampled DURING the timed regions (B200_PROFILING.md recipe). NVML is polled in-process
+    every 5 ms (the timed region of the default run is ~0.1 s, shorter than one nvidia-smi start-up)."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.sm, self.mask, self.max_mhz, self.handle, self.nvml = index, [], 0, None, None, None
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.error = None
 
     def start(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+            import pynvml
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            try:
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+        except Exception as e:  # noqa: BLE001
+            self.error = f"nvml unavailable: {e}"
+
+    def _poll(self):
+        nv = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                try:
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            except Exception as e:  # noqa: BLE001
+                self.error = str(e)
+                return
+            time.sleep(0.005)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[k] for r in self.rows if len(r) >= 7 for k in range(4) if r[3 + k].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.error or "nvml unavailable"], "samples": 0}
+        self.stop_flag.set()
+        self.thread.join(timeout=2)
+        reasons = sorted(name for bit, name in self.REASONS.items() if self.mask & bit)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(self.sm)}
 
 
 def run_reference(args, rank, world):
@@ -202,7 +229,6 @@ def main():
         ev1.record()
         torch.cuda.synchronize()
         total_ms += ev0.elapsed_time(ev1)
-    clocks = sampler.stop()
     barrier()
     res = solver.get_results()
     its_per_step = int(res["iterations"].sum())
@@ -230,6 +256,7 @@ def main():
         r = e2e_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()  # sampled across the device-resident and the end-to-end timed regions
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -243,11 +270,38 @@ def main():
         return
     peaks = measured_peaks()
     tf32_peak = 0.5 * peaks["bf16"]  # TF32 dense = half the bf16 rate (B200_PROFILING.md table); bf16 figure is the measured cuBLAS burst
-    jtj_flops = float(m_rows) * n * (n + 1)
-    jtj_ms = phase_ms[1] / max(1, phase_launches[1])
-    achieved = jtj_flops * B / (jtj_ms * 1e-3) / 1e12 if jtj_ms > 0 else 0.0
+    hbm_peak = peaks["hbm_gbs"]
+    st = solver.get_plan_stats()
     sweep_ms = phase_ms[0] / max(1, phase_launches[0])
+    jtj_ms = phase_ms[1] / max(1, phase_launches[1])
     chol_ms = phase_ms[2] / max(1, phase_launches[2])
+    target_floats = sum(tp.numel() for tp in target_pins) // B
+    # ALGORITHMIC bytes / flops per instance and launch (DESIGN.md section 4 derives each figure)
+    k1_bytes = 4.0 * (n + target_floats + st["jacobian_nonzeros"] + m_rows) + 8.0
+    jtj_flops = float(m_rows) * n * (n + 1)
+    k2_bytes = 4.0 * (m_rows * (st["jacobian_columns"] + 1) + (st["normal_parameters"] + 1) * (st["normal_parameters"] + 2) / 2)
+    k3_entries = st["cholesky_tiles"] * 256 if st["cholesky_tiles"] else st["normal_parameters"] * (st["normal_parameters"] + 1) / 2
+    k3_bytes = 4.0 * (k3_entries + 4 * st["normal_parameters"])
+    traffic = measured_traffic(args.workload, B)
+
+    def hbm_entry(name, key, bytes_per_instance, ms):
+        ach = bytes_per_instance * B / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                "peak_source": f"{peaks['src']} copy bandwidth", "traffic": traffic.get(key), "ms_per_launch": ms,
+                "algorithmic_bytes_per_instance": bytes_per_instance}
+
+    jtj_ach = jtj_flops * B / (jtj_ms * 1e-3) / 1e12 if jtj_ms > 0 else 0.0
+    kernels = [
+        hbm_entry("sweepKernel<true> (FK + residual + Jacobian)", "fk_residual_jacobian", k1_bytes, sweep_ms),
+        {"kernel": "jtjTensorKernel (JtJ/Jtr, tcgen05 3xTF32)" if st["jacobian_columns"] + 1 <= 256 and args.jtj_mode in (0, 2, 3) else "jtjSimtKernel",
+         "bound": "tensor", "achieved": jtj_ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": jtj_ach / tf32_peak,
+         "peak_source": f"0.5 x {peaks['src']} bf16 cuBLAS burst ({peaks['bf16']} TF/s) = TF32 dense", "traffic": traffic.get("jtj_jtr"),
+         "ms_per_launch": jtj_ms, "algorithmic_flops_per_instance": jtj_flops, "algorithmic_bytes_per_instance": k2_bytes,
+         "hbm_frac": (k2_bytes * B / (jtj_ms * 1e-3) / 1e9 / hbm_peak) if jtj_ms > 0 else 0.0},
+        hbm_entry("choleskyScheduledKernel (damped LLT + solves + update)" if st["cholesky_tiles"] else "choleskyKernel (dense LLT + solves + update)",
+                  "cholesky_update", k3_bytes, chol_ms),
+    ]
+    dominant = max(kernels, key=lambda k: k["ms_per_launch"])
     line = {
         "metric": "GN iterations/sec (batched 72-joint IK)", "value": value, "unit": "GN it/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -258,9 +312,8 @@ def main():
         "e2e": {"value": e2e_value, "unit": "GN it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "JtJ/Jtr", "bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
-                     "peak_source": f"0.5 x {peaks['src']} bf16 cuBLAS burst ({peaks['bf16']} TF/s) = TF32 dense", "traffic": None,
-                     "ms_per_launch": jtj_ms, "algorithmic_flops_per_instance": jtj_flops},
+        "roofline": dominant,
+        "roofline_all_kernels": kernels,
         "kernels_ms_per_iteration": {"fk_residual_jacobian": sweep_ms, "jtj_jtr": jtj_ms, "cholesky_update": chol_ms},
     }
     if not args.no_cpu_baseline:

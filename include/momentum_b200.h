@@ -213,6 +213,12 @@ int mb2_solver_get_counters(mb2_solver* s, uint64_t* total_iterations, uint64_t*
  * mb2_solver_set_profiling(s, 1); off by default (events serialise the stream). */
 int mb2_solver_set_profiling(mb2_solver* s, int32_t enabled);
 int mb2_solver_get_phase_times(mb2_solver* s, double ms[4], uint64_t launches[4]);
+/* Per-instance algorithmic sizes of the plan the last solve ran on (roofline accounting in bench.py; no reference
+ * counterpart): [0] structurally non-zero Jacobian entries written per iteration, [1] device Jacobian columns (without
+ * the residual column), [2] ldJ, [3] parameters in the normal equations (ns), [4] 16x16 tiles held by the tile-sparse
+ * Cholesky (0: dense Eigen-structured kernel), [5] tile multiply-accumulate blocks per factorisation, [6] levels of the
+ * tile elimination tree, [7] residual rows m. */
+int mb2_solver_get_plan_stats(mb2_solver* s, int64_t stats[8]);
 
 #ifdef __cplusplus
 }

@@ -956,6 +956,23 @@ int mb2_solver_get_counters(mb2_solver* s, uint64_t* totalIterations, uint64_t* 
   return MB2_OK;
 }
 
+int mb2_solver_get_plan_stats(mb2_solver* s, int64_t stats[8]) {
+  MB2_CHECK(s != nullptr && stats != nullptr, "null argument");
+  const mb2_solver_function* f = s->fn;
+  int64_t nnz = 0;
+  for (const CellDesc& c : f->plan.cells) nnz += f->plan.units[c.unit].numRows;
+  const bool tiles = f->planMode == 2 && f->sched && f->sched->valid;
+  stats[0] = nnz;
+  stats[1] = f->plan.numCols;
+  stats[2] = f->ldJ;
+  stats[3] = int64_t(f->plan.enabledList.size());
+  stats[4] = tiles ? f->sched->host.numTiles : 0;
+  stats[5] = tiles ? f->sched->host.tileOps : 0;
+  stats[6] = tiles ? f->sched->host.numLevels : 0;
+  stats[7] = f->plan.numRows;
+  return MB2_OK;
+}
+
 int mb2_solver_get_phase_times(mb2_solver* s, double ms[4], uint64_t launches[4]) {
   MB2_CHECK(s != nullptr, "null solver");
   for (int k = 0; k < 4; ++k) {

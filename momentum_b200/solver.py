@@ -60,7 +60,7 @@ CABI_SYMBOLS = [
     "mb2_solver_function_get_jacobian", "mb2_solver_function_get_jtjr", "mb2_solver_function_get_skeleton_state", "mb2_solver_create",
     "mb2_solver_destroy", "mb2_solver_set_options", "mb2_solver_set_enabled_parameters", "mb2_solver_solve", "mb2_solver_solve_device",
     "mb2_solver_get_results", "mb2_solver_get_error_history", "mb2_solver_get_counters", "mb2_solver_set_profiling",
-    "mb2_solver_get_phase_times",
+    "mb2_solver_get_phase_times", "mb2_solver_get_plan_stats",
 ]
 
 _libs = {}
@@ -109,6 +109,8 @@ def load_library(path: Optional[str] = None):
         L.mb2_solver_get_phase_times.argtypes = [vp, _dp, _up]
     L.mb2_solver_get_error_history.argtypes = [vp, _dp]
     L.mb2_solver_get_counters.argtypes = [vp, _up, _up]
+    if hasattr(L, "mb2_solver_get_plan_stats"):
+        L.mb2_solver_get_plan_stats.argtypes = [vp, C.POINTER(C.c_int64)]
     L.mb2_default_gauss_newton_options.argtypes = [C.POINTER(_Options)]
     _libs[path] = L
     return L
@@ -375,6 +377,13 @@ class GaussNewtonSolver(_Base):
         a = C.c_uint64(0); b = C.c_uint64(0)
         self._check(self._L.mb2_solver_get_counters(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def get_plan_stats(self):
+        """Per-instance algorithmic sizes of the plan the last solve ran on (see momentum_b200.h)."""
+        st = (C.c_int64 * 8)()
+        self._check(self._L.mb2_solver_get_plan_stats(self._h, st))
+        keys = ["jacobian_nonzeros", "jacobian_columns", "ldj", "normal_parameters", "cholesky_tiles", "cholesky_tile_ops", "cholesky_levels", "rows"]
+        return dict(zip(keys, (int(v) for v in st)))
 
     def set_profiling(self, enabled: bool):
         self._check(self._L.mb2_solver_set_profiling(self._h, int(enabled)))
