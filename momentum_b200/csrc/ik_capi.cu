@@ -122,7 +122,7 @@ struct PhaseEvent {
 struct mb2_solver {
   mb2_solver_function* fn{nullptr};
   mb2_gauss_newton_options opt{};
-  DeviceBuffer<float> dH, dDelta, dThetaOrig, dTheta0, dScale, dGradDotDelta, dThetaStage;
+  DeviceBuffer<float> dH, dDelta, dThetaOrig, dTheta0, dScale, dGradDotDelta, dThetaStage, dGrad;
   DeviceBuffer<double> dLastErrors, dTrialErrors, dHistory;
   DeviceBuffer<int32_t> dActive, dIterations, dStatus, dSearching, dActiveCount;
   int* hActiveCount{nullptr}; // pinned
@@ -254,12 +254,12 @@ int ensurePlan(mb2_solver_function* f, int mode, bool schedDense = false) {
     for (const CellDesc& c : f->plan.cells) cliques[c.unit].push_back(int(c.col));
     err = buildCholSchedule(ns, cliques, schedDense, ds->host);
     if (!err.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, err);
-    // re-plan with the device columns in elimination order, then express the schedule in those columns
-    std::vector<int32_t> colOrder(ns);
-    for (int i = 0; i < ns; ++i) colOrder[i] = f->plan.enabledList[ds->host.order[i]];
+    // re-plan with the device columns in elimination order (tile starts aligned to 4 columns), the schedule expressed in them
+    std::vector<int32_t> colOrder;
+    layoutDeviceColumns(ds->host, colOrder);
+    for (int32_t& c : colOrder) if (c >= 0) c = f->plan.enabledList[c];
     err = buildPlan(f->ch->host, f->efs, f->enabled, true, f->plan, &colOrder);
     if (!err.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, err);
-    relabelScheduleToEliminationOrder(ds->host);
     ds->dense = schedDense;
     int rc = uploadSchedule(f, ds);
     if (rc != MB2_OK) return rc;
@@ -381,7 +381,7 @@ int resolveJtjMode(const mb2_solver_function* f, int requested, int ns) {
   return ok ? requested : -1;
 }
 
-int runJtJ(mb2_solver_function* f, int mode, int ns, float* H, int ldH, size_t hStride, const int32_t* active, cudaStream_t st) {
+int runJtJ(mb2_solver_function* f, int mode, int ns, float* H, int ldH, size_t hStride, const int32_t* active, cudaStream_t st, float* g = nullptr, int ldG = 0) {
   JtJArgs a{};
   a.batch = f->B;
   a.jacobian = f->dJ.p;
@@ -393,6 +393,8 @@ int runJtJ(mb2_solver_function* f, int mode, int ns, float* H, int ldH, size_t h
   a.ldH = ldH;
   a.hStride = hStride;
   a.active = active;
+  a.g = g;
+  a.ldG = ldG;
   if (mode == MB2_JTJ_FP32_SIMT) { MB2_CUDA(launchJtJSimt(a, st)); }
   else { MB2_CUDA(launchJtJTensor(a, mode == MB2_JTJ_TF32X3 ? 3 : 1, st)); }
   return MB2_OK;
@@ -790,6 +792,8 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
   const size_t hStride = size_t(ns + 1) * ldH;
   MB2_CUDA(s->dH.resize(size_t(B) * hStride));
   float* Hbuf = s->dH.p;
+  const int ldG = cholGradientLd(ns);
+  MB2_CUDA(s->dGrad.resize(size_t(B) * ldG));
   MB2_CUDA(s->dDelta.resize(size_t(B) * ns));
   MB2_CUDA(s->dTheta0.resize(size_t(B) * n));
   MB2_CUDA(s->dLastErrors.resize(B));
@@ -825,7 +829,7 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
     MB2_CUDA(launchSweep(sweepArgs(f, theta, s->dActive.p), true, st));
     recordPhaseStop(s, st);
     recordPhaseStart(s, 1, st);
-    rc = runJtJ(f, mode, ns, Hbuf, ldH, hStride, s->dActive.p, st);
+    rc = runJtJ(f, mode, ns, Hbuf, ldH, hStride, s->dActive.p, st, s->dGrad.p, ldG);
     if (rc != MB2_OK) return rc;
     recordPhaseStop(s, st);
     CholArgs c{};
@@ -853,7 +857,10 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
     c.activeCount = s->dActiveCount.p;
     c.bookkeeping = lineSearch ? 0 : 1;
     c.gradDotDelta = lineSearch ? s->dGradDotDelta.p : nullptr;
+    c.g = s->dGrad.p;
+    c.ldG = ldG;
     c.profile = (it == 0 && getenv("MB2_CHOL_PROFILE") != nullptr) ? 1 : 0;
+    if (const char* ex = getenv("MB2_CHOL_EXPERIMENT")) c.profile |= atoi(ex) << 8; // timing experiments only (results invalid)
     recordPhaseStart(s, 2, st);
     if (useSchedule) MB2_CUDA(launchCholeskyScheduled(c, f->sched->dev, st));
     else MB2_CUDA(launchCholesky(c, st));
@@ -965,7 +972,7 @@ int mb2_solver_get_plan_stats(mb2_solver* s, int64_t stats[8]) {
   stats[0] = nnz;
   stats[1] = f->plan.numCols;
   stats[2] = f->ldJ;
-  stats[3] = int64_t(f->plan.enabledList.size());
+  stats[3] = f->planMode == 0 ? int64_t(f->plan.enabledList.size()) : int64_t(f->plan.numCols);
   stats[4] = tiles ? f->sched->host.numTiles : 0;
   stats[5] = tiles ? f->sched->host.tileOps : 0;
   stats[6] = tiles ? f->sched->host.numLevels : 0;

@@ -77,6 +77,7 @@ std::string buildCholSchedule(int n, const std::vector<std::vector<int>>& clique
   out = CholSchedule();
   if (n <= 0) return "empty system";
   out.n = n;
+  out.nParams = n;
 
   // 1. ordering
   std::vector<int> order(n);
@@ -118,11 +119,12 @@ std::string buildCholSchedule(int n, const std::vector<std::vector<int>>& clique
         for (size_t k = 1; k < col[j].size(); ++k) F.set(col[j][k], pj);
       }
     }
+    const bool alignSupernodes = std::getenv("MB2_SCHED_PACK") == nullptr;
     int fill = 0, start = 0; // greedy packing of supernodes into tiles
     int padded = 0;
     auto flushSupernode = [&](int first, int lastExcl) {
       const int sz = lastExcl - first;
-      if (sz <= kCholTile && fill + sz > kCholTile) { padded += kCholTile - fill; fill = 0; } // do not split: pad to the tile boundary
+      if (alignSupernodes && sz <= kCholTile && fill + sz > kCholTile) { padded += kCholTile - fill; fill = 0; } // do not split: pad to the tile boundary
       for (int j = first; j < lastExcl; ++j) { slot[j] = padded++; fill = (fill + 1) % kCholTile; }
     };
     for (int j = 1; j <= n; ++j) {
@@ -238,15 +240,23 @@ std::string buildCholSchedule(int n, const std::vector<std::vector<int>>& clique
   return "";
 }
 
-void relabelScheduleToEliminationOrder(CholSchedule& s) {
-  // device column of the i-th eliminated parameter becomes i: perm[slot] = rank, pos[rank] = slot (monotone)
-  std::vector<int> rank(s.n);
-  for (int i = 0; i < s.n; ++i) rank[s.order[i]] = i;
-  for (auto& p : s.perm) if (p >= 0) p = int16_t(rank[p]);
-  std::vector<int16_t> pos(s.n);
-  for (int slot = 0; slot < s.nPad; ++slot) if (s.perm[slot] >= 0) pos[s.perm[slot]] = int16_t(slot);
-  s.pos = pos;
-  for (int i = 0; i < s.n; ++i) s.order[i] = i;
+void layoutDeviceColumns(CholSchedule& s, std::vector<int32_t>& deviceColumnOrder) {
+  deviceColumnOrder.clear();
+  s.nParams = s.n;
+  for (int K = 0; K < s.numTileCols; ++K) {
+    while (deviceColumnOrder.size() % 4 != 0) deviceColumnOrder.push_back(-1);
+    for (int j = 0; j < kCholTile; ++j) {
+      int16_t& p = s.perm[16 * K + j];
+      if (p < 0) continue;
+      const int dev = int(deviceColumnOrder.size());
+      deviceColumnOrder.push_back(p);
+      p = int16_t(dev);
+    }
+  }
+  s.n = int32_t(deviceColumnOrder.size());
+  s.pos.assign(s.n, int16_t(-1));
+  for (int slot = 0; slot < s.nPad; ++slot) if (s.perm[slot] >= 0) s.pos[s.perm[slot]] = int16_t(slot);
+  s.order.assign(deviceColumnOrder.begin(), deviceColumnOrder.end());
 }
 
 } // namespace mb2
@@ -262,6 +272,18 @@ void makeScheduleBlob(const CholSchedule& s, std::vector<int32_t>& blob, CholSch
   add32(s.diagTile); add32(s.levelColStart); add32(s.levelCols); add32(s.levelPanelStart); add32(s.panelTile); add32(s.panelDiag);
   add32(s.levelTaskStart); add32(s.taskDst); add32(s.taskPairStart); add32(s.pairA); add32(s.pairB); add32(s.levelVTaskStart); add32(s.vtaskRow);
   add32(s.vtaskSrcStart); add32(s.vsrcTile); add32(s.vsrcCol); add32(s.colPanelStart); add32(s.colPanelTile); add32(s.colPanelRow);
+  {
+    std::vector<int32_t> info(size_t(s.numTiles) * 3, 0);
+    auto validOf = [&](int K) { int v = 0; while (v < kCholTile && s.perm[16 * K + v] >= 0) ++v; return v; };
+    for (int t = 0; t < s.numTiles; ++t) {
+      const int I = s.tileRow[t], J = s.tileCol[t];
+      const int vI = validOf(I), vJ = validOf(J);
+      info[3 * t] = vI > 0 ? s.perm[16 * I] : 0;
+      info[3 * t + 1] = vJ > 0 ? s.perm[16 * J] : 0;
+      info[3 * t + 2] = vI | (vJ << 8) | ((I == J ? 1 : 0) << 16);
+    }
+    add32(info);
+  }
   if (blob.empty()) blob.push_back(0);
   dev = CholSchedDev();
   dev.n = s.n; dev.nPad = s.nPad; dev.numTileCols = s.numTileCols; dev.numTiles = s.numTiles; dev.numLevels = s.numLevels;
@@ -274,7 +296,7 @@ void makeScheduleBlob(const CholSchedule& s, std::vector<int32_t>& blob, CholSch
   dev.panelTile = b + offs[k++]; dev.panelDiag = b + offs[k++]; dev.levelTaskStart = b + offs[k++]; dev.taskDst = b + offs[k++];
   dev.taskPairStart = b + offs[k++]; dev.pairA = b + offs[k++]; dev.pairB = b + offs[k++]; dev.levelVTaskStart = b + offs[k++]; dev.vtaskRow = b + offs[k++];
   dev.vtaskSrcStart = b + offs[k++]; dev.vsrcTile = b + offs[k++]; dev.vsrcCol = b + offs[k++]; dev.colPanelStart = b + offs[k++];
-  dev.colPanelTile = b + offs[k++]; dev.colPanelRow = b + offs[k++];
+  dev.colPanelTile = b + offs[k++]; dev.colPanelRow = b + offs[k++]; dev.tileInfo = b + offs[k++];
 }
 
 } // namespace mb2

@@ -50,6 +50,7 @@ struct CholSchedDev {
   const int32_t* colPanelStart;
   const int32_t* colPanelTile;
   const int32_t* colPanelRow;
+  const int32_t* tileInfo;    // [numTiles][3] {gi0, gj0, validI | validJ << 8 | diag << 16}, see ik_chol_sched.h
 };
 // view of the same schedule with every table pointer moved to a copy of the blob at `newBlob`
 // Every pointer is re-derived FROM newBlob (newBlob + element offset): nvcc assumes kernel-parameter pointers address
@@ -62,19 +63,27 @@ MB2_HD CholSchedDev rebaseSchedule(const CholSchedDev& S, const int32_t* newBlob
   MB2_RB(perm) MB2_RB(pos) MB2_RB(tileIdTable) MB2_RB(tileRow) MB2_RB(tileCol) MB2_RB(diagTile) MB2_RB(levelColStart) MB2_RB(levelCols)
   MB2_RB(levelPanelStart) MB2_RB(panelTile) MB2_RB(panelDiag) MB2_RB(levelTaskStart) MB2_RB(taskDst) MB2_RB(taskPairStart) MB2_RB(pairA) MB2_RB(pairB)
   MB2_RB(levelVTaskStart) MB2_RB(vtaskRow) MB2_RB(vtaskSrcStart) MB2_RB(vsrcTile) MB2_RB(vsrcCol) MB2_RB(colPanelStart) MB2_RB(colPanelTile)
-  MB2_RB(colPanelRow)
+  MB2_RB(colPanelRow) MB2_RB(tileInfo)
 #undef MB2_RB
   return R;
 }
 
-// Slot-ordered normal equations ("Hs"): column-major, (nPad + 1) rows x nPad columns with leading dimension ldHs (a
-// multiple of 16 floats): element (si, sc), si >= sc, of the permuted+padded system at Hs[sc*ldHs + si]; row nPad holds the
-// permuted J^T r. Only structurally non-zero entries are ever written (the buffer is zeroed once per plan), so a tile
-// (I,J) is sixteen 64-byte segments that the scheduled Cholesky copies with coalesced loads.
-MB2_HD int slotLd(int nPad) { return nPad + 16; }
-
 MB2_HD int tileIdx(int r, int c) { return r * 16 + ((((c >> 2) ^ ((r >> 1) & 3)) << 2) | (c & 3)); }
 MB2_HD int tileGrp(int r, int g) { return r * 16 + ((g ^ ((r >> 1) & 3)) << 2); }
+
+// Padding pass: after the 16x16 box of H has landed in tile storage (TMA on the device), rows >= validJ / columns >= validI
+// belong to the NEXT parameters of the elimination order, not to this tile: overwrite them with the identity extension.
+// One work item = storage row c, float4 group g (matrix rows 4g..4g+3).
+MB2_HD void cholPadGroup(float* tile, int info, int c, int g) {
+  const int vI = info & 0xFF, vJ = (info >> 8) & 0xFF, diag = (info >> 16) & 1;
+  if (c < vJ && 4 * g + 3 < vI) return;
+  float* dst = tile + tileGrp(c, g);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int r = 4 * g + q;
+    if (c >= vJ || r >= vI) dst[q] = (diag && r == c) ? 1.f : 0.f;
+  }
+}
 
 MB2_HD void tileLoadRow(const float* tile, int r, float* a) {
 #pragma unroll

@@ -26,6 +26,7 @@ constexpr int kCholTile = 16;
 
 struct CholSchedule {
   int32_t n{0}, nPad{0}, numTileCols{0}, numTiles{0}, numLevels{0};
+  int32_t nParams{0};                   // parameters in the system (n also counts alignment gaps after layoutDeviceColumns)
   std::vector<int16_t> perm;            // [nPad] permuted position -> device column, -1 = padding
   std::vector<int16_t> pos;             // [n] device column -> permuted position (inverse of perm)
   std::vector<int16_t> tileIdTable;     // [numTileCols * numTileCols] tile id of (I,J), I >= J, or -1
@@ -47,10 +48,18 @@ struct CholSchedule {
 // `cliques`: for every Jacobian row group, the device columns it touches (each list is a clique of the
 // pattern). n = number of device columns that enter the normal equations.
 std::string buildCholSchedule(int n, const std::vector<std::vector<int>>& cliques, bool forceDense, CholSchedule& out);
-// After the caller has re-ordered the device columns into elimination order (column i = i-th eliminated parameter),
-// rewrite perm/pos accordingly (pos becomes monotone: lower triangle of JtJ == lower triangle of the permuted system).
-void relabelScheduleToEliminationOrder(CholSchedule& s);
+// Device column layout of the solver plan: parameters in elimination order, and every tile column starting on a device column
+// that is a multiple of 4 (TMA fetches a tile as one 16 x 16 box of the row-major H; the first byte of each box row must be
+// 16-byte aligned). The up-to-3 skipped device columns before such a start are all-zero Jacobian columns ("gaps").
+// deviceColumnOrder[d] = input column (as numbered in `cliques`) held by device column d, or -1 for a gap. Rewrites perm / pos
+// to device columns (pos[d] = slot or -1) and sets n to the number of device columns (nParams keeps the original count).
+void layoutDeviceColumns(CholSchedule& s, std::vector<int32_t>& deviceColumnOrder);
 
+// Leading dimension of the row-major symmetric matrix [J r]^T [J r] the JtJ kernels write and the scheduled Cholesky reads.
+inline int cholSchedLdH(int n) { return (n + 1 + 15) / 16 * 16; }
+// tileInfo (3 ints per tile, in the device blob): {gi0, gj0, validI | validJ << 8 | diag << 16}: tile (I,J) is the 16x16 box of
+// H with first row gj0 (device column of slot 16 J) and first column gi0 (slot 16 I); only its first validJ rows / validI columns
+// are real (padding only closes a tile), the rest is overwritten by the padding pass.
 struct CholSchedDev;
 // Concatenates every table into one int32 blob; `dev` gets pointers into blob.data() (rebase them after uploading).
 void makeScheduleBlob(const CholSchedule& s, std::vector<int32_t>& blob, CholSchedDev& dev);

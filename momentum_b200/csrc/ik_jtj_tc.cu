@@ -24,6 +24,7 @@
 //                 every store instruction covering four full 128-byte lines
 // Pipelines: smem ring full -> converted -> (MMA) -> empty; TMEM full/empty between MMA and epilogue.
 #include "ik_jtj_tc.cuh"
+#include "ik_ptx.cuh"
 
 #include <cuda.h>
 
@@ -44,7 +45,6 @@ constexpr int kStageRowFloats = 36;  // epilogue staging row: 32 floats + 4 pad 
 constexpr int kKBlock = 32;         // floats per K block = one 128-byte swizzle row
 constexpr int kRowBytes = 128;
 constexpr int kUmmaK = 8;           // tf32: 32 bytes of K per instruction
-constexpr uint64_t kSpinLimit = 4000000000ull; // cycles before a stuck barrier traps instead of hanging the box
 
 struct TcParams {
   int batch;
@@ -59,44 +59,11 @@ struct TcParams {
   int tmemCols;   // power of two >= n0 + n1
   int stages;
   size_t hStride;
+  float* G;       // optional [batch][ldG]: J^T r as a contiguous vector (the scheduled Cholesky bulk-copies it)
+  int ldG;
   int profile;    // MB2_TC_PROFILE=1: block 0 prints per-role wait/busy cycles (debug aid, off by default)
 };
 
-__device__ __forceinline__ uint32_t smemAddr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbarInit(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbarExpectTx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbarArrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbarWait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  const long long t0 = clock64();
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    if ((uint64_t)(clock64() - t0) > kSpinLimit) {
-      printf("momentum_b200: JtJ tensor kernel barrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void tmaLoad3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
-      : "memory");
-}
 __device__ __forceinline__ void ummaTf32(uint32_t tmemD, uint64_t descA, uint64_t descB, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -304,6 +271,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
           // solver path: full rows. 32x32 blocks go TMEM -> registers -> shared (row = TMEM lane) -> global, re-mapped so
           // that one store instruction writes four rows x 128 contiguous bytes.
           for (int c0 = 0; c0 < nT; c0 += 32) {
+            if (t * 128 + c0 + 32 <= rowBase && !(t * 128 + c0 <= p.numCols && p.numCols < t * 128 + c0 + 32)) continue; // entirely left of the diagonal
             float v[32];
             const long long tl0 = p.profile ? clock64() : 0;
             if (c0 + 32 <= nT) tmemLoad32(colBase + (uint32_t)c0, v);
@@ -313,6 +281,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
             for (int g4 = 0; g4 < 8; ++g4)
               *reinterpret_cast<float4*>(stage + lane * kStageRowFloats + 4 * g4) = make_float4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
             __syncwarp();
+            if (p.G != nullptr && t * 128 + c0 <= p.numCols && p.numCols < t * 128 + c0 + 32 && i >= 0 && i < p.ns) // column numCols = J^T r
+              p.G[(size_t)b * p.ldG + i] = stage[lane * kStageRowFloats + (p.numCols - t * 128 - c0)];
             const int c = t * 128 + c0 + 4 * (lane & 7); // matrix column of this lane's float4
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -390,6 +360,19 @@ Shape shapeFor(int numCols) {
 
 } // namespace
 
+cudaError_t makeTensorMap3d(CUtensorMap* map, const float* base, const uint64_t dims[3], const uint64_t strideBytes[2], const uint32_t box[3], int swizzleBytes) {
+  if (encodeTiled() == nullptr) return cudaErrorNotSupported;
+  const cuuint64_t d[3] = {dims[0], dims[1], dims[2]};
+  const cuuint64_t st[2] = {strideBytes[0], strideBytes[1]};
+  const cuuint32_t bx[3] = {box[0], box[1], box[2]};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  const CUtensorMapSwizzle sw = swizzleBytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzleBytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                              : swizzleBytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  const CUresult r = encodeTiled()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), d, st, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 bool jtjTensorSupported(int ns, int numCols, int ldJ) {
   if (encodeTiled() == nullptr) return false;
   return ns >= 1 && ns <= numCols && numCols + 1 <= 256 && (ldJ % kKBlock) == 0;
@@ -400,14 +383,11 @@ cudaError_t launchJtJTensor(const JtJArgs& a, int passes, cudaStream_t stream) {
   const Shape sh = shapeFor(a.numCols);
   // TMA descriptor over the device Jacobian [batch][numCols + 1][ldJ] (innermost first)
   CUtensorMap map;
-  const cuuint64_t dims[3] = {(cuuint64_t)a.ldJ, (cuuint64_t)(a.numCols + 1), (cuuint64_t)a.batch};
-  const cuuint64_t strides[2] = {(cuuint64_t)a.ldJ * sizeof(float), (cuuint64_t)(a.numCols + 1) * a.ldJ * sizeof(float)};
-  const cuuint32_t box[3] = {(cuuint32_t)kKBlock, (cuuint32_t)sh.boxRows, 1u};
-  const cuuint32_t estr[3] = {1u, 1u, 1u};
-  const CUresult r = encodeTiled()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(a.jacobian), dims, strides, box, estr,
-                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+  const uint64_t dims[3] = {(uint64_t)a.ldJ, (uint64_t)(a.numCols + 1), (uint64_t)a.batch};
+  const uint64_t strides[2] = {(uint64_t)a.ldJ * sizeof(float), (uint64_t)(a.numCols + 1) * a.ldJ * sizeof(float)};
+  const uint32_t box[3] = {(uint32_t)kKBlock, (uint32_t)sh.boxRows, 1u};
+  const cudaError_t me = makeTensorMap3d(&map, a.jacobian, dims, strides, box, 128);
+  if (me != cudaSuccess) return me;
   TcParams p{};
   p.batch = a.batch;
   p.ns = a.ns;
@@ -424,6 +404,8 @@ cudaError_t launchJtJTensor(const JtJArgs& a, int passes, cudaStream_t stream) {
   p.n1 = sh.n1;
   p.tmemCols = sh.tmemCols;
   p.hStride = a.hStride;
+  p.G = a.g;
+  p.ldG = a.ldG;
   p.profile = getenv("MB2_TC_PROFILE") != nullptr ? 1 : 0;
   const size_t stageBytes = size_t(sh.boxRows) * kRowBytes * (p.passes == 3 ? 2 : 1);
   int stages = int((196 * 1024) / stageBytes);

@@ -12,6 +12,8 @@
 #include <cstdio>
 
 #include "ik_chol.cuh"
+#include "ik_jtj_tc.cuh"
+#include "ik_ptx.cuh"
 #include "ik_device.cuh"
 
 namespace mb2 {
@@ -212,7 +214,10 @@ __global__ void __launch_bounds__(256) jtjSimtKernel(const JtJArgs a) {
     }
   if (diag && threadIdx.x < kJtjTile) {
     const int gi = ti * kJtjTile + threadIdx.x;
-    if (gi < a.ns) { H[size_t(gi) * a.ldH + a.ns] = gacc; H[size_t(a.ns) * a.ldH + gi] = gacc; }
+    if (gi < a.ns) {
+      H[size_t(gi) * a.ldH + a.ns] = gacc; H[size_t(a.ns) * a.ldH + gi] = gacc;
+      if (a.g != nullptr) a.g[size_t(b) * a.ldG + gi] = gacc;
+    }
   }
 }
 
@@ -236,10 +241,11 @@ __device__ void cholFinish(const CholArgs& a, int b, int n, const float* dsub, c
   float* theta = a.theta + size_t(b) * a.ldTheta;
   float part = 0.f;
   for (int i = tid; i < n; i += blockDim.x) {
-    const float d = dsub[i];
+    const int c = a.cols[i];
+    const float d = c >= 0 ? dsub[i] : 0.f; // c < 0: all-zero alignment column of the scheduled layout (ik_chol_sched.h)
     a.delta[size_t(b) * n + i] = d;
-    part += gsub[i] * d;
-    if (a.applyUpdate) theta[a.cols[i]] -= d;
+    if (c >= 0) part += gsub[i] * d;
+    if (a.applyUpdate && c >= 0) theta[c] -= d;
   }
   if (a.gradDotDelta != nullptr) {
     __shared__ float red[32];
@@ -390,68 +396,64 @@ cudaError_t launchCholesky(const CholArgs& a, cudaStream_t stream) {
 constexpr int kSchedThreads = 256;
 
 size_t choleskyScheduledSmemBytes(int n, int nPad, int numTiles, int blobInts) {
-  return sizeof(float) * (size_t(numTiles) * 256 + size_t(nPad) + 2 * size_t((n + 3) & ~3)) + sizeof(int32_t) * size_t((blobInts + 3) & ~3) + 16;
+  return 1024 /*tile storage is aligned to the TMA swizzle atom*/ + sizeof(float) * (size_t(numTiles) * 256 + size_t(nPad) + 2 * size_t((n + 3) & ~3)) +
+         sizeof(int32_t) * size_t((blobInts + 3) & ~3) + 32;
 }
 
-__global__ void __launch_bounds__(kSchedThreads, 3) choleskyScheduledKernel(const CholArgs a, const CholSchedDev Sg) {
-  extern __shared__ __align__(16) float smemS[];
+__global__ void __launch_bounds__(kSchedThreads, 3) choleskyScheduledKernel(const __grid_constant__ CUtensorMap hmap, const CholArgs a, const CholSchedDev Sg) {
+  extern __shared__ __align__(16) float smemRaw[];
   const int b = blockIdx.x;
   if (a.active[b] == 0) return;
   const int n = a.ns, tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31, hw = tid >> 4, hl = tid & 15;
   const unsigned hmask = 0xFFFFu << (16 * ((tid >> 4) & 1));
-  float* tiles = smemS;
+  float* tiles = smemRaw + (((1024u - (smemAddr(smemRaw) & 1023u)) & 1023u) >> 2); // 1 KB aligned in the shared window (TMA swizzle atom)
   float* y = tiles + size_t(Sg.numTiles) * 256;
   float* gsub = y + Sg.nPad;
   float* dsub = gsub + ((n + 3) & ~3);
   int32_t* blob = reinterpret_cast<int32_t*>(dsub + ((n + 3) & ~3));
   int* flags = reinterpret_cast<int*>(blob + ((Sg.blobInts + 3) & ~3));
-  // the schedule (a few KB of int32 tables) is read many times per level: stage it in shared memory once
-  long long pc[6] = {0, 0, 0, 0, 0, 0}, pt = clock64();
-#define MB2_PROF(k) if (a.profile) { const long long now = clock64(); pc[k] += now - pt; pt = now; }
-  for (int i = tid; i < Sg.blobInts; i += kSchedThreads) blob[i] = Sg.blob[i];
-  if (tid == 0) flags[0] = 0;
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(flags + 2);
+  long long pc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, pt = clock64();
+#define MB2_PROF(k) if (a.profile & 1) { const long long now = clock64(); pc[k] += now - pt; pt = now; }
+  // Prologue: everything this instance reads arrives asynchronously on one mbarrier -- the schedule tables and J^T r as 1-D
+  // bulk copies, every stored tile as one TMA box (16 rows x 64 bytes of the row-major upper triangle of H, written
+  // straight into the swizzled tile layout: SWIZZLE_64B is the XOR of tileIdx). No thread touches the data on the way in.
+  const uint32_t barAddr = smemAddr(bar);
+  const uint32_t blobBytes = uint32_t((Sg.blobInts + 3) & ~3) * 4u, gBytes = uint32_t(a.ldG) * 4u;
+  if (tid == 0) {
+    flags[0] = 0;
+    mbarInit(barAddr, 1);
+    fenceBarrierInit();
+    mbarExpectTx(barAddr, blobBytes + gBytes + uint32_t(Sg.numTiles) * 1024u);
+  }
   __syncthreads();
-  const CholSchedDev S = rebaseSchedule(Sg, blob);
-  // Gather the stored tiles from the symmetric matrix. Device columns are in elimination order and padding only closes a
-  // tile, so block row I covers device columns tileBase(I) .. tileBase(I) + valid(I) - 1: the transposed tile
-  // T[c][r] = H(r,c) = H(c,r) is sixteen contiguous runs of row (tileBase(J)+c) of H. All copies are 4-byte cp.async
-  // (LDGSTS) so that every thread has its ~60 loads in flight at once.
-  const float* Hs = a.H + size_t(b) * a.hStride;
-  // one work item = four consecutive matrix rows r4..r4+3 of one tile column c (16 bytes of the transposed tile row c)
-#pragma unroll 2
-  for (int idx = tid; idx < S.numTiles * 64; idx += kSchedThreads) {
-    const int t = idx >> 6, e = idx & 63, c = e >> 2, r4 = (e & 3) << 2;
-    const int I = S.tileRow[t], J = S.tileCol[t];
-    if (I == J && r4 + 3 < c) continue; // diagonal tiles are only read at (row >= col), see cholDiagTile
-    const int gj = S.perm[16 * J + c];
-    const int gi0 = S.perm[16 * I + r4], gi3 = S.perm[16 * I + r4 + 3];
-    float* dst = tiles + (size_t(t) * 256 + tileGrp(c, r4 >> 2));
-    const unsigned sdst = static_cast<unsigned>(__cvta_generic_to_shared(dst));
-    if (gj >= 0 && gi3 >= 0 && (gi0 & 3) == 0 && gi0 >= gj) {
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(Hs + size_t(gj) * a.ldH + gi0) : "memory");
-    } else {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int gi = S.perm[16 * I + r4 + q];
-        if (gi >= 0 && gj >= 0) {
-          const int lo = gi < gj ? gi : gj, hi = gi < gj ? gj : gi;
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst + 4u * q), "l"(Hs + size_t(lo) * a.ldH + hi) : "memory");
-        } else {
-          dst[q] = (I == J && r4 + q == c) ? 1.f : 0.f; // padding variable: identity row/column
-        }
-      }
+  if (lane == 0) { // TMA instructions take warp-uniform operands: one elected lane per warp issues, the tiles are dealt round-robin to the warps
+    if (warp == 0) {
+      bulkLoad(smemAddr(blob), Sg.blob, blobBytes, barAddr);
+      bulkLoad(smemAddr(gsub), a.g + size_t(b) * a.ldG, gBytes, barAddr);
+    }
+    for (int t = warp; t < Sg.numTiles; t += kSchedThreads / 32) {
+      const int gi0 = __ldg(Sg.tileInfo + 3 * t), gj0 = __ldg(Sg.tileInfo + 3 * t + 1);
+      tmaLoad3d(smemAddr(tiles + size_t(t) * 256), &hmap, gi0, gj0, b, barAddr);
     }
   }
+  MB2_PROF(6)
+  mbarWait(barAddr, 0);
+  MB2_PROF(7)
+  const CholSchedDev S = rebaseSchedule(Sg, blob);
+  // padding pass (cholPadGroup): one work item = (tile, storage row, float4 group)
+  if (!(a.profile & 0x800))
+    for (int idx = tid; idx < S.numTiles * 64; idx += kSchedThreads) {
+      const int t = idx >> 6, e = idx & 63;
+      cholPadGroup(tiles + size_t(t) * 256, S.tileInfo[3 * t + 2], e >> 2, e & 3);
+    }
   for (int s = tid; s < S.nPad; s += kSchedThreads) {
     const int p = S.perm[s];
-    const float g = p >= 0 ? Hs[size_t(p) * a.ldH + n] : 0.f; // J^T r sits in column n of every row
-    y[s] = g;
-    if (p >= 0) gsub[p] = g;
+    y[s] = p >= 0 ? gsub[p] : 0.f;
   }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
+  MB2_PROF(8)
   for (int s = tid; s < S.nPad; s += kSchedThreads)
     if (S.perm[s] >= 0) tiles[size_t(S.diagTile[s >> 4]) * 256 + tileIdx(s & 15, s & 15)] += a.regularization; // gauss_newton_solver.cpp:248
   __syncthreads();
@@ -461,24 +463,24 @@ __global__ void __launch_bounds__(kSchedThreads, 3) choleskyScheduledKernel(cons
     // A: diagonal tiles of this level (one half-warp each) + forward solve of their rhs block
     for (int ci = S.levelColStart[L] + hw; ci < S.levelColStart[L + 1]; ci += kSchedThreads / 16) {
       const int K = S.levelCols[ci];
-      cholDiagTile(tiles + size_t(S.diagTile[K]) * 256, y + 16 * K, hl, hmask, a.regularization, flags);
+      if (!(a.profile & 0x400)) cholDiagTile(tiles + size_t(S.diagTile[K]) * 256, y + 16 * K, hl, hmask, a.regularization, flags);
     }
     __syncthreads();
     MB2_PROF(1)
     // B: panel tiles
-    for (int pi = S.levelPanelStart[L] + hw; pi < S.levelPanelStart[L + 1]; pi += kSchedThreads / 16) {
+    if (!(a.profile & 0x200)) for (int pi = S.levelPanelStart[L] + hw; pi < S.levelPanelStart[L + 1]; pi += kSchedThreads / 16) {
       cholPanelSolve(tiles + size_t(S.panelTile[pi]) * 256, tiles + size_t(S.panelDiag[pi]) * 256, hl);
     }
     __syncthreads();
     MB2_PROF(2)
     // C: update tasks (warp each) and rhs updates (half-warp each)
-    for (int ti = S.levelTaskStart[L] + warp; ti < S.levelTaskStart[L + 1]; ti += kSchedThreads / 32) cholUpdateTask(tiles, S, ti, lane);
-    for (int vi = S.levelVTaskStart[L] + hw; vi < S.levelVTaskStart[L + 1]; vi += kSchedThreads / 16) cholVectorTask(tiles, y, S, vi, hl);
+    if (!(a.profile & 0x100)) for (int ti = S.levelTaskStart[L] + warp; ti < S.levelTaskStart[L + 1]; ti += kSchedThreads / 32) cholUpdateTask(tiles, S, ti, lane);
+    if (!(a.profile & 0x2000)) for (int vi = S.levelVTaskStart[L] + hw; vi < S.levelVTaskStart[L + 1]; vi += kSchedThreads / 16) cholVectorTask(tiles, y, S, vi, hl);
     __syncthreads();
     MB2_PROF(3)
   }
   for (int L = S.numLevels - 1; L >= 0; --L) {
-    for (int ci = S.levelColStart[L] + hw; ci < S.levelColStart[L + 1]; ci += kSchedThreads / 16) cholBackwardColumn(tiles, y, S, S.levelCols[ci], hl, hmask);
+    if (!(a.profile & 0x1000)) for (int ci = S.levelColStart[L] + hw; ci < S.levelColStart[L + 1]; ci += kSchedThreads / 16) cholBackwardColumn(tiles, y, S, S.levelCols[ci], hl, hmask);
     __syncthreads();
   }
   MB2_PROF(4)
@@ -486,9 +488,9 @@ __global__ void __launch_bounds__(kSchedThreads, 3) choleskyScheduledKernel(cons
   __syncthreads();
   cholFinish(a, b, n, dsub, gsub, flags[0] != 0);
   MB2_PROF(5)
-  if (a.profile && b == 0 && tid == 0)
-    printf("chol-profile (cycles, block 0): load %lld diag %lld panel %lld update %lld backward %lld finish %lld | levels %d tiles %d\n", pc[0], pc[1], pc[2], pc[3],
-           pc[4], pc[5], S.numLevels, S.numTiles);
+  if ((a.profile & 1) && b == 0 && tid == 0)
+    printf("chol-profile (cycles, block 0): blob %lld issue %lld wait %lld lambda %lld diag %lld panel %lld update %lld backward %lld finish %lld | levels %d tiles %d\n", pc[6], pc[7],
+           pc[8], pc[0], pc[1], pc[2], pc[3], pc[4], pc[5], S.numLevels, S.numTiles);
 #undef MB2_PROF
 }
 
@@ -497,7 +499,14 @@ cudaError_t launchCholeskyScheduled(const CholArgs& a, const CholSchedDev& sched
   if (smem > size_t(g_maxSmemOptin)) return cudaErrorInvalidConfiguration;
   cudaError_t e = cudaFuncSetAttribute(choleskyScheduledKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
-  choleskyScheduledKernel<<<a.batch, kSchedThreads, smem, stream>>>(a, sched);
+  if (a.g == nullptr || a.ldG != cholGradientLd(a.ns) || (a.ldH & 3) != 0 || (a.hStride & 3) != 0) return cudaErrorInvalidValue;
+  CUtensorMap hmap; // H as [batch][ns + 1][ldH]; one 16 x 16 box per stored tile
+  const uint64_t dims[3] = {uint64_t(a.ldH), uint64_t(a.ns + 1), uint64_t(a.batch)};
+  const uint64_t strides[2] = {uint64_t(a.ldH) * sizeof(float), uint64_t(a.hStride) * sizeof(float)};
+  const uint32_t box[3] = {16u, 16u, 1u};
+  e = makeTensorMap3d(&hmap, a.H, dims, strides, box, 64);
+  if (e != cudaSuccess) return e;
+  choleskyScheduledKernel<<<a.batch, kSchedThreads, smem, stream>>>(hmap, a, sched);
   return cudaGetLastError();
 }
 
@@ -523,7 +532,7 @@ __global__ void trialUpdateKernel(int batch, const float* thetaOrig, int ldTheta
   const float s = scale[b];
   for (int i = threadIdx.x; i < ns; i += blockDim.x) {
     const int c = cols[i];
-    thetaTrial[size_t(b) * ldTheta + c] = thetaOrig[size_t(b) * ldTheta + c] - s * delta[size_t(b) * ns + i];
+    if (c >= 0) thetaTrial[size_t(b) * ldTheta + c] = thetaOrig[size_t(b) * ldTheta + c] - s * delta[size_t(b) * ns + i]; // c < 0: alignment column
   }
 }
 cudaError_t launchTrialUpdate(int batch, const float* thetaOrig, int ldTheta, const float* delta, int ns, const int32_t* cols, const float* scale,

@@ -32,6 +32,8 @@ struct JtJArgs {             // K2
   int32_t ldH;               // multiple of 16, >= ns + 1
   size_t hStride;            // floats per instance in H
   const int32_t* active;
+  float* g;                  // optional [B][ldG]: J^T r again, as a contiguous vector
+  int32_t ldG;
 };
 
 struct CholArgs {            // K3: damped Cholesky + solve + update + SolverT bookkeeping
@@ -56,6 +58,8 @@ struct CholArgs {            // K3: damped Cholesky + solve + update + SolverT b
   int32_t* activeCount;      // device counter (atomicAdd of instances still active)
   int32_t bookkeeping;       // 1: run the SolverT convergence test here (no line search)
   float* gradDotDelta;       // optional [B]: Jtr . delta (SubsetGaussNewtonSolverT line search)
+  const float* g;            // scheduled kernel: [B][ldG] J^T r as a contiguous vector (ldG = ns rounded up to 4)
+  int32_t ldG;
   int32_t profile;           // MB2_CHOL_PROFILE=1: block 0 prints per-phase cycles (debug aid)
 };
 
@@ -66,6 +70,7 @@ cudaError_t launchCholesky(const CholArgs& a, cudaStream_t stream);
 // level-scheduled tile-sparse variant (ik_chol_sched.h); returns cudaErrorInvalidConfiguration when the tiles do not fit in shared memory
 // `a.H` is the full symmetric system in device-column (= elimination) order
 cudaError_t launchCholeskyScheduled(const CholArgs& a, const CholSchedDev& sched, cudaStream_t stream);
+inline int cholGradientLd(int ns) { return (ns + 3) & ~3; }
 size_t choleskyScheduledSmemBytes(int n, int nPad, int numTiles, int blobInts);
 cudaError_t initKernelAttributes();
 

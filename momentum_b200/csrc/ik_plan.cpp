@@ -119,15 +119,16 @@ std::string buildPlan(const HostCharacter& ch, const std::vector<HostErrorFuncti
   std::vector<int> colMap(n, -1); // model parameter -> device column
   if (compact) {
     out.deviceCols = out.enabledList;
-    if (columnOrder != nullptr) {
-      if (columnOrder->size() != out.enabledList.size()) return "column order must list every enabled parameter once";
-      out.deviceCols = *columnOrder;
-    }
+    if (columnOrder != nullptr) out.deviceCols = *columnOrder; // may hold -1 entries: all-zero alignment columns (ik_chol_sched.h)
+    size_t listed = 0;
     for (size_t a = 0; a < out.deviceCols.size(); ++a) {
       const int p = out.deviceCols[a];
+      if (p == -1 && columnOrder != nullptr) continue;
       if (p < 0 || p >= n || !enabled[p] || colMap[p] >= 0) return "column order must list every enabled parameter once";
       colMap[p] = int(a);
+      ++listed;
     }
+    if (listed != out.enabledList.size()) return "column order must list every enabled parameter once";
     out.numCols = int(out.deviceCols.size());
   } else {
     for (int i = 0; i < n; ++i) colMap[i] = i;

@@ -173,12 +173,13 @@ static int cholScheduledOne(const CholSchedDev& S, const float* Hs, int ldH, int
   while ((reinterpret_cast<uintptr_t>(tl) & 15) != 0) ++tl; // float4 alignment
   float* y = tl + size_t(S.numTiles) * 256;
   std::vector<float> gsub(n, 0.f);
-  for (int idx = 0; idx < S.numTiles * 256; ++idx) {
-    const int t = idx >> 8, e = idx & 255, c = e >> 4, r = e & 15;
-    const int I = S.tileRow[t], J = S.tileCol[t];
-    const int gi = S.perm[16 * I + r], gj = S.perm[16 * J + c];
-    if (I == J && r < c) { tl[idx - e + tileIdx(c, r)] = -12345.f; continue; } // not gathered on the device either (must never be read)
-    tl[idx - e + tileIdx(c, r)] = (gi >= 0 && gj >= 0) ? Hs[size_t(std::min(gi, gj)) * ldH + std::max(gi, gj)] : ((I == J && r == c) ? 1.f : 0.f);
+  std::fill(delta, delta + n, 0.f); // alignment columns keep a zero step
+  for (int t = 0; t < S.numTiles; ++t) { // the TMA box: 16 rows x 16 columns of H starting at (gj0, gi0), zero outside [ns+1] x [ldH]
+    const int gi0 = S.tileInfo[3 * t], gj0 = S.tileInfo[3 * t + 1];
+    for (int c = 0; c < 16; ++c)
+      for (int r = 0; r < 16; ++r)
+        tl[size_t(t) * 256 + tileIdx(c, r)] = (gj0 + c <= n && gi0 + r < ldH) ? Hs[size_t(gj0 + c) * ldH + gi0 + r] : 0.f;
+    for (int e = 0; e < 64; ++e) cholPadGroup(tl + size_t(t) * 256, S.tileInfo[3 * t + 2], e >> 2, e & 3);
   }
   for (int s2 = 0; s2 < S.nPad; ++s2) {
     const int p = S.perm[s2];
@@ -431,12 +432,12 @@ int mb2_solver_solve(mb2_solver* s, float* params, double* errors, int32_t* iter
     for (const CellDesc& c : f->plan.cells) cliques[c.unit].push_back(int(c.col));
     e = buildCholSchedule(ns0, cliques, cholMode == 2, sched);
     if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
-    std::vector<int32_t> colOrder(ns0);
-    for (int i = 0; i < ns0; ++i) colOrder[i] = f->plan.enabledList[sched.order[i]];
+    std::vector<int32_t> colOrder;
+    layoutDeviceColumns(sched, colOrder);
+    for (int32_t& c : colOrder) if (c >= 0) c = f->plan.enabledList[c];
     e = buildPlan(f->ch->host, f->efs, f->enabled, true, f->plan, &colOrder);
     if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
     f->J.assign(size_t(f->B) * (f->plan.numCols + 1) * f->ldJ, 0.f);
-    relabelScheduleToEliminationOrder(sched);
   }
   std::vector<int32_t> blob;
   CholSchedDev S{};
@@ -456,7 +457,7 @@ int mb2_solver_solve(mb2_solver* s, float* params, double* errors, int32_t* iter
       sweepOne<true>(f, T, b, theta, &error, nullptr);
       float gdd = 0.f;
       int failed;
-      std::fill(H.begin(), H.end(), 0.f);
+      std::fill(H.begin(), H.end(), std::nanf("")); // entries the device never writes (lower triangle) are garbage there: poison them here
       jtjOne(f, b, ns, H.data(), ldH);
       if (cholMode >= 2) {
         failed = cholScheduledOne(S, H.data(), ldH, ns, o.regularization, delta.data(), &gdd);
@@ -465,12 +466,12 @@ int mb2_solver_solve(mb2_solver* s, float* params, double* errors, int32_t* iter
       }
       if (failed && s->status[b] == 0) s->status[b] = MB2_INSTANCE_CHOLESKY_BREAKDOWN;
       if (!o.do_line_search) {
-        for (int a = 0; a < ns; ++a) theta[f->plan.deviceCols[a]] -= delta[a];
+        for (int a = 0; a < ns; ++a) if (f->plan.deviceCols[a] >= 0) theta[f->plan.deviceCols[a]] -= delta[a];
       } else {
         std::copy(theta, theta + n, orig.begin());
         float scale = 1.f;
         for (int step = 0; step < 10; ++step) {
-          for (int a = 0; a < ns; ++a) { const int c = f->plan.deviceCols[a]; theta[c] = orig[c] - scale * delta[a]; }
+          for (int a = 0; a < ns; ++a) { const int c = f->plan.deviceCols[a]; if (c >= 0) theta[c] = orig[c] - scale * delta[a]; }
           double en;
           sweepOne<false>(f, T, b, theta, &en, nullptr);
           bool accept;
