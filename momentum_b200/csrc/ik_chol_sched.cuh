@@ -108,80 +108,82 @@ MB2_HD void tileStoreRow(float* tile, int r, const float* a) {
 // block (panel solve, backward substitution) is then a 16x16 product with W — no dependent 16-step chain on the
 // critical path of a level. L(K,K) itself is not needed again.
 MB2_HD void cholDiagTile(float* tile, float* y16, int hl, unsigned hmask, float fallback, int* fail) {
+  // Square-root-free elimination keeps the per-step dependency chain short (pivot broadcast -> reciprocal -> one multiply ->
+  // one fused multiply-add); the 1/sqrt(pivot) scalings and the right-hand side ride along off that chain:
+  //   A = U D U^T (U unit lower, U[r][k] = a_r[k] / d_k),  L = U D^1/2,  y = L^-1 g = D^-1/2 U^-1 g.
+  // The gather fills the tile as S[c][r] = H(r, c) for r >= c only: matrix row hl, columns k <= hl, is storage column hl.
 #if defined(__CUDA_ARCH__)
-  // the gather fills the diagonal tile as S[c][r] = H(r, c) for r >= c only (contiguous runs of the upper triangle of H):
-  // matrix row hl, columns k <= hl, is therefore storage column hl
-  float a[16];
+  float a[16], rd[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) a[k] = tile[tileIdx(k, hl)];
-  float yv = y16[hl];
-  float rdSelf = 0.f;
-  __syncwarp(hmask); // every lane has read its column before any lane overwrites the tile with rows of L
+  float z = y16[hl], rdSelf = 0.f;
+  __syncwarp(hmask); // every lane has read its column before any lane overwrites the tile
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
     float piv = __shfl_sync(hmask, a[k], k, 16);
     if (!(piv > 0.f)) { piv = fallback; if (hl == k) *fail = 1; }
-    const float rd = rsqrtf(piv);
-    const float d = piv * rd;
-    const float lk = a[k] * rd; // L[r][k] for r > k
-    const float xk = __shfl_sync(hmask, yv, k, 16) * rd;
+    float inv;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(piv)); // one MUFU on the dependency chain (1 ulp; the step is damped Gauss-Newton)
+    rd[k] = rsqrtf(piv);
+    if (hl == k) rdSelf = rd[k];
+    const float zk = __shfl_sync(hmask, z, k, 16);
+    const float t = a[k] * inv; // U[hl][k] for hl > k
 #pragma unroll
-    for (int j = k + 1; j < 16; ++j) {
-      const float ljk = __shfl_sync(hmask, lk, j, 16);
-      a[j] -= lk * ljk;
-    }
-    if (hl > k) yv -= lk * xk;
-    else if (hl == k) { yv = xk; rdSelf = rd; }
-    a[k] = (hl == k) ? d : lk;
+    for (int j = k + 1; j < 16; ++j) a[j] -= t * __shfl_sync(hmask, a[k], j, 16);
+    if (hl > k) z -= t * zk;
   }
-  tileStoreRow(tile, hl, a); // L (lower part valid)
-  y16[hl] = yv;
+  y16[hl] = z * rdSelf; // (rd[hl] would index the register array dynamically and push it to local memory)
+  // L^T into the tile: Lt[k][hl] = L[hl][k] = a_hl[k] / sqrt(d_k)  (k < hl); the diagonal is not needed (rd holds its inverse)
+#pragma unroll
+  for (int k = 0; k < 16; ++k) tile[tileIdx(k, hl)] = a[k] * rd[k];
   __syncwarp(hmask);
-  // column hl of W = L^-1 by forward substitution against e_hl (rows of L are broadcast reads)
-  float w[16];
+  // column hl of W = L^-1 by column-oriented forward substitution against e_hl: one dependent multiply-add per step;
+  // row i of L^T (= column i of L) is a broadcast read
+  float sacc[16], w[16];
+#pragma unroll
+  for (int m = 0; m < 16; ++m) sacc[m] = (m == hl) ? 1.f : 0.f;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    const float rdi = __shfl_sync(hmask, rdSelf, i, 16);
-    float Lrow[16];
-    tileLoadRow(tile, i, Lrow);
-    float s0 = (i == hl) ? 1.f : 0.f, s1 = 0.f;
+    w[i] = sacc[i] * rd[i];
+    float Lcol[16];
+    tileLoadRow(tile, i, Lcol);
 #pragma unroll
-    for (int m = 0; m < 16; ++m)
-      if (m < i) { if (m & 1) s1 += Lrow[m] * w[m]; else s0 -= Lrow[m] * w[m]; }
-    w[i] = (s0 - s1) * rdi;
+    for (int m = i + 1; m < 16; ++m) sacc[m] -= Lcol[m] * w[i];
   }
   __syncwarp(hmask);
 #pragma unroll
   for (int i = 0; i < 16; ++i) tile[tileIdx(i, hl)] = w[i]; // W[i][hl]; zero above the diagonal
 #else
-  if (hl != 0) return; // host emulation: one caller does the whole tile with the same operation order
-  float rdv[16];
-  { // same convention as the device path: the valid half of the tile is S[c][r], r >= c; mirror it first
-    for (int r = 0; r < 16; ++r) for (int c = 0; c < r; ++c) tile[tileIdx(r, c)] = tile[tileIdx(c, r)];
-  }
+  if (hl != 0) return; // host emulation: one caller plays the sixteen lanes in lock step with the same operation order
+  (void)hmask;
+  float A[16][16], z[16], rd[16]; // A[lane][k]
+  for (int l = 0; l < 16; ++l) { for (int k = 0; k < 16; ++k) A[l][k] = tile[tileIdx(k, l)]; z[l] = y16[l]; }
   for (int k = 0; k < 16; ++k) {
-    float piv = tile[tileIdx(k, k)];
+    float piv = A[k][k];
     if (!(piv > 0.f)) { piv = fallback; *fail = 1; }
-    const float rd = 1.f / sqrtf(piv);
-    const float d = piv * rd;
-    rdv[k] = rd;
-    float lk[16];
-    for (int r = 0; r < 16; ++r) lk[r] = tile[tileIdx(r, k)] * rd;
-    const float xk = y16[k] * rd;
-    for (int r = k + 1; r < 16; ++r)
-      for (int j = k + 1; j <= r; ++j) tile[tileIdx(r, j)] -= lk[r] * lk[j];
-    for (int r = k + 1; r < 16; ++r) { y16[r] -= lk[r] * xk; tile[tileIdx(r, k)] = lk[r]; }
-    y16[k] = xk;
-    tile[tileIdx(k, k)] = d;
-  }
-  float W[16][16];
-  for (int j = 0; j < 16; ++j)
-    for (int i = 0; i < 16; ++i) {
-      float s0 = (i == j) ? 1.f : 0.f, s1 = 0.f;
-      for (int m = 0; m < i; ++m) { if (m & 1) s1 += tile[tileIdx(i, m)] * W[m][j]; else s0 -= tile[tileIdx(i, m)] * W[m][j]; }
-      W[i][j] = (s0 - s1) * rdv[i];
+    const float inv = 1.f / piv;
+    rd[k] = 1.f / sqrtf(piv);
+    const float zk = z[k];
+    float colk[16];
+    for (int l = 0; l < 16; ++l) colk[l] = A[l][k];
+    for (int l = 0; l < 16; ++l) {
+      const float t = colk[l] * inv;
+      for (int j = k + 1; j < 16; ++j) A[l][j] -= t * colk[j];
+      if (l > k) z[l] -= t * zk;
     }
-  for (int i = 0; i < 16; ++i) for (int j = 0; j < 16; ++j) tile[tileIdx(i, j)] = W[i][j];
+  }
+  for (int l = 0; l < 16; ++l) y16[l] = z[l] * rd[l];
+  for (int l = 0; l < 16; ++l) for (int k = 0; k < 16; ++k) tile[tileIdx(k, l)] = A[l][k] * rd[k];
+  float W[16][16]; // W[i][lane]
+  for (int l = 0; l < 16; ++l) {
+    float sacc[16];
+    for (int m = 0; m < 16; ++m) sacc[m] = (m == l) ? 1.f : 0.f;
+    for (int i = 0; i < 16; ++i) {
+      W[i][l] = sacc[i] * rd[i];
+      for (int m = i + 1; m < 16; ++m) sacc[m] -= tile[tileIdx(i, m)] * W[i][l];
+    }
+  }
+  for (int i = 0; i < 16; ++i) for (int l = 0; l < 16; ++l) tile[tileIdx(i, l)] = W[i][l];
 #endif
 }
 
@@ -193,11 +195,18 @@ MB2_HD void cholPanelSolve(float* tile, const float* diagW, int hl) {
   for (int c = 0; c < 16; ++c) a[c] = tile[tileIdx(c, hl)];
 #pragma unroll
   for (int c = 0; c < 16; ++c) {
-    float wr[16];
-    tileLoadRow(diagW, c, wr); // row c of W: broadcast reads; entries beyond the diagonal are zero
+    // row c of W (broadcast reads); W is lower triangular: only columns j <= c contribute
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { if (j & 1) s1 += a[j] * wr[j]; else s0 += a[j] * wr[j]; }
+    for (int g = 0; g <= (c >> 2); ++g) {
+      const float4 wv = *reinterpret_cast<const float4*>(diagW + tileGrp(c, g));
+      const float wr[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = 4 * g + q;
+        if (j <= c) { if (j & 1) s1 += a[j] * wr[q]; else s0 += a[j] * wr[q]; }
+      }
+    }
     x[c] = s0 + s1;
   }
 #pragma unroll
@@ -235,33 +244,42 @@ MB2_HD void cholUpdateTask(float* tiles, const CholSchedDev& S, int task, int la
 
 // ---- phase C (vector part): y_I -= sum L(I,K) y_K over this level's columns; lane hl = row ----
 MB2_HD void cholVectorTask(const float* tiles, float* y, const CholSchedDev& S, int vtask, int hl) {
-  float s = 0.f;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f; // four partial sums: the dependent chain is 4 deep instead of 16 per source tile
   for (int p = S.vtaskSrcStart[vtask]; p < S.vtaskSrcStart[vtask + 1]; ++p) {
     const float* T = tiles + size_t(S.vsrcTile[p]) * 256;
     const float* yk = y + S.vsrcCol[p] * 16;
 #pragma unroll
-    for (int c = 0; c < 16; ++c) s += T[tileIdx(c, hl)] * yk[c];
+    for (int c = 0; c < 16; c += 4) {
+      s0 += T[tileIdx(c, hl)] * yk[c];
+      s1 += T[tileIdx(c + 1, hl)] * yk[c + 1];
+      s2 += T[tileIdx(c + 2, hl)] * yk[c + 2];
+      s3 += T[tileIdx(c + 3, hl)] * yk[c + 3];
+    }
   }
-  y[S.vtaskRow[vtask] * 16 + hl] -= s;
+  y[S.vtaskRow[vtask] * 16 + hl] -= (s0 + s1) + (s2 + s3);
 }
 
 // ---- backward substitution for one tile column K: y_K <- L(K,K)^-T (y_K - sum_I L(I,K)^T y_I) ----
 MB2_HD void cholBackwardColumn(const float* tiles, float* y, const CholSchedDev& S, int K, int hl, unsigned hmask) {
-  float s = y[K * 16 + hl];
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   for (int p = S.colPanelStart[K]; p < S.colPanelStart[K + 1]; ++p) {
     float t[16];
     tileLoadRow(tiles + size_t(S.colPanelTile[p]) * 256, hl, t); // row c = hl of the transposed tile: L[r][c], r = 0..15
     const float* yi = y + S.colPanelRow[p] * 16;
 #pragma unroll
-    for (int r = 0; r < 16; ++r) s -= t[r] * yi[r];
+    for (int r = 0; r < 16; r += 4) { s0 += t[r] * yi[r]; s1 += t[r + 1] * yi[r + 1]; s2 += t[r + 2] * yi[r + 2]; s3 += t[r + 3] * yi[r + 3]; }
   }
+  const float s = y[K * 16 + hl] - ((s0 + s1) + (s2 + s3));
   // x_K = W^T s with W = L(K,K)^-1 stored by phase A: stage s, then lane c accumulates column c of W
   const float* W = tiles + size_t(S.diagTile[K]) * 256;
 #if defined(__CUDA_ARCH__)
-  float x = 0.f;
+  float x0 = 0.f, x1 = 0.f;
 #pragma unroll
-  for (int r = 0; r < 16; ++r) x += W[tileIdx(r, hl)] * __shfl_sync(hmask, s, r, 16);
-  y[K * 16 + hl] = x;
+  for (int r = 0; r < 16; r += 2) {
+    x0 += W[tileIdx(r, hl)] * __shfl_sync(hmask, s, r, 16);
+    x1 += W[tileIdx(r + 1, hl)] * __shfl_sync(hmask, s, r + 1, 16);
+  }
+  y[K * 16 + hl] = x0 + x1;
 #else
   // host emulation: lanes run one after the other, so stage the sums, then lane 15 (last) finishes the block
   y[K * 16 + hl] = s;
@@ -269,9 +287,9 @@ MB2_HD void cholBackwardColumn(const float* tiles, float* y, const CholSchedDev&
   float sv[16];
   for (int r = 0; r < 16; ++r) sv[r] = y[K * 16 + r];
   for (int c = 0; c < 16; ++c) {
-    float x = 0.f;
-    for (int r = 0; r < 16; ++r) x += W[tileIdx(r, c)] * sv[r];
-    y[K * 16 + c] = x;
+    float x0 = 0.f, x1 = 0.f;
+    for (int r = 0; r < 16; r += 2) { x0 += W[tileIdx(r, c)] * sv[r]; x1 += W[tileIdx(r + 1, c)] * sv[r + 1]; }
+    y[K * 16 + c] = x0 + x1;
   }
 #endif
 }

@@ -428,15 +428,13 @@ __global__ void __launch_bounds__(kSchedThreads, 3) choleskyScheduledKernel(cons
     mbarExpectTx(barAddr, blobBytes + gBytes + uint32_t(Sg.numTiles) * 1024u);
   }
   __syncthreads();
-  if (lane == 0) { // TMA instructions take warp-uniform operands: one elected lane per warp issues, the tiles are dealt round-robin to the warps
-    if (warp == 0) {
-      bulkLoad(smemAddr(blob), Sg.blob, blobBytes, barAddr);
-      bulkLoad(smemAddr(gsub), a.g + size_t(b) * a.ldG, gBytes, barAddr);
-    }
-    for (int t = warp; t < Sg.numTiles; t += kSchedThreads / 32) {
-      const int gi0 = __ldg(Sg.tileInfo + 3 * t), gj0 = __ldg(Sg.tileInfo + 3 * t + 1);
-      tmaLoad3d(smemAddr(tiles + size_t(t) * 256), &hmap, gi0, gj0, b, barAddr);
-    }
+  if (tid == 0) {
+    bulkLoad(smemAddr(blob), Sg.blob, blobBytes, barAddr);
+    bulkLoad(smemAddr(gsub), a.g + size_t(b) * a.ldG, gBytes, barAddr);
+  }
+  for (int t = tid; t < Sg.numTiles; t += kSchedThreads) { // one thread per tile: the table reads overlap, the compiler serialises the TMA issue per warp
+    const int gi0 = __ldg(Sg.tileInfo + 3 * t), gj0 = __ldg(Sg.tileInfo + 3 * t + 1);
+    tmaLoad3d(smemAddr(tiles + size_t(t) * 256), &hmap, gi0, gj0, b, barAddr);
   }
   MB2_PROF(6)
   mbarWait(barAddr, 0);
