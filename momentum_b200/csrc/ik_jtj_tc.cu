@@ -122,7 +122,7 @@ __device__ __forceinline__ uint32_t makeInstrDesc(int m, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
+__global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmapHalf, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smemRaw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = (smemAddr(smemRaw) + 1023u) & ~1023u;
@@ -132,16 +132,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
   auto fullBar = [&](int s) { return barBase + 8u * s; };
   auto convBar = [&](int s) { return barBase + 8u * (p.stages + s); };
   auto emptyBar = [&](int s) { return barBase + 8u * (2 * p.stages + s); };
-  const uint32_t tmemFullBar = barBase + 8u * (3 * p.stages);
-  const uint32_t tmemEmptyBar = tmemFullBar + 8u;
-  const uint32_t tmemSlot = tmemEmptyBar + 8u;
+  // Work items: one accumulator tile of one instance. With two tiles an instance is the pair (tile 1: rows/cols 128.., then
+  // tile 0: rows 0..127 x all columns); each has its own TMEM columns and full/empty barriers, so the epilogue of one item
+  // drains while the MMAs of the next item run (TMEM cannot hold two complete instances: 2 x (n0 + n1) > 512 columns).
+  auto tmemFullBar = [&](int t) { return barBase + 8u * (3 * p.stages + t); };
+  auto tmemEmptyBar = [&](int t) { return barBase + 8u * (3 * p.stages + 2 + t); };
+  const uint32_t tmemSlot = barBase + 8u * (3 * p.stages + 4);
   const uint32_t stageOff = ((tmemSlot + 16u - base) + 15u) & ~15u; // epilogue transpose stages: 4 warps x 32 rows x 36 floats
   uint8_t* gen = smemRaw + (base - smemAddr(smemRaw)); // generic pointer to the aligned base
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbarInit(fullBar(s), 1); mbarInit(convBar(s), kConvThreads); mbarInit(emptyBar(s), 1); }
-    mbarInit(tmemFullBar, 1);
-    mbarInit(tmemEmptyBar, 128);
+    for (int t = 0; t < 2; ++t) { mbarInit(tmemFullBar(t), 1); mbarInit(tmemEmptyBar(t), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -161,115 +163,129 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
       long long wEmpty = 0, tStart = clock64();
       for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
         if (p.active != nullptr && p.active[b] == 0) continue;
-        for (int kb = 0; kb < p.kBlocks; ++kb) {
-          long long t0 = clock64();
-          mbarWait(emptyBar(s), ph ^ 1u);
-          wEmpty += clock64() - t0;
-          mbarExpectTx(fullBar(s), slabBytes);
-          tmaLoad3d(base + stageBytes * s, &tmap, kb * kKBlock, 0, b, fullBar(s));
-          if (++s == p.stages) { s = 0; ph ^= 1u; }
+        for (int t = p.mTiles - 1; t >= 0; --t) {
+          const bool half = t == 1; // tile 1 only needs columns 128.. of J: a 128-row box
+          for (int kb = 0; kb < p.kBlocks; ++kb) {
+            long long t0 = clock64();
+            mbarWaitRelaxed(emptyBar(s), ph ^ 1u);
+            wEmpty += clock64() - t0;
+            mbarExpectTx(fullBar(s), half ? 128u * kRowBytes : slabBytes);
+            tmaLoad3d(base + stageBytes * s, half ? &tmapHalf : &tmap, kb * kKBlock, half ? 128 : 0, b, fullBar(s));
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
+          }
         }
       }
-      if (p.profile && blockIdx.x == 0) printf("tc-profile producer: total %lld waitEmpty %lld\n", clock64() - tStart, wEmpty);
+      if ((p.profile & 1) && blockIdx.x == 0) printf("tc-profile producer: total %lld waitEmpty %lld\n", clock64() - tStart, wEmpty);
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
       int s = 0;
-      uint32_t ph = 0, tph = 0;
+      uint32_t ph = 0, tph[2] = {0, 0};
       const uint32_t idesc0 = makeInstrDesc(128, p.n0), idesc1 = makeInstrDesc(128, p.n1);
       long long wTmem = 0, wConv = 0, tStart = clock64();
       for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
         if (p.active != nullptr && p.active[b] == 0) continue;
-        long long t0 = clock64();
-        mbarWait(tmemEmptyBar, tph ^ 1u); // epilogue has drained the previous instance's accumulators
-        wTmem += clock64() - t0;
-        tcFenceAfter();
-        for (int kb = 0; kb < p.kBlocks; ++kb) {
-          t0 = clock64();
-          mbarWait(convBar(s), ph);
-          wConv += clock64() - t0;
+        for (int t = p.mTiles - 1; t >= 0; --t) {
+          long long t0 = clock64();
+          mbarWait(tmemEmptyBar(t), tph[t] ^ 1u); // the epilogue has drained this tile's accumulator of the previous instance
+          wTmem += clock64() - t0;
           tcFenceAfter();
-          const uint32_t hi = base + stageBytes * s, lo = hi + slabBytes;
-          for (int t = 0; t < p.mTiles; ++t) {
-            const uint32_t dcol = tmemBase + (t == 0 ? 0u : (uint32_t)p.n0);
-            const uint32_t idesc = t == 0 ? idesc0 : idesc1;
-            const uint32_t aOff = (uint32_t)t * 128u * kRowBytes;
+          const uint32_t dcol = tmemBase + (t == 0 ? 0u : (uint32_t)p.n0);
+          const uint32_t idesc = t == 0 ? idesc0 : idesc1;
+          for (int kb = 0; kb < p.kBlocks; ++kb) {
+            t0 = clock64();
+            mbarWait(convBar(s), ph);
+            wConv += clock64() - t0;
+            tcFenceAfter();
+            const uint32_t hi = base + stageBytes * s, lo = hi + slabBytes;
             for (int pass = 0; pass < p.passes; ++pass) {
-              const uint32_t aBase = (pass == 2 ? lo : hi) + aOff; // hi*hi, hi*lo, lo*hi
-              const uint32_t bBase = (pass == 1 ? lo : hi) + aOff; // tile 1 multiplies against rows 128.. only (upper triangle)
+              // A = the tile's 128 rows, B = every row of the slab (tile 1's slab starts at row 128: upper triangle only)
+              const uint32_t aBase = pass == 2 ? lo : hi; // hi*hi, hi*lo, lo*hi
+              const uint32_t bBase = pass == 1 ? lo : hi;
 #pragma unroll
               for (int k4 = 0; k4 < kKBlock / kUmmaK; ++k4) {
                 const uint32_t acc = (kb == 0 && pass == 0 && k4 == 0) ? 0u : 1u;
                 ummaTf32(dcol, makeSmemDesc(aBase + k4 * 32u), makeSmemDesc(bBase + k4 * 32u), idesc, acc);
               }
             }
+            ummaCommit(emptyBar(s)); // smem slab reusable once these MMAs have read it
+            if (kb == p.kBlocks - 1) ummaCommit(tmemFullBar(t));
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
           }
-          ummaCommit(emptyBar(s)); // smem slab reusable once these MMAs have read it
-          if (kb == p.kBlocks - 1) ummaCommit(tmemFullBar);
-          if (++s == p.stages) { s = 0; ph ^= 1u; }
+          tph[t] ^= 1u;
         }
-        tph ^= 1u;
       }
-      if (p.profile && blockIdx.x == 0) printf("tc-profile mma: total %lld waitTmemEmpty %lld waitConverted %lld\n", clock64() - tStart, wTmem, wConv);
+      if ((p.profile & 1) && blockIdx.x == 0) printf("tc-profile mma: total %lld waitTmemEmpty %lld waitConverted %lld\n", clock64() - tStart, wTmem, wConv);
     }
   } else if (warp < 10) {
     // ---------------- converters: raw fp32 -> tf32 hi (in place) and lo ----------------
     const int ct = threadIdx.x - 64; // 0..255
     int s = 0;
     uint32_t ph = 0;
-    const int vecs = (int)(slabBytes / 16u);
     long long wFull = 0, tStart = clock64();
     for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
       if (p.active != nullptr && p.active[b] == 0) continue;
-      for (int kb = 0; kb < p.kBlocks; ++kb) {
-        long long t0 = clock64();
-        mbarWait(fullBar(s), ph);
-        wFull += clock64() - t0;
-        float4* hi = reinterpret_cast<float4*>(gen + stageBytes * s);
-        float4* lo = reinterpret_cast<float4*>(gen + stageBytes * s + slabBytes);
+      for (int t = p.mTiles - 1; t >= 0; --t) {
+        const int vecs = t == 1 ? 128 * kRowBytes / 16 : (int)(slabBytes / 16u);
+        for (int kb = 0; kb < p.kBlocks; ++kb) {
+          long long t0 = clock64();
+          mbarWaitRelaxed(fullBar(s), ph);
+          wFull += clock64() - t0;
+          float4* hi = reinterpret_cast<float4*>(gen + stageBytes * s);
+          float4* lo = reinterpret_cast<float4*>(gen + stageBytes * s + slabBytes);
 #pragma unroll 4
-        for (int i = ct; i < vecs; i += kConvThreads) {
-          const float4 x = hi[i];
-          uint4 h;
-          h.x = toTf32(x.x); h.y = toTf32(x.y); h.z = toTf32(x.z); h.w = toTf32(x.w);
-          reinterpret_cast<uint4*>(hi)[i] = h;
-          if (p.passes == 3) {
-            uint4 l;
-            l.x = toTf32(x.x - __uint_as_float(h.x)); l.y = toTf32(x.y - __uint_as_float(h.y));
-            l.z = toTf32(x.z - __uint_as_float(h.z)); l.w = toTf32(x.w - __uint_as_float(h.w));
-            reinterpret_cast<uint4*>(lo)[i] = l;
+          for (int i = ct; i < vecs; i += kConvThreads) {
+            const float4 x = hi[i];
+            uint4 h;
+            h.x = toTf32(x.x); h.y = toTf32(x.y); h.z = toTf32(x.z); h.w = toTf32(x.w);
+            reinterpret_cast<uint4*>(hi)[i] = h;
+            if (p.passes == 3) {
+              uint4 l;
+              l.x = toTf32(x.x - __uint_as_float(h.x)); l.y = toTf32(x.y - __uint_as_float(h.y));
+              l.z = toTf32(x.z - __uint_as_float(h.z)); l.w = toTf32(x.w - __uint_as_float(h.w));
+              reinterpret_cast<uint4*>(lo)[i] = l;
+            }
           }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy stores -> visible to the tensor core (async proxy)
+          mbarArrive(convBar(s));
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy stores -> visible to the tensor core (async proxy)
-        mbarArrive(convBar(s));
-        if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
     }
-    if (p.profile && blockIdx.x == 0 && ct == 0) printf("tc-profile converter: total %lld waitFull %lld\n", clock64() - tStart, wFull);
+    if ((p.profile & 1) && blockIdx.x == 0 && ct == 0) printf("tc-profile converter: total %lld waitFull %lld\n", clock64() - tStart, wFull);
   } else {
     // ---------------- epilogue: TMEM -> global, column-major lower triangle of [JtJ; Jtr] ----------------
     const int q = warp & 3; // TMEM lane quarter this warp may access
     float* stage = reinterpret_cast<float*>(gen + stageOff) + (warp - 10) * 32 * kStageRowFloats;
-    uint32_t eph = 0;
-    long long wFullT = 0, tStart = clock64(), tLd = 0, nChunks = 0;
+    uint32_t eph[2] = {0, 0};
+    long long wFullT = 0, tStart = clock64(), tLd = 0, nChunks = 0, tSts = 0, tStg = 0;
     for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
       if (p.active != nullptr && p.active[b] == 0) continue;
       float* H = p.H + (size_t)b * p.hStride;
-      long long t0 = clock64();
-      mbarWait(tmemFullBar, eph);
-      wFullT += clock64() - t0;
-      tcFenceAfter();
-      for (int t = 0; t < p.mTiles; ++t) {
+      for (int t = p.mTiles - 1; t >= 0; --t) {
+        long long t0 = clock64();
+        mbarWaitRelaxed(tmemFullBar(t), eph[t]);
+        wFullT += clock64() - t0;
+        tcFenceAfter();
         const int rowBase = t * 128 + q * 32;                     // first of this warp's 32 rows of [J r]^T [J r]
         const int row = rowBase + lane;
         const int i = row < p.ns ? row : (row == p.numCols ? p.ns : -1); // row of the (ns+1) system; -1: not wanted
-        if (__reduce_max_sync(0xffffffffu, i) < 0) continue;       // warp-uniform: nothing to write from these 32 rows
+        if (__reduce_max_sync(0xffffffffu, i) < 0) { tcFenceBefore(); mbarArrive(tmemEmptyBar(t)); eph[t] ^= 1u; continue; } // warp-uniform: nothing to write
         const int nT = t == 0 ? p.n0 : p.n1;
         const uint32_t colBase = tmemBase + ((uint32_t)(q * 32) << 16) + (t == 0 ? 0u : (uint32_t)p.n0);
         if (p.ns == p.numCols) {
           // solver path: full rows. 32x32 blocks go TMEM -> registers -> shared (row = TMEM lane) -> global, re-mapped so
           // that one store instruction writes four rows x 128 contiguous bytes.
+          // the four rows x 128 bytes this lane stores per instruction are the same for every chunk of the tile
+          float* rowPtr[8];
+          int rowIo[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int rowAbs = rowBase + 4 * k + (lane >> 3);
+            rowIo[k] = rowAbs < p.ns ? rowAbs : (rowAbs == p.numCols ? p.ns : (1 << 30)); // 1 << 30: never stored (col + 3 >= row fails)
+            rowPtr[k] = H + (size_t)(rowIo[k] < (1 << 30) ? rowIo[k] : 0) * p.ldH + 4 * (lane & 7);
+          }
           for (int c0 = 0; c0 < nT; c0 += 32) {
             if (t * 128 + c0 + 32 <= rowBase && !(t * 128 + c0 <= p.numCols && p.numCols < t * 128 + c0 + 32)) continue; // entirely left of the diagonal
             float v[32];
@@ -281,18 +297,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
             for (int g4 = 0; g4 < 8; ++g4)
               *reinterpret_cast<float4*>(stage + lane * kStageRowFloats + 4 * g4) = make_float4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
             __syncwarp();
+            if (p.profile) { tSts += clock64() - tl0; }
             if (p.G != nullptr && t * 128 + c0 <= p.numCols && p.numCols < t * 128 + c0 + 32 && i >= 0 && i < p.ns) // column numCols = J^T r
               p.G[(size_t)b * p.ldG + i] = stage[lane * kStageRowFloats + (p.numCols - t * 128 - c0)];
             const int c = t * 128 + c0 + 4 * (lane & 7); // matrix column of this lane's float4
+            float4 vals[8]; // all shared-memory reads first: the compiler cannot move them across the global stores itself (possible aliasing)
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const int rr = 4 * k + (lane >> 3);
-              const int rowAbs = rowBase + rr;
-              const int io = rowAbs < p.ns ? rowAbs : (rowAbs == p.numCols ? p.ns : -1);
-              if (io >= 0 && c < p.ldH && c + 3 >= io) // upper triangle (col >= row) only: everything downstream reads H(min, max)
-                *reinterpret_cast<float4*>(H + (size_t)io * p.ldH + c) = *reinterpret_cast<const float4*>(stage + rr * kStageRowFloats + 4 * (lane & 7));
+            for (int k = 0; k < 8; ++k) vals[k] = *reinterpret_cast<const float4*>(stage + (4 * k + (lane >> 3)) * kStageRowFloats + 4 * (lane & 7));
+            if (!(p.profile & 2) && c < p.ldH) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                if (c + 3 >= rowIo[k]) *reinterpret_cast<float4*>(rowPtr[k] + (t * 128 + c0)) = vals[k]; // upper triangle (col >= row) only: everything downstream reads H(min, max)
             }
             __syncwarp();
+            if (p.profile) { tStg += clock64() - tl0; }
           }
         } else {
           // leading-block request (ns < numCols, getJtJR parity entry): columns ns.. are skipped except the residual column
@@ -309,12 +327,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
             }
           }
         }
+        tcFenceBefore();
+        mbarArrive(tmemEmptyBar(t));
+        eph[t] ^= 1u;
       }
-      tcFenceBefore();
-      mbarArrive(tmemEmptyBar);
-      eph ^= 1u;
     }
-    if (p.profile && blockIdx.x == 0 && threadIdx.x == 10 * 32) printf("tc-profile epilogue: total %lld waitTmemFull %lld tmemLoad %lld chunks %lld\n", clock64() - tStart, wFullT, tLd, nChunks);
+    if ((p.profile & 1) && blockIdx.x == 0 && lane == 0)
+      printf("tc-profile epilogue q%d: total %lld waitTmemFull %lld chunks %lld | cumulative per chunk: tmemLoad %lld +sts %lld +stg %lld\n", q, clock64() - tStart, wFullT, nChunks,
+             tLd / (nChunks ? nChunks : 1), tSts / (nChunks ? nChunks : 1), tStg / (nChunks ? nChunks : 1));
   }
   tcFenceBefore();
   __syncthreads();
@@ -386,7 +406,11 @@ cudaError_t launchJtJTensor(const JtJArgs& a, int passes, cudaStream_t stream) {
   const uint64_t dims[3] = {(uint64_t)a.ldJ, (uint64_t)(a.numCols + 1), (uint64_t)a.batch};
   const uint64_t strides[2] = {(uint64_t)a.ldJ * sizeof(float), (uint64_t)(a.numCols + 1) * a.ldJ * sizeof(float)};
   const uint32_t box[3] = {(uint32_t)kKBlock, (uint32_t)sh.boxRows, 1u};
-  const cudaError_t me = makeTensorMap3d(&map, a.jacobian, dims, strides, box, 128);
+  cudaError_t me = makeTensorMap3d(&map, a.jacobian, dims, strides, box, 128);
+  if (me != cudaSuccess) return me;
+  CUtensorMap mapHalf; // 128-row box for the second accumulator tile (columns 128.. of J)
+  const uint32_t boxHalf[3] = {(uint32_t)kKBlock, 128u, 1u};
+  me = makeTensorMap3d(&mapHalf, a.jacobian, dims, strides, boxHalf, 128);
   if (me != cudaSuccess) return me;
   TcParams p{};
   p.batch = a.batch;
@@ -406,20 +430,20 @@ cudaError_t launchJtJTensor(const JtJArgs& a, int passes, cudaStream_t stream) {
   p.hStride = a.hStride;
   p.G = a.g;
   p.ldG = a.ldG;
-  p.profile = getenv("MB2_TC_PROFILE") != nullptr ? 1 : 0;
+  p.profile = getenv("MB2_TC_PROFILE") != nullptr ? atoi(getenv("MB2_TC_PROFILE")) : 0;
   const size_t stageBytes = size_t(sh.boxRows) * kRowBytes * (p.passes == 3 ? 2 : 1);
   int stages = int((196 * 1024) / stageBytes);
   if (stages > 6) stages = 6;
   if (stages < 2) return cudaErrorInvalidConfiguration;
   p.stages = stages;
-  const size_t smem = stageBytes * stages + 1024 /*alignment slack*/ + 8 * (3 * stages + 2) + 48 + 4 * 32 * kStageRowFloats * sizeof(float);
+  const size_t smem = stageBytes * stages + 1024 /*alignment slack*/ + 8 * (3 * stages + 4) + 48 + 4 * 32 * kStageRowFloats * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(jtjTensorKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = a.batch < sms ? a.batch : sms;
-  jtjTensorKernel<<<grid, kTcThreads, smem, stream>>>(map, p);
+  jtjTensorKernel<<<grid, kTcThreads, smem, stream>>>(map, mapHalf, p);
   return cudaGetLastError();
 }
 

@@ -39,6 +39,27 @@ __device__ __forceinline__ void mbarWait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// same, for waiters with slack (producer / converter / epilogue roles): sleeps between polls so that the spinning warp does not
+// take issue slots from the warps doing the work
+__device__ __forceinline__ void mbarWaitRelaxed(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(32);
+    if ((uint64_t)(clock64() - t0) > kSpinLimit) {
+      printf("momentum_b200: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ void tmaLoad3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),

@@ -545,3 +545,27 @@ extern "C" int emu_chol_schedule_dump(int n, int numCliques, const int* cliqueSt
   }
   return MB2_OK;
 }
+
+extern "C" int emu_chol_chunk_stats(int n, int numCliques, const int* cliqueStart, const int* cliqueCols) {
+  std::vector<std::vector<int>> cl(numCliques);
+  for (int c = 0; c < numCliques; ++c) cl[c].assign(cliqueCols + cliqueStart[c], cliqueCols + cliqueStart[c + 1]);
+  CholSchedule s;
+  const std::string e = buildCholSchedule(n, cl, false, s);
+  if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
+  std::vector<int32_t> order;
+  layoutDeviceColumns(s, order);
+  const int nd = s.n + 1; // + residual column
+  const int nb = (nd + 31) / 32;
+  std::vector<int> need(nb * nb, 0);
+  auto validOf = [&](int K) { int v = 0; while (v < 16 && s.perm[16 * K + v] >= 0) ++v; return v; };
+  for (int t = 0; t < s.numTiles; ++t) {
+    const int I = s.tileRow[t], J = s.tileCol[t];
+    const int vI = validOf(I), vJ = validOf(J), gi0 = s.perm[16 * I], gj0 = s.perm[16 * J];
+    for (int r = gj0; r < gj0 + vJ; ++r) for (int c = gi0; c < gi0 + vI; ++c) if (c >= r) need[(r / 32) * nb + c / 32] = 1;
+  }
+  int total = 0, needed = 0;
+  for (int a = 0; a < nb; ++a) for (int b2 = a; b2 < nb; ++b2) { ++total; needed += need[a * nb + b2] || b2 == (nd - 1) / 32; }
+  std::printf("device columns %d (+1), 32x32 chunks in the upper triangle %d, needed %d\n", s.n, total, needed);
+  for (int a = 0; a < nb; ++a) { for (int b2 = 0; b2 < nb; ++b2) std::printf("%c", b2 < a ? ' ' : (need[a * nb + b2] ? '#' : (b2 == (nd - 1) / 32 ? 'g' : '.'))); std::printf("\n"); }
+  return MB2_OK;
+}
