@@ -84,10 +84,11 @@ typedef enum mb2_rotation_error_type {
 
 /* How JtJ is formed on the device (extension; the reference always uses Eigen fp32/fp64 GEMM). */
 typedef enum mb2_jtj_mode {
-  MB2_JTJ_AUTO = 0,      /* tensor-core 3xTF32 where the shape allows, else FP32 SIMT */
+  MB2_JTJ_AUTO = 0,      /* tile-sparse fp32 Gram with the tile-scheduled Cholesky; else tensor-core 3xTF32 where the shape allows, else FP32 SIMT */
   MB2_JTJ_FP32_SIMT = 1, /* CUDA-core fp32 (validation path) */
   MB2_JTJ_TF32X3 = 2,    /* tcgen05 kind::tf32, 3-term split, fp32 accumulate in TMEM (fp32-class accuracy) */
-  MB2_JTJ_TF32 = 3       /* tcgen05 kind::tf32 single pass (~1e-3 relative; changes the GN path, not the fixed point) */
+  MB2_JTJ_TF32 = 3,      /* tcgen05 kind::tf32 single pass (~1e-3 relative; changes the GN path, not the fixed point) */
+  MB2_JTJ_SPARSE_TILES = 4 /* fp32 CUDA cores over the non-zero strips of J only, straight into the Cholesky tile layout (tile-scheduled Cholesky only) */
 } mb2_jtj_mode;
 
 /* How (JtJ + lambda I) delta = Jtr is solved on the device (extension; the reference always runs a dense

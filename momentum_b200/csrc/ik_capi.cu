@@ -83,6 +83,9 @@ struct DeviceSchedule {
   bool valid{false};
   bool dense{false};
   DeviceBuffer<int32_t> blob;
+  GramPlan gram;          // tile-sparse Gram tables of the same plan (rows aligned to quads)
+  bool gramValid{false};
+  DeviceBuffer<int32_t> gStripCoord, gTileOrder, gTilePairStart, gPairA, gPairB, gColStripStart, gColStrip;
 };
 
 struct mb2_solver_function {
@@ -96,6 +99,7 @@ struct mb2_solver_function {
   bool planDirty{true};
   int planMode{0};        // 0 full columns (API parity), 1 solver: enabled columns in natural order, 2 solver: elimination order + tile schedule
   bool planSchedDense{false};
+  bool planAlignRows{false}; // row groups aligned to 4 (tile-sparse Gram reads the Jacobian in 4-row strips)
   uint64_t planLimitsVersion{~0ull};
   Plan plan;
   int ldJ{32};
@@ -122,7 +126,7 @@ struct PhaseEvent {
 struct mb2_solver {
   mb2_solver_function* fn{nullptr};
   mb2_gauss_newton_options opt{};
-  DeviceBuffer<float> dH, dDelta, dThetaOrig, dTheta0, dScale, dGradDotDelta, dThetaStage, dGrad;
+  DeviceBuffer<float> dH, dDelta, dThetaOrig, dTheta0, dScale, dGradDotDelta, dThetaStage, dGrad, dTiles;
   DeviceBuffer<double> dLastErrors, dTrialErrors, dHistory;
   DeviceBuffer<int32_t> dActive, dIterations, dStatus, dSearching, dActiveCount;
   int* hActiveCount{nullptr}; // pinned
@@ -171,6 +175,10 @@ FunctionTables mb2_solver_function::tables() const {
   T.ptNnz = int(h.ptInner.size());
   T.numContribs = int(plan.contribs.size());
   T.numLimitData = int(plan.limitData.size());
+  const bool strips = planMode == 2 && planAlignRows && sched && sched->gramValid;
+  T.stripMode = strips ? 1 : 0;
+  T.residOff = strips ? sched->gram.residOff : 0;
+  T.jacobianStride = strips ? size_t(sched->gram.stride) : size_t(plan.numCols + 1) * ldJ;
   return T;
 }
 
@@ -237,11 +245,13 @@ int uploadSchedule(mb2_solver_function* f, std::unique_ptr<DeviceSchedule>& ds) 
 // mode 1: solver, only the enabled columns, ascending (dense Eigen-structured Cholesky);
 // mode 2: solver, enabled columns in the Cholesky elimination order + tile schedule (schedDense: dense pattern).
 // Modes 0 and 1 coincide when every parameter is enabled.
-int ensurePlan(mb2_solver_function* f, int mode, bool schedDense = false) {
+int ensurePlan(mb2_solver_function* f, int mode, bool schedDense = false, bool alignRows = false) {
   bool allEnabled = true;
   for (uint8_t e : f->enabled) allEnabled = allEnabled && e;
   if (allEnabled && mode == 1) mode = 0;
-  if (!f->planDirty && f->planLimitsVersion == f->ch->limitsVersion && f->planMode == mode && (mode != 2 || f->planSchedDense == schedDense)) return MB2_OK;
+  if (mode != 2) alignRows = false;
+  if (!f->planDirty && f->planLimitsVersion == f->ch->limitsVersion && f->planMode == mode && (mode != 2 || (f->planSchedDense == schedDense && f->planAlignRows == alignRows)))
+    return MB2_OK;
   MB2_CUDA(cudaSetDevice(f->ch->device));
   cudaStream_t s = f->stream;
   f->sched.reset();
@@ -258,8 +268,23 @@ int ensurePlan(mb2_solver_function* f, int mode, bool schedDense = false) {
     std::vector<int32_t> colOrder;
     layoutDeviceColumns(ds->host, colOrder);
     for (int32_t& c : colOrder) if (c >= 0) c = f->plan.enabledList[c];
-    err = buildPlan(f->ch->host, f->efs, f->enabled, true, f->plan, &colOrder);
+    err = buildPlan(f->ch->host, f->efs, f->enabled, true, f->plan, &colOrder, alignRows);
     if (!err.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, err);
+    if (alignRows) {
+      std::vector<int32_t> cr0, crn, cc;
+      for (const CellDesc& c : f->plan.cells) { cr0.push_back(f->plan.units[c.unit].row0); crn.push_back(f->plan.units[c.unit].numRows); cc.push_back(int32_t(c.col)); }
+      err = buildGramPlan(ds->host, cr0, crn, cc, f->plan.numRows, ds->gram);
+      if (!err.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, err);
+      for (size_t i = 0; i < f->plan.cells.size(); ++i) { f->plan.cells[i].stripOff = ds->gram.cellStripOff[i]; f->plan.cells[i].quadStride = ds->gram.cellQuadStride[i]; }
+      MB2_CUDA(ds->gStripCoord.upload(ds->gram.stripCoord, s));
+      MB2_CUDA(ds->gTileOrder.upload(ds->gram.tileOrder, s));
+      MB2_CUDA(ds->gTilePairStart.upload(ds->gram.tilePairStart, s));
+      MB2_CUDA(ds->gPairA.upload(ds->gram.pairA, s));
+      MB2_CUDA(ds->gPairB.upload(ds->gram.pairB, s));
+      MB2_CUDA(ds->gColStripStart.upload(ds->gram.colStripStart, s));
+      MB2_CUDA(ds->gColStrip.upload(ds->gram.colStrip, s));
+      ds->gramValid = true;
+    }
     ds->dense = schedDense;
     int rc = uploadSchedule(f, ds);
     if (rc != MB2_OK) return rc;
@@ -267,6 +292,7 @@ int ensurePlan(mb2_solver_function* f, int mode, bool schedDense = false) {
   }
   f->planMode = mode;
   f->planSchedDense = schedDense;
+  f->planAlignRows = alignRows;
   MB2_CUDA(f->dEfs.upload(f->plan.efs, s));
   MB2_CUDA(f->dUnits.upload(f->plan.units, s));
   MB2_CUDA(f->dCells.upload(f->plan.cells, s));
@@ -278,7 +304,8 @@ int ensurePlan(mb2_solver_function* f, int mode, bool schedDense = false) {
   for (size_t i = 0; i < ident.size(); ++i) ident[i] = int32_t(i);
   MB2_CUDA(f->dIdentity.upload(ident, s));
   f->ldJ = std::max(32, roundUp(f->plan.numRows, 32));
-  const size_t jElems = size_t(f->B) * (f->plan.numCols + 1) * f->ldJ;
+  const bool stripLayout = mode == 2 && alignRows; // strips + residual instead of the K-major matrix
+  const size_t jElems = stripLayout ? size_t(f->B) * size_t(f->sched->gram.stride) : size_t(f->B) * (f->plan.numCols + 1) * f->ldJ;
   MB2_CUDA(f->dJ.resize(jElems));
   // cells outside the plan are never written: zero once per plan (ResizeableMatrix::resizeAndSetZero
   // happens every iteration in the reference, solver_function.cpp:96)
@@ -653,7 +680,7 @@ int mb2_solver_function_set_enabled_parameters(mb2_solver_function* f, const uin
 
 int mb2_solver_function_get_error(mb2_solver_function* f, const float* params, double* errors) {
   MB2_CHECK(f != nullptr && params && errors, "null argument");
-  int rc = ensurePlan(f, f->planMode, f->planSchedDense);
+  int rc = ensurePlan(f, f->planMode, f->planSchedDense, f->planAlignRows);
   if (rc != MB2_OK) return rc;
   const size_t n = f->ch->host.numParams;
   MB2_CUDA(cudaMemcpyAsync(f->dTheta.p, params, size_t(f->B) * n * sizeof(float), cudaMemcpyHostToDevice, f->stream));
@@ -718,7 +745,7 @@ int mb2_solver_function_get_jtjr(mb2_solver_function* f, const float* params, in
 
 int mb2_solver_function_get_skeleton_state(mb2_solver_function* f, const float* params, float* state) {
   MB2_CHECK(f != nullptr && params && state, "null argument");
-  int rc = ensurePlan(f, f->planMode, f->planSchedDense);
+  int rc = ensurePlan(f, f->planMode, f->planSchedDense, f->planAlignRows);
   if (rc != MB2_OK) return rc;
   const size_t n = f->ch->host.numParams;
   const size_t sz = size_t(f->B) * f->ch->host.numJoints * 8;
@@ -770,12 +797,16 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
   for (uint8_t e : f->enabled) numEnabled += e ? 1 : 0;
   int cholMode = o.cholesky_mode;
   if (cholMode == 0) cholMode = numEnabled >= 48 ? 3 : 1;
-  int rc = ensurePlan(f, cholMode >= 2 ? 2 : 1, cholMode == 2);
+  // tile-sparse Gram: default whenever the tile-scheduled Cholesky runs (MB2_JTJ_AUTO), or on request
+  bool useGram = cholMode >= 2 && (o.jtj_mode == MB2_JTJ_AUTO || o.jtj_mode == MB2_JTJ_SPARSE_TILES);
+  if (o.jtj_mode == MB2_JTJ_SPARSE_TILES && cholMode < 2) return fail(MB2_ERR_UNSUPPORTED, "MB2_JTJ_SPARSE_TILES needs the tile-scheduled Cholesky");
+  int rc = ensurePlan(f, cholMode >= 2 ? 2 : 1, cholMode == 2, useGram);
   if (rc != MB2_OK) return rc;
   bool useSchedule = cholMode >= 2;
   if (useSchedule && choleskyScheduledSmemBytes(f->plan.numCols, f->sched->host.nPad, f->sched->host.numTiles, f->sched->dev.blobInts) > size_t(200 * 1024)) {
     if (o.cholesky_mode >= 2) return fail(MB2_ERR_UNSUPPORTED, "tile schedule does not fit in shared memory for this system");
     useSchedule = false; // fall back to the dense kernel (matrix in global memory)
+    useGram = false;
     rc = ensurePlan(f, 1);
     if (rc != MB2_OK) return rc;
   }
@@ -785,13 +816,21 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
   const int maxIt = int(std::min<uint64_t>(o.max_iterations, 1u << 30));
   const int minIt = int(std::min<uint64_t>(o.min_iterations, 1u << 30));
   MB2_CHECK(ns > 0, "no enabled parameters");
-  const int mode = resolveJtjMode(f, o.jtj_mode, ns);
+  if (useGram && gramTilesSmemBytes(size_t(f->sched->gram.stride)) > size_t(200 * 1024)) {
+    if (o.jtj_mode == MB2_JTJ_SPARSE_TILES) return fail(MB2_ERR_UNSUPPORTED, "Jacobian strips do not fit in shared memory for this system");
+    useGram = false;
+    rc = ensurePlan(f, 2, cholMode == 2, false);
+    if (rc != MB2_OK) return rc;
+  }
+  const int mode = useGram ? MB2_JTJ_SPARSE_TILES : resolveJtjMode(f, o.jtj_mode == MB2_JTJ_SPARSE_TILES ? MB2_JTJ_AUTO : o.jtj_mode, ns);
   if (mode < 0) return fail(MB2_ERR_UNSUPPORTED, "tensor-core JtJ does not support this shape");
   // normal equations: full symmetric [ns+1][ldH] in device-column order (row/column ns = J^T r)
   const int ldH = roundUp(ns + 1, 16);
   const size_t hStride = size_t(ns + 1) * ldH;
-  MB2_CUDA(s->dH.resize(size_t(B) * hStride));
+  if (!useGram) MB2_CUDA(s->dH.resize(size_t(B) * hStride));
   float* Hbuf = s->dH.p;
+  const size_t tilesStride = useGram ? size_t(f->sched->host.numTiles) * 256 + f->sched->host.nPad : 0;
+  if (useGram) MB2_CUDA(s->dTiles.resize(size_t(B) * tilesStride));
   const int ldG = cholGradientLd(ns);
   MB2_CUDA(s->dGrad.resize(size_t(B) * ldG));
   MB2_CUDA(s->dDelta.resize(size_t(B) * ns));
@@ -829,8 +868,34 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
     MB2_CUDA(launchSweep(sweepArgs(f, theta, s->dActive.p), true, st));
     recordPhaseStop(s, st);
     recordPhaseStart(s, 1, st);
-    rc = runJtJ(f, mode, ns, Hbuf, ldH, hStride, s->dActive.p, st, s->dGrad.p, ldG);
-    if (rc != MB2_OK) return rc;
+    if (useGram) {
+      const DeviceSchedule& ds = *f->sched;
+      GramArgs g{};
+      g.batch = B;
+      g.strips = f->dJ.p;
+      g.stripStride = size_t(ds.gram.stride);
+      g.residOff = ds.gram.residOff;
+      g.active = s->dActive.p;
+      g.numStrips = ds.gram.numStrips;
+      g.numTiles = ds.host.numTiles;
+      g.numTileCols = ds.host.numTileCols;
+      g.nPad = ds.host.nPad;
+      g.stripCoord = ds.gStripCoord.p;
+      g.tileOrder = ds.gTileOrder.p;
+      g.tilePairStart = ds.gTilePairStart.p;
+      g.pairA = ds.gPairA.p;
+      g.pairB = ds.gPairB.p;
+      g.colStripStart = ds.gColStripStart.p;
+      g.colStrip = ds.gColStrip.p;
+      g.tileInfo = ds.dev.tileInfo;
+      g.regularization = o.regularization;
+      g.out = s->dTiles.p;
+      g.outStride = tilesStride;
+      MB2_CUDA(launchGramTiles(g, st));
+    } else {
+      rc = runJtJ(f, mode, ns, Hbuf, ldH, hStride, s->dActive.p, st, s->dGrad.p, ldG);
+      if (rc != MB2_OK) return rc;
+    }
     recordPhaseStop(s, st);
     CholArgs c{};
     c.batch = B;
@@ -859,6 +924,8 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
     c.gradDotDelta = lineSearch ? s->dGradDotDelta.p : nullptr;
     c.g = s->dGrad.p;
     c.ldG = ldG;
+    c.tilesIn = useGram ? s->dTiles.p : nullptr;
+    c.tilesStride = tilesStride;
     c.profile = (it == 0 && getenv("MB2_CHOL_PROFILE") != nullptr) ? 1 : 0;
     if (const char* ex = getenv("MB2_CHOL_EXPERIMENT")) c.profile |= atoi(ex) << 8; // timing experiments only (results invalid)
     recordPhaseStart(s, 2, st);

@@ -240,6 +240,76 @@ std::string buildCholSchedule(int n, const std::vector<std::vector<int>>& clique
   return "";
 }
 
+std::string buildGramPlan(const CholSchedule& s, const std::vector<int32_t>& cellRow0, const std::vector<int32_t>& cellRows, const std::vector<int32_t>& cellCol,
+                          int numRows, GramPlan& out) {
+  out = GramPlan();
+  out.numTiles = s.numTiles;
+  out.numTileCols = s.numTileCols;
+  const int T = s.numTileCols;
+  std::map<std::pair<int, int>, int> stripId; // (quad, tile column) -> strip, in (quad, K) order
+  for (size_t i = 0; i < cellCol.size(); ++i) {
+    const int d = cellCol[i];
+    if (d < 0 || d >= s.n || s.pos[d] < 0) return "Jacobian cell in a column outside the schedule";
+    const int K = s.pos[d] >> 4;
+    for (int q = cellRow0[i] >> 2; q <= (cellRow0[i] + cellRows[i] - 1) >> 2; ++q) stripId[{q, K}] = 0;
+  }
+  int next = 0;
+  for (auto& kv : stripId) kv.second = next++;
+  out.numStrips = next;
+  out.stripCoord.resize(size_t(next) * 2);
+  std::vector<std::vector<int>> ofCol(T);
+  std::map<int, std::vector<int>> colsOfQuad;
+  for (const auto& kv : stripId) {
+    const int q = kv.first.first, K = kv.first.second;
+    out.stripCoord[2 * kv.second] = 4 * q;
+    out.stripCoord[2 * kv.second + 1] = s.perm[16 * K]; // first slot of a tile column is always a real device column
+    ofCol[K].push_back(kv.second);
+    colsOfQuad[q].push_back(K);
+  }
+  std::vector<std::vector<std::pair<int, int>>> pairs(s.numTiles);
+  for (const auto& kv : colsOfQuad) {
+    const int q = kv.first;
+    const std::vector<int>& cols = kv.second; // ascending
+    for (size_t a = 0; a < cols.size(); ++a)
+      for (size_t b = 0; b <= a; ++b) {
+        const int I = cols[a], J = cols[b];
+        const int t = s.tileIdTable[size_t(I) * T + J];
+        if (t < 0) return "Gram plan: a Jacobian row couples two tile columns whose tile is not in the schedule";
+        pairs[t].push_back({stripId[{q, I}], stripId[{q, J}]});
+      }
+  }
+  out.tilePairStart.assign(s.numTiles + 1, 0);
+  for (int t = 0; t < s.numTiles; ++t) {
+    out.tilePairStart[t + 1] = out.tilePairStart[t] + int(pairs[t].size());
+    for (const auto& pr : pairs[t]) { out.pairA.push_back(pr.first); out.pairB.push_back(pr.second); }
+    out.macs += int64_t(pairs[t].size()) * 16 * 16 * 4;
+  }
+  out.tileOrder.resize(s.numTiles);
+  for (int t = 0; t < s.numTiles; ++t) out.tileOrder[t] = t;
+  std::stable_sort(out.tileOrder.begin(), out.tileOrder.end(), [&](int a, int b) { return pairs[a].size() > pairs[b].size(); });
+  // where each cell writes: strips of one quad are consecutive (ascending tile column); a multi-row unit owns its quads, so its
+  // quads all have the same tile columns and the same cell is a constant number of strips further in the next quad
+  std::map<int, int> stripsOfQuad;
+  for (const auto& kv : stripId) ++stripsOfQuad[kv.first.first];
+  out.cellStripOff.resize(cellCol.size());
+  out.cellQuadStride.resize(cellCol.size());
+  for (size_t i = 0; i < cellCol.size(); ++i) {
+    const int d = cellCol[i], K = s.pos[d] >> 4, q0 = cellRow0[i] >> 2;
+    out.cellStripOff[i] = uint32_t(stripId[{q0, K}]) * 64u + uint32_t(d - s.perm[16 * K]) * 4u;
+    out.cellQuadStride[i] = uint16_t(stripsOfQuad[q0]);
+    for (int q = q0 + 1; q <= (cellRow0[i] + cellRows[i] - 1) >> 2; ++q)
+      if (stripsOfQuad[q] != stripsOfQuad[q0] || stripId[{q, K}] != stripId[{q0, K}] + (q - q0) * stripsOfQuad[q0]) return "Gram plan: row quads of one unit are not laid out uniformly";
+  }
+  out.residOff = out.numStrips * 64;
+  out.stride = out.residOff + ((numRows + 3) & ~3);
+  out.colStripStart.assign(T + 1, 0);
+  for (int K = 0; K < T; ++K) {
+    out.colStripStart[K + 1] = out.colStripStart[K] + int(ofCol[K].size());
+    out.colStrip.insert(out.colStrip.end(), ofCol[K].begin(), ofCol[K].end());
+  }
+  return "";
+}
+
 void layoutDeviceColumns(CholSchedule& s, std::vector<int32_t>& deviceColumnOrder) {
   deviceColumnOrder.clear();
   s.nParams = s.n;

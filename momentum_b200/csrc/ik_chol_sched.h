@@ -60,6 +60,29 @@ inline int cholSchedLdH(int n) { return (n + 1 + 15) / 16 * 16; }
 // tileInfo (3 ints per tile, in the device blob): {gi0, gj0, validI | validJ << 8 | diag << 16}: tile (I,J) is the 16x16 box of
 // H with first row gj0 (device column of slot 16 J) and first column gi0 (slot 16 I); only its first validJ rows / validI columns
 // are real (padding only closes a tile), the rest is overwritten by the padding pass.
+// ---- Tile-sparse Gram plan: the stored tiles of J^T J straight from the non-zero pieces of the Jacobian ----
+// Row quads: rows 4q..4q+3 of the (row-group aligned) Jacobian. A *strip* is (quad q, tile column K): the 4 x 16 piece
+// J[4q..4q+3][gi0(K)..gi0(K)+15] -- one TMA box of the K-major device Jacobian, landing as [16 columns][4 rows]. A strip
+// exists only where a unit with rows in q has a cell in tile column K. Tile (I,J) = sum over quads touching both I and J
+// of strip(q,I)^T strip(q,J); block K of J^T r = sum over its strips of strip^T r[4q..4q+3].
+struct GramPlan {
+  int32_t numStrips{0}, numTiles{0}, numTileCols{0};
+  std::vector<int32_t> stripCoord;    // [numStrips][2] {first row 4q, first device column gi0(K)}; strips are ordered by (quad, tile column)
+  std::vector<int32_t> tileOrder;     // tiles by decreasing pair count (work is dealt round-robin to warps in this order)
+  std::vector<int32_t> tilePairStart; // [numTiles + 1] indexed by tile id
+  std::vector<int32_t> pairA, pairB;  // strips of block row I / block column J of the tile
+  std::vector<int32_t> colStripStart; // [numTileCols + 1]
+  std::vector<int32_t> colStrip;      // strips of tile column K
+  std::vector<uint32_t> cellStripOff; // per Jacobian cell: float offset of (first row quad, its column) in the strip buffer
+  std::vector<uint16_t> cellQuadStride; // per cell: strips between consecutive row quads of its unit
+  int32_t residOff{0};                // the residual (aligned row numbering) follows the strips
+  int32_t stride{0};                  // floats per instance: residOff + rows rounded up to 4
+  int64_t macs{0};                    // multiply-accumulates per instance (statistics)
+};
+// rowsOfCell[i] = {first row, row count, device column} of Jacobian cell i; needs layoutDeviceColumns() first.
+std::string buildGramPlan(const CholSchedule& s, const std::vector<int32_t>& cellRow0, const std::vector<int32_t>& cellRows, const std::vector<int32_t>& cellCol,
+                          int numRows, GramPlan& out);
+
 struct CholSchedDev;
 // Concatenates every table into one int32 blob; `dev` gets pointers into blob.data() (rebase them after uploading).
 void makeScheduleBlob(const CholSchedule& s, std::vector<int32_t>& blob, CholSchedDev& dev);

@@ -451,7 +451,11 @@ MB2_HD void jacobianCell(const FunctionTables& T, int ci, const float* js, const
   const CellDesc& c = T.cells[ci];
   const UnitDesc& u = T.units[c.unit];
   const float* rc = rec + u.recOff;
-  float* out = Jbase + (size_t)c.col * T.ldJ + u.row0;
+  // row k of the unit lands at out[MB2_ROW(k)]: contiguous in the K-major matrix; in the strip layout four rows of one quad are
+  // contiguous and consecutive quads are quadStride strips apart
+  float* out = T.stripMode ? Jbase + c.stripOff : Jbase + (size_t)c.col * T.ldJ + u.row0;
+  const int rowShift = T.stripMode ? (u.row0 & 3) : 0, quadFloats = T.stripMode ? int(c.quadStride) * 64 : 4;
+#define MB2_ROW(k) ((((k) + rowShift) >> 2) * quadFloats + (((k) + rowShift) & 3))
   const ContribDesc* cb = T.contribs + c.contribBegin;
   switch (u.kind) {
     case kUnitPosition:
@@ -460,7 +464,7 @@ MB2_HD void jacobianCell(const FunctionTables& T, int ci, const float* js, const
       const float ds = rc[3];
       F3 acc = f3(0.f, 0.f, 0.f);
       for (int k = 0; k < c.contribCount; ++k) acc = acc + (pointDerivative(T, js, cb[k].joint, cb[k].dof, v) * ds) * cb[k].coef;
-      out[0] = acc.x; out[1] = acc.y; out[2] = acc.z;
+      out[MB2_ROW(0)] = acc.x; out[MB2_ROW(1)] = acc.y; out[MB2_ROW(2)] = acc.z;
       break;
     }
     case kUnitOrientation:
@@ -478,7 +482,7 @@ MB2_HD void jacobianCell(const FunctionTables& T, int ci, const float* js, const
           acc[3 * jv] += (ds * d.x) * cb[k].coef; acc[3 * jv + 1] += (ds * d.y) * cb[k].coef; acc[3 * jv + 2] += (ds * d.z) * cb[k].coef;
         }
       }
-      for (int k = 0; k < 9; ++k) out[k] = acc[k];
+      for (int k = 0; k < 9; ++k) out[MB2_ROW(k)] = acc[k];
       break;
     }
     case kUnitStateMatrix:
@@ -512,13 +516,14 @@ MB2_HD void jacobianCell(const FunctionTables& T, int ci, const float* js, const
         }
       }
       const int nr = lm ? 6 : 12;
-      for (int k = 0; k < nr; ++k) out[k] = acc[k];
+      for (int k = 0; k < nr; ++k) out[MB2_ROW(k)] = acc[k];
       break;
     }
     default: // simple limits: value = wgtLoss * static coefficient
-      out[0] = rc[0] * c.coef;
+      out[MB2_ROW(0)] = rc[0] * c.coef;
       break;
   }
+#undef MB2_ROW
 }
 
 } // namespace mb2

@@ -100,8 +100,9 @@ __global__ void __launch_bounds__(512) sweepKernel(const SweepArgs a) {
     }
     const float* targets = a.targets + size_t(b) * T.targetStride;
     const float* cw = a.cweights + (T.weightsPerInstance ? size_t(b) * T.numWeights : 0);
-    float* J = kJacobian ? a.jacobian + size_t(b) * (T.numCols + 1) * T.ldJ : nullptr;
-    float* residual = kJacobian ? J + size_t(T.numCols) * T.ldJ : nullptr; // the residual is the last column of the device matrix
+    float* J = kJacobian ? a.jacobian + size_t(b) * T.jacobianStride : nullptr;
+    // the residual is the last column of the device matrix, or follows the strips
+    float* residual = kJacobian ? J + (T.stripMode ? size_t(T.residOff) : size_t(T.numCols) * T.ldJ) : nullptr;
     double err = 0.0;
     for (int u = lane; u < T.numUnits; u += 32) err += (double)evalUnit<kJacobian>(T, u, th, jp, js, targets, cw, rec, residual);
     __syncwarp();
@@ -389,6 +390,60 @@ cudaError_t launchCholesky(const CholArgs& a, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// K2s: tile-sparse Gram. A skeleton Jacobian is mostly structural zeros (a row only touches the parameters of one
+// root-to-constraint chain), so the stored 16x16 tiles of J^T J are accumulated from the non-zero 4-row x 16-column strips only
+// (GramPlan): ~20x fewer multiply-adds than the dense product, exact fp32. One CTA per instance: every strip arrives as one
+// TMA box of the K-major Jacobian, a warp owns a tile at a time, the output is already in the Cholesky kernel's tile layout.
+// ------------------------------------------------------------------------------------------------
+constexpr int kGramThreads = 256;
+
+size_t gramTilesSmemBytes(size_t stripStride) { return 128 + sizeof(float) * stripStride + 16; }
+
+__global__ void __launch_bounds__(kGramThreads) gramTilesKernel(const GramArgs a) {
+  extern __shared__ __align__(16) float gramSmem[];
+  const int b = blockIdx.x;
+  if (a.active != nullptr && a.active[b] == 0) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, hw = tid >> 4, hl = tid & 15;
+  float* strips = gramSmem + (((128u - (smemAddr(gramSmem) & 127u)) & 127u) >> 2);
+  float* resid = strips + a.residOff;
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(strips + a.stripStride);
+  const uint32_t barAddr = smemAddr(bar);
+  const uint32_t total = uint32_t(a.stripStride) * 4u;
+  if (tid == 0) {
+    mbarInit(barAddr, 1);
+    fenceBarrierInit();
+    mbarExpectTx(barAddr, total);
+    const char* src = reinterpret_cast<const char*>(a.strips + size_t(b) * a.stripStride);
+    for (uint32_t off = 0; off < total; off += 16384u) bulkLoad(smemAddr(strips) + off, src + off, total - off < 16384u ? total - off : 16384u, barAddr);
+  }
+  __syncthreads();
+  mbarWait(barAddr, 0);
+  float* out = a.out + size_t(b) * a.outStride;
+  for (int ti = warp; ti < a.numTiles; ti += kGramThreads / 32) {
+    const int t = __ldg(a.tileOrder + ti);
+    float acc[2][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    gramTileAccumulate(strips, a.pairA, a.pairB, __ldg(a.tilePairStart + t), __ldg(a.tilePairStart + t + 1), lane, acc);
+    gramTileStore(out + size_t(t) * 256, acc, __ldg(a.tileInfo + 3 * t + 2), a.regularization, lane);
+  }
+  float* y = out + size_t(a.numTiles) * 256;
+  for (int K = hw; K < a.numTileCols; K += kGramThreads / 16)
+    y[16 * K + hl] = gramVectorEntry(strips, resid, a.colStrip, a.stripCoord, __ldg(a.colStripStart + K), __ldg(a.colStripStart + K + 1), hl, 0xFFFFu << (16 * ((tid >> 4) & 1)));
+}
+
+cudaError_t launchGramTiles(const GramArgs& a, cudaStream_t stream) {
+  const size_t smem = gramTilesSmemBytes(a.stripStride);
+  if (smem > size_t(g_maxSmemOptin) || (a.stripStride & 3) != 0) return cudaErrorInvalidConfiguration;
+  cudaError_t e = cudaFuncSetAttribute(gramTilesKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (e != cudaSuccess) return e;
+  gramTilesKernel<<<a.batch, kGramThreads, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // K3 (scheduled): level-scheduled tile-sparse Cholesky of the permuted system (ik_chol_sched.h).
 // One CTA per instance; tiles, right-hand side and scratch live in shared memory (<= ~64 KB for the
 // humanoid rig => several CTAs per SM hide each other's latencies).
@@ -421,39 +476,58 @@ __global__ void __launch_bounds__(kSchedThreads, 3) choleskyScheduledKernel(cons
   // straight into the swizzled tile layout: SWIZZLE_64B is the XOR of tileIdx). No thread touches the data on the way in.
   const uint32_t barAddr = smemAddr(bar);
   const uint32_t blobBytes = uint32_t((Sg.blobInts + 3) & ~3) * 4u, gBytes = uint32_t(a.ldG) * 4u;
+  const bool fromGram = a.tilesIn != nullptr; // tiles (+ lambda, identity extension) and the slot-ordered J^T r come ready-made from the Gram kernel
+  const uint32_t tileBytes = uint32_t(Sg.numTiles) * 1024u, yBytes = uint32_t(Sg.nPad) * 4u;
   if (tid == 0) {
     flags[0] = 0;
     mbarInit(barAddr, 1);
     fenceBarrierInit();
-    mbarExpectTx(barAddr, blobBytes + gBytes + uint32_t(Sg.numTiles) * 1024u);
+    mbarExpectTx(barAddr, blobBytes + tileBytes + (fromGram ? yBytes : gBytes));
   }
   __syncthreads();
-  if (tid == 0) {
-    bulkLoad(smemAddr(blob), Sg.blob, blobBytes, barAddr);
-    bulkLoad(smemAddr(gsub), a.g + size_t(b) * a.ldG, gBytes, barAddr);
-  }
-  for (int t = tid; t < Sg.numTiles; t += kSchedThreads) { // one thread per tile: the table reads overlap, the compiler serialises the TMA issue per warp
-    const int gi0 = __ldg(Sg.tileInfo + 3 * t), gj0 = __ldg(Sg.tileInfo + 3 * t + 1);
-    tmaLoad3d(smemAddr(tiles + size_t(t) * 256), &hmap, gi0, gj0, b, barAddr);
+  if (fromGram) {
+    if (tid == 0) {
+      bulkLoad(smemAddr(blob), Sg.blob, blobBytes, barAddr);
+      const float* src = a.tilesIn + size_t(b) * a.tilesStride;
+      const uint32_t total = tileBytes + yBytes; // y follows the tiles in both layouts
+      for (uint32_t off = 0; off < total; off += 16384u)
+        bulkLoad(smemAddr(tiles) + off, reinterpret_cast<const char*>(src) + off, total - off < 16384u ? total - off : 16384u, barAddr);
+    }
+  } else {
+    if (tid == 0) {
+      bulkLoad(smemAddr(blob), Sg.blob, blobBytes, barAddr);
+      bulkLoad(smemAddr(gsub), a.g + size_t(b) * a.ldG, gBytes, barAddr);
+    }
+    for (int t = tid; t < Sg.numTiles; t += kSchedThreads) { // one thread per tile: the table reads overlap, the compiler serialises the TMA issue per warp
+      const int gi0 = __ldg(Sg.tileInfo + 3 * t), gj0 = __ldg(Sg.tileInfo + 3 * t + 1);
+      tmaLoad3d(smemAddr(tiles + size_t(t) * 256), &hmap, gi0, gj0, b, barAddr);
+    }
   }
   MB2_PROF(6)
   mbarWait(barAddr, 0);
   MB2_PROF(7)
   const CholSchedDev S = rebaseSchedule(Sg, blob);
-  // padding pass (cholPadGroup): one work item = (tile, storage row, float4 group)
-  if (!(a.profile & 0x800))
+  if (fromGram) {
+    for (int s = tid; s < S.nPad; s += kSchedThreads) {
+      const int p = S.perm[s];
+      if (p >= 0) gsub[p] = y[s];
+    }
+  } else {
+    // padding pass (cholPadGroup): one work item = (tile, storage row, float4 group)
     for (int idx = tid; idx < S.numTiles * 64; idx += kSchedThreads) {
       const int t = idx >> 6, e = idx & 63;
       cholPadGroup(tiles + size_t(t) * 256, S.tileInfo[3 * t + 2], e >> 2, e & 3);
     }
-  for (int s = tid; s < S.nPad; s += kSchedThreads) {
-    const int p = S.perm[s];
-    y[s] = p >= 0 ? gsub[p] : 0.f;
+    for (int s = tid; s < S.nPad; s += kSchedThreads) {
+      const int p = S.perm[s];
+      y[s] = p >= 0 ? gsub[p] : 0.f;
+    }
   }
   __syncthreads();
   MB2_PROF(8)
-  for (int s = tid; s < S.nPad; s += kSchedThreads)
-    if (S.perm[s] >= 0) tiles[size_t(S.diagTile[s >> 4]) * 256 + tileIdx(s & 15, s & 15)] += a.regularization; // gauss_newton_solver.cpp:248
+  if (!fromGram)
+    for (int s = tid; s < S.nPad; s += kSchedThreads)
+      if (S.perm[s] >= 0) tiles[size_t(S.diagTile[s >> 4]) * 256 + tileIdx(s & 15, s & 15)] += a.regularization; // gauss_newton_solver.cpp:248
   __syncthreads();
   MB2_PROF(0)
 
@@ -497,12 +571,14 @@ cudaError_t launchCholeskyScheduled(const CholArgs& a, const CholSchedDev& sched
   if (smem > size_t(g_maxSmemOptin)) return cudaErrorInvalidConfiguration;
   cudaError_t e = cudaFuncSetAttribute(choleskyScheduledKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
-  if (a.g == nullptr || a.ldG != cholGradientLd(a.ns) || (a.ldH & 3) != 0 || (a.hStride & 3) != 0) return cudaErrorInvalidValue;
-  CUtensorMap hmap; // H as [batch][ns + 1][ldH]; one 16 x 16 box per stored tile
-  const uint64_t dims[3] = {uint64_t(a.ldH), uint64_t(a.ns + 1), uint64_t(a.batch)};
-  const uint64_t strides[2] = {uint64_t(a.ldH) * sizeof(float), uint64_t(a.hStride) * sizeof(float)};
+  if (a.tilesIn == nullptr && (a.g == nullptr || a.ldG != cholGradientLd(a.ns))) return cudaErrorInvalidValue;
+  if ((a.ldH & 3) != 0 || (a.hStride & 3) != 0 || (a.tilesStride & 3) != 0) return cudaErrorInvalidValue;
+  CUtensorMap hmap; // H as [batch][ns + 1][ldH]; one 16 x 16 box per stored tile (unused, but still a valid map, when the tiles come from the Gram kernel)
+  const bool fromGram = a.tilesIn != nullptr;
+  const uint64_t dims[3] = {uint64_t(fromGram ? 256 : a.ldH), uint64_t(fromGram ? sched.numTiles : a.ns + 1), uint64_t(a.batch)};
+  const uint64_t strides[2] = {uint64_t(fromGram ? 256 : a.ldH) * sizeof(float), uint64_t(fromGram ? a.tilesStride : a.hStride) * sizeof(float)};
   const uint32_t box[3] = {16u, 16u, 1u};
-  e = makeTensorMap3d(&hmap, a.H, dims, strides, box, 64);
+  e = makeTensorMap3d(&hmap, fromGram ? a.tilesIn : a.H, dims, strides, box, 64);
   if (e != cudaSuccess) return e;
   choleskyScheduledKernel<<<a.batch, kSchedThreads, smem, stream>>>(hmap, a, sched);
   return cudaGetLastError();

@@ -60,8 +60,32 @@ struct CholArgs {            // K3: damped Cholesky + solve + update + SolverT b
   float* gradDotDelta;       // optional [B]: Jtr . delta (SubsetGaussNewtonSolverT line search)
   const float* g;            // scheduled kernel: [B][ldG] J^T r as a contiguous vector (ldG = ns rounded up to 4)
   int32_t ldG;
+  const float* tilesIn;      // scheduled kernel, optional: [B][tilesStride] tiles + slot-ordered J^T r from the Gram kernel (H, g unused)
+  size_t tilesStride;
   int32_t profile;           // MB2_CHOL_PROFILE=1: block 0 prints per-phase cycles (debug aid)
 };
+
+struct GramArgs {            // K2s: stored tiles of J^T J + lambda I and J^T r from the non-zero strips of the Jacobian (GramPlan)
+  int32_t batch;
+  const float* strips;       // [B][stripStride]: the Jacobian in strip layout + residual (FunctionTables::stripMode), written by the sweep kernel
+  size_t stripStride;        // GramPlan::stride
+  int32_t residOff;          // GramPlan::residOff
+  const int32_t* active;
+  int32_t numStrips, numTiles, numTileCols, nPad;
+  const int32_t* stripCoord; // device copies of the GramPlan tables
+  const int32_t* tileOrder;
+  const int32_t* tilePairStart;
+  const int32_t* pairA;
+  const int32_t* pairB;
+  const int32_t* colStripStart;
+  const int32_t* colStrip;
+  const int32_t* tileInfo;   // the schedule's [numTiles][3]
+  float regularization;
+  float* out;                // [B][outStride]: numTiles x 256 floats in tile storage order, then the slot-ordered J^T r [nPad]
+  size_t outStride;
+};
+cudaError_t launchGramTiles(const GramArgs& a, cudaStream_t stream);
+size_t gramTilesSmemBytes(size_t stripStride);
 
 cudaError_t launchSweep(const SweepArgs& a, bool jacobian, cudaStream_t stream);
 size_t sweepSmemPerInstance(const FunctionTables& T);

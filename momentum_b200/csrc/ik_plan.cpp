@@ -108,7 +108,7 @@ struct CellBuilder {
 } // namespace
 
 std::string buildPlan(const HostCharacter& ch, const std::vector<HostErrorFunction>& efs, const std::vector<uint8_t>& enabled, bool compact, Plan& out,
-                      const std::vector<int32_t>* columnOrder) {
+                      const std::vector<int32_t>* columnOrder, bool alignRowGroups) {
   out = Plan();
   out.compact = compact;
   const int n = ch.numParams;
@@ -175,6 +175,7 @@ std::string buildPlan(const HostCharacter& ch, const std::vector<HostErrorFuncti
         u.kind = isPos ? kUnitPosition : (ef.kind == 1 ? kUnitOrientation : kUnitOrientationRotDiff);
         u.ef = int32_t(e);
         u.joint = ef.parents[c];
+        if (alignRowGroups) row = (row + 3) & ~3;
         u.row0 = row;
         u.numRows = isPos ? 3 : 9;
         u.targetOff = ef.targetOff + per * c;
@@ -206,6 +207,7 @@ std::string buildPlan(const HostCharacter& ch, const std::vector<HostErrorFuncti
         u.kind = lm ? kUnitStateLogMap : kUnitStateMatrix;
         u.ef = int32_t(e);
         u.joint = i;
+        if (alignRowGroups) row = (row + 3) & ~3;
         u.row0 = row;
         u.numRows = lm ? 6 : 12;
         u.targetOff = ef.targetOff + 8 * i;
@@ -316,6 +318,7 @@ std::string buildPlan(const HostCharacter& ch, const std::vector<HostErrorFuncti
           case 5: { // Ellipsoid :701-785
             u.kind = kUnitLimitEllipsoid;
             u.numRows = 3;
+            if (alignRowGroups) { row = (row + 3) & ~3; u.row0 = row; }
             u.i[0] = l.i[0]; // ellipsoidParent
             u.joint = l.i[1]; // parent
             if (l.i[0] < 0 || l.i[0] >= ch.numJoints || l.i[1] < 0 || l.i[1] >= ch.numJoints) return "Ellipsoid limit joint index out of range";

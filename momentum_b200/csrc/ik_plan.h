@@ -72,10 +72,12 @@ struct Plan {
 // compact = true drops the columns of disabled parameters and packs the enabled ones in order (what the solver
 // needs: gauss_newton_solver.cpp:204-209 discards the others anyway); compact = false keeps the reference's
 // full column positions (getJacobian / getJtJR parity).
+// alignRowGroups: every multi-row unit starts on a row that is a multiple of 4 (the rows in between stay zero), so that four
+// consecutive rows of a column are one aligned 16-byte piece of the K-major device Jacobian (tile-sparse Gram kernel).
 // columnOrder (optional, compact only): model parameters in the order the device columns should take (a permutation
 // of the enabled parameters, e.g. the Cholesky elimination order); default = ascending enabled parameters.
 std::string buildPlan(const HostCharacter& ch, const std::vector<HostErrorFunction>& efs, const std::vector<uint8_t>& enabled, bool compact, Plan& out,
-                      const std::vector<int32_t>* columnOrder = nullptr);
+                      const std::vector<int32_t>* columnOrder = nullptr, bool alignRowGroups = false);
 
 // getJacobianSize() of a block (joint_error_function-inl.h:300-302, state_error_function.cpp:394-404,
 // limit_error_function.cpp:1138-1161)

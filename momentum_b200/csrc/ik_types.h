@@ -71,8 +71,9 @@ struct CellDesc {
   uint16_t col;           // device column of J (model parameter index, or its rank in the enabled list when compacted)
   uint32_t contribBegin;  // into ContribDesc table
   uint16_t contribCount;  // 0 for limit cells that only scale by coef
-  uint16_t pad;
+  uint16_t quadStride;    // strip layout: strips between consecutive row quads of this cell's unit (same tile column)
   float coef;             // static coefficient for limit cells
+  uint32_t stripOff;      // strip layout: float offset of (first row quad, this column) in the instance's strip buffer
 };
 
 // One chain-rule contribution: joint-parameter (joint, dof) with ParameterTransform coefficient
@@ -113,6 +114,10 @@ struct FunctionTables {
   int32_t numWeights;
   // table sizes (the sweep kernel stages every table in shared memory when they fit)
   int32_t ptNnz, numContribs, numLimitData;
+  // Jacobian output layout. 0: K-major matrix [numCols + 1][ldJ] (column numCols = residual). 1: strips (GramPlan in
+  // ik_chol_sched.h): [numStrips][16 columns][4 rows] then the residual at residOff, rows numbered with 4-aligned row groups.
+  int32_t stripMode, residOff;
+  size_t jacobianStride;     // floats per instance in the Jacobian buffer
 };
 
 } // namespace mb2

@@ -24,7 +24,7 @@ DEFAULT_LIB = os.path.join(_HERE, "lib", "libmomentum_b200.so")
 
 SIZE_MAX = 2 ** 64 - 1
 
-JTJ_AUTO, JTJ_FP32_SIMT, JTJ_TF32X3, JTJ_TF32 = 0, 1, 2, 3
+JTJ_AUTO, JTJ_FP32_SIMT, JTJ_TF32X3, JTJ_TF32, JTJ_SPARSE_TILES = 0, 1, 2, 3, 4
 INSTANCE_OK, INSTANCE_CHOLESKY_BREAKDOWN, INSTANCE_NON_FINITE = 0, 1, 2
 CHOLESKY_AUTO, CHOLESKY_DENSE_EIGEN, CHOLESKY_TILES_DENSE, CHOLESKY_TILES_SPARSE = 0, 1, 2, 3
 

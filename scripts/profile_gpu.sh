@@ -7,7 +7,7 @@ OUT=gpurun_out
 mkdir -p $OUT
 BENCH="python bench.py --steps 1 --warmup 1 --no-cpu-baseline"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv $BENCH > $OUT/${TAG}_launches.log 2>&1
-for spec in "k1:sweepKernel" "k2:jtjTensorKernel" "k3:choleskyScheduledKernel"; do
+for spec in "k1:sweepKernel" "k2:gramTilesKernel" "k3:choleskyScheduledKernel"; do
   name=${spec%%:*}; regex=${spec##*:}
   ncu --set full --clock-control none --import-source on -k regex:$regex --launch-skip 12 -c 1 -f -o $OUT/${TAG}_${name} $BENCH > $OUT/${TAG}_${name}.log 2>&1
 done

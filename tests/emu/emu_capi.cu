@@ -38,6 +38,8 @@ struct mb2_solver_function {
   int ldJ{32};
   std::vector<float> J;
   bool planCompact{false};
+  bool stripMode{false};   // Jacobian buffer in strip layout (GramPlan) instead of the K-major matrix
+  int residOff{0}, stripStride{0};
   std::vector<double> errors;
 };
 struct mb2_solver {
@@ -54,6 +56,7 @@ static std::string plan(mb2_solver_function* f, bool compact) {
   std::string e = buildPlan(f->ch->host, f->efs, f->enabled, compact, f->plan);
   if (!e.empty()) return e;
   f->planCompact = compact;
+  f->stripMode = false;
   f->ldJ = std::max(32, roundUp(f->plan.numRows, 32));
   f->J.assign(size_t(f->B) * (f->plan.numCols + 1) * f->ldJ, 0.f);
   f->errors.assign(f->B, 0.0);
@@ -74,6 +77,8 @@ static FunctionTables tables(const mb2_solver_function* f) {
   T.limitData = f->plan.limitData.data();
   T.targetStride = f->targetStride; T.recStride = f->plan.recStride; T.numRows = f->plan.numRows; T.ldJ = f->ldJ; T.numCols = f->plan.numCols;
   T.weightsPerInstance = f->weightsPerInstance; T.numWeights = f->numWeights;
+  T.stripMode = f->stripMode ? 1 : 0; T.residOff = f->residOff;
+  T.jacobianStride = f->stripMode ? size_t(f->stripStride) : size_t(f->plan.numCols + 1) * f->ldJ;
   return T;
 }
 
@@ -88,8 +93,8 @@ static void sweepOne(mb2_solver_function* f, const FunctionTables& T, int b, con
     for (int i = 0; i < T.numJoints * 8; ++i) stateOut[i] = js[(i >> 3) * kJointStateStride + (i & 7)];
   const float* tg = f->targets.data() + size_t(b) * T.targetStride;
   const float* cw = f->weights.data() + (T.weightsPerInstance ? size_t(b) * T.numWeights : 0);
-  float* Jb = f->J.data() + size_t(b) * (T.numCols + 1) * T.ldJ;
-  float* res = kJacobian ? Jb + size_t(T.numCols) * T.ldJ : nullptr;
+  float* Jb = f->J.data() + size_t(b) * T.jacobianStride;
+  float* res = kJacobian ? Jb + (T.stripMode ? size_t(T.residOff) : size_t(T.numCols) * T.ldJ) : nullptr;
   // lanes accumulate in double, then a butterfly reduction: emulate the same association
   double lane[32];
   for (int l = 0; l < 32; ++l) lane[l] = 0.0;
@@ -166,14 +171,40 @@ static int cholDispatch(float* Hg, int n, int ldH, float reg, float* delta, floa
   return cholOne<32>(Hg, n, ldH, reg, delta, gdd);
 }
 
+// emulation of gramTilesKernel for one instance: strips = TMA boxes of the K-major Jacobian, warps / half-warps in sequence
+static void gramOne(const mb2_solver_function* f, int b, const GramPlan& G, const CholSchedDev& S, float reg, float* out) {
+  std::vector<float> store(size_t(G.stride) + 8, 0.f);
+  float* strips = store.data();
+  while ((reinterpret_cast<uintptr_t>(strips) & 15) != 0) ++strips;
+  std::copy(f->J.data() + size_t(b) * G.stride, f->J.data() + size_t(b + 1) * G.stride, strips); // the bulk copy
+  float* resid = strips + G.residOff;
+  std::vector<float> tileBuf(256 + 8);
+  for (int ti = 0; ti < G.numTiles; ++ti) {
+    const int t = G.tileOrder[ti];
+    float* tile = out + size_t(t) * 256;
+    for (int lane = 0; lane < 32; ++lane) {
+      float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      gramTileAccumulate(strips, G.pairA.data(), G.pairB.data(), G.tilePairStart[t], G.tilePairStart[t + 1], lane, acc);
+      gramTileStore(tile, acc, S.tileInfo[3 * t + 2], reg, lane);
+    }
+  }
+  float* y = out + size_t(G.numTiles) * 256;
+  for (int K = 0; K < G.numTileCols; ++K)
+    for (int hl = 0; hl < 16; ++hl) y[16 * K + hl] = gramVectorEntry(strips, resid, G.colStrip.data(), G.stripCoord.data(), G.colStripStart[K], G.colStripStart[K + 1], hl, 0xFFFFu);
+}
+
 // emulation of choleskyScheduledKernel for one instance: phases in the same order, half-warps/warps in sequence
-static int cholScheduledOne(const CholSchedDev& S, const float* Hs, int ldH, int n, float reg, float* delta, float* gdd) {
+static int cholScheduledOne(const CholSchedDev& S, const float* Hs, int ldH, int n, float reg, float* delta, float* gdd, const float* gramOut = nullptr) {
   std::vector<float> store(size_t(S.numTiles) * 256 + S.nPad + 16, 0.f);
   float* tl = store.data();
   while ((reinterpret_cast<uintptr_t>(tl) & 15) != 0) ++tl; // float4 alignment
   float* y = tl + size_t(S.numTiles) * 256;
   std::vector<float> gsub(n, 0.f);
   std::fill(delta, delta + n, 0.f); // alignment columns keep a zero step
+  if (gramOut != nullptr) { // tiles (+ lambda, identity extension) and the slot-ordered J^T r straight from the Gram kernel
+    std::copy(gramOut, gramOut + size_t(S.numTiles) * 256 + S.nPad, tl);
+    for (int s2 = 0; s2 < S.nPad; ++s2) { const int p = S.perm[s2]; if (p >= 0) gsub[p] = y[s2]; }
+  } else {
   for (int t = 0; t < S.numTiles; ++t) { // the TMA box: 16 rows x 16 columns of H starting at (gj0, gi0), zero outside [ns+1] x [ldH]
     const int gi0 = S.tileInfo[3 * t], gj0 = S.tileInfo[3 * t + 1];
     for (int c = 0; c < 16; ++c)
@@ -186,6 +217,7 @@ static int cholScheduledOne(const CholSchedDev& S, const float* Hs, int ldH, int
     const float g = p >= 0 ? Hs[size_t(p) * ldH + n] : 0.f;
     y[s2] = g;
     if (p >= 0) { gsub[p] = g; tl[size_t(S.diagTile[s2 >> 4]) * 256 + tileIdx(s2 & 15, s2 & 15)] += reg; }
+  }
   }
   int flag = 0;
   for (int L = 0; L < S.numLevels; ++L) {
@@ -426,6 +458,8 @@ int mb2_solver_solve(mb2_solver* s, float* params, double* errors, int32_t* iter
   std::string e = plan(f, true);
   if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
   CholSchedule sched;
+  GramPlan gram;
+  const bool useGram = cholMode >= 2 && (o.jtj_mode == MB2_JTJ_AUTO || o.jtj_mode == MB2_JTJ_SPARSE_TILES);
   if (cholMode >= 2) { // same two-pass planning as ensurePlan(mode 2) in ik_capi.cu
     const int ns0 = f->plan.numCols;
     std::vector<std::vector<int>> cliques(f->plan.units.size());
@@ -435,9 +469,18 @@ int mb2_solver_solve(mb2_solver* s, float* params, double* errors, int32_t* iter
     std::vector<int32_t> colOrder;
     layoutDeviceColumns(sched, colOrder);
     for (int32_t& c : colOrder) if (c >= 0) c = f->plan.enabledList[c];
-    e = buildPlan(f->ch->host, f->efs, f->enabled, true, f->plan, &colOrder);
+    e = buildPlan(f->ch->host, f->efs, f->enabled, true, f->plan, &colOrder, useGram);
     if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
-    f->J.assign(size_t(f->B) * (f->plan.numCols + 1) * f->ldJ, 0.f);
+    if (useGram) {
+      std::vector<int32_t> cr0, crn, cc;
+      for (const CellDesc& c : f->plan.cells) { cr0.push_back(f->plan.units[c.unit].row0); crn.push_back(f->plan.units[c.unit].numRows); cc.push_back(int32_t(c.col)); }
+      e = buildGramPlan(sched, cr0, crn, cc, f->plan.numRows, gram);
+      if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
+      for (size_t i = 0; i < f->plan.cells.size(); ++i) { f->plan.cells[i].stripOff = gram.cellStripOff[i]; f->plan.cells[i].quadStride = gram.cellQuadStride[i]; }
+    }
+    f->stripMode = useGram; f->residOff = gram.residOff; f->stripStride = gram.stride;
+    f->ldJ = std::max(32, roundUp(f->plan.numRows, 32));
+    f->J.assign(useGram ? size_t(f->B) * gram.stride : size_t(f->B) * (f->plan.numCols + 1) * f->ldJ, 0.f);
   }
   std::vector<int32_t> blob;
   CholSchedDev S{};
@@ -447,7 +490,7 @@ int mb2_solver_solve(mb2_solver* s, float* params, double* errors, int32_t* iter
   const int maxIt = int(o.max_iterations), minIt = int(o.min_iterations);
   s->errors.assign(f->B, DBL_MAX); s->iterations.assign(f->B, 0); s->status.assign(f->B, 0);
   s->history.assign(size_t(f->B) * std::max(maxIt, 1), 0.0);
-  std::vector<float> H(size_t(ns + 1) * ldH, 0.f), delta(ns), orig(n);
+  std::vector<float> H(size_t(ns + 1) * ldH, 0.f), delta(ns), orig(n), gramOut(useGram ? size_t(sched.numTiles) * 256 + sched.nPad : 1, 0.f);
   s->totalIterations = 0;
   for (int b = 0; b < f->B; ++b) {
     float* theta = params + size_t(b) * n;
@@ -459,7 +502,10 @@ int mb2_solver_solve(mb2_solver* s, float* params, double* errors, int32_t* iter
       int failed;
       std::fill(H.begin(), H.end(), std::nanf("")); // entries the device never writes (lower triangle) are garbage there: poison them here
       jtjOne(f, b, ns, H.data(), ldH);
-      if (cholMode >= 2) {
+      if (cholMode >= 2 && useGram) {
+        gramOne(f, b, gram, S, o.regularization, gramOut.data());
+        failed = cholScheduledOne(S, nullptr, ldH, ns, o.regularization, delta.data(), &gdd, gramOut.data());
+      } else if (cholMode >= 2) {
         failed = cholScheduledOne(S, H.data(), ldH, ns, o.regularization, delta.data(), &gdd);
       } else {
         failed = cholDispatch(H.data(), ns, ldH, o.regularization, delta.data(), &gdd);
@@ -567,5 +613,33 @@ extern "C" int emu_chol_chunk_stats(int n, int numCliques, const int* cliqueStar
   for (int a = 0; a < nb; ++a) for (int b2 = a; b2 < nb; ++b2) { ++total; needed += need[a * nb + b2] || b2 == (nd - 1) / 32; }
   std::printf("device columns %d (+1), 32x32 chunks in the upper triangle %d, needed %d\n", s.n, total, needed);
   for (int a = 0; a < nb; ++a) { for (int b2 = 0; b2 < nb; ++b2) std::printf("%c", b2 < a ? ' ' : (need[a * nb + b2] ? '#' : (b2 == (nd - 1) / 32 ? 'g' : '.'))); std::printf("\n"); }
+  return MB2_OK;
+}
+
+extern "C" int emu_gram_stats(mb2_solver_function* f) {
+  std::string e = plan(f, true);
+  if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
+  CholSchedule sched;
+  std::vector<std::vector<int>> cliques(f->plan.units.size());
+  for (const CellDesc& c : f->plan.cells) cliques[c.unit].push_back(int(c.col));
+  e = buildCholSchedule(f->plan.numCols, cliques, false, sched);
+  if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
+  std::vector<int32_t> colOrder;
+  layoutDeviceColumns(sched, colOrder);
+  for (int32_t& c : colOrder) if (c >= 0) c = f->plan.enabledList[c];
+  e = buildPlan(f->ch->host, f->efs, f->enabled, true, f->plan, &colOrder, true);
+  if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
+  std::vector<int32_t> cr0, crn, cc;
+  for (const CellDesc& c : f->plan.cells) { cr0.push_back(f->plan.units[c.unit].row0); crn.push_back(f->plan.units[c.unit].numRows); cc.push_back(int32_t(c.col)); }
+  GramPlan g;
+  e = buildGramPlan(sched, cr0, crn, cc, f->plan.numRows, g);
+  if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
+  int maxPairs = 0;
+  for (int t = 0; t < g.numTiles; ++t) maxPairs = std::max(maxPairs, g.tilePairStart[t + 1] - g.tilePairStart[t]);
+  std::printf("rows %d (aligned), device columns %d, strips %d (%d KB), tiles %d, pairs %zu (max per tile %d), MACs %lld\n", f->plan.numRows, f->plan.numCols, g.numStrips,
+              g.numStrips / 4, g.numTiles, g.pairA.size(), maxPairs, (long long)g.macs);
+  std::printf("pairs per tile in order:");
+  for (int ti = 0; ti < g.numTiles; ++ti) { const int t = g.tileOrder[ti]; std::printf(" %d", g.tilePairStart[t + 1] - g.tilePairStart[t]); }
+  std::printf("\n");
   return MB2_OK;
 }
