@@ -85,7 +85,8 @@ struct DeviceSchedule {
   DeviceBuffer<int32_t> blob;
   GramPlan gram;          // tile-sparse Gram tables of the same plan (rows aligned to quads)
   bool gramValid{false};
-  DeviceBuffer<int32_t> gStripCoord, gTileOrder, gTilePairStart, gPairA, gPairB, gColStripStart, gColStrip;
+  DeviceBuffer<int32_t> gBlob;
+  int32_t gBlobInts{0}, gOffsets[8]{};
 };
 
 struct mb2_solver_function {
@@ -276,13 +277,10 @@ int ensurePlan(mb2_solver_function* f, int mode, bool schedDense = false, bool a
       err = buildGramPlan(ds->host, cr0, crn, cc, f->plan.numRows, ds->gram);
       if (!err.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, err);
       for (size_t i = 0; i < f->plan.cells.size(); ++i) { f->plan.cells[i].stripOff = ds->gram.cellStripOff[i]; f->plan.cells[i].quadStride = ds->gram.cellQuadStride[i]; }
-      MB2_CUDA(ds->gStripCoord.upload(ds->gram.stripCoord, s));
-      MB2_CUDA(ds->gTileOrder.upload(ds->gram.tileOrder, s));
-      MB2_CUDA(ds->gTilePairStart.upload(ds->gram.tilePairStart, s));
-      MB2_CUDA(ds->gPairA.upload(ds->gram.pairA, s));
-      MB2_CUDA(ds->gPairB.upload(ds->gram.pairB, s));
-      MB2_CUDA(ds->gColStripStart.upload(ds->gram.colStripStart, s));
-      MB2_CUDA(ds->gColStrip.upload(ds->gram.colStrip, s));
+      std::vector<int32_t> gblob;
+      makeGramBlob(ds->gram, ds->host, gblob, ds->gOffsets);
+      ds->gBlobInts = int32_t(gblob.size());
+      MB2_CUDA(ds->gBlob.upload(gblob, s));
       ds->gramValid = true;
     }
     ds->dense = schedDense;
@@ -816,7 +814,7 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
   const int maxIt = int(std::min<uint64_t>(o.max_iterations, 1u << 30));
   const int minIt = int(std::min<uint64_t>(o.min_iterations, 1u << 30));
   MB2_CHECK(ns > 0, "no enabled parameters");
-  if (useGram && gramTilesSmemBytes(size_t(f->sched->gram.stride)) > size_t(200 * 1024)) {
+  if (useGram && gramTilesSmemBytes(size_t(f->sched->gram.stride), f->sched->gBlobInts) > size_t(200 * 1024)) {
     if (o.jtj_mode == MB2_JTJ_SPARSE_TILES) return fail(MB2_ERR_UNSUPPORTED, "Jacobian strips do not fit in shared memory for this system");
     useGram = false;
     rc = ensurePlan(f, 2, cholMode == 2, false);
@@ -880,14 +878,10 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
       g.numTiles = ds.host.numTiles;
       g.numTileCols = ds.host.numTileCols;
       g.nPad = ds.host.nPad;
-      g.stripCoord = ds.gStripCoord.p;
-      g.tileOrder = ds.gTileOrder.p;
-      g.tilePairStart = ds.gTilePairStart.p;
-      g.pairA = ds.gPairA.p;
-      g.pairB = ds.gPairB.p;
-      g.colStripStart = ds.gColStripStart.p;
-      g.colStrip = ds.gColStrip.p;
-      g.tileInfo = ds.dev.tileInfo;
+      g.blob = ds.gBlob.p;
+      g.blobInts = ds.gBlobInts;
+      g.offTileOrder = ds.gOffsets[0]; g.offTilePairStart = ds.gOffsets[1]; g.offPairA = ds.gOffsets[2]; g.offPairB = ds.gOffsets[3];
+      g.offColStripStart = ds.gOffsets[4]; g.offColStrip = ds.gOffsets[5]; g.offStripRow = ds.gOffsets[6]; g.offTileInfo = ds.gOffsets[7];
       g.regularization = o.regularization;
       g.out = s->dTiles.p;
       g.outStride = tilesStride;

@@ -278,11 +278,15 @@ std::string buildGramPlan(const CholSchedule& s, const std::vector<int32_t>& cel
         pairs[t].push_back({stripId[{q, I}], stripId[{q, J}]});
       }
   }
+  out.residOff = out.numStrips * 64;
+  out.stride = (out.residOff + ((numRows + 3) & ~3) + 63) / 64 * 64; // whole strips, so that "strip stride / 64" is the all-zero strip the kernel appends
+  const int zeroStrip = out.stride / 64;
   out.tilePairStart.assign(s.numTiles + 1, 0);
   for (int t = 0; t < s.numTiles; ++t) {
+    out.macs += int64_t(pairs[t].size()) * 16 * 16 * 4;
+    if (pairs[t].size() % 2) pairs[t].push_back({zeroStrip, zeroStrip}); // the kernel consumes two pairs per step
     out.tilePairStart[t + 1] = out.tilePairStart[t] + int(pairs[t].size());
     for (const auto& pr : pairs[t]) { out.pairA.push_back(pr.first); out.pairB.push_back(pr.second); }
-    out.macs += int64_t(pairs[t].size()) * 16 * 16 * 4;
   }
   out.tileOrder.resize(s.numTiles);
   for (int t = 0; t < s.numTiles; ++t) out.tileOrder[t] = t;
@@ -300,14 +304,25 @@ std::string buildGramPlan(const CholSchedule& s, const std::vector<int32_t>& cel
     for (int q = q0 + 1; q <= (cellRow0[i] + cellRows[i] - 1) >> 2; ++q)
       if (stripsOfQuad[q] != stripsOfQuad[q0] || stripId[{q, K}] != stripId[{q0, K}] + (q - q0) * stripsOfQuad[q0]) return "Gram plan: row quads of one unit are not laid out uniformly";
   }
-  out.residOff = out.numStrips * 64;
-  out.stride = out.residOff + ((numRows + 3) & ~3);
   out.colStripStart.assign(T + 1, 0);
   for (int K = 0; K < T; ++K) {
     out.colStripStart[K + 1] = out.colStripStart[K] + int(ofCol[K].size());
     out.colStrip.insert(out.colStrip.end(), ofCol[K].begin(), ofCol[K].end());
   }
   return "";
+}
+
+void makeGramBlob(const GramPlan& g, const CholSchedule& s, std::vector<int32_t>& blob, int32_t offsets[8]) {
+  blob.clear();
+  int k = 0;
+  auto add = [&](const std::vector<int32_t>& v) { offsets[k++] = int32_t(blob.size()); blob.insert(blob.end(), v.begin(), v.end()); while (blob.size() % 4) blob.push_back(0); };
+  add(g.tileOrder); add(g.tilePairStart); add(g.pairA); add(g.pairB); add(g.colStripStart); add(g.colStrip);
+  std::vector<int32_t> stripRow(g.numStrips), info(s.numTiles);
+  for (int i = 0; i < g.numStrips; ++i) stripRow[i] = g.stripCoord[2 * i];
+  auto validOf = [&](int K) { int v = 0; while (v < kCholTile && s.perm[16 * K + v] >= 0) ++v; return v; };
+  for (int t = 0; t < s.numTiles; ++t) info[t] = validOf(s.tileRow[t]) | (validOf(s.tileCol[t]) << 8) | ((s.tileRow[t] == s.tileCol[t] ? 1 : 0) << 16);
+  add(stripRow); add(info);
+  if (blob.empty()) blob.push_back(0);
 }
 
 void layoutDeviceColumns(CholSchedule& s, std::vector<int32_t>& deviceColumnOrder) {

@@ -87,75 +87,86 @@ MB2_HD void cholPadGroup(float* tile, int info, int c, int g) {
 }
 
 // ---- tile-sparse Gram (see GramPlan in ik_chol_sched.h): a warp owns one tile and accumulates it on the tensor cores ----
-// strips: [strip][16 columns][4 rows] floats, so S[c][k] of a strip is float 4 c + k. One pair is the 16 x 16 x 4 product
-// out(r, c) += sum_k A[r][k] B[c][k] = two mma.sync.m16n8k4 (column halves) per term of the 3xTF32 split
-// (hi*hi + hi*lo + lo*hi, fp32 accumulate: fp32-class accuracy). Every fragment is one conflict-free 128-byte warp read:
+// strips: [strip][16 columns][4 rows] floats, so S[c][k] of a strip is float 4 c + k. Two pairs at a time form the
+// 16 x 16 x 8 product out(r, c) += sum_k A[r][k] B[c][k] (k 0..3 from the first pair, 4..7 from the second; lists are padded
+// to even length with an all-zero strip) = two mma.sync.m16n8k8 (column halves) per term of the three-term TF32 split
+// hi*hi + hi*lo + lo*hi with fp32 accumulation (fp32-class accuracy). hi = nearest tf32 of x, lo = x - hi (exact; the tensor
+// core reads its leading 10 mantissa bits: a 2^-22 relative perturbation). Every fragment is one conflict-free 128-byte warp read:
 //   a0 = A[g][t], a1 = A[g + 8][t], b(h) = B[8 h + g][t]   with g = lane >> 2, t = lane & 3  ->  float index lane (+ 32).
 // Accumulators d[h][0..3] follow the mma C layout: (row g, cols 8h + 2t, 8h + 2t + 1), (row g + 8, same cols).
-MB2_HD float tf32Round(float x) { // cvt.rna.tf32.f32: round to nearest (ties away) on 10 mantissa bits
+MB2_HD float tf32High(float x) { // nearest tf32 (ties away from zero), 10 mantissa bits: what cvt.rna.tf32.f32 returns for finite x, but on
+                                  // the integer ALU (the conversion instruction runs on the quarter-rate XU pipe)
 #if defined(__CUDA_ARCH__)
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 #else
   uint32_t u;
   std::memcpy(&u, &x, 4);
-  u = (u + 0x1000u) & ~0x1FFFu;
+  u = (u + 0x1000u) & 0xFFFFE000u;
   float r;
   std::memcpy(&r, &u, 4);
   return r;
 #endif
 }
 #if defined(__CUDA_ARCH__)
-__device__ __forceinline__ void mmaTf32K4(float d[4], float a0, float a1, float b0) {
-  asm volatile("mma.sync.aligned.m16n8k4.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%0, %1, %2, %3};"
+__device__ __forceinline__ void mmaTf32K8(float d[4], float a0, float a1, float a2, float a3, float b0, float b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(__float_as_uint(a0)), "r"(__float_as_uint(a1)), "r"(__float_as_uint(b0)));
+               : "r"(__float_as_uint(a0)), "r"(__float_as_uint(a1)), "r"(__float_as_uint(a2)), "r"(__float_as_uint(a3)), "r"(__float_as_uint(b0)),
+                 "r"(__float_as_uint(b1)));
 }
 #endif
-MB2_HD void gramTilePair(const float* strips, int sa, int sb, int lane, float d[2][4]) {
-  const float* A = strips + size_t(sa) * 64;
-  const float* B = strips + size_t(sb) * 64;
+MB2_HD void gramTilePairs(const float* strips, int sa0, int sb0, int sa1, int sb1, int lane, float d[2][4]) {
+  const float* A0 = strips + size_t(sa0) * 64;
+  const float* B0 = strips + size_t(sb0) * 64;
+  const float* A1 = strips + size_t(sa1) * 64;
+  const float* B1 = strips + size_t(sb1) * 64;
 #if defined(__CUDA_ARCH__)
-  const float a0 = A[lane], a1 = A[32 + lane], b0 = B[lane], b1 = B[32 + lane];
-  const float a0h = tf32Round(a0), a1h = tf32Round(a1), b0h = tf32Round(b0), b1h = tf32Round(b1);
-  const float a0l = tf32Round(a0 - a0h), a1l = tf32Round(a1 - a1h), b0l = tf32Round(b0 - b0h), b1l = tf32Round(b1 - b1h);
-  mmaTf32K4(d[0], a0l, a1l, b0h); mmaTf32K4(d[1], a0l, a1l, b1h); // small terms first
-  mmaTf32K4(d[0], a0h, a1h, b0l); mmaTf32K4(d[1], a0h, a1h, b1l);
-  mmaTf32K4(d[0], a0h, a1h, b0h); mmaTf32K4(d[1], a0h, a1h, b1h);
+  const float a0 = A0[lane], a1 = A0[32 + lane], a2 = A1[lane], a3 = A1[32 + lane];
+  const float b00 = B0[lane], b01 = B1[lane], b10 = B0[32 + lane], b11 = B1[32 + lane]; // b[h][k half]
+  const float a0h = tf32High(a0), a1h = tf32High(a1), a2h = tf32High(a2), a3h = tf32High(a3);
+  const float b00h = tf32High(b00), b01h = tf32High(b01), b10h = tf32High(b10), b11h = tf32High(b11);
+  const float a0l = a0 - a0h, a1l = a1 - a1h, a2l = a2 - a2h, a3l = a3 - a3h; // (the tensor core drops the low bits of lo itself)
+  const float b00l = b00 - b00h, b01l = b01 - b01h, b10l = b10 - b10h, b11l = b11 - b11h;
+  mmaTf32K8(d[0], a0l, a1l, a2l, a3l, b00h, b01h); mmaTf32K8(d[1], a0l, a1l, a2l, a3l, b10h, b11h); // small terms first
+  mmaTf32K8(d[0], a0h, a1h, a2h, a3h, b00l, b01l); mmaTf32K8(d[1], a0h, a1h, a2h, a3h, b10l, b11l);
+  mmaTf32K8(d[0], a0h, a1h, a2h, a3h, b00h, b01h); mmaTf32K8(d[1], a0h, a1h, a2h, a3h, b10h, b11h);
 #else
   const int g = lane >> 2, t = lane & 3; // host emulation: the lane's eight outputs from the same three-term split
   for (int h = 0; h < 2; ++h)
     for (int e = 0; e < 4; ++e) {
       const int r = g + 8 * (e >> 1), c = 8 * h + 2 * t + (e & 1);
       float lo = 0.f, mid = 0.f, hi = 0.f;
-      for (int k = 0; k < 4; ++k) {
-        const float av = A[4 * r + k], bv = B[4 * c + k];
-        const float ah = tf32Round(av), bh = tf32Round(bv), al = tf32Round(av - ah), bl = tf32Round(bv - bh);
+      for (int k = 0; k < 8; ++k) {
+        const float av = k < 4 ? A0[4 * r + k] : A1[4 * r + k - 4], bv = k < 4 ? B0[4 * c + k] : B1[4 * c + k - 4];
+        const float ah = tf32High(av), bh = tf32High(bv), al = av - ah, bl = bv - bh;
         lo += al * bh; mid += ah * bl; hi += ah * bh;
       }
       d[h][e] += (lo + mid) + hi;
     }
 #endif
 }
+// pair lists are padded to even length (GramPlan), tables are staged in shared memory (broadcast reads)
 MB2_HD void gramTileAccumulate(const float* strips, const int32_t* pairA, const int32_t* pairB, int p0, int p1, int lane, float d[2][4]) {
-#if defined(__CUDA_ARCH__)
-  // the pair lists live in global memory: fetch 32 entries at a time (one per lane) and hand them out by shuffle, so that the
-  // inner loop has no dependent global load
-  for (int base = p0; base < p1; base += 32) {
-    const int cnt = p1 - base < 32 ? p1 - base : 32;
-    const int mineA = lane < cnt ? __ldg(pairA + base + lane) : 0, mineB = lane < cnt ? __ldg(pairB + base + lane) : 0;
-    for (int i = 0; i < cnt; ++i) gramTilePair(strips, __shfl_sync(0xffffffffu, mineA, i), __shfl_sync(0xffffffffu, mineB, i), lane, d);
-  }
-#else
-  for (int p = p0; p < p1; ++p) gramTilePair(strips, pairA[p], pairB[p], lane, d);
-#endif
+  for (int p = p0; p < p1; p += 2) gramTilePairs(strips, pairA[p], pairB[p], pairA[p + 1], pairB[p + 1], lane, d);
 }
-// writes the lane's accumulators into tile storage T[c][r] = H(r, c) with the identity extension on padded rows/columns and the
-// damping added to the real diagonal (info = validI | validJ << 8 | diag << 16 as in tileInfo)
-MB2_HD void gramTileStore(float* tile, const float d[2][4], int info, float lambda, int lane) {
+// float offsets of the lane's eight outputs in tile storage T[c][r] = H(r, c) (same for every tile: computed once per kernel)
+MB2_HD void gramLaneOffsets(int lane, int off[8]) {
   const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) off[4 * h + e] = tileIdx(8 * h + 2 * t + (e & 1), g + 8 * (e >> 1));
+}
+// writes the lane's accumulators with the identity extension on padded rows/columns and the damping added to the real diagonal
+// (info = validI | validJ << 8 | diag << 16 as in tileInfo); full off-diagonal tiles take the plain path
+MB2_HD void gramTileStore(float* tile, const float d[2][4], int info, float lambda, int lane, const int off[8]) {
   const int vI = info & 0xFF, vJ = (info >> 8) & 0xFF, diag = (info >> 16) & 1;
+  if (vI == 16 && vJ == 16 && !diag) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tile[off[i]] = d[i >> 2][i & 3];
+    return;
+  }
+  const int g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int h = 0; h < 2; ++h)
 #pragma unroll
@@ -164,35 +175,19 @@ MB2_HD void gramTileStore(float* tile, const float d[2][4], int info, float lamb
       float x = d[h][e];
       if (r >= vI || c >= vJ) x = (diag && r == c) ? 1.f : 0.f;
       else if (diag && r == c) x += lambda;
-      tile[tileIdx(c, r)] = x;
+      tile[off[4 * h + e]] = x;
     }
 }
 // entry hl of block K of J^T r: sum over the strips of tile column K of strip[hl][0..3] . r[4q..4q+3]
-MB2_HD float gramVectorEntry(const float* strips, const float* resid, const int32_t* colStrip, const int32_t* stripCoord, int s0, int s1, int hl, unsigned hmask) {
+MB2_HD float gramVectorEntry(const float* strips, const float* resid, const int32_t* colStrip, const int32_t* stripRow, int s0, int s1, int hl) {
   float g0 = 0.f, g1 = 0.f;
-#if defined(__CUDA_ARCH__)
-  for (int base = s0; base < s1; base += 16) { // same prefetch-and-shuffle scheme per half-warp
-    const int cnt = s1 - base < 16 ? s1 - base : 16;
-    const int mine = hl < cnt ? __ldg(colStrip + base + hl) : 0;
-    const int mineRow = hl < cnt ? __ldg(stripCoord + 2 * mine) : 0;
-    for (int i = 0; i < cnt; ++i) {
-      const int sidx = __shfl_sync(hmask, mine, i, 16), row0 = __shfl_sync(hmask, mineRow, i, 16);
-      const float4 sv = *reinterpret_cast<const float4*>(strips + size_t(sidx) * 64 + 4 * hl);
-      const float4 rv = *reinterpret_cast<const float4*>(resid + row0);
-      g0 += sv.x * rv.x + sv.y * rv.y;
-      g1 += sv.z * rv.z + sv.w * rv.w;
-    }
-  }
-#else
-  (void)hmask;
   for (int k = s0; k < s1; ++k) {
     const int sidx = colStrip[k];
     const float4 sv = *reinterpret_cast<const float4*>(strips + size_t(sidx) * 64 + 4 * hl);
-    const float4 rv = *reinterpret_cast<const float4*>(resid + stripCoord[2 * sidx]);
+    const float4 rv = *reinterpret_cast<const float4*>(resid + stripRow[sidx]);
     g0 += sv.x * rv.x + sv.y * rv.y;
     g1 += sv.z * rv.z + sv.w * rv.w;
   }
-#endif
   return g0 + g1;
 }
 

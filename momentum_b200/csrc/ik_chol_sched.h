@@ -83,6 +83,10 @@ struct GramPlan {
 std::string buildGramPlan(const CholSchedule& s, const std::vector<int32_t>& cellRow0, const std::vector<int32_t>& cellRows, const std::vector<int32_t>& cellCol,
                           int numRows, GramPlan& out);
 
+// The Gram tables as one int32 blob; offsets[8] = {tileOrder, tilePairStart, pairA, pairB, colStripStart, colStrip, stripRow, tileInfo}
+// (stripRow[s] = first row of strip s; tileInfo[t] = validI | validJ << 8 | diag << 16 of the schedule).
+void makeGramBlob(const GramPlan& g, const CholSchedule& s, std::vector<int32_t>& blob, int32_t offsets[8]);
+
 struct CholSchedDev;
 // Concatenates every table into one int32 blob; `dev` gets pointers into blob.data() (rebase them after uploading).
 void makeScheduleBlob(const CholSchedule& s, std::vector<int32_t>& blob, CholSchedDev& dev);

@@ -397,7 +397,7 @@ cudaError_t launchCholesky(const CholArgs& a, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------------
 constexpr int kGramThreads = 256;
 
-size_t gramTilesSmemBytes(size_t stripStride) { return 128 + sizeof(float) * stripStride + 16; }
+size_t gramTilesSmemBytes(size_t stripStride, int blobInts) { return 128 + sizeof(float) * (stripStride + 64) + 16 + sizeof(int32_t) * size_t((blobInts + 3) & ~3); }
 
 __global__ void __launch_bounds__(kGramThreads) gramTilesKernel(const GramArgs a) {
   extern __shared__ __align__(16) float gramSmem[];
@@ -406,9 +406,12 @@ __global__ void __launch_bounds__(kGramThreads) gramTilesKernel(const GramArgs a
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, hw = tid >> 4, hl = tid & 15;
   float* strips = gramSmem + (((128u - (smemAddr(gramSmem) & 127u)) & 127u) >> 2);
   float* resid = strips + a.residOff;
-  unsigned long long* bar = reinterpret_cast<unsigned long long*>(strips + a.stripStride);
+  // smem: [strips | residual] as in global memory, then the all-zero strip that pads odd pair lists (index zeroStrip), barrier, tables
+  float* zero = strips + a.stripStride;
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(zero + 64);
   const uint32_t barAddr = smemAddr(bar);
   const uint32_t total = uint32_t(a.stripStride) * 4u;
+  if (tid < 64) zero[tid] = 0.f;
   if (tid == 0) {
     mbarInit(barAddr, 1);
     fenceBarrierInit();
@@ -416,26 +419,33 @@ __global__ void __launch_bounds__(kGramThreads) gramTilesKernel(const GramArgs a
     const char* src = reinterpret_cast<const char*>(a.strips + size_t(b) * a.stripStride);
     for (uint32_t off = 0; off < total; off += 16384u) bulkLoad(smemAddr(strips) + off, src + off, total - off < 16384u ? total - off : 16384u, barAddr);
   }
+  // the plan tables are read in dependent chains (tile -> pair range -> strips): stage them in shared memory while the copy is in flight
+  int32_t* tab = reinterpret_cast<int32_t*>(bar + 2);
+  for (int i = tid; i < a.blobInts; i += kGramThreads) tab[i] = __ldg(a.blob + i);
   __syncthreads();
-  mbarWait(barAddr, 0);
+  mbarWaitRelaxed(barAddr, 0);
+  const int32_t* tileOrder = tab + a.offTileOrder, *tilePairStart = tab + a.offTilePairStart, *pairA = tab + a.offPairA, *pairB = tab + a.offPairB;
+  const int32_t* colStripStart = tab + a.offColStripStart, *colStrip = tab + a.offColStrip, *stripRow = tab + a.offStripRow, *tileInfo = tab + a.offTileInfo;
   float* out = a.out + size_t(b) * a.outStride;
+  int laneOff[8];
+  gramLaneOffsets(lane, laneOff);
   for (int ti = warp; ti < a.numTiles; ti += kGramThreads / 32) {
-    const int t = __ldg(a.tileOrder + ti);
+    const int t = tileOrder[ti];
     float acc[2][4];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    gramTileAccumulate(strips, a.pairA, a.pairB, __ldg(a.tilePairStart + t), __ldg(a.tilePairStart + t + 1), lane, acc);
-    gramTileStore(out + size_t(t) * 256, acc, __ldg(a.tileInfo + 3 * t + 2), a.regularization, lane);
+    gramTileAccumulate(strips, pairA, pairB, tilePairStart[t], tilePairStart[t + 1], lane, acc);
+    gramTileStore(out + size_t(t) * 256, acc, tileInfo[t], a.regularization, lane, laneOff);
   }
   float* y = out + size_t(a.numTiles) * 256;
   for (int K = hw; K < a.numTileCols; K += kGramThreads / 16)
-    y[16 * K + hl] = gramVectorEntry(strips, resid, a.colStrip, a.stripCoord, __ldg(a.colStripStart + K), __ldg(a.colStripStart + K + 1), hl, 0xFFFFu << (16 * ((tid >> 4) & 1)));
+    y[16 * K + hl] = gramVectorEntry(strips, resid, colStrip, stripRow, colStripStart[K], colStripStart[K + 1], hl);
 }
 
 cudaError_t launchGramTiles(const GramArgs& a, cudaStream_t stream) {
-  const size_t smem = gramTilesSmemBytes(a.stripStride);
+  const size_t smem = gramTilesSmemBytes(a.stripStride, a.blobInts);
   if (smem > size_t(g_maxSmemOptin) || (a.stripStride & 3) != 0) return cudaErrorInvalidConfiguration;
   cudaError_t e = cudaFuncSetAttribute(gramTilesKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
@@ -504,7 +514,7 @@ __global__ void __launch_bounds__(kSchedThreads, 3) choleskyScheduledKernel(cons
     }
   }
   MB2_PROF(6)
-  mbarWait(barAddr, 0);
+  mbarWaitRelaxed(barAddr, 0); // 256 spinning threads would take issue slots from the other CTAs of the SM
   MB2_PROF(7)
   const CholSchedDev S = rebaseSchedule(Sg, blob);
   if (fromGram) {

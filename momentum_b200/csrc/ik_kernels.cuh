@@ -72,20 +72,16 @@ struct GramArgs {            // K2s: stored tiles of J^T J + lambda I and J^T r 
   int32_t residOff;          // GramPlan::residOff
   const int32_t* active;
   int32_t numStrips, numTiles, numTileCols, nPad;
-  const int32_t* stripCoord; // device copies of the GramPlan tables
-  const int32_t* tileOrder;
-  const int32_t* tilePairStart;
-  const int32_t* pairA;
-  const int32_t* pairB;
-  const int32_t* colStripStart;
-  const int32_t* colStrip;
-  const int32_t* tileInfo;   // the schedule's [numTiles][3]
+  // the GramPlan tables as one int32 blob (staged in shared memory by the kernel); offsets in ints
+  const int32_t* blob;
+  int32_t blobInts;
+  int32_t offTileOrder, offTilePairStart, offPairA, offPairB, offColStripStart, offColStrip, offStripRow, offTileInfo;
   float regularization;
   float* out;                // [B][outStride]: numTiles x 256 floats in tile storage order, then the slot-ordered J^T r [nPad]
   size_t outStride;
 };
 cudaError_t launchGramTiles(const GramArgs& a, cudaStream_t stream);
-size_t gramTilesSmemBytes(size_t stripStride);
+size_t gramTilesSmemBytes(size_t stripStride, int blobInts);
 
 cudaError_t launchSweep(const SweepArgs& a, bool jacobian, cudaStream_t stream);
 size_t sweepSmemPerInstance(const FunctionTables& T);

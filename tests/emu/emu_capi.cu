@@ -173,7 +173,7 @@ static int cholDispatch(float* Hg, int n, int ldH, float reg, float* delta, floa
 
 // emulation of gramTilesKernel for one instance: strips = TMA boxes of the K-major Jacobian, warps / half-warps in sequence
 static void gramOne(const mb2_solver_function* f, int b, const GramPlan& G, const CholSchedDev& S, float reg, float* out) {
-  std::vector<float> store(size_t(G.stride) + 8, 0.f);
+  std::vector<float> store(size_t(G.stride) + 64 + 8, 0.f); // + the all-zero strip
   float* strips = store.data();
   while ((reinterpret_cast<uintptr_t>(strips) & 15) != 0) ++strips;
   std::copy(f->J.data() + size_t(b) * G.stride, f->J.data() + size_t(b + 1) * G.stride, strips); // the bulk copy
@@ -185,12 +185,16 @@ static void gramOne(const mb2_solver_function* f, int b, const GramPlan& G, cons
     for (int lane = 0; lane < 32; ++lane) {
       float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
       gramTileAccumulate(strips, G.pairA.data(), G.pairB.data(), G.tilePairStart[t], G.tilePairStart[t + 1], lane, acc);
-      gramTileStore(tile, acc, S.tileInfo[3 * t + 2], reg, lane);
+      int off[8];
+      gramLaneOffsets(lane, off);
+      gramTileStore(tile, acc, S.tileInfo[3 * t + 2], reg, lane, off);
     }
   }
   float* y = out + size_t(G.numTiles) * 256;
+  std::vector<int32_t> stripRow(G.numStrips);
+  for (int i = 0; i < G.numStrips; ++i) stripRow[i] = G.stripCoord[2 * i];
   for (int K = 0; K < G.numTileCols; ++K)
-    for (int hl = 0; hl < 16; ++hl) y[16 * K + hl] = gramVectorEntry(strips, resid, G.colStrip.data(), G.stripCoord.data(), G.colStripStart[K], G.colStripStart[K + 1], hl, 0xFFFFu);
+    for (int hl = 0; hl < 16; ++hl) y[16 * K + hl] = gramVectorEntry(strips, resid, G.colStrip.data(), stripRow.data(), G.colStripStart[K], G.colStripStart[K + 1], hl);
 }
 
 // emulation of choleskyScheduledKernel for one instance: phases in the same order, half-warps/warps in sequence
