@@ -290,14 +290,24 @@ def main():
                 "peak_source": f"{peaks['src']} copy bandwidth", "traffic": traffic.get(key), "ms_per_launch": ms,
                 "algorithmic_bytes_per_instance": bytes_per_instance}
 
-    jtj_ach = jtj_flops * B / (jtj_ms * 1e-3) / 1e12 if jtj_ms > 0 else 0.0
+    gram = st["strip_floats"] > 0  # tile-sparse Gram path: strips in, tiles out, no dense J / H
+    if gram:
+        k1_bytes = 4.0 * (n + target_floats + st["jacobian_nonzeros"] + m_rows) + 8.0
+        gram_bytes = 4.0 * (st["strip_floats"] + st["cholesky_tiles"] * 256 + 16 * ((st["normal_parameters"] + 15) // 16))
+        gram_flops = 2.0 * st["gram_macs"]
+        gram_ach = gram_flops * B / (jtj_ms * 1e-3) / 1e12 if jtj_ms > 0 else 0.0
+        k2_entry = hbm_entry("gramTilesKernel (tile-sparse J^T J / J^T r, mma.sync 3xTF32 over non-zero strips)", "jtj_jtr", gram_bytes, jtj_ms)
+        k2_entry.update({"algorithmic_flops_per_instance": gram_flops, "tflops": gram_ach, "dense_equivalent_flops_per_instance": jtj_flops})
+    else:
+        jtj_ach = jtj_flops * B / (jtj_ms * 1e-3) / 1e12 if jtj_ms > 0 else 0.0
+        k2_entry = {"kernel": "jtjTensorKernel (JtJ/Jtr, tcgen05 3xTF32)" if st["jacobian_columns"] + 1 <= 256 and args.jtj_mode in (0, 2, 3) else "jtjSimtKernel",
+                    "bound": "tensor", "achieved": jtj_ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": jtj_ach / tf32_peak,
+                    "peak_source": f"0.5 x {peaks['src']} bf16 cuBLAS burst ({peaks['bf16']} TF/s) = TF32 dense", "traffic": traffic.get("jtj_jtr"),
+                    "ms_per_launch": jtj_ms, "algorithmic_flops_per_instance": jtj_flops, "algorithmic_bytes_per_instance": k2_bytes,
+                    "hbm_frac": (k2_bytes * B / (jtj_ms * 1e-3) / 1e9 / hbm_peak) if jtj_ms > 0 else 0.0}
     kernels = [
         hbm_entry("sweepKernel<true> (FK + residual + Jacobian)", "fk_residual_jacobian", k1_bytes, sweep_ms),
-        {"kernel": "jtjTensorKernel (JtJ/Jtr, tcgen05 3xTF32)" if st["jacobian_columns"] + 1 <= 256 and args.jtj_mode in (0, 2, 3) else "jtjSimtKernel",
-         "bound": "tensor", "achieved": jtj_ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": jtj_ach / tf32_peak,
-         "peak_source": f"0.5 x {peaks['src']} bf16 cuBLAS burst ({peaks['bf16']} TF/s) = TF32 dense", "traffic": traffic.get("jtj_jtr"),
-         "ms_per_launch": jtj_ms, "algorithmic_flops_per_instance": jtj_flops, "algorithmic_bytes_per_instance": k2_bytes,
-         "hbm_frac": (k2_bytes * B / (jtj_ms * 1e-3) / 1e9 / hbm_peak) if jtj_ms > 0 else 0.0},
+        k2_entry,
         hbm_entry("choleskyScheduledKernel (damped LLT + solves + update)" if st["cholesky_tiles"] else "choleskyKernel (dense LLT + solves + update)",
                   "cholesky_update", k3_bytes, chol_ms),
     ]

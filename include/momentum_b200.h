@@ -218,8 +218,10 @@ int mb2_solver_get_phase_times(mb2_solver* s, double ms[4], uint64_t launches[4]
  * counterpart): [0] structurally non-zero Jacobian entries written per iteration, [1] device Jacobian columns (without
  * the residual column), [2] ldJ, [3] parameters in the normal equations (ns), [4] 16x16 tiles held by the tile-sparse
  * Cholesky (0: dense Eigen-structured kernel), [5] tile multiply-accumulate blocks per factorisation, [6] levels of the
- * tile elimination tree, [7] residual rows m. */
-int mb2_solver_get_plan_stats(mb2_solver* s, int64_t stats[8]);
+ * tile elimination tree, [7] residual rows m (row groups aligned to 4 in the strip layout), [8] floats per instance of the Jacobian in
+ * strip layout (0: K-major matrix), [9] multiply-accumulates per instance of the tile-sparse Gram kernel, [10] its strip pairs,
+ * [11] reserved. */
+int mb2_solver_get_plan_stats(mb2_solver* s, int64_t stats[12]);
 
 #ifdef __cplusplus
 }

@@ -8,11 +8,11 @@
 //     momentum_b200::GaussNewtonSolverOptions      <- momentum::GaussNewtonSolverOptions        (gauss_newton_solver.h:17-59)
 // Errors are rethrown as std::runtime_error like MT_CHECK / MT_THROW (common/exception.h:31,60-67).
 //
-// Part 2 (compiled only when momentum's headers are on the include path): drop-in subclasses
-//     momentum_b200::CudaSkeletonSolverFunction : momentum::SolverFunctionT<float>
-//     momentum_b200::CudaGaussNewtonSolver      : momentum::SolverT<float>
-// that translate momentum::Character / PositionErrorFunction / OrientationErrorFunction / StateErrorFunction /
-// LimitErrorFunction objects into the C-ABI, so existing callers keep calling solver.solve(params).
+// Part 2 (compiled only when momentum's headers are on the include path):
+//     momentum_b200::makeCharacter(const momentum::Character&)       translates skeleton / parameterTransform / limits
+//     momentum_b200::CudaSkeletonSolverFunction : momentum::SolverFunctionT<float>   (single instance; getError / getJacobian / getJtJR)
+// so that existing callers can hand the solver function to momentum's own solvers; the batched device-side Gauss-Newton loop is
+// reached through BatchedGaussNewtonSolver of part 1 (wrapping it in a momentum::SolverT subclass is a few lines on top of it).
 // Part 2 cannot be compiled in the development image (Eigen 5, ms-gsl, fmt are absent); see INTEGRATION.md.
 #pragma once
 

@@ -112,7 +112,7 @@ struct mb2_solver_function {
   DeviceBuffer<float> dLimitData;
   DeviceBuffer<int32_t> dEnabledList, dIdentity, dDeviceCols;
   // device data
-  DeviceBuffer<float> dTargets, dWeights, dJ, dTheta, dState, dH, dPacked;
+  DeviceBuffer<float> dTargets, dWeights, dJ, dTheta, dState, dH;
   DeviceBuffer<double> dErrors;
   std::vector<float> hWeights; // shared weights mirror
   std::unique_ptr<DeviceSchedule> sched; // Cholesky schedule of the current (compact) plan
@@ -1024,7 +1024,7 @@ int mb2_solver_get_counters(mb2_solver* s, uint64_t* totalIterations, uint64_t* 
   return MB2_OK;
 }
 
-int mb2_solver_get_plan_stats(mb2_solver* s, int64_t stats[8]) {
+int mb2_solver_get_plan_stats(mb2_solver* s, int64_t stats[12]) {
   MB2_CHECK(s != nullptr && stats != nullptr, "null argument");
   const mb2_solver_function* f = s->fn;
   int64_t nnz = 0;
@@ -1038,6 +1038,11 @@ int mb2_solver_get_plan_stats(mb2_solver* s, int64_t stats[8]) {
   stats[5] = tiles ? f->sched->host.tileOps : 0;
   stats[6] = tiles ? f->sched->host.numLevels : 0;
   stats[7] = f->plan.numRows;
+  const bool gram = tiles && f->planAlignRows && f->sched->gramValid;
+  stats[8] = gram ? f->sched->gram.stride : 0;
+  stats[9] = gram ? f->sched->gram.macs : 0;
+  stats[10] = gram ? int64_t(f->sched->gram.pairA.size()) : 0;
+  stats[11] = 0;
   return MB2_OK;
 }
 

@@ -380,9 +380,10 @@ class GaussNewtonSolver(_Base):
 
     def get_plan_stats(self):
         """Per-instance algorithmic sizes of the plan the last solve ran on (see momentum_b200.h)."""
-        st = (C.c_int64 * 8)()
+        st = (C.c_int64 * 12)()
         self._check(self._L.mb2_solver_get_plan_stats(self._h, st))
-        keys = ["jacobian_nonzeros", "jacobian_columns", "ldj", "normal_parameters", "cholesky_tiles", "cholesky_tile_ops", "cholesky_levels", "rows"]
+        keys = ["jacobian_nonzeros", "jacobian_columns", "ldj", "normal_parameters", "cholesky_tiles", "cholesky_tile_ops", "cholesky_levels", "rows",
+                "strip_floats", "gram_macs", "gram_pairs", "reserved"]
         return dict(zip(keys, (int(v) for v in st)))
 
     def set_profiling(self, enabled: bool):

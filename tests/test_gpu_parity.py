@@ -71,6 +71,20 @@ def test_solve_with_tensor_core_jtj_matches_oracle():
     print("max rel param diff (3xTF32 JtJ)", worst)
 
 
+def test_solve_jtj_paths_into_the_tile_cholesky():
+    """The tile-scheduled Cholesky fed three ways: tile-sparse Gram (default and on request), dense SIMT JtJ through TMA boxes."""
+    B = 16
+    ch, efs, theta0, _ = humanoid_problem(B, orientation=True)
+    for jtj in (ms.JTJ_SPARSE_TILES, ms.JTJ_FP32_SIMT):
+        opts = ms.GaussNewtonSolverOptions(min_iterations=1, max_iterations=8, regularization=0.05, jtj_mode=jtj, cholesky_mode=ms.CHOLESKY_TILES_SPARSE)
+        parity.check_solve(ch, efs, theta0, opts, instances=[0, 5, 15])
+    # the strip layout only exists with the tile schedule
+    opts = ms.GaussNewtonSolverOptions(min_iterations=1, max_iterations=2, jtj_mode=ms.JTJ_SPARSE_TILES, cholesky_mode=ms.CHOLESKY_DENSE_EIGEN)
+    fn = parity.build_function(ch, efs, B)
+    with pytest.raises(ms.MomentumB200Error):
+        ms.GaussNewtonSolver(opts, fn).solve(theta0)
+
+
 def test_bodyhands_single_iteration_wide_rig():
     # 300 joints / n = 424 / m = 600: multi-pass levels (>32 joints per depth level), matrix too big for smem Cholesky
     ch, efs, theta0, theta_star = bodyhands_problem(3)
