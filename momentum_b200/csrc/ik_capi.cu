@@ -232,6 +232,18 @@ int uploadWeights(mb2_solver_function* f) {
   return MB2_OK;
 }
 
+// depth (in the joint tree) of the deepest joint each enabled parameter drives: tie-break priority of the elimination order
+static std::vector<int> columnDepthPriority(const HostCharacter& h, const std::vector<int32_t>& enabledList) {
+  std::vector<int> jointDepth(h.numJoints, 0);
+  for (int j = 0; j < h.numJoints; ++j) { int d = 0; for (int a = h.parent[j]; a >= 0; a = h.parent[a]) ++d; jointDepth[j] = d; }
+  std::vector<int> paramDepth(h.numParams, 0);
+  for (int r = 0; r < kParametersPerJoint * h.numJoints; ++r)
+    for (int k = h.ptOuter[r]; k < h.ptOuter[r + 1]; ++k) paramDepth[h.ptInner[k]] = std::max(paramDepth[h.ptInner[k]], jointDepth[r / kParametersPerJoint]);
+  std::vector<int> prio(enabledList.size());
+  for (size_t a = 0; a < enabledList.size(); ++a) prio[a] = paramDepth[enabledList[a]];
+  return prio;
+}
+
 int uploadSchedule(mb2_solver_function* f, std::unique_ptr<DeviceSchedule>& ds) {
   std::vector<int32_t> blob;
   CholSchedDev hostView;
@@ -263,7 +275,8 @@ int ensurePlan(mb2_solver_function* f, int mode, bool schedDense = false, bool a
     const int ns = f->plan.numCols;
     std::vector<std::vector<int>> cliques(f->plan.units.size());
     for (const CellDesc& c : f->plan.cells) cliques[c.unit].push_back(int(c.col));
-    err = buildCholSchedule(ns, cliques, schedDense, ds->host);
+    const std::vector<int> prio = columnDepthPriority(f->ch->host, f->plan.enabledList);
+    err = buildCholSchedule(ns, cliques, schedDense, ds->host, &prio);
     if (!err.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, err);
     // re-plan with the device columns in elimination order (tile starts aligned to 4 columns), the schedule expressed in them
     std::vector<int32_t> colOrder;

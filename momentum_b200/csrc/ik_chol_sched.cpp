@@ -27,7 +27,7 @@ struct BitRows {
 
 // Minimum-degree ordering on the symmetric pattern; ties go to a neighbour of the vertex eliminated
 // last (keeps the parameters of one kinematic chain contiguous), then to the lowest index.
-std::vector<int> minimumDegreeOrder(BitRows& adj) {
+std::vector<int> minimumDegreeOrder(BitRows& adj, const std::vector<int>* priority) {
   const int n = adj.n;
   std::vector<int> order;
   order.reserve(n);
@@ -39,8 +39,11 @@ std::vector<int> minimumDegreeOrder(BitRows& adj) {
     int best = -1;
     for (int i = 0; i < n; ++i) {
       if (done[i]) continue;
-      if (best < 0 || degree[i] < degree[best]) best = i;
-      else if (degree[i] == degree[best] && last >= 0 && adj.test(last, i) && !adj.test(last, best)) best = i;
+      if (best < 0 || degree[i] < degree[best]) { best = i; continue; }
+      if (degree[i] != degree[best]) continue;
+      const int pi = priority ? (*priority)[i] : 0, pb = priority ? (*priority)[best] : 0;
+      if (pi > pb) best = i;
+      else if (pi == pb && last >= 0 && adj.test(last, i) && !adj.test(last, best)) best = i;
     }
     // eliminate `best`: its remaining neighbours become a clique
     std::vector<int> nb;
@@ -73,7 +76,7 @@ std::vector<int> minimumDegreeOrder(BitRows& adj) {
 
 } // namespace
 
-std::string buildCholSchedule(int n, const std::vector<std::vector<int>>& cliques, bool forceDense, CholSchedule& out) {
+std::string buildCholSchedule(int n, const std::vector<std::vector<int>>& cliques, bool forceDense, CholSchedule& out, const std::vector<int>* priority) {
   out = CholSchedule();
   if (n <= 0) return "empty system";
   out.n = n;
@@ -94,7 +97,8 @@ std::string buildCholSchedule(int n, const std::vector<std::vector<int>>& clique
       }
     BitRows work = pattern;
     for (int i = 0; i < n; ++i) work.clear(i, i);
-    order = minimumDegreeOrder(work);
+    if (priority != nullptr && int(priority->size()) != n) return "priority must have one entry per column";
+    order = minimumDegreeOrder(work, priority);
   }
   // 1b. supernodes of the element-level factor (columns with nested structure) decide where tiles may
   //     break: a supernode that fits in one tile is never split across two (padding instead), because a

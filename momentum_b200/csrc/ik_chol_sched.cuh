@@ -115,7 +115,10 @@ __device__ __forceinline__ void mmaTf32K8(float d[4], float a0, float a1, float 
                  "r"(__float_as_uint(b1)));
 }
 #endif
-MB2_HD void gramTilePairs(const float* strips, int sa0, int sb0, int sa1, int sb1, int lane, float d[2][4]) {
+// d: running sums of the leading term, added in fp32 registers (round to nearest) after every step: the tensor core's own
+// accumulator truncates, which over a few hundred steps becomes a visible bias. small: the two correction terms, accumulated
+// inside the tensor core (they are 2^-11 of the result: their truncation does not matter); added to d once at the end.
+MB2_HD void gramTilePairs(const float* strips, int sa0, int sb0, int sa1, int sb1, int lane, float d[2][4], float small[2][4]) {
   const float* A0 = strips + size_t(sa0) * 64;
   const float* B0 = strips + size_t(sb0) * 64;
   const float* A1 = strips + size_t(sa1) * 64;
@@ -125,11 +128,14 @@ MB2_HD void gramTilePairs(const float* strips, int sa0, int sb0, int sa1, int sb
   const float b00 = B0[lane], b01 = B1[lane], b10 = B0[32 + lane], b11 = B1[32 + lane]; // b[h][k half]
   const float a0h = tf32High(a0), a1h = tf32High(a1), a2h = tf32High(a2), a3h = tf32High(a3);
   const float b00h = tf32High(b00), b01h = tf32High(b01), b10h = tf32High(b10), b11h = tf32High(b11);
-  const float a0l = a0 - a0h, a1l = a1 - a1h, a2l = a2 - a2h, a3l = a3 - a3h; // (the tensor core drops the low bits of lo itself)
+  const float a0l = a0 - a0h, a1l = a1 - a1h, a2l = a2 - a2h, a3l = a3 - a3h; // (the tensor core reads the leading bits of lo)
   const float b00l = b00 - b00h, b01l = b01 - b01h, b10l = b10 - b10h, b11l = b11 - b11h;
-  mmaTf32K8(d[0], a0l, a1l, a2l, a3l, b00h, b01h); mmaTf32K8(d[1], a0l, a1l, a2l, a3l, b10h, b11h); // small terms first
-  mmaTf32K8(d[0], a0h, a1h, a2h, a3h, b00l, b01l); mmaTf32K8(d[1], a0h, a1h, a2h, a3h, b10l, b11l);
-  mmaTf32K8(d[0], a0h, a1h, a2h, a3h, b00h, b01h); mmaTf32K8(d[1], a0h, a1h, a2h, a3h, b10h, b11h);
+  mmaTf32K8(small[0], a0l, a1l, a2l, a3l, b00h, b01h); mmaTf32K8(small[1], a0l, a1l, a2l, a3l, b10h, b11h);
+  mmaTf32K8(small[0], a0h, a1h, a2h, a3h, b00l, b01l); mmaTf32K8(small[1], a0h, a1h, a2h, a3h, b10l, b11l);
+  float t0[4] = {0.f, 0.f, 0.f, 0.f}, t1[4] = {0.f, 0.f, 0.f, 0.f};
+  mmaTf32K8(t0, a0h, a1h, a2h, a3h, b00h, b01h); mmaTf32K8(t1, a0h, a1h, a2h, a3h, b10h, b11h);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { d[0][e] += t0[e]; d[1][e] += t1[e]; }
 #else
   const int g = lane >> 2, t = lane & 3; // host emulation: the lane's eight outputs from the same three-term split
   for (int h = 0; h < 2; ++h)
@@ -141,13 +147,19 @@ MB2_HD void gramTilePairs(const float* strips, int sa0, int sb0, int sa1, int sb
         const float ah = tf32High(av), bh = tf32High(bv), al = av - ah, bl = bv - bh;
         lo += al * bh; mid += ah * bl; hi += ah * bh;
       }
-      d[h][e] += (lo + mid) + hi;
+      small[h][e] += lo + mid;
+      d[h][e] += hi;
     }
 #endif
 }
 // pair lists are padded to even length (GramPlan), tables are staged in shared memory (broadcast reads)
 MB2_HD void gramTileAccumulate(const float* strips, const int32_t* pairA, const int32_t* pairB, int p0, int p1, int lane, float d[2][4]) {
-  for (int p = p0; p < p1; p += 2) gramTilePairs(strips, pairA[p], pairB[p], pairA[p + 1], pairB[p + 1], lane, d);
+  float small[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  for (int p = p0; p < p1; p += 2) gramTilePairs(strips, pairA[p], pairB[p], pairA[p + 1], pairB[p + 1], lane, d, small);
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) d[h][e] += small[h][e];
 }
 // float offsets of the lane's eight outputs in tile storage T[c][r] = H(r, c) (same for every tile: computed once per kernel)
 MB2_HD void gramLaneOffsets(int lane, int off[8]) {

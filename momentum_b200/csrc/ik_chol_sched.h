@@ -47,7 +47,10 @@ struct CholSchedule {
 
 // `cliques`: for every Jacobian row group, the device columns it touches (each list is a clique of the
 // pattern). n = number of device columns that enter the normal equations.
-std::string buildCholSchedule(int n, const std::vector<std::vector<int>>& cliques, bool forceDense, CholSchedule& out);
+// `priority` (optional, per column): among columns of equal degree the ordering eliminates the larger priority first. Callers pass
+// the depth of the joint a parameter drives: in the final cliques of a kinematic tree every order has the same fill, but only
+// leaf-to-root orders keep independent limbs in separate subtrees of the tile elimination tree (= fewer levels).
+std::string buildCholSchedule(int n, const std::vector<std::vector<int>>& cliques, bool forceDense, CholSchedule& out, const std::vector<int>* priority = nullptr);
 // Device column layout of the solver plan: parameters in elimination order, and every tile column starting on a device column
 // that is a multiple of 4 (TMA fetches a tile as one 16 x 16 box of the row-major H; the first byte of each box row must be
 // 16-byte aligned). The up-to-3 skipped device columns before such a start are all-zero Jacobian columns ("gaps").

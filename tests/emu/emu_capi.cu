@@ -65,6 +65,18 @@ static std::string plan(mb2_solver_function* f, bool compact) {
   return "";
 }
 
+// depth (in the joint tree) of the deepest joint each enabled parameter drives: tie-break priority of the elimination order
+static std::vector<int> columnDepthPriority(const HostCharacter& h, const std::vector<int32_t>& enabledList) {
+  std::vector<int> jointDepth(h.numJoints, 0);
+  for (int j = 0; j < h.numJoints; ++j) { int d = 0; for (int a = h.parent[j]; a >= 0; a = h.parent[a]) ++d; jointDepth[j] = d; }
+  std::vector<int> paramDepth(h.numParams, 0);
+  for (int r = 0; r < kParametersPerJoint * h.numJoints; ++r)
+    for (int k = h.ptOuter[r]; k < h.ptOuter[r + 1]; ++k) paramDepth[h.ptInner[k]] = std::max(paramDepth[h.ptInner[k]], jointDepth[r / kParametersPerJoint]);
+  std::vector<int> prio(enabledList.size());
+  for (size_t a = 0; a < enabledList.size(); ++a) prio[a] = paramDepth[enabledList[a]];
+  return prio;
+}
+
 static FunctionTables tables(const mb2_solver_function* f) {
   FunctionTables T{};
   const HostCharacter& h = f->ch->host;
@@ -468,7 +480,8 @@ int mb2_solver_solve(mb2_solver* s, float* params, double* errors, int32_t* iter
     const int ns0 = f->plan.numCols;
     std::vector<std::vector<int>> cliques(f->plan.units.size());
     for (const CellDesc& c : f->plan.cells) cliques[c.unit].push_back(int(c.col));
-    e = buildCholSchedule(ns0, cliques, cholMode == 2, sched);
+    const std::vector<int> prio = columnDepthPriority(f->ch->host, f->plan.enabledList);
+    e = buildCholSchedule(ns0, cliques, cholMode == 2, sched, &prio);
     if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
     std::vector<int32_t> colOrder;
     layoutDeviceColumns(sched, colOrder);
@@ -626,7 +639,8 @@ extern "C" int emu_gram_stats(mb2_solver_function* f) {
   CholSchedule sched;
   std::vector<std::vector<int>> cliques(f->plan.units.size());
   for (const CellDesc& c : f->plan.cells) cliques[c.unit].push_back(int(c.col));
-  e = buildCholSchedule(f->plan.numCols, cliques, false, sched);
+  const std::vector<int> prio = columnDepthPriority(f->ch->host, f->plan.enabledList);
+  e = buildCholSchedule(f->plan.numCols, cliques, false, sched, &prio);
   if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
   std::vector<int32_t> colOrder;
   layoutDeviceColumns(sched, colOrder);
@@ -644,6 +658,37 @@ extern "C" int emu_gram_stats(mb2_solver_function* f) {
               g.numStrips / 4, g.numTiles, g.pairA.size(), maxPairs, (long long)g.macs);
   std::printf("pairs per tile in order:");
   for (int ti = 0; ti < g.numTiles; ++ti) { const int t = g.tileOrder[ti]; std::printf(" %d", g.tilePairStart[t + 1] - g.tilePairStart[t]); }
+  std::printf("\n");
+  return MB2_OK;
+}
+
+extern "C" int emu_sched_structure(mb2_solver_function* f) {
+  std::string e = plan(f, true);
+  if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
+  CholSchedule s;
+  std::vector<std::vector<int>> cliques(f->plan.units.size());
+  for (const CellDesc& c : f->plan.cells) cliques[c.unit].push_back(int(c.col));
+  const std::vector<int> prio = columnDepthPriority(f->ch->host, f->plan.enabledList);
+  e = buildCholSchedule(f->plan.numCols, cliques, false, s, &prio);
+  if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
+  std::printf("levels %d tiles %d\n", s.numLevels, s.numTiles);
+  for (int L = 0; L < s.numLevels; ++L) { std::printf(" level %d:", L); for (int c = s.levelColStart[L]; c < s.levelColStart[L + 1]; ++c) std::printf(" %d", s.levelCols[c]); std::printf("\n"); }
+  const int T = s.numTileCols;
+  const HostCharacter& h = f->ch->host;
+  // parameter -> a joint it drives (first one)
+  std::vector<int> jointOf(h.numParams, -1);
+  for (int r = 0; r < 7 * h.numJoints; ++r)
+    for (int k = h.ptOuter[r]; k < h.ptOuter[r + 1]; ++k) if (jointOf[h.ptInner[k]] < 0) jointOf[h.ptInner[k]] = r / 7;
+  for (int K = 0; K < T; ++K) {
+    std::printf("tile col %2d: joints {", K);
+    int last = -2;
+    for (int j = 0; j < 16; ++j) { const int p = s.perm[16 * K + j]; if (p < 0) continue; const int jt = jointOf[f->plan.enabledList[p]]; if (jt != last) std::printf(" %d", jt); last = jt; }
+    std::printf(" }  rows below:");
+    for (int I = K + 1; I < T; ++I) if (s.tileIdTable[size_t(I) * T + K] >= 0) std::printf(" %d", I);
+    std::printf("\n");
+  }
+  std::printf("parents:");
+  for (int j = 0; j < h.numJoints; ++j) std::printf(" %d:%d", j, h.parent[j]);
   std::printf("\n");
   return MB2_OK;
 }
