@@ -28,9 +28,9 @@ __device__ __forceinline__ double warpSum(double v) {
   return v;
 }
 
-size_t sweepSmemPerInstance(const FunctionTables& T) {
+size_t sweepSmemPerInstance(const FunctionTables& T, int warpsPerInstance) {
   const size_t nPad = (T.numParams + 3) & ~3;
-  return sizeof(float) * (nPad + size_t(T.numJoints) * (kParametersPerJoint + kJointStateStride) + size_t(T.recStride) + 4);
+  return sizeof(float) * (nPad + size_t(T.numJoints) * (kParametersPerJoint + kJointStateStride) + size_t((T.recStride + 1) & ~1) + 4 + 2 * size_t(warpsPerInstance));
 }
 
 // The read-only tables (character + plan) are walked by dependent loads (cell -> unit -> contributions -> joint);
@@ -62,16 +62,23 @@ __global__ void __launch_bounds__(512) sweepKernel(const SweepArgs a) {
   extern __shared__ __align__(16) float smem[];
   FunctionTables T = a.T;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int warpsPerCta = blockDim.x >> 5;
+  // a group of W warps works on one instance: gl = lane within the group, gs = lanes of the group
+  const int W = a.warpsPerInstance, group = warp / W, gl = (warp % W) * 32 + lane, gs = 32 * W;
+  const int groupsPerCta = (blockDim.x >> 5) / W;
   const int nPad = (T.numParams + 3) & ~3;
-  const int perWarp = nPad + T.numJoints * (kParametersPerJoint + kJointStateStride) + T.recStride + 4;
-  float* th = smem + size_t(warp) * perWarp;
+  const int perGroup = nPad + T.numJoints * (kParametersPerJoint + kJointStateStride) + ((T.recStride + 1) & ~1) + 4 + 2 * W; // even: doubles stay aligned
+  float* th = smem + size_t(group) * perGroup;
   float* jp = th + nPad;
   float* js = jp + T.numJoints * kParametersPerJoint;
   float* rec = js + T.numJoints * kJointStateStride;
+  double* errSlots = reinterpret_cast<double*>(rec + ((T.recStride + 1) & ~1)); // W partial sums (8-byte aligned: every preceding size is even)
   const int numJointParams = T.numJoints * kParametersPerJoint;
+  auto groupSync = [&]() {
+    if (W == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(gs) : "memory");
+  };
   if (a.stageTables) {
-    uint32_t* cursor = reinterpret_cast<uint32_t*>(smem + ((size_t(warpsPerCta) * perWarp + 3) & ~size_t(3)));
+    uint32_t* cursor = reinterpret_cast<uint32_t*>(smem + ((size_t(groupsPerCta) * perGroup + 3) & ~size_t(3)));
     const size_t J = T.numJoints;
     stageTable(T.parent, J, cursor); stageTable(T.offset, 3 * J, cursor); stageTable(T.prerot, 4 * J, cursor);
     stageTable(T.ptOuter, 7 * J + 1, cursor); stageTable(T.ptInner, T.ptNnz, cursor); stageTable(T.ptVals, T.ptNnz, cursor);
@@ -82,21 +89,21 @@ __global__ void __launch_bounds__(512) sweepKernel(const SweepArgs a) {
     __syncthreads();
   }
 
-  for (int b = blockIdx.x * warpsPerCta + warp; b < a.batch; b += gridDim.x * warpsPerCta) {
-    if (a.active != nullptr && a.active[b] == 0) continue;
+  for (int b = blockIdx.x * groupsPerCta + group; b < a.batch; b += gridDim.x * groupsPerCta) {
+    if (a.active != nullptr && a.active[b] == 0) continue; // (the whole group skips together)
     const float* theta = a.theta + size_t(b) * a.ldTheta;
-    for (int i = lane; i < T.numParams; i += 32) th[i] = theta[i];
-    __syncwarp();
-    for (int row = lane; row < numJointParams; row += 32) jp[row] = jointParameterRow(T, row, th);
-    __syncwarp();
+    for (int i = gl; i < T.numParams; i += gs) th[i] = theta[i];
+    groupSync();
+    for (int row = gl; row < numJointParams; row += gs) jp[row] = jointParameterRow(T, row, th);
+    groupSync();
     for (int lvl = 0; lvl < T.numLevels; ++lvl) {
       const int end = T.levelStart[lvl + 1];
-      for (int k = T.levelStart[lvl] + lane; k < end; k += 32) fkJoint<kJacobian>(T, T.levelJoints[k], jp, js);
-      __syncwarp();
+      for (int k = T.levelStart[lvl] + gl; k < end; k += gs) fkJoint<kJacobian>(T, T.levelJoints[k], jp, js);
+      groupSync();
     }
     if (a.stateOut != nullptr) {
       float* so = a.stateOut + size_t(b) * T.numJoints * 8;
-      for (int i = lane; i < T.numJoints * 8; i += 32) so[i] = js[(i >> 3) * kJointStateStride + (i & 7)];
+      for (int i = gl; i < T.numJoints * 8; i += gs) so[i] = js[(i >> 3) * kJointStateStride + (i & 7)];
     }
     const float* targets = a.targets + size_t(b) * T.targetStride;
     const float* cw = a.cweights + (T.weightsPerInstance ? size_t(b) * T.numWeights : 0);
@@ -104,14 +111,18 @@ __global__ void __launch_bounds__(512) sweepKernel(const SweepArgs a) {
     // the residual is the last column of the device matrix, or follows the strips
     float* residual = kJacobian ? J + (T.stripMode ? size_t(T.residOff) : size_t(T.numCols) * T.ldJ) : nullptr;
     double err = 0.0;
-    for (int u = lane; u < T.numUnits; u += 32) err += (double)evalUnit<kJacobian>(T, u, th, jp, js, targets, cw, rec, residual);
-    __syncwarp();
-    if (kJacobian)
-      for (int c = lane; c < T.numCells; c += 32) jacobianCell(T, c, js, rec, targets, J);
+    for (int u = gl; u < T.numUnits; u += gs) err += (double)evalUnit<kJacobian>(T, u, th, jp, js, targets, cw, rec, residual);
     err = warpSum(err);
-    // getError() rounds through float (skeleton_solver_function.cpp:82); the Jacobian pass keeps double
-    if (lane == 0) a.errors[b] = kJacobian ? err : (double)(float)err;
-    __syncwarp();
+    if (W > 1 && lane == 0) errSlots[warp % W] = err;
+    groupSync();
+    if (kJacobian)
+      for (int c = gl; c < T.numCells; c += gs) jacobianCell(T, c, js, rec, targets, J);
+    if (gl == 0) {
+      if (W > 1) { err = 0.0; for (int w = 0; w < W; ++w) err += errSlots[w]; } // fixed order: deterministic
+      // getError() rounds through float (skeleton_solver_function.cpp:82); the Jacobian pass keeps double
+      a.errors[b] = kJacobian ? err : (double)(float)err;
+    }
+    groupSync();
   }
 }
 
@@ -121,25 +132,28 @@ static int g_maxSmemPerSm = 0;
 
 cudaError_t launchSweep(const SweepArgs& a0, bool jacobian, cudaStream_t stream) {
   SweepArgs a = a0;
-  const size_t per = sweepSmemPerInstance(a.T);
   const size_t tableBytes = sweepTableBytes(a.T) + 16;
   const size_t budget = size_t(g_maxSmemOptin);
-  // persistent CTAs: 16 warps (instances in flight) + the staged tables when they fit, else the tables stay in L2
-  int warps = 16;
-  a.stageTables = 1;
-  while (warps > 4 && per * warps + tableBytes > budget) warps >>= 1;
-  if (per * warps + tableBytes > budget) {
-    a.stageTables = 0;
-    warps = 8;
-    while (warps > 1 && per * warps > 100 * 1024) warps >>= 1;
-  }
-  const size_t smem = per * warps + (a.stageTables ? tableBytes : 0);
+  // Persistent CTAs of up to 16 warps. As many instances in flight as shared memory holds next to the staged tables (if those
+  // fit with at least two instances; else they stay in L2); when that is fewer than 16, several warps share one instance.
+  const size_t per1 = sweepSmemPerInstance(a.T, 8);
+  a.stageTables = (2 * per1 + tableBytes <= budget) ? 1 : 0;
+  int groups = int((budget - (a.stageTables ? tableBytes : 0)) / per1);
+  if (groups < 1) return cudaErrorInvalidConfiguration;
+  if (groups > 15) groups = 16; // one warp each (15 named barriers otherwise)
+  int W = 1;
+  while (W < 8 && groups * W * 2 <= 16) W *= 2;
+  if (W == 1) groups = groups > 16 ? 16 : groups;
+  a.warpsPerInstance = W;
+  const int warps = groups * W;
+  const size_t per = sweepSmemPerInstance(a.T, W);
+  const size_t smem = per * groups + 16 + (a.stageTables ? tableBytes : 0);
   if (smem > budget) return cudaErrorInvalidConfiguration;
   cudaError_t e;
   if (jacobian) e = cudaFuncSetAttribute(sweepKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   else e = cudaFuncSetAttribute(sweepKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
-  const int ctasNeeded = (a.batch + warps - 1) / warps;
+  const int ctasNeeded = (a.batch + groups - 1) / groups;
   int ctasPerSm = (int)((size_t(g_maxSmemPerSm)) / (smem + 1024));
   if (ctasPerSm < 1) ctasPerSm = 1;
   if (ctasPerSm * warps > 32) ctasPerSm = 32 / warps > 0 ? 32 / warps : 1;

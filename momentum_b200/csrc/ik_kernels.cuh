@@ -20,6 +20,7 @@ struct SweepArgs {           // K1 (FK + residual + Jacobian) and K4 (FK + error
   const int32_t* active;     // optional per-instance mask
   float* stateOut;           // optional [B][J][8]
   int32_t stageTables;       // set by launchSweep: copy the read-only tables into shared memory
+  int32_t warpsPerInstance;  // set by launchSweep: 1, 2, 4 or 8 warps share one instance (large rigs: few instances fit in shared memory)
 };
 
 struct JtJArgs {             // K2
@@ -84,7 +85,7 @@ cudaError_t launchGramTiles(const GramArgs& a, cudaStream_t stream);
 size_t gramTilesSmemBytes(size_t stripStride, int blobInts);
 
 cudaError_t launchSweep(const SweepArgs& a, bool jacobian, cudaStream_t stream);
-size_t sweepSmemPerInstance(const FunctionTables& T);
+size_t sweepSmemPerInstance(const FunctionTables& T, int warpsPerInstance);
 cudaError_t launchJtJSimt(const JtJArgs& a, cudaStream_t stream);
 cudaError_t launchCholesky(const CholArgs& a, cudaStream_t stream);
 // level-scheduled tile-sparse variant (ik_chol_sched.h); returns cudaErrorInvalidConfiguration when the tiles do not fit in shared memory
