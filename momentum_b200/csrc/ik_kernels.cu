@@ -57,13 +57,14 @@ __device__ __forceinline__ void stageTable(const E*& table, size_t count, uint32
   cursor += tableWords(count, sizeof(E));
 }
 
-template <bool kJacobian>
+template <bool kJacobian, int W>
 __global__ void __launch_bounds__(512) sweepKernel(const SweepArgs a) {
   extern __shared__ __align__(16) float smem[];
   FunctionTables T = a.T;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // a group of W warps works on one instance: gl = lane within the group, gs = lanes of the group
-  const int W = a.warpsPerInstance, group = warp / W, gl = (warp % W) * 32 + lane, gs = 32 * W;
+  const int group = warp / W, gl = (warp % W) * 32 + lane;
+  constexpr int gs = 32 * W;
   const int groupsPerCta = (blockDim.x >> 5) / W;
   const int nPad = (T.numParams + 3) & ~3;
   const int perGroup = nPad + T.numJoints * (kParametersPerJoint + kJointStateStride) + ((T.recStride + 1) & ~1) + 4 + 2 * W; // even: doubles stay aligned
@@ -149,10 +150,6 @@ cudaError_t launchSweep(const SweepArgs& a0, bool jacobian, cudaStream_t stream)
   const size_t per = sweepSmemPerInstance(a.T, W);
   const size_t smem = per * groups + 16 + (a.stageTables ? tableBytes : 0);
   if (smem > budget) return cudaErrorInvalidConfiguration;
-  cudaError_t e;
-  if (jacobian) e = cudaFuncSetAttribute(sweepKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-  else e = cudaFuncSetAttribute(sweepKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-  if (e != cudaSuccess) return e;
   const int ctasNeeded = (a.batch + groups - 1) / groups;
   int ctasPerSm = (int)((size_t(g_maxSmemPerSm)) / (smem + 1024));
   if (ctasPerSm < 1) ctasPerSm = 1;
@@ -160,10 +157,28 @@ cudaError_t launchSweep(const SweepArgs& a0, bool jacobian, cudaStream_t stream)
   int grid = g_numSms * ctasPerSm;
   if (grid > ctasNeeded) grid = ctasNeeded;
   if (grid < 1) grid = 1;
-  if (jacobian) sweepKernel<true><<<grid, warps * 32, smem, stream>>>(a);
-  else sweepKernel<false><<<grid, warps * 32, smem, stream>>>(a);
-  return cudaGetLastError();
+  auto launch = [&](auto kernel) -> cudaError_t {
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, warps * 32, smem, stream>>>(a);
+    return cudaGetLastError();
+  };
+  if (jacobian) {
+    switch (W) {
+      case 1: return launch(sweepKernel<true, 1>);
+      case 2: return launch(sweepKernel<true, 2>);
+      case 4: return launch(sweepKernel<true, 4>);
+      default: return launch(sweepKernel<true, 8>);
+    }
+  }
+  switch (W) {
+    case 1: return launch(sweepKernel<false, 1>);
+    case 2: return launch(sweepKernel<false, 2>);
+    case 4: return launch(sweepKernel<false, 4>);
+    default: return launch(sweepKernel<false, 8>);
+  }
 }
+
 
 // ------------------------------------------------------------------------------------------------
 // K2 (SIMT validation path): H[i][j] = sum_k J[k][cols[i]] J[k][cols[j]] for i >= j; g = J^T r.

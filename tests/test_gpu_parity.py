@@ -167,6 +167,30 @@ def test_cfg4_bodyhands_solve():
     parity.check_solve(ch, efs, theta0, opts, instances=[0, 5])
 
 
+def test_cfg5_mixed_rigs_on_concurrent_streams():
+    """cfg5: a mixed-rig batch is one solver function per rig; the handles are independent, so three rigs in flight on three CUDA
+    streams must give bit-identical results to running them one after the other (no shared mutable state between handles)."""
+    import torch
+
+    groups = [chain22_problem(), humanoid_problem(40, orientation=True)[:4], bodyhands_problem(4)]
+    opts = ms.GaussNewtonSolverOptions(min_iterations=1, max_iterations=6, threshold=1.0, regularization=0.05)
+    runs = []
+    for ch, efs, theta0, _ in groups:
+        fn = parity.build_function(ch, efs, theta0.shape[0])
+        runs.append((fn, ms.GaussNewtonSolver(opts, fn), theta0.astype(np.float32)))
+    sequential = [solver.solve(theta0.copy()) for _, solver, theta0 in runs]
+    streams = [torch.cuda.Stream() for _ in runs]
+    dev = [torch.from_numpy(theta0).cuda() for _, _, theta0 in runs]
+    torch.cuda.synchronize()
+    for (fn, solver, _), st, th in zip(runs, streams, dev):
+        solver.solve_device(th.data_ptr(), st.cuda_stream)  # no synchronisation in between: the three solves overlap
+    torch.cuda.synchronize()
+    for (fn, solver, _), th, ref in zip(runs, dev, sequential):
+        res = solver.get_results()
+        assert np.array_equal(th.cpu().numpy(), ref["params"])
+        assert np.array_equal(res["errors"], ref["errors"]) and np.array_equal(res["iterations"], ref["iterations"])
+
+
 def test_full_size_properties_cfg3_shard():
     """BASELINE cfg3 per-GPU shard (8192 x humanoid72, m=126): properties that need no oracle."""
     B = 8192
