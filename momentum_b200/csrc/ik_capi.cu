@@ -112,7 +112,7 @@ struct mb2_solver_function {
   DeviceBuffer<float> dLimitData;
   DeviceBuffer<int32_t> dEnabledList, dIdentity, dDeviceCols;
   // device data
-  DeviceBuffer<float> dTargets, dWeights, dJ, dTheta, dState, dH;
+  DeviceBuffer<float> dTargets, dWeights, dJ, dTheta, dState, dH, dTargetStage;
   DeviceBuffer<double> dErrors;
   std::vector<float> hWeights; // shared weights mirror
   std::unique_ptr<DeviceSchedule> sched; // Cholesky schedule of the current (compact) plan
@@ -640,8 +640,13 @@ static int setTargetsImpl(mb2_solver_function* f, int32_t index, const float* ta
   int rc = ensureTargets(f);
   if (rc != MB2_OK) return rc;
   float* dst = f->dTargets.p + ef.targetOff;
-  MB2_CUDA(cudaMemcpy2DAsync(dst, size_t(f->targetStride) * sizeof(float), targets, size_t(ef.targetSize) * sizeof(float),
-                             size_t(ef.targetSize) * sizeof(float), f->B, deviceSrc ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  const float* packed = targets;
+  if (!deviceSrc) { // one contiguous transfer, then a kernel spreads it into the per-instance records
+    MB2_CUDA(f->dTargetStage.resize(size_t(f->B) * ef.targetSize));
+    MB2_CUDA(cudaMemcpyAsync(f->dTargetStage.p, targets, size_t(f->B) * ef.targetSize * sizeof(float), cudaMemcpyHostToDevice, st));
+    packed = f->dTargetStage.p;
+  }
+  MB2_CUDA(launchScatterTargets(packed, dst, ef.targetSize, f->targetStride, f->B, st));
   if (ef.kind == 1 || ef.kind == 2) MB2_CUDA(launchNormalizeQuats(dst, 0, f->targetStride, ef.numConstraints(), f->B, st));
   return MB2_OK;
 }

@@ -707,6 +707,19 @@ __global__ void normalizeQuatsKernel(float* base, int count, int strideFloats, i
   const float n = sqrtf(p[0] * p[0] + p[1] * p[1] + p[2] * p[2] + p[3] * p[3]);
   p[0] /= n; p[1] /= n; p[2] /= n; p[3] /= n;
 }
+// packed [batch][size] -> records [batch][strideFloats] at dst (a strided 2-D copy from the host takes one DMA descriptor per row)
+__global__ void scatterTargetsKernel(const float* packed, float* dst, int size, int strideFloats, int batch) {
+  const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= size_t(batch) * size) return;
+  const size_t b = idx / size, k = idx % size;
+  dst[b * strideFloats + k] = packed[idx];
+}
+cudaError_t launchScatterTargets(const float* packed, float* dst, int size, int strideFloats, int batch, cudaStream_t stream) {
+  const size_t total = size_t(batch) * size;
+  if (total == 0) return cudaSuccess;
+  scatterTargetsKernel<<<unsigned((total + 255) / 256), 256, 0, stream>>>(packed, dst, size, strideFloats, batch);
+  return cudaGetLastError();
+}
 cudaError_t launchNormalizeQuats(float* base, int count, int strideFloats, int quatsPerRecord, int batch, cudaStream_t stream) {
   const int total = batch * quatsPerRecord;
   if (total == 0) return cudaSuccess;

@@ -118,6 +118,7 @@ struct BookkeepingArgs {
   int32_t iteration, minIterations, maxIterations; float threshold; int32_t* activeCount;
 };
 cudaError_t launchBookkeeping(const BookkeepingArgs& a, cudaStream_t stream);
+cudaError_t launchScatterTargets(const float* packed, float* dst, int size, int strideFloats, int batch, cudaStream_t stream);
 cudaError_t launchNormalizeQuats(float* base, int count, int strideFloats, int quatsPerRecord, int batch, cudaStream_t stream);
 
 } // namespace mb2
