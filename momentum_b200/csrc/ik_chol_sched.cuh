@@ -118,14 +118,11 @@ __device__ __forceinline__ void mmaTf32K8(float d[4], float a0, float a1, float 
 // d: running sums of the leading term, added in fp32 registers (round to nearest) after every step: the tensor core's own
 // accumulator truncates, which over a few hundred steps becomes a visible bias. small: the two correction terms, accumulated
 // inside the tensor core (they are 2^-11 of the result: their truncation does not matter); added to d once at the end.
-MB2_HD void gramTilePairs(const float* strips, int sa0, int sb0, int sa1, int sb1, int lane, float d[2][4], float small[2][4]) {
-  const float* A0 = strips + size_t(sa0) * 64;
-  const float* B0 = strips + size_t(sb0) * 64;
-  const float* A1 = strips + size_t(sa1) * 64;
-  const float* B1 = strips + size_t(sb1) * 64;
+// One k = 8 step of out += A B^T on the tensor cores with the three-term TF32 split (see gramTilePairs for the accuracy notes):
+// a0..a3 / b[h][0..1] are the raw fp32 fragment values of mma.m16n8k8 (A: rows g, g + 8 x k = t, t + 4; B: n = 8 h + g).
+// d += hi*hi in fp32 registers (round to nearest), small += lo*hi + hi*lo inside the tensor core.
 #if defined(__CUDA_ARCH__)
-  const float a0 = A0[lane], a1 = A0[32 + lane], a2 = A1[lane], a3 = A1[32 + lane];
-  const float b00 = B0[lane], b01 = B1[lane], b10 = B0[32 + lane], b11 = B1[32 + lane]; // b[h][k half]
+__device__ __forceinline__ void mma3xTf32Step(float d[2][4], float small[2][4], float a0, float a1, float a2, float a3, float b00, float b01, float b10, float b11) {
   const float a0h = tf32High(a0), a1h = tf32High(a1), a2h = tf32High(a2), a3h = tf32High(a3);
   const float b00h = tf32High(b00), b01h = tf32High(b01), b10h = tf32High(b10), b11h = tf32High(b11);
   const float a0l = a0 - a0h, a1l = a1 - a1h, a2l = a2 - a2h, a3l = a3 - a3h; // (the tensor core reads the leading bits of lo)
@@ -136,6 +133,26 @@ MB2_HD void gramTilePairs(const float* strips, int sa0, int sb0, int sa1, int sb
   mmaTf32K8(t0, a0h, a1h, a2h, a3h, b00h, b01h); mmaTf32K8(t1, a0h, a1h, a2h, a3h, b10h, b11h);
 #pragma unroll
   for (int e = 0; e < 4; ++e) { d[0][e] += t0[e]; d[1][e] += t1[e]; }
+}
+#endif
+// host emulation of the same step for one output: sum over the step's eight k of the split products
+MB2_HD void mma3xEmulate(float& d, float& small, const float av[8], const float bv[8]) {
+  float lo = 0.f, mid = 0.f, hi = 0.f;
+  for (int k = 0; k < 8; ++k) {
+    const float ah = tf32High(av[k]), bh = tf32High(bv[k]), al = av[k] - ah, bl = bv[k] - bh;
+    lo += al * bh; mid += ah * bl; hi += ah * bh;
+  }
+  small += lo + mid;
+  d += hi;
+}
+
+MB2_HD void gramTilePairs(const float* strips, int sa0, int sb0, int sa1, int sb1, int lane, float d[2][4], float small[2][4]) {
+  const float* A0 = strips + size_t(sa0) * 64;
+  const float* B0 = strips + size_t(sb0) * 64;
+  const float* A1 = strips + size_t(sa1) * 64;
+  const float* B1 = strips + size_t(sb1) * 64;
+#if defined(__CUDA_ARCH__)
+  mma3xTf32Step(d, small, A0[lane], A0[32 + lane], A1[lane], A1[32 + lane], B0[lane], B1[lane], B0[32 + lane], B1[32 + lane]); // b[h][k half]
 #else
   const int g = lane >> 2, t = lane & 3; // host emulation: the lane's eight outputs from the same three-term split
   for (int h = 0; h < 2; ++h)
@@ -331,33 +348,74 @@ MB2_HD void cholPanelSolve(float* tile, const float* diagW, int hl) {
   for (int c = 0; c < 16; ++c) tile[tileIdx(c, hl)] = x[c]; // transposed: T[c][r]
 }
 
-// ---- phase C: one update task, D(I,J) -= sum_pairs L(I,K) L(J,K)^T; a warp, lane = 2x4 block ----
-MB2_HD void cholUpdateTask(float* tiles, const CholSchedDev& S, int task, int lane) {
-  const int lr = lane >> 2, lc = lane & 3;
-  float acc[2][4];
+// ---- 16x16x16 tile products on the tensor cores (mma.sync m16n8k8, three-term TF32 split, fp32 accumulate) ----
+// out(r, c) += sum_k A(r, k) Bop(c, k); A is a panel tile in transposed storage TA[k][r]. B is either another panel tile
+// (kMajorB: TB[k][c]) or a row-major tile (W[c][k]). The k index of the fragments is permuted ({0,1,4,5} / {2,3,6,7} per step of 8)
+// so that the XOR-swizzled rows give conflict-free (k-major) or 2-way (row-major) shared-memory reads; any permutation is valid
+// as long as A and B use the same one. Lane's outputs follow the mma C layout: d[h][e] = out(g + 8 (e >> 1), 8 h + 2 t + (e & 1)).
+template <bool kMajorB>
+MB2_HD void tileProduct(const float* TA, const float* TB, int lane, float d[2][4], float small[2][4]) {
+  const int g = lane >> 2, t = lane & 3;
+#if defined(__CUDA_ARCH__)
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int p = S.taskPairStart[task]; p < S.taskPairStart[task + 1]; ++p) {
-    const float* A = tiles + size_t(S.pairA[p]) * 256;
-    const float* B = tiles + size_t(S.pairB[p]) * 256;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const float2 av = *reinterpret_cast<const float2*>(A + tileGrp(k, lr >> 1) + 2 * (lr & 1));
-      const float4 bv = *reinterpret_cast<const float4*>(B + tileGrp(k, lc));
-      acc[0][0] += av.x * bv.x; acc[0][1] += av.x * bv.y; acc[0][2] += av.x * bv.z; acc[0][3] += av.x * bv.w;
-      acc[1][0] += av.y * bv.x; acc[1][1] += av.y * bv.y; acc[1][2] += av.y * bv.z; acc[1][3] += av.y * bv.w;
+  for (int ks = 0; ks < 2; ++ks) {
+    const int k0 = 8 * ks + ((t & 1) | ((t & 2) << 1)), k1 = k0 + 2;
+    const float a0 = TA[tileIdx(k0, g)], a1 = TA[tileIdx(k0, g + 8)], a2 = TA[tileIdx(k1, g)], a3 = TA[tileIdx(k1, g + 8)];
+    float b00, b01, b10, b11;
+    if (kMajorB) { b00 = TB[tileIdx(k0, g)]; b01 = TB[tileIdx(k1, g)]; b10 = TB[tileIdx(k0, g + 8)]; b11 = TB[tileIdx(k1, g + 8)]; }
+    else { b00 = TB[tileIdx(g, k0)]; b01 = TB[tileIdx(g, k1)]; b10 = TB[tileIdx(g + 8, k0)]; b11 = TB[tileIdx(g + 8, k1)]; }
+    mma3xTf32Step(d, small, a0, a1, a2, a3, b00, b01, b10, b11);
+  }
+#else
+  for (int h = 0; h < 2; ++h)
+    for (int e = 0; e < 4; ++e) {
+      const int r = g + 8 * (e >> 1), c = 8 * h + 2 * t + (e & 1);
+      for (int ks = 0; ks < 2; ++ks) {
+        float av[8], bv[8];
+        for (int k = 0; k < 8; ++k) { av[k] = TA[tileIdx(8 * ks + k, r)]; bv[k] = kMajorB ? TB[tileIdx(8 * ks + k, c)] : TB[tileIdx(c, 8 * ks + k)]; }
+        mma3xEmulate(d[h][e], small[h][e], av, bv);
+      }
     }
-  }
-  float* D = tiles + size_t(S.taskDst[task]) * 256;
+#endif
+}
+
+// ---- phase B: X = A(I,K) L(K,K)^-T = A W^T for one panel tile, a warp per tile; the result replaces A (transposed storage) ----
+// split in two so that every lane has read the tile before any lane overwrites it (device: __syncwarp in between)
+MB2_HD void cholPanelProduct(const float* tile, const float* diagW, int lane, float out[2][4]) {
+  float small[2][4];
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    float4* dp = reinterpret_cast<float4*>(D + tileGrp(2 * lr + i, lc));
-    float4 v = *dp;
-    v.x -= acc[i][0]; v.y -= acc[i][1]; v.z -= acc[i][2]; v.w -= acc[i][3];
-    *dp = v;
-  }
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { out[h][e] = 0.f; small[h][e] = 0.f; }
+  tileProduct<false>(tile, diagW, lane, out, small);
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) out[h][e] += small[h][e];
+}
+MB2_HD void cholPanelStore(float* tile, int lane, const float out[2][4]) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) tile[tileIdx(8 * h + 2 * t + (e & 1), g + 8 * (e >> 1))] = out[h][e]; // T[c][r] = X(r, c)
+}
+
+// ---- phase C: one update task, D(I,J) -= sum_pairs L(I,K) L(J,K)^T; a warp per destination tile ----
+MB2_HD void cholUpdateTask(float* tiles, const CholSchedDev& S, int task, int lane) {
+  float d[2][4], small[2][4];
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { d[h][e] = 0.f; small[h][e] = 0.f; }
+  for (int p = S.taskPairStart[task]; p < S.taskPairStart[task + 1]; ++p)
+    tileProduct<true>(tiles + size_t(S.pairA[p]) * 256, tiles + size_t(S.pairB[p]) * 256, lane, d, small);
+  float* D = tiles + size_t(S.taskDst[task]) * 256;
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) D[tileIdx(g + 8 * (e >> 1), 8 * h + 2 * t + (e & 1))] -= d[h][e] + small[h][e]; // storage row = index of the A operand (the schedule orders each pair accordingly)
 }
 
 // ---- phase C (vector part): y_I -= sum L(I,K) y_K over this level's columns; lane hl = row ----

@@ -579,8 +579,12 @@ __global__ void __launch_bounds__(kSchedThreads, 3) choleskyScheduledKernel(cons
     __syncthreads();
     MB2_PROF(1)
     // B: panel tiles
-    if (!(a.profile & 0x200)) for (int pi = S.levelPanelStart[L] + hw; pi < S.levelPanelStart[L + 1]; pi += kSchedThreads / 16) {
-      cholPanelSolve(tiles + size_t(S.panelTile[pi]) * 256, tiles + size_t(S.panelDiag[pi]) * 256, hl);
+    if (!(a.profile & 0x200)) for (int pi = S.levelPanelStart[L] + warp; pi < S.levelPanelStart[L + 1]; pi += kSchedThreads / 32) {
+      float* ptile = tiles + size_t(S.panelTile[pi]) * 256;
+      float x[2][4];
+      cholPanelProduct(ptile, tiles + size_t(S.panelDiag[pi]) * 256, lane, x);
+      __syncwarp();
+      cholPanelStore(ptile, lane, x);
     }
     __syncthreads();
     MB2_PROF(2)

@@ -242,7 +242,11 @@ static int cholScheduledOne(const CholSchedDev& S, const float* Hs, int ldH, int
       for (int hl = 0; hl < 16; ++hl) cholDiagTile(tl + size_t(S.diagTile[K]) * 256, y + 16 * K, hl, 0xFFFFu, reg, &flag);
     }
     for (int pi = S.levelPanelStart[L]; pi < S.levelPanelStart[L + 1]; ++pi)
-      for (int hl = 0; hl < 16; ++hl) cholPanelSolve(tl + size_t(S.panelTile[pi]) * 256, tl + size_t(S.panelDiag[pi]) * 256, hl);
+    {
+      float x[32][2][4];
+      for (int lane = 0; lane < 32; ++lane) cholPanelProduct(tl + size_t(S.panelTile[pi]) * 256, tl + size_t(S.panelDiag[pi]) * 256, lane, x[lane]);
+      for (int lane = 0; lane < 32; ++lane) cholPanelStore(tl + size_t(S.panelTile[pi]) * 256, lane, x[lane]);
+    }
     for (int ti = S.levelTaskStart[L]; ti < S.levelTaskStart[L + 1]; ++ti)
       for (int lane = 0; lane < 32; ++lane) cholUpdateTask(tl, S, ti, lane);
     for (int vi = S.levelVTaskStart[L]; vi < S.levelVTaskStart[L + 1]; ++vi)
