@@ -123,12 +123,23 @@ std::string buildCholSchedule(int n, const std::vector<std::vector<int>>& clique
         for (size_t k = 1; k < col[j].size(); ++k) F.set(col[j][k], pj);
       }
     }
-    const bool alignSupernodes = std::getenv("MB2_SCHED_PACK") == nullptr;
     int fill = 0, start = 0; // greedy packing of supernodes into tiles
     int padded = 0;
+    auto closeTile = [&]() { if (fill != 0) { padded += kCholTile - fill; fill = 0; } };
     auto flushSupernode = [&](int first, int lastExcl) {
       const int sz = lastExcl - first;
-      if (alignSupernodes && sz <= kCholTile && fill + sz > kCholTile) { padded += kCholTile - fill; fill = 0; } // do not split: pad to the tile boundary
+      if (sz <= kCholTile) {
+        if (fill + sz > kCholTile) closeTile(); // do not split: pad to the tile boundary
+      } else {
+        // A chain longer than one tile is a sequence of dependent tile columns whatever we do: keep that sequence as short as
+        // possible by giving it whole tiles of its own, the partial one FIRST (its leading entries are the deepest joints, which
+        // depend on nothing outside the chain, so that tile still sits in an early level).
+        closeTile();
+        const int head = sz % kCholTile;
+        for (int j = first; j < first + head; ++j) { slot[j] = padded++; fill = (fill + 1) % kCholTile; }
+        closeTile();
+        first += head;
+      }
       for (int j = first; j < lastExcl; ++j) { slot[j] = padded++; fill = (fill + 1) % kCholTile; }
     };
     for (int j = 1; j <= n; ++j) {
