@@ -939,7 +939,6 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
     c.tilesIn = useGram ? s->dTiles.p : nullptr;
     c.tilesStride = tilesStride;
     c.profile = (it == 0 && getenv("MB2_CHOL_PROFILE") != nullptr) ? 1 : 0;
-    if (const char* ex = getenv("MB2_CHOL_EXPERIMENT")) c.profile |= atoi(ex) << 8; // timing experiments only (results invalid)
     recordPhaseStart(s, 2, st);
     if (useSchedule) MB2_CUDA(launchCholeskyScheduled(c, f->sched->dev, st));
     else MB2_CUDA(launchCholesky(c, st));

@@ -7,10 +7,10 @@
 // Panel tiles L(I,K) are stored TRANSPOSED once solved (T[c][r] = L[r][c]): update tasks then read
 // both operands along rows (float2 / float4), and the substitution phases read along rows too.
 //
-// Work is mapped to half-warps (one 16-row tile each) except the 16x16x16 update tasks (one warp,
-// each lane a 2x4 register block). Cross-lane steps (diagonal tile factorisation, the two 16x16
-// triangular solves) use width-16 shuffles on the device; the host build (tests/emu) runs the same
-// arithmetic serially so that the schedule and the tile algebra are validated without a GPU.
+// Diagonal tiles and the substitutions are mapped to half-warps (one 16-row tile each, width-16 shuffles); the 16x16x16
+// products (panel tiles, update tasks, the Gram kernel) are one warp each on mma.sync with the three-term TF32 split.
+// The host build (tests/emu) runs the same arithmetic lane by lane so that the schedule and the tile algebra are
+// validated without a GPU.
 #pragma once
 
 #include <cmath>
@@ -320,32 +320,6 @@ MB2_HD void cholDiagTile(float* tile, float* y16, int hl, unsigned hmask, float 
   }
   for (int i = 0; i < 16; ++i) for (int l = 0; l < 16; ++l) tile[tileIdx(i, l)] = W[i][l];
 #endif
-}
-
-// ---- phase B: X = A(I,K) L(K,K)^-T = A W^T for one panel tile; lane hl owns matrix row hl ----
-// (panel tiles are stored transposed from the start, so a lane reads and writes only its own column)
-MB2_HD void cholPanelSolve(float* tile, const float* diagW, int hl) {
-  float a[16], x[16];
-#pragma unroll
-  for (int c = 0; c < 16; ++c) a[c] = tile[tileIdx(c, hl)];
-#pragma unroll
-  for (int c = 0; c < 16; ++c) {
-    // row c of W (broadcast reads); W is lower triangular: only columns j <= c contribute
-    float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-    for (int g = 0; g <= (c >> 2); ++g) {
-      const float4 wv = *reinterpret_cast<const float4*>(diagW + tileGrp(c, g));
-      const float wr[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int j = 4 * g + q;
-        if (j <= c) { if (j & 1) s1 += a[j] * wr[q]; else s0 += a[j] * wr[q]; }
-      }
-    }
-    x[c] = s0 + s1;
-  }
-#pragma unroll
-  for (int c = 0; c < 16; ++c) tile[tileIdx(c, hl)] = x[c]; // transposed: T[c][r]
 }
 
 // ---- 16x16x16 tile products on the tensor cores (mma.sync m16n8k8, three-term TF32 split, fp32 accumulate) ----

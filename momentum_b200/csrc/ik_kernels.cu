@@ -574,12 +574,12 @@ __global__ void __launch_bounds__(kSchedThreads, 3) choleskyScheduledKernel(cons
     // A: diagonal tiles of this level (one half-warp each) + forward solve of their rhs block
     for (int ci = S.levelColStart[L] + hw; ci < S.levelColStart[L + 1]; ci += kSchedThreads / 16) {
       const int K = S.levelCols[ci];
-      if (!(a.profile & 0x400)) cholDiagTile(tiles + size_t(S.diagTile[K]) * 256, y + 16 * K, hl, hmask, a.regularization, flags);
+      cholDiagTile(tiles + size_t(S.diagTile[K]) * 256, y + 16 * K, hl, hmask, a.regularization, flags);
     }
     __syncthreads();
     MB2_PROF(1)
     // B: panel tiles
-    if (!(a.profile & 0x200)) for (int pi = S.levelPanelStart[L] + warp; pi < S.levelPanelStart[L + 1]; pi += kSchedThreads / 32) {
+    for (int pi = S.levelPanelStart[L] + warp; pi < S.levelPanelStart[L + 1]; pi += kSchedThreads / 32) {
       float* ptile = tiles + size_t(S.panelTile[pi]) * 256;
       float x[2][4];
       cholPanelProduct(ptile, tiles + size_t(S.panelDiag[pi]) * 256, lane, x);
@@ -589,13 +589,13 @@ __global__ void __launch_bounds__(kSchedThreads, 3) choleskyScheduledKernel(cons
     __syncthreads();
     MB2_PROF(2)
     // C: update tasks (warp each) and rhs updates (half-warp each)
-    if (!(a.profile & 0x100)) for (int ti = S.levelTaskStart[L] + warp; ti < S.levelTaskStart[L + 1]; ti += kSchedThreads / 32) cholUpdateTask(tiles, S, ti, lane);
-    if (!(a.profile & 0x2000)) for (int vi = S.levelVTaskStart[L] + hw; vi < S.levelVTaskStart[L + 1]; vi += kSchedThreads / 16) cholVectorTask(tiles, y, S, vi, hl);
+    for (int ti = S.levelTaskStart[L] + warp; ti < S.levelTaskStart[L + 1]; ti += kSchedThreads / 32) cholUpdateTask(tiles, S, ti, lane);
+    for (int vi = S.levelVTaskStart[L] + hw; vi < S.levelVTaskStart[L + 1]; vi += kSchedThreads / 16) cholVectorTask(tiles, y, S, vi, hl);
     __syncthreads();
     MB2_PROF(3)
   }
   for (int L = S.numLevels - 1; L >= 0; --L) {
-    if (!(a.profile & 0x1000)) for (int ci = S.levelColStart[L] + hw; ci < S.levelColStart[L + 1]; ci += kSchedThreads / 16) cholBackwardColumn(tiles, y, S, S.levelCols[ci], hl, hmask);
+    for (int ci = S.levelColStart[L] + hw; ci < S.levelColStart[L + 1]; ci += kSchedThreads / 16) cholBackwardColumn(tiles, y, S, S.levelCols[ci], hl, hmask);
     __syncthreads();
   }
   MB2_PROF(4)
