@@ -696,3 +696,36 @@ extern "C" int emu_sched_structure(mb2_solver_function* f) {
   std::printf("\n");
   return MB2_OK;
 }
+
+// schedule / Gram-plan figures of the solver plan (mode 2 planning of ik_capi.cu): out = {levels, tiles, tile columns, nPad, device
+// columns, strips, pairs, misaligned tile starts, odd pair lists, cells outside their strip}
+extern "C" int emu_plan_figures(mb2_solver_function* f, int64_t out[10]) {
+  std::string e = plan(f, true);
+  if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
+  CholSchedule s;
+  std::vector<std::vector<int>> cliques(f->plan.units.size());
+  for (const CellDesc& c : f->plan.cells) cliques[c.unit].push_back(int(c.col));
+  const std::vector<int> prio = columnDepthPriority(f->ch->host, f->plan.enabledList);
+  e = buildCholSchedule(f->plan.numCols, cliques, false, s, &prio);
+  if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
+  std::vector<int32_t> colOrder;
+  layoutDeviceColumns(s, colOrder);
+  for (int32_t& c : colOrder) if (c >= 0) c = f->plan.enabledList[c];
+  e = buildPlan(f->ch->host, f->efs, f->enabled, true, f->plan, &colOrder, true);
+  if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
+  std::vector<int32_t> cr0, crn, cc;
+  for (const CellDesc& c : f->plan.cells) { cr0.push_back(f->plan.units[c.unit].row0); crn.push_back(f->plan.units[c.unit].numRows); cc.push_back(int32_t(c.col)); }
+  GramPlan g;
+  e = buildGramPlan(s, cr0, crn, cc, f->plan.numRows, g);
+  if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
+  int64_t misaligned = 0, odd = 0, outside = 0;
+  for (int K = 0; K < s.numTileCols; ++K) misaligned += (s.perm[16 * K] < 0 || (s.perm[16 * K] & 3) != 0) ? 1 : 0;
+  for (int t = 0; t < s.numTiles; ++t) odd += (g.tilePairStart[t + 1] - g.tilePairStart[t]) & 1;
+  for (size_t i = 0; i < cc.size(); ++i) {
+    const int strip = int(g.cellStripOff[i] / 64), colInStrip = int(g.cellStripOff[i] % 64) / 4;
+    if (strip >= g.numStrips || g.stripCoord[2 * strip] != (cr0[i] & ~3) || g.stripCoord[2 * strip + 1] + colInStrip != cc[i]) ++outside;
+  }
+  out[0] = s.numLevels; out[1] = s.numTiles; out[2] = s.numTileCols; out[3] = s.nPad; out[4] = s.n; out[5] = g.numStrips; out[6] = int64_t(g.pairA.size());
+  out[7] = misaligned; out[8] = odd; out[9] = outside;
+  return MB2_OK;
+}

@@ -121,3 +121,24 @@ def test_chain22_cfg1():
     ch, efs, theta0, _ = chain22_problem()
     opts = ms.GaussNewtonSolverOptions(min_iterations=1, max_iterations=50, threshold=1.0, regularization=0.05)
     parity.check_solve(ch, efs, theta0, opts, EMU_LIB, param_tol=2e-4)
+
+
+def test_solver_plan_figures_humanoid_and_bodyhands():
+    """Host planning of the solver path: elimination order + tile schedule + device-column layout + Gram plan. Guards the
+    structural invariants the kernels rely on and the schedule quality reached in round 1 (levels / tiles of humanoid72)."""
+    import ctypes as C
+
+    from momentum_b200.problems import bodyhands_problem
+
+    for make, max_levels, max_tiles in ((lambda: humanoid_problem(2, orientation=True), 4, 55), (lambda: bodyhands_problem(2), 9, 130)):
+        ch, efs, _, _ = make()
+        fn = ms.SkeletonSolverFunction(ch, 2, efs, lib_path=EMU_LIB)
+        out = (C.c_int64 * 10)()
+        assert fn._L.emu_plan_figures(fn._h, out) == 0
+        levels, tiles, tile_cols, n_pad, dev_cols, strips, pairs, misaligned, odd, outside = list(out)
+        assert levels <= max_levels and tiles <= max_tiles, (levels, tiles)
+        assert n_pad == 16 * tile_cols and dev_cols >= ch.num_params and dev_cols <= ch.num_params + 3 * tile_cols
+        assert misaligned == 0  # every tile column starts on a device column that is a multiple of 4 (TMA box alignment)
+        assert odd == 0         # pair lists are consumed two at a time
+        assert outside == 0     # every Jacobian cell lands inside the strip of its (row quad, tile column)
+        assert strips > 0 and pairs >= strips
