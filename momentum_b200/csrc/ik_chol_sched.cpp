@@ -303,6 +303,14 @@ std::string buildGramPlan(const CholSchedule& s, const std::vector<int32_t>& cel
     out.tilePairStart[t + 1] = out.tilePairStart[t] + int(pairs[t].size());
     for (const auto& pr : pairs[t]) { out.pairA.push_back(pr.first); out.pairB.push_back(pr.second); }
   }
+  out.tileQuadStart.assign(s.numTiles + 1, 0);
+  for (int t = 0; t < s.numTiles; ++t) {
+    out.tileQuadStart[t + 1] = out.tileQuadStart[t] + (out.tilePairStart[t + 1] - out.tilePairStart[t]) / 2;
+    for (int p = out.tilePairStart[t]; p < out.tilePairStart[t + 1]; p += 2) {
+      out.quad.push_back(out.pairA[p] * 64); out.quad.push_back(out.pairB[p] * 64);
+      out.quad.push_back(out.pairA[p + 1] * 64); out.quad.push_back(out.pairB[p + 1] * 64);
+    }
+  }
   out.tileOrder.resize(s.numTiles);
   for (int t = 0; t < s.numTiles; ++t) out.tileOrder[t] = t;
   std::stable_sort(out.tileOrder.begin(), out.tileOrder.end(), [&](int a, int b) { return pairs[a].size() > pairs[b].size(); });
@@ -331,7 +339,7 @@ void makeGramBlob(const GramPlan& g, const CholSchedule& s, std::vector<int32_t>
   blob.clear();
   int k = 0;
   auto add = [&](const std::vector<int32_t>& v) { offsets[k++] = int32_t(blob.size()); blob.insert(blob.end(), v.begin(), v.end()); while (blob.size() % 4) blob.push_back(0); };
-  add(g.tileOrder); add(g.tilePairStart); add(g.pairA); add(g.pairB); add(g.colStripStart); add(g.colStrip);
+  add(g.tileOrder); add(g.tileQuadStart); add(g.quad); add(std::vector<int32_t>()); add(g.colStripStart); add(g.colStrip);
   std::vector<int32_t> stripRow(g.numStrips), info(s.numTiles);
   for (int i = 0; i < g.numStrips; ++i) stripRow[i] = g.stripCoord[2 * i];
   auto validOf = [&](int K) { int v = 0; while (v < kCholTile && s.perm[16 * K + v] >= 0) ++v; return v; };

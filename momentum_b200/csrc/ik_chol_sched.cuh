@@ -146,11 +146,11 @@ MB2_HD void mma3xEmulate(float& d, float& small, const float av[8], const float 
   d += hi;
 }
 
-MB2_HD void gramTilePairs(const float* strips, int sa0, int sb0, int sa1, int sb1, int lane, float d[2][4], float small[2][4]) {
-  const float* A0 = strips + size_t(sa0) * 64;
-  const float* B0 = strips + size_t(sb0) * 64;
-  const float* A1 = strips + size_t(sa1) * 64;
-  const float* B1 = strips + size_t(sb1) * 64;
+MB2_HD void gramTilePairs(const float* strips, int oa0, int ob0, int oa1, int ob1, int lane, float d[2][4], float small[2][4]) {
+  const float* A0 = strips + oa0; // float offsets of the four strips
+  const float* B0 = strips + ob0;
+  const float* A1 = strips + oa1;
+  const float* B1 = strips + ob1;
 #if defined(__CUDA_ARCH__)
   mma3xTf32Step(d, small, A0[lane], A0[32 + lane], A1[lane], A1[32 + lane], B0[lane], B1[lane], B0[32 + lane], B1[32 + lane]); // b[h][k half]
 #else
@@ -169,10 +169,17 @@ MB2_HD void gramTilePairs(const float* strips, int sa0, int sb0, int sa1, int sb
     }
 #endif
 }
-// pair lists are padded to even length (GramPlan), tables are staged in shared memory (broadcast reads)
-MB2_HD void gramTileAccumulate(const float* strips, const int32_t* pairA, const int32_t* pairB, int p0, int p1, int lane, float d[2][4]) {
+// quads: {A0, B0, A1, B1} float offsets per step (GramPlan::quad, pair lists padded to even length), staged in shared memory
+MB2_HD void gramTileAccumulate(const float* strips, const int32_t* quads, int q0, int q1, int lane, float d[2][4]) {
   float small[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-  for (int p = p0; p < p1; p += 2) gramTilePairs(strips, pairA[p], pairB[p], pairA[p + 1], pairB[p + 1], lane, d, small);
+  for (int q = q0; q < q1; ++q) {
+#if defined(__CUDA_ARCH__)
+    const int4 o = *reinterpret_cast<const int4*>(quads + 4 * q); // one broadcast read
+    gramTilePairs(strips, o.x, o.y, o.z, o.w, lane, d, small);
+#else
+    gramTilePairs(strips, quads[4 * q], quads[4 * q + 1], quads[4 * q + 2], quads[4 * q + 3], lane, d, small);
+#endif
+  }
 #pragma unroll
   for (int h = 0; h < 2; ++h)
 #pragma unroll
@@ -196,16 +203,23 @@ MB2_HD void gramTileStore(float* tile, const float d[2][4], int info, float lamb
     return;
   }
   const int g = lane >> 2, t = lane & 3;
+  const bool rowOk[2] = {g < vI, g + 8 < vI}; // the lane owns two rows and four columns: six comparisons instead of sixteen
+  bool colOk[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) colOk[i] = 8 * (i >> 1) + 2 * t + (i & 1) < vJ;
 #pragma unroll
   for (int h = 0; h < 2; ++h)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int r = g + 8 * (e >> 1), c = 8 * h + 2 * t + (e & 1);
-      float x = d[h][e];
-      if (r >= vI || c >= vJ) x = (diag && r == c) ? 1.f : 0.f;
-      else if (diag && r == c) x += lambda;
-      tile[off[4 * h + e]] = x;
-    }
+    for (int e = 0; e < 4; ++e) tile[off[4 * h + e]] = (rowOk[e >> 1] && colOk[2 * h + (e & 1)]) ? d[h][e] : 0.f;
+  if (diag) { // the lane's outputs on the diagonal: r == c <=> g (+8) == 8 h + 2 t (+1)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int r = g + 8 * (e >> 1), c = 8 * h + 2 * t + (e & 1);
+        if (r == c) tile[off[4 * h + e]] = (r < vI) ? d[h][e] + lambda : 1.f;
+      }
+  }
 }
 // entry hl of block K of J^T r: sum over the strips of tile column K of strip[hl][0..3] . r[4q..4q+3]
 MB2_HD float gramVectorEntry(const float* strips, const float* resid, const int32_t* colStrip, const int32_t* stripRow, int s0, int s1, int hl) {

@@ -74,6 +74,8 @@ struct GramPlan {
   std::vector<int32_t> tileOrder;     // tiles by decreasing pair count (work is dealt round-robin to warps in this order)
   std::vector<int32_t> tilePairStart; // [numTiles + 1] indexed by tile id
   std::vector<int32_t> pairA, pairB;  // strips of block row I / block column J of the tile
+  std::vector<int32_t> tileQuadStart; // [numTiles + 1] the same lists, two pairs per entry, as the kernel consumes them:
+  std::vector<int32_t> quad;          // [numQuads][4] float offsets {A0, B0, A1, B1} of the four strips (16-byte aligned records)
   std::vector<int32_t> colStripStart; // [numTileCols + 1]
   std::vector<int32_t> colStrip;      // strips of tile column K
   std::vector<uint32_t> cellStripOff; // per Jacobian cell: float offset of (first row quad, its column) in the strip buffer
@@ -86,7 +88,7 @@ struct GramPlan {
 std::string buildGramPlan(const CholSchedule& s, const std::vector<int32_t>& cellRow0, const std::vector<int32_t>& cellRows, const std::vector<int32_t>& cellCol,
                           int numRows, GramPlan& out);
 
-// The Gram tables as one int32 blob; offsets[8] = {tileOrder, tilePairStart, pairA, pairB, colStripStart, colStrip, stripRow, tileInfo}
+// The Gram tables as one int32 blob; offsets[8] = {tileOrder, tileQuadStart, quad, (unused), colStripStart, colStrip, stripRow, tileInfo}
 // (stripRow[s] = first row of strip s; tileInfo[t] = validI | validJ << 8 | diag << 16 of the schedule).
 void makeGramBlob(const GramPlan& g, const CholSchedule& s, std::vector<int32_t>& blob, int32_t offsets[8]);
 

@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(kGramThreads) gramTilesKernel(const GramArgs a
   for (int i = tid; i < a.blobInts; i += kGramThreads) tab[i] = __ldg(a.blob + i);
   __syncthreads();
   mbarWaitRelaxed(barAddr, 0);
-  const int32_t* tileOrder = tab + a.offTileOrder, *tilePairStart = tab + a.offTilePairStart, *pairA = tab + a.offPairA, *pairB = tab + a.offPairB;
+  const int32_t* tileOrder = tab + a.offTileOrder, *tileQuadStart = tab + a.offTilePairStart, *quads = tab + a.offPairA; // (blob tables are 16-byte aligned)
   const int32_t* colStripStart = tab + a.offColStripStart, *colStrip = tab + a.offColStrip, *stripRow = tab + a.offStripRow, *tileInfo = tab + a.offTileInfo;
   float* out = a.out + size_t(b) * a.outStride;
   int laneOff[8];
@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(kGramThreads) gramTilesKernel(const GramArgs a
     for (int i = 0; i < 2; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    gramTileAccumulate(strips, pairA, pairB, tilePairStart[t], tilePairStart[t + 1], lane, acc);
+    gramTileAccumulate(strips, quads, tileQuadStart[t], tileQuadStart[t + 1], lane, acc);
     gramTileStore(out + size_t(t) * 256, acc, tileInfo[t], a.regularization, lane, laneOff);
   }
   float* y = out + size_t(a.numTiles) * 256;
@@ -487,14 +487,16 @@ cudaError_t launchGramTiles(const GramArgs& a, cudaStream_t stream) {
 // One CTA per instance; tiles, right-hand side and scratch live in shared memory (<= ~64 KB for the
 // humanoid rig => several CTAs per SM hide each other's latencies).
 // ------------------------------------------------------------------------------------------------
-constexpr int kSchedThreads = 256;
+// 256 threads and three CTAs per SM when the tiles of one instance take a third of shared memory (humanoid-size rigs); 512 threads in
+// the single resident CTA when one instance needs more than half of it (body + hands)
 
 size_t choleskyScheduledSmemBytes(int n, int nPad, int numTiles, int blobInts) {
   return 1024 /*tile storage is aligned to the TMA swizzle atom*/ + sizeof(float) * (size_t(numTiles) * 256 + size_t(nPad) + 2 * size_t((n + 3) & ~3)) +
          sizeof(int32_t) * size_t((blobInts + 3) & ~3) + 32;
 }
 
-__global__ void __launch_bounds__(kSchedThreads, 3) choleskyScheduledKernel(const __grid_constant__ CUtensorMap hmap, const CholArgs a, const CholSchedDev Sg) {
+template <int kSchedThreads>
+__global__ void __launch_bounds__(kSchedThreads, kSchedThreads == 256 ? 3 : 1) choleskyScheduledKernel(const __grid_constant__ CUtensorMap hmap, const CholArgs a, const CholSchedDev Sg) {
   extern __shared__ __align__(16) float smemRaw[];
   const int b = blockIdx.x;
   if (a.active[b] == 0) return;
@@ -612,7 +614,9 @@ __global__ void __launch_bounds__(kSchedThreads, 3) choleskyScheduledKernel(cons
 cudaError_t launchCholeskyScheduled(const CholArgs& a, const CholSchedDev& sched, cudaStream_t stream) {
   const size_t smem = choleskyScheduledSmemBytes(a.ns, sched.nPad, sched.numTiles, sched.blobInts);
   if (smem > size_t(g_maxSmemOptin)) return cudaErrorInvalidConfiguration;
-  cudaError_t e = cudaFuncSetAttribute(choleskyScheduledKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  const bool wide = 2 * (smem + 1024) > size_t(g_maxSmemPerSm); // one CTA per SM anyway: give it 16 warps
+  cudaError_t e = wide ? cudaFuncSetAttribute(choleskyScheduledKernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))
+                       : cudaFuncSetAttribute(choleskyScheduledKernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
   if (a.tilesIn == nullptr && (a.g == nullptr || a.ldG != cholGradientLd(a.ns))) return cudaErrorInvalidValue;
   if ((a.ldH & 3) != 0 || (a.hStride & 3) != 0 || (a.tilesStride & 3) != 0) return cudaErrorInvalidValue;
@@ -623,7 +627,8 @@ cudaError_t launchCholeskyScheduled(const CholArgs& a, const CholSchedDev& sched
   const uint32_t box[3] = {16u, 16u, 1u};
   e = makeTensorMap3d(&hmap, fromGram ? a.tilesIn : a.H, dims, strides, box, 64);
   if (e != cudaSuccess) return e;
-  choleskyScheduledKernel<<<a.batch, kSchedThreads, smem, stream>>>(hmap, a, sched);
+  if (wide) choleskyScheduledKernel<512><<<a.batch, 512, smem, stream>>>(hmap, a, sched);
+  else choleskyScheduledKernel<256><<<a.batch, 256, smem, stream>>>(hmap, a, sched);
   return cudaGetLastError();
 }
 

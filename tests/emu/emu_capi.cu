@@ -196,7 +196,7 @@ static void gramOne(const mb2_solver_function* f, int b, const GramPlan& G, cons
     float* tile = out + size_t(t) * 256;
     for (int lane = 0; lane < 32; ++lane) {
       float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-      gramTileAccumulate(strips, G.pairA.data(), G.pairB.data(), G.tilePairStart[t], G.tilePairStart[t + 1], lane, acc);
+      gramTileAccumulate(strips, G.quad.data(), G.tileQuadStart[t], G.tileQuadStart[t + 1], lane, acc);
       int off[8];
       gramLaneOffsets(lane, off);
       gramTileStore(tile, acc, S.tileInfo[3 * t + 2], reg, lane, off);
