@@ -495,7 +495,9 @@ size_t choleskyScheduledSmemBytes(int n, int nPad, int numTiles, int blobInts) {
          sizeof(int32_t) * size_t((blobInts + 3) & ~3) + 32;
 }
 
-template <int kSchedThreads>
+// kProfile: per-phase cycle counters of block 0 (MB2_CHOL_PROFILE=1); a separate instantiation so that the production kernel does not
+// carry the counters in its register budget
+template <int kSchedThreads, bool kProfile>
 __global__ void __launch_bounds__(kSchedThreads, kSchedThreads == 256 ? 3 : 1) choleskyScheduledKernel(const __grid_constant__ CUtensorMap hmap, const CholArgs a, const CholSchedDev Sg) {
   extern __shared__ __align__(16) float smemRaw[];
   const int b = blockIdx.x;
@@ -511,7 +513,7 @@ __global__ void __launch_bounds__(kSchedThreads, kSchedThreads == 256 ? 3 : 1) c
   int* flags = reinterpret_cast<int*>(blob + ((Sg.blobInts + 3) & ~3));
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(flags + 2);
   long long pc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, pt = clock64();
-#define MB2_PROF(k) if (a.profile & 1) { const long long now = clock64(); pc[k] += now - pt; pt = now; }
+#define MB2_PROF(k) if constexpr (kProfile) { const long long now = clock64(); pc[k] += now - pt; pt = now; }
   // Prologue: everything this instance reads arrives asynchronously on one mbarrier -- the schedule tables and J^T r as 1-D
   // bulk copies, every stored tile as one TMA box (16 rows x 64 bytes of the row-major upper triangle of H, written
   // straight into the swizzled tile layout: SWIZZLE_64B is the XOR of tileIdx). No thread touches the data on the way in.
@@ -605,7 +607,7 @@ __global__ void __launch_bounds__(kSchedThreads, kSchedThreads == 256 ? 3 : 1) c
   __syncthreads();
   cholFinish(a, b, n, dsub, gsub, flags[0] != 0);
   MB2_PROF(5)
-  if ((a.profile & 1) && b == 0 && tid == 0)
+  if (kProfile && b == 0 && tid == 0)
     printf("chol-profile (cycles, block 0): blob %lld issue %lld wait %lld lambda %lld diag %lld panel %lld update %lld backward %lld finish %lld | levels %d tiles %d\n", pc[6], pc[7],
            pc[8], pc[0], pc[1], pc[2], pc[3], pc[4], pc[5], S.numLevels, S.numTiles);
 #undef MB2_PROF
@@ -615,8 +617,12 @@ cudaError_t launchCholeskyScheduled(const CholArgs& a, const CholSchedDev& sched
   const size_t smem = choleskyScheduledSmemBytes(a.ns, sched.nPad, sched.numTiles, sched.blobInts);
   if (smem > size_t(g_maxSmemOptin)) return cudaErrorInvalidConfiguration;
   const bool wide = 2 * (smem + 1024) > size_t(g_maxSmemPerSm); // one CTA per SM anyway: give it 16 warps
-  cudaError_t e = wide ? cudaFuncSetAttribute(choleskyScheduledKernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))
-                       : cudaFuncSetAttribute(choleskyScheduledKernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  const bool prof = (a.profile & 1) != 0;
+  cudaError_t e;
+  if (wide) e = prof ? cudaFuncSetAttribute(choleskyScheduledKernel<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))
+                     : cudaFuncSetAttribute(choleskyScheduledKernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  else e = prof ? cudaFuncSetAttribute(choleskyScheduledKernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))
+                : cudaFuncSetAttribute(choleskyScheduledKernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
   if (a.tilesIn == nullptr && (a.g == nullptr || a.ldG != cholGradientLd(a.ns))) return cudaErrorInvalidValue;
   if ((a.ldH & 3) != 0 || (a.hStride & 3) != 0 || (a.tilesStride & 3) != 0) return cudaErrorInvalidValue;
@@ -627,8 +633,10 @@ cudaError_t launchCholeskyScheduled(const CholArgs& a, const CholSchedDev& sched
   const uint32_t box[3] = {16u, 16u, 1u};
   e = makeTensorMap3d(&hmap, fromGram ? a.tilesIn : a.H, dims, strides, box, 64);
   if (e != cudaSuccess) return e;
-  if (wide) choleskyScheduledKernel<512><<<a.batch, 512, smem, stream>>>(hmap, a, sched);
-  else choleskyScheduledKernel<256><<<a.batch, 256, smem, stream>>>(hmap, a, sched);
+  if (wide && prof) choleskyScheduledKernel<512, true><<<a.batch, 512, smem, stream>>>(hmap, a, sched);
+  else if (wide) choleskyScheduledKernel<512, false><<<a.batch, 512, smem, stream>>>(hmap, a, sched);
+  else if (prof) choleskyScheduledKernel<256, true><<<a.batch, 256, smem, stream>>>(hmap, a, sched);
+  else choleskyScheduledKernel<256, false><<<a.batch, 256, smem, stream>>>(hmap, a, sched);
   return cudaGetLastError();
 }
 
