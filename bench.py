@@ -22,7 +22,6 @@ single-GPU configs.
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
