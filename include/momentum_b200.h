@@ -156,6 +156,17 @@ int32_t mb2_solver_function_jacobian_stride(const mb2_solver_function* f);
 int mb2_add_position_error_function(mb2_solver_function* f, float weight, float loss_alpha, float loss_c,
                                     int32_t num_constraints, const int32_t* parents, const float* offsets /*[nc*3]*/,
                                     const float* weights /*[nc]*/, int32_t* out_index);
+/* addErrorFunction(PlaneErrorFunctionT) — plane_error_function.h:20-101, .cpp:49-70: signed distance of T_parent * offset to the plane
+ * (normal, d), one residual row per constraint; above != 0 is the half-plane mode (only val < 0 is penalised). Per-instance targets
+ * (mb2_set_targets): [B][nc*4] = normal xyz (normalised as in PlaneDataT's ctor), d. kLegacyWeight = 1e-4 (.h:83). */
+int mb2_add_plane_error_function(mb2_solver_function* f, float weight, float loss_alpha, float loss_c, int32_t above,
+                                 int32_t num_constraints, const int32_t* parents, const float* offsets /*[nc*3]*/,
+                                 const float* weights /*[nc]*/, int32_t* out_index);
+/* addErrorFunction(ModelParametersErrorFunctionT) — model_parameters_error_function.h/.cpp: row sqrt(weight * kMotionWeight) * w_i *
+ * (theta_i - target_i) for every enabled parameter with target weight w_i > 0 (kMotionWeight = 1e-1, .h:61). Per-instance targets
+ * (mb2_set_targets): [B][numParams] target parameters; target_weights [numParams] is shared by the batch. */
+int mb2_add_model_parameters_error_function(mb2_solver_function* f, float weight, const float* target_weights /*[numParams]*/,
+                                            int32_t* out_index);
 /* addErrorFunction(OrientationErrorFunctionT / OrientationRotDiffErrorFunctionT) —
  * orientation_error_function.h:16-108; offsets are normalised as in OrientationDataT's ctor. */
 int mb2_add_orientation_error_function(mb2_solver_function* f, float weight, float loss_alpha, float loss_c,

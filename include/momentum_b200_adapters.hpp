@@ -111,6 +111,19 @@ class BatchedSkeletonSolverFunction {
     check(mb2_add_position_error_function(h_, weight, lossAlpha, lossC, int32_t(parents.size()), parents.data(), offsets.data(), weights.data(), &idx));
     return idx;
   }
+  // PlaneErrorFunctionT(character, above) + setConstraints; targets [B][nc*4] = normal, d per instance
+  int addPlaneErrorFunction(float weight, const std::vector<int32_t>& parents, const std::vector<float>& offsets, const std::vector<float>& weights,
+                            bool above = false, float lossAlpha = 2.f, float lossC = 1.f) {
+    int32_t idx = -1;
+    check(mb2_add_plane_error_function(h_, weight, lossAlpha, lossC, above, int32_t(parents.size()), parents.data(), offsets.data(), weights.data(), &idx));
+    return idx;
+  }
+  // ModelParametersErrorFunctionT + setTargetParameters (weights here, per-instance target parameters through setTargets)
+  int addModelParametersErrorFunction(float weight, const std::vector<float>& targetWeights) {
+    int32_t idx = -1;
+    check(mb2_add_model_parameters_error_function(h_, weight, targetWeights.data(), &idx));
+    return idx;
+  }
   int addOrientationErrorFunction(float weight, const std::vector<int32_t>& parents, const std::vector<float>& offsetsXYZW, const std::vector<float>& weights,
                                   bool rotDiff = false, float lossAlpha = 2.f, float lossC = 1.f) {
     int32_t idx = -1;

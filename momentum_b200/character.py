@@ -37,7 +37,7 @@ LOSS_WELSCH = float("-inf")
 ROTATION_MATRIX_DIFFERENCE, QUATERNION_LOG_MAP = 0, 1
 
 # error-function kinds (shared numbering with include/momentum_b200.h and oracle/ik_oracle.hpp)
-KIND_POSITION, KIND_ORIENTATION, KIND_ORIENTATION_ROTDIFF, KIND_STATE, KIND_LIMIT = range(5)
+KIND_POSITION, KIND_ORIENTATION, KIND_ORIENTATION_ROTDIFF, KIND_STATE, KIND_LIMIT, KIND_PLANE, KIND_MODEL_PARAMETERS = range(7)
 
 
 @dataclass
@@ -350,6 +350,36 @@ class LimitErrorFunction:
     kind: int = KIND_LIMIT
 
 
+@dataclass
+class PlaneErrorFunction:
+    """PlaneErrorFunctionT (plane_error_function.h:20-101, .cpp:49-70): signed distance of T_parent * offset to the plane
+    (normal, d), one row per constraint; ``above`` = half-plane mode (only penetration is penalised). ``targets`` [B, nc, 4] =
+    (normal xyz, d) per instance; normals are normalised on entry as in PlaneDataT's constructor."""
+
+    parents: np.ndarray
+    offsets: np.ndarray  # [nc,3]
+    weights: np.ndarray  # [nc]
+    targets: np.ndarray  # [B,nc,4]
+    above: bool = False
+    weight: float = 1.0
+    loss_alpha: float = LOSS_L2
+    loss_c: float = 1.0
+    kind: int = KIND_PLANE
+    kLegacyWeight = 1e-4  # plane_error_function.h:83
+
+
+@dataclass
+class ModelParametersErrorFunction:
+    """ModelParametersErrorFunctionT (model_parameters_error_function.h/.cpp): w_i (theta_i - target_i) on every enabled parameter
+    with target weight > 0, scaled by weight * kMotionWeight (1e-1). ``targets`` [B, n] per instance, ``target_weights`` [n] shared."""
+
+    target_weights: np.ndarray  # [n]
+    targets: np.ndarray  # [B,n]
+    weight: float = 1.0
+    kind: int = KIND_MODEL_PARAMETERS
+    kMotionWeight = 1e-1  # model_parameters_error_function.h:61
+
+
 def jacobian_size(character: Character, ef) -> int:
     """getJacobianSize() of each family (joint_error_function-inl.h:300-302,
     state_error_function.cpp:394-404, limit_error_function.cpp:1138-1161)."""
@@ -360,6 +390,10 @@ def jacobian_size(character: Character, ef) -> int:
     if ef.kind == KIND_STATE:
         active = int(np.count_nonzero((np.asarray(ef.pos_weights) != 0) | (np.asarray(ef.rot_weights) != 0)))
         return active * (6 if ef.rotation_error_type == QUATERNION_LOG_MAP else 12)
+    if ef.kind == KIND_PLANE:
+        return len(ef.parents)
+    if ef.kind == KIND_MODEL_PARAMETERS:  # model_parameters_error_function.cpp:93-95
+        return int(np.count_nonzero(np.asarray(ef.target_weights) > 0))
     if ef.kind == KIND_LIMIT:
         return sum(0 if l.type == LIMIT_MINMAX_JOINT_PASSIVE else (3 if l.type == LIMIT_ELLIPSOID else 1) for l in character.limits)
     raise ValueError(ef.kind)

@@ -351,7 +351,7 @@ int addBlock(mb2_solver_function* f, HostErrorFunction& ef, int32_t* outIndex) {
   ef.targetOff = f->targetStride;
   ef.weightOff = f->numWeights;
   f->targetStride += ef.targetSize;
-  if (ef.kind <= 2) {
+  if (ef.kind <= 2 || ef.kind == 5) {
     f->numWeights += ef.numConstraints();
     f->hWeights.insert(f->hWeights.end(), ef.weights.begin(), ef.weights.end());
     if (f->weightsPerInstance) return fail(MB2_ERR_UNSUPPORTED, "add all error functions before setting per-instance constraint weights");
@@ -574,6 +574,34 @@ int mb2_add_position_error_function(mb2_solver_function* f, float weight, float 
   return addBlock(f, ef, outIndex);
 }
 
+int mb2_add_plane_error_function(mb2_solver_function* f, float weight, float alpha, float c, int32_t above, int32_t nc, const int32_t* parents,
+                                 const float* offsets, const float* weights, int32_t* outIndex) {
+  MB2_CHECK(f != nullptr && nc >= 0 && (nc == 0 || (parents && offsets && weights)), "invalid plane constraints");
+  MB2_CHECK(c > 0.f, "Parameter c should be positive");
+  HostErrorFunction ef;
+  ef.kind = 5;
+  ef.weight = weight;
+  ef.lossAlpha = alpha;
+  ef.lossC = c;
+  ef.halfPlane = above != 0;
+  ef.parents.assign(parents, parents + nc);
+  for (int p : ef.parents) MB2_CHECK(p >= 0 && p < f->ch->host.numJoints, "constraint parent joint out of range");
+  ef.offsets.assign(offsets, offsets + 3 * size_t(nc));
+  ef.weights.assign(weights, weights + nc);
+  ef.targetSize = 4 * nc;
+  return addBlock(f, ef, outIndex);
+}
+
+int mb2_add_model_parameters_error_function(mb2_solver_function* f, float weight, const float* targetWeights, int32_t* outIndex) {
+  MB2_CHECK(f != nullptr && targetWeights != nullptr, "invalid model-parameter weights");
+  HostErrorFunction ef;
+  ef.kind = 6;
+  ef.weight = weight;
+  ef.paramWeights.assign(targetWeights, targetWeights + f->ch->host.numParams);
+  ef.targetSize = f->ch->host.numParams;
+  return addBlock(f, ef, outIndex);
+}
+
 int mb2_add_orientation_error_function(mb2_solver_function* f, float weight, float alpha, float c, int32_t rotDiff, int32_t nc,
                                        const int32_t* parents, const float* offsets, const float* weights, int32_t* outIndex) {
   MB2_CHECK(f != nullptr && nc >= 0 && (nc == 0 || (parents && offsets && weights)), "invalid orientation constraints");
@@ -665,7 +693,7 @@ int mb2_set_targets_device(mb2_solver_function* f, int32_t index, const float* t
 int mb2_set_constraint_weights(mb2_solver_function* f, int32_t index, const float* weights, int32_t perInstance) {
   MB2_CHECK(f != nullptr && index >= 0 && index < int(f->efs.size()) && weights, "invalid constraint weights");
   HostErrorFunction& ef = f->efs[index];
-  MB2_CHECK(ef.kind <= 2, "constraint weights apply to Position/Orientation error functions");
+  MB2_CHECK(ef.kind <= 2 || ef.kind == 5, "constraint weights apply to Position/Orientation/Plane error functions");
   MB2_CUDA(cudaSetDevice(f->ch->device));
   const int nc = ef.numConstraints();
   if (!perInstance) {

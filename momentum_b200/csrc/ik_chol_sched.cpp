@@ -4,6 +4,8 @@
 
 #include <algorithm>
 #include <map>
+#include <set>
+#include <tuple>
 
 namespace mb2 {
 
@@ -273,25 +275,32 @@ std::string buildGramPlan(const CholSchedule& s, const std::vector<int32_t>& cel
   out.numStrips = next;
   out.stripCoord.resize(size_t(next) * 2);
   std::vector<std::vector<int>> ofCol(T);
-  std::map<int, std::vector<int>> colsOfQuad;
   for (const auto& kv : stripId) {
     const int q = kv.first.first, K = kv.first.second;
     out.stripCoord[2 * kv.second] = 4 * q;
     out.stripCoord[2 * kv.second + 1] = s.perm[16 * K]; // first slot of a tile column is always a real device column
     ofCol[K].push_back(kv.second);
-    colsOfQuad[q].push_back(K);
+  }
+  // Pairs: tile (I,J) needs strip(q,I)^T strip(q,J) only when ONE row of quad q touches both tile columns. Rows of a unit share
+  // their columns, so the pairs of a quad are the union over the units with rows in it (one-row units packed into the same quad
+  // do not couple each other's columns: those products are exactly zero and their tiles need not exist).
+  std::map<int, std::set<int>> colsOfUnit; // keyed by the unit's first row
+  std::map<int, int> rowsOfUnit;
+  for (size_t i = 0; i < cellCol.size(); ++i) { colsOfUnit[cellRow0[i]].insert(s.pos[cellCol[i]] >> 4); rowsOfUnit[cellRow0[i]] = cellRows[i]; }
+  std::set<std::tuple<int, int, int>> quadPairs; // (quad, I, J), I >= J
+  for (const auto& kv : colsOfUnit) {
+    const int r0 = kv.first, r1 = r0 + rowsOfUnit[r0] - 1;
+    for (int q = r0 >> 2; q <= r1 >> 2; ++q)
+      for (int I : kv.second)
+        for (int J : kv.second)
+          if (I >= J) quadPairs.insert(std::make_tuple(q, I, J));
   }
   std::vector<std::vector<std::pair<int, int>>> pairs(s.numTiles);
-  for (const auto& kv : colsOfQuad) {
-    const int q = kv.first;
-    const std::vector<int>& cols = kv.second; // ascending
-    for (size_t a = 0; a < cols.size(); ++a)
-      for (size_t b = 0; b <= a; ++b) {
-        const int I = cols[a], J = cols[b];
-        const int t = s.tileIdTable[size_t(I) * T + J];
-        if (t < 0) return "Gram plan: a Jacobian row couples two tile columns whose tile is not in the schedule";
-        pairs[t].push_back({stripId[{q, I}], stripId[{q, J}]});
-      }
+  for (const auto& qp : quadPairs) {
+    const int q = std::get<0>(qp), I = std::get<1>(qp), J = std::get<2>(qp);
+    const int t = s.tileIdTable[size_t(I) * T + J];
+    if (t < 0) return "Gram plan: a Jacobian row couples two tile columns whose tile is not in the schedule";
+    pairs[t].push_back({stripId[{q, I}], stripId[{q, J}]});
   }
   out.residOff = out.numStrips * 64;
   out.stride = (out.residOff + ((numRows + 3) & ~3) + 63) / 64 * 64; // whole strips, so that "strip stride / 64" is the all-zero strip the kernel appends

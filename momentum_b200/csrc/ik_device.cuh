@@ -349,6 +349,36 @@ MB2_HD float evalUnit(const FunctionTables& T, int ui, const float* theta, const
       }
       return dot(td, td) * pwgt + rotationError * rwgt;
     }
+    case kUnitPlane: { // plane_error_function.cpp:49-70 through joint_error_function-inl.h (FuncDim = 1)
+      const float cw = cweights[u.weightIdx];
+      if (cw == 0.f) {
+        if (kJacobian) { r[0] = 0.f; for (int k = 0; k < 6; ++k) rc[k] = 0.f; }
+        return 0.f;
+      }
+      const float* ps = js + u.joint * kJointStateStride;
+      const F3 v = ld3(ps) + qrot(ld4(ps + 3), ps[7] * f3(u.f[0], u.f[1], u.f[2]));
+      const float* tg = targets + u.targetOff; // normal (not necessarily unit: PlaneDataT's ctor normalises), d
+      const float nlen = sqrtf(tg[0] * tg[0] + tg[1] * tg[1] + tg[2] * tg[2]);
+      const F3 nrm = f3(tg[0] / nlen, tg[1] / nlen, tg[2] / nlen);
+      float val = dot(v, nrm) - tg[3];
+      if (e.halfPlane && val > 0.f) val = 0.f;
+      const bool on = !e.halfPlane || val < 0.f;
+      const float sq = val * val;
+      if (!kJacobian) return cw * lossValue(e, sq) * e.weight;
+      const float w = cw * e.weight;
+      float ds = sqrtf(w * lossDeriv(e, sq));
+      r[0] = ds * val;
+      if (fabsf(ds) < 1e-9f || !on) ds = 0.f; // :216-223 tiny scale or all-zero dfdv: the row stays zero
+      rc[0] = v.x; rc[1] = v.y; rc[2] = v.z;
+      rc[3] = ds * nrm.x; rc[4] = ds * nrm.y; rc[5] = ds * nrm.z;
+      return w * lossValue(e, sq);
+    }
+    case kUnitModelParameter: { // model_parameters_error_function.cpp:38-58, 90-133; kMotionWeight = 1e-1 (.h:61)
+      const float pdiff = u.f[0] * (theta[u.i[0]] - targets[u.targetOff]);
+      const float scale = e.weight * 1e-1f;
+      if (kJacobian) { const float sw = sqrtf(scale); r[0] = pdiff * sw; rc[0] = sw; }
+      return pdiff * pdiff * scale;
+    }
     default: break;
   }
   // ---- limits (limit_error_function.cpp) ----
@@ -465,6 +495,13 @@ MB2_HD void jacobianCell(const FunctionTables& T, int ci, const float* js, const
       F3 acc = f3(0.f, 0.f, 0.f);
       for (int k = 0; k < c.contribCount; ++k) acc = acc + (pointDerivative(T, js, cb[k].joint, cb[k].dof, v) * ds) * cb[k].coef;
       out[MB2_ROW(0)] = acc.x; out[MB2_ROW(1)] = acc.y; out[MB2_ROW(2)] = acc.z;
+      break;
+    }
+    case kUnitPlane: {
+      const F3 v = ld3(rc);
+      F3 acc = f3(0.f, 0.f, 0.f);
+      for (int k = 0; k < c.contribCount; ++k) acc = acc + pointDerivative(T, js, cb[k].joint, cb[k].dof, v) * cb[k].coef;
+      out[MB2_ROW(0)] = dot(ld3(rc + 3), acc); // (sqrt(w loss') n)^T dv/dp
       break;
     }
     case kUnitOrientation:

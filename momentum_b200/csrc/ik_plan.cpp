@@ -58,6 +58,12 @@ int32_t jacobianBlockSize(const HostCharacter& ch, const HostErrorFunction& ef) 
       for (int j = 0; j < ch.numJoints; ++j) n += (ef.posW[j] != 0.f || ef.rotW[j] != 0.f) ? 1 : 0;
       return n * (ef.rotationErrorType == 1 ? 6 : 12);
     }
+    case 5: return ef.numConstraints(); // joint_error_function-inl.h:300-302 with FuncDim = 1
+    case 6: { // model_parameters_error_function.cpp:93-95
+      int n = 0;
+      for (float w : ef.paramWeights) n += w > 0.f ? 1 : 0;
+      return n;
+    }
     case 4: {
       int n = 0;
       for (const auto& l : ch.limits) {
@@ -86,6 +92,7 @@ static EfDesc makeEfDesc(const HostErrorFunction& ef) {
   d.posWgt = ef.posWgt;
   d.rotWgt = ef.rotWgt;
   d.kind = ef.kind;
+  d.halfPlane = ef.halfPlane ? 1 : 0;
   return d;
 }
 
@@ -186,6 +193,7 @@ std::string buildPlan(const HostCharacter& ch, const std::vector<HostErrorFuncti
         const int ui = int(out.units.size());
         out.units.push_back(u);
         row += u.numRows;
+        if (alignRowGroups) row = (row + 3) & ~3; // a multi-row unit owns its row quads (one-row units pack among themselves)
         rec += isPos ? 4 : 10;
         CellBuilder cb;
         for (int jnt = ef.parents[c]; jnt >= 0; jnt = ch.parent[jnt]) { // joint_error_function-inl.h:229-294
@@ -219,6 +227,7 @@ std::string buildPlan(const HostCharacter& ch, const std::vector<HostErrorFuncti
         const int ui = int(out.units.size());
         out.units.push_back(u);
         row += u.numRows;
+        if (alignRowGroups) row = (row + 3) & ~3;
         rec += lm ? 14 : 2;
         CellBuilder cb;
         for (int jnt = i; jnt >= 0; jnt = ch.parent[jnt]) { // state_error_function.cpp:486-555 (no enabledParameters gate)
@@ -231,6 +240,59 @@ std::string buildPlan(const HostCharacter& ch, const std::vector<HostErrorFuncti
         }
         flushCells(ui, cb);
       }
+    } else if (ef.kind == 5) { // Plane: a one-row position-type constraint (JointErrorFunctionT<T, PlaneDataT<T>, 1>)
+      for (int c = 0; c < ef.numConstraints(); ++c) {
+        if (ef.parents[c] < 0 || ef.parents[c] >= ch.numJoints) return "constraint parent joint out of range";
+        UnitDesc u{};
+        u.kind = kUnitPlane;
+        u.ef = int32_t(e);
+        u.joint = ef.parents[c];
+        u.row0 = row;
+        u.numRows = 1;
+        u.targetOff = ef.targetOff + 4 * c;
+        u.weightIdx = ef.weightOff + c;
+        u.recOff = rec;
+        u.extra = -1;
+        for (int k = 0; k < 3; ++k) u.f[k] = ef.offsets[size_t(3) * c + k];
+        const int ui = int(out.units.size());
+        out.units.push_back(u);
+        row += 1;
+        rec += 6; // world point, scaled normal
+        CellBuilder cb;
+        for (int jnt = ef.parents[c]; jnt >= 0; jnt = ch.parent[jnt]) { // joint_error_function-inl.h:229-294, NumPos = 1
+          const int pb = jnt * kParametersPerJoint;
+          for (int d = 0; d < 3; ++d)
+            if (active[pb + d]) cb.add(ch, pb + d, jnt, d, &enabled);
+          for (int d = 0; d < 3; ++d)
+            if (active[pb + 3 + d]) cb.add(ch, pb + 3 + d, jnt, 3 + d, &enabled);
+          if (active[pb + 6]) cb.add(ch, pb + 6, jnt, 6, &enabled);
+        }
+        flushCells(ui, cb);
+      }
+    } else if (ef.kind == 6) { // ModelParameters: rows are packed over the enabled parameters with weight > 0 (:113-123); the block
+      if (int(ef.paramWeights.size()) != n) return "model-parameter target weights must have one entry per parameter"; // keeps getJacobianSize rows
+      const int blockStart = row;
+      for (int i = 0; i < n; ++i) {
+        if (!(ef.paramWeights[i] > 0.f) || !enabled[i]) continue;
+        UnitDesc u{};
+        u.kind = kUnitModelParameter;
+        u.ef = int32_t(e);
+        u.joint = -1;
+        u.row0 = row;
+        u.numRows = 1;
+        u.targetOff = ef.targetOff + i;
+        u.weightIdx = -1;
+        u.recOff = rec;
+        u.extra = -1;
+        u.i[0] = i;
+        u.f[0] = ef.paramWeights[i];
+        const int ui = int(out.units.size());
+        out.units.push_back(u);
+        row += 1;
+        rec += 1;
+        staticCell(ui, i, ef.paramWeights[i]);
+      }
+      row = blockStart + jacobianBlockSize(ch, ef);
     } else if (ef.kind == 4) {
       for (const HostLimit& l : ch.limits) {
         if (l.type == 2) continue; // MinMaxJointPassive: no rows (limit_error_function.cpp:1051-1052)
@@ -342,6 +404,7 @@ std::string buildPlan(const HostCharacter& ch, const std::vector<HostErrorFuncti
         }
         out.units[ui].pad[0] = disabled ? 1 : 0;
         row += out.units[ui].numRows;
+        if (alignRowGroups && out.units[ui].numRows > 1) row = (row + 3) & ~3;
         rec += (l.type == 5) ? 4 : 1;
       }
     } else {

@@ -38,7 +38,7 @@ struct HostCharacter {
 };
 
 struct HostErrorFunction {
-  int32_t kind{0}; // 0 position, 1 orientation, 2 orientation rot-diff, 3 state, 4 limit
+  int32_t kind{0}; // 0 position, 1 orientation, 2 orientation rot-diff, 3 state, 4 limit, 5 plane, 6 model parameters
   float weight{1.f};
   float lossAlpha{2.f}, lossC{1.f};
   std::vector<int32_t> parents;
@@ -47,6 +47,8 @@ struct HostErrorFunction {
   int32_t rotationErrorType{0};
   float posWgt{1.f}, rotWgt{1.f};
   std::vector<float> posW, rotW;
+  bool halfPlane{false};            // plane: PlaneErrorFunctionT(above)
+  std::vector<float> paramWeights; // model parameters: targetWeights_ [numParams]
   // layout (assigned when added)
   int32_t targetOff{0}, targetSize{0}; // floats per instance
   int32_t weightOff{0};                // into the constraint-weight array

@@ -35,6 +35,8 @@ enum UnitKind : int32_t {
   kUnitLimitLinearJoint = 8, // :600-656
   kUnitLimitHalfPlane = 9,  // :658-699
   kUnitLimitEllipsoid = 10, // :701-785
+  kUnitPlane = 11,          // plane_error_function.cpp:49-70 (one row; half-plane mode clamps)
+  kUnitModelParameter = 12, // model_parameters_error_function.cpp:90-133 (one row per enabled parameter with target weight > 0)
 };
 
 enum LossType : int32_t { kLossL2 = 0, kLossL1 = 1, kLossCauchy = 2, kLossWelsch = 3, kLossGeneral = 4 };
@@ -46,8 +48,8 @@ struct EfDesc {
   float alpha;
   float invC2;
   float posWgt, rotWgt; // StateErrorFunctionT::posWgt_/rotWgt_
-  int32_t kind;         // 0 pos, 1 ori, 2 rotdiff, 3 state, 4 limit
-  int32_t pad;
+  int32_t kind;         // 0 pos, 1 ori, 2 rotdiff, 3 state, 4 limit, 5 plane, 6 model parameters
+  int32_t halfPlane;    // PlaneErrorFunctionT(above)
 };
 
 struct UnitDesc {

@@ -72,6 +72,21 @@ def chain_problem(J=6, B=3, seed=0, families=("position", "orientation", "state"
                                          rotation_error_type=mc.QUATERNION_LOG_MAP if logmap else mc.ROTATION_MATRIX_DIFFERENCE))
     if "limit" in families:
         efs.append(mc.LimitErrorFunction(weight=0.5, loss_alpha=loss[0], loss_c=loss[1]))
+    for fam in ("plane", "halfplane"):  # (after the original families: their random streams stay as they were)
+        if fam in families:
+            par = rng.integers(0, J, 4).astype(np.int32)
+            off = rng.uniform(-1, 1, (4, 3))
+            nrm = rng.normal(size=(B, 4, 3)) * rng.uniform(0.5, 2.0, (B, 4, 1))  # not unit length: PlaneDataT normalises
+            unit = nrm / np.linalg.norm(nrm, axis=-1, keepdims=True)
+            pts = mc.world_points(ch, theta_star, par, off)
+            d = np.sum(unit * pts, -1) + 0.2 * rng.normal(size=(B, 4))  # the plane passes near the reachable point, on either side
+            w = rng.uniform(0.5, 1.5, 4); w[2] = 0.0
+            efs.append(mc.PlaneErrorFunction(par, off, w, np.concatenate([nrm, d[..., None]], -1), above=(fam == "halfplane"), weight=0.8,
+                                             loss_alpha=loss[0], loss_c=loss[1]))
+    if "model_parameters" in families:
+        tw = rng.uniform(0.5, 1.5, n)
+        tw[rng.integers(0, n, max(1, n // 4))] = 0.0  # parameters without a target contribute no row
+        efs.append(mc.ModelParametersErrorFunction(tw, theta_star + 0.1 * rng.normal(size=(B, n)), weight=0.6))
     theta0 = rng.uniform(-0.3, 0.3, (B, n))
     return ch, efs, theta0, theta_star
 

@@ -55,6 +55,7 @@ CABI_SYMBOLS = [
     "mb2_character_destroy", "mb2_solver_function_create", "mb2_solver_function_destroy", "mb2_solver_function_num_parameters",
     "mb2_solver_function_actual_parameters", "mb2_solver_function_batch", "mb2_solver_function_jacobian_rows",
     "mb2_solver_function_jacobian_stride", "mb2_add_position_error_function", "mb2_add_orientation_error_function",
+    "mb2_add_plane_error_function", "mb2_add_model_parameters_error_function",
     "mb2_add_state_error_function", "mb2_add_limit_error_function", "mb2_set_error_function_weight", "mb2_set_targets",
     "mb2_set_targets_device", "mb2_set_constraint_weights", "mb2_solver_function_set_enabled_parameters", "mb2_solver_function_get_error",
     "mb2_solver_function_get_jacobian", "mb2_solver_function_get_jtjr", "mb2_solver_function_get_skeleton_state", "mb2_solver_create",
@@ -87,6 +88,9 @@ def load_library(path: Optional[str] = None):
     L.mb2_add_orientation_error_function.argtypes = [vp, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_int32, _ip, _fp, _fp, _ip]
     L.mb2_add_state_error_function.argtypes = [vp, C.c_float, C.c_int32, C.c_float, C.c_float, _fp, _fp, _ip]
     L.mb2_add_limit_error_function.argtypes = [vp, C.c_float, C.c_float, C.c_float, _ip]
+    if hasattr(L, "mb2_add_plane_error_function"):
+        L.mb2_add_plane_error_function.argtypes = [vp, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_int32, _ip, _fp, _fp, _ip]
+        L.mb2_add_model_parameters_error_function.argtypes = [vp, C.c_float, _fp, _ip]
     L.mb2_set_error_function_weight.argtypes = [vp, C.c_int32, C.c_float]
     L.mb2_set_targets.argtypes = [vp, C.c_int32, _fp]
     if hasattr(L, "mb2_set_targets_device"):
@@ -239,6 +243,13 @@ class SkeletonSolverFunction(_Base):
                                                              C.byref(idx)))
         elif ef.kind == mc.KIND_LIMIT:
             self._check(self._L.mb2_add_limit_error_function(self._h, ef.weight, alpha, ef.loss_c, C.byref(idx)))
+        elif ef.kind == mc.KIND_PLANE:
+            pa, pp = _i32(ef.parents); of, op = _f32(ef.offsets); w, wp = _f32(ef.weights)
+            self._check(self._L.mb2_add_plane_error_function(self._h, ef.weight, alpha, ef.loss_c, int(bool(ef.above)), len(pa), pp, op, wp, C.byref(idx)))
+        elif ef.kind == mc.KIND_MODEL_PARAMETERS:
+            tw, twp = _f32(ef.target_weights)
+            assert tw.size == self.character.num_params if hasattr(self, "character") else True
+            self._check(self._L.mb2_add_model_parameters_error_function(self._h, ef.weight, twp, C.byref(idx)))
         else:
             raise ValueError(ef.kind)
         self.error_functions.append(ef)

@@ -43,6 +43,8 @@ def lib():
         L.orc_fn_add_joint_ef.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, _ip, _dp, _dp, _dp]
         L.orc_fn_add_state_ef.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_double, _dp, _dp, _dp]
         L.orc_fn_add_limit_ef.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+        L.orc_fn_set_half_plane.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc_fn_add_model_parameters_ef.argtypes = [C.c_void_p, C.c_double, _dp, _dp]
         L.orc_fn_set_targets.argtypes = [C.c_void_p, C.c_int, _dp]
         L.orc_fn_set_cweights.argtypes = [C.c_void_p, C.c_int, _dp]
         L.orc_fn_set_weight.argtypes = [C.c_void_p, C.c_int, C.c_double]
@@ -118,6 +120,17 @@ class OracleFunction:
                 L.orc_fn_add_state_ef(self.fn, float(ef.weight), int(ef.rotation_error_type), float(ef.pos_wgt), float(ef.rot_wgt), pwp, rwp, tgp)
             elif k == 4:
                 L.orc_fn_add_limit_ef(self.fn, float(ef.weight), float(ef.loss_alpha), float(ef.loss_c))
+            elif k == 5:
+                pa, pp = _i(ef.parents)
+                cw, cwp = _d(ef.weights)
+                of, op = _d(ef.offsets)
+                tg, tgp = _d(np.asarray(ef.targets)[instance])
+                idx = L.orc_fn_add_joint_ef(self.fn, k, float(ef.weight), float(ef.loss_alpha), float(ef.loss_c), len(ef.parents), pp, cwp, op, tgp)
+                L.orc_fn_set_half_plane(self.fn, idx, int(bool(ef.above)))
+            elif k == 6:
+                tw, twp = _d(ef.target_weights)
+                tg, tgp = _d(np.asarray(ef.targets)[instance])
+                L.orc_fn_add_model_parameters_ef(self.fn, float(ef.weight), tgp, twp)
             else:
                 raise ValueError(k)
         self.n = character.num_params
@@ -137,7 +150,7 @@ class OracleFunction:
     def select_instance(self, b: int):
         L = lib()
         for idx, ef in enumerate(self.efs):
-            if ef.kind in (0, 1, 2, 3):
+            if ef.kind in (0, 1, 2, 3, 5, 6):
                 tg, tgp = _d(np.asarray(ef.targets)[b])
                 L.orc_fn_set_targets(self.fn, idx, tgp)
 
@@ -202,7 +215,7 @@ class OracleFunction:
         sl = instances if instances is not None else slice(0, B)
         tg_arrays, ptrs = [], (_dp * len(self.efs))()
         for idx, ef in enumerate(self.efs):
-            if ef.kind in (0, 1, 2, 3):
+            if ef.kind in (0, 1, 2, 3, 5, 6):
                 a = np.ascontiguousarray(np.asarray(ef.targets)[sl], np.float64)
                 assert a.shape[0] == B, (a.shape, B)
                 tg_arrays.append(a)

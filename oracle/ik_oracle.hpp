@@ -408,7 +408,10 @@ struct Mat {
 // ----------------------------------------------------------------------------------------------
 // Error functions (character_solver/skeleton_error_function.h:19-150 base contract)
 // ----------------------------------------------------------------------------------------------
-enum Kind { kPosition = 0, kOrientation = 1, kOrientationRotDiff = 2, kState = 3, kLimit = 4 };
+enum Kind { kPosition = 0, kOrientation = 1, kOrientationRotDiff = 2, kState = 3, kLimit = 4, kPlane = 5, kModelParameters = 6 };
+inline int funcDimOf(int kind) { return kind == kPosition ? 3 : kind == kPlane ? 1 : 9; } // JointErrorFunctionT<T, Data, FuncDim, NumVec, NumPos>
+inline int numVecOf(int kind) { return (kind == kPosition || kind == kPlane) ? 1 : 3; }
+inline int numPosOf(int kind) { return (kind == kPosition || kind == kPlane) ? 1 : 0; }
 enum RotationErrorType { RotationMatrixDifference = 0, QuaternionLogMap = 1 }; // state_error_function.h:17-32
 
 template <class T>
@@ -419,8 +422,11 @@ struct ErrorFunction {
   // joint-type constraints (error_function_types.h:34-44 ConstraintData: parent, float weight)
   std::vector<int> cparent;
   std::vector<float> cweight;
-  std::vector<T> coffset; // 3 (position) or 4 xyzw (orientation; normalised like OrientationDataT ctor)
-  std::vector<T> ctarget;
+  std::vector<T> coffset; // 3 (position, plane) or 4 xyzw (orientation; normalised like OrientationDataT ctor)
+  std::vector<T> ctarget; // 3 (position), 4 xyzw (orientation), or plane: unit normal xyz + d (PlaneDataT ctor normalises, plane_error_function.h:28-36)
+  bool halfPlane{false};  // PlaneErrorFunctionT(above): plane_error_function.h:54-61
+  // model parameters (model_parameters_error_function.h): per-parameter target and weight
+  std::vector<T> targetParameters, targetWeights;
   // state
   int rotErrType{RotationMatrixDifference};
   T posWgt{1}, rotWgt{1};
@@ -443,6 +449,12 @@ struct ErrorFunction {
         int n = 0;
         for (size_t i = 0; i < targetPosW.size(); ++i) n += (targetPosW[i] != 0 || targetRotW[i] != 0) ? 1 : 0;
         return n * (rotErrType == QuaternionLogMap ? 6 : 12);
+      }
+      case kPlane: return numConstraints();
+      case kModelParameters: { // model_parameters_error_function.cpp:93-95
+        int n = 0;
+        for (T w : targetWeights) n += w > 0 ? 1 : 0;
+        return n;
       }
       case kLimit: {
         int n = 0;
@@ -469,6 +481,17 @@ void evalJointFunction(const ErrorFunction<T>& ef, int c, const JointState<T>& s
     for (int r = 0; r < 3; ++r) for (int k = 0; k < 3; ++k) dfdv[0][r][k] = (r == k) ? T(1) : T(0);
     return;
   }
+  if (ef.kind == kPlane) { // plane_error_function.cpp:49-70
+    const V3<T> off{ef.coffset[3 * c], ef.coffset[3 * c + 1], ef.coffset[3 * c + 2]};
+    const V3<T> nrm{ef.ctarget[4 * c], ef.ctarget[4 * c + 1], ef.ctarget[4 * c + 2]};
+    v[0] = st.world.transformPoint(off);
+    T val = dot(v[0], nrm) - ef.ctarget[4 * c + 3];
+    if (ef.halfPlane && val > T(0)) val = T(0);
+    f[0] = val;
+    const bool on = !ef.halfPlane || val < T(0);
+    for (int k = 0; k < 3; ++k) dfdv[0][0][k] = on ? nrm[k] : T(0);
+    return;
+  }
   const Quat<T> off{ef.coffset[4 * c], ef.coffset[4 * c + 1], ef.coffset[4 * c + 2], ef.coffset[4 * c + 3]};
   const Quat<T> tgt{ef.ctarget[4 * c], ef.ctarget[4 * c + 1], ef.ctarget[4 * c + 2], ef.ctarget[4 * c + 3]};
   const M3<T> rotMat = toRotationMatrix(off);
@@ -493,7 +516,7 @@ void evalJointFunction(const ErrorFunction<T>& ef, int c, const JointState<T>& s
 // joint_error_function-inl.h:35-54 getError
 template <class T>
 double jointGetError(const Rig&, const ErrorFunction<T>& ef, const SkeletonState<T>& state) {
-  const int FuncDim = ef.kind == kPosition ? 3 : 9;
+  const int FuncDim = funcDimOf(ef.kind);
   const GeneralizedLoss<T> loss(ef.lossAlpha, ef.lossC);
   T f[9];
   V3<T> v[3];
@@ -512,9 +535,7 @@ double jointGetError(const Rig&, const ErrorFunction<T>& ef, const SkeletonState
 // joint_error_function-inl.h:179-297 getJacobian
 template <class T>
 double jointGetJacobian(const Rig& rig, const ErrorFunction<T>& ef, const SkeletonState<T>& state, Mat<T>& jac, int row0, T* residual, int& usedRows) {
-  const int FuncDim = ef.kind == kPosition ? 3 : 9;
-  const int NumVec = ef.kind == kPosition ? 1 : 3;
-  const int NumPos = ef.kind == kPosition ? 1 : 0;
+  const int FuncDim = funcDimOf(ef.kind), NumVec = numVecOf(ef.kind), NumPos = numPosOf(ef.kind);
   const GeneralizedLoss<T> loss(ef.lossAlpha, ef.lossC);
   usedRows = FuncDim * ef.numConstraints();
   T f[9];
@@ -532,7 +553,11 @@ double jointGetJacobian(const Rig& rig, const ErrorFunction<T>& ef, const Skelet
     const int rowIndex = row0 + FuncDim * c;
     for (int r = 0; r < FuncDim; ++r) residual[rowIndex + r] = derivScale * f[r];
     if (std::abs(derivScale - T(0)) < Eps<T>(1e-9, 1e-16)) continue; // :216-218
-    // (dfdv is never all-zero for the Position/Orientation families: :219-223 cannot trigger)
+    { // :219-223 all-zero dfdv (the clamped half plane): rows stay zero
+      bool any = false;
+      for (int jv = 0; jv < NumVec; ++jv) for (int r = 0; r < FuncDim; ++r) for (int k = 0; k < 3; ++k) any = any || dfdv[jv][r][k] != T(0);
+      if (!any) continue;
+    }
     int jnt = ef.cparent[c];
     while (jnt != kInvalid) { // :229-294
       const JointState<T>& js = state.jointState[jnt];
@@ -903,6 +928,39 @@ double limitGetJacobian(const Rig& rig, const ErrorFunction<T>& ef, const T* par
   return error;
 }
 
+// --- ModelParametersErrorFunctionT: model_parameters_error_function.cpp:38-58 (error), :90-133 (Jacobian); kMotionWeight = 1e-1 (.h:61)
+template <class T>
+double modelParametersGetError(const ErrorFunction<T>& ef, const T* params, int n) {
+  if (int(ef.targetParameters.size()) != n || int(ef.targetWeights.size()) != n) return 0.0;
+  const T kMotionWeight = T(1e-1);
+  double error = 0;
+  for (int i = 0; i < n; ++i)
+    if (ef.enabledParameters[i]) {
+      const T pdiff = ef.targetWeights[i] * (params[i] - ef.targetParameters[i]);
+      error += pdiff * pdiff;
+    }
+  return error * ef.weight * kMotionWeight;
+}
+template <class T>
+double modelParametersGetJacobian(const ErrorFunction<T>& ef, const T* params, int n, Mat<T>& jac, int row0, T* residual, int& usedRows) {
+  usedRows = 0;
+  if (int(ef.targetParameters.size()) != n || int(ef.targetWeights.size()) != n) return 0.0;
+  const T kMotionWeight = T(1e-1);
+  const float sWeight = std::sqrt(float(ef.weight * kMotionWeight)); // `const float sWeight` in the reference (:108)
+  int out = 0;
+  double error = 0;
+  for (int i = 0; i < n; ++i)
+    if (ef.enabledParameters[i] && ef.targetWeights[i] > 0) {
+      const T pdiff = ef.targetWeights[i] * (params[i] - ef.targetParameters[i]);
+      error += pdiff * pdiff;
+      residual[row0 + out] = pdiff * T(sWeight);
+      jac(row0 + out, i) = T(sWeight) * ef.targetWeights[i];
+      ++out;
+    }
+  usedRows = out;
+  return error * ef.weight * kMotionWeight;
+}
+
 // ----------------------------------------------------------------------------------------------
 // character_solver/skeleton_solver_function.{h,cpp} + solver/solver_function.{h,cpp}
 // ----------------------------------------------------------------------------------------------
@@ -948,6 +1006,7 @@ struct SkeletonSolverFunction {
       double e = 0;
       if (ef.kind == kState) e = stateGetError(*rig, ef, state);
       else if (ef.kind == kLimit) e = limitGetError(*rig, ef, params, state);
+      else if (ef.kind == kModelParameters) e = modelParametersGetError(ef, params, numParameters);
       else e = jointGetError(*rig, ef, state);
       error += e;
     }
@@ -965,6 +1024,7 @@ struct SkeletonSolverFunction {
     if (!(ef.weight > 0)) return 0.0;
     if (ef.kind == kState) return stateGetJacobian(*rig, ef, state, jac, row0, residual, actualRows);
     if (ef.kind == kLimit) return limitGetJacobian(*rig, ef, params, state, jac, row0, residual, actualRows);
+    if (ef.kind == kModelParameters) return modelParametersGetJacobian(ef, params, numParameters, jac, row0, residual, actualRows);
     return jointGetJacobian(*rig, ef, state, jac, row0, residual, actualRows);
   }
   // solver_function.cpp:22-71 default getJacobian (rows padded to 8)

@@ -37,19 +37,30 @@ std::vector<T> narrow(const double* p, size_t n) {
 }
 
 template <class T>
+void normalizePlanes(ErrorFunction<T>& ef) { // PlaneDataT ctor: normal(inNormal.normalized()) (plane_error_function.h:35)
+  for (size_t i = 0; i < ef.cparent.size(); ++i) {
+    T* p = &ef.ctarget[4 * i];
+    const T n = std::sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+    p[0] /= n; p[1] /= n; p[2] /= n;
+  }
+}
+
+template <class T>
 int addJointEf(FnHandle* h, int kind, double weight, double alpha, double c, int nc, const int* parents, const double* cw, const double* offsets, const double* targets) {
   ErrorFunction<T> ef;
   ef.kind = kind;
   ef.weight = T(weight);
   ef.lossAlpha = std::isinf(alpha) && alpha < 0 ? GeneralizedLoss<T>::kWelsch() : T(alpha);
   ef.lossC = T(c);
-  const int per = kind == kPosition ? 3 : 4;
+  const int per = kind == kPosition ? 3 : 4;                      // target record: 3 (position), 4 (orientation quaternion / plane normal + d)
+  const int perOff = (kind == kPosition || kind == kPlane) ? 3 : 4; // offset record
   ef.cparent.assign(parents, parents + nc);
   ef.cweight.resize(nc);
   for (int i = 0; i < nc; ++i) ef.cweight[i] = float(cw[i]);
-  ef.coffset = narrow<T>(offsets, size_t(nc) * per);
+  ef.coffset = narrow<T>(offsets, size_t(nc) * perOff);
   ef.ctarget = narrow<T>(targets, size_t(nc) * per);
-  if (kind != kPosition) { // OrientationDataT ctor normalises (orientation_error_function.h:33-35)
+  if (kind == kPlane) normalizePlanes(ef);
+  else if (kind != kPosition) { // OrientationDataT ctor normalises (orientation_error_function.h:33-35)
     for (int i = 0; i < nc; ++i) {
       for (std::vector<T>* arr : {&ef.coffset, &ef.ctarget}) {
         Quat<T> q{(*arr)[4 * i], (*arr)[4 * i + 1], (*arr)[4 * i + 2], (*arr)[4 * i + 3]};
@@ -71,6 +82,11 @@ void setTargetsFn(SkeletonSolverFunction<T>& fn, int idx, const double* t) {
     ef.targetState = narrow<T>(t, size_t(fn.rig->numJoints) * 8);
   } else if (ef.kind == kPosition) {
     ef.ctarget = narrow<T>(t, ef.cparent.size() * 3);
+  } else if (ef.kind == kPlane) {
+    ef.ctarget = narrow<T>(t, ef.cparent.size() * 4);
+    normalizePlanes(ef);
+  } else if (ef.kind == kModelParameters) {
+    ef.targetParameters = narrow<T>(t, size_t(fn.rig->numParams));
   } else {
     ef.ctarget = narrow<T>(t, ef.cparent.size() * 4);
     for (size_t i = 0; i < ef.cparent.size(); ++i) {
@@ -89,6 +105,7 @@ int targetSize(FnHandle* h, int idx) {
   auto& ef = get<T>(h).errorFunctions.at(idx);
   if (ef.kind == kState) return h->rig->numJoints * 8;
   if (ef.kind == kLimit) return 0;
+  if (ef.kind == kModelParameters) return h->rig->numParams;
   return int(ef.cparent.size()) * (ef.kind == kPosition ? 3 : 4);
 }
 
@@ -283,6 +300,27 @@ int orc_fn_add_joint_ef(void* fn, int kind, double weight, double alpha, double 
 int orc_fn_add_state_ef(void* fn, double weight, int rotErrType, double posWgt, double rotWgt, const double* posW, const double* rotW, const double* target) {
   FnHandle* h = static_cast<FnHandle*>(fn);
   return DISPATCH(h, addStateEf<float>(h, weight, rotErrType, posWgt, rotWgt, posW, rotW, target), addStateEf<double>(h, weight, rotErrType, posWgt, rotWgt, posW, rotW, target));
+}
+
+int orc_fn_set_half_plane(void* fn, int idx, int above) { // PlaneErrorFunctionT(character, above)
+  FnHandle* h = static_cast<FnHandle*>(fn);
+  if (h->dtype == 0) h->f->errorFunctions.at(idx).halfPlane = above != 0; else h->d->errorFunctions.at(idx).halfPlane = above != 0;
+  return 0;
+}
+int orc_fn_add_model_parameters_ef(void* fn, double weight, const double* targetParameters, const double* targetWeights) {
+  FnHandle* h = static_cast<FnHandle*>(fn);
+  auto add = [&](auto& f, auto tag) {
+    using T = decltype(tag);
+    ErrorFunction<T> ef;
+    ef.kind = kModelParameters;
+    ef.weight = T(weight);
+    ef.targetParameters = narrow<T>(targetParameters, size_t(h->rig->numParams));
+    ef.targetWeights = narrow<T>(targetWeights, size_t(h->rig->numParams));
+    f.addErrorFunction(ef);
+    if (h->enabledSet) f.setEnabledParameters(h->enabled);
+    return int(f.errorFunctions.size()) - 1;
+  };
+  return h->dtype == 0 ? add(*h->f, float()) : add(*h->d, double());
 }
 
 int orc_fn_add_limit_ef(void* fn, double weight, double alpha, double c) {

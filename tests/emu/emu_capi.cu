@@ -330,7 +330,7 @@ int32_t mb2_solver_function_jacobian_stride(const mb2_solver_function* f) {
 static int addBlock(mb2_solver_function* f, HostErrorFunction& ef, int32_t* outIndex) {
   ef.targetOff = f->targetStride; ef.weightOff = f->numWeights;
   f->targetStride += ef.targetSize;
-  if (ef.kind <= 2) { f->numWeights += ef.numConstraints(); f->weights.insert(f->weights.end(), ef.weights.begin(), ef.weights.end()); }
+  if (ef.kind <= 2 || ef.kind == 5) { f->numWeights += ef.numConstraints(); f->weights.insert(f->weights.end(), ef.weights.begin(), ef.weights.end()); }
   f->efs.push_back(ef);
   // re-layout targets (tests add all blocks before setting targets)
   f->targets.assign(size_t(f->B) * std::max(f->targetStride, 1), 0.f);
@@ -343,6 +343,21 @@ int mb2_add_position_error_function(mb2_solver_function* f, float weight, float 
   ef.kind = 0; ef.weight = weight; ef.lossAlpha = alpha; ef.lossC = c;
   ef.parents.assign(parents, parents + nc); ef.offsets.assign(offsets, offsets + 3 * size_t(nc)); ef.weights.assign(weights, weights + nc);
   ef.targetSize = 3 * nc;
+  return addBlock(f, ef, outIndex);
+}
+int mb2_add_plane_error_function(mb2_solver_function* f, float weight, float alpha, float c, int32_t above, int32_t nc, const int32_t* parents,
+                                 const float* offsets, const float* weights, int32_t* outIndex) {
+  HostErrorFunction ef;
+  ef.kind = 5; ef.weight = weight; ef.lossAlpha = alpha; ef.lossC = c; ef.halfPlane = above != 0;
+  ef.parents.assign(parents, parents + nc); ef.offsets.assign(offsets, offsets + 3 * size_t(nc)); ef.weights.assign(weights, weights + nc);
+  ef.targetSize = 4 * nc;
+  return addBlock(f, ef, outIndex);
+}
+int mb2_add_model_parameters_error_function(mb2_solver_function* f, float weight, const float* targetWeights, int32_t* outIndex) {
+  HostErrorFunction ef;
+  ef.kind = 6; ef.weight = weight;
+  ef.paramWeights.assign(targetWeights, targetWeights + f->ch->host.numParams);
+  ef.targetSize = f->ch->host.numParams;
   return addBlock(f, ef, outIndex);
 }
 int mb2_add_orientation_error_function(mb2_solver_function* f, float weight, float alpha, float c, int32_t rotDiff, int32_t nc, const int32_t* parents,

@@ -23,7 +23,8 @@ def _build_emu():
     subprocess.check_call(["make", "-C", EMU_DIR, "-s"])
 
 
-FAMS = [("position",), ("orientation",), ("state",), ("limit",), ("position", "orientation", "state", "limit")]
+FAMS = [("position",), ("orientation",), ("state",), ("limit",), ("position", "orientation", "state", "limit"), ("plane",), ("halfplane",),
+        ("model_parameters",), ("position", "limit", "plane", "halfplane", "model_parameters")]
 
 
 @pytest.mark.parametrize("fams", FAMS)
@@ -49,6 +50,26 @@ def test_single_iteration_enabled_subset():
     ch, efs, theta0, _ = chain_problem(J=6, B=2, seed=24)
     en = np.ones(ch.num_params, bool); en[[0, 2, 5, 8, ch.num_params - 1]] = False
     parity.check_single_iteration(ch, efs, theta0, EMU_LIB, enabled=en)
+
+
+def test_plane_and_model_parameters_with_enabled_subset_and_solve():
+    """The two 'next' error functions of SURVEY 8(f): Plane (half-plane mode included) and ModelParameters, with a disabled
+    parameter subset (ModelParameters packs its rows over the enabled parameters) and through a full solve."""
+    ch, efs, theta0, _ = chain_problem(J=6, B=3, seed=31, families=("position", "plane", "halfplane", "model_parameters"))
+    en = np.ones(ch.num_params, bool); en[[1, 4, 9]] = False
+    parity.check_single_iteration(ch, efs, theta0, EMU_LIB, enabled=en)
+    opts = ms.GaussNewtonSolverOptions(min_iterations=1, max_iterations=10, threshold=10.0, regularization=0.05)
+    parity.check_solve(ch, efs, theta0, opts, EMU_LIB, param_tol=2e-4)
+    parity.check_solve(ch, efs, theta0, opts, EMU_LIB, enabled=en, param_tol=2e-4)
+
+
+def test_all_families_on_the_tile_scheduled_path():
+    """Every error-function family at once through the strip layout / tile-sparse Gram / tile Cholesky: multi-row units own their row
+    quads, one-row units (limits, planes, model parameters) share quads without coupling each other's tile columns."""
+    ch, efs, theta0, ts = chain_problem(J=20, B=2, seed=33, families=("position", "orientation", "state", "limit", "plane", "halfplane", "model_parameters"))
+    theta0 = ts + 0.05 * theta0
+    opts = ms.GaussNewtonSolverOptions(min_iterations=1, max_iterations=5, threshold=1.0, regularization=0.05, cholesky_mode=ms.CHOLESKY_TILES_SPARSE)
+    parity.check_solve(ch, efs, theta0, opts, EMU_LIB, param_tol=3e-4)
 
 
 def test_humanoid_single_iteration():

@@ -71,6 +71,34 @@ def test_solve_with_tensor_core_jtj_matches_oracle():
     print("max rel param diff (3xTF32 JtJ)", worst)
 
 
+def test_plane_and_model_parameters_error_functions():
+    """PlaneErrorFunction (plain and half-plane) and ModelParametersErrorFunction on the device path."""
+    ch, efs, theta0, _ = chain_problem(J=6, B=5, seed=31, families=("position", "limit", "plane", "halfplane", "model_parameters"))
+    parity.check_single_iteration(ch, efs, theta0)
+    en = np.ones(ch.num_params, bool); en[[1, 4, 9]] = False
+    parity.check_single_iteration(ch, efs, theta0, enabled=en)
+    opts = ms.GaussNewtonSolverOptions(min_iterations=1, max_iterations=10, threshold=10.0, regularization=0.05)
+    parity.check_solve(ch, efs, theta0, opts, param_tol=2e-4)
+    parity.check_solve(ch, efs, theta0, opts, enabled=en, param_tol=2e-4)
+    # on the tile-scheduled path (>= 48 parameters): floor planes + a pose prior on the humanoid
+    ch, efs, theta0, theta_star = humanoid_problem(8, orientation=True)
+    rng = np.random.default_rng(5)
+    feet = np.array([60, 61, 65, 66], np.int32)
+    off = rng.uniform(-1, 1, (4, 3))
+    pts = mc.world_points(ch, theta_star, feet, off)
+    nrm = np.tile(np.array([0.0, 1.0, 0.0]), (8, 4, 1))
+    d = pts[..., 1] + 0.5 * rng.normal(size=(8, 4))
+    efs.append(mc.PlaneErrorFunction(feet, off, np.ones(4), np.concatenate([nrm, d[..., None]], -1), above=True, weight=mc.PlaneErrorFunction.kLegacyWeight))
+    efs.append(mc.ModelParametersErrorFunction(np.where(np.arange(ch.num_params) % 3 == 0, 1.0, 0.0), 0.9 * theta_star, weight=1e-3))
+    opts = ms.GaussNewtonSolverOptions(min_iterations=1, max_iterations=8, threshold=1.0, regularization=0.05)
+    parity.check_solve(ch, efs, theta0, opts, instances=[0, 3, 7])
+    # every family at once on the tile path (one-row units share row quads)
+    ch, efs, theta0, ts = chain_problem(J=20, B=3, seed=33, families=("position", "orientation", "state", "limit", "plane", "halfplane", "model_parameters"))
+    theta0 = ts + 0.05 * theta0
+    opts = ms.GaussNewtonSolverOptions(min_iterations=1, max_iterations=5, threshold=1.0, regularization=0.05, cholesky_mode=ms.CHOLESKY_TILES_SPARSE)
+    parity.check_solve(ch, efs, theta0, opts, param_tol=3e-4)
+
+
 def test_solve_jtj_paths_into_the_tile_cholesky():
     """The tile-scheduled Cholesky fed three ways: tile-sparse Gram (default and on request), dense SIMT JtJ through TMA boxes."""
     B = 16

@@ -9,7 +9,8 @@ from momentum_b200 import character as mc
 from oracle.binding import OracleFunction
 from momentum_b200.problems import chain_problem, humanoid_problem
 
-FAMS = [("position",), ("orientation",), ("state",), ("limit",), ("position", "orientation", "state", "limit")]
+FAMS = [("position",), ("orientation",), ("state",), ("limit",), ("position", "orientation", "state", "limit"), ("plane",), ("halfplane",),
+        ("model_parameters",), ("position", "plane", "halfplane", "model_parameters")]
 
 
 def _check(ch, efs, theta, enabled=None, l2=True):
