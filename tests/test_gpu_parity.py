@@ -77,7 +77,9 @@ def test_plane_and_model_parameters_error_functions():
     parity.check_single_iteration(ch, efs, theta0)
     en = np.ones(ch.num_params, bool); en[[1, 4, 9]] = False
     parity.check_single_iteration(ch, efs, theta0, enabled=en)
-    opts = ms.GaussNewtonSolverOptions(min_iterations=1, max_iterations=10, threshold=10.0, regularization=0.05)
+    # fixed iteration count: the relative-change stop (solver.cpp:98-101) sits at the float rounding floor on this fixture, so the
+    # iteration at which it fires is not comparable between two float implementations
+    opts = ms.GaussNewtonSolverOptions(min_iterations=8, max_iterations=8, threshold=10.0, regularization=0.05)
     parity.check_solve(ch, efs, theta0, opts, param_tol=2e-4)
     parity.check_solve(ch, efs, theta0, opts, enabled=en, param_tol=2e-4)
     # on the tile-scheduled path (>= 48 parameters): floor planes + a pose prior on the humanoid
