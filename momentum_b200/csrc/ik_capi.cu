@@ -663,6 +663,7 @@ int mb2_set_error_function_weight(mb2_solver_function* f, int32_t index, float w
 static int setTargetsImpl(mb2_solver_function* f, int32_t index, const float* targets, bool deviceSrc, cudaStream_t st) {
   MB2_CHECK(f != nullptr && index >= 0 && index < int(f->efs.size()) && targets, "invalid targets");
   const HostErrorFunction& ef = f->efs[index];
+  if (ef.targetSize == 0 && ef.kind != 4) return MB2_OK; // a block without constraints: nothing to send (setConstraints({}) in the reference)
   MB2_CHECK(ef.targetSize > 0, "this error function has no per-instance targets");
   MB2_CUDA(cudaSetDevice(f->ch->device));
   int rc = ensureTargets(f);

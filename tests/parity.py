@@ -104,3 +104,30 @@ def check_solve(ch, efs, theta0, opts: ms.GaussNewtonSolverOptions, lib_path=Non
             dis = ~np.asarray(enabled, bool)
             assert np.array_equal(out["params"][b][dis], np.asarray(theta0[b], np.float32)[dis])
     return out, worst
+
+
+def check_edge_cases(lib_path=None):
+    """Degenerate inputs the reference accepts: an error function without constraints, a zero-weight block (no rows:
+    skeleton_solver_function.cpp:228-230), all constraint weights zero (joint_error_function-inl.h:197-199), a batch of one,
+    a single enabled parameter."""
+    from momentum_b200.problems import chain_problem
+
+    ch, efs, theta0, _ = chain_problem(J=5, B=1, seed=41, families=("position", "orientation", "limit"))
+    n = ch.num_params
+    empty = mc.PositionErrorFunction(np.zeros(0, np.int32), np.zeros((0, 3)), np.zeros(0), np.zeros((1, 0, 3)), weight=1.0)
+    off_block = mc.OrientationErrorFunction(efs[1].parents, efs[1].offsets, efs[1].weights, efs[1].targets, weight=0.0)
+    # (a) empty block + zero-weight block next to real ones, batch of one
+    mixed = [efs[0], empty, off_block, efs[2]]
+    check_single_iteration(ch, mixed, theta0, lib_path)
+    opts = ms.GaussNewtonSolverOptions(min_iterations=4, max_iterations=4, threshold=1.0, regularization=0.05)
+    check_solve(ch, mixed, theta0, opts, lib_path, param_tol=2e-4)
+    # (b) every constraint weight zero: no error, zero Jacobian, the step is exactly zero
+    dead = mc.PositionErrorFunction(efs[0].parents, efs[0].offsets, np.zeros_like(np.asarray(efs[0].weights)), efs[0].targets, weight=1.0)
+    fn = build_function(ch, [dead], 1, lib_path)
+    assert fn.get_error(theta0)[0] == 0.0
+    out = ms.GaussNewtonSolver(opts, fn).solve(theta0)
+    assert np.array_equal(out["params"], theta0.astype(np.float32)) and out["errors"][0] == 0.0
+    # (c) a single enabled parameter
+    en = np.zeros(n, bool); en[4] = True
+    check_single_iteration(ch, [efs[0]], theta0, lib_path, enabled=en)
+    check_solve(ch, [efs[0]], theta0, opts, lib_path, enabled=en, param_tol=2e-4)

@@ -72,6 +72,10 @@ def test_all_families_on_the_tile_scheduled_path():
     parity.check_solve(ch, efs, theta0, opts, EMU_LIB, param_tol=3e-4)
 
 
+def test_edge_cases_empty_and_degenerate_inputs():
+    parity.check_edge_cases(EMU_LIB)
+
+
 def test_humanoid_single_iteration():
     ch, efs, theta0, theta_star = humanoid_problem(2, orientation=True)
     th = (theta0 + 0.3 * theta_star).astype(np.float32)

@@ -38,6 +38,10 @@ def test_single_iteration_enabled_subset():
     parity.check_single_iteration(ch, efs, theta0, enabled=en)
 
 
+def test_edge_cases_empty_and_degenerate_inputs():
+    parity.check_edge_cases()
+
+
 def test_humanoid_single_iteration():
     ch, efs, theta0, theta_star = humanoid_problem(40, orientation=True)
     th = (theta0 + 0.3 * theta_star).astype(np.float32)
