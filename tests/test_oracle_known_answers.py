@@ -113,3 +113,44 @@ def test_ka5_block_jtj_equivalence_with_noncontiguous_enabled_subset(dtype, use_
         results.append((err, p))
     assert abs(results[0][0] - results[1][0]) <= 1e-6
     assert np.max(np.abs(results[0][1] - results[1][1])) <= 1e-4
+
+
+@pytest.mark.parametrize("dtype,rtol", [("float32", 1e-6), ("float64", 1e-10)])
+def test_ka7_plane_jacobian_with_zero_function_value(dtype, rtol):
+    """plane_error_function_test.cpp:115-159 (PlaneErrorL2_JacobianWithZeroFunctionValue): the point lies exactly on the plane, so the
+    error and the residual vanish while the Jacobian does not."""
+    ch = mc.create_test_character(3)
+    theta = np.zeros(ch.num_params)
+    theta[0], theta[1] = 0.5, -0.3
+    offset = np.array([[0.0, 1.0, 0.0]])
+    wp = mc.world_points(ch, theta[None], np.array([2], np.int32), offset)[0, 0]
+    normal = np.array([0.0, 0.0, 1.0])
+    ef = mc.PlaneErrorFunction(np.array([2], np.int32), offset, np.ones(1), np.concatenate([normal, [normal @ wp]])[None, None, :], weight=1.0)
+    fn = OracleFunction(ch, [ef], dtype)
+    e, J, r, rows = fn.get_jacobian(theta)
+    assert abs(e) <= 1e-10 and np.linalg.norm(r) <= rtol
+    assert np.linalg.norm(J) > 0.0
+
+
+def test_ka8_model_parameters_rows_follow_enabled_parameters_with_weight():
+    """model_parameters_error_function.cpp:90-133: one row per enabled parameter with target weight > 0, value
+    sqrt(weight * kMotionWeight) * w_i * (theta_i - target_i), Jacobian entry sqrt(weight * kMotionWeight) * w_i; the block keeps
+    getJacobianSize() = count(w > 0) rows (:93-95) and leaves the unused ones zero."""
+    ch = mc.create_test_character(3)
+    n = ch.num_params
+    rng = np.random.default_rng(8)
+    w = rng.uniform(0.5, 1.5, n); w[[2, 5]] = 0.0
+    theta, tgt = rng.normal(size=n), rng.normal(size=n)
+    ef = mc.ModelParametersErrorFunction(w, tgt[None], weight=0.7)
+    fn = OracleFunction(ch, [ef], "float64")
+    en = np.ones(n, bool); en[[0, 7]] = False
+    fn.set_enabled_parameters(en)
+    e, J, r, rows = fn.get_jacobian(theta)
+    sw = np.sqrt(np.float32(0.7 * 1e-1))  # `const float sWeight` in the reference
+    live = [i for i in range(n) if en[i] and w[i] > 0]
+    assert rows >= int(np.count_nonzero(w > 0))
+    for k, i in enumerate(live):
+        assert abs(r[k] - sw * w[i] * (theta[i] - tgt[i])) <= 1e-12
+        assert abs(J[k, i] - sw * w[i]) <= 1e-12 and np.count_nonzero(J[k]) == 1
+    assert not np.any(J[len(live):]) and not np.any(r[len(live):])
+    assert abs(e - 0.07 * sum((w[i] * (theta[i] - tgt[i])) ** 2 for i in range(n) if en[i])) <= 1e-6 * max(1.0, e)
