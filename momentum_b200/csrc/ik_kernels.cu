@@ -1,12 +1,14 @@
 // sm_100a kernels for one Gauss-Newton iteration over a batch of IK instances.
 //
-//   K1 sweepKernel<true>   FK sweep + residual + Jacobian cells      (skeleton_solver_function.cpp:200-261)
-//   K4 sweepKernel<false>  FK sweep + error only (line search)       (skeleton_solver_function.cpp:64-83)
-//   K2 jtjSimtKernel       JtJ (lower) and Jtr, fp32 CUDA cores      (solver_function.cpp:113-116) — validation path
-//   K3 choleskyKernel      (JtJ + lambda I) delta = Jtr via blocked LLT, theta -= delta, SolverT bookkeeping
-//                          (gauss_newton_solver.cpp:248-259, solver.cpp:89-122)
+//   K1  sweepKernel<true, W>      FK sweep + residual + Jacobian cells (strip layout or K-major matrix)  (skeleton_solver_function.cpp:200-261)
+//   K4  sweepKernel<false, W>     FK sweep + error only (line search)                                    (skeleton_solver_function.cpp:64-83)
+//   K2s gramTilesKernel           stored tiles of JtJ + lambda I and Jtr from the non-zero strips of J (mma.sync, three-term TF32 split)
+//   K2' jtjSimtKernel             dense JtJ and Jtr, fp32 CUDA cores (solver_function.cpp:113-116): validation path / wide systems
+//   K3  choleskyScheduledKernel   level-scheduled tile-sparse damped Cholesky + solves + theta -= delta + SolverT bookkeeping
+//   K3' choleskyKernel<NB>        dense blocked LLT with Eigen's block structure and early exit (gauss_newton_solver.cpp:248-259, solver.cpp:89-122)
+//   small kernels                 line search, bookkeeping, target scatter / quaternion normalisation
 //
-// The tensor-core JtJ (tcgen05, TMEM accumulators, TMA-fed) lives in ik_jtj_tc.cu.
+// The dense tensor-core JtJ (tcgen05, TMEM accumulators, TMA-fed) lives in ik_jtj_tc.cu; PTX wrappers in ik_ptx.cuh.
 #include "ik_kernels.cuh"
 
 #include <cstdio>
