@@ -27,12 +27,13 @@ int main() {
     BatchedSkeletonSolverFunction fn(ch, 4);
     GaussNewtonSolverOptions o; o.maxIterations = 6; o.minIterations = 6; o.regularization = 1e-7f; o.useBlockJtJ = true;
     int pos = fn.addPositionErrorFunction(1.f, {2}, {0.f, 1.f, 0.f}, {1.f});
+    int pl = fn.addPlaneErrorFunction(1e-4f, {2}, {0.f, 0.5f, 0.f}, {1.f}, /*above=*/true);
+    int mp = fn.addModelParametersErrorFunction(1e-3f, std::vector<float>(10, 1.f));
+    // every block first, then the per-instance data (the record layout is fixed by the block list)
     std::vector<float> tg(4 * 3, 0.f); for (int b = 0; b < 4; ++b) { tg[3*b] = 0.3f * b; tg[3*b+1] = 2.5f; }
     fn.setTargets(pos, tg);
-    int pl = fn.addPlaneErrorFunction(1e-4f, {2}, {0.f, 0.5f, 0.f}, {1.f}, /*above=*/true);
     std::vector<float> planes(4 * 4, 0.f); for (int b = 0; b < 4; ++b) { planes[4*b+1] = 1.f; planes[4*b+3] = -1.f; }
     fn.setTargets(pl, planes);
-    int mp = fn.addModelParametersErrorFunction(1e-3f, std::vector<float>(10, 1.f));
     fn.setTargets(mp, std::vector<float>(4 * 10, 0.f));
     BatchedGaussNewtonSolver solver(o, &fn);
     std::vector<float> params(4 * 10, 0.f);
