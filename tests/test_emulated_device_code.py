@@ -76,6 +76,25 @@ def test_edge_cases_empty_and_degenerate_inputs():
     parity.check_edge_cases(EMU_LIB)
 
 
+def test_ka6_python_ik_basic_through_the_device_code():
+    """pymomentum/test/test_solver2.py:135-199 on the emulated device path: joint positions reach the targets within 1e-4 and a second
+    solve reproduces the error history bit for bit."""
+    from tests.test_oracle_known_answers import _ka6_problem
+
+    ch, ef, parents, offsets, targets = _ka6_problem()
+    fn = parity.build_function(ch, [ef], 1, EMU_LIB)
+    opts = ms.GaussNewtonSolverOptions(min_iterations=1, max_iterations=200, threshold=1.0, regularization=1e-5, store_error_history=True)
+    solver = ms.GaussNewtonSolver(opts, fn)
+    theta0 = np.zeros((1, ch.num_params))
+    out = solver.solve(theta0)
+    hist = solver.get_error_history()[0, : out["iterations"][0]]
+    got = mc.world_points(ch, out["params"].astype(np.float64), parents, offsets)
+    assert np.allclose(got, targets, rtol=1e-4, atol=1e-4)
+    assert len(hist) > 1 and hist[-1] < hist[0]
+    out2 = solver.solve(theta0)
+    assert np.array_equal(solver.get_error_history()[0, : out2["iterations"][0]], hist) and np.array_equal(out["params"], out2["params"])
+
+
 def test_humanoid_single_iteration():
     ch, efs, theta0, theta_star = humanoid_problem(2, orientation=True)
     th = (theta0 + 0.3 * theta_star).astype(np.float32)

@@ -154,3 +154,29 @@ def test_ka8_model_parameters_rows_follow_enabled_parameters_with_weight():
         assert abs(J[k, i] - sw * w[i]) <= 1e-12 and np.count_nonzero(J[k]) == 1
     assert not np.any(J[len(live):]) and not np.any(r[len(live):])
     assert abs(e - 0.07 * sum((w[i] * (theta[i] - tgt[i])) ** 2 for i in range(n) if en[i])) <= 1e-6 * max(1.0, e)
+
+
+def _ka6_problem():
+    """pymomentum/test/test_solver2.py:135-199 (test_ik_basic): 4-joint fixture, np.random.seed(42), target pose 0.5 * rand(n), one
+    Position constraint per joint (zero offset, weight 1) on the target joint positions, start from zero."""
+    ch = mc.create_test_character(4)
+    n = ch.num_params
+    np.random.seed(42)
+    theta_target = (0.5 * np.random.rand(n)).astype(np.float32).astype(np.float64)
+    parents = np.arange(ch.num_joints, dtype=np.int32)
+    offsets = np.zeros((ch.num_joints, 3))
+    targets = mc.world_points(ch, theta_target[None], parents, offsets)
+    ef = mc.PositionErrorFunction(parents, offsets, np.ones(ch.num_joints), targets, weight=1.0)
+    return ch, ef, parents, offsets, targets
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_ka6_python_ik_basic(dtype):
+    ch, ef, parents, offsets, targets = _ka6_problem()
+    fn = OracleFunction(ch, [ef], dtype)
+    err, p, it, hist = fn.solve(np.zeros(ch.num_params), min_iterations=1, max_iterations=200, threshold=1.0, regularization=1e-5)
+    got = mc.world_points(ch, p[None], parents, offsets)
+    assert np.allclose(got, targets, rtol=1e-4, atol=1e-4)
+    assert len(hist) > 1 and hist[-1] < hist[0]
+    err2, p2, it2, hist2 = fn.solve(np.zeros(ch.num_params), min_iterations=1, max_iterations=200, threshold=1.0, regularization=1e-5)
+    assert np.array_equal(hist, hist2) and np.array_equal(p, p2)  # "make sure it's deterministic"
