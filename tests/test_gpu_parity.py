@@ -178,6 +178,32 @@ def test_ka4_three_joint_ik_with_cholesky_breakdown():
     assert np.all(out["errors"] <= 5e-7)
 
 
+def test_ka6_python_ik_basic_is_reached_and_deterministic():
+    """pymomentum/test/test_solver2.py:135-199 on the CUDA path: joint positions reach the targets within 1e-4 and a second solve
+    reproduces the error history and the parameters bit for bit (no atomics / no order-dependent sums on the data path)."""
+    from tests.test_oracle_known_answers import _ka6_problem
+
+    ch, ef, parents, offsets, targets = _ka6_problem()
+    fn = parity.build_function(ch, [ef], 1)
+    opts = ms.GaussNewtonSolverOptions(min_iterations=1, max_iterations=200, threshold=1.0, regularization=1e-5, store_error_history=True)
+    solver = ms.GaussNewtonSolver(opts, fn)
+    theta0 = np.zeros((1, ch.num_params))
+    out = solver.solve(theta0)
+    hist = solver.get_error_history()[0, : out["iterations"][0]]
+    got = mc.world_points(ch, out["params"].astype(np.float64), parents, offsets)
+    assert np.allclose(got, targets, rtol=1e-4, atol=1e-4)
+    assert len(hist) > 1 and hist[-1] < hist[0]
+    out2 = solver.solve(theta0)
+    assert np.array_equal(solver.get_error_history()[0, : out2["iterations"][0]], hist) and np.array_equal(out["params"], out2["params"])
+    # and on the tile-scheduled path (humanoid, Gram kernel + level-scheduled Cholesky)
+    ch, efs, theta0, _ = humanoid_problem(16, orientation=True)
+    fn = parity.build_function(ch, efs, 16)
+    solver = ms.GaussNewtonSolver(ms.GaussNewtonSolverOptions(min_iterations=6, max_iterations=6, regularization=0.05, store_error_history=True), fn)
+    a = solver.solve(theta0); ha = solver.get_error_history().copy()
+    b = solver.solve(theta0); hb = solver.get_error_history()
+    assert np.array_equal(a["params"], b["params"]) and np.array_equal(ha, hb)
+
+
 def test_cfg1_chain22():
     ch, efs, theta0, _ = chain22_problem()
     opts = ms.GaussNewtonSolverOptions(min_iterations=1, max_iterations=50, threshold=1.0, regularization=0.05)
