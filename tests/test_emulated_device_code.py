@@ -95,6 +95,18 @@ def test_ka6_python_ik_basic_through_the_device_code():
     assert np.array_equal(solver.get_error_history()[0, : out2["iterations"][0]], hist) and np.array_equal(out["params"], out2["params"])
 
 
+@pytest.mark.parametrize("subset", [False, True])
+def test_line_search_on_the_tile_scheduled_path(subset):
+    """Armijo search (gauss_newton_solver.cpp:283-313 / subset_gauss_newton_solver.cpp:119-141) with the strip layout: the step lives in
+    device-column order with alignment gaps, the trial update maps it back through the column table."""
+    ch, efs, theta0, _ = humanoid_problem(2, orientation=True)
+    en = np.ones(ch.num_params, bool); en[[5, 17, 40, 41, 100, 150, 219]] = False
+    opts = ms.GaussNewtonSolverOptions(min_iterations=5, max_iterations=5, threshold=1.0, regularization=0.05, do_line_search=True,
+                                       subset_line_search=subset)
+    parity.check_solve(ch, efs, theta0, opts, EMU_LIB)
+    parity.check_solve(ch, efs, theta0, opts, EMU_LIB, enabled=en)
+
+
 def test_humanoid_single_iteration():
     ch, efs, theta0, theta_star = humanoid_problem(2, orientation=True)
     th = (theta0 + 0.3 * theta_star).astype(np.float32)
