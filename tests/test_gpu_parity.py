@@ -204,6 +204,17 @@ def test_ka6_python_ik_basic_is_reached_and_deterministic():
     assert np.array_equal(a["params"], b["params"]) and np.array_equal(ha, hb)
 
 
+@pytest.mark.parametrize("subset", [False, True])
+def test_line_search_on_the_tile_scheduled_path(subset):
+    """Armijo search with the strip layout / Gram kernel / tile Cholesky, with and without a disabled parameter subset."""
+    ch, efs, theta0, _ = humanoid_problem(2, orientation=True)
+    en = np.ones(ch.num_params, bool); en[[5, 17, 40, 41, 100, 150, 219]] = False
+    opts = ms.GaussNewtonSolverOptions(min_iterations=5, max_iterations=5, threshold=1.0, regularization=0.05, do_line_search=True,
+                                       subset_line_search=subset)
+    parity.check_solve(ch, efs, theta0, opts)
+    parity.check_solve(ch, efs, theta0, opts, enabled=en)
+
+
 def test_cfg1_chain22():
     ch, efs, theta0, _ = chain22_problem()
     opts = ms.GaussNewtonSolverOptions(min_iterations=1, max_iterations=50, threshold=1.0, regularization=0.05)
