@@ -33,9 +33,9 @@ sys.path.insert(0, ROOT)
 
 ITERS = 10
 WORKLOADS = {
-    "cfg3-shard": dict(batch=8192, rig="humanoid72", orientation=True, desc="8192/GPU x humanoid72, 24 Position + 6 Orientation (m=126->128, n=220), lambda=0.05"),
-    "cfg2": dict(batch=4096, rig="humanoid72", orientation=False, desc="4096/GPU x humanoid72, 24 Position (m=72, n=220), lambda=0.05"),
-    "cfg4": dict(batch=2048, rig="bodyhands300", orientation=False, desc="2048/GPU x bodyhands300, 200 Position (m=600, n=424), lambda=0.05"),
+    "cfg3-shard": dict(batch=8192, rig="humanoid72", orientation=True, rows_m=126, params_n=220, desc="8192/GPU x humanoid72, 24 Position + 6 Orientation (m=126->128, n=220), lambda=0.05"),
+    "cfg2": dict(batch=4096, rig="humanoid72", orientation=False, rows_m=72, params_n=220, desc="4096/GPU x humanoid72, 24 Position (m=72, n=220), lambda=0.05"),
+    "cfg4": dict(batch=2048, rig="bodyhands300", orientation=False, rows_m=600, params_n=424, desc="2048/GPU x bodyhands300, 200 Position (m=600, n=424), lambda=0.05"),
 }
 
 
@@ -118,32 +118,62 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(self.sm)}
 
 
+def bench_config(args, world):
+    """The `config` dict of both arms' JSON lines (the driver compares them key by key): the workload as named in BASELINE.json, never
+    anything measured. The CPU arm times a bounded sample of this workload (its size is in cpu_baseline.sample)."""
+    w = WORKLOADS[args.workload]
+    B = args.batch_per_gpu or w["batch"]
+    return {"workload": args.workload, "desc": w["desc"], "batch_per_gpu": B, "global_batch": B * world, "iterations_per_solve": ITERS,
+            "rows_m": w["rows_m"], "params_n": w["params_n"], "parallelism": f"dp{world} (instances sharded, no data-path collective)",
+            "jtj_mode": args.jtj_mode, "cholesky_mode": args.cholesky_mode, "l2": "256 MB buffer written between timed steps (L2 flush)"}
+
+
+def time_cpu_arm(workload, seconds, threads=None):
+    """The reference's CPU algorithm (oracle restatement, float, -march=native timing build, one solver per instance over the host
+    threads this process may use — affinity mask capped by the cgroup quota — as tensor_ik.cpp:127 does with dispenso) on a bounded
+    sample of the workload. Returns (it/s, threads, sample description, single-thread it/s)."""
+    from oracle.binding import OracleFunction, hardware_threads
+
+    threads = threads or hardware_threads()
+    sample = max(threads * 4, 64)
+    ch, efs, theta0, _ = make_problem(workload, sample)
+    orc = OracleFunction(ch, efs, "float32", native=True)
+    kw = dict(min_iterations=ITERS, max_iterations=ITERS, threshold=1.0, regularization=0.05, final_errors=False)
+    orc.solve_batch(theta0, threads=threads, **kw)
+    reps, its, t0 = 0, 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        its += int(orc.solve_batch(theta0, threads=threads, **kw)["iterations"].sum())
+        reps += 1
+    dt = time.perf_counter() - t0
+    # single-thread figure on a few instances (SURVEY 8d (ii))
+    n1 = min(sample, 8)
+    t1 = time.perf_counter()
+    its1 = int(orc.solve_batch(theta0[:n1], threads=1, **kw)["iterations"].sum()) if n1 == sample else None
+    if its1 is None:
+        ch1, efs1, th1, _ = make_problem(workload, n1)
+        o1 = OracleFunction(ch1, efs1, "float32", native=True)
+        t1 = time.perf_counter()
+        its1 = int(o1.solve_batch(th1, threads=1, **kw)["iterations"].sum())
+    single = its1 / (time.perf_counter() - t1)
+    build = "-O3 -march=native, FMA + reassociation, row-major blocked LLT" if getattr(orc._L, "is_native", False) else "portable x86-64-v3 checker build"
+    desc = (f"{reps} x {sample} instances x {ITERS} GN iterations (oracle restatement of the reference solver, float, {build}; one solver per "
+            f"instance over {threads} host threads; single thread: {single:.0f} GN it/s)")
+    return its / dt, threads, desc, single, sample
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU algorithm (oracle port, float) on the host cores."""
     if rank != 0:
         return
-    from oracle.binding import OracleFunction, hardware_threads
-
-    threads = hardware_threads()
-    sample = max(threads * 4, 64)
-    ch, efs, theta0, _ = make_problem(args.workload, sample)
-    orc = OracleFunction(ch, efs, "float32")
-    kw = dict(threads=threads, min_iterations=ITERS, max_iterations=ITERS, threshold=1.0, regularization=0.05, final_errors=False)
-    for _ in range(args.warmup):
-        orc.solve_batch(theta0, **kw)
+    budget = max(5.0, min(20.0, 2.0 * (args.steps + args.warmup)))  # bounded: the whole run ends within a few minutes whatever K / W are
     t0 = time.perf_counter()
-    its = 0
-    for _ in range(args.steps):
-        r = orc.solve_batch(theta0, **kw)
-        its += int(r["iterations"].sum())
+    value, threads, desc, single, sample = time_cpu_arm(args.workload, budget)
     dt = time.perf_counter() - t0
-    value = its / dt
     line = {"impl": "reference", "metric": "GN iterations/sec (batched 72-joint IK)", "value": value, "unit": "GN it/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": {"workload": args.workload, "desc": WORKLOADS[args.workload]["desc"], "iterations_per_solve": ITERS},
-            "cpu_baseline": {"value": value, "unit": "GN it/s", "cores": threads, "kind": "port",
-                             "sample": f"{sample} instances x {ITERS} GN iterations per step (oracle restatement, float, one solver per instance over {threads} threads)"},
-            "e2e": {"value": value, "unit": "GN it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "warmup": args.warmup, "ms_per_step": 1e3 * sample * ITERS / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": bench_config(args, world),
+            "cpu_baseline": {"value": value, "unit": "GN it/s", "cores": threads, "kind": "port", "sample": desc, "single_thread_value": single},
+            "e2e": {"value": value, "unit": "GN it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "wall_s": dt}
     print(json.dumps(line))
 
 
@@ -183,6 +213,7 @@ def main():
     opts = ms.GaussNewtonSolverOptions(min_iterations=ITERS, max_iterations=ITERS, threshold=1.0, regularization=0.05, jtj_mode=args.jtj_mode, cholesky_mode=args.cholesky_mode)
     solver = ms.GaussNewtonSolver(opts, fn)
     m_rows = sum(3 * len(e.parents) if e.kind == 0 else 9 * len(e.parents) for e in efs)
+    assert m_rows == WORKLOADS[args.workload]["rows_m"] and n == WORKLOADS[args.workload]["params_n"]
 
     work_stream = torch.cuda.Stream()  # a real (non-NULL) stream: NULL means "the handle's own stream" in the C-ABI
     torch.cuda.set_stream(work_stream)
@@ -325,9 +356,7 @@ def main():
     line = {
         "metric": "GN iterations/sec (batched 72-joint IK)", "value": value, "unit": "GN it/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "desc": WORKLOADS[args.workload]["desc"], "batch_per_gpu": B, "global_batch": B * world, "iterations_per_solve": ITERS,
-                   "rows_m": m_rows, "params_n": n, "parallelism": f"dp{world} (instances sharded, no data-path collective)",
-                   "jtj_mode": args.jtj_mode, "cholesky_mode": args.cholesky_mode, "l2": "256 MB buffer written between timed steps (L2 flush)"},
+        "config": bench_config(args, world),
         "solves_per_sec": value / ITERS, "aggregate_final_error": err_total,
         "e2e": {"value": e2e_value, "unit": "GN it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
@@ -337,22 +366,8 @@ def main():
         "kernels_ms_per_iteration": {"fk_residual_jacobian": sweep_ms, "jtj_jtr": jtj_ms, "cholesky_update": chol_ms},
     }
     if not args.no_cpu_baseline:
-        from oracle.binding import OracleFunction, hardware_threads
-
-        threads = hardware_threads()
-        sample = max(threads * 4, 64)
-        ch_s, efs_s, th_s, _ = make_problem(args.workload, sample)
-        orc = OracleFunction(ch_s, efs_s, "float32")
-        kw = dict(threads=threads, min_iterations=ITERS, max_iterations=ITERS, threshold=1.0, regularization=0.05, final_errors=False)
-        orc.solve_batch(th_s, **kw)
-        reps, t0 = 0, time.perf_counter()
-        its = 0
-        while time.perf_counter() - t0 < 10.0:
-            its += int(orc.solve_batch(th_s, **kw)["iterations"].sum())
-            reps += 1
-        dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": its / dt, "unit": "GN it/s", "cores": threads, "kind": "port",
-                                "sample": f"{reps} x {sample} instances x {ITERS} GN iterations (oracle restatement of the reference solver, float, one solver per instance over {threads} threads)"}
+        value_cpu, threads, desc, single, _ = time_cpu_arm(args.workload, 10.0)
+        line["cpu_baseline"] = {"value": value_cpu, "unit": "GN it/s", "cores": threads, "kind": "port", "sample": desc, "single_thread_value": single}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -84,11 +84,12 @@ typedef enum mb2_rotation_error_type {
 
 /* How JtJ is formed on the device (extension; the reference always uses Eigen fp32/fp64 GEMM). */
 typedef enum mb2_jtj_mode {
-  MB2_JTJ_AUTO = 0,      /* tile-sparse fp32 Gram with the tile-scheduled Cholesky; else tensor-core 3xTF32 where the shape allows, else FP32 SIMT */
+  MB2_JTJ_AUTO = 0,      /* tile-sparse Gram (mma.sync, three-term TF32 split: fp32-class, not bit-exact fp32) with the tile-scheduled Cholesky; else tcgen05 3xTF32 where the shape allows, else FP32 SIMT */
   MB2_JTJ_FP32_SIMT = 1, /* CUDA-core fp32 (validation path) */
   MB2_JTJ_TF32X3 = 2,    /* tcgen05 kind::tf32, 3-term split, fp32 accumulate in TMEM (fp32-class accuracy) */
   MB2_JTJ_TF32 = 3,      /* tcgen05 kind::tf32 single pass (~1e-3 relative; changes the GN path, not the fixed point) */
-  MB2_JTJ_SPARSE_TILES = 4 /* fp32 CUDA cores over the non-zero strips of J only, straight into the Cholesky tile layout (tile-scheduled Cholesky only) */
+  MB2_JTJ_SPARSE_TILES = 4 /* tensor cores (mma.sync m16n8k8, hi*hi + hi*lo + lo*hi TF32 split, the lo*lo term is dropped: ~2^-21 relative) over the non-zero
+                              strips of J only, straight into the Cholesky tile layout (tile-scheduled Cholesky only) */
 } mb2_jtj_mode;
 
 /* How (JtJ + lambda I) delta = Jtr is solved on the device (extension; the reference always runs a dense
@@ -212,8 +213,10 @@ int mb2_solver_set_enabled_parameters(mb2_solver* s, const uint64_t bits[MB2_PAR
  * the objective before the last update (what solve() returns); iterations[b] = number of
  * doIteration calls; status[b] = mb2_instance_status. Any of errors/iterations/status may be NULL. */
 int mb2_solver_solve(mb2_solver* s, float* parameters, double* errors, int32_t* iterations, int32_t* status);
-/* Same with parameters resident on the device; asynchronous on `cuda_stream` (NULL = handle stream).
- * Results are fetched with mb2_solver_get_results after synchronising. */
+/* Same with parameters resident on the device, on `cuda_stream` (NULL = handle stream). Results are fetched with
+ * mb2_solver_get_results after synchronising. The fused single-kernel path (default options on a rig whose tiles fit in shared
+ * memory, no line search) is fully asynchronous; the multi-kernel path is asynchronous up to min_iterations and then reads the
+ * device-side active counter every fourth iteration (a host round trip on `cuda_stream`) so that a converged batch stops early. */
 int mb2_solver_solve_device(mb2_solver* s, float* parameters_device, void* cuda_stream);
 int mb2_solver_get_results(mb2_solver* s, double* errors, int32_t* iterations, int32_t* status);
 /* getErrorHistory (solver.h:90): [B][max_iterations], valid up to iterations[b] */

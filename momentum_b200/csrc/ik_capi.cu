@@ -4,6 +4,7 @@
 #include "../../include/momentum_b200.h"
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <cfloat>
@@ -66,6 +67,33 @@ struct DeviceBuffer {
 };
 
 int roundUp(int v, int m) { return (v + m - 1) / m * m; }
+
+int usableDevices();
+
+// Every entry point that allocates or launches runs with the handle's device current and restores the caller's device on exit
+// (a single process may drive several GPUs: one character / solver function per device).
+struct DeviceGuard {
+  int prev{-1};
+  bool switched{false};
+  cudaError_t err{cudaSuccess};
+  explicit DeviceGuard(int device) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != device) { err = cudaSetDevice(device); switched = err == cudaSuccess; }
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define MB2_DEVICE_GUARD(device)                                                                                      \
+  if (usableDevices() <= 0) return fail(MB2_ERR_CUDA, "no usable sm_100 CUDA device: momentum_b200 has no CPU fallback"); \
+  DeviceGuard _guard(device);                                                                                         \
+  MB2_CUDA(_guard.err)
+
+// NVTX ranges named like the reference's MT_PROFILE_FUNCTION zones (solver.cpp:51, gauss_newton_solver.cpp:225, skeleton_state.cpp:88)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 } // namespace
 
@@ -187,7 +215,8 @@ namespace {
 
 bool g_deviceChecked = false;
 int g_usableDevices = 0;
-
+} // namespace
+namespace {
 int usableDevices() {
   if (!g_deviceChecked) {
     int n = 0;
@@ -218,6 +247,8 @@ int ensureTargets(mb2_solver_function* f) {
     std::swap(old.n, f->dTargets.n);
     MB2_CUDA(f->dTargets.resize(need));
     MB2_CUDA(cudaMemsetAsync(f->dTargets.p, 0, need * sizeof(float), f->stream));
+    // the next writer may be mb2_set_targets_device on a caller's stream: the zero fill must have landed first
+    MB2_CUDA(cudaStreamSynchronize(f->stream));
     (void)old; // targets of blocks added earlier must be re-sent after adding blocks (documented)
   }
   return MB2_OK;
@@ -265,7 +296,7 @@ int ensurePlan(mb2_solver_function* f, int mode, bool schedDense = false, bool a
   if (mode != 2) alignRows = false;
   if (!f->planDirty && f->planLimitsVersion == f->ch->limitsVersion && f->planMode == mode && (mode != 2 || (f->planSchedDense == schedDense && f->planAlignRows == alignRows)))
     return MB2_OK;
-  MB2_CUDA(cudaSetDevice(f->ch->device));
+  MB2_DEVICE_GUARD(f->ch->device);
   cudaStream_t s = f->stream;
   f->sched.reset();
   std::string err = buildPlan(f->ch->host, f->efs, f->enabled, mode != 0, f->plan);
@@ -327,6 +358,9 @@ int ensurePlan(mb2_solver_function* f, int mode, bool schedDense = false, bool a
   if (rc != MB2_OK) return rc;
   rc = uploadWeights(f);
   if (rc != MB2_OK) return rc;
+  // Plan tables, schedule / Gram blobs, weights and the Jacobian zero fill were issued on the handle's stream; the solve may run on a
+  // caller's stream. A plan build is a rare host-side event: wait for it here instead of threading events through every launch.
+  MB2_CUDA(cudaStreamSynchronize(s));
   f->planDirty = false;
   f->planLimitsVersion = f->ch->limitsVersion;
   return MB2_OK;
@@ -348,13 +382,14 @@ SweepArgs sweepArgs(mb2_solver_function* f, const float* theta, const int32_t* a
 }
 
 int addBlock(mb2_solver_function* f, HostErrorFunction& ef, int32_t* outIndex) {
+  const bool hasWeights = ef.kind <= 2 || ef.kind == 5;
+  if (hasWeights && f->weightsPerInstance) return fail(MB2_ERR_UNSUPPORTED, "add all error functions before setting per-instance constraint weights");
   ef.targetOff = f->targetStride;
   ef.weightOff = f->numWeights;
   f->targetStride += ef.targetSize;
-  if (ef.kind <= 2 || ef.kind == 5) {
+  if (hasWeights) {
     f->numWeights += ef.numConstraints();
     f->hWeights.insert(f->hWeights.end(), ef.weights.begin(), ef.weights.end());
-    if (f->weightsPerInstance) return fail(MB2_ERR_UNSUPPORTED, "add all error functions before setting per-instance constraint weights");
   }
   f->efs.push_back(ef);
   f->planDirty = true;
@@ -481,6 +516,7 @@ int mb2_character_create(int device, int32_t J, const int32_t* parents, const fl
   const std::string err = h.validate();
   if (!err.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, err);
   h.buildLevels();
+  MB2_DEVICE_GUARD(device);
   int rc = requireDevice(device);
   if (rc != MB2_OK) return rc;
   c->device = device;
@@ -519,6 +555,7 @@ void mb2_character_destroy(mb2_character* c) { delete c; }
 int mb2_solver_function_create(const mb2_character* c, int32_t batch, mb2_solver_function** out) {
   MB2_CHECK(c != nullptr && out != nullptr, "null argument");
   MB2_CHECK(batch > 0, "batch must be positive");
+  MB2_DEVICE_GUARD(c->device);
   int rc = requireDevice(c->device);
   if (rc != MB2_OK) return rc;
   auto f = std::make_unique<mb2_solver_function>();
@@ -665,7 +702,7 @@ static int setTargetsImpl(mb2_solver_function* f, int32_t index, const float* ta
   const HostErrorFunction& ef = f->efs[index];
   if (ef.targetSize == 0 && ef.kind != 4) return MB2_OK; // a block without constraints: nothing to send (setConstraints({}) in the reference)
   MB2_CHECK(ef.targetSize > 0, "this error function has no per-instance targets");
-  MB2_CUDA(cudaSetDevice(f->ch->device));
+  MB2_DEVICE_GUARD(f->ch->device);
   int rc = ensureTargets(f);
   if (rc != MB2_OK) return rc;
   float* dst = f->dTargets.p + ef.targetOff;
@@ -695,7 +732,7 @@ int mb2_set_constraint_weights(mb2_solver_function* f, int32_t index, const floa
   MB2_CHECK(f != nullptr && index >= 0 && index < int(f->efs.size()) && weights, "invalid constraint weights");
   HostErrorFunction& ef = f->efs[index];
   MB2_CHECK(ef.kind <= 2 || ef.kind == 5, "constraint weights apply to Position/Orientation/Plane error functions");
-  MB2_CUDA(cudaSetDevice(f->ch->device));
+  MB2_DEVICE_GUARD(f->ch->device);
   const int nc = ef.numConstraints();
   if (!perInstance) {
     MB2_CHECK(!f->weightsPerInstance, "solver function already uses per-instance constraint weights");
@@ -725,6 +762,7 @@ int mb2_solver_function_set_enabled_parameters(mb2_solver_function* f, const uin
 
 int mb2_solver_function_get_error(mb2_solver_function* f, const float* params, double* errors) {
   MB2_CHECK(f != nullptr && params && errors, "null argument");
+  MB2_DEVICE_GUARD(f->ch->device);
   int rc = ensurePlan(f, f->planMode, f->planSchedDense, f->planAlignRows);
   if (rc != MB2_OK) return rc;
   const size_t n = f->ch->host.numParams;
@@ -737,6 +775,7 @@ int mb2_solver_function_get_error(mb2_solver_function* f, const float* params, d
 
 int mb2_solver_function_get_jacobian(mb2_solver_function* f, const float* params, float* jac, float* residual, double* errors, int32_t* actualRows) {
   MB2_CHECK(f != nullptr && params, "null argument");
+  MB2_DEVICE_GUARD(f->ch->device);
   int rc = ensurePlan(f, 0);
   if (rc != MB2_OK) return rc;
   const size_t n = f->ch->host.numParams;
@@ -759,6 +798,7 @@ int mb2_solver_function_get_jacobian(mb2_solver_function* f, const float* params
 
 int mb2_solver_function_get_jtjr(mb2_solver_function* f, const float* params, int32_t jtjMode, float* jtj, float* jtr, double* errors) {
   MB2_CHECK(f != nullptr && params, "null argument");
+  MB2_DEVICE_GUARD(f->ch->device);
   int rc = ensurePlan(f, 0);
   if (rc != MB2_OK) return rc;
   const size_t n = f->ch->host.numParams;
@@ -790,6 +830,7 @@ int mb2_solver_function_get_jtjr(mb2_solver_function* f, const float* params, in
 
 int mb2_solver_function_get_skeleton_state(mb2_solver_function* f, const float* params, float* state) {
   MB2_CHECK(f != nullptr && params && state, "null argument");
+  MB2_DEVICE_GUARD(f->ch->device);
   int rc = ensurePlan(f, f->planMode, f->planSchedDense, f->planAlignRows);
   if (rc != MB2_OK) return rc;
   const size_t n = f->ch->host.numParams;
@@ -812,7 +853,7 @@ int mb2_solver_create(mb2_solver_function* f, const mb2_gauss_newton_options* op
   auto s = std::make_unique<mb2_solver>();
   s->fn = f;
   if (opt) s->opt = *opt; else mb2_default_gauss_newton_options(&s->opt);
-  MB2_CUDA(cudaSetDevice(f->ch->device));
+  MB2_DEVICE_GUARD(f->ch->device);
   MB2_CUDA(cudaMallocHost(&s->hActiveCount, sizeof(int)));
   *out = s.release();
   return MB2_OK;
@@ -836,6 +877,8 @@ int mb2_solver_set_profiling(mb2_solver* s, int32_t enabled) {
 int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
   MB2_CHECK(s != nullptr && theta != nullptr, "null argument");
   mb2_solver_function* f = s->fn;
+  MB2_DEVICE_GUARD(f->ch->device);
+  NvtxRange nvtxSolve("mb2::SolverT::solve");
   const mb2_gauss_newton_options& o = s->opt;
   // Cholesky path: 0 auto, 1 dense Eigen-structured kernel, 2 tile schedule on the dense pattern, 3 tile schedule on the sparse pattern
   int numEnabled = 0;
@@ -906,6 +949,8 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
   MB2_CUDA(cudaGetLastError());
   MB2_CUDA(cudaMemcpyAsync(s->dTheta0.p, theta, size_t(B) * n * sizeof(float), cudaMemcpyDeviceToDevice, st));
 
+  static const bool cholProfile = getenv("MB2_CHOL_PROFILE") != nullptr;
+  constexpr int kPollEvery = 4; // iterations between two reads of the device-side active counter (each read blocks the host on `st`)
   for (int it = 0; it < maxIt; ++it) {
     MB2_CUDA(cudaMemsetAsync(s->dActiveCount.p, 0, sizeof(int), st));
     // --- doIteration (gauss_newton_solver.cpp:224-280) ---
@@ -967,7 +1012,7 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
     c.ldG = ldG;
     c.tilesIn = useGram ? s->dTiles.p : nullptr;
     c.tilesStride = tilesStride;
-    c.profile = (it == 0 && getenv("MB2_CHOL_PROFILE") != nullptr) ? 1 : 0;
+    c.profile = (it == 0 && cholProfile) ? 1 : 0;
     recordPhaseStart(s, 2, st);
     if (useSchedule) MB2_CUDA(launchCholeskyScheduled(c, f->sched->dev, st));
     else MB2_CUDA(launchCholesky(c, st));
@@ -1005,9 +1050,10 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
       MB2_CUDA(launchBookkeeping(ba, st));
       s->kernelLaunches += 1;
     }
-    // Instances can only stop once iteration >= minIterations (solver.cpp:113): poll the device
-    // counter from then on so a converged batch does not run to maxIterations.
-    if (it + 1 < maxIt && it >= minIt) {
+    // Instances can only stop once iteration >= minIterations (solver.cpp:113): poll the device counter from then on (every
+    // kPollEvery-th iteration: converged instances cost nothing on the device, the poll costs a host round trip) so that a
+    // converged batch does not run to maxIterations.
+    if (it + 1 < maxIt && it >= minIt && (it - minIt) % kPollEvery == kPollEvery - 1) {
       MB2_CUDA(cudaMemcpyAsync(s->hActiveCount, s->dActiveCount.p, sizeof(int), cudaMemcpyDeviceToHost, st));
       MB2_CUDA(cudaStreamSynchronize(st));
       if (*s->hActiveCount == 0) break;
@@ -1023,7 +1069,7 @@ int mb2_solver_get_results(mb2_solver* s, double* errors, int32_t* iterations, i
   MB2_CHECK(s != nullptr, "null solver");
   mb2_solver_function* f = s->fn;
   const int B = f->B;
-  MB2_CUDA(cudaSetDevice(f->ch->device));
+  MB2_DEVICE_GUARD(f->ch->device);
   MB2_CUDA(cudaDeviceSynchronize());
   if (errors) MB2_CUDA(cudaMemcpy(errors, f->dErrors.p, size_t(B) * sizeof(double), cudaMemcpyDeviceToHost));
   std::vector<int32_t> its(B);
@@ -1045,7 +1091,7 @@ int mb2_solver_get_results(mb2_solver* s, double* errors, int32_t* iterations, i
 int mb2_solver_solve(mb2_solver* s, float* params, double* errors, int32_t* iterations, int32_t* status) {
   MB2_CHECK(s != nullptr && params != nullptr, "null argument");
   mb2_solver_function* f = s->fn;
-  MB2_CUDA(cudaSetDevice(f->ch->device));
+  MB2_DEVICE_GUARD(f->ch->device);
   const size_t bytes = size_t(f->B) * f->ch->host.numParams * sizeof(float);
   MB2_CUDA(s->dThetaStage.resize(size_t(f->B) * f->ch->host.numParams));
   MB2_CUDA(cudaMemcpyAsync(s->dThetaStage.p, params, bytes, cudaMemcpyHostToDevice, f->stream));

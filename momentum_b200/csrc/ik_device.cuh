@@ -376,6 +376,7 @@ MB2_HD float evalUnit(const FunctionTables& T, int ui, const float* theta, const
     case kUnitModelParameter: { // model_parameters_error_function.cpp:38-58, 90-133; kMotionWeight = 1e-1 (.h:61)
       const float pdiff = u.f[0] * (theta[u.i[0]] - targets[u.targetOff]);
       const float scale = e.weight * 1e-1f;
+      if (u.pad[1] != 0) return kJacobian ? 0.f : pdiff * pdiff * scale; // negative target weight: counted by getError only (:56-59 vs :113)
       if (kJacobian) { const float sw = sqrtf(scale); r[0] = pdiff * sw; rc[0] = sw; }
       return pdiff * pdiff * scale;
     }

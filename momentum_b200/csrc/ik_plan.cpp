@@ -273,7 +273,24 @@ std::string buildPlan(const HostCharacter& ch, const std::vector<HostErrorFuncti
       if (int(ef.paramWeights.size()) != n) return "model-parameter target weights must have one entry per parameter"; // keeps getJacobianSize rows
       const int blockStart = row;
       for (int i = 0; i < n; ++i) {
-        if (!(ef.paramWeights[i] > 0.f) || !enabled[i]) continue;
+        if (!enabled[i] || ef.paramWeights[i] == 0.f) continue;
+        if (ef.paramWeights[i] < 0.f) { // no Jacobian row (:113 tests weight > 0) but getError still counts it (:56-59): an error-only unit
+          UnitDesc u{};
+          u.kind = kUnitModelParameter;
+          u.ef = int32_t(e);
+          u.joint = -1;
+          u.row0 = row;
+          u.numRows = 0;
+          u.targetOff = ef.targetOff + i;
+          u.weightIdx = -1;
+          u.recOff = rec;
+          u.extra = -1;
+          u.i[0] = i;
+          u.f[0] = ef.paramWeights[i];
+          u.pad[1] = 1;
+          out.units.push_back(u);
+          continue;
+        }
         UnitDesc u{};
         u.kind = kUnitModelParameter;
         u.ef = int32_t(e);

@@ -14,7 +14,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liboracle.so")
+_NATIVE_PATH = os.path.join(_HERE, "liboracle_native.so")  # timing arm only, built on the machine that runs it (oracle/Makefile)
 _lib = None
+_native = None
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -27,12 +29,32 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
+def native_lib():
+    """The -march=native / fast-math build for bench.py's CPU arm. Always rebuilt by the process that times it (a copy built on
+    another host may use instructions this one lacks); falls back to the portable checker build if the compile fails."""
+    global _native
+    if _native is None:
+        try:
+            subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "native"])
+            _native = _bind(C.CDLL(_NATIVE_PATH))
+            _native.is_native = True
+        except Exception as e:  # noqa: BLE001
+            print(f"[oracle] native build unavailable ({e}); timing the portable build", flush=True)
+            _native = lib()
+    return _native
+
+
 def lib():
     global _lib
     if _lib is None:
         if not os.path.exists(_LIB_PATH):
             build()
-        L = C.CDLL(_LIB_PATH)
+        _lib = _bind(C.CDLL(_LIB_PATH))
+    return _lib
+
+
+def _bind(L):
+    if True:  # (keeps the declaration block at its historical indentation)
         L.orc_rig_create.restype = C.c_void_p
         L.orc_rig_create.argtypes = [C.c_int, _ip, _dp, _dp, C.c_int, _ip, _ip, _dp, _dp]
         L.orc_rig_add_limit.argtypes = [C.c_void_p, C.c_int, C.c_double, _ip, _dp]
@@ -64,8 +86,7 @@ def lib():
         L.orc_solve_batch.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, _dp,
                                       C.POINTER(_dp), C.c_int, _dp, _ip, _dp]
         L.orc_hardware_threads.restype = C.c_int
-        _lib = L
-    return _lib
+    return L
 
 
 def _d(a):
@@ -85,8 +106,9 @@ class OracleFunction:
     is taken from batch index ``b`` (default 0) and can be switched with :meth:`select_instance`.
     """
 
-    def __init__(self, character, error_functions: Sequence, dtype: str = "float32", instance: int = 0):
-        L = lib()
+    def __init__(self, character, error_functions: Sequence, dtype: str = "float32", instance: int = 0, native: bool = False):
+        # native=True: the -march=native timing build (bench.py CPU arm only); parity checks always use the portable checker build
+        L = self._L = native_lib() if native else lib()
         self.ch = character
         self.efs = list(error_functions)
         self.dtype = 0 if dtype in ("float32", "f32", np.float32) else 1
@@ -137,7 +159,7 @@ class OracleFunction:
 
     def __del__(self):
         try:
-            L = lib()
+            L = self._L
             if getattr(self, "fn", None):
                 L.orc_fn_destroy(self.fn)
                 self.fn = None
@@ -148,7 +170,7 @@ class OracleFunction:
             pass
 
     def select_instance(self, b: int):
-        L = lib()
+        L = self._L
         for idx, ef in enumerate(self.efs):
             if ef.kind in (0, 1, 2, 3, 5, 6):
                 tg, tgp = _d(np.asarray(ef.targets)[b])
@@ -157,20 +179,20 @@ class OracleFunction:
     def set_enabled_parameters(self, enabled):
         e = np.ascontiguousarray(np.asarray(enabled, bool).astype(np.uint8))
         assert e.size == self.n
-        lib().orc_fn_set_enabled(self.fn, e.ctypes.data_as(C.POINTER(C.c_uint8)))
+        self._L.orc_fn_set_enabled(self.fn, e.ctypes.data_as(C.POINTER(C.c_uint8)))
 
     @property
     def actual_parameters(self):
-        return lib().orc_fn_actual_parameters(self.fn)
+        return self._L.orc_fn_actual_parameters(self.fn)
 
     def get_error(self, params) -> float:
         p, pp = _d(params)
-        return lib().orc_fn_get_error(self.fn, pp)
+        return self._L.orc_fn_get_error(self.fn, pp)
 
     def get_jacobian(self, params):
         """Returns (error, J [rows, n] , residual [rows], rows) — J as a numpy (rows x n) view of the
         reference's column-major storage."""
-        L = lib()
+        L = self._L
         rows = L.orc_fn_jacobian_rows(self.fn)
         p, pp = _d(params)
         jac = np.zeros((self.n, rows), np.float64)
@@ -181,7 +203,7 @@ class OracleFunction:
 
     def get_jtjr(self, params):
         """(error, JtJ [ap, ap] lower triangle, Jtr [ap]) as solver_function.cpp:74-121."""
-        L = lib()
+        L = self._L
         ap = self.actual_parameters
         p, pp = _d(params)
         H = np.zeros((ap, ap), np.float64)
@@ -193,7 +215,7 @@ class OracleFunction:
         J = self.ch.num_joints
         p, pp = _d(params)
         xf = np.zeros((J, 8)); ra = np.zeros((J, 9)); ta = np.zeros((J, 9))
-        lib().orc_fn_fk(self.fn, pp, xf.ctypes.data_as(_dp), ra.ctypes.data_as(_dp), ta.ctypes.data_as(_dp))
+        self._L.orc_fn_fk(self.fn, pp, xf.ctypes.data_as(_dp), ra.ctypes.data_as(_dp), ta.ctypes.data_as(_dp))
         # axes returned column-major per joint -> [J, row, col]
         return xf, ra.reshape(J, 3, 3).transpose(0, 2, 1), ta.reshape(J, 3, 3).transpose(0, 2, 1)
 
@@ -203,7 +225,7 @@ class OracleFunction:
         p = np.ascontiguousarray(params, np.float64).copy()
         hist = np.zeros(max(1, max_iterations), np.float64)
         it = C.c_int(0)
-        err = lib().orc_solve(self.fn, min_iterations, max_iterations, threshold, regularization, int(do_line_search), int(use_block_jtj),
+        err = self._L.orc_solve(self.fn, min_iterations, max_iterations, threshold, regularization, int(do_line_search), int(use_block_jtj),
                               int(subset_solver), p.ctypes.data_as(_dp), C.byref(it), hist.ctypes.data_as(_dp))
         return err, p, it.value, hist[: it.value].copy()
 
@@ -223,7 +245,7 @@ class OracleFunction:
             else:
                 ptrs[idx] = None
         errs = np.zeros(B); fin = np.zeros(B); its = np.zeros(B, np.int32)
-        secs = lib().orc_solve_batch(self.fn, min_iterations, max_iterations, threshold, regularization, int(do_line_search), int(use_block_jtj),
+        secs = self._L.orc_solve_batch(self.fn, min_iterations, max_iterations, threshold, regularization, int(do_line_search), int(use_block_jtj),
                                      int(subset_solver), B, P.ctypes.data_as(_dp), ptrs, int(threads), errs.ctypes.data_as(_dp),
                                      its.ctypes.data_as(_ip), fin.ctypes.data_as(_dp) if final_errors else None)
         return {"params": P, "errors": errs, "final_errors": fin, "iterations": its, "seconds": secs}

@@ -1140,8 +1140,66 @@ int lltBlocked(Mat<T>& A, int n) {
   }
   return -1;
 }
+#ifdef ORACLE_FAST
+// TIMING BUILD ONLY (liboracle_native.so, bench.py's CPU arm): the same blocked LLT on a row-major copy of the lower triangle, so
+// that every inner loop is a contiguous dot product / axpy the compiler vectorises (built with -march=native and reassociation
+// allowed, like Eigen's vectorised kernels). The checker build keeps the strictly ordered column-major restatement above.
+template <class T>
+bool choleskySolveLowerFast(Mat<T>& A, int n, std::vector<T>& b) {
+  std::vector<T> R(size_t(n) * n);
+  for (int i = 0; i < n; ++i) for (int j = 0; j <= i; ++j) R[size_t(i) * n + j] = A(i, j);
+  auto row = [&](int i) { return R.data() + size_t(i) * n; };
+  int blockSize = n < 32 ? n : std::min(std::max((n / 8 / 16) * 16, 8), 128);
+  bool ok = true;
+  for (int k = 0; k < n && ok; k += blockSize) {
+    const int bs = std::min(blockSize, n - k);
+    for (int c = k; c < k + bs; ++c) { // diagonal block + panel, left-looking inside the block (columns k..c-1)
+      T* rc = row(c);
+      T x = rc[c];
+      for (int j = k; j < c; ++j) x -= rc[j] * rc[j];
+      if (!(x > T(0))) { ok = false; break; }
+      x = std::sqrt(x);
+      rc[c] = x;
+      const T inv = T(1) / x;
+      for (int i = c + 1; i < n; ++i) {
+        T* ri = row(i);
+        T s = ri[c];
+        for (int j = k; j < c; ++j) s -= ri[j] * rc[j];
+        ri[c] = s * inv;
+      }
+    }
+    if (!ok) break;
+    for (int i = k + bs; i < n; ++i) { // trailing update, lower part
+      T* ri = row(i);
+      for (int j = k + bs; j <= i; ++j) {
+        const T* rj = row(j);
+        T s = 0;
+        for (int c = k; c < k + bs; ++c) s += ri[c] * rj[c];
+        ri[j] -= s;
+      }
+    }
+  }
+  for (int i = 0; i < n; ++i) { // L y = b
+    const T* ri = row(i);
+    T s = b[i];
+    for (int k = 0; k < i; ++k) s -= ri[k] * b[k];
+    b[i] = s / ri[i];
+  }
+  for (int i = n - 1; i >= 0; --i) { // L^T x = y, column-oriented: row i of L is contiguous
+    const T* ri = row(i);
+    const T x = b[i] / ri[i];
+    b[i] = x;
+    for (int k = 0; k < i; ++k) b[k] -= ri[k] * x;
+  }
+  for (int i = 0; i < n; ++i) for (int j = 0; j <= i; ++j) A(i, j) = R[size_t(i) * n + j];
+  return ok;
+}
+#endif
 template <class T>
 bool choleskySolveLower(Mat<T>& A, int n, std::vector<T>& b) { // A overwritten by L (lower), b by solution
+#ifdef ORACLE_FAST
+  return choleskySolveLowerFast(A, n, b);
+#endif
   const bool ok = lltBlocked(A, n) < 0;
   for (int i = 0; i < n; ++i) { // L y = b
     T s = b[i];

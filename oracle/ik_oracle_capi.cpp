@@ -9,6 +9,9 @@
 #include <memory>
 #include <thread>
 
+#include <sched.h>
+#include <cstdio>
+
 using namespace oracle;
 
 namespace {
@@ -397,6 +400,32 @@ double orc_solve_batch(void* fn, int64_t minIt, int64_t maxIt, double threshold,
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
-int orc_hardware_threads() { return int(std::thread::hardware_concurrency()); }
+// Host threads this process may actually use: the CPU affinity mask, capped by the cgroup CPU quota (cpu.max = "<quota> <period>"),
+// not std::thread::hardware_concurrency() (which reports every core of the host even inside a container with a few CPUs' worth of quota).
+int orc_hardware_threads() {
+  int n = int(std::thread::hardware_concurrency());
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) { const int c = CPU_COUNT(&set); if (c > 0) n = c; }
+  for (const char* path : {"/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"}) {
+    FILE* f = std::fopen(path, "r");
+    if (!f) continue;
+    char buf[128] = {0};
+    if (std::fgets(buf, sizeof(buf), f)) {
+      long long quota = -1, period = 100000;
+      if (std::strncmp(buf, "max", 3) != 0) {
+        if (std::sscanf(buf, "%lld %lld", &quota, &period) < 2) {
+          period = 100000;
+          FILE* pf = std::fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r");
+          if (pf) { if (std::fscanf(pf, "%lld", &period) != 1) period = 100000; std::fclose(pf); }
+        }
+        if (quota > 0 && period > 0) { const int q = int((quota + period - 1) / period); if (q > 0 && q < n) n = q; }
+      }
+    }
+    std::fclose(f);
+    break;
+  }
+  return n > 0 ? n : 1;
+}
 
 } // extern "C"

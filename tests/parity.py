@@ -66,8 +66,15 @@ def check_single_iteration(ch, efs, theta, lib_path=None, enabled=None, rtol=1e-
     return fn
 
 
+# how often check_solve fell back to the float-vs-double calibration (per process; tests read and reset it)
+CALIBRATED = {"count": 0, "cases": []}
+
+
 def check_solve(ch, efs, theta0, opts: ms.GaussNewtonSolverOptions, lib_path=None, enabled=None, param_tol=1e-4, instances=None,
-                compare_history=True):
+                compare_history=True, allow_calibration=True):
+    """``allow_calibration=False``: every compared instance must meet the stated tolerance as is (cfg2 / cfg3 / cfg4); otherwise an
+    instance that misses it is judged against 3x the oracle's own float-vs-double gap on the same inputs, and the use is counted
+    in ``CALIBRATED`` and printed."""
     B = theta0.shape[0]
     fn = build_function(ch, efs, B, lib_path, enabled)
     solver = ms.GaussNewtonSolver(opts, fn)
@@ -85,6 +92,10 @@ def check_solve(ch, efs, theta0, opts: ms.GaussNewtonSolverOptions, lib_path=Non
         worst = max(worst, d)
         tol, etol = param_tol, 1e-3 * abs(err) + 1e-7
         if d > param_tol or abs(out["errors"][b] - err) > etol:
+            assert allow_calibration, ("instance misses the stated tolerance and calibration is not allowed here", b, d, param_tol, out["errors"][b], err)
+            CALIBRATED["count"] += 1
+            CALIBRATED["cases"].append((ch.num_joints, int(b), float(d)))
+            print(f"[parity] calibrated against the oracle's float-vs-double gap: J={ch.num_joints} instance {b} d={d:.3e} (uses so far: {CALIBRATED['count']})")
             # ill-conditioned instance: float rounding alone moves the reference by more than the
             # nominal tolerance. Calibrate with the reference's own float-vs-double gap on the same
             # inputs (the reference runs its tests in both precisions, error_function_helpers.h:38-52).

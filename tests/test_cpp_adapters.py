@@ -48,7 +48,7 @@ int main() {
 """
 
 
-def test_adapter_header_compiles_and_fails_loudly_without_gpu():
+def _build_and_run():
     import __graft_entry__ as g
 
     g.build()
@@ -59,10 +59,19 @@ def test_adapter_header_compiles_and_fails_loudly_without_gpu():
         lib_dir = os.path.dirname(ms.DEFAULT_LIB)
         subprocess.check_call(["g++", "-std=c++17", "-I", os.path.join(ROOT, "include"), src, "-o", exe, "-L", lib_dir, "-lmomentum_b200",
                                f"-Wl,-rpath,{lib_dir}"])
-        p = subprocess.run([exe], capture_output=True, text=True)
-        import torch
+        return subprocess.run([exe], capture_output=True, text=True)
 
-        if torch.cuda.is_available():
-            assert p.returncode == 0 and "solved" in p.stdout, p.stdout + p.stderr
-        else:
-            assert p.returncode == 3 and "no usable sm_100 CUDA device" in p.stdout, p.stdout + p.stderr
+
+def test_adapter_header_compiles_and_fails_loudly_without_gpu():
+    p = _build_and_run()
+    if ms.load_library().mb2_device_count() > 0:
+        assert p.returncode == 0 and "solved" in p.stdout, p.stdout + p.stderr
+    else:
+        assert p.returncode == 3 and "no usable sm_100 CUDA device" in p.stdout, p.stdout + p.stderr
+
+
+@pytest.mark.gpu
+def test_adapter_part1_solves_on_the_gpu():
+    """The C++ host side (Part 1 of the adapters header) drives a real solve on the B200 under `pytest -m gpu`."""
+    p = _build_and_run()
+    assert p.returncode == 0 and "solved" in p.stdout, p.stdout + p.stderr

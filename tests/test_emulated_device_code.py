@@ -61,6 +61,14 @@ def test_plane_and_model_parameters_with_enabled_subset_and_solve():
     opts = ms.GaussNewtonSolverOptions(min_iterations=1, max_iterations=10, threshold=10.0, regularization=0.05)
     parity.check_solve(ch, efs, theta0, opts, EMU_LIB, param_tol=2e-4)
     parity.check_solve(ch, efs, theta0, opts, EMU_LIB, enabled=en, param_tol=2e-4)
+    # negative target weights: no Jacobian row (model_parameters_error_function.cpp:113) but getError counts them (:56-59); the line
+    # search is the consumer of that asymmetry
+    tw = np.asarray(efs[-1].target_weights, np.float64).copy(); tw[[0, 3, 7]] = [-0.7, -1.2, -0.4]
+    efs[-1] = mc.ModelParametersErrorFunction(tw, efs[-1].targets, weight=0.6)
+    parity.check_single_iteration(ch, efs, theta0, EMU_LIB)
+    parity.check_single_iteration(ch, efs, theta0, EMU_LIB, enabled=en)
+    ls = ms.GaussNewtonSolverOptions(min_iterations=4, max_iterations=4, threshold=10.0, regularization=0.05, do_line_search=True)
+    parity.check_solve(ch, efs, theta0, ls, EMU_LIB, param_tol=2e-4)
 
 
 def test_all_families_on_the_tile_scheduled_path():
