@@ -104,6 +104,24 @@ typedef enum mb2_cholesky_mode {
   MB2_CHOLESKY_TILES_SPARSE = 3     /* level-scheduled tiles over the kinematic-tree sparsity of JtJ (min-degree order) */
 } mb2_cholesky_mode;
 
+/* Which kernels run one Gauss-Newton iteration on the tile path (extension; every mode solves the same system with the same device
+ * functions, results agree to float rounding).
+ *   GRAM_CHOLESKY  two launches per iteration: FK / residual / Jacobian strips, then ONE kernel that forms the stored tiles of
+ *                  J^T J + lambda I from the strips on the tensor cores, parks them in TMEM, writes them over the dead strips in shared
+ *                  memory and runs the tile Cholesky + update on them: the normal equations never exist in HBM.
+ *   OFF            three launches per iteration (sweep, tile-sparse Gram to HBM, tile Cholesky).
+ *   PERSISTENT     ONE launch per solve: groups of 256 threads keep an instance in shared memory for all of its iterations (FK sweep
+ *                  included) and stop it on the device; no host round trip, no HBM traffic beyond theta / targets / results. Needs no
+ *                  line search and a plan whose tiles fit in shared memory next to the staged tables. Measured slower than GRAM_CHOLESKY
+ *                  at thousands of instances (three instances per SM cannot hide the sweep's dependent chains; profiles/), so AUTO does
+ *                  not pick it. */
+typedef enum mb2_fused_mode {
+  MB2_FUSED_AUTO = 0,          /* GRAM_CHOLESKY when strips / tiles fit in shared memory, else OFF */
+  MB2_FUSED_OFF = 1,
+  MB2_FUSED_PERSISTENT = 2,    /* or MB2_ERR_UNSUPPORTED */
+  MB2_FUSED_GRAM_CHOLESKY = 3  /* or MB2_ERR_UNSUPPORTED */
+} mb2_fused_mode;
+
 /* solver/solver.h:19-34 SolverOptions + solver/gauss_newton_solver.h:17-59 GaussNewtonSolverOptions,
  * field for field, plus device extensions at the end. */
 typedef struct mb2_gauss_newton_options {
@@ -119,6 +137,7 @@ typedef struct mb2_gauss_newton_options {
   int32_t jtj_mode;               /* mb2_jtj_mode */
   int32_t store_error_history;    /* keep per-iteration error per instance (solver.h:90 getErrorHistory) */
   int32_t cholesky_mode;          /* mb2_cholesky_mode */
+  int32_t fused_mode;             /* mb2_fused_mode */
 } mb2_gauss_newton_options;
 
 typedef struct mb2_character mb2_character;             /* Skeleton + ParameterTransform + ParameterLimits on device */
@@ -234,8 +253,15 @@ int mb2_solver_get_phase_times(mb2_solver* s, double ms[4], uint64_t launches[4]
  * Cholesky (0: dense Eigen-structured kernel), [5] tile multiply-accumulate blocks per factorisation, [6] levels of the
  * tile elimination tree, [7] residual rows m (row groups aligned to 4 in the strip layout), [8] floats per instance of the Jacobian in
  * strip layout (0: K-major matrix), [9] multiply-accumulates per instance of the tile-sparse Gram kernel, [10] its strip pairs,
- * [11] reserved. */
+ * [11] instance groups per CTA of the fused persistent kernel (0: the plan does not fit / was not built for it). */
 int mb2_solver_get_plan_stats(mb2_solver* s, int64_t stats[12]);
+/* Which fused kernel the last solve ran (fused: 0 none, 1 persistent whole-solve kernel, 2 Gram + Cholesky per iteration) and, after
+ * mb2_solver_set_profiling(s, 1), its device time and the per-phase SM cycles of one instance group (persistent kernel: over its whole
+ * share of the batch; Gram + Cholesky: CTA 0 summed over the iterations, [0] = prologue, [1..4] unused): [0] work fetch + theta load, [1] ParameterTransform
+ * + strip zero fill, [2] FK sweep, [3] residual/units, [4] Jacobian cells, [5] Gram (J^T J, J^T r), [6] tiles out of TMEM,
+ * [7] Cholesky diagonal tiles, [8] panel tiles, [9] updates, [10] backward substitution, [11] update + bookkeeping + write-back.
+ * groups = instance groups per CTA of the persistent kernel. Any output pointer may be NULL. No reference counterpart. */
+int mb2_solver_get_fused_profile(mb2_solver* s, int32_t* fused, int32_t* groups, double* kernel_ms, uint64_t phase_cycles[12]);
 
 #ifdef __cplusplus
 }

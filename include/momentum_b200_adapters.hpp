@@ -52,6 +52,7 @@ struct GaussNewtonSolverOptions { // solver.h:19-34 + gauss_newton_solver.h:17-5
   bool subsetLineSearch = false;
   mb2_jtj_mode jtjMode = MB2_JTJ_AUTO;
   mb2_cholesky_mode choleskyMode = MB2_CHOLESKY_AUTO;
+  mb2_fused_mode fusedMode = MB2_FUSED_AUTO;
   bool storeErrorHistory = false;
 
   mb2_gauss_newton_options c() const {
@@ -68,6 +69,7 @@ struct GaussNewtonSolverOptions { // solver.h:19-34 + gauss_newton_solver.h:17-5
     o.subset_line_search = subsetLineSearch;
     o.jtj_mode = jtjMode;
     o.cholesky_mode = choleskyMode;
+    o.fused_mode = fusedMode;
     o.store_error_history = storeErrorHistory;
     return o;
   }

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "ik_chol_sched.h"
+#include "ik_fused.cuh"
 #include "ik_jtj_tc.cuh"
 #include "ik_kernels.cuh"
 #include "ik_plan.h"
@@ -115,6 +116,10 @@ struct DeviceSchedule {
   bool gramValid{false};
   DeviceBuffer<int32_t> gBlob;
   int32_t gBlobInts{0}, gOffsets[8]{};
+  // fused persistent kernel (ik_fused.cuh): every table of the plan as one blob + how many instance groups fit beside it
+  DeviceBuffer<int32_t> fBlob;
+  FusedBlobLayout fLayout{};
+  FusedConfig fConfig{};
 };
 
 struct mb2_solver_function {
@@ -157,7 +162,12 @@ struct mb2_solver {
   mb2_gauss_newton_options opt{};
   DeviceBuffer<float> dH, dDelta, dThetaOrig, dTheta0, dScale, dGradDotDelta, dThetaStage, dGrad, dTiles;
   DeviceBuffer<double> dLastErrors, dTrialErrors, dHistory;
-  DeviceBuffer<int32_t> dActive, dIterations, dStatus, dSearching, dActiveCount;
+  DeviceBuffer<int32_t> dActive, dIterations, dStatus, dSearching, dActiveCount, dWorkCounter;
+  DeviceBuffer<unsigned long long> dPhaseCycles;
+  bool lastFused{false}, lastGramChol{false};
+  int lastFusedGroups{0};
+  cudaEvent_t fusedStart{nullptr}, fusedStop{nullptr};
+  double fusedMs{0};
   int* hActiveCount{nullptr}; // pinned
   uint64_t totalIterations{0}, kernelLaunches{0};
   bool profiling{false};
@@ -167,6 +177,8 @@ struct mb2_solver {
   size_t historyStride{0};
   ~mb2_solver() {
     if (hActiveCount) cudaFreeHost(hActiveCount);
+    if (fusedStart) cudaEventDestroy(fusedStart);
+    if (fusedStop) cudaEventDestroy(fusedStop);
     for (auto& e : events) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }
   }
 };
@@ -285,6 +297,44 @@ int uploadSchedule(mb2_solver_function* f, std::unique_ptr<DeviceSchedule>& ds) 
   return MB2_OK;
 }
 
+// Every table the fused kernel walks, as one 16-byte-aligned blob (bulk-copied into shared memory once per CTA).
+int buildFusedBlob(mb2_solver_function* f, DeviceSchedule& ds, const std::vector<int32_t>& gramBlob, const std::vector<int32_t>& schedBlob, cudaStream_t s) {
+  std::vector<int32_t> blob;
+  auto add = [&](const void* data, size_t bytes) {
+    const int32_t off = int32_t(blob.size());
+    const size_t words = (bytes + 3) / 4;
+    blob.resize(blob.size() + words, 0);
+    if (bytes) std::memcpy(blob.data() + off, data, bytes);
+    while (blob.size() % 4) blob.push_back(0);
+    return off;
+  };
+  const HostCharacter& h = f->ch->host;
+  const Plan& p = f->plan;
+  FusedBlobLayout& L = ds.fLayout;
+  L.parent = add(h.parent.data(), h.parent.size() * 4);
+  L.offset = add(h.offset.data(), h.offset.size() * 4);
+  L.prerot = add(h.prerot.data(), h.prerot.size() * 4);
+  L.ptOuter = add(h.ptOuter.data(), h.ptOuter.size() * 4);
+  L.ptInner = add(h.ptInner.data(), h.ptInner.size() * 4);
+  L.ptVals = add(h.ptVals.data(), h.ptVals.size() * 4);
+  L.ptOffsets = add(h.ptOffsets.data(), h.ptOffsets.size() * 4);
+  L.levelStart = add(h.levelStart.data(), h.levelStart.size() * 4);
+  L.levelJoints = add(h.levelJoints.data(), h.levelJoints.size() * 4);
+  L.efs = add(p.efs.data(), p.efs.size() * sizeof(EfDesc));
+  L.units = add(p.units.data(), p.units.size() * sizeof(UnitDesc));
+  L.cells = add(p.cells.data(), p.cells.size() * sizeof(CellDesc));
+  L.contribs = add(p.contribs.data(), p.contribs.size() * sizeof(ContribDesc));
+  L.limitData = add(p.limitData.data(), p.limitData.size() * 4);
+  L.cols = add(p.deviceCols.data(), p.deviceCols.size() * 4);
+  L.gram = add(gramBlob.data(), gramBlob.size() * 4);
+  L.sched = add(schedBlob.data(), schedBlob.size() * 4);
+  if (blob.empty()) blob.push_back(0);
+  while (blob.size() % 4) blob.push_back(0);
+  L.words = int32_t(blob.size());
+  MB2_CUDA(ds.fBlob.upload(blob, s));
+  return MB2_OK;
+}
+
 // mode 0: every column at its model-parameter index (getJacobian / getJtJR parity);
 // mode 1: solver, only the enabled columns, ascending (dense Eigen-structured Cholesky);
 // mode 2: solver, enabled columns in the Cholesky elimination order + tile schedule (schedDense: dense pattern).
@@ -330,6 +380,15 @@ int ensurePlan(mb2_solver_function* f, int mode, bool schedDense = false, bool a
     ds->dense = schedDense;
     int rc = uploadSchedule(f, ds);
     if (rc != MB2_OK) return rc;
+    if (alignRows) {
+      std::vector<int32_t> gblob2, sblob;
+      int32_t goff[8];
+      makeGramBlob(ds->gram, ds->host, gblob2, goff);
+      CholSchedDev hostView;
+      makeScheduleBlob(ds->host, sblob, hostView);
+      rc = buildFusedBlob(f, *ds, gblob2, sblob, s);
+      if (rc != MB2_OK) return rc;
+    }
     f->sched = std::move(ds);
   }
   f->planMode = mode;
@@ -358,6 +417,14 @@ int ensurePlan(mb2_solver_function* f, int mode, bool schedDense = false, bool a
   if (rc != MB2_OK) return rc;
   rc = uploadWeights(f);
   if (rc != MB2_OK) return rc;
+  if (stripLayout && f->sched) {
+    int dev = 0, optin = 0;
+    MB2_CUDA(cudaGetDevice(&dev));
+    MB2_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    f->planMode = mode; // tables() reads the mode
+    f->planAlignRows = alignRows;
+    f->sched->fConfig = fusedConfigure(f->tables(), f->sched->fLayout, f->sched->dev, f->sched->gram.stride, int(f->sched->gram.tileOrder.size()) / kGramWarps, optin);
+  }
   // Plan tables, schedule / Gram blobs, weights and the Jacobian zero fill were issued on the handle's stream; the solve may run on a
   // caller's stream. A plan build is a rare host-side event: wait for it here instead of threading events through every launch.
   MB2_CUDA(cudaStreamSynchronize(s));
@@ -494,6 +561,8 @@ void mb2_default_gauss_newton_options(mb2_gauss_newton_options* o) {
   o->subset_line_search = 0;
   o->jtj_mode = MB2_JTJ_AUTO;
   o->store_error_history = 0;
+  o->cholesky_mode = MB2_CHOLESKY_AUTO;
+  o->fused_mode = MB2_FUSED_AUTO;
 }
 
 int mb2_character_create(int device, int32_t J, const int32_t* parents, const float* offsets, const float* prerot, int32_t n,
@@ -910,6 +979,88 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
     rc = ensurePlan(f, 2, cholMode == 2, false);
     if (rc != MB2_OK) return rc;
   }
+  // ---- fused persistent kernel: the whole solve in one launch (ik_fused.cuh) ----
+  s->lastFused = false;
+  {
+    const bool eligible = useGram && useSchedule && o.do_line_search == 0 && f->sched->fConfig.groups >= 1 && f->sched->fBlob.p != nullptr;
+    if (o.fused_mode == MB2_FUSED_PERSISTENT && !eligible)
+      return fail(MB2_ERR_UNSUPPORTED, "the fused kernel needs the tile-sparse Gram + tile-scheduled Cholesky path, no line search, and a plan that fits in shared memory");
+    if (o.fused_mode == MB2_FUSED_PERSISTENT && eligible) {
+      const DeviceSchedule& ds = *f->sched;
+      MB2_CUDA(s->dIterations.resize(B));
+      MB2_CUDA(s->dStatus.resize(B));
+      MB2_CUDA(s->dWorkCounter.resize(1));
+      MB2_CUDA(cudaMemsetAsync(s->dWorkCounter.p, 0, sizeof(int32_t), st));
+      if (o.store_error_history) {
+        MB2_CUDA(s->dHistory.resize(size_t(B) * std::max(maxIt, 1)));
+        MB2_CUDA(cudaMemsetAsync(s->dHistory.p, 0, size_t(B) * std::max(maxIt, 1) * sizeof(double), st));
+        s->historyStride = size_t(std::max(maxIt, 1));
+      }
+      FusedArgs fa{};
+      fa.batch = B;
+      fa.T = f->tables();
+      fa.blob = ds.fBlob.p;
+      fa.L = ds.fLayout;
+      fa.S = ds.dev;
+      fa.schedGlobal = ds.dev.blob;
+      for (int k = 0; k < 8; ++k) fa.gramOff[k] = ds.gOffsets[k];
+      fa.numStrips = ds.gram.numStrips;
+      fa.stripStride = ds.gram.stride;
+      fa.residOff = ds.gram.residOff;
+      fa.numOrder = int32_t(ds.gram.tileOrder.size());
+      fa.regularization = o.regularization;
+      fa.threshold = o.threshold;
+      fa.minIterations = minIt;
+      fa.maxIterations = maxIt;
+      fa.theta = theta;
+      fa.ldTheta = n;
+      fa.targets = f->dTargets.p;
+      fa.cweights = f->dWeights.p;
+      fa.errors = f->dErrors.p;
+      fa.iterations = s->dIterations.p;
+      fa.status = s->dStatus.p;
+      fa.history = o.store_error_history ? s->dHistory.p : nullptr;
+      fa.workCounter = s->dWorkCounter.p;
+      fa.phaseCycles = nullptr;
+      if (s->profiling) {
+        MB2_CUDA(s->dPhaseCycles.resize(16));
+        MB2_CUDA(cudaMemsetAsync(s->dPhaseCycles.p, 0, 16 * sizeof(unsigned long long), st));
+        fa.phaseCycles = s->dPhaseCycles.p;
+        if (!s->fusedStart) { MB2_CUDA(cudaEventCreate(&s->fusedStart)); MB2_CUDA(cudaEventCreate(&s->fusedStop)); }
+        MB2_CUDA(cudaEventRecord(s->fusedStart, st));
+      }
+      int dev = 0, sms = 0;
+      MB2_CUDA(cudaGetDevice(&dev));
+      MB2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      {
+        NvtxRange nvtxIt("mb2::fusedSolveKernel (GaussNewtonSolverT::doIteration x maxIterations)");
+        MB2_CUDA(launchFusedSolve(fa, ds.fConfig, sms, s->profiling, st));
+      }
+      if (s->profiling) MB2_CUDA(cudaEventRecord(s->fusedStop, st));
+      for (auto& e : s->events) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }
+      s->events.clear();
+      s->kernelLaunches = 1;
+      s->lastFused = true;
+      s->lastFusedGroups = ds.fConfig.groups;
+      return MB2_OK;
+    }
+  }
+  // ---- Gram + Cholesky in one launch per iteration (gramCholeskyKernel): the default on the tile path ----
+  bool useGramChol = false;
+  if (useGram && useSchedule) {
+    const DeviceSchedule& ds = *f->sched;
+    const int rounds = std::max(int(ds.gram.tileOrder.size()) / kGramWarps, 1);
+    const bool fits = gramCholeskySmemBytes(size_t(ds.gram.stride), ds.gBlobInts, ns, ds.host.nPad, ds.host.numTiles, ds.dev.blobInts) <= size_t(200 * 1024) && 16 * rounds <= 128;
+    if (o.fused_mode == MB2_FUSED_GRAM_CHOLESKY && !fits) return fail(MB2_ERR_UNSUPPORTED, "Gram + Cholesky fusion: strips / tiles of this plan do not fit in shared memory or TMEM");
+    useGramChol = fits && (o.fused_mode == MB2_FUSED_AUTO || o.fused_mode == MB2_FUSED_GRAM_CHOLESKY);
+  } else if (o.fused_mode == MB2_FUSED_GRAM_CHOLESKY) {
+    return fail(MB2_ERR_UNSUPPORTED, "Gram + Cholesky fusion needs the tile-sparse Gram + tile-scheduled Cholesky path");
+  }
+  s->lastGramChol = useGramChol;
+  if (useGramChol && s->profiling) {
+    MB2_CUDA(s->dPhaseCycles.resize(16));
+    MB2_CUDA(cudaMemsetAsync(s->dPhaseCycles.p, 0, 16 * sizeof(unsigned long long), st));
+  }
   const int mode = useGram ? MB2_JTJ_SPARSE_TILES : resolveJtjMode(f, o.jtj_mode == MB2_JTJ_SPARSE_TILES ? MB2_JTJ_AUTO : o.jtj_mode, ns);
   if (mode < 0) return fail(MB2_ERR_UNSUPPORTED, "tensor-core JtJ does not support this shape");
   // normal equations: full symmetric [ns+1][ldH] in device-column order (row/column ns = J^T r)
@@ -918,7 +1069,7 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
   if (!useGram) MB2_CUDA(s->dH.resize(size_t(B) * hStride));
   float* Hbuf = s->dH.p;
   const size_t tilesStride = useGram ? size_t(f->sched->host.numTiles) * 256 + f->sched->host.nPad : 0;
-  if (useGram) MB2_CUDA(s->dTiles.resize(size_t(B) * tilesStride));
+  if (useGram && !(o.fused_mode == MB2_FUSED_AUTO || o.fused_mode == MB2_FUSED_GRAM_CHOLESKY)) MB2_CUDA(s->dTiles.resize(size_t(B) * tilesStride));
   const int ldG = cholGradientLd(ns);
   MB2_CUDA(s->dGrad.resize(size_t(B) * ldG));
   MB2_CUDA(s->dDelta.resize(size_t(B) * ns));
@@ -957,10 +1108,10 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
     recordPhaseStart(s, 0, st);
     MB2_CUDA(launchSweep(sweepArgs(f, theta, s->dActive.p), true, st));
     recordPhaseStop(s, st);
-    recordPhaseStart(s, 1, st);
+    GramArgs g{};
+    if (!useGramChol) recordPhaseStart(s, 1, st);
     if (useGram) {
       const DeviceSchedule& ds = *f->sched;
-      GramArgs g{};
       g.batch = B;
       g.strips = f->dJ.p;
       g.stripStride = size_t(ds.gram.stride);
@@ -970,6 +1121,7 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
       g.numTiles = ds.host.numTiles;
       g.numTileCols = ds.host.numTileCols;
       g.nPad = ds.host.nPad;
+      g.numOrder = int32_t(ds.gram.tileOrder.size());
       g.blob = ds.gBlob.p;
       g.blobInts = ds.gBlobInts;
       g.offTileOrder = ds.gOffsets[0]; g.offTilePairStart = ds.gOffsets[1]; g.offPairA = ds.gOffsets[2]; g.offPairB = ds.gOffsets[3];
@@ -977,12 +1129,16 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
       g.regularization = o.regularization;
       g.out = s->dTiles.p;
       g.outStride = tilesStride;
-      MB2_CUDA(launchGramTiles(g, st));
+      if (!useGramChol) {
+        if (s->dTiles.n < size_t(B) * tilesStride) MB2_CUDA(s->dTiles.resize(size_t(B) * tilesStride));
+        g.out = s->dTiles.p;
+        MB2_CUDA(launchGramTiles(g, st));
+      }
     } else {
       rc = runJtJ(f, mode, ns, Hbuf, ldH, hStride, s->dActive.p, st, s->dGrad.p, ldG);
       if (rc != MB2_OK) return rc;
     }
-    recordPhaseStop(s, st);
+    if (!useGramChol) recordPhaseStop(s, st);
     CholArgs c{};
     c.batch = B;
     c.H = Hbuf;
@@ -1014,7 +1170,14 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
     c.tilesStride = tilesStride;
     c.profile = (it == 0 && cholProfile) ? 1 : 0;
     recordPhaseStart(s, 2, st);
-    if (useSchedule) MB2_CUDA(launchCholeskyScheduled(c, f->sched->dev, st));
+    if (useGramChol) {
+      GramCholArgs gc{};
+      gc.g = g;
+      gc.c = c;
+      gc.c.tilesIn = nullptr;
+      gc.phaseCycles = s->profiling ? s->dPhaseCycles.p : nullptr;
+      MB2_CUDA(launchGramCholesky(gc, f->sched->dev, s->profiling, st));
+    } else if (useSchedule) MB2_CUDA(launchCholeskyScheduled(c, f->sched->dev, st));
     else MB2_CUDA(launchCholesky(c, st));
     recordPhaseStop(s, st);
     if (lineSearch) { // gauss_newton_solver.cpp:283-313 / subset_gauss_newton_solver.cpp:119-141
@@ -1078,6 +1241,10 @@ int mb2_solver_get_results(mb2_solver* s, double* errors, int32_t* iterations, i
   for (int v : its) s->totalIterations += uint64_t(v);
   if (iterations) std::copy(its.begin(), its.end(), iterations);
   if (status) MB2_CUDA(cudaMemcpy(status, s->dStatus.p, size_t(B) * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (s->profiling && s->lastFused && s->fusedStart) {
+    float ms = 0.f;
+    s->fusedMs = cudaEventElapsedTime(&ms, s->fusedStart, s->fusedStop) == cudaSuccess ? double(ms) : 0.0;
+  }
   if (s->profiling) {
     for (int k = 0; k < 4; ++k) { s->phaseMs[k] = 0; s->phaseLaunches[k] = 0; }
     for (auto& e : s->events) {
@@ -1134,7 +1301,29 @@ int mb2_solver_get_plan_stats(mb2_solver* s, int64_t stats[12]) {
   stats[8] = gram ? f->sched->gram.stride : 0;
   stats[9] = gram ? f->sched->gram.macs : 0;
   stats[10] = gram ? int64_t(f->sched->gram.pairA.size()) : 0;
-  stats[11] = 0;
+  stats[11] = gram ? f->sched->fConfig.groups : 0;
+  return MB2_OK;
+}
+
+int mb2_solver_get_fused_profile(mb2_solver* s, int32_t* fused, int32_t* groups, double* kernelMs, uint64_t phaseCycles[12]) {
+  MB2_CHECK(s != nullptr, "null solver");
+  if (fused) *fused = s->lastFused ? 1 : (s->lastGramChol ? 2 : 0);
+  if (groups) *groups = s->lastFused ? s->lastFusedGroups : 0;
+  if (kernelMs) *kernelMs = s->lastFused ? s->fusedMs : (s->lastGramChol ? s->phaseMs[2] : 0.0);
+  if (phaseCycles) {
+    for (int k = 0; k < 12; ++k) phaseCycles[k] = 0;
+    if ((s->lastFused || s->lastGramChol) && s->profiling && s->dPhaseCycles.p) {
+      MB2_DEVICE_GUARD(s->fn->ch->device);
+      unsigned long long h[12];
+      MB2_CUDA(cudaMemcpy(h, s->dPhaseCycles.p, sizeof(h), cudaMemcpyDeviceToHost));
+      if (s->lastFused) {
+        for (int k = 0; k < 12; ++k) phaseCycles[k] = h[k];
+      } else { // gramCholeskyKernel (block 0, summed over the iterations): prologue, gram, tiles from TMEM, diag, panel, update, backward, finish
+        phaseCycles[0] = h[0];
+        for (int k = 1; k < 8; ++k) phaseCycles[4 + k] = h[k];
+      }
+    }
+  }
   return MB2_OK;
 }
 

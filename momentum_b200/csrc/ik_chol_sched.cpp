@@ -320,9 +320,27 @@ std::string buildGramPlan(const CholSchedule& s, const std::vector<int32_t>& cel
       out.quad.push_back(out.pairA[p + 1] * 64); out.quad.push_back(out.pairB[p + 1] * 64);
     }
   }
-  out.tileOrder.resize(s.numTiles);
-  for (int t = 0; t < s.numTiles; ++t) out.tileOrder[t] = t;
-  std::stable_sort(out.tileOrder.begin(), out.tileOrder.end(), [&](int a, int b) { return pairs[a].size() > pairs[b].size(); });
+  // Tiles are dealt to the kGramWarps warps of a CTA / instance group: longest first, each to the least loaded warp (the root tile of
+  // a humanoid collects 42 pairs, the median tile 2). tileOrder is the resulting [rounds][kGramWarps] table, -1 = nothing this round:
+  // warp w walks entries w, w + kGramWarps, ...
+  {
+    std::vector<int> byLoad(s.numTiles);
+    for (int t = 0; t < s.numTiles; ++t) byLoad[t] = t;
+    std::stable_sort(byLoad.begin(), byLoad.end(), [&](int a, int b) { return pairs[a].size() > pairs[b].size(); });
+    std::vector<std::vector<int>> ofWarp(kGramWarps);
+    std::vector<int64_t> load(kGramWarps, 0);
+    for (int t : byLoad) {
+      int w = 0;
+      for (int k = 1; k < kGramWarps; ++k) if (load[k] < load[w]) w = k;
+      ofWarp[w].push_back(t);
+      load[w] += int64_t(pairs[t].size()) / 2 + 2; // mma steps + the tile's fixed cost (epilogue)
+    }
+    size_t rounds = 0;
+    for (const auto& v : ofWarp) rounds = std::max(rounds, v.size());
+    out.tileOrder.assign(rounds * kGramWarps, -1);
+    for (int w = 0; w < kGramWarps; ++w)
+      for (size_t r = 0; r < ofWarp[w].size(); ++r) out.tileOrder[r * kGramWarps + w] = ofWarp[w][r];
+  }
   // where each cell writes: strips of one quad are consecutive (ascending tile column); a multi-row unit owns its quads, so its
   // quads all have the same tile columns and the same cell is a constant number of strips further in the next quad
   std::map<int, int> stripsOfQuad;

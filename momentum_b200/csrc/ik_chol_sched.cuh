@@ -260,11 +260,14 @@ MB2_HD void cholDiagTile(float* tile, float* y16, int hl, unsigned hmask, float 
   // Square-root-free elimination keeps the per-step dependency chain short (pivot broadcast -> reciprocal -> one multiply ->
   // one fused multiply-add); the 1/sqrt(pivot) scalings and the right-hand side ride along off that chain:
   //   A = U D U^T (U unit lower, U[r][k] = a_r[k] / d_k),  L = U D^1/2,  y = L^-1 g = D^-1/2 U^-1 g.
-  // The gather fills the tile as S[c][r] = H(r, c) for r >= c only: matrix row hl, columns k <= hl, is storage column hl.
+  // W = L^-1 = D^-1/2 U^-1 comes out of the SAME sixteen steps (Gauss-Jordan): the row operations that eliminate A are applied to an
+  // identity matrix E as well, row_r(E) -= U[r][k] row_k(E) for r > k, which leaves E = U^-1. One dependent chain of sixteen steps per
+  // diagonal tile instead of two (factorise, then invert by substitution), and no shared-memory traffic inside it.
+  // The gather fills the tile as S[c][r] = H(r, c), a symmetric tile: matrix row hl is storage column hl.
 #if defined(__CUDA_ARCH__)
-  float a[16], rd[16];
+  float a[16], e[16];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) a[k] = tile[tileIdx(k, hl)];
+  for (int k = 0; k < 16; ++k) { a[k] = tile[tileIdx(k, hl)]; e[k] = (k == hl) ? 1.f : 0.f; }
   float z = y16[hl], rdSelf = 0.f;
   __syncwarp(hmask); // every lane has read its column before any lane overwrites the tile
 #pragma unroll
@@ -273,66 +276,51 @@ MB2_HD void cholDiagTile(float* tile, float* y16, int hl, unsigned hmask, float 
     if (!(piv > 0.f)) { piv = fallback; if (hl == k) *fail = 1; }
     float inv;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(piv)); // one MUFU on the dependency chain (1 ulp; the step is damped Gauss-Newton)
-    rd[k] = rsqrtf(piv);
-    if (hl == k) rdSelf = rd[k];
+    const float rdk = rsqrtf(piv);
+    if (hl == k) rdSelf = rdk;
     const float zk = __shfl_sync(hmask, z, k, 16);
-    const float t = a[k] * inv; // U[hl][k] for hl > k
+    const float t = a[k] * inv;           // U[hl][k] for hl > k
+    const float tm = hl > k ? t : 0.f;    // rows <= k of E (and of the right-hand side) are finished
 #pragma unroll
     for (int j = k + 1; j < 16; ++j) a[j] -= t * __shfl_sync(hmask, a[k], j, 16);
-    if (hl > k) z -= t * zk;
+#pragma unroll
+    for (int j = 0; j < k; ++j) e[j] -= tm * __shfl_sync(hmask, e[j], k, 16);
+    e[k] -= tm;                           // row k of E has a one on the diagonal
+    z -= tm * zk;
   }
-  y16[hl] = z * rdSelf; // (rd[hl] would index the register array dynamically and push it to local memory)
-  // L^T into the tile: Lt[k][hl] = L[hl][k] = a_hl[k] / sqrt(d_k)  (k < hl); the diagonal is not needed (rd holds its inverse)
+  y16[hl] = z * rdSelf;
+  // row hl of W = D^-1/2 U^-1 (zero above the diagonal, 1/sqrt(d) on it), written as one swizzled row: conflict-free float4 stores
 #pragma unroll
-  for (int k = 0; k < 16; ++k) tile[tileIdx(k, hl)] = a[k] * rd[k];
-  __syncwarp(hmask);
-  // column hl of W = L^-1 by column-oriented forward substitution against e_hl: one dependent multiply-add per step;
-  // row i of L^T (= column i of L) is a broadcast read
-  float sacc[16], w[16];
-#pragma unroll
-  for (int m = 0; m < 16; ++m) sacc[m] = (m == hl) ? 1.f : 0.f;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    w[i] = sacc[i] * rd[i];
-    float Lcol[16];
-    tileLoadRow(tile, i, Lcol);
-#pragma unroll
-    for (int m = i + 1; m < 16; ++m) sacc[m] -= Lcol[m] * w[i];
-  }
-  __syncwarp(hmask);
-#pragma unroll
-  for (int i = 0; i < 16; ++i) tile[tileIdx(i, hl)] = w[i]; // W[i][hl]; zero above the diagonal
+  for (int j = 0; j < 16; ++j) e[j] *= rdSelf;
+  tileStoreRow(tile, hl, e);
 #else
   if (hl != 0) return; // host emulation: one caller plays the sixteen lanes in lock step with the same operation order
   (void)hmask;
-  float A[16][16], z[16], rd[16]; // A[lane][k]
-  for (int l = 0; l < 16; ++l) { for (int k = 0; k < 16; ++k) A[l][k] = tile[tileIdx(k, l)]; z[l] = y16[l]; }
+  float A[16][16], E[16][16], z[16], rd[16]; // A[lane][k], E[lane][j]
+  for (int l = 0; l < 16; ++l) { for (int k = 0; k < 16; ++k) { A[l][k] = tile[tileIdx(k, l)]; E[l][k] = (k == l) ? 1.f : 0.f; } z[l] = y16[l]; }
   for (int k = 0; k < 16; ++k) {
     float piv = A[k][k];
     if (!(piv > 0.f)) { piv = fallback; *fail = 1; }
     const float inv = 1.f / piv;
     rd[k] = 1.f / sqrtf(piv);
     const float zk = z[k];
-    float colk[16];
-    for (int l = 0; l < 16; ++l) colk[l] = A[l][k];
+    float colk[16], ek[16];
+    for (int l = 0; l < 16; ++l) { colk[l] = A[l][k]; ek[l] = E[k][l]; }
     for (int l = 0; l < 16; ++l) {
       const float t = colk[l] * inv;
+      const float tm = l > k ? t : 0.f;
       for (int j = k + 1; j < 16; ++j) A[l][j] -= t * colk[j];
-      if (l > k) z[l] -= t * zk;
+      for (int j = 0; j < k; ++j) E[l][j] -= tm * ek[j];
+      E[l][k] -= tm;
+      z[l] -= tm * zk;
     }
   }
-  for (int l = 0; l < 16; ++l) y16[l] = z[l] * rd[l];
-  for (int l = 0; l < 16; ++l) for (int k = 0; k < 16; ++k) tile[tileIdx(k, l)] = A[l][k] * rd[k];
-  float W[16][16]; // W[i][lane]
   for (int l = 0; l < 16; ++l) {
-    float sacc[16];
-    for (int m = 0; m < 16; ++m) sacc[m] = (m == l) ? 1.f : 0.f;
-    for (int i = 0; i < 16; ++i) {
-      W[i][l] = sacc[i] * rd[i];
-      for (int m = i + 1; m < 16; ++m) sacc[m] -= tile[tileIdx(i, m)] * W[i][l];
-    }
+    y16[l] = z[l] * rd[l];
+    float w[16];
+    for (int j = 0; j < 16; ++j) w[j] = E[l][j] * rd[l];
+    tileStoreRow(tile, l, w);
   }
-  for (int i = 0; i < 16; ++i) for (int l = 0; l < 16; ++l) tile[tileIdx(i, l)] = W[i][l];
 #endif
 }
 

@@ -68,10 +68,11 @@ inline int cholSchedLdH(int n) { return (n + 1 + 15) / 16 * 16; }
 // J[4q..4q+3][gi0(K)..gi0(K)+15] -- one TMA box of the K-major device Jacobian, landing as [16 columns][4 rows]. A strip
 // exists only where a unit with rows in q has a cell in tile column K. Tile (I,J) = sum over quads touching both I and J
 // of strip(q,I)^T strip(q,J); block K of J^T r = sum over its strips of strip^T r[4q..4q+3].
+constexpr int kGramWarps = 8; // warps that share the tiles of one instance (gramTilesKernel, gramCholeskyKernel, a group of the fused kernel)
 struct GramPlan {
   int32_t numStrips{0}, numTiles{0}, numTileCols{0};
   std::vector<int32_t> stripCoord;    // [numStrips][2] {first row 4q, first device column gi0(K)}; strips are ordered by (quad, tile column)
-  std::vector<int32_t> tileOrder;     // tiles by decreasing pair count (work is dealt round-robin to warps in this order)
+  std::vector<int32_t> tileOrder;     // [rounds][kGramWarps] tile of warp w in round r, -1 = none (longest-first / least-loaded assignment)
   std::vector<int32_t> tilePairStart; // [numTiles + 1] indexed by tile id
   std::vector<int32_t> pairA, pairB;  // strips of block row I / block column J of the tile
   std::vector<int32_t> tileQuadStart; // [numTiles + 1] the same lists, two pairs per entry, as the kernel consumes them:

@@ -134,6 +134,64 @@ MB2_HD void fkJoint(const FunctionTables& T, int j, const float* jp, float* js) 
   out[7] = sp * sl;
 }
 
+// ---- The same joint state in three data-parallel passes (what the kernels run) -----------------------------------------------
+// JointStateT::set mixes work that needs the parent (two compositions) with work that does not (three sin/cos pairs, the local
+// rotation chain, exp2). Splitting it lets every joint of the skeleton do the expensive part at once, leaves ~50 dependent
+// flops per tree level, and turns the derivative axes into one more flat pass:
+//   fkLocal   (all joints)         t_l, q_l = preRot Rz Ry Rx, s_l, and the DOF axes in the PARENT frame: a_2 = preRot z, a_1 = (preRot Rz) y,
+//                                  a_0 = (preRot Rz Ry) x                                                   (joint_state.cpp:44-62)
+//   fkCompose (level by level)     t = t_p + q_p (s_p t_l), q = q_p q_l, s = s_p s_l                          (transform.h:124-129)
+//   fkAxis    (all joints x 3)     rotationAxis.col(i) = q_p a_i   [= (q_p preRot ...) e_i of joint_state.cpp:51-55: one rotation of a
+//                                  rotated vector instead of a rotation by a quaternion product; equal up to rounding]
+// fkJoint above stays the statement-by-statement form (CPU emulation of the oracle order, tests).
+template <bool kDeriv>
+MB2_HD void fkLocal(const FunctionTables& T, int j, const float* jp, float* js) {
+  const float* p = jp + j * kParametersPerJoint;
+  Q4 ql = ld4(T.prerot + 4 * j);
+  float* out = js + j * kJointStateStride;
+#pragma unroll
+  for (int index = 2; index >= 0; --index) {
+    if (kDeriv) {
+      const F3 a = qrot(ql, f3(index == 0 ? 1.f : 0.f, index == 1 ? 1.f : 0.f, index == 2 ? 1.f : 0.f));
+      out[8 + 3 * index] = a.x; out[9 + 3 * index] = a.y; out[10 + 3 * index] = a.z;
+    }
+    const float ha = 0.5f * p[3 + index];
+    float sn, cs;
+#if defined(__CUDA_ARCH__)
+    sincosf(ha, &sn, &cs);
+#else
+    sn = sinf(ha); cs = cosf(ha);
+#endif
+    ql = qmul(ql, q4(index == 0 ? sn : 0.f, index == 1 ? sn : 0.f, index == 2 ? sn : 0.f, cs));
+  }
+  out[0] = T.offset[3 * j] + p[0]; out[1] = T.offset[3 * j + 1] + p[1]; out[2] = T.offset[3 * j + 2] + p[2];
+  out[3] = ql.x; out[4] = ql.y; out[5] = ql.z; out[6] = ql.w;
+  out[7] = exp2f(p[6]);
+}
+// the parent (if any) already holds its world transform
+MB2_HD void fkCompose(const FunctionTables& T, int j, float* js) {
+  const int par = T.parent[j];
+  if (par < 0) return; // identity parent: world = local, bit for bit
+  const float* ps = js + par * kJointStateStride;
+  float* out = js + j * kJointStateStride;
+  const F3 tp = ld3(ps);
+  const Q4 qp = ld4(ps + 3);
+  const float sp = ps[7];
+  const F3 t = tp + qrot(qp, sp * ld3(out));
+  const Q4 q = qmul(qp, ld4(out + 3));
+  out[0] = t.x; out[1] = t.y; out[2] = t.z;
+  out[3] = q.x; out[4] = q.y; out[5] = q.z; out[6] = q.w;
+  out[7] = sp * out[7];
+}
+// after every joint is composed: world direction of DOF axis `index` of joint j
+MB2_HD void fkAxis(const FunctionTables& T, int j, int index, float* js) {
+  const int par = T.parent[j];
+  if (par < 0) return;
+  float* a = js + j * kJointStateStride + 8 + 3 * index;
+  const F3 w = qrot(ld4(js + par * kJointStateStride + 3), ld3(a));
+  a[0] = w.x; a[1] = w.y; a[2] = w.z;
+}
+
 // translationAxis of joint a = parent.toLinear() (joint_state.cpp:36-42), column d
 MB2_HD F3 translationAxisCol(const FunctionTables& T, const float* js, int a, int d) {
   const int par = T.parent[a];

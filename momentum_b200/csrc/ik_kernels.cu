@@ -11,9 +11,11 @@
 // The dense tensor-core JtJ (tcgen05, TMEM accumulators, TMA-fed) lives in ik_jtj_tc.cu; PTX wrappers in ik_ptx.cuh.
 #include "ik_kernels.cuh"
 
+#include <algorithm>
 #include <cstdio>
 
 #include "ik_chol.cuh"
+#include "ik_chol_sched.h"
 #include "ik_jtj_tc.cuh"
 #include "ik_ptx.cuh"
 #include "ik_device.cuh"
@@ -99,9 +101,17 @@ __global__ void __launch_bounds__(512) sweepKernel(const SweepArgs a) {
     groupSync();
     for (int row = gl; row < numJointParams; row += gs) jp[row] = jointParameterRow(T, row, th);
     groupSync();
-    for (int lvl = 0; lvl < T.numLevels; ++lvl) {
+    // SkeletonState::set in three data-parallel passes (ik_device.cuh): every joint's local part at once, ~50 dependent flops per
+    // tree level, then the derivative axes of all joints at once
+    for (int j = gl; j < T.numJoints; j += gs) fkLocal<kJacobian>(T, j, jp, js);
+    groupSync();
+    for (int lvl = 1; lvl < T.numLevels; ++lvl) { // level 0 = roots: world = local
       const int end = T.levelStart[lvl + 1];
-      for (int k = T.levelStart[lvl] + gl; k < end; k += gs) fkJoint<kJacobian>(T, T.levelJoints[k], jp, js);
+      for (int k = T.levelStart[lvl] + gl; k < end; k += gs) fkCompose(T, T.levelJoints[k], js);
+      groupSync();
+    }
+    if (kJacobian) {
+      for (int i = gl; i < 3 * T.numJoints; i += gs) fkAxis(T, i / 3, i % 3, js);
       groupSync();
     }
     if (a.stateOut != nullptr) {
@@ -426,7 +436,7 @@ cudaError_t launchCholesky(const CholArgs& a, cudaStream_t stream) {
 // (GramPlan): ~20x fewer multiply-adds than the dense product, exact fp32. One CTA per instance: every strip arrives as one
 // TMA box of the K-major Jacobian, a warp owns a tile at a time, the output is already in the Cholesky kernel's tile layout.
 // ------------------------------------------------------------------------------------------------
-constexpr int kGramThreads = 256;
+constexpr int kGramThreads = 32 * kGramWarps;
 
 size_t gramTilesSmemBytes(size_t stripStride, int blobInts) { return 128 + sizeof(float) * (stripStride + 64) + 16 + sizeof(int32_t) * size_t((blobInts + 3) & ~3); }
 
@@ -460,8 +470,9 @@ __global__ void __launch_bounds__(kGramThreads) gramTilesKernel(const GramArgs a
   float* out = a.out + size_t(b) * a.outStride;
   int laneOff[8];
   gramLaneOffsets(lane, laneOff);
-  for (int ti = warp; ti < a.numTiles; ti += kGramThreads / 32) {
+  for (int ti = warp; ti < a.numOrder; ti += kGramThreads / 32) {
     const int t = tileOrder[ti];
+    if (t < 0) continue;
     float acc[2][4];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
@@ -639,6 +650,167 @@ cudaError_t launchCholeskyScheduled(const CholArgs& a, const CholSchedDev& sched
   else if (wide) choleskyScheduledKernel<512, false><<<a.batch, 512, smem, stream>>>(hmap, a, sched);
   else if (prof) choleskyScheduledKernel<256, true><<<a.batch, 256, smem, stream>>>(hmap, a, sched);
   else choleskyScheduledKernel<256, false><<<a.batch, 256, smem, stream>>>(hmap, a, sched);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2s + K3 fused (default on the tile path): one CTA per instance, three CTAs per SM.
+//   prologue   strips + residual of the instance, the Gram plan and the Cholesky schedule arrive as bulk copies on one mbarrier
+//   Gram       a warp owns a tile at a time (longest-first assignment); finished accumulators are parked in TMEM
+//              (tcgen05.st) because the tiles are about to overwrite the strips they are computed from
+//   restore    tcgen05.ld -> 16x16 tiles of J^T J + lambda I in the Cholesky layout, over the dead strips
+//   Cholesky   level-scheduled tile factorisation, both substitutions, theta -= delta, SolverT bookkeeping (cholFinish)
+// The stored tiles (0.45 GB per iteration on the cfg3 shard) never exist in HBM and the second launch is gone.
+// ------------------------------------------------------------------------------------------------
+size_t gramCholeskySmemBytes(size_t stripStride, int gramBlobInts, int n, int nPad, int numTiles, int schedBlobInts) {
+  const size_t uni = std::max<size_t>(size_t(numTiles) * 256, stripStride + 64);
+  return 128 + sizeof(float) * (((uni + 3) & ~size_t(3)) + size_t(nPad) + 2 * size_t((n + 3) & ~3)) + sizeof(int32_t) * (size_t((gramBlobInts + 3) & ~3) + size_t((schedBlobInts + 3) & ~3)) + 64;
+}
+
+template <bool kProfile>
+__global__ void __launch_bounds__(kGramThreads, 3) gramCholeskyKernel(const GramCholArgs a, const CholSchedDev Sg, const int tmemColumns) {
+  extern __shared__ __align__(16) float gcSmem[];
+  const GramArgs& g = a.g;
+  const CholArgs& c = a.c;
+  const int b = blockIdx.x;
+  if (c.active[b] == 0) return;
+  const int n = c.ns, tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31, hw = tid >> 4, hl = tid & 15;
+  const unsigned hmask = 0xFFFFu << (16 * ((tid >> 4) & 1));
+  float* U = gcSmem + (((128u - (smemAddr(gcSmem) & 127u)) & 127u) >> 2); // strips | residual | zero strip, later the tiles
+  const size_t tileFloats = size_t(Sg.numTiles) * 256, sweepFloats = g.stripStride + 64;
+  const size_t uni = ((tileFloats > sweepFloats ? tileFloats : sweepFloats) + 3) & ~size_t(3);
+  float* strips = U;
+  float* resid = U + g.residOff;
+  float* tiles = U;
+  float* y = U + uni;
+  float* gsub = y + Sg.nPad;
+  float* dsub = gsub + ((n + 3) & ~3);
+  int32_t* gtab = reinterpret_cast<int32_t*>(dsub + ((n + 3) & ~3));
+  int32_t* stab = gtab + ((g.blobInts + 3) & ~3);
+  int* flags = reinterpret_cast<int*>(stab + ((Sg.blobInts + 3) & ~3));
+  uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(flags + 2);
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(flags + 4);
+  long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt = 0;
+  if constexpr (kProfile) pt = clock64();
+#define MB2_GC(k) if constexpr (kProfile) { const long long now = clock64(); pc[k] += now - pt; pt = now; }
+  const uint32_t barAddr = smemAddr(bar);
+  const uint32_t stripBytes = uint32_t(g.stripStride) * 4u, gBytes = uint32_t((g.blobInts + 3) & ~3) * 4u, sBytes = uint32_t((Sg.blobInts + 3) & ~3) * 4u;
+  if (tid == 0) {
+    flags[0] = 0;
+    mbarInit(barAddr, 1);
+    fenceBarrierInit();
+    mbarExpectTx(barAddr, stripBytes + gBytes + sBytes);
+    const char* src = reinterpret_cast<const char*>(g.strips + size_t(b) * g.stripStride);
+    for (uint32_t off = 0; off < stripBytes; off += 16384u) bulkLoad(smemAddr(strips) + off, src + off, stripBytes - off < 16384u ? stripBytes - off : 16384u, barAddr);
+    bulkLoad(smemAddr(gtab), g.blob, gBytes, barAddr);
+    bulkLoad(smemAddr(stab), Sg.blob, sBytes, barAddr);
+  }
+  if (warp == 1) tmemAlloc(smemAddr(tmemSlot), uint32_t(tmemColumns));
+  if (tid >= 64 && tid < 128) strips[g.stripStride + (tid - 64)] = 0.f; // the all-zero strip that pads odd pair lists
+  tcgenFenceBeforeSync();
+  __syncthreads();
+  tcgenFenceAfterSync();
+  const uint32_t tmemBase = *reinterpret_cast<volatile uint32_t*>(tmemSlot);
+  const uint32_t tmemWarp = tmemBase + (uint32_t((warp & 3) * 32) << 16) + uint32_t((warp >> 2) * (tmemColumns / 2)); // lane quarter; two warps share one
+  mbarWaitRelaxed(barAddr, 0);
+  MB2_GC(0)
+  const int32_t* tileOrder = gtab + g.offTileOrder, *tileQuadStart = gtab + g.offTilePairStart, *quads = gtab + g.offPairA;
+  const int32_t* colStripStart = gtab + g.offColStripStart, *colStrip = gtab + g.offColStrip, *stripRow = gtab + g.offStripRow, *tileInfo = gtab + g.offTileInfo;
+  const CholSchedDev S = rebaseSchedule(Sg, stab);
+  int laneOff[8];
+  gramLaneOffsets(lane, laneOff);
+  // ---- Gram ----
+  {
+    int slot = 0;
+    for (int ti = warp; ti < g.numOrder; ti += kGramThreads / 32, ++slot) {
+      const int t = tileOrder[ti];
+      if (t < 0) continue;
+      float acc[2][4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      gramTileAccumulate(strips, quads, tileQuadStart[t], tileQuadStart[t + 1], lane, acc);
+      tmemPark8(tmemWarp + 8u * slot, &acc[0][0]);
+    }
+    for (int K = hw; K < S.numTileCols; K += kGramThreads / 16)
+      y[16 * K + hl] = gramVectorEntry(strips, resid, colStrip, stripRow, colStripStart[K], colStripStart[K + 1], hl);
+    tmemParkWait();
+  }
+  __syncthreads();
+  MB2_GC(1)
+  {
+    int slot = 0;
+    for (int ti = warp; ti < g.numOrder; ti += kGramThreads / 32, ++slot) {
+      const int t = tileOrder[ti];
+      if (t < 0) continue;
+      float acc[2][4];
+      tmemFetch8(tmemWarp + 8u * slot, &acc[0][0]);
+      gramTileStore(tiles + size_t(t) * 256, acc, tileInfo[t], g.regularization, lane, laneOff);
+    }
+    for (int s2 = tid; s2 < S.nPad; s2 += kGramThreads) {
+      const int p = S.perm[s2];
+      if (p >= 0) gsub[p] = y[s2];
+    }
+  }
+  __syncthreads();
+  MB2_GC(2)
+  // ---- level-scheduled Cholesky (same phases as choleskyScheduledKernel) ----
+  for (int L = 0; L < S.numLevels; ++L) {
+    for (int ci = S.levelColStart[L] + hw; ci < S.levelColStart[L + 1]; ci += kGramThreads / 16) {
+      const int K = S.levelCols[ci];
+      cholDiagTile(tiles + size_t(S.diagTile[K]) * 256, y + 16 * K, hl, hmask, c.regularization, flags);
+    }
+    __syncthreads();
+    MB2_GC(3)
+    for (int pi = S.levelPanelStart[L] + warp; pi < S.levelPanelStart[L + 1]; pi += kGramThreads / 32) {
+      float* ptile = tiles + size_t(S.panelTile[pi]) * 256;
+      float x[2][4];
+      cholPanelProduct(ptile, tiles + size_t(S.panelDiag[pi]) * 256, lane, x);
+      __syncwarp();
+      cholPanelStore(ptile, lane, x);
+    }
+    __syncthreads();
+    MB2_GC(4)
+    for (int ti = S.levelTaskStart[L] + warp; ti < S.levelTaskStart[L + 1]; ti += kGramThreads / 32) cholUpdateTask(tiles, S, ti, lane);
+    for (int vi = S.levelVTaskStart[L] + hw; vi < S.levelVTaskStart[L + 1]; vi += kGramThreads / 16) cholVectorTask(tiles, y, S, vi, hl);
+    __syncthreads();
+    MB2_GC(5)
+  }
+  for (int L = S.numLevels - 1; L >= 0; --L) {
+    for (int ci = S.levelColStart[L] + hw; ci < S.levelColStart[L + 1]; ci += kGramThreads / 16) cholBackwardColumn(tiles, y, S, S.levelCols[ci], hl, hmask);
+    __syncthreads();
+  }
+  MB2_GC(6)
+  for (int i = tid; i < S.nPad; i += kGramThreads) { const int p = S.perm[i]; if (p >= 0) dsub[p] = y[i]; }
+  __syncthreads();
+  cholFinish(c, b, n, dsub, gsub, flags[0] != 0);
+  MB2_GC(7)
+  if constexpr (kProfile) {
+    if (b == 0 && tid == 0 && a.phaseCycles != nullptr)
+      for (int k = 0; k < 8; ++k) a.phaseCycles[k] += (unsigned long long)pc[k];
+  }
+#undef MB2_GC
+  tcgenFenceBeforeSync();
+  __syncthreads();
+  if (warp == 1) tmemFree(tmemBase, uint32_t(tmemColumns));
+}
+
+cudaError_t launchGramCholesky(const GramCholArgs& a, const CholSchedDev& sched, bool profile, cudaStream_t stream) {
+  const size_t smem = gramCholeskySmemBytes(a.g.stripStride, a.g.blobInts, a.c.ns, sched.nPad, sched.numTiles, sched.blobInts);
+  if (smem > size_t(g_maxSmemOptin) || (a.g.stripStride & 3) != 0) return cudaErrorInvalidConfiguration;
+  // TMEM: two warps share a lane quarter, each parks up to `rounds` tiles of 8 columns; allocations are powers of two >= 32,
+  // and the (up to three) CTAs of an SM must fit in its 512 columns together
+  const int rounds = std::max(a.g.numOrder / (kGramThreads / 32), 1);
+  int columns = 32;
+  while (columns < 2 * 8 * rounds) columns <<= 1;
+  if (columns > 128) return cudaErrorInvalidConfiguration;
+  cudaError_t e = profile ? cudaFuncSetAttribute(gramCholeskyKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))
+                          : cudaFuncSetAttribute(gramCholeskyKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (e != cudaSuccess) return e;
+  if (profile) gramCholeskyKernel<true><<<a.c.batch, kGramThreads, smem, stream>>>(a, sched, columns);
+  else gramCholeskyKernel<false><<<a.c.batch, kGramThreads, smem, stream>>>(a, sched, columns);
   return cudaGetLastError();
 }
 

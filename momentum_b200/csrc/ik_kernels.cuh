@@ -73,6 +73,7 @@ struct GramArgs {            // K2s: stored tiles of J^T J + lambda I and J^T r 
   int32_t residOff;          // GramPlan::residOff
   const int32_t* active;
   int32_t numStrips, numTiles, numTileCols, nPad;
+  int32_t numOrder;          // entries of the tile-order table ([rounds][kGramWarps], -1 = idle)
   // the GramPlan tables as one int32 blob (staged in shared memory by the kernel); offsets in ints
   const int32_t* blob;
   int32_t blobInts;
@@ -83,6 +84,16 @@ struct GramArgs {            // K2s: stored tiles of J^T J + lambda I and J^T r 
 };
 cudaError_t launchGramTiles(const GramArgs& a, cudaStream_t stream);
 size_t gramTilesSmemBytes(size_t stripStride, int blobInts);
+
+// K2s + K3 in one launch: strips in (bulk copy), Gram accumulators parked in TMEM, tiles written over the strips, tile Cholesky,
+// update. No tile round trip through HBM and no second launch; `g.out` is unused.
+struct GramCholArgs {
+  GramArgs g;
+  CholArgs c;
+  unsigned long long* phaseCycles; // optional [8], profiling instantiation: prologue, gram, tiles from TMEM, diag, panel, update, backward, finish (block 0)
+};
+size_t gramCholeskySmemBytes(size_t stripStride, int gramBlobInts, int n, int nPad, int numTiles, int schedBlobInts);
+cudaError_t launchGramCholesky(const GramCholArgs& a, const CholSchedDev& sched, bool profile, cudaStream_t stream);
 
 cudaError_t launchSweep(const SweepArgs& a, bool jacobian, cudaStream_t stream);
 size_t sweepSmemPerInstance(const FunctionTables& T, int warpsPerInstance);

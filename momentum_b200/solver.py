@@ -27,6 +27,8 @@ SIZE_MAX = 2 ** 64 - 1
 JTJ_AUTO, JTJ_FP32_SIMT, JTJ_TF32X3, JTJ_TF32, JTJ_SPARSE_TILES = 0, 1, 2, 3, 4
 INSTANCE_OK, INSTANCE_CHOLESKY_BREAKDOWN, INSTANCE_NON_FINITE = 0, 1, 2
 CHOLESKY_AUTO, CHOLESKY_DENSE_EIGEN, CHOLESKY_TILES_DENSE, CHOLESKY_TILES_SPARSE = 0, 1, 2, 3
+FUSED_AUTO, FUSED_OFF, FUSED_PERSISTENT, FUSED_GRAM_CHOLESKY = 0, 1, 2, 3
+FUSED_ON = FUSED_PERSISTENT
 
 
 class MomentumB200Error(RuntimeError):
@@ -41,7 +43,7 @@ class _Options(C.Structure):
     _fields_ = [("min_iterations", C.c_uint64), ("max_iterations", C.c_uint64), ("threshold", C.c_float), ("verbose", C.c_int32),
                 ("regularization", C.c_float), ("do_line_search", C.c_int32), ("use_block_jtj", C.c_int32),
                 ("target_rows_per_chunk", C.c_uint64), ("subset_line_search", C.c_int32), ("jtj_mode", C.c_int32),
-                ("store_error_history", C.c_int32), ("cholesky_mode", C.c_int32)]
+                ("store_error_history", C.c_int32), ("cholesky_mode", C.c_int32), ("fused_mode", C.c_int32)]
 
 
 _fp = C.POINTER(C.c_float)
@@ -61,7 +63,7 @@ CABI_SYMBOLS = [
     "mb2_solver_function_get_jacobian", "mb2_solver_function_get_jtjr", "mb2_solver_function_get_skeleton_state", "mb2_solver_create",
     "mb2_solver_destroy", "mb2_solver_set_options", "mb2_solver_set_enabled_parameters", "mb2_solver_solve", "mb2_solver_solve_device",
     "mb2_solver_get_results", "mb2_solver_get_error_history", "mb2_solver_get_counters", "mb2_solver_set_profiling",
-    "mb2_solver_get_phase_times", "mb2_solver_get_plan_stats",
+    "mb2_solver_get_phase_times", "mb2_solver_get_plan_stats", "mb2_solver_get_fused_profile",
 ]
 
 _libs = {}
@@ -115,6 +117,8 @@ def load_library(path: Optional[str] = None):
     L.mb2_solver_get_counters.argtypes = [vp, _up, _up]
     if hasattr(L, "mb2_solver_get_plan_stats"):
         L.mb2_solver_get_plan_stats.argtypes = [vp, C.POINTER(C.c_int64)]
+    if hasattr(L, "mb2_solver_get_fused_profile"):
+        L.mb2_solver_get_fused_profile.argtypes = [vp, _ip, _ip, _dp, _up]
     L.mb2_default_gauss_newton_options.argtypes = [C.POINTER(_Options)]
     _libs[path] = L
     return L
@@ -159,11 +163,12 @@ class GaussNewtonSolverOptions(SolverOptions):
     jtj_mode: int = JTJ_AUTO
     store_error_history: bool = False
     cholesky_mode: int = 0  # CHOLESKY_AUTO
+    fused_mode: int = 0     # FUSED_AUTO: Gram + Cholesky in one launch per iteration when the plan fits (momentum_b200.h mb2_fused_mode)
 
     def _c(self) -> _Options:
         return _Options(self.min_iterations, self.max_iterations, self.threshold, int(self.verbose), self.regularization,
                         int(self.do_line_search), int(self.use_block_jtj), self.target_rows_per_chunk, int(self.subset_line_search),
-                        int(self.jtj_mode), int(self.store_error_history), int(self.cholesky_mode))
+                        int(self.jtj_mode), int(self.store_error_history), int(self.cholesky_mode), int(self.fused_mode))
 
 
 class _Base:
@@ -394,8 +399,17 @@ class GaussNewtonSolver(_Base):
         st = (C.c_int64 * 12)()
         self._check(self._L.mb2_solver_get_plan_stats(self._h, st))
         keys = ["jacobian_nonzeros", "jacobian_columns", "ldj", "normal_parameters", "cholesky_tiles", "cholesky_tile_ops", "cholesky_levels", "rows",
-                "strip_floats", "gram_macs", "gram_pairs", "reserved"]
+                "strip_floats", "gram_macs", "gram_pairs", "fused_groups"]
         return dict(zip(keys, (int(v) for v in st)))
+
+    FUSED_PHASES = ["fetch", "joint_parameters", "fk", "units", "cells", "gram", "tiles_from_tmem", "chol_diag", "chol_panel", "chol_update",
+                    "chol_backward", "update_bookkeeping"]
+
+    def get_fused_profile(self):
+        """{fused, groups, kernel_ms, phase_cycles{name: cycles}} of the last solve (kernel_ms / cycles need set_profiling(True))."""
+        fused = C.c_int32(0); groups = C.c_int32(0); ms_ = C.c_double(0.0); cyc = (C.c_uint64 * 12)()
+        self._check(self._L.mb2_solver_get_fused_profile(self._h, C.byref(fused), C.byref(groups), C.byref(ms_), cyc))
+        return {"fused": int(fused.value), "groups": groups.value, "kernel_ms": ms_.value, "phase_cycles": dict(zip(self.FUSED_PHASES, (int(v) for v in cyc)))}
 
     def set_profiling(self, enabled: bool):
         self._check(self._L.mb2_solver_set_profiling(self._h, int(enabled)))

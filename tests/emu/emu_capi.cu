@@ -8,6 +8,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -99,8 +100,21 @@ template <bool kJacobian>
 static void sweepOne(mb2_solver_function* f, const FunctionTables& T, int b, const float* theta, double* errOut, float* stateOut) {
   std::vector<float> jp(size_t(T.numJoints) * 7), js(size_t(T.numJoints) * kJointStateStride), rec(T.recStride + 4);
   for (int row = 0; row < T.numJoints * 7; ++row) jp[row] = jointParameterRow(T, row, theta);
-  for (int lvl = 0; lvl < T.numLevels; ++lvl)
-    for (int k = T.levelStart[lvl]; k < T.levelStart[lvl + 1]; ++k) fkJoint<kJacobian>(T, T.levelJoints[k], jp.data(), js.data());
+  // the kernels' three passes (fkJoint, the statement-by-statement form, is checked against them below)
+  for (int j = 0; j < T.numJoints; ++j) fkLocal<kJacobian>(T, j, jp.data(), js.data());
+  for (int lvl = 1; lvl < T.numLevels; ++lvl)
+    for (int k = T.levelStart[lvl]; k < T.levelStart[lvl + 1]; ++k) fkCompose(T, T.levelJoints[k], js.data());
+  if (kJacobian)
+    for (int i = 0; i < 3 * T.numJoints; ++i) fkAxis(T, i / 3, i % 3, js.data());
+  if (kJacobian && getenv("MB2_EMU_CHECK_FK") != nullptr) { // both forms of JointStateT::set agree to rounding
+    std::vector<float> ref(js.size());
+    for (int lvl = 0; lvl < T.numLevels; ++lvl)
+      for (int k = T.levelStart[lvl]; k < T.levelStart[lvl + 1]; ++k) fkJoint<true>(T, T.levelJoints[k], jp.data(), ref.data());
+    for (size_t i = 0; i < js.size(); ++i) {
+      const float scale = std::max(1.f, std::fabs(ref[i]));
+      if (std::fabs(js[i] - ref[i]) > 2e-5f * scale) { std::fprintf(stderr, "emu: three-pass FK differs from fkJoint at %zu: %g vs %g\n", i, js[i], ref[i]); std::abort(); }
+    }
+  }
   if (stateOut)
     for (int i = 0; i < T.numJoints * 8; ++i) stateOut[i] = js[(i >> 3) * kJointStateStride + (i & 7)];
   const float* tg = f->targets.data() + size_t(b) * T.targetStride;
@@ -191,8 +205,9 @@ static void gramOne(const mb2_solver_function* f, int b, const GramPlan& G, cons
   std::copy(f->J.data() + size_t(b) * G.stride, f->J.data() + size_t(b + 1) * G.stride, strips); // the bulk copy
   float* resid = strips + G.residOff;
   std::vector<float> tileBuf(256 + 8);
-  for (int ti = 0; ti < G.numTiles; ++ti) {
+  for (size_t ti = 0; ti < G.tileOrder.size(); ++ti) {
     const int t = G.tileOrder[ti];
+    if (t < 0) continue;
     float* tile = out + size_t(t) * 256;
     for (int lane = 0; lane < 32; ++lane) {
       float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
@@ -676,7 +691,7 @@ extern "C" int emu_gram_stats(mb2_solver_function* f) {
   std::printf("rows %d (aligned), device columns %d, strips %d (%d KB), tiles %d, pairs %zu (max per tile %d), MACs %lld\n", f->plan.numRows, f->plan.numCols, g.numStrips,
               g.numStrips / 4, g.numTiles, g.pairA.size(), maxPairs, (long long)g.macs);
   std::printf("pairs per tile in order:");
-  for (int ti = 0; ti < g.numTiles; ++ti) { const int t = g.tileOrder[ti]; std::printf(" %d", g.tilePairStart[t + 1] - g.tilePairStart[t]); }
+  for (size_t ti = 0; ti < g.tileOrder.size(); ++ti) { const int t = g.tileOrder[ti]; if (t >= 0) std::printf(" %d", g.tilePairStart[t + 1] - g.tilePairStart[t]); else std::printf(" -"); }
   std::printf("\n");
   return MB2_OK;
 }
@@ -742,5 +757,27 @@ extern "C" int emu_plan_figures(mb2_solver_function* f, int64_t out[10]) {
   }
   out[0] = s.numLevels; out[1] = s.numTiles; out[2] = s.numTileCols; out[3] = s.nPad; out[4] = s.n; out[5] = g.numStrips; out[6] = int64_t(g.pairA.size());
   out[7] = misaligned; out[8] = odd; out[9] = outside;
+  return MB2_OK;
+}
+
+// table sizes of the solver plan (bytes): what a kernel that stages every table in shared memory has to hold
+extern "C" int emu_table_sizes(mb2_solver_function* f, int64_t out[12]) {
+  int64_t fig[10];
+  if (emu_plan_figures(f, fig) != MB2_OK) return MB2_ERR_INVALID_ARGUMENT; // leaves f->plan in the solver layout
+  const HostCharacter& h = f->ch->host;
+  out[0] = int64_t(f->plan.units.size());
+  out[1] = int64_t(f->plan.cells.size());
+  out[2] = int64_t(f->plan.contribs.size());
+  out[3] = int64_t(h.ptInner.size());
+  out[4] = int64_t(f->plan.limitData.size());
+  out[5] = f->plan.recStride;
+  out[6] = f->targetStride;
+  out[7] = int64_t(sizeof(UnitDesc));
+  out[8] = int64_t(sizeof(CellDesc));
+  out[9] = int64_t(sizeof(ContribDesc));
+  out[10] = int64_t(h.levelStart.size()) - 1;
+  int maxContrib = 0;
+  for (const CellDesc& c : f->plan.cells) maxContrib = std::max<int>(maxContrib, c.contribCount);
+  out[11] = maxContrib;
   return MB2_OK;
 }

@@ -71,16 +71,20 @@ CALIBRATED = {"count": 0, "cases": []}
 
 
 def check_solve(ch, efs, theta0, opts: ms.GaussNewtonSolverOptions, lib_path=None, enabled=None, param_tol=1e-4, instances=None,
-                compare_history=True, allow_calibration=True):
-    """``allow_calibration=False``: every compared instance must meet the stated tolerance as is (cfg2 / cfg3 / cfg4); otherwise an
-    instance that misses it is judged against 3x the oracle's own float-vs-double gap on the same inputs, and the use is counted
-    in ``CALIBRATED`` and printed."""
+                compare_history=True, allow_calibration=True, strict_double=False, max_calibrated=None):
+    """An instance that misses the stated tolerance against the FLOAT oracle is re-judged with the DOUBLE oracle on the same inputs
+    (the reference runs its own tests in both precisions, error_function_helpers.h:38-52); every such use is counted in ``CALIBRATED``
+    and printed. ``strict_double`` (cfg2 / cfg3 / cfg4): the CUDA result must then be as close to the double-precision answer as the
+    reference's own float build is, d(cuda, f64) <= max(tol, 1.5 d(f32, f64)); otherwise (long chains far from their targets, where
+    float rounding alone moves the reference by more than the tolerance) d(cuda, f32) <= max(tol, 3 d(f32, f64)).
+    ``max_calibrated`` bounds how many instances may need the second look; ``allow_calibration=False`` forbids it."""
     B = theta0.shape[0]
     fn = build_function(ch, efs, B, lib_path, enabled)
     solver = ms.GaussNewtonSolver(opts, fn)
     out = solver.solve(theta0)
     idx = range(B) if instances is None else instances
     worst = 0.0
+    local_cal = 0
     for b in idx:
         orc = OracleFunction(ch, efs, "float32", instance=b)
         if enabled is not None:
@@ -105,8 +109,16 @@ def check_solve(ch, efs, theta0, opts: ms.GaussNewtonSolverOptions, lib_path=Non
             err64, p64, _, _ = orc64.solve(f32(theta0[b]), min_iterations=opts.min_iterations, max_iterations=opts.max_iterations,
                                            threshold=opts.threshold, regularization=opts.regularization, do_line_search=opts.do_line_search,
                                            use_block_jtj=opts.use_block_jtj, subset_solver=opts.subset_line_search)
-            tol = max(param_tol, 3.0 * np.max(np.abs(p - p64)) / max(1.0, np.max(np.abs(p))))
+            gap = np.max(np.abs(p - p64)) / max(1.0, np.max(np.abs(p)))
+            if strict_double:
+                d = np.max(np.abs(out["params"][b] - p64)) / max(1.0, np.max(np.abs(p64)))
+                tol = max(param_tol, 1.5 * gap)
+                assert abs(out["errors"][b] - err64) <= max(1e-3 * abs(err64) + 1e-7, 1.5 * abs(err - err64)), (b, out["errors"][b], err, err64)
+            else:
+                tol = max(param_tol, 3.0 * gap)
             etol = max(etol, 3.0 * abs(err - err64))
+            local_cal += 1
+            assert max_calibrated is None or local_cal <= max_calibrated, ("too many instances needed the double-precision second look", CALIBRATED["cases"][-8:])
         assert d <= tol, (b, d, tol, out["iterations"][b], it)
         assert abs(out["errors"][b] - err) <= etol, (b, out["errors"][b], err)
         if compare_history:
