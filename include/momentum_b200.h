@@ -176,6 +176,11 @@ int32_t mb2_solver_function_jacobian_stride(const mb2_solver_function* f);
 int mb2_add_position_error_function(mb2_solver_function* f, float weight, float loss_alpha, float loss_c,
                                     int32_t num_constraints, const int32_t* parents, const float* offsets /*[nc*3]*/,
                                     const float* weights /*[nc]*/, int32_t* out_index);
+/* Same, with the constraint OFFSETS per instance as well (the reference builds its error functions per batch element,
+ * pymomentum/tensor_ik/tensor_ik.cpp:136-140: offsets and targets may differ from element to element; the parent joints fix the
+ * sparsity pattern and stay shared). Per-instance record (mb2_set_targets): [B][nc*6] = target xyz, offset xyz per constraint. */
+int mb2_add_position_error_function_instanced(mb2_solver_function* f, float weight, float loss_alpha, float loss_c, int32_t num_constraints,
+                                              const int32_t* parents, const float* weights /*[nc]*/, int32_t* out_index);
 /* addErrorFunction(PlaneErrorFunctionT) — plane_error_function.h:20-101, .cpp:49-70: signed distance of T_parent * offset to the plane
  * (normal, d), one residual row per constraint; above != 0 is the half-plane mode (only val < 0 is penalised). Per-instance targets
  * (mb2_set_targets): [B][nc*4] = normal xyz (normalised as in PlaneDataT's ctor), d. kLegacyWeight = 1e-4 (.h:83). */
@@ -232,6 +237,11 @@ int mb2_solver_set_enabled_parameters(mb2_solver* s, const uint64_t bits[MB2_PAR
  * the objective before the last update (what solve() returns); iterations[b] = number of
  * doIteration calls; status[b] = mb2_instance_status. Any of errors/iterations/status may be NULL. */
 int mb2_solver_solve(mb2_solver* s, float* parameters, double* errors, int32_t* iterations, int32_t* status);
+/* The same call in two halves, for callers that keep several handles busy (e.g. the buckets of a mixed-rig batch): solve_async queues
+ * the H2D copy, the solve and the D2H copy on the handle's stream and returns (use pinned host memory for a truly asynchronous copy);
+ * wait blocks until they are done and returns the per-instance results. */
+int mb2_solver_solve_async(mb2_solver* s, float* parameters);
+int mb2_solver_wait(mb2_solver* s, double* errors, int32_t* iterations, int32_t* status);
 /* Same with parameters resident on the device, on `cuda_stream` (NULL = handle stream). Results are fetched with
  * mb2_solver_get_results after synchronising. The fused single-kernel path (default options on a rig whose tiles fit in shared
  * memory, no line search) is fully asynchronous; the multi-kernel path is asynchronous up to min_iterations and then reads the
@@ -262,6 +272,29 @@ int mb2_solver_get_plan_stats(mb2_solver* s, int64_t stats[12]);
  * [7] Cholesky diagonal tiles, [8] panel tiles, [9] updates, [10] backward substitution, [11] update + bookkeeping + write-back.
  * groups = instance groups per CTA of the persistent kernel. Any output pointer may be NULL. No reference counterpart. */
 int mb2_solver_get_fused_profile(mb2_solver* s, int32_t* fused, int32_t* groups, double* kernel_ms, uint64_t phase_cycles[12]);
+
+/* ---- Mixed-rig batches (BASELINE.json configs[4]): heterogeneous instances -> buckets sharing one plan -> batched solves --------
+ * The reference treats a batch element by element (pymomentum/tensor_ik/tensor_ik.cpp:127-177 builds error functions, solver function
+ * and solver per element). Here instances are bucketed by (rig, constraint parents): inside a bucket offsets, targets, weights and
+ * the number of constraints are per instance (shorter instances are padded with zero-weight constraints, at most granule - 1 of them),
+ * every bucket is one batched solve, results come back in input order. Position constraints (+ optionally the rig's ParameterLimits). */
+typedef struct mb2_mixed_batch mb2_mixed_batch;
+const char* mb2_mixed_batch_last_error(void);
+int mb2_mixed_batch_create(int device, int32_t granule /*constraints; <= 0: 8*/, mb2_mixed_batch** out);
+void mb2_mixed_batch_destroy(mb2_mixed_batch* b);
+/* the character must outlive the batch (ownership as everywhere in momentum: non-owning references) */
+int mb2_mixed_batch_add_rig(mb2_mixed_batch* b, const mb2_character* c, int32_t num_parameters, int32_t* rig_id);
+int mb2_mixed_batch_use_limits(mb2_mixed_batch* b, int32_t enabled, float weight); /* LimitErrorFunctionT over each rig's limits */
+int mb2_mixed_batch_add_instance(mb2_mixed_batch* b, int32_t rig_id, int32_t num_constraints, const int32_t* parents, const float* offsets /*[nc*3]*/,
+                                 const float* weights /*[nc]*/, const float* targets /*[nc*3]*/, const float* theta0 /*[n of the rig]*/, int32_t* instance_id);
+int mb2_mixed_batch_set_parameters(mb2_mixed_batch* b, int32_t instance_id, const float* theta0);
+int mb2_mixed_batch_solve(mb2_mixed_batch* b, const mb2_gauss_newton_options* opt);
+int mb2_mixed_batch_get_result(mb2_mixed_batch* b, int32_t instance_id, float* theta, double* error, int32_t* iterations, int32_t* status);
+int mb2_mixed_batch_get_results(mb2_mixed_batch* b, float* theta, const int64_t* theta_offsets, double* errors, int32_t* iterations, int32_t* status);
+/* [0] instances, [1] buckets, [2] residual rows before padding, [3] after, [4] largest bucket, [5] singleton buckets */
+int mb2_mixed_batch_stats(mb2_mixed_batch* b, int64_t stats[6]);
+/* [0] rig, [1] instances, [2] constraints (padded), [3] Gauss-Newton iterations of the last solve */
+int mb2_mixed_batch_bucket_info(mb2_mixed_batch* b, int32_t bucket, int64_t info[4]);
 
 #ifdef __cplusplus
 }

@@ -223,11 +223,11 @@ def humanoid72(seed: int = 12346) -> "tuple[Character, dict]":
     return ch, sets
 
 
-def bodyhands300(seed: int = 12348) -> "tuple[Character, dict]":
-    """300-joint body+hands rig, n = 424: 60 body joints (root 6 DOF + scale, 3
-    rotation DOF on the other 59) + 240 one-DOF (rx) finger/helper joints in chains of four; every
-    8th helper joint's rx row is additionally driven by its parent's parameter with weight 0.5
-    (mirrors ``shared_rz`` of the reference fixture, character_helpers.cpp:137-138)."""
+def bodyhands_rig(num_chains: int = 60, chain_len: int = 4, seed: int = 12348, name: str = "bodyhands300") -> "tuple[Character, dict]":
+    """Body + helper-chain rig: 60 body joints (root 6 DOF + scale, 3 rotation DOF on the other 59) + ``num_chains`` chains of
+    ``chain_len`` one-DOF (rx) finger/helper joints; every 8th helper joint's rx row is additionally driven by its parent's parameter
+    with weight 0.5 (mirrors ``shared_rz`` of the reference fixture, character_helpers.cpp:137-138).
+    60 x 4 = the 300-joint body+hands rig with n = 424 of SURVEY.md §8d; 30 x 3 = the 150-joint rig of cfg5 (n = 274)."""
     rng = np.random.default_rng(seed)
     tb = _TreeBuilder(rng)
     U = lambda a, b: float(rng.uniform(a, b))
@@ -254,14 +254,14 @@ def bodyhands300(seed: int = 12348) -> "tuple[Character, dict]":
     while len(attach) < 60:  # remaining helper chains hang off body joints round-robin
         attach.append(body_all[(7 * k) % len(body_all)])
         k += 1
-    chain_parents = attach[:60]
-    assert len(chain_parents) == 60
+    chain_parents = attach[:num_chains]
+    assert len(chain_parents) == num_chains
     helper_ids = []
     for ci, par in enumerate(chain_parents):
-        ids = tb.chain(f"h{ci}_", par, [U(2, 6) for _ in range(4)], rng.normal(size=3))
+        ids = tb.chain(f"h{ci}_", par, [U(2, 6) for _ in range(chain_len)], rng.normal(size=3))
         helper_ids += ids
     J = len(tb.parents)
-    assert J == 300, J
+    assert J == 60 + num_chains * chain_len, J
     trip = [(k, k, 1.0) for k in range(7)]
     col = 7
     for j in range(1, n_body):
@@ -278,12 +278,22 @@ def bodyhands300(seed: int = 12348) -> "tuple[Character, dict]":
         if idx % 8 == 7 and p in own:
             trip.append((j * 7 + 3, own[p], 0.5))
     n = col
-    assert n == 424, n
+    assert n == 7 + 3 * 59 + num_chains * chain_len, n
     outer, inner, vals = _csr_from_triplets(7 * J, n, trip)
-    ch = Character(np.array(tb.parents, np.int32), np.stack(tb.offsets).astype(np.float32), np.stack(tb.prerot).astype(np.float32), n, outer, inner, vals, np.zeros(7 * J, np.float32), [], "bodyhands300")
+    ch = Character(np.array(tb.parents, np.int32), np.stack(tb.offsets).astype(np.float32), np.stack(tb.prerot).astype(np.float32), n, outer, inner, vals, np.zeros(7 * J, np.float32), [], name)
     ch.validate()
-    sets = {"marker_joints": [int(j) for j in np.round(np.linspace(1, J - 1, 200)).astype(int)]}
+    sets = {"marker_joints": [int(j) for j in np.round(np.linspace(1, J - 1, min(200, J - 1))).astype(int)]}
     return ch, sets
+
+
+def bodyhands300(seed: int = 12348) -> "tuple[Character, dict]":
+    """300-joint body+hands rig, n = 424."""
+    return bodyhands_rig(60, 4, seed, "bodyhands300")
+
+
+def body150(seed: int = 12350) -> "tuple[Character, dict]":
+    """150-joint rig of the cfg5 mix (60 body joints + 30 helper chains of three), n = 274."""
+    return bodyhands_rig(30, 3, seed, "body150")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -302,6 +312,7 @@ class PositionErrorFunction:
     loss_alpha: float = LOSS_L2
     loss_c: float = 1.0
     kind: int = KIND_POSITION
+    instance_offsets: Optional[np.ndarray] = None  # [B,nc,3]: offsets per batch element (tensor_ik.cpp:136-140 builds them per element)
     kLegacyWeight = 1e-4  # position_error_function.h:64
 
 

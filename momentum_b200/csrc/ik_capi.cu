@@ -680,6 +680,24 @@ int mb2_add_position_error_function(mb2_solver_function* f, float weight, float 
   return addBlock(f, ef, outIndex);
 }
 
+int mb2_add_position_error_function_instanced(mb2_solver_function* f, float weight, float alpha, float c, int32_t nc, const int32_t* parents, const float* weights,
+                                              int32_t* outIndex) {
+  MB2_CHECK(f != nullptr && nc >= 0 && (nc == 0 || (parents && weights)), "invalid position constraints");
+  MB2_CHECK(c > 0.f, "Parameter c should be positive");
+  HostErrorFunction ef;
+  ef.kind = 0;
+  ef.weight = weight;
+  ef.lossAlpha = alpha;
+  ef.lossC = c;
+  ef.instanceOffsets = true;
+  ef.parents.assign(parents, parents + nc);
+  for (int p : ef.parents) MB2_CHECK(p >= 0 && p < f->ch->host.numJoints, "constraint parent joint out of range");
+  ef.offsets.assign(3 * size_t(nc), 0.f);
+  ef.weights.assign(weights, weights + nc);
+  ef.targetSize = 6 * nc;
+  return addBlock(f, ef, outIndex);
+}
+
 int mb2_add_plane_error_function(mb2_solver_function* f, float weight, float alpha, float c, int32_t above, int32_t nc, const int32_t* parents,
                                  const float* offsets, const float* weights, int32_t* outIndex) {
   MB2_CHECK(f != nullptr && nc >= 0 && (nc == 0 || (parents && offsets && weights)), "invalid plane constraints");
@@ -1255,7 +1273,7 @@ int mb2_solver_get_results(mb2_solver* s, double* errors, int32_t* iterations, i
   return MB2_OK;
 }
 
-int mb2_solver_solve(mb2_solver* s, float* params, double* errors, int32_t* iterations, int32_t* status) {
+int mb2_solver_solve_async(mb2_solver* s, float* params) {
   MB2_CHECK(s != nullptr && params != nullptr, "null argument");
   mb2_solver_function* f = s->fn;
   MB2_DEVICE_GUARD(f->ch->device);
@@ -1265,8 +1283,20 @@ int mb2_solver_solve(mb2_solver* s, float* params, double* errors, int32_t* iter
   int rc = mb2_solver_solve_device(s, s->dThetaStage.p, f->stream);
   if (rc != MB2_OK) return rc;
   MB2_CUDA(cudaMemcpyAsync(params, s->dThetaStage.p, bytes, cudaMemcpyDeviceToHost, f->stream));
-  MB2_CUDA(cudaStreamSynchronize(f->stream));
+  return MB2_OK;
+}
+
+int mb2_solver_wait(mb2_solver* s, double* errors, int32_t* iterations, int32_t* status) {
+  MB2_CHECK(s != nullptr, "null solver");
+  MB2_DEVICE_GUARD(s->fn->ch->device);
+  MB2_CUDA(cudaStreamSynchronize(s->fn->stream));
   return mb2_solver_get_results(s, errors, iterations, status);
+}
+
+int mb2_solver_solve(mb2_solver* s, float* params, double* errors, int32_t* iterations, int32_t* status) {
+  const int rc = mb2_solver_solve_async(s, params);
+  if (rc != MB2_OK) return rc;
+  return mb2_solver_wait(s, errors, iterations, status);
 }
 
 int mb2_solver_get_error_history(mb2_solver* s, double* history) {

@@ -320,8 +320,10 @@ MB2_HD float evalUnit(const FunctionTables& T, int ui, const float* theta, const
         return 0.f;
       }
       const float* ps = js + u.joint * kJointStateStride;
-      const F3 v = ld3(ps) + qrot(ld4(ps + 3), ps[7] * f3(u.f[0], u.f[1], u.f[2])); // transform.h:193-195
       const float* tg = targets + u.targetOff;
+      // the constraint offset is shared by the batch (u.f) or, for an "instanced" block, follows the target in the instance's record
+      const F3 off = u.pad[2] != 0 ? f3(tg[3], tg[4], tg[5]) : f3(u.f[0], u.f[1], u.f[2]);
+      const F3 v = ld3(ps) + qrot(ld4(ps + 3), ps[7] * off); // transform.h:193-195
       const F3 f = f3(v.x - tg[0], v.y - tg[1], v.z - tg[2]);
       const float sq = dot(f, f);
       if (!kJacobian) return cw * lossValue(e, sq) * e.weight;

@@ -185,11 +185,13 @@ std::string buildPlan(const HostCharacter& ch, const std::vector<HostErrorFuncti
         if (alignRowGroups) row = (row + 3) & ~3;
         u.row0 = row;
         u.numRows = isPos ? 3 : 9;
-        u.targetOff = ef.targetOff + per * c;
+        const bool instanced = isPos && ef.instanceOffsets;
+        u.targetOff = ef.targetOff + (instanced ? 6 : per) * c;
         u.weightIdx = ef.weightOff + c;
         u.recOff = rec;
         u.extra = -1;
-        for (int k = 0; k < per; ++k) u.f[k] = ef.offsets[size_t(per) * c + k];
+        u.pad[2] = instanced ? 1 : 0;
+        if (!instanced) for (int k = 0; k < per; ++k) u.f[k] = ef.offsets[size_t(per) * c + k];
         const int ui = int(out.units.size());
         out.units.push_back(u);
         row += u.numRows;

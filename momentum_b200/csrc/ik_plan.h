@@ -48,6 +48,7 @@ struct HostErrorFunction {
   float posWgt{1.f}, rotWgt{1.f};
   std::vector<float> posW, rotW;
   bool halfPlane{false};            // plane: PlaneErrorFunctionT(above)
+  bool instanceOffsets{false};      // position: offsets are per instance (record = target xyz, offset xyz per constraint)
   std::vector<float> paramWeights; // model parameters: targetWeights_ [numParams]
   // layout (assigned when added)
   int32_t targetOff{0}, targetSize{0}; // floats per instance

@@ -137,3 +137,51 @@ def chain22_problem(seed=12345):
     poff = rng.uniform(-1, 1, (4, 3))
     efs = [mc.PositionErrorFunction(pj, poff, np.ones(4), mc.world_points(ch, theta_star, pj, poff), weight=1.0)]
     return ch, efs, np.zeros((1, n)), theta_star
+
+
+# ---- cfg5: mixed-rig batch -----------------------------------------------------------------------------------------
+MIXED_RIGS = (("chain22", 0.25), ("humanoid72", 0.50), ("body150", 0.15), ("bodyhands300", 0.10))
+
+
+def mixed_rigs():
+    """The four rig classes of cfg5 with their canonical marker joints: an instance with c constraints uses the first c of them (so the
+    constraint parents of two instances of one rig are prefixes of one another: the bucketing key of the device path)."""
+    out = {}
+    ch = mc.create_test_character(22)
+    out["chain22"] = (ch, [int(j) for j in (np.arange(22) * 5 + 21) % 22])              # every joint once, spread
+    ch, sets = mc.humanoid72()
+    rest = [j for j in range(1, ch.num_joints) if j not in sets["position_joints"]]
+    out["humanoid72"] = (ch, [int(j) for j in list(sets["position_joints"]) + rest])      # end effectors / limb mids first, then the rest
+    ch, sets = mc.body150()
+    out["body150"] = (ch, list(sets["marker_joints"]))
+    ch, sets = mc.bodyhands300()
+    out["bodyhands300"] = (ch, list(sets["marker_joints"]))
+    return out
+
+
+def mixed_problem(N, seed=12351, rigs=None):
+    """N instances: rig drawn 25/50/15/10 %, constraint count U{4..200} capped by the rig's marker list, offsets and targets per
+    instance (reachable poses), theta0 = 0. Returns (rigs dict, list of instance dicts)."""
+    rng = np.random.default_rng(seed)
+    rigs = rigs or mixed_rigs()
+    names = [n for n, _ in MIXED_RIGS]
+    probs = np.array([p for _, p in MIXED_RIGS])
+    which = rng.choice(len(names), size=N, p=probs)
+    counts = rng.integers(4, 201, size=N)
+    inst = []
+    for i in range(N):
+        name = names[which[i]]
+        ch, markers = rigs[name]
+        c = int(min(counts[i], len(markers)))
+        n = ch.num_params
+        theta_star = np.zeros(n)
+        theta_star[7:] = rng.uniform(-0.4, 0.4, n - 7)
+        theta_star[3:6] = rng.uniform(-0.5, 0.5, 3)
+        theta_star[0:3] = rng.uniform(-10.0, 10.0, 3) if name != "chain22" else rng.uniform(-1.0, 1.0, 3)
+        parents = np.array(markers[:c], np.int32)
+        scale = 1.0 if name == "chain22" else 3.0
+        offsets = rng.uniform(-scale, scale, (c, 3))
+        targets = mc.world_points(ch, theta_star[None], parents, offsets)[0]
+        inst.append(dict(rig=name, parents=parents, offsets=offsets.astype(np.float32), weights=np.ones(c, np.float32), targets=targets.astype(np.float32),
+                         theta0=np.zeros(n, np.float32), theta_star=theta_star))
+    return rigs, inst

@@ -56,14 +56,17 @@ CABI_SYMBOLS = [
     "mb2_last_error", "mb2_device_count", "mb2_default_gauss_newton_options", "mb2_character_create", "mb2_character_set_parameter_limits",
     "mb2_character_destroy", "mb2_solver_function_create", "mb2_solver_function_destroy", "mb2_solver_function_num_parameters",
     "mb2_solver_function_actual_parameters", "mb2_solver_function_batch", "mb2_solver_function_jacobian_rows",
-    "mb2_solver_function_jacobian_stride", "mb2_add_position_error_function", "mb2_add_orientation_error_function",
+    "mb2_solver_function_jacobian_stride", "mb2_add_position_error_function", "mb2_add_position_error_function_instanced", "mb2_add_orientation_error_function",
     "mb2_add_plane_error_function", "mb2_add_model_parameters_error_function",
     "mb2_add_state_error_function", "mb2_add_limit_error_function", "mb2_set_error_function_weight", "mb2_set_targets",
     "mb2_set_targets_device", "mb2_set_constraint_weights", "mb2_solver_function_set_enabled_parameters", "mb2_solver_function_get_error",
     "mb2_solver_function_get_jacobian", "mb2_solver_function_get_jtjr", "mb2_solver_function_get_skeleton_state", "mb2_solver_create",
     "mb2_solver_destroy", "mb2_solver_set_options", "mb2_solver_set_enabled_parameters", "mb2_solver_solve", "mb2_solver_solve_device",
     "mb2_solver_get_results", "mb2_solver_get_error_history", "mb2_solver_get_counters", "mb2_solver_set_profiling",
-    "mb2_solver_get_phase_times", "mb2_solver_get_plan_stats", "mb2_solver_get_fused_profile",
+    "mb2_solver_get_phase_times", "mb2_solver_get_plan_stats", "mb2_solver_get_fused_profile", "mb2_solver_solve_async", "mb2_solver_wait",
+    "mb2_mixed_batch_last_error", "mb2_mixed_batch_create", "mb2_mixed_batch_destroy", "mb2_mixed_batch_add_rig", "mb2_mixed_batch_use_limits",
+    "mb2_mixed_batch_add_instance", "mb2_mixed_batch_set_parameters", "mb2_mixed_batch_solve", "mb2_mixed_batch_get_result", "mb2_mixed_batch_get_results",
+    "mb2_mixed_batch_stats", "mb2_mixed_batch_bucket_info",
 ]
 
 _libs = {}
@@ -87,6 +90,8 @@ def load_library(path: Optional[str] = None):
     for name in ("num_parameters", "actual_parameters", "batch", "jacobian_rows", "jacobian_stride"):
         getattr(L, f"mb2_solver_function_{name}").argtypes = [vp]
     L.mb2_add_position_error_function.argtypes = [vp, C.c_float, C.c_float, C.c_float, C.c_int32, _ip, _fp, _fp, _ip]
+    if hasattr(L, "mb2_add_position_error_function_instanced"):
+        L.mb2_add_position_error_function_instanced.argtypes = [vp, C.c_float, C.c_float, C.c_float, C.c_int32, _ip, _fp, _ip]
     L.mb2_add_orientation_error_function.argtypes = [vp, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_int32, _ip, _fp, _fp, _ip]
     L.mb2_add_state_error_function.argtypes = [vp, C.c_float, C.c_int32, C.c_float, C.c_float, _fp, _fp, _ip]
     L.mb2_add_limit_error_function.argtypes = [vp, C.c_float, C.c_float, C.c_float, _ip]
@@ -120,6 +125,21 @@ def load_library(path: Optional[str] = None):
     if hasattr(L, "mb2_solver_get_fused_profile"):
         L.mb2_solver_get_fused_profile.argtypes = [vp, _ip, _ip, _dp, _up]
     L.mb2_default_gauss_newton_options.argtypes = [C.POINTER(_Options)]
+    if hasattr(L, "mb2_mixed_batch_create"):
+        L.mb2_solver_solve_async.argtypes = [vp, vp]
+        L.mb2_solver_wait.argtypes = [vp, _dp, _ip, _ip]
+        L.mb2_mixed_batch_last_error.restype = C.c_char_p
+        L.mb2_mixed_batch_create.argtypes = [C.c_int, C.c_int32, C.POINTER(vp)]
+        L.mb2_mixed_batch_destroy.argtypes = [vp]
+        L.mb2_mixed_batch_add_rig.argtypes = [vp, vp, C.c_int32, _ip]
+        L.mb2_mixed_batch_use_limits.argtypes = [vp, C.c_int32, C.c_float]
+        L.mb2_mixed_batch_add_instance.argtypes = [vp, C.c_int32, C.c_int32, _ip, _fp, _fp, _fp, _fp, _ip]
+        L.mb2_mixed_batch_set_parameters.argtypes = [vp, C.c_int32, _fp]
+        L.mb2_mixed_batch_solve.argtypes = [vp, C.POINTER(_Options)]
+        L.mb2_mixed_batch_get_result.argtypes = [vp, C.c_int32, _fp, _dp, _ip, _ip]
+        L.mb2_mixed_batch_get_results.argtypes = [vp, _fp, C.POINTER(C.c_int64), _dp, _ip, _ip]
+        L.mb2_mixed_batch_stats.argtypes = [vp, C.POINTER(C.c_int64)]
+        L.mb2_mixed_batch_bucket_info.argtypes = [vp, C.c_int32, C.POINTER(C.c_int64)]
     _libs[path] = L
     return L
 
@@ -235,7 +255,10 @@ class SkeletonSolverFunction(_Base):
     def add_error_function(self, ef) -> int:
         idx = C.c_int32(-1)
         alpha = float(getattr(ef, "loss_alpha", 2.0))
-        if ef.kind == mc.KIND_POSITION:
+        if ef.kind == mc.KIND_POSITION and getattr(ef, "instance_offsets", None) is not None:
+            pa, pp = _i32(ef.parents); w, wp = _f32(ef.weights)
+            self._check(self._L.mb2_add_position_error_function_instanced(self._h, ef.weight, alpha, ef.loss_c, len(pa), pp, wp, C.byref(idx)))
+        elif ef.kind == mc.KIND_POSITION:
             pa, pp = _i32(ef.parents); of, op = _f32(ef.offsets); w, wp = _f32(ef.weights)
             self._check(self._L.mb2_add_position_error_function(self._h, ef.weight, alpha, ef.loss_c, len(pa), pp, op, wp, C.byref(idx)))
         elif ef.kind in (mc.KIND_ORIENTATION, mc.KIND_ORIENTATION_ROTDIFF):
@@ -264,7 +287,10 @@ class SkeletonSolverFunction(_Base):
         """(Re)send every block's per-instance targets from the spec objects."""
         for idx, ef in enumerate(self.error_functions):
             if getattr(ef, "targets", None) is not None and ef.kind != mc.KIND_LIMIT:
-                self.set_targets(idx, ef.targets)
+                if ef.kind == mc.KIND_POSITION and getattr(ef, "instance_offsets", None) is not None:  # record = target xyz, offset xyz
+                    self.set_targets(idx, np.concatenate([np.asarray(ef.targets, np.float32), np.asarray(ef.instance_offsets, np.float32)], -1))
+                else:
+                    self.set_targets(idx, ef.targets)
 
     def set_targets(self, index: int, targets):
         t, tp = _f32(targets)
@@ -418,3 +444,72 @@ class GaussNewtonSolver(_Base):
         ms = (C.c_double * 4)(); ln = (C.c_uint64 * 4)()
         self._check(self._L.mb2_solver_get_phase_times(self._h, ms, ln))
         return list(ms), list(ln)
+
+
+class MixedBatch(_Base):
+    """Heterogeneous IK instances (different rigs, different constraint sets) -> buckets that share a plan -> one batched solve per
+    bucket -> results in input order (BASELINE.json configs[4]; the reference loops over batch elements, tensor_ik.cpp:127-177)."""
+
+    def __init__(self, device: int = 0, granule: int = 8, lib_path: Optional[str] = None):
+        self._L = load_library(lib_path)
+        self._h = C.c_void_p()
+        self._check(self._L.mb2_mixed_batch_create(device, granule, C.byref(self._h)))
+        self.device = device
+        self._rigs: List[DeviceCharacter] = []
+        self._sizes: List[int] = []   # parameters per instance, input order
+        self.lib_path = lib_path
+
+    def _check(self, rc):
+        if rc != 0:
+            raise MomentumB200Error(self._L.mb2_mixed_batch_last_error().decode())
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.mb2_mixed_batch_destroy(self._h)
+            self._h = None
+
+    def add_rig(self, character) -> int:
+        dc = character if isinstance(character, DeviceCharacter) else DeviceCharacter(character, self.device, self.lib_path)
+        rid = C.c_int32(-1)
+        self._check(self._L.mb2_mixed_batch_add_rig(self._h, dc._h, dc.character.num_params, C.byref(rid)))
+        self._rigs.append(dc)  # keeps the device character alive
+        return rid.value
+
+    def use_limits(self, enabled: bool = True, weight: float = 1.0):
+        self._check(self._L.mb2_mixed_batch_use_limits(self._h, int(enabled), weight))
+
+    def add_instance(self, rig: int, parents, offsets, weights, targets, theta0) -> int:
+        pa, pp = _i32(parents); of, op = _f32(offsets); w, wp = _f32(weights); tg, tp = _f32(targets); th, thp = _f32(theta0)
+        assert of.size == 3 * pa.size and tg.size == 3 * pa.size and w.size == pa.size and th.size == self._rigs[rig].character.num_params
+        iid = C.c_int32(-1)
+        self._check(self._L.mb2_mixed_batch_add_instance(self._h, rig, pa.size, pp, op, wp, tp, thp, C.byref(iid)))
+        self._sizes.append(th.size)
+        return iid.value
+
+    def set_parameters(self, instance: int, theta0):
+        th, thp = _f32(theta0)
+        self._check(self._L.mb2_mixed_batch_set_parameters(self._h, instance, thp))
+
+    def solve(self, options: "GaussNewtonSolverOptions"):
+        o = options._c()
+        self._check(self._L.mb2_mixed_batch_solve(self._h, C.byref(o)))
+        N = len(self._sizes)
+        offs = np.zeros(N + 1, np.int64)
+        np.cumsum(self._sizes, out=offs[1:])
+        theta = np.zeros(int(offs[-1]), np.float32)
+        err = np.zeros(N, np.float64); it = np.zeros(N, np.int32); st = np.zeros(N, np.int32)
+        self._check(self._L.mb2_mixed_batch_get_results(self._h, theta.ctypes.data_as(_fp), offs.ctypes.data_as(C.POINTER(C.c_int64)), err.ctypes.data_as(_dp),
+                                                        it.ctypes.data_as(_ip), st.ctypes.data_as(_ip)))
+        return {"params": [theta[offs[i]:offs[i + 1]] for i in range(N)], "errors": err, "iterations": it, "status": st}
+
+    def stats(self):
+        st = (C.c_int64 * 6)()
+        self._check(self._L.mb2_mixed_batch_stats(self._h, st))
+        d = dict(zip(["instances", "buckets", "rows", "padded_rows", "largest_bucket", "singleton_buckets"], (int(v) for v in st)))
+        d["padding_waste"] = 1.0 - d["rows"] / d["padded_rows"] if d["padded_rows"] else 0.0
+        return d
+
+    def bucket_info(self, bucket: int):
+        info = (C.c_int64 * 4)()
+        self._check(self._L.mb2_mixed_batch_bucket_info(self._h, bucket, info))
+        return dict(zip(["rig", "instances", "constraints", "iterations"], (int(v) for v in info)))

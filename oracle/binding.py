@@ -132,7 +132,9 @@ class OracleFunction:
             if k in (0, 1, 2):
                 pa, pp = _i(ef.parents)
                 cw, cwp = _d(ef.weights)
-                of, op = _d(ef.offsets)
+                inst_off = getattr(ef, "instance_offsets", None)  # offsets per batch element: this oracle object is then tied to `instance`
+                of, op = _d(ef.offsets if inst_off is None else np.asarray(inst_off)[instance])
+                self.instanced = getattr(self, "instanced", False) or inst_off is not None
                 tg, tgp = _d(np.asarray(ef.targets)[instance])
                 L.orc_fn_add_joint_ef(self.fn, k, float(ef.weight), float(ef.loss_alpha), float(ef.loss_c), len(ef.parents), pp, cwp, op, tgp)
             elif k == 3:
@@ -171,6 +173,8 @@ class OracleFunction:
 
     def select_instance(self, b: int):
         L = self._L
+        if getattr(self, "instanced", False):
+            raise ValueError("error functions with per-instance offsets: build one OracleFunction per instance")
         for idx, ef in enumerate(self.efs):
             if ef.kind in (0, 1, 2, 3, 5, 6):
                 tg, tgp = _d(np.asarray(ef.targets)[b])

@@ -360,6 +360,16 @@ int mb2_add_position_error_function(mb2_solver_function* f, float weight, float 
   ef.targetSize = 3 * nc;
   return addBlock(f, ef, outIndex);
 }
+int mb2_add_position_error_function_instanced(mb2_solver_function* f, float weight, float alpha, float c, int32_t nc, const int32_t* parents, const float* weights,
+                                              int32_t* outIndex) {
+  HostErrorFunction ef;
+  ef.kind = 0; ef.weight = weight; ef.lossAlpha = alpha; ef.lossC = c; ef.instanceOffsets = true;
+  ef.parents.assign(parents, parents + nc);
+  ef.offsets.assign(3 * size_t(nc), 0.f);
+  ef.weights.assign(weights, weights + nc);
+  ef.targetSize = 6 * nc;
+  return addBlock(f, ef, outIndex);
+}
 int mb2_add_plane_error_function(mb2_solver_function* f, float weight, float alpha, float c, int32_t above, int32_t nc, const int32_t* parents,
                                  const float* offsets, const float* weights, int32_t* outIndex) {
   HostErrorFunction ef;
