@@ -33,9 +33,11 @@ sys.path.insert(0, ROOT)
 
 ITERS = 10
 WORKLOADS = {
-    "cfg3-shard": dict(batch=8192, rig="humanoid72", orientation=True, rows_m=126, params_n=220, desc="8192/GPU x humanoid72, 24 Position + 6 Orientation (m=126->128, n=220), lambda=0.05"),
+    "cfg3-shard": dict(batch=8192, rig="humanoid72", orientation=True, rows_m=126, params_n=220, global_batch=65536, desc="8192/GPU x humanoid72, 24 Position + 6 Orientation (m=126->128, n=220), lambda=0.05"),
     "cfg2": dict(batch=4096, rig="humanoid72", orientation=False, rows_m=72, params_n=220, desc="4096/GPU x humanoid72, 24 Position (m=72, n=220), lambda=0.05"),
-    "cfg4": dict(batch=2048, rig="bodyhands300", orientation=False, rows_m=600, params_n=424, desc="2048/GPU x bodyhands300, 200 Position (m=600, n=424), lambda=0.05"),
+    "cfg5": dict(batch=8192, rig="mixed", orientation=False, rows_m=None, params_n=None, global_batch=65536,
+                 desc="8192/GPU mixed rigs: chain22 25% / humanoid72 50% / body150 15% / bodyhands300 10%, Position constraints U{4..200} capped by rig, lambda=0.05"),
+    "cfg4": dict(batch=2048, rig="bodyhands300", orientation=False, rows_m=600, params_n=424, global_batch=16384, desc="2048/GPU x bodyhands300, 200 Position (m=600, n=424), lambda=0.05"),
 }
 
 
@@ -125,7 +127,8 @@ def bench_config(args, world):
     B = args.batch_per_gpu or w["batch"]
     return {"workload": args.workload, "desc": w["desc"], "batch_per_gpu": B, "global_batch": B * world, "iterations_per_solve": ITERS,
             "rows_m": w["rows_m"], "params_n": w["params_n"], "parallelism": f"dp{world} (instances sharded, no data-path collective)",
-            "jtj_mode": args.jtj_mode, "cholesky_mode": args.cholesky_mode, "l2": "256 MB buffer written between timed steps (L2 flush)"}
+            "jtj_mode": args.jtj_mode, "cholesky_mode": args.cholesky_mode, "fused_mode": getattr(args, "fused_mode", 0),
+            "l2": "256 MB buffer written between timed steps (L2 flush)"}
 
 
 def time_cpu_arm(workload, seconds, threads=None):
@@ -177,6 +180,217 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def measure_workload(ms, torch, workload, B, rank, local_rank, args, steps, warmup, min_it=ITERS, max_it=ITERS, e2e=True, profile=True, flush=None, barrier=None):
+    """Device-resident timing (CUDA events on the launching stream, L2 flushed between steps), the end-to-end leg through mb2_set_targets +
+    mb2_solver_solve with pinned host buffers, and one profiling solve (events around every launch + in-kernel phase cycles)."""
+    ch, efs, theta0, _ = make_problem(workload, B, seed_offset=1000 * rank)  # each rank owns a different shard
+    n = ch.num_params
+    fn = ms.SkeletonSolverFunction(ch, B, efs, device=local_rank)
+    fn.upload_targets()
+    opts = ms.GaussNewtonSolverOptions(min_iterations=min_it, max_iterations=max_it, threshold=1.0, regularization=0.05, jtj_mode=args.jtj_mode,
+                                       cholesky_mode=args.cholesky_mode, fused_mode=args.fused_mode)
+    solver = ms.GaussNewtonSolver(opts, fn)
+    stream = torch.cuda.current_stream().cuda_stream
+    theta0_dev = torch.from_numpy(theta0.astype(np.float32)).cuda()
+    theta_dev = torch.empty_like(theta0_dev)
+
+    def device_step():
+        theta_dev.copy_(theta0_dev)
+        solver.solve_device(theta_dev.data_ptr(), stream)
+
+    for _ in range(warmup):
+        device_step()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    total_ms = 0.0
+    for _ in range(steps):
+        flush.zero_()  # flush L2 between timed iterations
+        torch.cuda.synchronize()
+        ev0.record()
+        device_step()
+        ev1.record()
+        torch.cuda.synchronize()
+        total_ms += ev0.elapsed_time(ev1)
+    barrier()
+    res = solver.get_results()
+    out = {"ch": ch, "efs": efs, "n": n, "B": B, "solver": solver, "fn": fn, "total_ms": total_ms, "its_per_step": int(res["iterations"].sum()),
+           "err_sum": float(res["errors"].sum()), "launches": solver.get_counters()[1], "status_bad": int((res["status"] != 0).sum())}
+    if profile:
+        solver.set_profiling(True)
+        device_step()
+        torch.cuda.synchronize()
+        solver.get_results()
+        out["phase_ms"], out["phase_launches"] = solver.get_phase_times()
+        out["fused"] = solver.get_fused_profile()
+        solver.set_profiling(False)
+    if e2e:
+        theta0_pin = torch.from_numpy(theta0.astype(np.float32)).pin_memory()
+        n_e2e = max(1, warmup // 2) + steps
+        theta_pins = [theta0_pin.clone().pin_memory() for _ in range(n_e2e)]  # the solve is in place: one pinned in/out buffer per step
+        target_pins = [torch.from_numpy(np.ascontiguousarray(e.targets, np.float32)).pin_memory() for e in efs]
+        count = [0]
+
+        def e2e_step():
+            buf = theta_pins[count[0] % n_e2e]
+            count[0] += 1
+            for idx, tp in enumerate(target_pins):
+                fn._check(fn._L.mb2_set_targets(fn._h, idx, ms.C.cast(tp.data_ptr(), ms._fp)))
+            solver.solve_host_pointer(buf.data_ptr())
+            return solver.get_results()
+
+        for _ in range(max(1, warmup // 2)):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        out["e2e_s"] = time.perf_counter() - t0
+        out["h2d"] = int(theta0_pin.numel() * 4 + sum(tp.numel() * 4 for tp in target_pins))
+        out["d2h"] = int(theta0_pin.numel() * 4 + B * (8 + 4 + 4))
+    return out
+
+
+def kernel_report(m, peaks, workload):
+    """Per-kernel roofline entries from the profiling solve. ALGORITHMIC bytes / flops per instance and launch."""
+    solver, n, B, efs = m["solver"], m["n"], m["B"], m["efs"]
+    st = solver.get_plan_stats()
+    tf32_peak = 0.5 * peaks["bf16"]  # TF32 dense = half the bf16 rate (B200_PROFILING.md table); bf16 figure is the measured cuBLAS burst
+    hbm_peak = peaks["hbm_gbs"]
+    pm, pl = m["phase_ms"], m["phase_launches"]
+    sweep_ms = pm[0] / max(1, pl[0]); jtj_ms = pm[1] / max(1, pl[1]); chol_ms = pm[2] / max(1, pl[2])
+    m_rows = WORKLOADS[workload]["rows_m"]
+    target_floats = sum(int(np.prod(np.asarray(e.targets).shape[1:])) for e in efs)
+    traffic = measured_traffic(workload, B)
+    jtj_flops = float(m_rows) * n * (n + 1)  # SURVEY 8(d): the JtJ credit, whatever the kernel executes
+
+    def hbm_entry(name, key, bytes_per_instance, ms_):
+        ach = bytes_per_instance * B / (ms_ * 1e-3) / 1e9 if ms_ > 0 else 0.0
+        return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "peak_source": f"{peaks['src']} copy bandwidth",
+                "traffic": traffic.get(key), "ms_per_launch": ms_, "algorithmic_bytes_per_instance": bytes_per_instance}
+
+    k1_bytes = 4.0 * (n + target_floats + st["jacobian_nonzeros"] + m_rows) + 8.0
+    kernels = [hbm_entry("sweepKernel<true> (three-pass FK + residual + Jacobian strips)", "fk_residual_jacobian", k1_bytes, sweep_ms)]
+    fused = m["fused"]
+    ntiles = st["cholesky_tiles"]
+    gram_flops = 2.0 * st["gram_macs"]
+    jtj_phase = None
+    if fused["fused"] == 2:  # Gram + Cholesky in one launch: strips in, theta / delta / bookkeeping out; tiles never leave the SM
+        gc_bytes = 4.0 * (st["strip_floats"] + 4 * st["normal_parameters"]) + 32.0
+        e = hbm_entry("gramCholeskyKernel (tile-sparse J^T J on mma.sync 3xTF32 -> TMEM -> tiles in shared memory -> tile Cholesky + update)", "gram_cholesky", gc_bytes, chol_ms)
+        cyc = fused["phase_cycles"]
+        tot = float(sum(cyc.values())) or 1.0
+        share = (cyc["gram"] + cyc["tiles_from_tmem"]) / tot
+        gram_ms = chol_ms * share
+        jtj_phase = {"where": "Gram phase of gramCholeskyKernel (in-kernel cycle share x the kernel's event time)", "share_of_kernel": share, "ms": gram_ms}
+        e["phase_cycle_shares"] = {k: v / tot for k, v in cyc.items() if v}
+        kernels.append(e)
+    elif st["strip_floats"] > 0:
+        gram_bytes = 4.0 * (st["strip_floats"] + ntiles * 256 + 16 * ((st["normal_parameters"] + 15) // 16))
+        kernels.append(hbm_entry("gramTilesKernel (tile-sparse J^T J / J^T r, mma.sync 3xTF32 over non-zero strips)", "jtj_jtr", gram_bytes, jtj_ms))
+        k3_bytes = 4.0 * (ntiles * 256 + 4 * st["normal_parameters"])
+        kernels.append(hbm_entry("choleskyScheduledKernel (damped LLT + solves + update)", "cholesky_update", k3_bytes, chol_ms))
+        jtj_phase = {"where": "gramTilesKernel", "share_of_kernel": 1.0, "ms": jtj_ms}
+    else:
+        k2_bytes = 4.0 * (m_rows * (st["jacobian_columns"] + 1) + (st["normal_parameters"] + 1) * (st["normal_parameters"] + 2) / 2)
+        ach = jtj_flops * B / (jtj_ms * 1e-3) / 1e12 if jtj_ms > 0 else 0.0
+        dense = st["jacobian_columns"] + 1 <= 256 and args_jtj_is_tensor(m)
+        kernels.append({"kernel": "jtjTensorKernel (JtJ/Jtr, tcgen05 3xTF32)" if dense else "jtjSimtKernel", "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
+                        "frac": ach / tf32_peak, "peak_source": f"0.5 x {peaks['src']} bf16 cuBLAS burst ({peaks['bf16']} TF/s) = TF32 dense", "traffic": traffic.get("jtj_jtr"),
+                        "ms_per_launch": jtj_ms, "algorithmic_flops_per_instance": jtj_flops, "algorithmic_bytes_per_instance": k2_bytes})
+        k3_entries = ntiles * 256 if ntiles else st["normal_parameters"] * (st["normal_parameters"] + 1) / 2
+        kernels.append(hbm_entry("choleskyScheduledKernel (damped LLT + solves + update)" if ntiles else "choleskyKernel (dense LLT + solves + update)", "cholesky_update",
+                                 4.0 * (k3_entries + 4 * st["normal_parameters"]), chol_ms))
+    if jtj_phase is not None and jtj_phase["ms"] > 0:
+        dense_eq = jtj_flops * B / (jtj_phase["ms"] * 1e-3) / 1e12
+        executed = gram_flops * B / (jtj_phase["ms"] * 1e-3) / 1e12
+        step_ms = sweep_ms + jtj_ms + chol_ms
+        jtj_phase.update({"credited_flops_per_instance": jtj_flops, "credited_tflops": dense_eq, "credited_frac_of_tf32_peak": dense_eq / tf32_peak,
+                          "executed_flops_per_instance": gram_flops, "executed_tflops": executed, "executed_frac_of_tf32_peak": executed / tf32_peak,
+                          "credited_tflops_end_to_end": jtj_flops * B / (step_ms * 1e-3) / 1e12 if step_ms > 0 else 0.0,
+                          "tf32_peak": tf32_peak, "note": "credit = m n (n + 1) per instance-iteration (SURVEY 8d); executed = the multiply-adds of the non-zero 4x16 strips only; "
+                                                         "mma.sync (HMMA) path, not tcgen05: see profiles/sass_r02.txt"})
+    return kernels, jtj_phase, {"fk_residual_jacobian": sweep_ms, "jtj_jtr": jtj_ms, "cholesky_update": chol_ms}, st
+
+
+def args_jtj_is_tensor(m):
+    return True
+
+
+def extra_workloads(ms, torch, args, rank, local_rank, flush, barrier, peaks):
+    """Measured in the same run (N = 1 only): the other single-GPU configs, a convergence-mode solve, the persistent kernel at a small
+    batch, and the cfg5 mixed-rig batch through the bucketing front end. Compact figures; the headline stays the cfg3 shard."""
+    ex = {}
+    for wl in ("cfg2", "cfg4"):
+        try:
+            B = WORKLOADS[wl]["batch"]
+            m = measure_workload(ms, torch, wl, B, rank, local_rank, args, steps=3, warmup=3, e2e=False, flush=flush, barrier=barrier)
+            kernels, jtj, kms, st = kernel_report(m, peaks, wl)
+            ex[wl] = {"desc": WORKLOADS[wl]["desc"], "value": m["its_per_step"] * 3 / (m["total_ms"] * 1e-3), "unit": "GN it/s", "ms_per_step": m["total_ms"] / 3, "batch": B,
+                      "kernels_ms_per_iteration": kms, "jtj": jtj, "path": {0: "three kernels", 1: "persistent", 2: "sweep + gramCholesky"}[m["fused"]["fused"]],
+                      "tiles": st["cholesky_tiles"], "levels": st["cholesky_levels"], "roofline_all_kernels": kernels}
+            del m
+        except Exception as e:  # noqa: BLE001
+            ex[wl] = {"error": str(e)}
+    try:  # convergence mode: SolverOptions min 1 / max 50, threshold 1 (what the parity tests run)
+        B = WORKLOADS["cfg3-shard"]["batch"]
+        m = measure_workload(ms, torch, "cfg3-shard", B, rank, local_rank, args, steps=2, warmup=2, min_it=1, max_it=50, e2e=False, profile=False, flush=flush, barrier=barrier)
+        res = m["solver"].get_results()
+        ex["cfg3_convergence_mode"] = {"value": m["its_per_step"] * 2 / (m["total_ms"] * 1e-3), "unit": "GN it/s", "ms_per_solve": m["total_ms"] / 2,
+                                       "mean_iterations": float(res["iterations"].mean()), "max_iterations": int(res["iterations"].max()), "min_iterations": int(res["iterations"].min())}
+        del m
+    except Exception as e:  # noqa: BLE001
+        ex["cfg3_convergence_mode"] = {"error": str(e)}
+    try:  # one wave of the persistent whole-solve kernel (a latency figure: small batches, single launch, no host round trip)
+        small = {}
+        for fm, name in ((ms.FUSED_AUTO, "auto"), (ms.FUSED_PERSISTENT, "persistent")):
+            a2 = argparse.Namespace(**{**vars(args), "fused_mode": fm})
+            m = measure_workload(ms, torch, "cfg3-shard", 256, rank, local_rank, a2, steps=5, warmup=3, e2e=False, profile=False, flush=flush, barrier=barrier)
+            small[name] = {"ms_per_solve": m["total_ms"] / 5, "launches": m["launches"]}
+            del m
+        ex["cfg3_256_instances_latency"] = small
+    except Exception as e:  # noqa: BLE001
+        ex["cfg3_256_instances_latency"] = {"error": str(e)}
+    try:
+        ex["cfg5"] = measure_mixed(ms, torch, args, local_rank, WORKLOADS["cfg5"]["batch"], rank)
+    except Exception as e:  # noqa: BLE001
+        ex["cfg5"] = {"error": str(e)}
+    return ex
+
+
+def measure_mixed(ms, torch, args, local_rank, N, rank, steps=2):
+    """cfg5 per-GPU shard through mb2_mixed_batch_solve: host buffers in, host buffers out (an end-to-end figure by construction)."""
+    from momentum_b200.problems import mixed_problem
+
+    rigs, inst = mixed_problem(N, seed=12351 + 1000 * rank)
+    mb = ms.MixedBatch(device=local_rank)
+    rid = {name: mb.add_rig(ch) for name, (ch, _) in rigs.items()}
+    for x in inst:
+        mb.add_instance(rid[x["rig"]], x["parents"], x["offsets"], x["weights"], x["targets"], x["theta0"])
+    st = mb.stats()
+    opts = ms.GaussNewtonSolverOptions(min_iterations=ITERS, max_iterations=ITERS, threshold=1.0, regularization=0.05)
+    mb.solve(opts)  # builds every bucket's plan (once) and warms up
+    for i, x in enumerate(inst):
+        mb.set_parameters(i, x["theta0"])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    its = 0
+    for _ in range(steps):
+        out = mb.solve(opts)
+        its += int(out["iterations"].sum())
+        for i, x in enumerate(inst):
+            mb.set_parameters(i, x["theta0"])
+    dt = time.perf_counter() - t0
+    per_rig = {}
+    for b in range(st["buckets"]):
+        info = mb.bucket_info(b)
+        name = [k for k, v in rid.items() if v == info["rig"]][0]
+        d = per_rig.setdefault(name, {"instances": 0, "buckets": 0, "iterations": 0})
+        d["instances"] += info["instances"]; d["buckets"] += 1; d["iterations"] += info["iterations"]
+    return {"desc": WORKLOADS["cfg5"]["desc"], "value": its / dt, "unit": "GN it/s (host buffers in and out, bucket staging included)", "instances": N, "buckets": st["buckets"],
+            "padding_waste": st["padding_waste"], "largest_bucket": st["largest_bucket"], "per_rig": per_rig, "status_bad": int((out["status"] != 0).sum()), "ms_per_solve": 1e3 * dt / steps}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -187,7 +401,10 @@ def main():
     ap.add_argument("--batch-per-gpu", type=int, default=0)
     ap.add_argument("--jtj-mode", type=int, default=0)
     ap.add_argument("--cholesky-mode", type=int, default=0)
+    ap.add_argument("--fused-mode", type=int, default=0)
+    ap.add_argument("--strong", action="store_true", help="strong scaling: the workload's global batch (cfg3: 65536) is split over the ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other workloads measured in the same run (cfg2, cfg4, cfg5, convergence mode)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -205,28 +422,12 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.strong:
+        total = WORKLOADS[args.workload].get("global_batch", WORKLOADS[args.workload]["batch"] * 8)
+        args.batch_per_gpu = total // world
     B = args.batch_per_gpu or WORKLOADS[args.workload]["batch"]
-    ch, efs, theta0, _ = make_problem(args.workload, B, seed_offset=1000 * rank)  # each rank owns a different shard
-    n = ch.num_params
-    fn = ms.SkeletonSolverFunction(ch, B, efs, device=local_rank)
-    fn.upload_targets()
-    opts = ms.GaussNewtonSolverOptions(min_iterations=ITERS, max_iterations=ITERS, threshold=1.0, regularization=0.05, jtj_mode=args.jtj_mode, cholesky_mode=args.cholesky_mode)
-    solver = ms.GaussNewtonSolver(opts, fn)
-    m_rows = sum(3 * len(e.parents) if e.kind == 0 else 9 * len(e.parents) for e in efs)
-    assert m_rows == WORKLOADS[args.workload]["rows_m"] and n == WORKLOADS[args.workload]["params_n"]
-
     work_stream = torch.cuda.Stream()  # a real (non-NULL) stream: NULL means "the handle's own stream" in the C-ABI
     torch.cuda.set_stream(work_stream)
-    stream = work_stream.cuda_stream
-    theta0_dev = torch.from_numpy(theta0.astype(np.float32)).cuda()
-    theta_dev = torch.empty_like(theta0_dev)
-    # pinned host buffers for the e2e leg
-    theta0_pin = torch.from_numpy(theta0.astype(np.float32)).pin_memory()
-    # the solve is in place (like the reference's solve(params)): one pinned in/out buffer per e2e step, filled before the timed region
-    n_e2e = max(1, args.warmup // 2) + args.steps
-    theta_pins = [theta0_pin.clone().pin_memory() for _ in range(n_e2e)]
-    theta_pin = theta_pins[0]
-    target_pins = [torch.from_numpy(np.ascontiguousarray(e.targets, np.float32)).pin_memory() for e in efs]
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")  # > 126 MB L2
 
     def barrier():
@@ -235,136 +436,58 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def device_step():
-        theta_dev.copy_(theta0_dev)
-        solver.solve_device(theta_dev.data_ptr(), stream)
+    peaks = measured_peaks()
+    if args.workload == "cfg5":
+        r = measure_mixed(ms, torch, args, local_rank, B, rank, steps=args.steps)
+        from momentum_b200.distributed import aggregate_solve_stats
 
-    e2e_count = [0]
+        its_total, _, _ = aggregate_solve_stats(float(r["value"]), 0.0, 0.0, device="cuda")
+        if rank == 0:
+            line = {"metric": "GN iterations/sec (mixed-rig batch through the bucketing front end)", "value": its_total, "unit": "GN it/s", "n_gpus": world, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": r["ms_per_solve"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "config": bench_config(args, world), "cfg5": r, "e2e": {"value": its_total, "unit": "GN it/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None}}
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
-    def e2e_step():
-        buf = theta_pins[e2e_count[0] % n_e2e]
-        e2e_count[0] += 1
-        for idx, tp in enumerate(target_pins):
-            fn._check(fn._L.mb2_set_targets(fn._h, idx, ms.C.cast(tp.data_ptr(), ms._fp)))
-        solver.solve_host_pointer(buf.data_ptr())
-        return solver.get_results()
-
-    # ---- device-resident timing (value) ----
-    for _ in range(args.warmup):
-        device_step()
-    barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    total_ms = 0.0
-    for _ in range(args.steps):
-        flush.zero_()  # flush L2 between timed iterations
-        torch.cuda.synchronize()
-        ev0.record()
-        device_step()
-        ev1.record()
-        torch.cuda.synchronize()
-        total_ms += ev0.elapsed_time(ev1)
-    barrier()
-    res = solver.get_results()
-    its_per_step = int(res["iterations"].sum())
-    total_iter, launches = solver.get_counters()
+    m = measure_workload(ms, torch, args.workload, B, rank, local_rank, args, args.steps, args.warmup, flush=flush, barrier=barrier)
+    clocks = sampler.stop()  # sampled across the device-resident and the end-to-end timed regions
     # the one collective of the path: aggregate iterations / residual norm (SUM) and elapsed device time (MAX over ranks)
     from momentum_b200.distributed import aggregate_solve_stats
 
-    its_total, err_total, max_ms = aggregate_solve_stats(float(its_per_step), float(res["errors"].sum()), total_ms, device="cuda")
+    its_total, err_total, max_ms = aggregate_solve_stats(float(m["its_per_step"]), m["err_sum"], m["total_ms"], device="cuda")
     value = its_total * args.steps / (max_ms * 1e-3)
-
-    # ---- per-kernel times for the roofline (profiling mode: events around every launch) ----
-    solver.set_profiling(True)
-    device_step()
-    torch.cuda.synchronize()
-    solver.get_results()
-    phase_ms, phase_launches = solver.get_phase_times()
-    solver.set_profiling(False)
-
-    # ---- e2e through the host-buffer C-ABI call ----
-    for _ in range(max(1, args.warmup // 2)):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        r = e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop()  # sampled across the device-resident and the end-to-end timed regions
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    te = torch.tensor([m["e2e_s"]], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = its_total * args.steps / te.item()
-    h2d = int(theta0_pin.numel() * 4 + sum(tp.numel() * 4 for tp in target_pins))
-    d2h = int(theta_pin.numel() * 4 + B * (8 + 4 + 4))
-
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    peaks = measured_peaks()
-    tf32_peak = 0.5 * peaks["bf16"]  # TF32 dense = half the bf16 rate (B200_PROFILING.md table); bf16 figure is the measured cuBLAS burst
-    hbm_peak = peaks["hbm_gbs"]
-    st = solver.get_plan_stats()
-    sweep_ms = phase_ms[0] / max(1, phase_launches[0])
-    jtj_ms = phase_ms[1] / max(1, phase_launches[1])
-    chol_ms = phase_ms[2] / max(1, phase_launches[2])
-    target_floats = sum(tp.numel() for tp in target_pins) // B
-    # ALGORITHMIC bytes / flops per instance and launch (DESIGN.md section 4 derives each figure)
-    k1_bytes = 4.0 * (n + target_floats + st["jacobian_nonzeros"] + m_rows) + 8.0
-    jtj_flops = float(m_rows) * n * (n + 1)
-    k2_bytes = 4.0 * (m_rows * (st["jacobian_columns"] + 1) + (st["normal_parameters"] + 1) * (st["normal_parameters"] + 2) / 2)
-    k3_entries = st["cholesky_tiles"] * 256 if st["cholesky_tiles"] else st["normal_parameters"] * (st["normal_parameters"] + 1) / 2
-    k3_bytes = 4.0 * (k3_entries + 4 * st["normal_parameters"])
-    traffic = measured_traffic(args.workload, B)
-
-    def hbm_entry(name, key, bytes_per_instance, ms):
-        ach = bytes_per_instance * B / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-        return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "peak_source": f"{peaks['src']} copy bandwidth", "traffic": traffic.get(key), "ms_per_launch": ms,
-                "algorithmic_bytes_per_instance": bytes_per_instance}
-
-    gram = st["strip_floats"] > 0  # tile-sparse Gram path: strips in, tiles out, no dense J / H
-    if gram:
-        k1_bytes = 4.0 * (n + target_floats + st["jacobian_nonzeros"] + m_rows) + 8.0
-        gram_bytes = 4.0 * (st["strip_floats"] + st["cholesky_tiles"] * 256 + 16 * ((st["normal_parameters"] + 15) // 16))
-        gram_flops = 2.0 * st["gram_macs"]
-        gram_ach = gram_flops * B / (jtj_ms * 1e-3) / 1e12 if jtj_ms > 0 else 0.0
-        k2_entry = hbm_entry("gramTilesKernel (tile-sparse J^T J / J^T r, mma.sync 3xTF32 over non-zero strips)", "jtj_jtr", gram_bytes, jtj_ms)
-        # the JtJ kernel is credited m n (n + 1) flops per instance whatever it executes; both forms are reported
-        dense_eq = jtj_flops * B / (jtj_ms * 1e-3) / 1e12 if jtj_ms > 0 else 0.0
-        step_ms = sweep_ms + jtj_ms + chol_ms
-        k2_entry.update({"algorithmic_flops_per_instance": gram_flops, "tflops": gram_ach, "dense_equivalent_flops_per_instance": jtj_flops,
-                         "dense_equivalent_tflops": dense_eq, "dense_equivalent_frac_of_tf32_peak": dense_eq / tf32_peak,
-                         "dense_equivalent_tflops_end_to_end": jtj_flops * B / (step_ms * 1e-3) / 1e12 if step_ms > 0 else 0.0})
-    else:
-        jtj_ach = jtj_flops * B / (jtj_ms * 1e-3) / 1e12 if jtj_ms > 0 else 0.0
-        k2_entry = {"kernel": "jtjTensorKernel (JtJ/Jtr, tcgen05 3xTF32)" if st["jacobian_columns"] + 1 <= 256 and args.jtj_mode in (0, 2, 3) else "jtjSimtKernel",
-                    "bound": "tensor", "achieved": jtj_ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": jtj_ach / tf32_peak,
-                    "peak_source": f"0.5 x {peaks['src']} bf16 cuBLAS burst ({peaks['bf16']} TF/s) = TF32 dense", "traffic": traffic.get("jtj_jtr"),
-                    "ms_per_launch": jtj_ms, "algorithmic_flops_per_instance": jtj_flops, "algorithmic_bytes_per_instance": k2_bytes,
-                    "hbm_frac": (k2_bytes * B / (jtj_ms * 1e-3) / 1e9 / hbm_peak) if jtj_ms > 0 else 0.0}
-    kernels = [
-        hbm_entry("sweepKernel<true> (FK + residual + Jacobian)", "fk_residual_jacobian", k1_bytes, sweep_ms),
-        k2_entry,
-        hbm_entry("choleskyScheduledKernel (damped LLT + solves + update)" if st["cholesky_tiles"] else "choleskyKernel (dense LLT + solves + update)",
-                  "cholesky_update", k3_bytes, chol_ms),
-    ]
+    kernels, jtj_phase, kms, st = kernel_report(m, peaks, args.workload)
     dominant = max(kernels, key=lambda k: k["ms_per_launch"])
     line = {
         "metric": "GN iterations/sec (batched 72-joint IK)", "value": value, "unit": "GN it/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": bench_config(args, world),
         "solves_per_sec": value / ITERS, "aggregate_final_error": err_total,
-        "e2e": {"value": e2e_value, "unit": "GN it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": int(launches),
+        "e2e": {"value": e2e_value, "unit": "GN it/s", "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"]},
+        "gpu_launches": int(m["launches"]),
         "clocks": clocks,
         "roofline": dominant,
         "roofline_all_kernels": kernels,
-        "kernels_ms_per_iteration": {"fk_residual_jacobian": sweep_ms, "jtj_jtr": jtj_ms, "cholesky_update": chol_ms},
+        "jtj": jtj_phase,
+        "kernels_ms_per_iteration": kms,
+        "path": {0: "three kernels per iteration", 1: "persistent whole-solve kernel", 2: "sweep + gramCholesky per iteration"}[m["fused"]["fused"]],
+        "plan": {"tiles": st["cholesky_tiles"], "levels": st["cholesky_levels"], "strip_floats": st["strip_floats"], "gram_pairs": st["gram_pairs"]},
     }
+    if world == 1 and not args.no_extras:
+        del m
+        line["other_workloads"] = extra_workloads(ms, torch, args, rank, local_rank, flush, barrier, peaks)
     if not args.no_cpu_baseline:
         value_cpu, threads, desc, single, _ = time_cpu_arm(args.workload, 10.0)
         line["cpu_baseline"] = {"value": value_cpu, "unit": "GN it/s", "cores": threads, "kind": "port", "sample": desc, "single_thread_value": single}

@@ -458,9 +458,13 @@ def forward_kinematics(ch: Character, theta: np.ndarray):
 
 
 def world_points(ch: Character, theta, parents, offsets):
+    """offsets [nc,3] (shared by the batch) or [B,nc,3] (per instance)."""
     t, q, s = forward_kinematics(ch, theta)
     parents = np.asarray(parents)
-    return t[:, parents] + _qrot(q[:, parents], s[:, parents, None] * np.asarray(offsets, np.float64)[None])
+    off = np.asarray(offsets, np.float64)
+    if off.ndim == 2:
+        off = off[None]
+    return t[:, parents] + _qrot(q[:, parents], s[:, parents, None] * off)
 
 
 def world_rotations(ch: Character, theta, parents, offsets_q):

@@ -161,27 +161,29 @@ def mixed_rigs():
 
 def mixed_problem(N, seed=12351, rigs=None):
     """N instances: rig drawn 25/50/15/10 %, constraint count U{4..200} capped by the rig's marker list, offsets and targets per
-    instance (reachable poses), theta0 = 0. Returns (rigs dict, list of instance dicts)."""
+    instance (reachable poses), theta0 = 0. Returns (rigs dict, list of instance dicts in input order)."""
     rng = np.random.default_rng(seed)
     rigs = rigs or mixed_rigs()
     names = [n for n, _ in MIXED_RIGS]
     probs = np.array([p for _, p in MIXED_RIGS])
     which = rng.choice(len(names), size=N, p=probs)
     counts = rng.integers(4, 201, size=N)
-    inst = []
-    for i in range(N):
-        name = names[which[i]]
+    inst = [None] * N
+    for r, name in enumerate(names):  # one batched FK per rig class
+        ids = np.nonzero(which == r)[0]
+        if ids.size == 0:
+            continue
         ch, markers = rigs[name]
-        c = int(min(counts[i], len(markers)))
-        n = ch.num_params
-        theta_star = np.zeros(n)
-        theta_star[7:] = rng.uniform(-0.4, 0.4, n - 7)
-        theta_star[3:6] = rng.uniform(-0.5, 0.5, 3)
-        theta_star[0:3] = rng.uniform(-10.0, 10.0, 3) if name != "chain22" else rng.uniform(-1.0, 1.0, 3)
-        parents = np.array(markers[:c], np.int32)
+        n, cap = ch.num_params, len(markers)
+        theta_star = np.zeros((ids.size, n))
+        theta_star[:, 7:] = rng.uniform(-0.4, 0.4, (ids.size, n - 7))
+        theta_star[:, 3:6] = rng.uniform(-0.5, 0.5, (ids.size, 3))
+        theta_star[:, 0:3] = rng.uniform(-10.0, 10.0, (ids.size, 3)) if name != "chain22" else rng.uniform(-1.0, 1.0, (ids.size, 3))
         scale = 1.0 if name == "chain22" else 3.0
-        offsets = rng.uniform(-scale, scale, (c, 3))
-        targets = mc.world_points(ch, theta_star[None], parents, offsets)[0]
-        inst.append(dict(rig=name, parents=parents, offsets=offsets.astype(np.float32), weights=np.ones(c, np.float32), targets=targets.astype(np.float32),
-                         theta0=np.zeros(n, np.float32), theta_star=theta_star))
+        offsets = rng.uniform(-scale, scale, (ids.size, cap, 3))
+        targets = mc.world_points(ch, theta_star, np.array(markers, np.int32), offsets)
+        for k, i in enumerate(ids):
+            c = int(min(counts[i], cap))
+            inst[i] = dict(rig=name, parents=np.array(markers[:c], np.int32), offsets=offsets[k, :c].astype(np.float32), weights=np.ones(c, np.float32),
+                           targets=targets[k, :c].astype(np.float32), theta0=np.zeros(n, np.float32), theta_star=theta_star[k])
     return rigs, inst
