@@ -216,13 +216,17 @@ def measure_workload(ms, torch, workload, B, rank, local_rank, args, steps, warm
     out = {"ch": ch, "efs": efs, "n": n, "B": B, "solver": solver, "fn": fn, "total_ms": total_ms, "its_per_step": int(res["iterations"].sum()),
            "err_sum": float(res["errors"].sum()), "launches": solver.get_counters()[1], "status_bad": int((res["status"] != 0).sum())}
     if profile:
-        solver.set_profiling(True)
+        solver.set_profiling(1)  # events around the production kernels: the per-kernel times
         device_step()
         torch.cuda.synchronize()
         solver.get_results()
         out["phase_ms"], out["phase_launches"] = solver.get_phase_times()
+        solver.set_profiling(2)  # instrumented instantiations: only the phase SHARES are taken from this pass
+        device_step()
+        torch.cuda.synchronize()
+        solver.get_results()
         out["fused"] = solver.get_fused_profile()
-        solver.set_profiling(False)
+        solver.set_profiling(0)
     if e2e:
         theta0_pin = torch.from_numpy(theta0.astype(np.float32)).pin_memory()
         n_e2e = max(1, warmup // 2) + steps

@@ -116,7 +116,8 @@ typedef enum mb2_cholesky_mode {
  *                  at thousands of instances (three instances per SM cannot hide the sweep's dependent chains; profiles/), so AUTO does
  *                  not pick it. */
 typedef enum mb2_fused_mode {
-  MB2_FUSED_AUTO = 0,          /* GRAM_CHOLESKY when strips / tiles fit in shared memory, else OFF */
+  MB2_FUSED_AUTO = 0,          /* PERSISTENT when the batch is a single wave of instance groups (<= 3 per SM), else GRAM_CHOLESKY when strips / tiles fit in
+                                  shared memory, else OFF */
   MB2_FUSED_OFF = 1,
   MB2_FUSED_PERSISTENT = 2,    /* or MB2_ERR_UNSUPPORTED */
   MB2_FUSED_GRAM_CHOLESKY = 3  /* or MB2_ERR_UNSUPPORTED */
@@ -211,6 +212,8 @@ int mb2_set_targets(mb2_solver_function* f, int32_t index, const float* targets)
 int mb2_set_targets_device(mb2_solver_function* f, int32_t index, const float* targets_device, void* cuda_stream);
 /* Optional per-instance constraint weights [B*nc] for a Position/Orientation block (ConstraintData::weight) */
 int mb2_set_constraint_weights(mb2_solver_function* f, int32_t index, const float* weights, int32_t per_instance);
+/* the same from device memory, [B][nc] contiguous, on `cuda_stream` (NULL = handle stream) */
+int mb2_set_constraint_weights_device(mb2_solver_function* f, int32_t index, const float* weights_device, void* cuda_stream);
 /* SolverFunctionT::setEnabledParameters(ParameterSet) — skeleton_solver_function.cpp:45-61 */
 int mb2_solver_function_set_enabled_parameters(mb2_solver_function* f, const uint64_t bits[MB2_PARAMETER_SET_WORDS]);
 
@@ -220,6 +223,10 @@ int mb2_solver_function_get_error(mb2_solver_function* f, const float* parameter
  * instance, rows = mb2_solver_function_jacobian_rows), residual [B][rows]. */
 int mb2_solver_function_get_jacobian(mb2_solver_function* f, const float* parameters, float* jacobian, float* residual,
                                      double* errors, int32_t* actual_rows);
+/* getJacobian with parameters and result on the device (no copy): *jacobian_device points at the handle's Jacobian buffer,
+ * [B][n + 1][ld] floats, column c of instance b at ((b * (n + 1)) + c) * ld, column n = residual; rows beyond
+ * mb2_solver_function_jacobian_rows are zero. Valid until the next call on the handle. */
+int mb2_solver_function_get_jacobian_device(mb2_solver_function* f, const float* parameters_device, const float** jacobian_device, int32_t* ld, void* cuda_stream);
 /* SolverFunctionT::getJtJR — solver_function.cpp:74-121. jtj [B][ap][ap] (lower triangle valid,
  * ap = actual parameters), jtr [B][ap]. */
 int mb2_solver_function_get_jtjr(mb2_solver_function* f, const float* parameters, int32_t jtj_mode, float* jtj, float* jtr,
@@ -254,7 +261,9 @@ int mb2_solver_get_error_history(mb2_solver* s, double* history);
 int mb2_solver_get_counters(mb2_solver* s, uint64_t* total_iterations, uint64_t* kernel_launches);
 /* device time of the dominant kernels in the last solve, milliseconds (CUDA events on the handle's
  * stream); index: 0 = FK+Jacobian, 1 = JtJ/Jtr, 2 = Cholesky/update, 3 = error-only. Enabled by
- * mb2_solver_set_profiling(s, 1); off by default (events serialise the stream). */
+ * mb2_solver_set_profiling(s, 1); off by default (events serialise the stream). Level 2 additionally runs the instrumented
+ * instantiations of the fused kernels (per-phase SM cycles, mb2_solver_get_fused_profile); those are slower, so take kernel times
+ * at level 1 and phase shares at level 2. */
 int mb2_solver_set_profiling(mb2_solver* s, int32_t enabled);
 int mb2_solver_get_phase_times(mb2_solver* s, double ms[4], uint64_t launches[4]);
 /* Per-instance algorithmic sizes of the plan the last solve ran on (roofline accounting in bench.py; no reference

@@ -171,6 +171,7 @@ struct mb2_solver {
   int* hActiveCount{nullptr}; // pinned
   uint64_t totalIterations{0}, kernelLaunches{0};
   bool profiling{false};
+  bool inKernelProfile{false}; // profiling level 2: the instrumented kernel instantiations (clock64 per phase; slower)
   std::vector<PhaseEvent> events;
   double phaseMs[4]{0, 0, 0, 0};
   uint64_t phaseLaunches[4]{0, 0, 0, 0};
@@ -840,6 +841,29 @@ int mb2_set_constraint_weights(mb2_solver_function* f, int32_t index, const floa
   return MB2_OK;
 }
 
+// per-instance weights of one block from DEVICE memory [B][nc] (the torch binding's path: no host round trip)
+int mb2_set_constraint_weights_device(mb2_solver_function* f, int32_t index, const float* weights_device, void* stream) {
+  MB2_CHECK(f != nullptr && index >= 0 && index < int(f->efs.size()) && weights_device, "invalid constraint weights");
+  HostErrorFunction& ef = f->efs[index];
+  MB2_CHECK(ef.kind <= 2 || ef.kind == 5, "constraint weights apply to Position/Orientation/Plane error functions");
+  MB2_DEVICE_GUARD(f->ch->device);
+  const int nc = ef.numConstraints();
+  if (!f->weightsPerInstance) { // expand the shared array to [B][numWeights]
+    std::vector<float> all(size_t(f->B) * f->numWeights);
+    for (int b = 0; b < f->B; ++b) std::copy(f->hWeights.begin(), f->hWeights.end(), all.begin() + size_t(b) * f->numWeights);
+    f->dWeights.release();
+    MB2_CUDA(f->dWeights.upload(all, f->stream));
+    MB2_CUDA(cudaStreamSynchronize(f->stream));
+    f->weightsPerInstance = true;
+    f->planDirty = true; // tables() carries the per-instance flag
+  }
+  cudaStream_t st = stream ? (cudaStream_t)stream : f->stream;
+  if (nc > 0)
+    MB2_CUDA(cudaMemcpy2DAsync(f->dWeights.p + ef.weightOff, size_t(f->numWeights) * sizeof(float), weights_device, size_t(nc) * sizeof(float), size_t(nc) * sizeof(float), f->B,
+                               cudaMemcpyDeviceToDevice, st));
+  return MB2_OK;
+}
+
 int mb2_solver_function_set_enabled_parameters(mb2_solver_function* f, const uint64_t* bits) {
   MB2_CHECK(f != nullptr && bits != nullptr, "null argument");
   bitsToEnabled(bits, f->ch->host.numParams, f->enabled);
@@ -880,6 +904,20 @@ int mb2_solver_function_get_jacobian(mb2_solver_function* f, const float* params
   if (errors) MB2_CUDA(cudaMemcpyAsync(errors, f->dErrors.p, size_t(f->B) * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
   MB2_CUDA(cudaStreamSynchronize(f->stream));
   if (actualRows) *actualRows = rows; // solver_function.cpp:50 actualRows = totalRows (padded)
+  return MB2_OK;
+}
+
+// getJacobian with parameters and outputs resident on the device (backward pass of the torch binding): jacobian [B][n][ldJ] in the
+// device layout (column c of instance b at (b * (n + 1) + c) * ldJ, ldJ = mb2_solver_function_jacobian_stride), residual = column n.
+int mb2_solver_function_get_jacobian_device(mb2_solver_function* f, const float* params_device, const float** jacobian_device, int32_t* ld, void* stream) {
+  MB2_CHECK(f != nullptr && params_device && jacobian_device, "null argument");
+  MB2_DEVICE_GUARD(f->ch->device);
+  int rc = ensurePlan(f, 0);
+  if (rc != MB2_OK) return rc;
+  cudaStream_t st = stream ? (cudaStream_t)stream : f->stream;
+  MB2_CUDA(launchSweep(sweepArgs(f, params_device, nullptr), true, st));
+  *jacobian_device = f->dJ.p;
+  if (ld) *ld = f->ldJ;
   return MB2_OK;
 }
 
@@ -958,6 +996,7 @@ int mb2_solver_set_enabled_parameters(mb2_solver* s, const uint64_t* bits) {
 int mb2_solver_set_profiling(mb2_solver* s, int32_t enabled) {
   MB2_CHECK(s != nullptr, "null solver");
   s->profiling = enabled != 0;
+  s->inKernelProfile = enabled >= 2;
   return MB2_OK;
 }
 
@@ -1003,7 +1042,17 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
     const bool eligible = useGram && useSchedule && o.do_line_search == 0 && f->sched->fConfig.groups >= 1 && f->sched->fBlob.p != nullptr;
     if (o.fused_mode == MB2_FUSED_PERSISTENT && !eligible)
       return fail(MB2_ERR_UNSUPPORTED, "the fused kernel needs the tile-sparse Gram + tile-scheduled Cholesky path, no line search, and a plan that fits in shared memory");
-    if (o.fused_mode == MB2_FUSED_PERSISTENT && eligible) {
+    // AUTO takes the persistent kernel when the whole batch is one wave of instance groups: a single launch with no host round trip
+    // beats ~2 launches per iteration there (measured 0.60 vs 0.89 ms at 256 x humanoid72 x 10 iterations); at thousands of instances
+    // the per-iteration kernels hide latency better (three instances per SM cannot) and AUTO keeps them
+    int smCount = 0;
+    if (eligible && o.fused_mode == MB2_FUSED_AUTO) {
+      int dev0 = 0;
+      MB2_CUDA(cudaGetDevice(&dev0));
+      MB2_CUDA(cudaDeviceGetAttribute(&smCount, cudaDevAttrMultiProcessorCount, dev0));
+    }
+    const bool oneWave = eligible && o.fused_mode == MB2_FUSED_AUTO && B <= f->sched->fConfig.groups * smCount;
+    if ((o.fused_mode == MB2_FUSED_PERSISTENT || oneWave) && eligible) {
       const DeviceSchedule& ds = *f->sched;
       MB2_CUDA(s->dIterations.resize(B));
       MB2_CUDA(s->dStatus.resize(B));
@@ -1043,7 +1092,7 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
       if (s->profiling) {
         MB2_CUDA(s->dPhaseCycles.resize(16));
         MB2_CUDA(cudaMemsetAsync(s->dPhaseCycles.p, 0, 16 * sizeof(unsigned long long), st));
-        fa.phaseCycles = s->dPhaseCycles.p;
+        fa.phaseCycles = s->inKernelProfile ? s->dPhaseCycles.p : nullptr;
         if (!s->fusedStart) { MB2_CUDA(cudaEventCreate(&s->fusedStart)); MB2_CUDA(cudaEventCreate(&s->fusedStop)); }
         MB2_CUDA(cudaEventRecord(s->fusedStart, st));
       }
@@ -1052,7 +1101,7 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
       MB2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
       {
         NvtxRange nvtxIt("mb2::fusedSolveKernel (GaussNewtonSolverT::doIteration x maxIterations)");
-        MB2_CUDA(launchFusedSolve(fa, ds.fConfig, sms, s->profiling, st));
+        MB2_CUDA(launchFusedSolve(fa, ds.fConfig, sms, s->inKernelProfile, st));
       }
       if (s->profiling) MB2_CUDA(cudaEventRecord(s->fusedStop, st));
       for (auto& e : s->events) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }
@@ -1193,8 +1242,8 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
       gc.g = g;
       gc.c = c;
       gc.c.tilesIn = nullptr;
-      gc.phaseCycles = s->profiling ? s->dPhaseCycles.p : nullptr;
-      MB2_CUDA(launchGramCholesky(gc, f->sched->dev, s->profiling, st));
+      gc.phaseCycles = s->inKernelProfile ? s->dPhaseCycles.p : nullptr;
+      MB2_CUDA(launchGramCholesky(gc, f->sched->dev, s->inKernelProfile, st));
     } else if (useSchedule) MB2_CUDA(launchCholeskyScheduled(c, f->sched->dev, st));
     else MB2_CUDA(launchCholesky(c, st));
     recordPhaseStop(s, st);

@@ -184,6 +184,9 @@ def mixed_problem(N, seed=12351, rigs=None):
         targets = mc.world_points(ch, theta_star, np.array(markers, np.int32), offsets)
         for k, i in enumerate(ids):
             c = int(min(counts[i], cap))
-            inst[i] = dict(rig=name, parents=np.array(markers[:c], np.int32), offsets=offsets[k, :c].astype(np.float32), weights=np.ones(c, np.float32),
+            # constraint weights carry PositionErrorFunction::kLegacyWeight (position_error_function.h:64), as in cfg2 / cfg3 / cfg4: with
+            # weight 1 and lambda = 0.05 the first Gauss-Newton steps from theta = 0 towards targets ~10 units away overshoot and diverge
+            inst[i] = dict(rig=name, parents=np.array(markers[:c], np.int32), offsets=offsets[k, :c].astype(np.float32),
+                           weights=np.full(c, mc.PositionErrorFunction.kLegacyWeight if name != "chain22" else 1.0, np.float32),
                            targets=targets[k, :c].astype(np.float32), theta0=np.zeros(n, np.float32), theta_star=theta_star[k])
     return rigs, inst

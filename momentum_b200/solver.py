@@ -64,6 +64,7 @@ CABI_SYMBOLS = [
     "mb2_solver_destroy", "mb2_solver_set_options", "mb2_solver_set_enabled_parameters", "mb2_solver_solve", "mb2_solver_solve_device",
     "mb2_solver_get_results", "mb2_solver_get_error_history", "mb2_solver_get_counters", "mb2_solver_set_profiling",
     "mb2_solver_get_phase_times", "mb2_solver_get_plan_stats", "mb2_solver_get_fused_profile", "mb2_solver_solve_async", "mb2_solver_wait",
+    "mb2_set_constraint_weights_device", "mb2_solver_function_get_jacobian_device",
     "mb2_mixed_batch_last_error", "mb2_mixed_batch_create", "mb2_mixed_batch_destroy", "mb2_mixed_batch_add_rig", "mb2_mixed_batch_use_limits",
     "mb2_mixed_batch_add_instance", "mb2_mixed_batch_set_parameters", "mb2_mixed_batch_solve", "mb2_mixed_batch_get_result", "mb2_mixed_batch_get_results",
     "mb2_mixed_batch_stats", "mb2_mixed_batch_bucket_info",
@@ -125,6 +126,9 @@ def load_library(path: Optional[str] = None):
     if hasattr(L, "mb2_solver_get_fused_profile"):
         L.mb2_solver_get_fused_profile.argtypes = [vp, _ip, _ip, _dp, _up]
     L.mb2_default_gauss_newton_options.argtypes = [C.POINTER(_Options)]
+    if hasattr(L, "mb2_set_constraint_weights_device"):
+        L.mb2_set_constraint_weights_device.argtypes = [vp, C.c_int32, vp, vp]
+        L.mb2_solver_function_get_jacobian_device.argtypes = [vp, vp, C.POINTER(vp), _ip, vp]
     if hasattr(L, "mb2_mixed_batch_create"):
         L.mb2_solver_solve_async.argtypes = [vp, vp]
         L.mb2_solver_wait.argtypes = [vp, _dp, _ip, _ip]
@@ -304,6 +308,15 @@ class SkeletonSolverFunction(_Base):
         w, wp = _f32(weights)
         self._check(self._L.mb2_set_constraint_weights(self._h, index, wp, int(per_instance)))
 
+    def set_constraint_weights_device(self, index: int, device_ptr: int, stream: int = 0):
+        self._check(self._L.mb2_set_constraint_weights_device(self._h, index, C.c_void_p(device_ptr), C.c_void_p(stream)))
+
+    def get_jacobian_device(self, params_device_ptr: int, stream: int = 0):
+        """(device pointer to [B][n + 1][ld] floats, ld): Jacobian columns then the residual column, in the handle's own buffer."""
+        ptr = C.c_void_p(); ld = C.c_int32(0)
+        self._check(self._L.mb2_solver_function_get_jacobian_device(self._h, C.c_void_p(params_device_ptr), C.byref(ptr), C.byref(ld), C.c_void_p(stream)))
+        return ptr.value, ld.value
+
     def set_error_function_weight(self, index: int, weight: float):
         self._check(self._L.mb2_set_error_function_weight(self._h, index, weight))
 
@@ -437,8 +450,9 @@ class GaussNewtonSolver(_Base):
         self._check(self._L.mb2_solver_get_fused_profile(self._h, C.byref(fused), C.byref(groups), C.byref(ms_), cyc))
         return {"fused": int(fused.value), "groups": groups.value, "kernel_ms": ms_.value, "phase_cycles": dict(zip(self.FUSED_PHASES, (int(v) for v in cyc)))}
 
-    def set_profiling(self, enabled: bool):
-        self._check(self._L.mb2_solver_set_profiling(self._h, int(enabled)))
+    def set_profiling(self, level):
+        """0 off, 1 CUDA events around every launch (production kernels), 2 + in-kernel phase cycles (instrumented, slower kernels)."""
+        self._check(self._L.mb2_solver_set_profiling(self._h, int(level)))
 
     def get_phase_times(self):
         ms = (C.c_double * 4)(); ln = (C.c_uint64 * 4)()

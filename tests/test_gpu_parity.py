@@ -294,15 +294,15 @@ def test_fused_kernels_match_the_three_kernel_path(case):
         enabled = np.ones(ch.num_params, bool); enabled[[0, 5, 6, 40, 41, 42, 100, 219]] = False
     fn = parity.build_function(ch, efs, theta0.shape[0], enabled=enabled)
     res = {}
-    for fm, code in ((ms.FUSED_OFF, 0), (ms.FUSED_GRAM_CHOLESKY, 2), (ms.FUSED_AUTO, 2), (ms.FUSED_PERSISTENT, 1)):
+    for fm, code in ((ms.FUSED_OFF, 0), (ms.FUSED_GRAM_CHOLESKY, 2), (ms.FUSED_AUTO, 1), (ms.FUSED_PERSISTENT, 1)):  # AUTO: these batches are a single wave
         solver = ms.GaussNewtonSolver(ms.GaussNewtonSolverOptions(regularization=0.05, fused_mode=fm, store_error_history=True, **kw), fn)
         out = solver.solve(theta0)
         assert solver.get_fused_profile()["fused"] == code
         res[fm] = (out, solver.get_error_history())
     (a, ha), (b, hb), (c, hc), (d, hd) = res[ms.FUSED_OFF], res[ms.FUSED_GRAM_CHOLESKY], res[ms.FUSED_AUTO], res[ms.FUSED_PERSISTENT]
-    for o, h in ((b, hb), (c, hc)):
-        assert np.array_equal(a["params"], o["params"]) and np.array_equal(a["iterations"], o["iterations"]) and np.array_equal(a["status"], o["status"])
-        assert np.array_equal(a["errors"], o["errors"]) and np.array_equal(ha, h)
+    for x, hx, o, h in ((a, ha, b, hb), (d, hd, c, hc)):  # three kernels == Gram + Cholesky; AUTO == persistent
+        assert np.array_equal(x["params"], o["params"]) and np.array_equal(x["iterations"], o["iterations"]) and np.array_equal(x["status"], o["status"])
+        assert np.array_equal(x["errors"], o["errors"]) and np.array_equal(hx, h)
     assert np.array_equal(a["status"], d["status"]) and np.all(np.abs(a["iterations"].astype(int) - d["iterations"]) <= 1)
     scale = np.maximum(1.0, np.abs(a["params"]).max(axis=1, keepdims=True))
     assert np.max(np.abs(a["params"] - d["params"]) / scale) <= 5e-4   # a few GN iterations amplify rounding-level differences
@@ -335,6 +335,12 @@ def test_fused_modes_reject_what_they_cannot_run():
     solver = ms.GaussNewtonSolver(ms.GaussNewtonSolverOptions(max_iterations=2), fn)
     solver.solve(theta0)
     assert solver.get_fused_profile()["fused"] == 0
+    # AUTO at a batch larger than one wave of instance groups: Gram + Cholesky per iteration
+    ch, efs, theta0, _ = humanoid_problem(600, orientation=True)
+    fn = parity.build_function(ch, efs, 600)
+    solver = ms.GaussNewtonSolver(ms.GaussNewtonSolverOptions(max_iterations=2), fn)
+    solver.solve(theta0)
+    assert solver.get_fused_profile()["fused"] == 2
 
 
 def test_full_size_properties_cfg3_shard():
