@@ -147,6 +147,11 @@ class BatchedSkeletonSolverFunction {
     return idx;
   }
   void setTargets(int index, const std::vector<float>& targets) { check(mb2_set_targets(h_, index, targets.data())); }
+  // ConstraintData::weight of a Position / Orientation / Plane block: [nc] shared by the batch, or [B * nc] per instance
+  void setConstraintWeights(int index, const std::vector<float>& weights, bool perInstance = false) {
+    check(mb2_set_constraint_weights(h_, index, weights.data(), perInstance ? 1 : 0));
+  }
+  void setErrorFunctionWeight(int index, float weight) { check(mb2_set_error_function_weight(h_, index, weight)); } // SkeletonErrorFunctionT::setWeight
   void setEnabledParameters(const ParameterSet& ps) {
     uint64_t w[MB2_PARAMETER_SET_WORDS];
     toWords(ps, w);
