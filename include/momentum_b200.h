@@ -123,6 +123,15 @@ typedef enum mb2_fused_mode {
   MB2_FUSED_GRAM_CHOLESKY = 3  /* or MB2_ERR_UNSUPPORTED */
 } mb2_fused_mode;
 
+/* How the Gauss-Newton step is computed from the Jacobian. CHOLESKY = GaussNewtonSolverT / SubsetGaussNewtonSolverT (normal equations,
+ * Eigen::LLT; gauss_newton_solver.cpp:248-251). QR = GaussNewtonSolverQRT (character_solver/gauss_newton_solver_qr.cpp:50-150): an online
+ * Householder QR of [sqrt(lambda) I; J] (math/online_householder_qr.cpp), the default solver of pymomentum's solve_ik and of the marker
+ * tracker; same step up to rounding without squaring the condition number; its line search is the c1 = 1e-4 / g.delta rule (:116-143). */
+typedef enum mb2_linear_solver {
+  MB2_LINEAR_SOLVER_CHOLESKY = 0,
+  MB2_LINEAR_SOLVER_QR = 1
+} mb2_linear_solver;
+
 /* solver/solver.h:19-34 SolverOptions + solver/gauss_newton_solver.h:17-59 GaussNewtonSolverOptions,
  * field for field, plus device extensions at the end. */
 typedef struct mb2_gauss_newton_options {
@@ -139,6 +148,7 @@ typedef struct mb2_gauss_newton_options {
   int32_t store_error_history;    /* keep per-iteration error per instance (solver.h:90 getErrorHistory) */
   int32_t cholesky_mode;          /* mb2_cholesky_mode */
   int32_t fused_mode;             /* mb2_fused_mode */
+  int32_t linear_solver;          /* mb2_linear_solver */
 } mb2_gauss_newton_options;
 
 typedef struct mb2_character mb2_character;             /* Skeleton + ParameterTransform + ParameterLimits on device */

@@ -162,7 +162,7 @@ struct mb2_solver {
   mb2_gauss_newton_options opt{};
   DeviceBuffer<float> dH, dDelta, dThetaOrig, dTheta0, dScale, dGradDotDelta, dThetaStage, dGrad, dTiles;
   DeviceBuffer<double> dLastErrors, dTrialErrors, dHistory;
-  DeviceBuffer<int32_t> dActive, dIterations, dStatus, dSearching, dActiveCount, dWorkCounter;
+  DeviceBuffer<int32_t> dActive, dIterations, dStatus, dSearching, dActiveCount, dWorkCounter, dQrChunks;
   DeviceBuffer<unsigned long long> dPhaseCycles;
   bool lastFused{false}, lastGramChol{false};
   int lastFusedGroups{0};
@@ -564,6 +564,7 @@ void mb2_default_gauss_newton_options(mb2_gauss_newton_options* o) {
   o->store_error_history = 0;
   o->cholesky_mode = MB2_CHOLESKY_AUTO;
   o->fused_mode = MB2_FUSED_AUTO;
+  o->linear_solver = MB2_LINEAR_SOLVER_CHOLESKY;
 }
 
 int mb2_character_create(int device, int32_t J, const int32_t* parents, const float* offsets, const float* prerot, int32_t n,
@@ -1011,6 +1012,12 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
   for (uint8_t e : f->enabled) numEnabled += e ? 1 : 0;
   int cholMode = o.cholesky_mode;
   if (cholMode == 0) cholMode = numEnabled >= 48 ? 3 : 1;
+  const bool useQr = o.linear_solver == MB2_LINEAR_SOLVER_QR; // GaussNewtonSolverQRT's step: Householder QR of the K-major Jacobian (ik_qr.cuh)
+  if (useQr) {
+    if (o.jtj_mode == MB2_JTJ_SPARSE_TILES || o.cholesky_mode >= 2 || o.fused_mode >= MB2_FUSED_PERSISTENT)
+      return fail(MB2_ERR_UNSUPPORTED, "the QR step works on the dense Jacobian: it excludes the tile-sparse Gram, the tile Cholesky and the fused kernels");
+    cholMode = 1;
+  }
   // tile-sparse Gram: default whenever the tile-scheduled Cholesky runs (MB2_JTJ_AUTO), or on request
   bool useGram = cholMode >= 2 && (o.jtj_mode == MB2_JTJ_AUTO || o.jtj_mode == MB2_JTJ_SPARSE_TILES);
   if (o.jtj_mode == MB2_JTJ_SPARSE_TILES && cholMode < 2) return fail(MB2_ERR_UNSUPPORTED, "MB2_JTJ_SPARSE_TILES needs the tile-scheduled Cholesky");
@@ -1133,7 +1140,23 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
   // normal equations: full symmetric [ns+1][ldH] in device-column order (row/column ns = J^T r)
   const int ldH = roundUp(ns + 1, 16);
   const size_t hStride = size_t(ns + 1) * ldH;
-  if (!useGram) MB2_CUDA(s->dH.resize(size_t(B) * hStride));
+  if (!useGram && !useQr) MB2_CUDA(s->dH.resize(size_t(B) * hStride));
+  int qrMaxRows = 0, qrChunks = 0;
+  if (useQr) { // row chunks: one per error-function block (the reference adds block by block), split when a block does not fit beside R
+    qrMaxRows = qrMaxChunkRows(ns, size_t(200 * 1024));
+    if (qrMaxRows < 8) return fail(MB2_ERR_UNSUPPORTED, "the QR step keeps R in shared memory: too many enabled parameters for this kernel");
+    std::vector<int32_t> starts{0};
+    int r0 = 0, widest = 0;
+    for (const auto& ef : f->efs) {
+      if (!(ef.weight > 0.f)) continue;
+      const int size = jacobianBlockSize(f->ch->host, ef);
+      for (int done = 0; done < size; done += qrMaxRows) { const int p = std::min(qrMaxRows, size - done); starts.push_back(r0 + done + p); widest = std::max(widest, p); }
+      r0 += size;
+    }
+    qrChunks = int(starts.size()) - 1;
+    qrMaxRows = std::max(widest, 1);
+    MB2_CUDA(s->dQrChunks.upload(starts, st));
+  }
   float* Hbuf = s->dH.p;
   const size_t tilesStride = useGram ? size_t(f->sched->host.numTiles) * 256 + f->sched->host.nPad : 0;
   if (useGram && !(o.fused_mode == MB2_FUSED_AUTO || o.fused_mode == MB2_FUSED_GRAM_CHOLESKY)) MB2_CUDA(s->dTiles.resize(size_t(B) * tilesStride));
@@ -1176,8 +1199,10 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
     MB2_CUDA(launchSweep(sweepArgs(f, theta, s->dActive.p), true, st));
     recordPhaseStop(s, st);
     GramArgs g{};
-    if (!useGramChol) recordPhaseStart(s, 1, st);
-    if (useGram) {
+    if (!useGramChol && !useQr) recordPhaseStart(s, 1, st);
+    if (useQr) {
+      // nothing: the QR kernel reads the Jacobian directly
+    } else if (useGram) {
       const DeviceSchedule& ds = *f->sched;
       g.batch = B;
       g.strips = f->dJ.p;
@@ -1205,7 +1230,7 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
       rc = runJtJ(f, mode, ns, Hbuf, ldH, hStride, s->dActive.p, st, s->dGrad.p, ldG);
       if (rc != MB2_OK) return rc;
     }
-    if (!useGramChol) recordPhaseStop(s, st);
+    if (!useGramChol && !useQr) recordPhaseStop(s, st);
     CholArgs c{};
     c.batch = B;
     c.H = Hbuf;
@@ -1237,7 +1262,16 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
     c.tilesStride = tilesStride;
     c.profile = (it == 0 && cholProfile) ? 1 : 0;
     recordPhaseStart(s, 2, st);
-    if (useGramChol) {
+    if (useQr) {
+      QrArgs q{};
+      q.c = c;
+      q.jacobian = f->dJ.p;
+      q.numCols = f->plan.numCols;
+      q.ldJ = f->ldJ;
+      q.chunkStart = s->dQrChunks.p;
+      q.numChunks = qrChunks;
+      MB2_CUDA(launchQrSolve(q, qrMaxRows, st));
+    } else if (useGramChol) {
       GramCholArgs gc{};
       gc.g = g;
       gc.c = c;

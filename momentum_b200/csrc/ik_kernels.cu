@@ -814,6 +814,10 @@ cudaError_t launchGramCholesky(const GramCholArgs& a, const CholSchedDev& sched,
   return cudaGetLastError();
 }
 
+} // namespace mb2
+#include "ik_qr.cuh"
+namespace mb2 {
+
 cudaError_t initKernelAttributes() {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);

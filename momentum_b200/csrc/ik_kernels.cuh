@@ -95,6 +95,17 @@ struct GramCholArgs {
 size_t gramCholeskySmemBytes(size_t stripStride, int gramBlobInts, int n, int nPad, int numTiles, int schedBlobInts);
 cudaError_t launchGramCholesky(const GramCholArgs& a, const CholSchedDev& sched, bool profile, cudaStream_t stream);
 
+// QR-accurate linear step (ik_qr.cu): Householder sweeps of the K-major Jacobian into a shared-memory R, replaces JtJ + Cholesky
+struct QrArgs {
+  CholArgs c;                // ns, regularization, cols, theta, delta, bookkeeping ... (H / tiles unused)
+  const float* jacobian;     // [B][numCols + 1][ldJ], column numCols = residual (compact plan: numCols = ns)
+  int32_t numCols, ldJ;
+  const int32_t* chunkStart; // [numChunks + 1] first row of every chunk (device memory); a chunk never crosses an error-function block
+  int32_t numChunks;
+};
+size_t qrSmemFloats(int n, int maxChunkRows);
+int qrMaxChunkRows(int n, size_t smemBytes); // rows of Jacobian that fit beside R (0: the system is too large for this kernel)
+cudaError_t launchQrSolve(const QrArgs& a, int maxChunkRows, cudaStream_t stream);
 cudaError_t launchSweep(const SweepArgs& a, bool jacobian, cudaStream_t stream);
 size_t sweepSmemPerInstance(const FunctionTables& T, int warpsPerInstance);
 cudaError_t launchJtJSimt(const JtJArgs& a, cudaStream_t stream);

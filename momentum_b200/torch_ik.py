@@ -203,7 +203,7 @@ def _device_view(ptr: int, shape, device):
         pass
 
     a = _Arr()
-    a.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), True), "version": 2}
+    a.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
     return torch.as_tensor(a, device=device)
 
 

@@ -86,6 +86,7 @@ def _bind(L):
         L.orc_solve_batch.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, _dp,
                                       C.POINTER(_dp), C.c_int, _dp, _ip, _dp]
         L.orc_hardware_threads.restype = C.c_int
+        L.orc_online_qr.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, _dp, _dp, C.c_int, _ip, _dp, _dp]
     return L
 
 
@@ -224,17 +225,17 @@ class OracleFunction:
         return xf, ra.reshape(J, 3, 3).transpose(0, 2, 1), ta.reshape(J, 3, 3).transpose(0, 2, 1)
 
     def solve(self, params, *, min_iterations=1, max_iterations=2, threshold=1.0, regularization=0.05, do_line_search=False,
-              use_block_jtj=False, subset_solver=False):
+              use_block_jtj=False, subset_solver=False, qr_solver=False):
         """GaussNewtonSolverT::solve. Returns (error, params, iterations, error_history)."""
         p = np.ascontiguousarray(params, np.float64).copy()
         hist = np.zeros(max(1, max_iterations), np.float64)
         it = C.c_int(0)
         err = self._L.orc_solve(self.fn, min_iterations, max_iterations, threshold, regularization, int(do_line_search), int(use_block_jtj),
-                              int(subset_solver), p.ctypes.data_as(_dp), C.byref(it), hist.ctypes.data_as(_dp))
+                              2 if qr_solver else int(subset_solver), p.ctypes.data_as(_dp), C.byref(it), hist.ctypes.data_as(_dp))
         return err, p, it.value, hist[: it.value].copy()
 
     def solve_batch(self, params, *, threads=1, min_iterations=1, max_iterations=2, threshold=1.0, regularization=0.05,
-                    do_line_search=False, use_block_jtj=False, subset_solver=False, instances: Optional[slice] = None, final_errors=True):
+                    do_line_search=False, use_block_jtj=False, subset_solver=False, instances: Optional[slice] = None, final_errors=True, qr_solver=False):
         """One solver per instance over ``threads`` host threads (tensor_ik.cpp:127). Returns dict."""
         P = np.ascontiguousarray(params, np.float64).copy()
         B = P.shape[0]
@@ -250,9 +251,21 @@ class OracleFunction:
                 ptrs[idx] = None
         errs = np.zeros(B); fin = np.zeros(B); its = np.zeros(B, np.int32)
         secs = self._L.orc_solve_batch(self.fn, min_iterations, max_iterations, threshold, regularization, int(do_line_search), int(use_block_jtj),
-                                     int(subset_solver), B, P.ctypes.data_as(_dp), ptrs, int(threads), errs.ctypes.data_as(_dp),
+                                     2 if qr_solver else int(subset_solver), B, P.ctypes.data_as(_dp), ptrs, int(threads), errs.ctypes.data_as(_dp),
                                      its.ctypes.data_as(_ip), fin.ctypes.data_as(_dp) if final_errors else None)
         return {"params": P, "errors": errs, "final_errors": fin, "iterations": its, "seconds": secs}
+
+
+def online_qr(A, b, lam=0.0, chunks=None, dtype="float64"):
+    """OnlineHouseholderQR (math/online_householder_qr.cpp): rows of A added chunk by chunk; returns (result(), At_times_b())."""
+    A = np.ascontiguousarray(A, np.float64); b = np.ascontiguousarray(b, np.float64)
+    rows, n = A.shape
+    ch = np.ascontiguousarray(chunks if chunks is not None else [rows], np.int32)
+    assert ch.sum() == rows
+    x = np.zeros(n); g = np.zeros(n)
+    lib().orc_online_qr(0 if dtype == "float32" else 1, rows, n, float(lam), A.ctypes.data_as(_dp), b.ctypes.data_as(_dp), len(ch), ch.ctypes.data_as(_ip),
+                        x.ctypes.data_as(_dp), g.ctypes.data_as(_dp))
+    return x, g
 
 
 def hardware_threads() -> int:

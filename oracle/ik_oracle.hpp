@@ -1224,6 +1224,63 @@ struct GaussNewtonOptions {
   bool doLineSearch{false};
   bool useBlockJtJ{false};
   bool subsetSolver{false}; // SubsetGaussNewtonSolverT semantics (line search c1=1e-4 w/ gradient)
+  bool qrSolver{false};     // GaussNewtonSolverQRT: the step from an online Householder QR of [sqrt(lambda) I; J] (gauss_newton_solver_qr.cpp:50-150)
+};
+
+// math/online_householder_qr.cpp:20-243 — OnlineHouseholderQR<T>: R starts as lambda * I (the caller passes sqrt of the damping), every
+// add() sweeps one Householder reflector per column over the stacked [R; A], leaving R upper triangular with R^T R = lambda^2 I + sum A^T A
+// and y = Q^T b. v_1 = 1 is implicit, the reflector tail overwrites A's column (computeHouseholderVec, Golub & van Loan alg. 5.1.1).
+template <class T>
+struct OnlineHouseholderQR {
+  int n{0};
+  std::vector<T> R; // n x n, R(i, j) at R[i * n + j]
+  std::vector<T> y;
+  void reset(int n_, T lambda) { // :133-144
+    n = n_;
+    R.assign(size_t(n) * n, T(0));
+    if (lambda != T(0)) for (int i = 0; i < n; ++i) R[size_t(i) * n + i] = lambda;
+    y.assign(n, T(0));
+  }
+  // A: rows x n, column c at A + c * lda (rows contiguous); b: rows. Both are overwritten (addMutating :171-221).
+  void addMutating(T* A, int lda, int rows, T* b) {
+    for (int iCol = 0; iCol < n; ++iCol) {
+      T* col = A + size_t(iCol) * lda;
+      T sigma = 0; // computeHouseholderVec :97-118
+      for (int k = 0; k < rows; ++k) sigma += col[k] * col[k];
+      if (sigma == T(0)) continue; // beta == 0: nothing below R(iCol, iCol)
+      const T x1 = R[size_t(iCol) * n + iCol];
+      const T mu = std::sqrt(x1 * x1 + sigma);
+      const T v1 = (x1 <= T(0)) ? (x1 - mu) : (-sigma / (x1 + mu));
+      const T beta = T(2) * v1 * v1 / (sigma + v1 * v1);
+      for (int k = 0; k < rows; ++k) col[k] /= v1;
+      R[size_t(iCol) * n + iCol] = mu;
+      for (int jCol = iCol + 1; jCol <= n; ++jCol) { // applyHouseholderTransformation :30-46 on the remaining columns, then on (y, b)
+        T* y2 = jCol < n ? A + size_t(jCol) * lda : b;
+        T& y1 = jCol < n ? R[size_t(iCol) * n + jCol] : y[iCol];
+        T dot = 0;
+        for (int k = 0; k < rows; ++k) dot += col[k] * y2[k];
+        const T scalar = (y1 + dot) * beta;
+        y1 -= scalar;
+        for (int k = 0; k < rows; ++k) y2[k] -= scalar * col[k];
+      }
+    }
+  }
+  std::vector<T> result() const { // R.triangularView<Upper>().solve(y); a zero pivot with a zero right-hand side gives 0 (:235-243)
+    std::vector<T> x(y);
+    for (int i = n - 1; i >= 0; --i) {
+      T s = x[i];
+      for (int k = i + 1; k < n; ++k) s -= R[size_t(i) * n + k] * x[k];
+      const T d = R[size_t(i) * n + i];
+      x[i] = (d == T(0) && s == T(0)) ? T(0) : s / d;
+    }
+    return x;
+  }
+  std::vector<T> AtTimesB() const { // R^T y (:224-232)
+    std::vector<T> g(n, T(0));
+    for (int i = 0; i < n; ++i)
+      for (int j = i; j < n; ++j) g[j] += R[size_t(i) * n + j] * y[i];
+    return g;
+  }
 };
 
 // solver/solver.cpp:50-128 + gauss_newton_solver.cpp:49-313 (+ subset_gauss_newton_solver.cpp:72-145)
@@ -1247,7 +1304,53 @@ struct GaussNewtonSolver {
     activeParameters = ps;
     fn->setEnabledParameters(ps);
   }
+  // character_solver/gauss_newton_solver_qr.cpp:50-150
+  void doIterationQR() {
+    const int n = fn->numParameters;
+    const int ns = int(enabled.size());
+    if (ns == 0) return;
+    fn->updateState(parameters.data()); // initializeJacobianComputation
+    OnlineHouseholderQR<T> qr;
+    qr.reset(ns, std::sqrt(T(opt.regularization))); // "the QR solver wants the square root of that lambda" (:74-76)
+    double errorOrig = 0.0;
+    Mat<T> jac;
+    std::vector<T> res;
+    for (size_t b = 0; b < fn->getJacobianBlockCount(); ++b) {
+      const int bs = fn->getJacobianBlockSize(b);
+      if (bs == 0) continue;
+      const int rows = padToSimdAlignment(bs);
+      jac.resizeAndSetZero(rows, n);
+      res.assign(rows, T(0));
+      int used = 0;
+      errorOrig += fn->computeJacobianBlock(parameters.data(), b, jac, 0, res.data(), used);
+      if (used == 0) continue;
+      std::vector<T> A(size_t(used) * ns); // ColumnIndexedMatrix(jacobian.topRows(used), enabledParameters)
+      for (int a = 0; a < ns; ++a) for (int k = 0; k < used; ++k) A[size_t(a) * used + k] = jac(k, enabled[a]);
+      qr.addMutating(A.data(), used, used, res.data());
+    }
+    error = errorOrig;
+    const std::vector<T> sub = qr.result();
+    std::vector<T> dir(n, T(0));
+    for (int a = 0; a < ns; ++a) dir[enabled[a]] = sub[a];
+    if (!opt.doLineSearch) { fn->updateParameters(parameters, dir); return; }
+    const std::vector<T> atb = qr.AtTimesB();
+    T dotp = 0;
+    for (int a = 0; a < ns; ++a) dotp += atb[a] * sub[a];
+    const double innerProd = -double(dotp);
+    const std::vector<T> orig = parameters;
+    float alpha = 1.0f;
+    for (size_t k = 0; k < 10 && std::fpclassify(alpha) == FP_NORMAL; ++k) { // :124-143
+      parameters = orig;
+      std::vector<T> d(n);
+      for (int q = 0; q < n; ++q) d[q] = alpha * dir[q];
+      fn->updateParameters(parameters, d);
+      const double errorNew = fn->getError(parameters.data());
+      if ((errorOrig - errorNew) >= 1e-4f * alpha * -innerProd) break;
+      alpha *= 0.5f;
+    }
+  }
   void doIteration() { // gauss_newton_solver.cpp:224-280
+    if (opt.qrSolver) { doIterationQR(); return; }
     const int n = fn->numParameters;
     const int ns = int(enabled.size());
     if (opt.useBlockJtJ && !opt.subsetSolver) { // :69-107

@@ -127,7 +127,8 @@ double solveOne(SkeletonSolverFunction<T>& fn, const std::vector<uint8_t>* enabl
   go.regularization = float(o.regularization);
   go.doLineSearch = o.doLineSearch != 0;
   go.useBlockJtJ = o.useBlockJtJ != 0;
-  go.subsetSolver = o.subsetSolver != 0;
+  go.subsetSolver = o.subsetSolver == 1; // 0 GaussNewtonSolverT, 1 SubsetGaussNewtonSolverT, 2 GaussNewtonSolverQRT
+  go.qrSolver = o.subsetSolver == 2;
   GaussNewtonSolver<T> solver(go, &fn);
   if (enabled) solver.setEnabledParameters(*enabled);
   std::vector<T> p = narrow<T>(params, fn.numParameters);
@@ -398,6 +399,28 @@ double orc_solve_batch(void* fn, int64_t minIt, int64_t maxIt, double threshold,
   if (h->dtype == 0) solveBatch<float>(h, o, B, params, targets, nthreads, errors, iters, finalErrors);
   else solveBatch<double>(h, o, B, params, targets, nthreads, errors, iters, finalErrors);
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// OnlineHouseholderQR on its own (known-answer tests of math/online_householder_qr): A row-major [rows x n], added in `numChunks`
+// consecutive row chunks; x = result(), atb = At_times_b().
+void orc_online_qr(int dtype, int rows, int n, double lambda, const double* A, const double* b, int numChunks, const int* chunkRows, double* x, double* atb) {
+  auto run = [&](auto tag) {
+    using T = decltype(tag);
+    OnlineHouseholderQR<T> qr;
+    qr.reset(n, T(lambda));
+    int r0 = 0;
+    for (int c = 0; c < numChunks; ++c) {
+      const int p = chunkRows[c];
+      std::vector<T> Ac(size_t(p) * n), bc(p);
+      for (int k = 0; k < p; ++k) { bc[k] = T(b[r0 + k]); for (int j = 0; j < n; ++j) Ac[size_t(j) * p + k] = T(A[size_t(r0 + k) * n + j]); }
+      qr.addMutating(Ac.data(), p, p, bc.data());
+      r0 += p;
+    }
+    const std::vector<T> xs = qr.result(), g = qr.AtTimesB();
+    for (int j = 0; j < n; ++j) { x[j] = double(xs[j]); atb[j] = double(g[j]); }
+  };
+  if (dtype == 0) run(float(0)); else run(double(0));
+  (void)rows;
 }
 
 // Host threads this process may actually use: the CPU affinity mask, capped by the cgroup CPU quota (cpu.max = "<quota> <period>"),

@@ -92,7 +92,7 @@ def check_solve(ch, efs, theta0, opts: ms.GaussNewtonSolverOptions, lib_path=Non
             orc.set_enabled_parameters(enabled)
         err, p, it, hist = orc.solve(f32(theta0[b]), min_iterations=opts.min_iterations, max_iterations=opts.max_iterations,
                                      threshold=opts.threshold, regularization=opts.regularization, do_line_search=opts.do_line_search,
-                                     use_block_jtj=opts.use_block_jtj, subset_solver=opts.subset_line_search)
+                                     use_block_jtj=opts.use_block_jtj, subset_solver=opts.subset_line_search, qr_solver=getattr(opts, "linear_solver", 0) == 1)
         d = np.max(np.abs(out["params"][b] - p)) / max(1.0, np.max(np.abs(p)))
         worst = max(worst, d)
         tol, etol = param_tol, 1e-3 * abs(err) + 1e-7
@@ -109,7 +109,7 @@ def check_solve(ch, efs, theta0, opts: ms.GaussNewtonSolverOptions, lib_path=Non
                 orc64.set_enabled_parameters(enabled)
             err64, p64, _, _ = orc64.solve(f32(theta0[b]), min_iterations=opts.min_iterations, max_iterations=opts.max_iterations,
                                            threshold=opts.threshold, regularization=opts.regularization, do_line_search=opts.do_line_search,
-                                           use_block_jtj=opts.use_block_jtj, subset_solver=opts.subset_line_search)
+                                           use_block_jtj=opts.use_block_jtj, subset_solver=opts.subset_line_search, qr_solver=getattr(opts, "linear_solver", 0) == 1)
             gap = np.max(np.abs(p - p64)) / max(1.0, np.max(np.abs(p)))
             if strict_double:
                 d = np.max(np.abs(out["params"][b] - p64)) / max(1.0, np.max(np.abs(p64)))

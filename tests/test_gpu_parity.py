@@ -343,6 +343,35 @@ def test_fused_modes_reject_what_they_cannot_run():
     assert solver.get_fused_profile()["fused"] == 2
 
 
+@pytest.mark.parametrize("case", ["chain_all_families", "chain_subset_line_search", "humanoid", "bodyhands_too_wide"])
+def test_gauss_newton_qr_step(case):
+    """GaussNewtonSolverQRT's step (online Householder QR of [sqrt(lambda) I; J], gauss_newton_solver_qr.cpp:50-150) as
+    the device linear solver, against the oracle's restatement of that solver (oracle: KA-9 / KA-10)."""
+    if case == "chain_all_families":
+        ch, efs, theta0, ts = chain_problem(J=6, B=5, seed=81, families=("position", "orientation", "state", "limit", "plane", "halfplane", "model_parameters"))
+        opts = ms.GaussNewtonSolverOptions(min_iterations=6, max_iterations=6, threshold=10.0, regularization=0.05, linear_solver=ms.LINEAR_SOLVER_QR)
+        parity.check_solve(ch, efs, ts + 0.1 * theta0, opts, param_tol=2e-4)
+    elif case == "chain_subset_line_search":
+        ch, efs, theta0, _ = chain_problem(J=6, B=4, seed=82)
+        en = np.ones(ch.num_params, bool); en[[0, 2, 5, 8]] = False
+        opts = ms.GaussNewtonSolverOptions(min_iterations=6, max_iterations=6, threshold=10.0, regularization=0.05, do_line_search=True, subset_line_search=True,
+                                           linear_solver=ms.LINEAR_SOLVER_QR)
+        parity.check_solve(ch, efs, theta0, opts, enabled=en, param_tol=2e-4)
+    elif case == "humanoid":
+        ch, efs, theta0, _ = humanoid_problem(12, orientation=True)
+        opts = ms.GaussNewtonSolverOptions(min_iterations=1, max_iterations=30, threshold=1.0, regularization=0.05, linear_solver=ms.LINEAR_SOLVER_QR)
+        out, worst = parity.check_solve(ch, efs, theta0, opts, strict_double=True, max_calibrated=2)
+        assert np.all(out["status"] == 0)
+        # and the two linear solvers agree with each other (same normal equations)
+        chol = ms.GaussNewtonSolver(ms.GaussNewtonSolverOptions(min_iterations=1, max_iterations=30, threshold=1.0, regularization=0.05), parity.build_function(ch, efs, 12)).solve(theta0)
+        assert np.max(np.abs(chol["params"] - out["params"])) <= 1e-3
+    else:
+        ch, efs, theta0, _ = bodyhands_problem(2)  # n = 424: R alone is 360 KB
+        fn = parity.build_function(ch, efs, 2)
+        with pytest.raises(ms.MomentumB200Error):
+            ms.GaussNewtonSolver(ms.GaussNewtonSolverOptions(max_iterations=2, linear_solver=ms.LINEAR_SOLVER_QR), fn).solve(theta0)
+
+
 def test_full_size_properties_cfg3_shard():
     """BASELINE cfg3 per-GPU shard (8192 x humanoid72, m=126): properties that need no oracle."""
     B = 8192

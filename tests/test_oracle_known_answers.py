@@ -180,3 +180,52 @@ def test_ka6_python_ik_basic(dtype):
     assert len(hist) > 1 and hist[-1] < hist[0]
     err2, p2, it2, hist2 = fn.solve(np.zeros(ch.num_params), min_iterations=1, max_iterations=200, threshold=1.0, regularization=1e-5)
     assert np.array_equal(hist, hist2) and np.array_equal(p, p2)  # "make sure it's deterministic"
+
+
+# ---- KA-9 / KA-10: OnlineHouseholderQR and GaussNewtonSolverQRT -------------------------------------------------
+def test_ka9_online_householder_qr_known_answers():
+    """momentum/test/math/online_qr_test.cpp:70-100 (Basic: the 3x3 system, whole and row by row), :134-169 (WithLambda: the damped
+    least-squares solution and At_times_b), :171-196 (MatrixWithZeros, float) against numpy's least squares."""
+    from oracle.binding import online_qr
+
+    A = np.array([[1.0, 3, 4], [2, 1, 4], [5, 2, 3]]); b = np.array([1.0, 2, 3])
+    x_ref = np.linalg.solve(A, b)
+    for chunks in ([3], [1, 1, 1], [2, 1]):
+        x, _ = online_qr(A, b, 0.0, chunks)
+        assert np.sum((x - x_ref) ** 2) < 1e-10
+    rng = np.random.default_rng(0)
+    A = rng.uniform(-1, 1, (5, 3)); b = rng.uniform(-1, 1, 5)
+    for i in range(5):
+        lam = i / 2.0
+        Aa = np.vstack([A, lam * np.eye(3)]); ba = np.concatenate([b, np.zeros(3)])
+        x_ref = np.linalg.lstsq(Aa, ba, rcond=None)[0]
+        x, atb = online_qr(A, b, lam, [2, 3])
+        assert np.sum((x - x_ref) ** 2) < 1e-10 and np.sum((atb - A.T @ b) ** 2) < 1e-10
+    blocks, rhs = [], []
+    for i in range(5):  # leading columns of later blocks are zero: the beta == 0 skip (online_householder_qr.cpp:202-206)
+        M = rng.normal(size=(i + 3, 3)); M[:, :min(i, 3)] = 0.0
+        blocks.append(M); rhs.append(rng.normal(size=i + 3))
+    A = np.vstack(blocks); b = np.concatenate(rhs)
+    x, _ = online_qr(A, b, 0.0, [m.shape[0] for m in blocks], dtype="float32")
+    assert np.linalg.norm(x - np.linalg.lstsq(A, b, rcond=None)[0]) < 1e-3
+
+
+def test_ka10_gauss_newton_qr_takes_the_same_step_as_the_normal_equations():
+    """GaussNewtonSolverQRT (gauss_newton_solver_qr.cpp:50-150) solves (J^T J + lambda I) delta = J^T r through R^T R = lambda I + J^T J: in
+    double precision its iterates coincide with GaussNewtonSolverT's; with the line search both variants agree too (c1 = 1e-4 on g.delta)."""
+    from momentum_b200.problems import chain_problem
+    from oracle.binding import OracleFunction
+
+    ch, efs, theta0, _ = chain_problem(J=6, B=2, seed=71, families=("position", "orientation", "limit", "plane", "model_parameters"))
+    en = np.ones(ch.num_params, bool); en[[2, 9]] = False
+    for b in range(2):
+        for enabled in (None, en):
+            for ls in (False, True):
+                res = []
+                for kw in (dict(subset_solver=ls), dict(qr_solver=True)):
+                    orc = OracleFunction(ch, efs, "float64", instance=b)
+                    if enabled is not None:
+                        orc.set_enabled_parameters(enabled)
+                    res.append(orc.solve(theta0[b], min_iterations=5, max_iterations=5, threshold=1.0, regularization=0.05, do_line_search=ls, **kw))
+                (e0, p0, _, h0), (e1, p1, _, h1) = res
+                assert np.max(np.abs(p0 - p1)) < 1e-8 and abs(e0 - e1) < 1e-9 * max(1.0, abs(e0)) and np.allclose(h0, h1, rtol=1e-9)
