@@ -247,6 +247,31 @@ std::string buildCholSchedule(int n, const std::vector<std::vector<int>>& clique
     out.levelTaskStart.push_back(int(out.taskDst.size()));
     out.levelVTaskStart.push_back(int(out.vtaskRow.size()));
   }
+  for (int W : {8, 16}) {
+    std::vector<int32_t>& start = W == 8 ? out.levelOrderStart8 : out.levelOrderStart16;
+    std::vector<int32_t>& order = W == 8 ? out.taskOrder8 : out.taskOrder16;
+    start.assign(1, 0);
+    for (int L = 0; L < numLevels; ++L) {
+      std::vector<int> ids;
+      for (int t = out.levelTaskStart[L]; t < out.levelTaskStart[L + 1]; ++t) ids.push_back(t);
+      std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) { return out.taskPairStart[a + 1] - out.taskPairStart[a] > out.taskPairStart[b + 1] - out.taskPairStart[b]; });
+      std::vector<std::vector<int>> ofWarp(W);
+      std::vector<int64_t> load(W, 0);
+      for (int t : ids) {
+        int w = 0;
+        for (int k = 1; k < W; ++k) if (load[k] < load[w]) w = k;
+        ofWarp[w].push_back(t);
+        load[w] += 2 * (out.taskPairStart[t + 1] - out.taskPairStart[t]) + 1; // k-steps + the read-modify-write of the destination
+      }
+      size_t rounds = 0;
+      for (const auto& v : ofWarp) rounds = std::max(rounds, v.size());
+      const size_t base = order.size();
+      order.resize(base + rounds * W, -1);
+      for (int w = 0; w < W; ++w)
+        for (size_t r = 0; r < ofWarp[w].size(); ++r) order[base + r * W + w] = ofWarp[w][r];
+      start.push_back(int32_t(order.size()));
+    }
+  }
   out.colPanelStart.assign(1, 0);
   for (int K = 0; K < T; ++K) {
     for (int I : st[K]) { out.colPanelTile.push_back(tileId[I][K]); out.colPanelRow.push_back(I); }
@@ -407,6 +432,7 @@ void makeScheduleBlob(const CholSchedule& s, std::vector<int32_t>& blob, CholSch
   add32(s.diagTile); add32(s.levelColStart); add32(s.levelCols); add32(s.levelPanelStart); add32(s.panelTile); add32(s.panelDiag);
   add32(s.levelTaskStart); add32(s.taskDst); add32(s.taskPairStart); add32(s.pairA); add32(s.pairB); add32(s.levelVTaskStart); add32(s.vtaskRow);
   add32(s.vtaskSrcStart); add32(s.vsrcTile); add32(s.vsrcCol); add32(s.colPanelStart); add32(s.colPanelTile); add32(s.colPanelRow);
+  add32(s.levelOrderStart8); add32(s.taskOrder8); add32(s.levelOrderStart16); add32(s.taskOrder16);
   {
     std::vector<int32_t> info(size_t(s.numTiles) * 3, 0);
     auto validOf = [&](int K) { int v = 0; while (v < kCholTile && s.perm[16 * K + v] >= 0) ++v; return v; };
@@ -431,7 +457,9 @@ void makeScheduleBlob(const CholSchedule& s, std::vector<int32_t>& blob, CholSch
   dev.panelTile = b + offs[k++]; dev.panelDiag = b + offs[k++]; dev.levelTaskStart = b + offs[k++]; dev.taskDst = b + offs[k++];
   dev.taskPairStart = b + offs[k++]; dev.pairA = b + offs[k++]; dev.pairB = b + offs[k++]; dev.levelVTaskStart = b + offs[k++]; dev.vtaskRow = b + offs[k++];
   dev.vtaskSrcStart = b + offs[k++]; dev.vsrcTile = b + offs[k++]; dev.vsrcCol = b + offs[k++]; dev.colPanelStart = b + offs[k++];
-  dev.colPanelTile = b + offs[k++]; dev.colPanelRow = b + offs[k++]; dev.tileInfo = b + offs[k++];
+  dev.colPanelTile = b + offs[k++]; dev.colPanelRow = b + offs[k++];
+  dev.levelOrderStart8 = b + offs[k++]; dev.taskOrder8 = b + offs[k++]; dev.levelOrderStart16 = b + offs[k++]; dev.taskOrder16 = b + offs[k++];
+  dev.tileInfo = b + offs[k++];
 }
 
 } // namespace mb2

@@ -51,6 +51,10 @@ struct CholSchedDev {
   const int32_t* colPanelStart;
   const int32_t* colPanelTile;
   const int32_t* colPanelRow;
+  const int32_t* levelOrderStart8;  // update-task assignment for 8 warps per instance: [numLevels + 1] into taskOrder8 ([rounds][8], -1 = idle)
+  const int32_t* taskOrder8;
+  const int32_t* levelOrderStart16; // ... for the 16-warp CTA of wide systems
+  const int32_t* taskOrder16;
   const int32_t* tileInfo;    // [numTiles][3] {gi0, gj0, validI | validJ << 8 | diag << 16}, see ik_chol_sched.h
 };
 // view of the same schedule with every table pointer moved to a copy of the blob at `newBlob`
@@ -64,7 +68,7 @@ MB2_HD CholSchedDev rebaseSchedule(const CholSchedDev& S, const int32_t* newBlob
   MB2_RB(perm) MB2_RB(pos) MB2_RB(tileIdTable) MB2_RB(tileRow) MB2_RB(tileCol) MB2_RB(diagTile) MB2_RB(levelColStart) MB2_RB(levelCols)
   MB2_RB(levelPanelStart) MB2_RB(panelTile) MB2_RB(panelDiag) MB2_RB(levelTaskStart) MB2_RB(taskDst) MB2_RB(taskPairStart) MB2_RB(pairA) MB2_RB(pairB)
   MB2_RB(levelVTaskStart) MB2_RB(vtaskRow) MB2_RB(vtaskSrcStart) MB2_RB(vsrcTile) MB2_RB(vsrcCol) MB2_RB(colPanelStart) MB2_RB(colPanelTile)
-  MB2_RB(colPanelRow) MB2_RB(tileInfo)
+  MB2_RB(colPanelRow) MB2_RB(levelOrderStart8) MB2_RB(taskOrder8) MB2_RB(levelOrderStart16) MB2_RB(taskOrder16) MB2_RB(tileInfo)
 #undef MB2_RB
   return R;
 }

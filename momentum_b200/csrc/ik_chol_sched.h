@@ -36,6 +36,9 @@ struct CholSchedule {
   std::vector<int32_t> levelColStart, levelCols;       // tile columns K of each level
   std::vector<int32_t> levelPanelStart, panelTile, panelDiag, panelRow; // panel tiles (I,K) of the level's columns; diag tile of K; block row I
   std::vector<int32_t> levelTaskStart, taskDst, taskPairStart, pairA, pairB; // matrix update tasks
+  // which warp runs which update task: per level a [rounds][W] table (W = 8 or 16 warps per instance), -1 = idle; longest task first to
+  // the least loaded warp (the root tile of a humanoid collects 12 pairs, the median task 4: dealing tasks round-robin made one warp do 17)
+  std::vector<int32_t> levelOrderStart8, taskOrder8, levelOrderStart16, taskOrder16;
   std::vector<int32_t> levelVTaskStart, vtaskRow, vtaskSrcStart, vsrcTile, vsrcCol; // forward-substitution updates y_I -= L(I,K) y_K
   // per tile column (backward substitution): its panel tiles
   std::vector<int32_t> colPanelStart, colPanelTile, colPanelRow;

@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(kFusedGroupThreads* kGroups, 1) fusedSolveKern
         }
         groupSync();
         MB2_PH(kPhPanel)
-        for (int ti = S.levelTaskStart[Lv] + warp; ti < S.levelTaskStart[Lv + 1]; ti += kFusedGroupThreads / 32) cholUpdateTask(tiles, S, ti, lane);
+        for (int oi = S.levelOrderStart8[Lv] + warp; oi < S.levelOrderStart8[Lv + 1]; oi += kFusedGroupThreads / 32) { const int ti = S.taskOrder8[oi]; if (ti >= 0) cholUpdateTask(tiles, S, ti, lane); }
         for (int vi = S.levelVTaskStart[Lv] + hw; vi < S.levelVTaskStart[Lv + 1]; vi += kFusedGroupThreads / 16) cholVectorTask(tiles, y, S, vi, hl);
         groupSync();
         MB2_PH(kPhUpdate)

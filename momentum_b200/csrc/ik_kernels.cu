@@ -606,7 +606,10 @@ __global__ void __launch_bounds__(kSchedThreads, kSchedThreads == 256 ? 3 : 1) c
     __syncthreads();
     MB2_PROF(2)
     // C: update tasks (warp each) and rhs updates (half-warp each)
-    for (int ti = S.levelTaskStart[L] + warp; ti < S.levelTaskStart[L + 1]; ti += kSchedThreads / 32) cholUpdateTask(tiles, S, ti, lane);
+    {
+      const int32_t* oStart = kSchedThreads == 256 ? S.levelOrderStart8 : S.levelOrderStart16, *order = kSchedThreads == 256 ? S.taskOrder8 : S.taskOrder16;
+      for (int oi = oStart[L] + warp; oi < oStart[L + 1]; oi += kSchedThreads / 32) { const int ti = order[oi]; if (ti >= 0) cholUpdateTask(tiles, S, ti, lane); }
+    }
     for (int vi = S.levelVTaskStart[L] + hw; vi < S.levelVTaskStart[L + 1]; vi += kSchedThreads / 16) cholVectorTask(tiles, y, S, vi, hl);
     __syncthreads();
     MB2_PROF(3)
@@ -773,7 +776,7 @@ __global__ void __launch_bounds__(kGramThreads, 3) gramCholeskyKernel(const Gram
     }
     __syncthreads();
     MB2_GC(4)
-    for (int ti = S.levelTaskStart[L] + warp; ti < S.levelTaskStart[L + 1]; ti += kGramThreads / 32) cholUpdateTask(tiles, S, ti, lane);
+    for (int oi = S.levelOrderStart8[L] + warp; oi < S.levelOrderStart8[L + 1]; oi += kGramThreads / 32) { const int ti = S.taskOrder8[oi]; if (ti >= 0) cholUpdateTask(tiles, S, ti, lane); }
     for (int vi = S.levelVTaskStart[L] + hw; vi < S.levelVTaskStart[L + 1]; vi += kGramThreads / 16) cholVectorTask(tiles, y, S, vi, hl);
     __syncthreads();
     MB2_GC(5)

@@ -791,3 +791,23 @@ extern "C" int emu_table_sizes(mb2_solver_function* f, int64_t out[12]) {
   out[11] = maxContrib;
   return MB2_OK;
 }
+
+// per-level update-task pair counts of the solver plan's schedule (balance analysis)
+extern "C" int emu_task_loads(mb2_solver_function* f) {
+  std::string e = plan(f, true);
+  if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
+  CholSchedule s;
+  std::vector<std::vector<int>> cliques(f->plan.units.size());
+  for (const CellDesc& c : f->plan.cells) cliques[c.unit].push_back(int(c.col));
+  const std::vector<int> prio = columnDepthPriority(f->ch->host, f->plan.enabledList);
+  e = buildCholSchedule(f->plan.numCols, cliques, false, s, &prio);
+  if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
+  for (int L = 0; L < s.numLevels; ++L) {
+    std::printf("level %d: diag %d panels %d tasks:", L, s.levelColStart[L + 1] - s.levelColStart[L], s.levelPanelStart[L + 1] - s.levelPanelStart[L]);
+    for (int t = s.levelTaskStart[L]; t < s.levelTaskStart[L + 1]; ++t) std::printf(" %d", s.taskPairStart[t + 1] - s.taskPairStart[t]);
+    std::printf(" | vtasks:");
+    for (int t = s.levelVTaskStart[L]; t < s.levelVTaskStart[L + 1]; ++t) std::printf(" %d", s.vtaskSrcStart[t + 1] - s.vtaskSrcStart[t]);
+    std::printf("\n");
+  }
+  return MB2_OK;
+}

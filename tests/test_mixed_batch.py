@@ -62,7 +62,10 @@ def test_mixed_batch_matches_the_oracle_instance_by_instance():
         err, p, it, _ = OracleFunction(ch, [ef], "float32").solve(x["theta0"].astype(np.float64), min_iterations=8, max_iterations=8, threshold=1.0, regularization=0.05)
         d = np.max(np.abs(out["params"][i] - p)) / max(1.0, np.max(np.abs(p)))
         worst = max(worst, d)
-        assert d <= (5e-4 if x["rig"] == "chain22" else 2e-4), (i, x["rig"], len(x["parents"]), d)  # 22-joint chains amplify rounding (like the other chain tests)
+        if d > 2e-4:  # the second look of tests/parity.py: a 22-joint chain amplifies float rounding; judge against the oracle's own float-vs-double gap
+            _, p64, _, _ = OracleFunction(ch, [ef], "float64").solve(x["theta0"].astype(np.float64), min_iterations=8, max_iterations=8, threshold=1.0, regularization=0.05)
+            gap = np.max(np.abs(p - p64)) / max(1.0, np.max(np.abs(p)))
+            assert x["rig"] == "chain22" and d <= 3.0 * gap, (i, x["rig"], len(x["parents"]), d, gap)
         assert abs(out["errors"][i] - err) <= (3e-2 if x["rig"] == "chain22" else 1e-3) * abs(err) + 1e-7
     print("mixed batch: buckets", st["buckets"], "padding waste %.1f %%" % (100 * st["padding_waste"]), "worst rel param diff", worst)
     # a second solve from the solutions: bucket handles and plans are reused, nothing gets worse
@@ -79,11 +82,11 @@ def test_instanced_position_offsets_single_bucket():
     from oracle.binding import OracleFunction
     from tests import parity
 
-    ch, efs, theta0, theta_star = humanoid_problem(6, orientation=False, legacy_weights=False)
+    ch, efs, theta0, theta_star = humanoid_problem(6, orientation=False)
     rng = np.random.default_rng(3)
     e = efs[0]
     off = np.asarray(e.offsets)[None] + rng.uniform(-1, 1, (6, len(e.parents), 3))
     tg = np.stack([mc.world_points(ch, theta_star[b:b + 1], e.parents, off[b])[0] for b in range(6)])
-    ef = mc.PositionErrorFunction(e.parents, e.offsets, e.weights, tg, weight=1.0, instance_offsets=off)
+    ef = mc.PositionErrorFunction(e.parents, e.offsets, e.weights, tg, weight=e.weight, instance_offsets=off)
     opts = ms.GaussNewtonSolverOptions(min_iterations=6, max_iterations=6, regularization=0.05)
     parity.check_solve(ch, [ef], theta0, opts, param_tol=2e-4)
