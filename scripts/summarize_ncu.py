@@ -107,7 +107,8 @@ def main():
         launches_summary(lp, lines)
         lines.append("")
     traffic = {}
-    for key, name in (("k1", "fk_residual_jacobian"), ("k2", "jtj_jtr"), ("k3", "cholesky_update")):
+    # r02 default path: k1 = sweepKernel, k2 = gramCholeskyKernel; the other captures (three-kernel path, persistent kernel) are for comparison
+    for key, name in (("k1", "fk_residual_jacobian"), ("k2", "gram_cholesky"), ("gram", "jtj_jtr"), ("chol", "cholesky_update"), ("persistent", "persistent_solve"), ("k3", "cholesky_update")):
         rep = os.path.join(g, f"{tag}_{key}.ncu-rep")
         if os.path.exists(rep):
             lines.append(f"== {key} ({name}) -- ncu --set full --clock-control none, one launch")

@@ -184,6 +184,22 @@ def test_ka4_three_joint_ik_with_cholesky_breakdown():
     assert np.all(out["errors"] <= 5e-7)
 
 
+@pytest.mark.parametrize("mode", [ms.CHOLESKY_DENSE_EIGEN, ms.CHOLESKY_TILES_SPARSE])
+def test_cholesky_breakdown_is_flagged_on_every_path(mode):
+    """A pivot that is exactly zero (no damping, a parameter no constraint depends on). Eigen::LLT returns early and the reference ignores
+    info() (gauss_newton_solver.cpp:251); the dense Eigen-structured kernel reproduces that and flags the instance; the tile schedule (the
+    default from 48 unknowns) substitutes the damping for the pivot - zero here, so the step is not finite, the NaN guard of the batched
+    caller (tensor_ik.cpp:168-173) restores the initial parameters. Either way the caller sees a non-zero status, never a silent wrong step."""
+    ch, efs, theta0, _ = humanoid_problem(3, orientation=False)
+    opts = ms.GaussNewtonSolverOptions(min_iterations=1, max_iterations=2, regularization=0.0, cholesky_mode=mode, fused_mode=ms.FUSED_OFF)
+    out = ms.GaussNewtonSolver(opts, parity.build_function(ch, efs, 3)).solve(theta0)
+    assert np.all(out["status"] != ms.INSTANCE_OK)
+    if mode == ms.CHOLESKY_TILES_SPARSE:
+        assert np.all(out["status"] == ms.INSTANCE_NON_FINITE) and np.array_equal(out["params"], theta0.astype(np.float32))
+    else:
+        assert np.all(out["status"] == ms.INSTANCE_CHOLESKY_BREAKDOWN)
+
+
 def test_ka6_python_ik_basic_is_reached_and_deterministic():
     """pymomentum/test/test_solver2.py:135-199 on the CUDA path: joint positions reach the targets within 1e-4 and a second solve
     reproduces the error history and the parameters bit for bit (no atomics / no order-dependent sums on the data path)."""
