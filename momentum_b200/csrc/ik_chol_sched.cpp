@@ -3,6 +3,8 @@
 #include "ik_chol_sched.cuh"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <set>
 #include <tuple>
@@ -279,6 +281,17 @@ std::string buildCholSchedule(int n, const std::vector<std::vector<int>>& clique
   }
   for (int K = 0; K < T; ++K) { const int64_t r = T - 1 - K; out.denseTileOps += r * (r + 1) / 2; }
   out.order = order;
+  if (getenv("MB2_SCHED_DUMP") != nullptr) { // planner diagnostics (host only): the shape of every level
+    fprintf(stderr, "chol schedule: n %d nPad %d tile columns %d tiles %d levels %d tile ops %lld (dense %lld)\n", n, out.nPad, T, out.numTiles, numLevels, (long long)out.tileOps, (long long)out.denseTileOps);
+    for (int L = 0; L < numLevels; ++L) {
+      int maxPairs = 0, pairs = 0;
+      for (int t = out.levelTaskStart[L]; t < out.levelTaskStart[L + 1]; ++t) { const int p = out.taskPairStart[t + 1] - out.taskPairStart[t]; pairs += p; maxPairs = std::max(maxPairs, p); }
+      fprintf(stderr, "  level %d: %d diagonal tiles, %d panel tiles, %d update tasks (%d pairs, longest %d), %d vector tasks; columns:", L, out.levelColStart[L + 1] - out.levelColStart[L],
+              out.levelPanelStart[L + 1] - out.levelPanelStart[L], out.levelTaskStart[L + 1] - out.levelTaskStart[L], pairs, maxPairs, out.levelVTaskStart[L + 1] - out.levelVTaskStart[L]);
+      for (int ci = out.levelColStart[L]; ci < out.levelColStart[L + 1]; ++ci) fprintf(stderr, " %d(%d)", out.levelCols[ci], int(st[out.levelCols[ci]].size()));
+      fprintf(stderr, "\n");
+    }
+  }
   return "";
 }
 
