@@ -228,9 +228,7 @@ std::string buildCholSchedule(int n, const std::vector<std::vector<int>>& clique
       for (size_t a = 0; a < st[K].size(); ++a)
         for (size_t b = 0; b <= a; ++b) {
           const int I = st[K][a], J = st[K][b];
-          // off-diagonal destinations are stored transposed: compute dst^T = L(J,K) L(I,K)^T instead
-          if (I == J) tasks[tileId[I][J]].push_back({tileId[I][K], tileId[J][K]});
-          else tasks[tileId[I][J]].push_back({tileId[J][K], tileId[I][K]});
+          tasks[tileId[I][J]].push_back({tileId[I][K], tileId[J][K]}); // D(I,J)(r, c) -= sum_k L(I,K)(r, k) L(J,K)(c, k)
           out.tileOps++;
         }
     }

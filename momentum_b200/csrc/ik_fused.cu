@@ -98,8 +98,6 @@ __global__ void __launch_bounds__(kFusedGroupThreads* kGroups, 1) fusedSolveKern
   auto groupSync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(kFusedGroupThreads) : "memory"); };
   const int numJointParams = T.numJoints * kParametersPerJoint;
   const uint32_t tmemWarp = tmemBase + (uint32_t(((tid >> 5) & 3) * 32) << 16) + uint32_t((tid >> 7) * a.tmemColsPerWarp); // lane quarter, column slot
-  int laneOff[8];
-  gramLaneOffsets(lane, laneOff);
 
   unsigned long long pc[kPhases];
   long long pt = 0;
@@ -179,7 +177,7 @@ __global__ void __launch_bounds__(kFusedGroupThreads* kGroups, 1) fusedSolveKern
           if (t < 0) continue;
           float acc[2][4];
           tmemFetch8(tmemWarp + 8u * slot, &acc[0][0]);
-          gramTileStore(tiles + size_t(t) * 256, acc, tileInfo[t], a.regularization, lane, laneOff);
+          gramTileStore(tiles + size_t(t) * 256, acc, tileInfo[t], a.regularization, lane);
         }
         for (int s = gt; s < S.nPad; s += kFusedGroupThreads) {
           const int p = S.perm[s];
@@ -190,9 +188,9 @@ __global__ void __launch_bounds__(kFusedGroupThreads* kGroups, 1) fusedSolveKern
       MB2_PH(kPhRestore)
       // ---- level-scheduled Cholesky (ik_chol_sched.h) ----
       for (int Lv = 0; Lv < S.numLevels; ++Lv) {
-        for (int ci = S.levelColStart[Lv] + hw; ci < S.levelColStart[Lv + 1]; ci += kFusedGroupThreads / 16) {
+        for (int ci = S.levelColStart[Lv] + warp; ci < S.levelColStart[Lv + 1]; ci += kFusedGroupThreads / 32) {
           const int K = S.levelCols[ci];
-          cholDiagTile(tiles + size_t(S.diagTile[K]) * 256, y + 16 * K, hl, hmask, a.regularization, flags);
+          cholDiagTile(tiles + size_t(S.diagTile[K]) * 256, y + 16 * K, lane, a.regularization, flags);
         }
         groupSync();
         MB2_PH(kPhDiag)
@@ -200,7 +198,6 @@ __global__ void __launch_bounds__(kFusedGroupThreads* kGroups, 1) fusedSolveKern
           float* ptile = tiles + size_t(S.panelTile[pi]) * 256;
           float x[2][4];
           cholPanelProduct(ptile, tiles + size_t(S.panelDiag[pi]) * 256, lane, x);
-          __syncwarp();
           cholPanelStore(ptile, lane, x);
         }
         groupSync();

@@ -278,13 +278,14 @@ cudaError_t launchJtJSimt(const JtJArgs& a, cudaStream_t stream) {
 // Common tail of both Cholesky kernels: delta, parameter update (skeleton_solver_function.cpp:153-159),
 // g.delta for the subset line search, status and the SolverT bookkeeping (solver.cpp:92-122).
 // dsub / gsub are indexed by subset position. Every thread of the CTA must call it.
-__device__ void cholFinish(const CholArgs& a, int b, int n, const float* dsub, const float* gsub, bool failed) {
+// dsub: the step per device column, or (slotOf != nullptr) per elimination slot with slotOf[i] = slot of device column i
+__device__ void cholFinish(const CholArgs& a, int b, int n, const float* dsub, const float* gsub, bool failed, const int32_t* slotOf = nullptr) {
   const int tid = threadIdx.x;
   float* theta = a.theta + size_t(b) * a.ldTheta;
   float part = 0.f;
   for (int i = tid; i < n; i += blockDim.x) {
     const int c = a.cols[i];
-    const float d = c >= 0 ? dsub[i] : 0.f; // c < 0: all-zero alignment column of the scheduled layout (ik_chol_sched.h)
+    const float d = c >= 0 ? dsub[slotOf != nullptr ? slotOf[i] : i] : 0.f; // c < 0: all-zero alignment column of the scheduled layout (ik_chol_sched.h)
     a.delta[size_t(b) * n + i] = d;
     if (c >= 0) part += gsub[i] * d;
     if (a.applyUpdate && c >= 0) theta[c] -= d;
@@ -468,8 +469,6 @@ __global__ void __launch_bounds__(kGramThreads) gramTilesKernel(const GramArgs a
   const int32_t* tileOrder = tab + a.offTileOrder, *tileQuadStart = tab + a.offTilePairStart, *quads = tab + a.offPairA; // (blob tables are 16-byte aligned)
   const int32_t* colStripStart = tab + a.offColStripStart, *colStrip = tab + a.offColStrip, *stripRow = tab + a.offStripRow, *tileInfo = tab + a.offTileInfo;
   float* out = a.out + size_t(b) * a.outStride;
-  int laneOff[8];
-  gramLaneOffsets(lane, laneOff);
   for (int ti = warp; ti < a.numOrder; ti += kGramThreads / 32) {
     const int t = tileOrder[ti];
     if (t < 0) continue;
@@ -479,7 +478,7 @@ __global__ void __launch_bounds__(kGramThreads) gramTilesKernel(const GramArgs a
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     gramTileAccumulate(strips, quads, tileQuadStart[t], tileQuadStart[t + 1], lane, acc);
-    gramTileStore(out + size_t(t) * 256, acc, tileInfo[t], a.regularization, lane, laneOff);
+    gramTileStore(out + size_t(t) * 256, acc, tileInfo[t], a.regularization, lane);
   }
   float* y = out + size_t(a.numTiles) * 256;
   for (int K = hw; K < a.numTileCols; K += kGramThreads / 16)
@@ -529,7 +528,7 @@ __global__ void __launch_bounds__(kSchedThreads, kSchedThreads == 256 ? 3 : 1) c
 #define MB2_PROF(k) if constexpr (kProfile) { const long long now = clock64(); pc[k] += now - pt; pt = now; }
   // Prologue: everything this instance reads arrives asynchronously on one mbarrier -- the schedule tables and J^T r as 1-D
   // bulk copies, every stored tile as one TMA box (16 rows x 64 bytes of the row-major upper triangle of H, written
-  // straight into the swizzled tile layout: SWIZZLE_64B is the XOR of tileIdx). No thread touches the data on the way in.
+  // as swizzled 64-byte rows: SWIZZLE_64B, see tmaBoxIdx; cholConvertBox then rewrites each box in the fragment layout).
   const uint32_t barAddr = smemAddr(bar);
   const uint32_t blobBytes = uint32_t((Sg.blobInts + 3) & ~3) * 4u, gBytes = uint32_t(a.ldG) * 4u;
   const bool fromGram = a.tilesIn != nullptr; // tiles (+ lambda, identity extension) and the slot-ordered J^T r come ready-made from the Gram kernel
@@ -569,11 +568,8 @@ __global__ void __launch_bounds__(kSchedThreads, kSchedThreads == 256 ? 3 : 1) c
       if (p >= 0) gsub[p] = y[s];
     }
   } else {
-    // padding pass (cholPadGroup): one work item = (tile, storage row, float4 group)
-    for (int idx = tid; idx < S.numTiles * 64; idx += kSchedThreads) {
-      const int t = idx >> 6, e = idx & 63;
-      cholPadGroup(tiles + size_t(t) * 256, S.tileInfo[3 * t + 2], e >> 2, e & 3);
-    }
+    // the boxes landed as swizzled 64-byte rows: a warp per tile turns them into the fragment layout (identity extension on padding)
+    for (int t = warp; t < S.numTiles; t += kSchedThreads / 32) cholConvertBox(tiles + size_t(t) * 256, S.tileInfo[3 * t + 2], lane);
     for (int s = tid; s < S.nPad; s += kSchedThreads) {
       const int p = S.perm[s];
       y[s] = p >= 0 ? gsub[p] : 0.f;
@@ -588,10 +584,10 @@ __global__ void __launch_bounds__(kSchedThreads, kSchedThreads == 256 ? 3 : 1) c
   MB2_PROF(0)
 
   for (int L = 0; L < S.numLevels; ++L) {
-    // A: diagonal tiles of this level (one half-warp each) + forward solve of their rhs block
-    for (int ci = S.levelColStart[L] + hw; ci < S.levelColStart[L + 1]; ci += kSchedThreads / 16) {
+    // A: diagonal tiles of this level (one warp each) + forward solve of their rhs block
+    for (int ci = S.levelColStart[L] + warp; ci < S.levelColStart[L + 1]; ci += kSchedThreads / 32) {
       const int K = S.levelCols[ci];
-      cholDiagTile(tiles + size_t(S.diagTile[K]) * 256, y + 16 * K, hl, hmask, a.regularization, flags);
+      cholDiagTile(tiles + size_t(S.diagTile[K]) * 256, y + 16 * K, lane, a.regularization, flags);
     }
     __syncthreads();
     MB2_PROF(1)
@@ -600,7 +596,6 @@ __global__ void __launch_bounds__(kSchedThreads, kSchedThreads == 256 ? 3 : 1) c
       float* ptile = tiles + size_t(S.panelTile[pi]) * 256;
       float x[2][4];
       cholPanelProduct(ptile, tiles + size_t(S.panelDiag[pi]) * 256, lane, x);
-      __syncwarp();
       cholPanelStore(ptile, lane, x);
     }
     __syncthreads();
@@ -666,12 +661,17 @@ cudaError_t launchCholeskyScheduled(const CholArgs& a, const CholSchedDev& sched
 // The stored tiles (0.45 GB per iteration on the cfg3 shard) never exist in HBM and the second launch is gone.
 // ------------------------------------------------------------------------------------------------
 size_t gramCholeskySmemBytes(size_t stripStride, int gramBlobInts, int n, int nPad, int numTiles, int schedBlobInts) {
+  (void)gramBlobInts; (void)schedBlobInts; // the plan tables stay in global memory (L1): see the kernel
   const size_t uni = std::max<size_t>(size_t(numTiles) * 256, stripStride + 64);
-  return 128 + sizeof(float) * (((uni + 3) & ~size_t(3)) + size_t(nPad) + 2 * size_t((n + 3) & ~3)) + sizeof(int32_t) * (size_t((gramBlobInts + 3) & ~3) + size_t((schedBlobInts + 3) & ~3)) + 64;
+  return 128 + sizeof(float) * (((uni + 3) & ~size_t(3)) + size_t(nPad) + size_t((n + 3) & ~3)) + 32;
 }
 
+// Shared memory holds only what is per instance: the strip / tile union, the right-hand side in slot order and J^T r per device column
+// (cfg3: 56.4 KB), so that FOUR CTAs fit on an SM (57 KB each, 64 registers per thread); the Gram plan and the Cholesky schedule
+// (10 KB, identical for every CTA) are read from global memory through L1 by the same device functions. The per-instance critical
+// path is a chain of dependent phases no wider than a few warps: instances in flight per SM are what buys throughput.
 template <bool kProfile>
-__global__ void __launch_bounds__(kGramThreads, 3) gramCholeskyKernel(const GramCholArgs a, const CholSchedDev Sg, const int tmemColumns) {
+__global__ void __launch_bounds__(kGramThreads, 4) gramCholeskyKernel(const GramCholArgs a, const CholSchedDev S, const int tmemColumns) {
   extern __shared__ __align__(16) float gcSmem[];
   const GramArgs& g = a.g;
   const CholArgs& c = a.c;
@@ -681,33 +681,28 @@ __global__ void __launch_bounds__(kGramThreads, 3) gramCholeskyKernel(const Gram
   const int warp = tid >> 5, lane = tid & 31, hw = tid >> 4, hl = tid & 15;
   const unsigned hmask = 0xFFFFu << (16 * ((tid >> 4) & 1));
   float* U = gcSmem + (((128u - (smemAddr(gcSmem) & 127u)) & 127u) >> 2); // strips | residual | zero strip, later the tiles
-  const size_t tileFloats = size_t(Sg.numTiles) * 256, sweepFloats = g.stripStride + 64;
+  const size_t tileFloats = size_t(S.numTiles) * 256, sweepFloats = g.stripStride + 64;
   const size_t uni = ((tileFloats > sweepFloats ? tileFloats : sweepFloats) + 3) & ~size_t(3);
   float* strips = U;
   float* resid = U + g.residOff;
   float* tiles = U;
   float* y = U + uni;
-  float* gsub = y + Sg.nPad;
-  float* dsub = gsub + ((n + 3) & ~3);
-  int32_t* gtab = reinterpret_cast<int32_t*>(dsub + ((n + 3) & ~3));
-  int32_t* stab = gtab + ((g.blobInts + 3) & ~3);
-  int* flags = reinterpret_cast<int*>(stab + ((Sg.blobInts + 3) & ~3));
+  float* gsub = y + S.nPad;
+  int* flags = reinterpret_cast<int*>(gsub + ((n + 3) & ~3));
   uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(flags + 2);
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(flags + 4);
   long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt = 0;
   if constexpr (kProfile) pt = clock64();
 #define MB2_GC(k) if constexpr (kProfile) { const long long now = clock64(); pc[k] += now - pt; pt = now; }
   const uint32_t barAddr = smemAddr(bar);
-  const uint32_t stripBytes = uint32_t(g.stripStride) * 4u, gBytes = uint32_t((g.blobInts + 3) & ~3) * 4u, sBytes = uint32_t((Sg.blobInts + 3) & ~3) * 4u;
+  const uint32_t stripBytes = uint32_t(g.stripStride) * 4u;
   if (tid == 0) {
     flags[0] = 0;
     mbarInit(barAddr, 1);
     fenceBarrierInit();
-    mbarExpectTx(barAddr, stripBytes + gBytes + sBytes);
+    mbarExpectTx(barAddr, stripBytes);
     const char* src = reinterpret_cast<const char*>(g.strips + size_t(b) * g.stripStride);
     for (uint32_t off = 0; off < stripBytes; off += 16384u) bulkLoad(smemAddr(strips) + off, src + off, stripBytes - off < 16384u ? stripBytes - off : 16384u, barAddr);
-    bulkLoad(smemAddr(gtab), g.blob, gBytes, barAddr);
-    bulkLoad(smemAddr(stab), Sg.blob, sBytes, barAddr);
   }
   if (warp == 1) tmemAlloc(smemAddr(tmemSlot), uint32_t(tmemColumns));
   if (tid >= 64 && tid < 128) strips[g.stripStride + (tid - 64)] = 0.f; // the all-zero strip that pads odd pair lists
@@ -718,11 +713,9 @@ __global__ void __launch_bounds__(kGramThreads, 3) gramCholeskyKernel(const Gram
   const uint32_t tmemWarp = tmemBase + (uint32_t((warp & 3) * 32) << 16) + uint32_t((warp >> 2) * (tmemColumns / 2)); // lane quarter; two warps share one
   mbarWaitRelaxed(barAddr, 0);
   MB2_GC(0)
+  const int32_t* __restrict__ gtab = g.blob;
   const int32_t* tileOrder = gtab + g.offTileOrder, *tileQuadStart = gtab + g.offTilePairStart, *quads = gtab + g.offPairA;
   const int32_t* colStripStart = gtab + g.offColStripStart, *colStrip = gtab + g.offColStrip, *stripRow = gtab + g.offStripRow, *tileInfo = gtab + g.offTileInfo;
-  const CholSchedDev S = rebaseSchedule(Sg, stab);
-  int laneOff[8];
-  gramLaneOffsets(lane, laneOff);
   // ---- Gram ----
   {
     int slot = 0;
@@ -750,7 +743,7 @@ __global__ void __launch_bounds__(kGramThreads, 3) gramCholeskyKernel(const Gram
       if (t < 0) continue;
       float acc[2][4];
       tmemFetch8(tmemWarp + 8u * slot, &acc[0][0]);
-      gramTileStore(tiles + size_t(t) * 256, acc, tileInfo[t], g.regularization, lane, laneOff);
+      gramTileStore(tiles + size_t(t) * 256, acc, tileInfo[t], g.regularization, lane);
     }
     for (int s2 = tid; s2 < S.nPad; s2 += kGramThreads) {
       const int p = S.perm[s2];
@@ -761,9 +754,9 @@ __global__ void __launch_bounds__(kGramThreads, 3) gramCholeskyKernel(const Gram
   MB2_GC(2)
   // ---- level-scheduled Cholesky (same phases as choleskyScheduledKernel) ----
   for (int L = 0; L < S.numLevels; ++L) {
-    for (int ci = S.levelColStart[L] + hw; ci < S.levelColStart[L + 1]; ci += kGramThreads / 16) {
+    for (int ci = S.levelColStart[L] + warp; ci < S.levelColStart[L + 1]; ci += kGramThreads / 32) {
       const int K = S.levelCols[ci];
-      cholDiagTile(tiles + size_t(S.diagTile[K]) * 256, y + 16 * K, hl, hmask, c.regularization, flags);
+      cholDiagTile(tiles + size_t(S.diagTile[K]) * 256, y + 16 * K, lane, c.regularization, flags);
     }
     __syncthreads();
     MB2_GC(3)
@@ -771,7 +764,6 @@ __global__ void __launch_bounds__(kGramThreads, 3) gramCholeskyKernel(const Gram
       float* ptile = tiles + size_t(S.panelTile[pi]) * 256;
       float x[2][4];
       cholPanelProduct(ptile, tiles + size_t(S.panelDiag[pi]) * 256, lane, x);
-      __syncwarp();
       cholPanelStore(ptile, lane, x);
     }
     __syncthreads();
@@ -786,9 +778,7 @@ __global__ void __launch_bounds__(kGramThreads, 3) gramCholeskyKernel(const Gram
     __syncthreads();
   }
   MB2_GC(6)
-  for (int i = tid; i < S.nPad; i += kGramThreads) { const int p = S.perm[i]; if (p >= 0) dsub[p] = y[i]; }
-  __syncthreads();
-  cholFinish(c, b, n, dsub, gsub, flags[0] != 0);
+  cholFinish(c, b, n, y, gsub, flags[0] != 0, S.pos); // y holds the step per elimination slot
   MB2_GC(7)
   if constexpr (kProfile) {
     if (b == 0 && tid == 0 && a.phaseCycles != nullptr)
@@ -804,13 +794,16 @@ cudaError_t launchGramCholesky(const GramCholArgs& a, const CholSchedDev& sched,
   const size_t smem = gramCholeskySmemBytes(a.g.stripStride, a.g.blobInts, a.c.ns, sched.nPad, sched.numTiles, sched.blobInts);
   if (smem > size_t(g_maxSmemOptin) || (a.g.stripStride & 3) != 0) return cudaErrorInvalidConfiguration;
   // TMEM: two warps share a lane quarter, each parks up to `rounds` tiles of 8 columns; allocations are powers of two >= 32,
-  // and the (up to three) CTAs of an SM must fit in its 512 columns together
+  // and the (up to four) CTAs of an SM must fit in its 512 columns together
   const int rounds = std::max(a.g.numOrder / (kGramThreads / 32), 1);
   int columns = 32;
   while (columns < 2 * 8 * rounds) columns <<= 1;
   if (columns > 128) return cudaErrorInvalidConfiguration;
   cudaError_t e = profile ? cudaFuncSetAttribute(gramCholeskyKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))
                           : cudaFuncSetAttribute(gramCholeskyKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (e != cudaSuccess) return e;
+  e = profile ? cudaFuncSetAttribute(gramCholeskyKernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, int(cudaSharedmemCarveoutMaxShared))
+              : cudaFuncSetAttribute(gramCholeskyKernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, int(cudaSharedmemCarveoutMaxShared));
   if (e != cudaSuccess) return e;
   if (profile) gramCholeskyKernel<true><<<a.c.batch, kGramThreads, smem, stream>>>(a, sched, columns);
   else gramCholeskyKernel<false><<<a.c.batch, kGramThreads, smem, stream>>>(a, sched, columns);

@@ -212,9 +212,7 @@ static void gramOne(const mb2_solver_function* f, int b, const GramPlan& G, cons
     for (int lane = 0; lane < 32; ++lane) {
       float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
       gramTileAccumulate(strips, G.quad.data(), G.tileQuadStart[t], G.tileQuadStart[t + 1], lane, acc);
-      int off[8];
-      gramLaneOffsets(lane, off);
-      gramTileStore(tile, acc, S.tileInfo[3 * t + 2], reg, lane, off);
+      gramTileStore(tile, acc, S.tileInfo[3 * t + 2], reg, lane);
     }
   }
   float* y = out + size_t(G.numTiles) * 256;
@@ -238,10 +236,10 @@ static int cholScheduledOne(const CholSchedDev& S, const float* Hs, int ldH, int
   } else {
   for (int t = 0; t < S.numTiles; ++t) { // the TMA box: 16 rows x 16 columns of H starting at (gj0, gi0), zero outside [ns+1] x [ldH]
     const int gi0 = S.tileInfo[3 * t], gj0 = S.tileInfo[3 * t + 1];
+    auto boxAt = [&](int row, int col) { return (gj0 + row <= n && gi0 + col < ldH) ? Hs[size_t(gj0 + row) * ldH + gi0 + col] : 0.f; };
     for (int c = 0; c < 16; ++c)
       for (int r = 0; r < 16; ++r)
-        tl[size_t(t) * 256 + tileIdx(c, r)] = (gj0 + c <= n && gi0 + r < ldH) ? Hs[size_t(gj0 + c) * ldH + gi0 + r] : 0.f;
-    for (int e = 0; e < 64; ++e) cholPadGroup(tl + size_t(t) * 256, S.tileInfo[3 * t + 2], e >> 2, e & 3);
+        tl[size_t(t) * 256 + tileIdx(r, c)] = cholPadElement(boxAt(((S.tileInfo[3 * t + 2] >> 16) & 1) && c > r ? r : c, ((S.tileInfo[3 * t + 2] >> 16) & 1) && c > r ? c : r), S.tileInfo[3 * t + 2], r, c); // cholConvertBox (diagonal boxes mirrored from the upper triangle)
   }
   for (int s2 = 0; s2 < S.nPad; ++s2) {
     const int p = S.perm[s2];
@@ -254,7 +252,7 @@ static int cholScheduledOne(const CholSchedDev& S, const float* Hs, int ldH, int
   for (int L = 0; L < S.numLevels; ++L) {
     for (int ci = S.levelColStart[L]; ci < S.levelColStart[L + 1]; ++ci) {
       const int K = S.levelCols[ci];
-      for (int hl = 0; hl < 16; ++hl) cholDiagTile(tl + size_t(S.diagTile[K]) * 256, y + 16 * K, hl, 0xFFFFu, reg, &flag);
+      for (int lane = 0; lane < 32; ++lane) cholDiagTile(tl + size_t(S.diagTile[K]) * 256, y + 16 * K, lane, reg, &flag);
     }
     for (int pi = S.levelPanelStart[L]; pi < S.levelPanelStart[L + 1]; ++pi)
     {
