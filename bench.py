@@ -70,11 +70,14 @@ def measured_traffic(workload, batch):
 
 class ClockSampler:
     """SM clock / clock-event reasons sampled DURING the timed regions (B200_PROFILING.md recipe). NVML is polled in-process
-    every 5 ms (the timed region of the default run is ~0.1 s, shorter than one nvidia-smi start-up)."""
+    (the timed regions of the default run are ~45 ms each, shorter than one nvidia-smi start-up) every 25 ms: an NVML query takes the
+    driver lock, and polling every 5 ms slowed the end-to-end leg (which issues copies and launches from the host all the time) by 8 %
+    (measured: 8.40 / 9.05 / 9.16 M it/s at 5 / 25 / 100 ms; the device-resident figure does not move) - --clock-poll-ms changes it."""
 
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
 
-    def __init__(self, index):
+    def __init__(self, index, period_s=0.025):
+        self.period_s = period_s
         self.index, self.sm, self.mask, self.max_mhz, self.handle, self.nvml = index, [], 0, None, None, None
         self.stop_flag = threading.Event()
         self.thread = None
@@ -109,7 +112,7 @@ class ClockSampler:
             except Exception as e:  # noqa: BLE001
                 self.error = str(e)
                 return
-            time.sleep(0.005)
+            time.sleep(self.period_s)
 
     def stop(self):
         if self.thread is None:
@@ -408,6 +411,7 @@ def main():
     ap.add_argument("--fused-mode", type=int, default=0)
     ap.add_argument("--strong", action="store_true", help="strong scaling: the workload's global batch (cfg3: 65536) is split over the ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--clock-poll-ms", type=float, default=25.0, help="NVML clock / throttle-reason sampling period during the timed regions")
     ap.add_argument("--no-extras", action="store_true", help="skip the other workloads measured in the same run (cfg2, cfg4, cfg5, convergence mode)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -455,7 +459,7 @@ def main():
             dist.destroy_process_group()
         return
 
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, args.clock_poll_ms * 1e-3)
     sampler.start()
     m = measure_workload(ms, torch, args.workload, B, rank, local_rank, args, args.steps, args.warmup, flush=flush, barrier=barrier)
     clocks = sampler.stop()  # sampled across the device-resident and the end-to-end timed regions

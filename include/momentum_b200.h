@@ -315,6 +315,40 @@ int mb2_mixed_batch_stats(mb2_mixed_batch* b, int64_t stats[6]);
 /* [0] rig, [1] instances, [2] constraints (padded), [3] Gauss-Newton iterations of the last solve */
 int mb2_mixed_batch_bucket_info(mb2_mixed_batch* b, int32_t bucket, int64_t info[4]);
 
+/* ---- single-process multi-GPU: one batch sharded over several devices (north_star "host code stays C++") ----
+ * The reference solves a batch element by element on host threads (pymomentum/tensor_ik/tensor_ik.cpp:127-177, dispenso::parallel_for);
+ * instances are independent, so a batch of total_batch instances is cut into contiguous blocks, one per device, each block an ordinary
+ * mb2_solver on its own device driven by its own host thread. There is no data-path collective: the only cross-device quantity is the
+ * aggregate {sum of final errors, total iterations, instances that ended with status OK}, summed on the host from the per-instance
+ * results (the 24-byte all-reduce of SURVEY 8e; with one process there is nothing to send over NVLink).
+ *
+ * Replicas: mb2_character_clone puts the rig on another device; mb2_solver_function_clone copies the DEFINITION of a solver function
+ * (error-function blocks, shared constraint weights, block weights, enabled parameters - no targets) for a new batch size. */
+int mb2_character_clone(const mb2_character* c, int device, mb2_character** out);
+int mb2_solver_function_clone(const mb2_solver_function* f, const mb2_character* c_on_device, int32_t batch, mb2_solver_function** out);
+int mb2_character_device(const mb2_character* c);
+const mb2_character* mb2_solver_function_character(const mb2_solver_function* f);
+int32_t mb2_solver_function_num_error_functions(const mb2_solver_function* f);
+int32_t mb2_solver_function_target_size(const mb2_solver_function* f, int32_t index); /* floats per instance of block `index` */
+
+typedef struct mb2_sharded_solver mb2_sharded_solver;
+const char* mb2_sharded_last_error(void);
+/* `prototype` defines the problem (it is only read, on its own device, and may be destroyed afterwards); devices[] may name a device more
+ * than once (several shards on one GPU). Shard k holds instances [first_k, first_k + count_k), count = total_batch / num_devices rounded
+ * so that the counts differ by at most one. */
+int mb2_sharded_solver_create(const mb2_solver_function* prototype, int32_t total_batch, int32_t num_devices, const int32_t* devices,
+                              const mb2_gauss_newton_options* opt, mb2_sharded_solver** out);
+void mb2_sharded_solver_destroy(mb2_sharded_solver* s);
+int32_t mb2_sharded_solver_num_shards(const mb2_sharded_solver* s);
+int mb2_sharded_solver_shard_info(const mb2_sharded_solver* s, int32_t shard, int32_t info[3] /* device, first instance, count */);
+int mb2_sharded_solver_set_options(mb2_sharded_solver* s, const mb2_gauss_newton_options* opt);
+/* targets[total_batch][size of block index] in instance order, host memory (SkeletonErrorFunction::setConstraints per instance) */
+int mb2_sharded_solver_set_targets(mb2_sharded_solver* s, int32_t index, const float* targets);
+/* SolverT::solve over the whole batch: parameters[total_batch * n] in/out (host), per-instance results optional */
+int mb2_sharded_solver_solve(mb2_sharded_solver* s, float* parameters, double* errors, int32_t* iterations, int32_t* status);
+/* aggregate of the last solve: [0] sum of final errors, [1] total Gauss-Newton iterations, [2] instances with status MB2_INSTANCE_OK */
+int mb2_sharded_solver_get_aggregate(const mb2_sharded_solver* s, double aggregate[3]);
+
 #ifdef __cplusplus
 }
 #endif

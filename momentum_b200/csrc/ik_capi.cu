@@ -644,6 +644,46 @@ void mb2_solver_function_destroy(mb2_solver_function* f) {
   delete f;
 }
 
+// ---- replicas on other devices (single-process multi-GPU: ik_sharded.cpp) ----
+// The rig (skeleton, parameter transform, parameter limits) on another device; independent of the original afterwards.
+int mb2_character_clone(const mb2_character* c, int device, mb2_character** out) {
+  MB2_CHECK(c != nullptr && out != nullptr, "null argument");
+  const HostCharacter& h = c->host;
+  mb2_character* copy = nullptr;
+  int rc = mb2_character_create(device, h.numJoints, h.parent.data(), h.offset.data(), h.prerot.data(), h.numParams, h.ptOuter.data(), h.ptInner.data(), h.ptVals.data(),
+                                h.ptOffsets.data(), &copy);
+  if (rc != MB2_OK) return rc;
+  copy->host.limits = h.limits;
+  copy->limitsVersion = 1;
+  *out = copy;
+  return MB2_OK;
+}
+// The DEFINITION of a solver function (error-function blocks with their shared constraint data and weights, block weights, enabled
+// parameters) for `batch` instances of character `c` (normally a clone of f's character on another device). Per-instance data
+// (targets, per-instance weights / offsets) is not copied: it belongs to the instances the new function will hold.
+int mb2_solver_function_clone(const mb2_solver_function* f, const mb2_character* c, int32_t batch, mb2_solver_function** out) {
+  MB2_CHECK(f != nullptr && c != nullptr && out != nullptr, "null argument");
+  MB2_CHECK(c->host.numJoints == f->ch->host.numJoints && c->host.numParams == f->ch->host.numParams, "clone target character has a different shape");
+  MB2_CHECK(!f->weightsPerInstance, "a function with per-instance constraint weights cannot be cloned (set them on the clone)");
+  mb2_solver_function* g = nullptr;
+  int rc = mb2_solver_function_create(c, batch, &g);
+  if (rc != MB2_OK) return rc;
+  g->efs = f->efs;
+  g->enabled = f->enabled;
+  g->targetStride = f->targetStride;
+  g->numWeights = f->numWeights;
+  g->hWeights = f->hWeights;
+  g->planDirty = true;
+  *out = g;
+  return MB2_OK;
+}
+int mb2_character_device(const mb2_character* c) { return c ? c->device : -1; }
+const mb2_character* mb2_solver_function_character(const mb2_solver_function* f) { return f ? f->ch : nullptr; }
+int32_t mb2_solver_function_num_error_functions(const mb2_solver_function* f) { return f ? int32_t(f->efs.size()) : 0; }
+int32_t mb2_solver_function_target_size(const mb2_solver_function* f, int32_t index) {
+  return (f && index >= 0 && index < int32_t(f->efs.size())) ? f->efs[index].targetSize : -1;
+}
+
 int32_t mb2_solver_function_num_parameters(const mb2_solver_function* f) { return f ? f->ch->host.numParams : 0; }
 int32_t mb2_solver_function_batch(const mb2_solver_function* f) { return f ? f->B : 0; }
 int32_t mb2_solver_function_actual_parameters(const mb2_solver_function* f) {

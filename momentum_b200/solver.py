@@ -69,6 +69,9 @@ CABI_SYMBOLS = [
     "mb2_mixed_batch_last_error", "mb2_mixed_batch_create", "mb2_mixed_batch_destroy", "mb2_mixed_batch_add_rig", "mb2_mixed_batch_use_limits",
     "mb2_mixed_batch_add_instance", "mb2_mixed_batch_set_parameters", "mb2_mixed_batch_solve", "mb2_mixed_batch_get_result", "mb2_mixed_batch_get_results",
     "mb2_mixed_batch_stats", "mb2_mixed_batch_bucket_info",
+    "mb2_character_clone", "mb2_solver_function_clone", "mb2_character_device", "mb2_solver_function_character", "mb2_solver_function_num_error_functions",
+    "mb2_solver_function_target_size", "mb2_sharded_last_error", "mb2_sharded_solver_create", "mb2_sharded_solver_destroy", "mb2_sharded_solver_num_shards",
+    "mb2_sharded_solver_shard_info", "mb2_sharded_solver_set_options", "mb2_sharded_solver_set_targets", "mb2_sharded_solver_solve", "mb2_sharded_solver_get_aggregate",
 ]
 
 _libs = {}
@@ -145,6 +148,23 @@ def load_library(path: Optional[str] = None):
         L.mb2_mixed_batch_get_results.argtypes = [vp, _fp, C.POINTER(C.c_int64), _dp, _ip, _ip]
         L.mb2_mixed_batch_stats.argtypes = [vp, C.POINTER(C.c_int64)]
         L.mb2_mixed_batch_bucket_info.argtypes = [vp, C.c_int32, C.POINTER(C.c_int64)]
+    if hasattr(L, "mb2_sharded_solver_create"):
+        L.mb2_sharded_last_error.restype = C.c_char_p
+        L.mb2_character_clone.argtypes = [vp, C.c_int, C.POINTER(vp)]
+        L.mb2_solver_function_clone.argtypes = [vp, vp, C.c_int32, C.POINTER(vp)]
+        L.mb2_character_device.argtypes = [vp]
+        L.mb2_solver_function_character.argtypes = [vp]
+        L.mb2_solver_function_character.restype = vp
+        L.mb2_solver_function_num_error_functions.argtypes = [vp]
+        L.mb2_solver_function_target_size.argtypes = [vp, C.c_int32]
+        L.mb2_sharded_solver_create.argtypes = [vp, C.c_int32, C.c_int32, _ip, C.POINTER(_Options), C.POINTER(vp)]
+        L.mb2_sharded_solver_destroy.argtypes = [vp]
+        L.mb2_sharded_solver_num_shards.argtypes = [vp]
+        L.mb2_sharded_solver_shard_info.argtypes = [vp, C.c_int32, _ip]
+        L.mb2_sharded_solver_set_options.argtypes = [vp, C.POINTER(_Options)]
+        L.mb2_sharded_solver_set_targets.argtypes = [vp, C.c_int32, _fp]
+        L.mb2_sharded_solver_solve.argtypes = [vp, vp, _dp, _ip, _ip]
+        L.mb2_sharded_solver_get_aggregate.argtypes = [vp, _dp]
     _libs[path] = L
     return L
 
@@ -529,3 +549,65 @@ class MixedBatch(_Base):
         info = (C.c_int64 * 4)()
         self._check(self._L.mb2_mixed_batch_bucket_info(self._h, bucket, info))
         return dict(zip(["rig", "instances", "constraints", "iterations"], (int(v) for v in info)))
+
+
+class ShardedGaussNewtonSolver(_Base):
+    """One batch over several GPUs from ONE process (mb2_sharded_solver_*): contiguous blocks of instances, one per device, each an
+    ordinary batched solver driven by its own host thread; no data-path collective (the reference's batch loop is an independent
+    parallel_for over instances, tensor_ik.cpp:127-177). ``function`` is the prototype: its definition (error functions, weights,
+    enabled set) is replicated on every device; ``error_functions`` supplies the per-instance targets of the whole batch."""
+
+    def __init__(self, options: "GaussNewtonSolverOptions", function: "SkeletonSolverFunction", total_batch: int, devices, error_functions=None):
+        self._L = function._L
+        self._h = C.c_void_p()
+        self.options = options
+        self.total_batch = int(total_batch)
+        self.num_params = function.character.num_params
+        dv, dp = _i32(devices)
+        o = options._c()
+        self._check(self._L.mb2_sharded_solver_create(function._h, self.total_batch, dv.size, dp, C.byref(o), C.byref(self._h)))
+        if error_functions is not None:
+            for idx, ef in enumerate(error_functions):
+                if getattr(ef, "targets", None) is not None and np.asarray(ef.targets).size:
+                    self.set_targets(idx, ef.targets)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise MomentumB200Error(self._L.mb2_sharded_last_error().decode())
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.mb2_sharded_solver_destroy(self._h)
+            self._h = None
+
+    def shards(self):
+        out = []
+        for k in range(self._L.mb2_sharded_solver_num_shards(self._h)):
+            info = (C.c_int32 * 3)()
+            self._check(self._L.mb2_sharded_solver_shard_info(self._h, k, info))
+            out.append({"device": info[0], "first": info[1], "count": info[2]})
+        return out
+
+    def set_targets(self, index: int, targets):
+        t, tp = _f32(targets)
+        assert t.shape[0] == self.total_batch
+        self._check(self._L.mb2_sharded_solver_set_targets(self._h, index, tp))
+
+    def solve(self, theta0):
+        p = np.ascontiguousarray(theta0, np.float32).copy()
+        assert p.shape == (self.total_batch, self.num_params)
+        B = self.total_batch
+        err = np.zeros(B, np.float64); it = np.zeros(B, np.int32); st = np.zeros(B, np.int32)
+        self._check(self._L.mb2_sharded_solver_solve(self._h, p.ctypes.data_as(C.c_void_p), err.ctypes.data_as(_dp), it.ctypes.data_as(_ip), st.ctypes.data_as(_ip)))
+        agg = (C.c_double * 3)()
+        self._check(self._L.mb2_sharded_solver_get_aggregate(self._h, agg))
+        return {"params": p, "errors": err, "iterations": it, "status": st, "aggregate": {"error_sum": agg[0], "iterations": int(agg[1]), "instances_ok": int(agg[2])}}
+
+    def solve_host_pointer(self, host_ptr: int):
+        """In place on a raw (pinned) host buffer [total_batch][n]; the aggregate via get_aggregate()."""
+        self._check(self._L.mb2_sharded_solver_solve(self._h, C.c_void_p(host_ptr), None, None, None))
+
+    def get_aggregate(self):
+        agg = (C.c_double * 3)()
+        self._check(self._L.mb2_sharded_solver_get_aggregate(self._h, agg))
+        return {"error_sum": agg[0], "iterations": int(agg[1]), "instances_ok": int(agg[2])}
