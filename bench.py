@@ -291,6 +291,7 @@ def kernel_report(m, peaks, workload):
         gram_ms = chol_ms * share
         jtj_phase = {"where": "Gram phase of gramCholeskyKernel (in-kernel cycle share x the kernel's event time)", "share_of_kernel": share, "ms": gram_ms}
         e["phase_cycle_shares"] = {k: v / tot for k, v in cyc.items() if v}
+        e["phase_cycles_per_launch"] = {k: v / max(1, pl[2]) for k, v in cyc.items() if v}  # SM cycles of one steady-state CTA (block batch / 2), barrier to barrier
         kernels.append(e)
     elif st["strip_floats"] > 0:
         gram_bytes = 4.0 * (st["strip_floats"] + ntiles * 256 + 16 * ((st["normal_parameters"] + 15) // 16))

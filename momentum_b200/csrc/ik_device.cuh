@@ -145,8 +145,22 @@ MB2_HD void fkJoint(const FunctionTables& T, int j, const float* jp, float* js) 
 //                                  rotated vector instead of a rotation by a quaternion product; equal up to rounding]
 // fkJoint above stays the statement-by-statement form (CPU emulation of the oracle order, tests).
 template <bool kDeriv>
-MB2_HD void fkLocal(const FunctionTables& T, int j, const float* jp, float* js) {
-  const float* p = jp + j * kParametersPerJoint;
+MB2_HD void fkLocalFromParameters(const FunctionTables& T, int j, const float* p, float* js);
+template <bool kDeriv>
+MB2_HD void fkLocal(const FunctionTables& T, int j, const float* jp, float* js) { fkLocalFromParameters<kDeriv>(T, j, jp + j * kParametersPerJoint, js); }
+// the joint's seven parameters straight from theta (ParameterTransform rows 7 j .. 7 j + 6): no [7 J] array in shared memory, and the
+// transform is spread over lanes = joints (three rounds for 72 joints) instead of lanes = rows (sixteen rounds of dependent loads)
+template <bool kDeriv>
+MB2_HD void fkLocalFromTheta(const FunctionTables& T, int j, const float* theta, float* js) {
+  float p[kParametersPerJoint];
+#pragma unroll
+  for (int r = 0; r < kParametersPerJoint; ++r) p[r] = jointParameterRow(T, j * kParametersPerJoint + r, theta);
+  fkLocalFromParameters<kDeriv>(T, j, p, js);
+}
+// jp == nullptr: the caller keeps no joint-parameter array (same value, recomputed from theta)
+MB2_HD float jointParameterAt(const FunctionTables& T, const float* jp, const float* theta, int row) { return jp != nullptr ? jp[row] : jointParameterRow(T, row, theta); }
+template <bool kDeriv>
+MB2_HD void fkLocalFromParameters(const FunctionTables& T, int j, const float* p, float* js) {
   Q4 ql = ld4(T.prerot + 4 * j);
   float* out = js + j * kJointStateStride;
 #pragma unroll
@@ -458,7 +472,7 @@ MB2_HD float evalUnit(const FunctionTables& T, int ui, const float* theta, const
         break;
       }
       case kUnitLimitMinMaxJoint: {
-        const float p = jp[u.i[0]];
+        const float p = jointParameterAt(T, jp, theta, u.i[0]);
         if (p < u.f[0]) sq = (u.f[0] - p) * (u.f[0] - p);
         if (p > u.f[1]) sq = (u.f[1] - p) * (u.f[1] - p);
         break;
@@ -468,7 +482,8 @@ MB2_HD float evalUnit(const FunctionTables& T, int ui, const float* theta, const
         break;
       }
       case kUnitLimitLinearJoint: {
-        if (limitInRange(u.f[2], u.f[3], jp[u.i[1]])) { const float res = jp[u.i[1]] * u.f[0] - u.f[1] - jp[u.i[0]]; sq = res * res; }
+        const float p1 = jointParameterAt(T, jp, theta, u.i[1]);
+        if (limitInRange(u.f[2], u.f[3], p1)) { const float res = p1 * u.f[0] - u.f[1] - jointParameterAt(T, jp, theta, u.i[0]); sq = res * res; }
         break;
       }
       case kUnitLimitHalfPlane: {
@@ -500,7 +515,7 @@ MB2_HD float evalUnit(const FunctionTables& T, int ui, const float* theta, const
       break;
     }
     case kUnitLimitMinMaxJoint: {
-      const float p = jp[u.i[0]];
+      const float p = jointParameterAt(T, jp, theta, u.i[0]);
       if (p < u.f[0]) { res = p - u.f[0]; active = true; }
       else if (p > u.f[1]) { res = p - u.f[1]; active = true; }
       break;
@@ -509,7 +524,8 @@ MB2_HD float evalUnit(const FunctionTables& T, int ui, const float* theta, const
       if (limitInRange(u.f[2], u.f[3], theta[u.i[1]])) { res = theta[u.i[1]] * u.f[0] - u.f[1] - theta[u.i[0]]; active = true; }
       break;
     case kUnitLimitLinearJoint:
-      if (limitInRange(u.f[2], u.f[3], jp[u.i[1]])) { res = jp[u.i[1]] * u.f[0] - u.f[1] - jp[u.i[0]]; active = true; }
+      { const float p1 = jointParameterAt(T, jp, theta, u.i[1]);
+        if (limitInRange(u.f[2], u.f[3], p1)) { res = p1 * u.f[0] - u.f[1] - jointParameterAt(T, jp, theta, u.i[0]); active = true; } }
       break;
     case kUnitLimitHalfPlane:
       res = theta[u.i[0]] * u.f[0] + theta[u.i[1]] * u.f[1] - u.f[2];

@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <type_traits>
 
 #include "ik_chol.cuh"
 #include "ik_chol_sched.h"
@@ -34,7 +35,9 @@ __device__ __forceinline__ double warpSum(double v) {
 
 size_t sweepSmemPerInstance(const FunctionTables& T, int warpsPerInstance) {
   const size_t nPad = (T.numParams + 3) & ~3;
-  return sizeof(float) * (nPad + size_t(T.numJoints) * (kParametersPerJoint + kJointStateStride) + size_t((T.recStride + 1) & ~1) + 4 + 2 * size_t(warpsPerInstance));
+  // several warps per instance (large rigs): the joint parameters [7 J] are staged too (lanes = rows: the lanes are plentiful there)
+  const size_t jp = warpsPerInstance > 1 ? size_t((T.numJoints * kParametersPerJoint + 1) & ~1) : 0;
+  return sizeof(float) * (nPad + jp + size_t((T.numJoints * kJointStateStride + 1) & ~1) + size_t((T.recStride + 1) & ~1) + 4 + 2 * size_t(warpsPerInstance));
 }
 
 // The read-only tables (character + plan) are walked by dependent loads (cell -> unit -> contributions -> joint);
@@ -61,8 +64,13 @@ __device__ __forceinline__ void stageTable(const E*& table, size_t count, uint32
   cursor += tableWords(count, sizeof(E));
 }
 
-template <bool kJacobian, int W>
-__global__ void __launch_bounds__(512) sweepKernel(const SweepArgs a) {
+// kStaged: the tables live in shared memory for the whole kernel. A template parameter rather than a run-time branch so that every
+// table pointer is PROVABLY a shared-memory address: with `if (a.stageTables)` the pointers could be either and all 273 table loads
+// of the kernel were generic LD instructions (address-space check on every hop of the dependent chains cell -> unit -> record ->
+// contributions; 43 % of the warp-state samples were long-scoreboard waits on them, profiles/r02k).
+constexpr int kSweepMaxWarps = 24; // one warp per instance: up to 24 instances in flight per SM (85 registers per thread)
+template <bool kJacobian, int W, bool kStaged>
+__global__ void __launch_bounds__(W == 1 ? 32 * kSweepMaxWarps : 512) sweepKernel(const SweepArgs a) {
   extern __shared__ __align__(16) float smem[];
   FunctionTables T = a.T;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -71,18 +79,19 @@ __global__ void __launch_bounds__(512) sweepKernel(const SweepArgs a) {
   constexpr int gs = 32 * W;
   const int groupsPerCta = (blockDim.x >> 5) / W;
   const int nPad = (T.numParams + 3) & ~3;
-  const int perGroup = nPad + T.numJoints * (kParametersPerJoint + kJointStateStride) + ((T.recStride + 1) & ~1) + 4 + 2 * W; // even: doubles stay aligned
+  // (kJointStateStride is odd: an odd joint count gets one float of padding so that the doubles below stay 8-byte aligned)
+  const int jpFloats = W > 1 ? ((T.numJoints * kParametersPerJoint + 1) & ~1) : 0;
+  const int perGroup = nPad + jpFloats + ((T.numJoints * kJointStateStride + 1) & ~1) + ((T.recStride + 1) & ~1) + 4 + 2 * W;
   float* th = smem + size_t(group) * perGroup;
-  float* jp = th + nPad;
-  float* js = jp + T.numJoints * kParametersPerJoint;
-  float* rec = js + T.numJoints * kJointStateStride;
+  float* jp = W > 1 ? th + nPad : nullptr;
+  float* js = th + nPad + jpFloats;
+  float* rec = js + ((T.numJoints * kJointStateStride + 1) & ~1);
   double* errSlots = reinterpret_cast<double*>(rec + ((T.recStride + 1) & ~1)); // W partial sums (8-byte aligned: every preceding size is even)
-  const int numJointParams = T.numJoints * kParametersPerJoint;
   auto groupSync = [&]() {
     if (W == 1) __syncwarp();
     else asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(gs) : "memory");
   };
-  if (a.stageTables) {
+  if constexpr (kStaged) {
     uint32_t* cursor = reinterpret_cast<uint32_t*>(smem + ((size_t(groupsPerCta) * perGroup + 3) & ~size_t(3)));
     const size_t J = T.numJoints;
     stageTable(T.parent, J, cursor); stageTable(T.offset, 3 * J, cursor); stageTable(T.prerot, 4 * J, cursor);
@@ -99,11 +108,16 @@ __global__ void __launch_bounds__(512) sweepKernel(const SweepArgs a) {
     const float* theta = a.theta + size_t(b) * a.ldTheta;
     for (int i = gl; i < T.numParams; i += gs) th[i] = theta[i];
     groupSync();
-    for (int row = gl; row < numJointParams; row += gs) jp[row] = jointParameterRow(T, row, th);
-    groupSync();
-    // SkeletonState::set in three data-parallel passes (ik_device.cuh): every joint's local part at once, ~50 dependent flops per
-    // tree level, then the derivative axes of all joints at once
-    for (int j = gl; j < T.numJoints; j += gs) fkLocal<kJacobian>(T, j, jp, js);
+    // SkeletonState::set in three data-parallel passes (ik_device.cuh): every joint's local part at once (its seven joint parameters
+    // come straight from theta: ParameterTransform::apply row by row), ~50 dependent flops per tree level, then the derivative axes
+    // (one warp per instance: three rounds of lanes = joints, each walking its seven rows; several warps per instance: lanes = rows first)
+    if constexpr (W > 1) {
+      for (int row = gl; row < T.numJoints * kParametersPerJoint; row += gs) jp[row] = jointParameterRow(T, row, th);
+      groupSync();
+      for (int j = gl; j < T.numJoints; j += gs) fkLocal<kJacobian>(T, j, jp, js);
+    } else {
+      for (int j = gl; j < T.numJoints; j += gs) fkLocalFromTheta<kJacobian>(T, j, th, js);
+    }
     groupSync();
     for (int lvl = 1; lvl < T.numLevels; ++lvl) { // level 0 = roots: world = local
       const int end = T.levelStart[lvl + 1];
@@ -147,16 +161,25 @@ cudaError_t launchSweep(const SweepArgs& a0, bool jacobian, cudaStream_t stream)
   SweepArgs a = a0;
   const size_t tableBytes = sweepTableBytes(a.T) + 16;
   const size_t budget = size_t(g_maxSmemOptin);
-  // Persistent CTAs of up to 16 warps. As many instances in flight as shared memory holds next to the staged tables (if those
-  // fit with at least two instances; else they stay in L2); when that is fewer than 16, several warps share one instance.
+  // Persistent CTAs. As many instances in flight as shared memory holds next to the staged tables (if those fit with at least two
+  // instances; else they stay in L2), one warp each, up to kSweepMaxWarps; when fewer than 16 fit, several warps share one instance.
   const size_t per1 = sweepSmemPerInstance(a.T, 8);
   a.stageTables = (2 * per1 + tableBytes <= budget) ? 1 : 0;
   int groups = int((budget - (a.stageTables ? tableBytes : 0)) / per1);
   if (groups < 1) return cudaErrorInvalidConfiguration;
-  if (groups > 15) groups = 16; // one warp each (15 named barriers otherwise)
+  const int groupsOneWarp = int((budget - (a.stageTables ? tableBytes : 0)) / sweepSmemPerInstance(a.T, 1)); // (no joint-parameter array)
   int W = 1;
-  while (W < 8 && groups * W * 2 <= 16) W *= 2;
-  if (W == 1) groups = groups > 16 ? 16 : groups;
+  if (groupsOneWarp >= 16) {
+    groups = groupsOneWarp;
+    groups = std::min(groups, kSweepMaxWarps);
+    // the instances of an SM are dealt to its warps round by round: keep the number of rounds the widest CTA gives and use the fewest
+    // warps that still finish in that many (8192 instances on 148 SMs: 24 warps -> 3 rounds, and 19 warps are enough for 3)
+    const int sms = std::max(g_numSms, 1);
+    const int rounds = (a.batch + sms * groups - 1) / (sms * groups);
+    groups = std::max(std::min(groups, (a.batch + sms * rounds - 1) / (sms * rounds)), std::min(groups, 16));
+  } else {
+    while (W < 8 && groups * W * 2 <= 16) W *= 2; // (at most 15 named barriers: groups <= 15 here)
+  }
   a.warpsPerInstance = W;
   const int warps = groups * W;
   const size_t per = sweepSmemPerInstance(a.T, W);
@@ -175,20 +198,17 @@ cudaError_t launchSweep(const SweepArgs& a0, bool jacobian, cudaStream_t stream)
     kernel<<<grid, warps * 32, smem, stream>>>(a);
     return cudaGetLastError();
   };
-  if (jacobian) {
+  auto pick = [&](auto jac, auto staged) -> cudaError_t {
+    constexpr bool kJ = decltype(jac)::value, kS = decltype(staged)::value;
     switch (W) {
-      case 1: return launch(sweepKernel<true, 1>);
-      case 2: return launch(sweepKernel<true, 2>);
-      case 4: return launch(sweepKernel<true, 4>);
-      default: return launch(sweepKernel<true, 8>);
+      case 1: return launch(sweepKernel<kJ, 1, kS>);
+      case 2: return launch(sweepKernel<kJ, 2, kS>);
+      case 4: return launch(sweepKernel<kJ, 4, kS>);
+      default: return launch(sweepKernel<kJ, 8, kS>);
     }
-  }
-  switch (W) {
-    case 1: return launch(sweepKernel<false, 1>);
-    case 2: return launch(sweepKernel<false, 2>);
-    case 4: return launch(sweepKernel<false, 4>);
-    default: return launch(sweepKernel<false, 8>);
-  }
+  };
+  if (jacobian) return a.stageTables ? pick(std::true_type{}, std::true_type{}) : pick(std::true_type{}, std::false_type{});
+  return a.stageTables ? pick(std::false_type{}, std::true_type{}) : pick(std::false_type{}, std::false_type{});
 }
 
 
@@ -781,7 +801,9 @@ __global__ void __launch_bounds__(kGramThreads, 4) gramCholeskyKernel(const Gram
   cholFinish(c, b, n, y, gsub, flags[0] != 0, S.pos); // y holds the step per elimination slot
   MB2_GC(7)
   if constexpr (kProfile) {
-    if (b == 0 && tid == 0 && a.phaseCycles != nullptr)
+    // a block from the middle of the grid: its SM is in steady state (the other resident CTAs are at unrelated phases), unlike block 0,
+    // whose whole first wave starts in lock step
+    if (b == int(gridDim.x >> 1) && tid == 0 && a.phaseCycles != nullptr)
       for (int k = 0; k < 8; ++k) a.phaseCycles[k] += (unsigned long long)pc[k];
   }
 #undef MB2_GC

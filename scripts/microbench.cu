@@ -134,6 +134,36 @@ __global__ void probe(float* out, long long* cyc, int warpsActive) {
 #endif
 }
 
+// SM-level throughput of the Gram inner loop and of bare HMMA issue: every warp of one CTA runs `steps` mma3x steps over strips in shared
+// memory (the gramTileAccumulate loop), then `steps` x 6 independent HMMAs; cycles for the whole CTA, so cycles / (steps * warps) is the
+// SM's cost per step (per 6 HMMAs) at that occupancy.
+__global__ void gramProbe(float* out, long long* cyc) {
+#if defined(__CUDA_ARCH__)
+  extern __shared__ __align__(16) float strips[]; // 116 strips of 64 floats
+  __shared__ __align__(16) int quads[4 * 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 116 * 64; i += blockDim.x) strips[i] = 0.01f * float((i * 37) % 101) - 0.5f;
+  for (int i = tid; i < 128; i += blockDim.x) quads[i] = 64 * ((i * 29 + 5) % 116);
+  __syncthreads();
+  float d[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+  long long t0 = clock64();
+  for (int rep = 0; rep < 4; ++rep) gramTileAccumulate(strips, quads, (warp & 15), (warp & 15) + 16, lane, d);
+  __syncthreads();
+  long long t1 = clock64();
+  if (tid == 0) cyc[0] = (t1 - t0) / 64;
+  float e0[4] = {0, 0, 0, 0}, e1[4] = {0, 0, 0, 0}, e2[4] = {0, 0, 0, 0}, e3[4] = {0, 0, 0, 0}, e4[4] = {0, 0, 0, 0}, e5[4] = {0, 0, 0, 0};
+  const float a = 1.0f + lane, b = 0.5f;
+  __syncthreads();
+  t0 = clock64();
+#pragma unroll 4
+  for (int i = 0; i < 64; ++i) { mmaTf32K8(e0, a, a, a, a, b, b); mmaTf32K8(e1, a, a, a, a, b, b); mmaTf32K8(e2, a, a, a, a, b, b); mmaTf32K8(e3, a, a, a, a, b, b); mmaTf32K8(e4, a, a, a, a, b, b); mmaTf32K8(e5, a, a, a, a, b, b); }
+  __syncthreads();
+  t1 = clock64();
+  if (tid == 0) cyc[1] = (t1 - t0) / 64;
+  out[tid] = d[0][0] + d[1][3] + e0[0] + e1[1] + e2[2] + e3[3] + e4[0] + e5[1];
+#endif
+}
+
 int main() {
   float* out; long long* cyc;
   cudaMalloc(&out, 1024 * 4); cudaMalloc(&cyc, 16 * 8);
@@ -150,6 +180,16 @@ int main() {
       printf("== %d threads, %d active warp(s): %s\n", threads, wa, cudaGetErrorString(cudaGetLastError()));
       for (int i = 0; i < 9; ++i) printf("  %-50s %lld\n", names[i], h[i]);
     }
+  }
+  cudaFuncSetAttribute(gramProbe, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 64 * 4);
+  for (int threads : {32, 128, 256, 512, 1024}) {
+    gramProbe<<<1, threads, 116 * 64 * 4>>>(out, cyc);
+    gramProbe<<<1, threads, 116 * 64 * 4>>>(out, cyc);
+    cudaDeviceSynchronize();
+    long long h[2];
+    cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+    printf("== gramProbe %d warps on one SM: %lld cycles per mma3x step-round (all warps one step each) = %.1f cycles per step per SM; 6 independent HMMA round: %lld cycles = %.1f per HMMA per SM  (%s)\n",
+           threads / 32, h[0], double(h[0]) / (threads / 32), h[1], double(h[1]) / (6.0 * threads / 32), cudaGetErrorString(cudaGetLastError()));
   }
   return 0;
 }

@@ -101,7 +101,7 @@ static void sweepOne(mb2_solver_function* f, const FunctionTables& T, int b, con
   std::vector<float> jp(size_t(T.numJoints) * 7), js(size_t(T.numJoints) * kJointStateStride), rec(T.recStride + 4);
   for (int row = 0; row < T.numJoints * 7; ++row) jp[row] = jointParameterRow(T, row, theta);
   // the kernels' three passes (fkJoint, the statement-by-statement form, is checked against them below)
-  for (int j = 0; j < T.numJoints; ++j) fkLocal<kJacobian>(T, j, jp.data(), js.data());
+  for (int j = 0; j < T.numJoints; ++j) fkLocalFromTheta<kJacobian>(T, j, theta, js.data()); // as sweepKernel: joint parameters straight from theta
   for (int lvl = 1; lvl < T.numLevels; ++lvl)
     for (int k = T.levelStart[lvl]; k < T.levelStart[lvl + 1]; ++k) fkCompose(T, T.levelJoints[k], js.data());
   if (kJacobian)
@@ -124,7 +124,7 @@ static void sweepOne(mb2_solver_function* f, const FunctionTables& T, int b, con
   // lanes accumulate in double, then a butterfly reduction: emulate the same association
   double lane[32];
   for (int l = 0; l < 32; ++l) lane[l] = 0.0;
-  for (int u = 0; u < T.numUnits; ++u) lane[u & 31] += (double)evalUnit<kJacobian>(T, u, theta, jp.data(), js.data(), tg, cw, rec.data(), res);
+  for (int u = 0; u < T.numUnits; ++u) lane[u & 31] += (double)evalUnit<kJacobian>(T, u, theta, (u & 1) ? jp.data() : nullptr, js.data(), tg, cw, rec.data(), res); // both forms of the joint-parameter access
   for (int o = 16; o > 0; o >>= 1) {
     double t[32];
     for (int l = 0; l < 32; ++l) t[l] = lane[l] + lane[l ^ o];
