@@ -45,6 +45,32 @@ def test_solve_ik_forward_matches_the_oracle_and_stays_on_the_device():
         assert d <= 5e-4, (b, d)  # a chain fixture with line search: rounding-sensitive like the other chain tests
 
 
+def test_solve_ik_qr_linear_solver_is_the_reference_default_path():
+    """LinearSolverType.QR = GaussNewtonSolverQRT with its line search (tensor_ik.cpp:153-158, the reference's default) against the
+    oracle's restatement of that solver; TrustRegionQR is rejected loudly (not built on the device)."""
+    from momentum_b200 import character as mc
+    from momentum_b200 import torch_ik as ti
+    from oracle.binding import OracleFunction
+
+    ch, parents, offsets, targets, active, torch = _problem(B=4, seed=9)
+    B, n = targets.shape[0], ch.num_params
+    dev = torch.device("cuda", 0)
+    opts = ti.SolverOptions(linear_solver_type=ti.LinearSolverType.QR, levmar_lambda=0.01, min_iter=4, max_iter=12, threshold=10.0, line_search=True)
+    efw = torch.tensor([[1.0]] * B, device=dev)
+    kw = dict(position_cons_parents=parents, position_cons_offsets=offsets, position_cons_weights=torch.ones(B, len(parents), device=dev),
+              position_cons_targets=torch.from_numpy(targets).to(dev))
+    out = ti.solve_ik(ch, active, torch.zeros(B, n, device=dev), [ti.ErrorFunctionType.Position], efw, opts, **kw)
+    for b in range(B):
+        efs = [mc.PositionErrorFunction(parents, offsets, np.ones(len(parents)), targets, weight=1.0)]
+        orc = OracleFunction(ch, efs, "float32", instance=b)
+        orc.set_enabled_parameters(active)
+        err, p, it, _ = orc.solve(np.zeros(n), min_iterations=4, max_iterations=12, threshold=10.0, regularization=0.01, do_line_search=True, qr_solver=True)
+        d = np.max(np.abs(out[b].cpu().numpy() - p)) / max(1.0, np.max(np.abs(p)))
+        assert d <= 5e-4, (b, d)
+    with pytest.raises(NotImplementedError, match="TrustRegionQR"):
+        ti.solve_ik(ch, active, torch.zeros(B, n, device=dev), [ti.ErrorFunctionType.Position], efw, ti.SolverOptions(linear_solver_type=ti.LinearSolverType.TrustRegionQR), **kw)
+
+
 def _ift_reference(ch, parents, offsets, weights, targets_b, active, theta_b, gout_b):
     """d_modelParams_d_inputs (fully_differentiable_body_ik.cpp:112-238) in numpy on the double oracle's Jacobian: v = (2 J^T J)^+ g by the SVD
     of J (s^2 < 1e-5 dropped), dLoss/dtarget_c = 2 sqrt(w_c) J_c v, dLoss/dweight_c = -2 (r_c . J_c v) / w_c."""
