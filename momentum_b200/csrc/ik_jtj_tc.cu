@@ -16,6 +16,14 @@
 // converter warps derives hi (in place) and lo (second buffer, same swizzled positions) from the raw
 // fp32 slab that TMA delivered.
 //
+// Work items. The result is cut into row tiles of 128 (UMMA M = 128); row tile t needs the columns 128 t .. only (consumers read the
+// upper triangle). An item is (row tile t, a chunk of at most 256 of those columns) = one accumulator of at most 256 TMEM columns:
+//   * diagonal item: columns 128 t .. 128 t + 255 - ONE box of up to 256 operand rows, whose first 128 rows are also the A operand;
+//   * far item (only when numCols + 1 > 128 t + 256): the remaining columns - a B box of those rows plus a separate 128-row A box.
+// numCols + 1 <= 256 gives the two diagonal items of the first version of this kernel; up to 512 (bodyhands300: 425) there are at most
+// four row tiles and at most one far item per tile. Two TMEM slots of 256 columns alternate between consecutive items, so the epilogue
+// of one item drains while the MMAs of the next run.
+//
 // Roles in one persistent CTA (1 CTA / SM, 448 threads):
 //   warp 0        TMA producer (one elected lane)
 //   warp 1        TMEM allocator + MMA issuer (one elected lane)
@@ -46,6 +54,14 @@ constexpr int kKBlock = 32;         // floats per K block = one 128-byte swizzle
 constexpr int kRowBytes = 128;
 constexpr int kUmmaK = 8;           // tf32: 32 bytes of K per instruction
 
+constexpr int kMaxItems = 8;
+struct TcItem {
+  int aRow0;    // first operand row of the A box = first row of the row tile (128 t)
+  int bRow0;    // first operand row of the B box = first column of the chunk
+  int n;        // UMMA N: columns of the chunk, a multiple of 16, <= 256
+  int bBoxRows; // 256 or 128: which tensor map loads the B box
+  int sepA;     // far item: the A rows are not in the B box, a second (128-row) box is loaded behind the B region
+};
 struct TcParams {
   int batch;
   int ns, numCols, ldJ, kBlocks;
@@ -53,10 +69,12 @@ struct TcParams {
   int ldH;
   const int32_t* active;
   int passes;     // 3 or 1
-  int mTiles;     // 1 or 2
-  int boxRows;    // 128 or 256
-  int n0, n1;     // UMMA N of tile 0 / tile 1 (multiples of 16)
-  int tmemCols;   // power of two >= n0 + n1
+  int numItems;
+  TcItem items[kMaxItems];
+  int bRegionRows; // operand rows reserved for the B box in a stage (256, or 128 when every item fits a 128-row box)
+  int planeRows;   // bRegionRows (+ 128 when some item needs a separate A box): rows of one hi (or lo) plane of a stage
+  int tmemCols;    // 2 slots x 256 (or the power of two that holds 2 x the widest item)
+  int slotCols;
   int stages;
   size_t hStride;
   float* G;       // optional [batch][ldG]: J^T r as a contiguous vector (the scheduled Cholesky bulk-copies it)
@@ -126,15 +144,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
   extern __shared__ __align__(1024) uint8_t smemRaw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = (smemAddr(smemRaw) + 1023u) & ~1023u;
-  const uint32_t slabBytes = (uint32_t)p.boxRows * kRowBytes;          // one K block of all rows
+  const uint32_t slabBytes = (uint32_t)p.planeRows * kRowBytes;        // one K block of every operand row of an item: [B box | A box of far items]
   const uint32_t stageBytes = slabBytes * (p.passes == 3 ? 2u : 1u);   // hi [+ lo]
+  const uint32_t aRegionOff = (uint32_t)p.bRegionRows * kRowBytes;     // where a far item's A box sits inside a plane
   const uint32_t barBase = base + stageBytes * p.stages;
   auto fullBar = [&](int s) { return barBase + 8u * s; };
   auto convBar = [&](int s) { return barBase + 8u * (p.stages + s); };
   auto emptyBar = [&](int s) { return barBase + 8u * (2 * p.stages + s); };
-  // Work items: one accumulator tile of one instance. With two tiles an instance is the pair (tile 1: rows/cols 128.., then
-  // tile 0: rows 0..127 x all columns); each has its own TMEM columns and full/empty barriers, so the epilogue of one item
-  // drains while the MMAs of the next item run (TMEM cannot hold two complete instances: 2 x (n0 + n1) > 512 columns).
+  // Two TMEM slots with their own full / empty barriers alternate between consecutive work items (file header)
   auto tmemFullBar = [&](int t) { return barBase + 8u * (3 * p.stages + t); };
   auto tmemEmptyBar = [&](int t) { return barBase + 8u * (3 * p.stages + 2 + t); };
   const uint32_t tmemSlot = barBase + 8u * (3 * p.stages + 4);
@@ -163,14 +180,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
       long long wEmpty = 0, tStart = clock64();
       for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
         if (p.active != nullptr && p.active[b] == 0) continue;
-        for (int t = p.mTiles - 1; t >= 0; --t) {
-          const bool half = t == 1; // tile 1 only needs columns 128.. of J: a 128-row box
+        for (int it = 0; it < p.numItems; ++it) {
+          const TcItem I = p.items[it];
+          const uint32_t bBytes = (uint32_t)I.bBoxRows * kRowBytes;
           for (int kb = 0; kb < p.kBlocks; ++kb) {
             long long t0 = clock64();
             mbarWaitRelaxed(emptyBar(s), ph ^ 1u);
             wEmpty += clock64() - t0;
-            mbarExpectTx(fullBar(s), half ? 128u * kRowBytes : slabBytes);
-            tmaLoad3d(base + stageBytes * s, half ? &tmapHalf : &tmap, kb * kKBlock, half ? 128 : 0, b, fullBar(s));
+            mbarExpectTx(fullBar(s), bBytes + (I.sepA ? 128u * kRowBytes : 0u));
+            tmaLoad3d(base + stageBytes * s, I.bBoxRows == 128 ? &tmapHalf : &tmap, kb * kKBlock, I.bRow0, b, fullBar(s));
+            if (I.sepA) tmaLoad3d(base + stageBytes * s + aRegionOff, &tmapHalf, kb * kKBlock, I.aRow0, b, fullBar(s));
             if (++s == p.stages) { s = 0; ph ^= 1u; }
           }
         }
@@ -181,18 +200,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
       int s = 0;
-      uint32_t ph = 0, tph[2] = {0, 0};
-      const uint32_t idesc0 = makeInstrDesc(128, p.n0), idesc1 = makeInstrDesc(128, p.n1);
+      uint32_t ph = 0, tph[2] = {0, 0}, count = 0;
       long long wTmem = 0, wConv = 0, tStart = clock64();
       for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
         if (p.active != nullptr && p.active[b] == 0) continue;
-        for (int t = p.mTiles - 1; t >= 0; --t) {
+        for (int it = 0; it < p.numItems; ++it, ++count) {
+          const TcItem I = p.items[it];
+          const int slot = int(count & 1u);
           long long t0 = clock64();
-          mbarWait(tmemEmptyBar(t), tph[t] ^ 1u); // the epilogue has drained this tile's accumulator of the previous instance
+          mbarWait(tmemEmptyBar(slot), tph[slot] ^ 1u); // the epilogue has drained the item that used this slot before
           wTmem += clock64() - t0;
           tcFenceAfter();
-          const uint32_t dcol = tmemBase + (t == 0 ? 0u : (uint32_t)p.n0);
-          const uint32_t idesc = t == 0 ? idesc0 : idesc1;
+          const uint32_t dcol = tmemBase + uint32_t(slot * p.slotCols);
+          const uint32_t idesc = makeInstrDesc(128, I.n);
+          const uint32_t aOff = I.sepA ? aRegionOff : 0u; // diagonal item: the A rows are the first 128 rows of the B box
           for (int kb = 0; kb < p.kBlocks; ++kb) {
             t0 = clock64();
             mbarWait(convBar(s), ph);
@@ -200,8 +221,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
             tcFenceAfter();
             const uint32_t hi = base + stageBytes * s, lo = hi + slabBytes;
             for (int pass = 0; pass < p.passes; ++pass) {
-              // A = the tile's 128 rows, B = every row of the slab (tile 1's slab starts at row 128: upper triangle only)
-              const uint32_t aBase = pass == 2 ? lo : hi; // hi*hi, hi*lo, lo*hi
+              const uint32_t aBase = (pass == 2 ? lo : hi) + aOff; // hi*hi, hi*lo, lo*hi
               const uint32_t bBase = pass == 1 ? lo : hi;
 #pragma unroll
               for (int k4 = 0; k4 < kKBlock / kUmmaK; ++k4) {
@@ -210,10 +230,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
               }
             }
             ummaCommit(emptyBar(s)); // smem slab reusable once these MMAs have read it
-            if (kb == p.kBlocks - 1) ummaCommit(tmemFullBar(t));
+            if (kb == p.kBlocks - 1) ummaCommit(tmemFullBar(slot));
             if (++s == p.stages) { s = 0; ph ^= 1u; }
           }
-          tph[t] ^= 1u;
+          tph[slot] ^= 1u;
         }
       }
       if ((p.profile & 1) && blockIdx.x == 0) printf("tc-profile mma: total %lld waitTmemEmpty %lld waitConverted %lld\n", clock64() - tStart, wTmem, wConv);
@@ -226,8 +246,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
     long long wFull = 0, tStart = clock64();
     for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
       if (p.active != nullptr && p.active[b] == 0) continue;
-      for (int t = p.mTiles - 1; t >= 0; --t) {
-        const int vecs = t == 1 ? 128 * kRowBytes / 16 : (int)(slabBytes / 16u);
+      for (int it = 0; it < p.numItems; ++it) {
+        const TcItem I = p.items[it];
+        // two segments of the plane: the B box, and (far items) the A box behind the B region
+        const int vecsB = I.bBoxRows * kRowBytes / 16, vecsA = I.sepA ? 128 * kRowBytes / 16 : 0, offA = int(aRegionOff / 16u);
         for (int kb = 0; kb < p.kBlocks; ++kb) {
           long long t0 = clock64();
           mbarWaitRelaxed(fullBar(s), ph);
@@ -235,7 +257,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
           float4* hi = reinterpret_cast<float4*>(gen + stageBytes * s);
           float4* lo = reinterpret_cast<float4*>(gen + stageBytes * s + slabBytes);
 #pragma unroll 4
-          for (int i = ct; i < vecs; i += kConvThreads) {
+          for (int j = ct; j < vecsB + vecsA; j += kConvThreads) {
+            const int i = j < vecsB ? j : offA + (j - vecsB);
             const float4 x = hi[i];
             uint4 h;
             h.x = toTf32(x.x); h.y = toTf32(x.y); h.z = toTf32(x.z); h.w = toTf32(x.w);
@@ -258,22 +281,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
     // ---------------- epilogue: TMEM -> global, column-major lower triangle of [JtJ; Jtr] ----------------
     const int q = warp & 3; // TMEM lane quarter this warp may access
     float* stage = reinterpret_cast<float*>(gen + stageOff) + (warp - 10) * 32 * kStageRowFloats;
-    uint32_t eph[2] = {0, 0};
+    uint32_t eph[2] = {0, 0}, count = 0;
     long long wFullT = 0, tStart = clock64(), tLd = 0, nChunks = 0, tSts = 0, tStg = 0;
     for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
       if (p.active != nullptr && p.active[b] == 0) continue;
       float* H = p.H + (size_t)b * p.hStride;
-      for (int t = p.mTiles - 1; t >= 0; --t) {
+      for (int it = 0; it < p.numItems; ++it, ++count) {
+        const TcItem I = p.items[it];
+        const int slot = int(count & 1u);
         long long t0 = clock64();
-        mbarWaitRelaxed(tmemFullBar(t), eph[t]);
+        mbarWaitRelaxed(tmemFullBar(slot), eph[slot]);
         wFullT += clock64() - t0;
         tcFenceAfter();
-        const int rowBase = t * 128 + q * 32;                     // first of this warp's 32 rows of [J r]^T [J r]
+        const int rowBase = I.aRow0 + q * 32;                     // first of this warp's 32 rows of [J r]^T [J r]
+        const int cb = I.bRow0;                                   // first matrix column of the item's accumulator
         const int row = rowBase + lane;
         const int i = row < p.ns ? row : (row == p.numCols ? p.ns : -1); // row of the (ns+1) system; -1: not wanted
-        if (__reduce_max_sync(0xffffffffu, i) < 0) { tcFenceBefore(); mbarArrive(tmemEmptyBar(t)); eph[t] ^= 1u; continue; } // warp-uniform: nothing to write
-        const int nT = t == 0 ? p.n0 : p.n1;
-        const uint32_t colBase = tmemBase + ((uint32_t)(q * 32) << 16) + (t == 0 ? 0u : (uint32_t)p.n0);
+        if (__reduce_max_sync(0xffffffffu, i) < 0) { tcFenceBefore(); mbarArrive(tmemEmptyBar(slot)); eph[slot] ^= 1u; continue; } // warp-uniform: nothing to write
+        const int nT = I.n;
+        const uint32_t colBase = tmemBase + ((uint32_t)(q * 32) << 16) + uint32_t(slot * p.slotCols);
         if (p.ns == p.numCols) {
           // solver path: full rows. 32x32 blocks go TMEM -> registers -> shared (row = TMEM lane) -> global, re-mapped so
           // that one store instruction writes four rows x 128 contiguous bytes.
@@ -287,7 +313,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
             rowPtr[k] = H + (size_t)(rowIo[k] < (1 << 30) ? rowIo[k] : 0) * p.ldH + 4 * (lane & 7);
           }
           for (int c0 = 0; c0 < nT; c0 += 32) {
-            if (t * 128 + c0 + 32 <= rowBase && !(t * 128 + c0 <= p.numCols && p.numCols < t * 128 + c0 + 32)) continue; // entirely left of the diagonal
+            if (cb + c0 + 32 <= rowBase && !(cb + c0 <= p.numCols && p.numCols < cb + c0 + 32)) continue; // entirely left of the diagonal
             float v[32];
             const long long tl0 = p.profile ? clock64() : 0;
             if (c0 + 32 <= nT) tmemLoad32(colBase + (uint32_t)c0, v);
@@ -298,16 +324,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
               *reinterpret_cast<float4*>(stage + lane * kStageRowFloats + 4 * g4) = make_float4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
             __syncwarp();
             if (p.profile) { tSts += clock64() - tl0; }
-            if (p.G != nullptr && t * 128 + c0 <= p.numCols && p.numCols < t * 128 + c0 + 32 && i >= 0 && i < p.ns) // column numCols = J^T r
-              p.G[(size_t)b * p.ldG + i] = stage[lane * kStageRowFloats + (p.numCols - t * 128 - c0)];
-            const int c = t * 128 + c0 + 4 * (lane & 7); // matrix column of this lane's float4
+            if (p.G != nullptr && cb + c0 <= p.numCols && p.numCols < cb + c0 + 32 && i >= 0 && i < p.ns) // column numCols = J^T r
+              p.G[(size_t)b * p.ldG + i] = stage[lane * kStageRowFloats + (p.numCols - cb - c0)];
+            const int c = cb + c0 + 4 * (lane & 7); // matrix column of this lane's float4
             float4 vals[8]; // all shared-memory reads first: the compiler cannot move them across the global stores itself (possible aliasing)
 #pragma unroll
             for (int k = 0; k < 8; ++k) vals[k] = *reinterpret_cast<const float4*>(stage + (4 * k + (lane >> 3)) * kStageRowFloats + 4 * (lane & 7));
             if (!(p.profile & 2) && c < p.ldH) {
 #pragma unroll
               for (int k = 0; k < 8; ++k)
-                if (c + 3 >= rowIo[k]) *reinterpret_cast<float4*>(rowPtr[k] + (t * 128 + c0)) = vals[k]; // upper triangle (col >= row) only: everything downstream reads H(min, max)
+                if (c + 3 >= rowIo[k]) *reinterpret_cast<float4*>(rowPtr[k] + (cb + c0)) = vals[k]; // upper triangle (col >= row) only: everything downstream reads H(min, max)
             }
             __syncwarp();
             if (p.profile) { tStg += clock64() - tl0; }
@@ -321,15 +347,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) jtjTensorKernel(const __grid_co
             if (i < 0) continue;
 #pragma unroll
             for (int cc = 0; cc < 16; ++cc) {
-              const int c = t * 128 + c0 + cc;
+              const int c = cb + c0 + cc;
               if (c < p.ns) Hrow[c] = v[cc];
               else if (c == p.numCols) Hrow[p.ns] = v[cc];
             }
           }
         }
         tcFenceBefore();
-        mbarArrive(tmemEmptyBar(t));
-        eph[t] ^= 1u;
+        mbarArrive(tmemEmptyBar(slot));
+        eph[slot] ^= 1u;
       }
     }
     if ((p.profile & 1) && blockIdx.x == 0 && lane == 0)
@@ -362,19 +388,29 @@ EncodeTiledFn encodeTiled() {
 int roundUpI(int v, int m) { return (v + m - 1) / m * m; }
 
 struct Shape {
-  int rows, mTiles, boxRows, n0, n1, tmemCols;
+  int rows, r16, numItems, bRegionRows, planeRows, maxN;
+  bool anySepA;
+  TcItem items[kMaxItems];
 };
 Shape shapeFor(int numCols) {
   Shape s{};
   s.rows = numCols + 1;
-  s.mTiles = s.rows > 128 ? 2 : 1;
-  s.boxRows = s.mTiles * 128;
-  const int r16 = roundUpI(s.rows, 16);
-  s.n0 = r16;                      // rows 0..127 against every column
-  s.n1 = s.mTiles == 2 ? r16 - 128 : 0; // rows 128.. against columns 128.. only: consumers read the upper triangle (col >= row)
-  int need = s.n0 + s.n1, c = 32;
-  while (c < need) c <<= 1;
-  s.tmemCols = c;
+  s.r16 = roundUpI(s.rows, 16);
+  const int tiles = (s.rows + 127) / 128;
+  for (int t = tiles - 1; t >= 0; --t) { // last row tile first, as the kernel's roles walk them
+    const int c0 = 128 * t, left = s.r16 - c0;
+    TcItem d{};
+    d.aRow0 = c0; d.bRow0 = c0; d.n = left < 256 ? left : 256; d.bBoxRows = d.n <= 128 ? 128 : 256; d.sepA = 0;
+    s.items[s.numItems++] = d;
+    if (left > 256) { // the columns beyond the diagonal box: a far item with its own A box
+      TcItem f{};
+      f.aRow0 = c0; f.bRow0 = c0 + 256; f.n = left - 256; f.bBoxRows = f.n <= 128 ? 128 : 256; f.sepA = 1;
+      s.items[s.numItems++] = f;
+      s.anySepA = true;
+    }
+  }
+  for (int i = 0; i < s.numItems; ++i) { s.bRegionRows = s.bRegionRows > s.items[i].bBoxRows ? s.bRegionRows : s.items[i].bBoxRows; s.maxN = s.maxN > s.items[i].n ? s.maxN : s.items[i].n; }
+  s.planeRows = s.bRegionRows + (s.anySepA ? 128 : 0);
   return s;
 }
 
@@ -395,20 +431,20 @@ cudaError_t makeTensorMap3d(CUtensorMap* map, const float* base, const uint64_t 
 
 bool jtjTensorSupported(int ns, int numCols, int ldJ) {
   if (encodeTiled() == nullptr) return false;
-  return ns >= 1 && ns <= numCols && numCols + 1 <= 256 && (ldJ % kKBlock) == 0;
+  return ns >= 1 && ns <= numCols && numCols + 1 <= 512 && (ldJ % kKBlock) == 0; // at most four row tiles, at most one far item per tile
 }
 
 cudaError_t launchJtJTensor(const JtJArgs& a, int passes, cudaStream_t stream) {
   if (!jtjTensorSupported(a.ns, a.numCols, a.ldJ)) return cudaErrorNotSupported;
   const Shape sh = shapeFor(a.numCols);
-  // TMA descriptor over the device Jacobian [batch][numCols + 1][ldJ] (innermost first)
+  // TMA descriptors over the device Jacobian [batch][numCols + 1][ldJ] (innermost first): 256-row and 128-row boxes of one 32-float K block
   CUtensorMap map;
   const uint64_t dims[3] = {(uint64_t)a.ldJ, (uint64_t)(a.numCols + 1), (uint64_t)a.batch};
   const uint64_t strides[2] = {(uint64_t)a.ldJ * sizeof(float), (uint64_t)(a.numCols + 1) * a.ldJ * sizeof(float)};
-  const uint32_t box[3] = {(uint32_t)kKBlock, (uint32_t)sh.boxRows, 1u};
+  const uint32_t box[3] = {(uint32_t)kKBlock, 256u, 1u};
   cudaError_t me = makeTensorMap3d(&map, a.jacobian, dims, strides, box, 128);
   if (me != cudaSuccess) return me;
-  CUtensorMap mapHalf; // 128-row box for the second accumulator tile (columns 128.. of J)
+  CUtensorMap mapHalf;
   const uint32_t boxHalf[3] = {(uint32_t)kKBlock, 128u, 1u};
   me = makeTensorMap3d(&mapHalf, a.jacobian, dims, strides, boxHalf, 128);
   if (me != cudaSuccess) return me;
@@ -422,16 +458,18 @@ cudaError_t launchJtJTensor(const JtJArgs& a, int passes, cudaStream_t stream) {
   p.ldH = a.ldH;
   p.active = a.active;
   p.passes = passes == 3 ? 3 : 1;
-  p.mTiles = sh.mTiles;
-  p.boxRows = sh.boxRows;
-  p.n0 = sh.n0;
-  p.n1 = sh.n1;
-  p.tmemCols = sh.tmemCols;
+  p.numItems = sh.numItems;
+  for (int i = 0; i < sh.numItems; ++i) p.items[i] = sh.items[i];
+  p.bRegionRows = sh.bRegionRows;
+  p.planeRows = sh.planeRows;
+  p.slotCols = 32;
+  while (p.slotCols < sh.maxN) p.slotCols <<= 1;
+  p.tmemCols = 2 * p.slotCols; // a power of two >= 64
   p.hStride = a.hStride;
   p.G = a.g;
   p.ldG = a.ldG;
   p.profile = getenv("MB2_TC_PROFILE") != nullptr ? atoi(getenv("MB2_TC_PROFILE")) : 0;
-  const size_t stageBytes = size_t(sh.boxRows) * kRowBytes * (p.passes == 3 ? 2 : 1);
+  const size_t stageBytes = size_t(sh.planeRows) * kRowBytes * (p.passes == 3 ? 2 : 1);
   int stages = int((196 * 1024) / stageBytes);
   if (stages > 6) stages = 6;
   if (stages < 2) return cudaErrorInvalidConfiguration;

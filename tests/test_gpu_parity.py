@@ -49,11 +49,16 @@ def test_humanoid_single_iteration():
 
 
 @pytest.mark.parametrize("mode,rtol", [(ms.JTJ_TF32X3, 2e-5), (ms.JTJ_TF32, 5e-3)])
-@pytest.mark.parametrize("case", ["humanoid", "chain22", "chain_all_families", "subset"])
+@pytest.mark.parametrize("case", ["humanoid", "chain22", "chain_all_families", "subset", "bodyhands", "bodyhands_subset"])
 def test_jtj_tensor_core_modes(case, mode, rtol):
     """tcgen05 JtJ (3xTF32 split: fp32-class; single TF32: ~1e-3) vs the float oracle's getJtJR."""
     enabled = None
-    if case == "humanoid":      # rows = 221 -> two 128-row M tiles, N = 128 / 224
+    if case.startswith("bodyhands"):  # cfg4 shape: 425 operand rows -> four row tiles, six work items (two with a separate A box), m = 600
+        ch, efs, theta0, theta_star = bodyhands_problem(5)
+        th = (theta0 + 0.3 * theta_star).astype(np.float32)
+        if case == "bodyhands_subset":
+            enabled = np.ones(ch.num_params, bool); enabled[[2, 130, 257, 300, 423]] = False
+    elif case == "humanoid":    # rows = 221 -> two 128-row M tiles, N = 128 / 224
         ch, efs, theta0, theta_star = humanoid_problem(37, orientation=True)
         th = (theta0 + 0.3 * theta_star).astype(np.float32)
     elif case == "chain22":     # rows = 30 -> one M tile, N = 32
@@ -73,6 +78,17 @@ def test_solve_with_tensor_core_jtj_matches_oracle():
     opts = ms.GaussNewtonSolverOptions(min_iterations=1, max_iterations=50, threshold=1.0, regularization=0.05, jtj_mode=ms.JTJ_TF32X3)
     out, worst = parity.check_solve(ch, efs, theta0, opts, instances=range(0, B, 7))
     print("max rel param diff (3xTF32 JtJ)", worst)
+
+
+def test_cfg4_solve_on_the_dense_tcgen05_jtj():
+    """BASELINE configs[3] "full JtJ tensor-core path": bodyhands300 (n = 424) with the dense tcgen05 JtJ (3xTF32) feeding the
+    tile-scheduled Cholesky, against the oracle and against the default tile-sparse path."""
+    ch, efs, theta0, _ = bodyhands_problem(8)
+    opts = ms.GaussNewtonSolverOptions(min_iterations=10, max_iterations=10, threshold=1.0, regularization=0.05, jtj_mode=ms.JTJ_TF32X3)
+    out, worst = parity.check_solve(ch, efs, theta0, opts, instances=range(0, 8, 3), param_tol=2e-4)
+    ref = ms.GaussNewtonSolver(ms.GaussNewtonSolverOptions(min_iterations=10, max_iterations=10, threshold=1.0, regularization=0.05), parity.build_function(ch, efs, 8)).solve(theta0)
+    assert np.all(out["status"] == 0) and np.max(np.abs(out["params"] - ref["params"])) <= 2e-3
+    print("cfg4 on the dense tcgen05 JtJ: max rel param diff vs oracle", worst)
 
 
 def test_plane_and_model_parameters_error_functions():
