@@ -43,14 +43,18 @@ size_t sweepSmemPerInstance(const FunctionTables& T, int warpsPerInstance) {
 // The read-only tables (character + plan) are walked by dependent loads (cell -> unit -> contributions -> joint);
 // from L2 each hop costs several hundred cycles, so a persistent CTA copies them into shared memory once.
 MB2_HD size_t tableWords(size_t count, size_t elemBytes) { return (count * elemBytes + 15) / 16 * 4; }
-size_t sweepTableBytes(const FunctionTables& T) {
+// mode 1: every table; mode 2: everything except the two big ones, cells and contributions (large rigs: those are streamed through
+// L1 / L2, one sequential record per lane and iteration, while the tables walked by dependent loads - character, units, error functions -
+// still sit in shared memory)
+size_t sweepTableBytes(const FunctionTables& T, int mode) {
+  if (mode == 0) return 0;
   const size_t J = T.numJoints;
   size_t w = 0;
   w += tableWords(J, 4) + tableWords(3 * J, 4) + tableWords(4 * J, 4);                       // parent, offset, prerot
   w += tableWords(7 * J + 1, 4) + tableWords(T.ptNnz, 4) * 2 + tableWords(7 * J, 4);         // ptOuter, ptInner, ptVals, ptOffsets
   w += tableWords(T.numLevels + 1, 4) + tableWords(J, 4);                                    // levelStart, levelJoints
-  w += tableWords(T.numEf, sizeof(EfDesc)) + tableWords(T.numUnits, sizeof(UnitDesc)) + tableWords(T.numCells, sizeof(CellDesc));
-  w += tableWords(T.numContribs, sizeof(ContribDesc)) + tableWords(T.numLimitData, 4);
+  w += tableWords(T.numEf, sizeof(EfDesc)) + tableWords(T.numUnits, sizeof(UnitDesc)) + tableWords(T.numLimitData, 4);
+  if (mode == 1) w += tableWords(T.numCells, sizeof(CellDesc)) + tableWords(T.numContribs, sizeof(ContribDesc));
   return w * 4;
 }
 
@@ -64,13 +68,13 @@ __device__ __forceinline__ void stageTable(const E*& table, size_t count, uint32
   cursor += tableWords(count, sizeof(E));
 }
 
-// kStaged: the tables live in shared memory for the whole kernel. A template parameter rather than a run-time branch so that every
+// kStage (1 all tables, 2 all but cells / contributions, 0 none): the tables live in shared memory for the whole kernel. A template parameter rather than a run-time branch so that every
 // table pointer is PROVABLY a shared-memory address: with `if (a.stageTables)` the pointers could be either and all 273 table loads
 // of the kernel were generic LD instructions (address-space check on every hop of the dependent chains cell -> unit -> record ->
 // contributions; 43 % of the warp-state samples were long-scoreboard waits on them, profiles/r02k).
 constexpr int kSweepMaxWarps = 24; // one warp per instance: up to 24 instances in flight per SM (85 registers per thread)
-template <bool kJacobian, int W, bool kStaged>
-__global__ void __launch_bounds__(W == 1 ? 32 * kSweepMaxWarps : 512) sweepKernel(const SweepArgs a) {
+template <bool kJacobian, int W, int kStage>
+__global__ void __launch_bounds__(32 * kSweepMaxWarps) sweepKernel(const SweepArgs a) {
   extern __shared__ __align__(16) float smem[];
   FunctionTables T = a.T;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -91,15 +95,15 @@ __global__ void __launch_bounds__(W == 1 ? 32 * kSweepMaxWarps : 512) sweepKerne
     if (W == 1) __syncwarp();
     else asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(gs) : "memory");
   };
-  if constexpr (kStaged) {
+  if constexpr (kStage != 0) {
     uint32_t* cursor = reinterpret_cast<uint32_t*>(smem + ((size_t(groupsPerCta) * perGroup + 3) & ~size_t(3)));
     const size_t J = T.numJoints;
     stageTable(T.parent, J, cursor); stageTable(T.offset, 3 * J, cursor); stageTable(T.prerot, 4 * J, cursor);
     stageTable(T.ptOuter, 7 * J + 1, cursor); stageTable(T.ptInner, T.ptNnz, cursor); stageTable(T.ptVals, T.ptNnz, cursor);
     stageTable(T.ptOffsets, 7 * J, cursor);
     stageTable(T.levelStart, T.numLevels + 1, cursor); stageTable(T.levelJoints, J, cursor);
-    stageTable(T.efs, T.numEf, cursor); stageTable(T.units, T.numUnits, cursor); stageTable(T.cells, T.numCells, cursor);
-    stageTable(T.contribs, T.numContribs, cursor); stageTable(T.limitData, T.numLimitData, cursor);
+    stageTable(T.efs, T.numEf, cursor); stageTable(T.units, T.numUnits, cursor); stageTable(T.limitData, T.numLimitData, cursor);
+    if constexpr (kStage == 1) { stageTable(T.cells, T.numCells, cursor); stageTable(T.contribs, T.numContribs, cursor); }
     __syncthreads();
   }
 
@@ -159,15 +163,16 @@ static int g_maxSmemPerSm = 0;
 
 cudaError_t launchSweep(const SweepArgs& a0, bool jacobian, cudaStream_t stream) {
   SweepArgs a = a0;
-  const size_t tableBytes = sweepTableBytes(a.T) + 16;
   const size_t budget = size_t(g_maxSmemOptin);
-  // Persistent CTAs. As many instances in flight as shared memory holds next to the staged tables (if those fit with at least two
-  // instances; else they stay in L2), one warp each, up to kSweepMaxWarps; when fewer than 16 fit, several warps share one instance.
+  // Persistent CTAs. As many instances in flight as shared memory holds next to the staged tables: all of them when they fit with at
+  // least two instances, else all but the cell / contribution records (large rigs), else none. One warp per instance, up to
+  // kSweepMaxWarps; when fewer than 16 instances fit, several warps share one instance (up to kSweepMaxWarps warps per CTA).
   const size_t per1 = sweepSmemPerInstance(a.T, 8);
-  a.stageTables = (2 * per1 + tableBytes <= budget) ? 1 : 0;
-  int groups = int((budget - (a.stageTables ? tableBytes : 0)) / per1);
+  a.stageTables = (2 * per1 + sweepTableBytes(a.T, 1) + 16 <= budget) ? 1 : (2 * per1 + sweepTableBytes(a.T, 2) + 16 <= budget) ? 2 : 0;
+  const size_t tableBytes = sweepTableBytes(a.T, a.stageTables) + 16;
+  int groups = int((budget - tableBytes) / per1);
   if (groups < 1) return cudaErrorInvalidConfiguration;
-  const int groupsOneWarp = int((budget - (a.stageTables ? tableBytes : 0)) / sweepSmemPerInstance(a.T, 1)); // (no joint-parameter array)
+  const int groupsOneWarp = int((budget - tableBytes) / sweepSmemPerInstance(a.T, 1)); // (no joint-parameter array)
   int W = 1;
   if (groupsOneWarp >= 16) {
     groups = groupsOneWarp;
@@ -178,12 +183,13 @@ cudaError_t launchSweep(const SweepArgs& a0, bool jacobian, cudaStream_t stream)
     const int rounds = (a.batch + sms * groups - 1) / (sms * groups);
     groups = std::max(std::min(groups, (a.batch + sms * rounds - 1) / (sms * rounds)), std::min(groups, 16));
   } else {
-    while (W < 8 && groups * W * 2 <= 16) W *= 2; // (at most 15 named barriers: groups <= 15 here)
+    if (groups > 15) groups = 15; // named barriers 1..15
+    while (W < 8 && groups * W * 2 <= kSweepMaxWarps) W *= 2; // these instances wait on L1 / L2 and on each other's barriers: as many warps as fit
   }
   a.warpsPerInstance = W;
   const int warps = groups * W;
   const size_t per = sweepSmemPerInstance(a.T, W);
-  const size_t smem = per * groups + 16 + (a.stageTables ? tableBytes : 0);
+  const size_t smem = per * groups + tableBytes;
   if (smem > budget) return cudaErrorInvalidConfiguration;
   const int ctasNeeded = (a.batch + groups - 1) / groups;
   int ctasPerSm = (int)((size_t(g_maxSmemPerSm)) / (smem + 1024));
@@ -199,7 +205,8 @@ cudaError_t launchSweep(const SweepArgs& a0, bool jacobian, cudaStream_t stream)
     return cudaGetLastError();
   };
   auto pick = [&](auto jac, auto staged) -> cudaError_t {
-    constexpr bool kJ = decltype(jac)::value, kS = decltype(staged)::value;
+    constexpr bool kJ = decltype(jac)::value;
+    constexpr int kS = decltype(staged)::value;
     switch (W) {
       case 1: return launch(sweepKernel<kJ, 1, kS>);
       case 2: return launch(sweepKernel<kJ, 2, kS>);
@@ -207,8 +214,14 @@ cudaError_t launchSweep(const SweepArgs& a0, bool jacobian, cudaStream_t stream)
       default: return launch(sweepKernel<kJ, 8, kS>);
     }
   };
-  if (jacobian) return a.stageTables ? pick(std::true_type{}, std::true_type{}) : pick(std::true_type{}, std::false_type{});
-  return a.stageTables ? pick(std::false_type{}, std::true_type{}) : pick(std::false_type{}, std::false_type{});
+  auto pickStage = [&](auto jac) -> cudaError_t {
+    switch (a.stageTables) {
+      case 1: return pick(jac, std::integral_constant<int, 1>{});
+      case 2: return pick(jac, std::integral_constant<int, 2>{});
+      default: return pick(jac, std::integral_constant<int, 0>{});
+    }
+  };
+  return jacobian ? pickStage(std::true_type{}) : pickStage(std::false_type{});
 }
 
 

@@ -19,7 +19,7 @@ struct SweepArgs {           // K1 (FK + residual + Jacobian) and K4 (FK + error
   double* errors;            // [B]
   const int32_t* active;     // optional per-instance mask
   float* stateOut;           // optional [B][J][8]
-  int32_t stageTables;       // set by launchSweep: copy the read-only tables into shared memory
+  int32_t stageTables;       // set by launchSweep: 1 every read-only table in shared memory, 2 all but cells / contributions, 0 none
   int32_t warpsPerInstance;  // set by launchSweep: 1, 2, 4 or 8 warps share one instance (large rigs: few instances fit in shared memory)
 };
 
