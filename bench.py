@@ -232,7 +232,7 @@ def measure_workload(ms, torch, workload, B, rank, local_rank, args, steps, warm
         solver.set_profiling(0)
     if e2e:
         theta0_pin = torch.from_numpy(theta0.astype(np.float32)).pin_memory()
-        n_e2e = max(1, warmup // 2) + steps
+        n_e2e = max(2, warmup // 2) + steps
         theta_pins = [theta0_pin.clone().pin_memory() for _ in range(n_e2e)]  # the solve is in place: one pinned in/out buffer per step
         target_pins = [torch.from_numpy(np.ascontiguousarray(e.targets, np.float32)).pin_memory() for e in efs]
         count = [0]
@@ -245,14 +245,18 @@ def measure_workload(ms, torch, workload, B, rank, local_rank, args, steps, warm
             solver.solve_host_pointer(buf.data_ptr())
             return solver.get_results()
 
-        for _ in range(max(1, warmup // 2)):
+        for _ in range(max(2, warmup // 2)):  # (the first call allocates the staging buffers: 20 - 30 ms)
             e2e_step()
         barrier()
+        step_s = []
         t0 = time.perf_counter()
         for _ in range(steps):
-            e2e_step()
+            t1 = time.perf_counter()
+            e2e_step()  # returns after the results are on the host (mb2_solver_solve + mb2_solver_get_results synchronise)
+            step_s.append(time.perf_counter() - t1)
         torch.cuda.synchronize()
         out["e2e_s"] = time.perf_counter() - t0
+        out["e2e_step_ms"] = [1e3 * x for x in step_s]
         out["h2d"] = int(theta0_pin.numel() * 4 + sum(tp.numel() * 4 for tp in target_pins))
         out["d2h"] = int(theta0_pin.numel() * 4 + B * (8 + 4 + 4))
     return out
@@ -484,7 +488,7 @@ def main():
         "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": bench_config(args, world),
         "solves_per_sec": value / ITERS, "aggregate_final_error": err_total,
-        "e2e": {"value": e2e_value, "unit": "GN it/s", "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"]},
+        "e2e": {"value": e2e_value, "unit": "GN it/s", "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"], "step_ms": [round(x, 3) for x in m["e2e_step_ms"]]},
         "gpu_launches": int(m["launches"]),
         "clocks": clocks,
         "roofline": dominant,
