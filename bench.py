@@ -70,9 +70,8 @@ def measured_traffic(workload, batch):
 
 class ClockSampler:
     """SM clock / clock-event reasons sampled DURING the timed regions (B200_PROFILING.md recipe). NVML is polled in-process
-    (the timed regions of the default run are ~45 ms each, shorter than one nvidia-smi start-up) every 25 ms: an NVML query takes the
-    driver lock, and polling every 5 ms slowed the end-to-end leg (which issues copies and launches from the host all the time) by 8 %
-    (measured: 8.40 / 9.05 / 9.16 M it/s at 5 / 25 / 100 ms; the device-resident figure does not move) - --clock-poll-ms changes it."""
+    (the timed regions of the default run are ~45 ms each, shorter than one nvidia-smi start-up) every 25 ms; the two queries take
+    microseconds (scripts/nvml_cost.py: median 3 us), --clock-poll-ms changes the period."""
 
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
 
