@@ -231,13 +231,18 @@ def measure_workload(ms, torch, workload, B, rank, local_rank, args, steps, warm
         solver.set_profiling(0)
     if e2e:
         theta0_pin = torch.from_numpy(theta0.astype(np.float32)).pin_memory()
-        n_e2e = max(2, warmup // 2) + steps
-        theta_pins = [theta0_pin.clone().pin_memory() for _ in range(n_e2e)]  # the solve is in place: one pinned in/out buffer per step
+        # Two long-lived pinned staging buffers used alternately, as a streaming caller keeps them: mb2_solver_solve uploads the buffer's
+        # parameters, solves in place and downloads the result into the same buffer. (Measured alternatives: a FRESH pinned buffer per step
+        # makes the 7.2 MB transfers 0.7 - 1.1 ms slower - the DMA path is slow on host pages it has not seen recently: 9.3 - 9.8 instead of
+        # 8.66 ms per step; refilling the idle buffer from the host while the device works costs more than it hides - the host memcpy fights
+        # the D2H for memory bandwidth and torch's copy threads stall for tens of ms now and then.) From its second use on a buffer holds the
+        # previous result of that buffer: with minIterations = maxIterations the work of a step does not depend on the starting point.
+        theta_pins = [theta0_pin.clone().pin_memory() for _ in range(2)]
         target_pins = [torch.from_numpy(np.ascontiguousarray(e.targets, np.float32)).pin_memory() for e in efs]
         count = [0]
 
         def e2e_step():
-            buf = theta_pins[count[0] % n_e2e]
+            buf = theta_pins[count[0] % 2]
             count[0] += 1
             for idx, tp in enumerate(target_pins):
                 fn._check(fn._L.mb2_set_targets(fn._h, idx, ms.C.cast(tp.data_ptr(), ms._fp)))

@@ -435,6 +435,18 @@ class GaussNewtonSolver(_Base):
         """Same through a raw (e.g. pinned) host pointer; results via get_results()."""
         self._check(self._L.mb2_solver_solve(self._h, C.c_void_p(host_ptr), None, None, None))
 
+    def solve_host_pointer_async(self, host_ptr: int):
+        """mb2_solver_solve_async: H2D of the parameters, the solve and the D2H of the result are enqueued on the handle's stream; the
+        (pinned) buffer belongs to the library until wait()."""
+        self._check(self._L.mb2_solver_solve_async(self._h, C.c_void_p(host_ptr)))
+
+    def wait(self):
+        """mb2_solver_wait: blocks until the asynchronous solve is done; per-instance results."""
+        B = self.fn.batch
+        err = np.zeros(B, np.float64); it = np.zeros(B, np.int32); st = np.zeros(B, np.int32)
+        self._check(self._L.mb2_solver_wait(self._h, err.ctypes.data_as(_dp), it.ctypes.data_as(_ip), st.ctypes.data_as(_ip)))
+        return {"errors": err, "iterations": it, "status": st}
+
     def solve_device(self, device_ptr: int, stream: int = 0):
         self._check(self._L.mb2_solver_solve_device(self._h, C.c_void_p(device_ptr), C.c_void_p(stream)))
 

@@ -59,3 +59,18 @@ for i in range(5):
     solver.get_results()
 torch.cuda.synchronize()
 print(f"{'e2e step as bench.py runs it':60s} {1e3 * (time.perf_counter() - t0) / 5:8.3f} ms")
+
+# kernels timed with CUDA events INSIDE the end-to-end call (profiling level 1): is the drift of the call on the device or on the host?
+solver.set_profiling(1)
+for i in range(8):
+    t0 = time.perf_counter()
+    solver.solve_host_pointer(bufs[i % 4].data_ptr())
+    wall = 1e3 * (time.perf_counter() - t0)
+    solver.get_results()
+    ms_, ln = solver.get_phase_times()
+    print(f"profiled e2e call {i}: wall {wall:.3f} ms, kernels (events) sweep {ms_[0]:.3f} + gram/chol {ms_[2]:.3f} = {ms_[0] + ms_[1] + ms_[2]:.3f} ms")
+solver.set_profiling(0)
+for i in range(12):
+    t0 = time.perf_counter()
+    solver.solve_host_pointer(bufs[i % 4].data_ptr())
+    print(f"plain e2e call {i}: wall {1e3 * (time.perf_counter() - t0):.3f} ms")
