@@ -407,6 +407,34 @@ def measure_mixed(ms, torch, args, local_rank, N, rank, steps=2):
             "padding_waste": st["padding_waste"], "largest_bucket": st["largest_bucket"], "per_rig": per_rig, "status_bad": int((out["status"] != 0).sum()), "ms_per_solve": 1e3 * dt / steps}
 
 
+def measure_sharded(ms, torch, args, B):
+    """Single-process multi-GPU (mb2_sharded_solver_*, ik_sharded.cpp): B instances per device, one host thread per shard, host buffers in
+    and out (pinned), aggregate on the host. Wall clock around mb2_sharded_solver_solve."""
+    N = args.sharded
+    ch, efs, theta0, _ = make_problem(args.workload, B * N)
+    proto = ms.SkeletonSolverFunction(ch, 1, efs, device=0)  # the definition only: targets go to the shards
+    opts = ms.GaussNewtonSolverOptions(min_iterations=ITERS, max_iterations=ITERS, threshold=1.0, regularization=0.05, jtj_mode=args.jtj_mode,
+                                       cholesky_mode=args.cholesky_mode, fused_mode=args.fused_mode)
+    sh = ms.ShardedGaussNewtonSolver(opts, proto, B * N, list(range(N)), error_functions=efs)
+    pins = [torch.from_numpy(theta0.astype(np.float32)).pin_memory() for _ in range(2)]
+    for i in range(max(2, args.warmup)):
+        sh.solve_host_pointer(pins[i % 2].data_ptr())
+    step_ms = []
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        t1 = time.perf_counter()
+        sh.solve_host_pointer(pins[i % 2].data_ptr())
+        step_ms.append(round(1e3 * (time.perf_counter() - t1), 3))
+    dt = time.perf_counter() - t0
+    agg = sh.get_aggregate()
+    value = agg["iterations"] * args.steps / dt
+    return {"metric": "GN iterations/sec (batched 72-joint IK)", "value": value, "unit": "GN it/s", "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "mode": "one process, mb2_sharded_solver_solve over host buffers (end to end by construction)", "config": bench_config(args, N),
+            "e2e": {"value": value, "unit": "GN it/s", "h2d_bytes_per_step": int(theta0.size * 4), "d2h_bytes_per_step": int(theta0.size * 4 + B * N * 16), "step_ms": step_ms},
+            "aggregate": agg, "shards": sh.shards()}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -419,6 +447,7 @@ def main():
     ap.add_argument("--cholesky-mode", type=int, default=0)
     ap.add_argument("--fused-mode", type=int, default=0)
     ap.add_argument("--strong", action="store_true", help="strong scaling: the workload's global batch (cfg3: 65536) is split over the ranks")
+    ap.add_argument("--sharded", type=int, default=0, help="ONE process driving this many GPUs through mb2_sharded_solver_* (end-to-end figure only; not the driver's torchrun mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--clock-poll-ms", type=float, default=25.0, help="NVML clock / throttle-reason sampling period during the timed regions")
     ap.add_argument("--no-extras", action="store_true", help="skip the other workloads measured in the same run (cfg2, cfg4, cfg5, convergence mode)")
@@ -454,6 +483,9 @@ def main():
         torch.cuda.synchronize()
 
     peaks = measured_peaks()
+    if args.sharded > 0:
+        print(json.dumps(measure_sharded(ms, torch, args, B)))
+        return
     if args.workload == "cfg5":
         r = measure_mixed(ms, torch, args, local_rank, B, rank, steps=args.steps)
         from momentum_b200.distributed import aggregate_solve_stats
