@@ -225,13 +225,13 @@ class OracleFunction:
         return xf, ra.reshape(J, 3, 3).transpose(0, 2, 1), ta.reshape(J, 3, 3).transpose(0, 2, 1)
 
     def solve(self, params, *, min_iterations=1, max_iterations=2, threshold=1.0, regularization=0.05, do_line_search=False,
-              use_block_jtj=False, subset_solver=False, qr_solver=False):
+              use_block_jtj=False, subset_solver=False, qr_solver=False, trust_region_qr=False):
         """GaussNewtonSolverT::solve. Returns (error, params, iterations, error_history)."""
         p = np.ascontiguousarray(params, np.float64).copy()
         hist = np.zeros(max(1, max_iterations), np.float64)
         it = C.c_int(0)
         err = self._L.orc_solve(self.fn, min_iterations, max_iterations, threshold, regularization, int(do_line_search), int(use_block_jtj),
-                              2 if qr_solver else int(subset_solver), p.ctypes.data_as(_dp), C.byref(it), hist.ctypes.data_as(_dp))
+                              3 if trust_region_qr else (2 if qr_solver else int(subset_solver)), p.ctypes.data_as(_dp), C.byref(it), hist.ctypes.data_as(_dp))
         return err, p, it.value, hist[: it.value].copy()
 
     def solve_batch(self, params, *, threads=1, min_iterations=1, max_iterations=2, threshold=1.0, regularization=0.05,

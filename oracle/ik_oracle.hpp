@@ -1225,6 +1225,8 @@ struct GaussNewtonOptions {
   bool useBlockJtJ{false};
   bool subsetSolver{false}; // SubsetGaussNewtonSolverT semantics (line search c1=1e-4 w/ gradient)
   bool qrSolver{false};     // GaussNewtonSolverQRT: the step from an online Householder QR of [sqrt(lambda) I; J] (gauss_newton_solver_qr.cpp:50-150)
+  bool trustRegionQr{false}; // TrustRegionQRT (trust_region_qr.cpp:52-270): QR of J, Newton search for the damping that keeps the step inside the radius
+  float trustRegionRadius{1.0f}; // TrustRegionQROptions::trustRegionRadius_ (trust_region_qr.h:23)
 };
 
 // math/online_householder_qr.cpp:20-243 — OnlineHouseholderQR<T>: R starts as lambda * I (the caller passes sqrt of the damping), every
@@ -1349,7 +1351,90 @@ struct GaussNewtonSolver {
       alpha *= 0.5f;
     }
   }
+  // character_solver/trust_region_qr.cpp:52-270. Arithmetic in T except where the reference mixes in the double error_.
+  T curTrustRegionRadius{1}, maxTrustRegionRadius{10}; // trust_region_qr.h:73-74; initializeSolver (:38-40) resets the current radius
+  void doIterationTrustRegionQR() {
+    const int n = fn->numParameters;
+    const int ns = int(enabled.size());
+    fn->updateState(parameters.data()); // :57-60 skeletonState_.set(...)
+    T lambda = T(1e-10); // :81-82 "a tiny lambda just to make sure we don't divide by zero"
+    OnlineHouseholderQR<T> qr;
+    qr.reset(ns, lambda);
+    double errorOrig = 0.0;
+    Mat<T> jac;
+    std::vector<T> res;
+    for (size_t b = 0; b < fn->getJacobianBlockCount(); ++b) { // :86-110, one block per error function with weight > 0
+      const int bs = fn->getJacobianBlockSize(b);
+      if (bs == 0) continue;
+      const int rows = padToSimdAlignment(bs);
+      jac.resizeAndSetZero(rows, n);
+      res.assign(rows, T(0));
+      int used = 0;
+      errorOrig += fn->computeJacobianBlock(parameters.data(), b, jac, 0, res.data(), used);
+      if (used == 0) continue;
+      std::vector<T> A(size_t(used) * ns);
+      for (int a = 0; a < ns; ++a) for (int k = 0; k < used; ++k) A[size_t(a) * used + k] = jac(k, enabled[a]);
+      qr.addMutating(A.data(), used, used, res.data());
+    }
+    error = errorOrig;
+    std::vector<T> grad = qr.AtTimesB(); // :116 gradientSub_ = 2 * At_times_b()
+    for (T& v : grad) v *= T(2);
+    const std::vector<T> Rsaved = qr.R; // :119
+    auto dotT = [&](const std::vector<T>& a, const std::vector<T>& b) { T s = 0; for (int i = 0; i < ns; ++i) s += a[i] * b[i]; return s; };
+    auto evalQuadraticModel = [&](const std::vector<T>& p) { // :133-140
+      T result = T(error);
+      result -= dotT(grad, p);
+      T sq = 0;
+      for (int i = 0; i < ns; ++i) { T r = 0; for (int j = i; j < ns; ++j) r += Rsaved[size_t(i) * ns + j] * p[j]; sq += r * r; }
+      result += sq;
+      return result;
+    };
+    auto solveUpper = [&](const std::vector<T>& R, std::vector<T> b) { // R x = b
+      for (int i = ns - 1; i >= 0; --i) { T s = b[i]; for (int k = i + 1; k < ns; ++k) s -= R[size_t(i) * ns + k] * b[k]; b[i] = s / R[size_t(i) * ns + i]; }
+      return b;
+    };
+    auto solveUpperTransposed = [&](const std::vector<T>& R, std::vector<T> b) { // R^T x = b
+      for (int i = 0; i < ns; ++i) { T s = b[i]; for (int k = 0; k < i; ++k) s -= R[size_t(k) * ns + i] * b[k]; b[i] = s / R[size_t(i) * ns + i]; }
+      return b;
+    };
+    const T nu = 0; // :153
+    for (size_t iTrustStep = 0; iTrustStep < 10; ++iTrustStep) {
+      std::vector<T> dir = qr.result();
+      if (double(dotT(dir, grad)) < double(std::numeric_limits<float>::epsilon() * (T(1.0) + error))) break; // :162-164 (FLT_EPSILON * (T(1) + double error_))
+      for (size_t iIter = 0; iIter < 3; ++iIter) { // :180-236 Newton iteration on lambda (Nocedal & Wright 4.3), lambda only grows
+        if (std::sqrt(dotT(dir, dir)) < T(1.05) * curTrustRegionRadius) break;
+        std::vector<T> mhg(ns);
+        for (int i = 0; i < ns; ++i) mhg[i] = -T(0.5) * grad[i];
+        const std::vector<T> pl = solveUpper(qr.R, solveUpperTransposed(qr.R, mhg));
+        const std::vector<T> ql = solveUpperTransposed(qr.R, pl);
+        const T pl2 = dotT(pl, pl), ql2 = dotT(ql, ql);
+        if (ql2 < std::numeric_limits<float>::epsilon()) break;
+        const T plNorm = std::sqrt(pl2);
+        const T deltaLambda = (pl2 / ql2) * ((plNorm - curTrustRegionRadius) / curTrustRegionRadius);
+        if (deltaLambda <= 0) break;
+        const T lambdaNew = lambda + deltaLambda;
+        const T yv = std::sqrt(lambdaNew - lambda);
+        std::vector<T> D(size_t(ns) * ns, T(0)), zero(ns, T(0)); // :214-222 lambdaDiag_ = y I as ns extra rows, right-hand side 0
+        for (int i = 0; i < ns; ++i) D[size_t(i) * ns + i] = yv;
+        qr.addMutating(D.data(), ns, ns, zero.data());
+        lambda = lambdaNew;
+        dir = qr.result();
+      }
+      const std::vector<T> orig = parameters;
+      std::vector<T> full(n, T(0)); // subsetToFullVector :142-150
+      for (int a = 0; a < ns; ++a) full[enabled[a]] = dir[a];
+      fn->updateParameters(parameters, full);
+      const double errorNew = fn->getError(parameters.data());
+      const T model = evalQuadraticModel(dir);
+      const T rho = T((error - errorNew) / (error - double(model))); // :249 (double - double) / (double - T)
+      if (rho < T(0.25)) curTrustRegionRadius = T(0.25) * curTrustRegionRadius;
+      else if (rho > T(0.75) && lambda > 0) curTrustRegionRadius = std::min(T(2) * curTrustRegionRadius, maxTrustRegionRadius);
+      if (rho > nu) break;
+      parameters = orig; // reject the step, the radius has shrunk: try again
+    }
+  }
   void doIteration() { // gauss_newton_solver.cpp:224-280
+    if (opt.trustRegionQr) { doIterationTrustRegionQR(); return; }
     if (opt.qrSolver) { doIterationQR(); return; }
     const int n = fn->numParameters;
     const int ns = int(enabled.size());
@@ -1422,6 +1507,7 @@ struct GaussNewtonSolver {
     errorHistory.clear();
     parameters = params;
     error = lastError = std::numeric_limits<double>::max();
+    curTrustRegionRadius = T(opt.trustRegionRadius); // TrustRegionQRT::initializeSolver (trust_region_qr.cpp:38-40)
     enabled.clear(); // gauss_newton_solver.cpp:57-66
     for (int i = 0; i < fn->numParameters; ++i) if (activeParameters[i]) enabled.push_back(i);
     for (iteration = 0; iteration < opt.maxIterations; ++iteration) {

@@ -127,8 +127,9 @@ double solveOne(SkeletonSolverFunction<T>& fn, const std::vector<uint8_t>* enabl
   go.regularization = float(o.regularization);
   go.doLineSearch = o.doLineSearch != 0;
   go.useBlockJtJ = o.useBlockJtJ != 0;
-  go.subsetSolver = o.subsetSolver == 1; // 0 GaussNewtonSolverT, 1 SubsetGaussNewtonSolverT, 2 GaussNewtonSolverQRT
+  go.subsetSolver = o.subsetSolver == 1; // 0 GaussNewtonSolverT, 1 SubsetGaussNewtonSolverT, 2 GaussNewtonSolverQRT, 3 TrustRegionQRT
   go.qrSolver = o.subsetSolver == 2;
+  go.trustRegionQr = o.subsetSolver == 3;
   GaussNewtonSolver<T> solver(go, &fn);
   if (enabled) solver.setEnabledParameters(*enabled);
   std::vector<T> p = narrow<T>(params, fn.numParameters);

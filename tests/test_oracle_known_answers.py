@@ -229,3 +229,56 @@ def test_ka10_gauss_newton_qr_takes_the_same_step_as_the_normal_equations():
                     res.append(orc.solve(theta0[b], min_iterations=5, max_iterations=5, threshold=1.0, regularization=0.05, do_line_search=ls, **kw))
                 (e0, p0, _, h0), (e1, p1, _, h1) = res
                 assert np.max(np.abs(p0 - p1)) < 1e-8 and abs(e0 - e1) < 1e-9 * max(1.0, abs(e0)) and np.allclose(h0, h1, rtol=1e-9)
+
+
+# ---- KA-11: TrustRegionQRT (second half) -----------------------------------------------------------------------------
+def test_ka11_trust_region_qr_does_at_least_as_well_as_gauss_newton():
+    """momentum/test/character_solver/solver_test.cpp:131-233 (TrustRegionTest.PerfectQuadratic / SanityCheck), float and double: on the test
+    character, ten random frames each, the trust-region solver ends at err_tr <= 1.001 err_gn + 0.001 with test::defaultSolverOptions
+    (min 4 / max 40 iterations, threshold 1000; solver_test_helpers.h:16-23); the final error is getError at the solution (:44)."""
+    from momentum_b200 import character as mc
+    from oracle.binding import OracleFunction
+
+    ch = mc.create_test_character()
+    n, J = ch.num_params, ch.num_joints
+    kw = dict(min_iterations=4, max_iterations=40, threshold=1000.0)
+    for dtype in ("float32", "float64"):
+        rng = np.random.default_rng(12345)
+        for frame in range(10):
+            # PerfectQuadratic: one ModelParametersErrorFunction with random targets and |random| weights
+            target = rng.uniform(-1, 1, n); w = np.abs(rng.uniform(-1, 1, n))
+            mp = [mc.ModelParametersErrorFunction(w, target[None], weight=1.0)]
+            # SanityCheck: a Position and an Orientation constraint on every joint at a random pose
+            pose = rng.uniform(-1, 1, (1, n))
+            joints = np.arange(J, dtype=np.int32)
+            tpos = mc.world_points(ch, pose, joints, np.zeros((J, 3)))
+            ident = np.tile([0.0, 0.0, 0.0, 1.0], (J, 1))
+            trot = mc.world_rotations(ch, pose, joints, ident)
+            efs_sets = [mp, [mc.PositionErrorFunction(joints, np.zeros((J, 3)), np.ones(J), tpos, weight=1.0),
+                             mc.OrientationErrorFunction(joints, ident, np.ones(J), trot, weight=1.0)]]
+            for efs in efs_sets:
+                final = {}
+                for name, opt in (("tr", dict(trust_region_qr=True)), ("gn", dict(regularization=0.05, use_block_jtj=True)), ("qr", dict(regularization=0.05, qr_solver=True))):
+                    orc = OracleFunction(ch, efs, dtype)
+                    _, p, it, hist = orc.solve(np.zeros(n), **kw, **opt)
+                    assert np.all(np.isfinite(p)) and 4 <= it <= 40
+                    final[name] = orc.get_error(p)
+                assert final["tr"] <= 1.001 * final["gn"] + 0.001, (dtype, frame, final)
+                assert final["qr"] <= 1.001 * final["gn"] + 0.001, (dtype, frame, final)
+
+
+def test_ka11_trust_region_radius_adapts_and_rejected_steps_restore_the_parameters():
+    """The mechanics of trust_region_qr.cpp:155-267 on a problem whose Gauss-Newton step overshoots (a chain far from its targets): the
+    error history never increases by more than rounding (a step with rho <= 0 is rejected and the parameters restored), and the first step
+    is no longer than 1.05 x the radius once the damping search has converged."""
+    from momentum_b200.problems import chain_problem
+    from oracle.binding import OracleFunction
+
+    ch, efs, theta0, _ = chain_problem(J=8, B=1, seed=5, families=("position",))
+    orc = OracleFunction(ch, efs, "float64", instance=0)
+    e, p, it, hist = orc.solve(theta0[0], min_iterations=6, max_iterations=6, threshold=1.0, trust_region_qr=True)
+    assert all(hist[i + 1] <= hist[i] * (1 + 1e-9) + 1e-12 for i in range(len(hist) - 1)), hist
+    # the damping search shortens the undamped Gauss-Newton step towards the radius (three Newton iterations at most: it may stop short of it)
+    e1, p1, _, _ = orc.solve(theta0[0], min_iterations=1, max_iterations=1, threshold=1.0, trust_region_qr=True)
+    e2, p2, _, _ = orc.solve(theta0[0], min_iterations=1, max_iterations=1, threshold=1.0, regularization=1e-20, qr_solver=True)
+    assert 1.0 < np.linalg.norm(p2 - theta0[0]) and np.linalg.norm(p1 - theta0[0]) < np.linalg.norm(p2 - theta0[0])
