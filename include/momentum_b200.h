@@ -129,7 +129,11 @@ typedef enum mb2_fused_mode {
  * tracker; same step up to rounding without squaring the condition number; its line search is the c1 = 1e-4 / g.delta rule (:116-143). */
 typedef enum mb2_linear_solver {
   MB2_LINEAR_SOLVER_CHOLESKY = 0,
-  MB2_LINEAR_SOLVER_QR = 1
+  MB2_LINEAR_SOLVER_QR = 1,
+  /* TrustRegionQRT (character_solver/trust_region_qr.cpp:52-270; LinearSolverType::TrustRegionQR of pymomentum's solve_ik): QR of the
+   * Jacobian, a Newton search for the damping that keeps the step inside the trust region, rho-driven radius, steps with rho <= 0 rejected.
+   * regularization, do_line_search and use_block_jtj do not apply (the reference's class takes plain SolverOptions + the radius). */
+  MB2_LINEAR_SOLVER_TRUST_REGION_QR = 2
 } mb2_linear_solver;
 
 /* solver/solver.h:19-34 SolverOptions + solver/gauss_newton_solver.h:17-59 GaussNewtonSolverOptions,
@@ -149,6 +153,7 @@ typedef struct mb2_gauss_newton_options {
   int32_t cholesky_mode;          /* mb2_cholesky_mode */
   int32_t fused_mode;             /* mb2_fused_mode */
   int32_t linear_solver;          /* mb2_linear_solver */
+  float trust_region_radius;      /* TrustRegionQROptions::trustRegionRadius_ = 1.0f (trust_region_qr.h:23); MB2_LINEAR_SOLVER_TRUST_REGION_QR only */
 } mb2_gauss_newton_options;
 
 typedef struct mb2_character mb2_character;             /* Skeleton + ParameterTransform + ParameterLimits on device */

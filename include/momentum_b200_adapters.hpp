@@ -55,7 +55,8 @@ struct GaussNewtonSolverOptions { // solver.h:19-34 + gauss_newton_solver.h:17-5
   mb2_jtj_mode jtjMode = MB2_JTJ_AUTO;
   mb2_cholesky_mode choleskyMode = MB2_CHOLESKY_AUTO;
   mb2_fused_mode fusedMode = MB2_FUSED_AUTO;
-  mb2_linear_solver linearSolver = MB2_LINEAR_SOLVER_CHOLESKY; // MB2_LINEAR_SOLVER_QR: GaussNewtonSolverQRT's step
+  mb2_linear_solver linearSolver = MB2_LINEAR_SOLVER_CHOLESKY; // MB2_LINEAR_SOLVER_QR: GaussNewtonSolverQRT's step; MB2_LINEAR_SOLVER_TRUST_REGION_QR: TrustRegionQRT
+  float trustRegionRadius = 1.0f;                              // TrustRegionQROptions::trustRegionRadius_ (trust_region_qr.h:23)
   bool storeErrorHistory = false;
 
   mb2_gauss_newton_options c() const {
@@ -74,6 +75,7 @@ struct GaussNewtonSolverOptions { // solver.h:19-34 + gauss_newton_solver.h:17-5
     o.cholesky_mode = choleskyMode;
     o.fused_mode = fusedMode;
     o.linear_solver = linearSolver;
+    o.trust_region_radius = trustRegionRadius;
     o.store_error_history = storeErrorHistory;
     return o;
   }

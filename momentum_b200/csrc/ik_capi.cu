@@ -160,7 +160,7 @@ struct PhaseEvent {
 struct mb2_solver {
   mb2_solver_function* fn{nullptr};
   mb2_gauss_newton_options opt{};
-  DeviceBuffer<float> dH, dDelta, dThetaOrig, dTheta0, dScale, dGradDotDelta, dThetaStage, dGrad, dTiles;
+  DeviceBuffer<float> dH, dDelta, dThetaOrig, dTheta0, dScale, dGradDotDelta, dThetaStage, dGrad, dTiles, dRadius, dRSaved;
   DeviceBuffer<double> dLastErrors, dTrialErrors, dHistory;
   DeviceBuffer<int32_t> dActive, dIterations, dStatus, dSearching, dActiveCount, dWorkCounter, dQrChunks;
   DeviceBuffer<unsigned long long> dPhaseCycles;
@@ -565,6 +565,7 @@ void mb2_default_gauss_newton_options(mb2_gauss_newton_options* o) {
   o->cholesky_mode = MB2_CHOLESKY_AUTO;
   o->fused_mode = MB2_FUSED_AUTO;
   o->linear_solver = MB2_LINEAR_SOLVER_CHOLESKY;
+  o->trust_region_radius = 1.0f; // trust_region_qr.h:23
 }
 
 int mb2_character_create(int device, int32_t J, const int32_t* parents, const float* offsets, const float* prerot, int32_t n,
@@ -1052,7 +1053,10 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
   for (uint8_t e : f->enabled) numEnabled += e ? 1 : 0;
   int cholMode = o.cholesky_mode;
   if (cholMode == 0) cholMode = numEnabled >= 48 ? 3 : 1;
-  const bool useQr = o.linear_solver == MB2_LINEAR_SOLVER_QR; // GaussNewtonSolverQRT's step: Householder QR of the K-major Jacobian (ik_qr.cuh)
+  // GaussNewtonSolverQRT's step: Householder QR of the K-major Jacobian (ik_qr.cuh); TrustRegionQRT's iteration builds on the same fold (ik_tr_qr.cuh)
+  const bool useTr = o.linear_solver == MB2_LINEAR_SOLVER_TRUST_REGION_QR;
+  const bool useQr = o.linear_solver == MB2_LINEAR_SOLVER_QR || useTr;
+  if (useTr && !(o.trust_region_radius > 0.f)) return fail(MB2_ERR_INVALID_ARGUMENT, "trust_region_radius must be positive");
   if (useQr) {
     if (o.jtj_mode == MB2_JTJ_SPARSE_TILES || o.cholesky_mode >= 2 || o.fused_mode >= MB2_FUSED_PERSISTENT)
       return fail(MB2_ERR_UNSUPPORTED, "the QR step works on the dense Jacobian: it excludes the tile-sparse Gram, the tile Cholesky and the fused kernels");
@@ -1185,6 +1189,11 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
   if (useQr) { // row chunks: one per error-function block (the reference adds block by block), split when a block does not fit beside R
     qrMaxRows = qrMaxChunkRows(ns, size_t(200 * 1024));
     if (qrMaxRows < 8) return fail(MB2_ERR_UNSUPPORTED, "the QR step keeps R in shared memory: too many enabled parameters for this kernel");
+    if (useTr) { // R and the damping rows D (both packed triangles) + the in-kernel getError scratch; the Jacobian chunk shares D's storage
+      qrMaxRows = std::min(qrMaxRows, std::max(8, ns / 2));
+      if (trQrSmemFloats(ns, n, f->ch->host.numJoints, qrMaxRows) * sizeof(float) > size_t(220 * 1024))
+        return fail(MB2_ERR_UNSUPPORTED, "the trust-region QR kernel keeps R and the damping rows in shared memory: too many enabled parameters / joints");
+    }
     std::vector<int32_t> starts{0};
     int r0 = 0, widest = 0;
     for (const auto& ef : f->efs) {
@@ -1196,6 +1205,10 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
     qrChunks = int(starts.size()) - 1;
     qrMaxRows = std::max(widest, 1);
     MB2_CUDA(s->dQrChunks.upload(starts, st));
+    if (useTr) { // TrustRegionQRT::initializeSolver (trust_region_qr.cpp:38-40): the current radius starts at the option's value
+      MB2_CUDA(s->dRadius.upload(std::vector<float>(size_t(B), o.trust_region_radius), st));
+      MB2_CUDA(s->dRSaved.resize(size_t(B) * ((size_t(ns) * (ns + 1) / 2 + 3) & ~size_t(3))));
+    }
   }
   float* Hbuf = s->dH.p;
   const size_t tilesStride = useGram ? size_t(f->sched->host.numTiles) * 256 + f->sched->host.nPad : 0;
@@ -1209,7 +1222,7 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
   MB2_CUDA(s->dIterations.resize(B));
   MB2_CUDA(s->dStatus.resize(B));
   MB2_CUDA(s->dActiveCount.resize(1));
-  const bool lineSearch = o.do_line_search != 0;
+  const bool lineSearch = o.do_line_search != 0 && !useTr; // (TrustRegionQRT has no line search: steps are accepted or rejected by rho)
   if (lineSearch) {
     MB2_CUDA(s->dThetaOrig.resize(size_t(B) * n));
     MB2_CUDA(s->dTrialErrors.resize(B));
@@ -1310,7 +1323,20 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
       q.ldJ = f->ldJ;
       q.chunkStart = s->dQrChunks.p;
       q.numChunks = qrChunks;
-      MB2_CUDA(launchQrSolve(q, qrMaxRows, st));
+      if (useTr) {
+        TrQrArgs t{};
+        t.q = q;
+        t.T = f->tables();
+        t.targets = f->dTargets.p;
+        t.cweights = f->dWeights.p;
+        t.radius = s->dRadius.p;
+        t.rSaved = s->dRSaved.p;
+        t.maxRadius = 10.f; // trust_region_qr.h:73
+        t.maxChunkRows = qrMaxRows;
+        MB2_CUDA(launchTrustRegionQr(t, st));
+      } else {
+        MB2_CUDA(launchQrSolve(q, qrMaxRows, st));
+      }
     } else if (useGramChol) {
       GramCholArgs gc{};
       gc.g = g;

@@ -847,6 +847,7 @@ cudaError_t launchGramCholesky(const GramCholArgs& a, const CholSchedDev& sched,
 
 } // namespace mb2
 #include "ik_qr.cuh"
+#include "ik_tr_qr.cuh"
 namespace mb2 {
 
 cudaError_t initKernelAttributes() {

@@ -103,6 +103,19 @@ struct QrArgs {
   const int32_t* chunkStart; // [numChunks + 1] first row of every chunk (device memory); a chunk never crosses an error-function block
   int32_t numChunks;
 };
+// TrustRegionQRT's iteration (ik_tr_qr.cuh): the QR arguments plus what getError needs inside the kernel and the solver's radius state
+struct TrQrArgs {
+  QrArgs q;
+  FunctionTables T;
+  const float* targets;
+  const float* cweights;
+  float* radius;      // [B] curTrustRegionRadius_ (in / out)
+  float* rSaved;      // [B][packed upper triangle, rounded up to 4 floats] scratch for Rmatrix_
+  float maxRadius;    // maxTrustRegionRadius_ = 10 (trust_region_qr.h:73)
+  int32_t maxChunkRows;
+};
+size_t trQrSmemFloats(int n, int numParams, int numJoints, int maxChunkRows);
+cudaError_t launchTrustRegionQr(const TrQrArgs& a, cudaStream_t stream);
 size_t qrSmemFloats(int n, int maxChunkRows);
 int qrMaxChunkRows(int n, size_t smemBytes); // rows of Jacobian that fit beside R (0: the system is too large for this kernel)
 cudaError_t launchQrSolve(const QrArgs& a, int maxChunkRows, cudaStream_t stream);

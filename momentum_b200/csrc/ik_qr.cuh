@@ -20,24 +20,13 @@ constexpr int kQrThreads = 256;
 
 __device__ __forceinline__ int qrRowOffset(int i, int n) { return i * n - (i * (i - 1)) / 2 - i; } // R(i, j), j >= i, at offset + j
 
-template <bool kUnused>
-__global__ void __launch_bounds__(kQrThreads, 1) qrSolveKernel(const QrArgs a) {
-  extern __shared__ __align__(16) float qrSmem[];
-  const CholArgs& c = a.c;
-  const int b = blockIdx.x;
-  if (c.active[b] == 0) return;
-  const int n = c.ns, tid = threadIdx.x, lane = tid & 31;
-  float* R = qrSmem;                                  // packed upper triangle, row-major
-  float* y = R + (size_t(n) * (n + 1) / 2 + 3 & ~size_t(3));
-  float* x = y + ((n + 3) & ~3);
-  float* g = x + ((n + 3) & ~3);
-  float* norms = g + ((n + 3) & ~3);                  // [n + 1] squared norms of the chunk's columns (column n = right-hand side)
-  float* As = norms + ((n + 4) & ~3);                 // [n + 1][ps] the chunk, column-major, odd stride
-  const float sqrtLambda = sqrtf(c.regularization);   // "the QR solver wants the square root of that lambda" (:74-76)
+// R = diag0 I, y = 0, then every row chunk of instance b's Jacobian folded in by Householder reflectors (see the file header). Block-wide.
+__device__ void qrFoldJacobian(const QrArgs& a, int b, float* R, float* y, float* norms, float* As, int n, float diag0) {
+  const int tid = threadIdx.x;
   for (int idx = tid; idx < n * (n + 1) / 2; idx += kQrThreads) R[idx] = 0.f;
   for (int i = tid; i < n; i += kQrThreads) y[i] = 0.f;
   __syncthreads();
-  for (int i = tid; i < n; i += kQrThreads) R[qrRowOffset(i, n) + i] = sqrtLambda;
+  for (int i = tid; i < n; i += kQrThreads) R[qrRowOffset(i, n) + i] = diag0;
   const float* Jg = a.jacobian + size_t(b) * size_t(a.numCols + 1) * a.ldJ;
   for (int ch = 0; ch < a.numChunks; ++ch) {
     const int r0 = a.chunkStart[ch], p = a.chunkStart[ch + 1] - r0, ps = p | 1;
@@ -82,18 +71,47 @@ __global__ void __launch_bounds__(kQrThreads, 1) qrSolveKernel(const QrArgs a) {
       if (tid == 0) R[ro + i] = mu;
     }
   }
-  __syncthreads();
-  // R x = y, one warp: row dot products over lanes (a zero pivot with a zero numerator gives 0 like Eigen's triangular solve, :235-243)
-  if (tid < 32) {
-    for (int i = n - 1; i >= 0; --i) {
-      const int ro = qrRowOffset(i, n);
-      float s = 0.f;
-      for (int k = i + 1 + lane; k < n; k += 32) s = fmaf(R[ro + k], x[k], s);
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) { const float num = y[i] - s, d = R[ro + i]; x[i] = (d == 0.f && num == 0.f) ? 0.f : num / d; }
-      __syncwarp();
-    }
+}
+// R x = rhs by one warp (lanes over the row's dot product); a zero pivot with a zero numerator gives 0 like Eigen's triangular solve
+// (online_householder_qr.cpp:235-243). x may alias rhs. Call from warp 0 only.
+__device__ void qrSolveUpperWarp(const float* R, const float* rhs, float* x, int n, int lane) {
+  for (int i = n - 1; i >= 0; --i) {
+    const int ro = qrRowOffset(i, n);
+    float s = 0.f;
+    for (int k = i + 1 + lane; k < n; k += 32) s = fmaf(R[ro + k], x[k], s);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) { const float num = rhs[i] - s, d = R[ro + i]; x[i] = (d == 0.f && num == 0.f) ? 0.f : num / d; }
+    __syncwarp();
   }
+}
+// R^T x = rhs by one warp. x may alias rhs.
+__device__ void qrSolveUpperTransposedWarp(const float* R, const float* rhs, float* x, int n, int lane) {
+  for (int i = 0; i < n; ++i) {
+    float s = 0.f;
+    for (int k = lane; k < i; k += 32) s = fmaf(R[qrRowOffset(k, n) + i], x[k], s);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) x[i] = (rhs[i] - s) / R[qrRowOffset(i, n) + i];
+    __syncwarp();
+  }
+}
+
+template <bool kUnused>
+__global__ void __launch_bounds__(kQrThreads, 1) qrSolveKernel(const QrArgs a) {
+  extern __shared__ __align__(16) float qrSmem[];
+  const CholArgs& c = a.c;
+  const int b = blockIdx.x;
+  if (c.active[b] == 0) return;
+  const int n = c.ns, tid = threadIdx.x, lane = tid & 31;
+  float* R = qrSmem;                                  // packed upper triangle, row-major
+  float* y = R + (size_t(n) * (n + 1) / 2 + 3 & ~size_t(3));
+  float* x = y + ((n + 3) & ~3);
+  float* g = x + ((n + 3) & ~3);
+  float* norms = g + ((n + 3) & ~3);                  // [n + 1] squared norms of the chunk's columns (column n = right-hand side)
+  float* As = norms + ((n + 4) & ~3);                 // [n + 1][ps] the chunk, column-major, odd stride
+  const float sqrtLambda = sqrtf(c.regularization);   // "the QR solver wants the square root of that lambda" (:74-76)
+  qrFoldJacobian(a, b, R, y, norms, As, n, sqrtLambda);
+  __syncthreads();
+  if (tid < 32) qrSolveUpperWarp(R, y, x, n, lane); // R x = y
   // g = R^T y = J^T r (At_times_b, :224-232)
   for (int j = tid; j < n; j += kQrThreads) {
     float s = 0.f;

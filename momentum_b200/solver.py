@@ -29,7 +29,7 @@ INSTANCE_OK, INSTANCE_CHOLESKY_BREAKDOWN, INSTANCE_NON_FINITE = 0, 1, 2
 CHOLESKY_AUTO, CHOLESKY_DENSE_EIGEN, CHOLESKY_TILES_DENSE, CHOLESKY_TILES_SPARSE = 0, 1, 2, 3
 FUSED_AUTO, FUSED_OFF, FUSED_PERSISTENT, FUSED_GRAM_CHOLESKY = 0, 1, 2, 3
 FUSED_ON = FUSED_PERSISTENT
-LINEAR_SOLVER_CHOLESKY, LINEAR_SOLVER_QR = 0, 1
+LINEAR_SOLVER_CHOLESKY, LINEAR_SOLVER_QR, LINEAR_SOLVER_TRUST_REGION_QR = 0, 1, 2
 
 
 class MomentumB200Error(RuntimeError):
@@ -44,7 +44,8 @@ class _Options(C.Structure):
     _fields_ = [("min_iterations", C.c_uint64), ("max_iterations", C.c_uint64), ("threshold", C.c_float), ("verbose", C.c_int32),
                 ("regularization", C.c_float), ("do_line_search", C.c_int32), ("use_block_jtj", C.c_int32),
                 ("target_rows_per_chunk", C.c_uint64), ("subset_line_search", C.c_int32), ("jtj_mode", C.c_int32),
-                ("store_error_history", C.c_int32), ("cholesky_mode", C.c_int32), ("fused_mode", C.c_int32), ("linear_solver", C.c_int32)]
+                ("store_error_history", C.c_int32), ("cholesky_mode", C.c_int32), ("fused_mode", C.c_int32), ("linear_solver", C.c_int32),
+                ("trust_region_radius", C.c_float)]
 
 
 _fp = C.POINTER(C.c_float)
@@ -209,12 +210,14 @@ class GaussNewtonSolverOptions(SolverOptions):
     store_error_history: bool = False
     cholesky_mode: int = 0  # CHOLESKY_AUTO
     fused_mode: int = 0     # FUSED_AUTO: Gram + Cholesky in one launch per iteration when the plan fits (momentum_b200.h mb2_fused_mode)
-    linear_solver: int = 0  # LINEAR_SOLVER_CHOLESKY; LINEAR_SOLVER_QR = GaussNewtonSolverQRT's Householder step
+    linear_solver: int = 0  # LINEAR_SOLVER_CHOLESKY; LINEAR_SOLVER_QR = GaussNewtonSolverQRT's Householder step; LINEAR_SOLVER_TRUST_REGION_QR = TrustRegionQRT
+    trust_region_radius: float = 1.0  # TrustRegionQROptions::trustRegionRadius_
 
     def _c(self) -> _Options:
         return _Options(self.min_iterations, self.max_iterations, self.threshold, int(self.verbose), self.regularization,
                         int(self.do_line_search), int(self.use_block_jtj), self.target_rows_per_chunk, int(self.subset_line_search),
-                        int(self.jtj_mode), int(self.store_error_history), int(self.cholesky_mode), int(self.fused_mode), int(self.linear_solver))
+                        int(self.jtj_mode), int(self.store_error_history), int(self.cholesky_mode), int(self.fused_mode), int(self.linear_solver),
+                        float(self.trust_region_radius))
 
 
 class _Base:

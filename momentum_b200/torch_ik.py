@@ -44,13 +44,13 @@ class LinearSolverType(IntEnum):
 
     Cholesky = 0       # SubsetGaussNewtonSolverT (tensor_ik.cpp:143-148): the tile-scheduled device path (the fast one)
     QR = 1             # GaussNewtonSolverQRT (tensor_ik.cpp:153-158): Householder QR of [sqrt(lambda) I; J], the reference's default
-    TrustRegionQR = 2  # TrustRegionQRT (tensor_ik.cpp:149-152): not built on the device; rejected loudly
+    TrustRegionQR = 2  # TrustRegionQRT (tensor_ik.cpp:149-152): the device trust-region iteration (ik_tr_qr.cuh); levmar_lambda / line_search do not apply
 
 
 @dataclass
 class SolverOptions:
     """pymomentum/tensor_ik/solver_options.h:27-47. The reference defaults to QR; here the default is Cholesky, the path this
-    repository accelerates (same normal equations, same minimiser); QR runs the device Householder kernel."""
+    repository accelerates (same normal equations, same minimiser); QR and TrustRegionQR run the device Householder kernels."""
 
     linear_solver_type: LinearSolverType = LinearSolverType.Cholesky
     levmar_lambda: float = 0.01
@@ -251,13 +251,13 @@ def solve_ik(character: mc.Character, active_parameters, model_parameters_init: 
     for name in order:
         block_rows[name] = {"position": lambda: 3 * len(pp), "orientation": lambda: 9 * len(op),
                             "limit": lambda: mc.jacobian_size(character, mc.LimitErrorFunction()), "motion": lambda: int(((mw > 0) & active[: len(mw)]).sum())}[name]()
-    if LinearSolverType(options.linear_solver_type) == LinearSolverType.TrustRegionQR:
-        raise NotImplementedError("TrustRegionQR is not built on the device (momentum/character_solver/trust_region_qr.cpp); use Cholesky or QR")
-    use_qr = LinearSolverType(options.linear_solver_type) == LinearSolverType.QR
+    lst = LinearSolverType(options.linear_solver_type)
+    linear = {LinearSolverType.Cholesky: ms.LINEAR_SOLVER_CHOLESKY, LinearSolverType.QR: ms.LINEAR_SOLVER_QR, LinearSolverType.TrustRegionQR: ms.LINEAR_SOLVER_TRUST_REGION_QR}[lst]
     # Cholesky: SubsetGaussNewtonSolverT's line search (c1 = 1e-4 with the directional derivative); QR: GaussNewtonSolverQRT's (same rule,
-    # gauss_newton_solver_qr.cpp:118-143): both are the subset variant on the device
+    # gauss_newton_solver_qr.cpp:118-143): both are the subset variant on the device. TrustRegionQR takes the plain SolverOptions
+    # (tensor_ik.cpp:149-152): iterations / threshold only, radius 1.
     opts = ms.GaussNewtonSolverOptions(min_iterations=options.min_iter, max_iterations=options.max_iter, threshold=options.threshold, regularization=options.levmar_lambda,
-                                       do_line_search=options.line_search, subset_line_search=True, linear_solver=ms.LINEAR_SOLVER_QR if use_qr else ms.LINEAR_SOLVER_CHOLESKY)
+                                       do_line_search=options.line_search, subset_line_search=True, linear_solver=linear)
     cfg = {"fn": fn, "blocks": blocks, "options": opts, "kinds": kinds, "active": active, "block_order": order, "block_rows": block_rows}
     ones = lambda nc: torch.ones(B, nc, device=dev)
     pw = position_cons_weights if position_cons_weights is not None else (ones(len(pp)) if use_pos else None)

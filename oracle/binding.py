@@ -62,6 +62,8 @@ def _bind(L):
         L.orc_fn_create.restype = C.c_void_p
         L.orc_fn_create.argtypes = [C.c_void_p, C.c_int]
         L.orc_fn_destroy.argtypes = [C.c_void_p]
+        L.orc_fn_set_trust_region_radius.argtypes = [C.c_void_p, C.c_double]
+        L.orc_fn_set_trust_region_radius.restype = None
         L.orc_fn_add_joint_ef.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, _ip, _dp, _dp, _dp]
         L.orc_fn_add_state_ef.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_double, _dp, _dp, _dp]
         L.orc_fn_add_limit_ef.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
@@ -225,8 +227,9 @@ class OracleFunction:
         return xf, ra.reshape(J, 3, 3).transpose(0, 2, 1), ta.reshape(J, 3, 3).transpose(0, 2, 1)
 
     def solve(self, params, *, min_iterations=1, max_iterations=2, threshold=1.0, regularization=0.05, do_line_search=False,
-              use_block_jtj=False, subset_solver=False, qr_solver=False, trust_region_qr=False):
+              use_block_jtj=False, subset_solver=False, qr_solver=False, trust_region_qr=False, trust_region_radius=1.0):
         """GaussNewtonSolverT::solve. Returns (error, params, iterations, error_history)."""
+        self._L.orc_fn_set_trust_region_radius(self.fn, C.c_double(trust_region_radius))
         p = np.ascontiguousarray(params, np.float64).copy()
         hist = np.zeros(max(1, max_iterations), np.float64)
         it = C.c_int(0)

@@ -23,6 +23,7 @@ struct FnHandle {
   std::unique_ptr<SkeletonSolverFunction<double>> d;
   std::vector<uint8_t> enabled;
   bool enabledSet{false};
+  double trustRegionRadius{1.0}; // TrustRegionQROptions::trustRegionRadius_
 };
 
 template <class T>
@@ -116,6 +117,7 @@ struct SolveOpts {
   int64_t minIterations, maxIterations;
   double threshold, regularization;
   int doLineSearch, useBlockJtJ, subsetSolver;
+  double trustRegionRadius{1.0};
 };
 
 template <class T>
@@ -130,6 +132,7 @@ double solveOne(SkeletonSolverFunction<T>& fn, const std::vector<uint8_t>* enabl
   go.subsetSolver = o.subsetSolver == 1; // 0 GaussNewtonSolverT, 1 SubsetGaussNewtonSolverT, 2 GaussNewtonSolverQRT, 3 TrustRegionQRT
   go.qrSolver = o.subsetSolver == 2;
   go.trustRegionQr = o.subsetSolver == 3;
+  go.trustRegionRadius = float(o.trustRegionRadius);
   GaussNewtonSolver<T> solver(go, &fn);
   if (enabled) solver.setEnabledParameters(*enabled);
   std::vector<T> p = narrow<T>(params, fn.numParameters);
@@ -383,9 +386,12 @@ void orc_fn_fk(void* fn, const double* params, double* xf, double* rotAxis, doub
   if (h->dtype == 0) fkT<float>(h, params, xf, rotAxis, transAxis); else fkT<double>(h, params, xf, rotAxis, transAxis);
 }
 
+void orc_fn_set_trust_region_radius(void* fn, double radius) { static_cast<FnHandle*>(fn)->trustRegionRadius = radius; }
+
 double orc_solve(void* fn, int64_t minIt, int64_t maxIt, double threshold, double regularization, int doLineSearch, int useBlockJtJ, int subsetSolver, double* params, int* iters, double* errHistory) {
   FnHandle* h = static_cast<FnHandle*>(fn);
   SolveOpts o{minIt, maxIt, threshold, regularization, doLineSearch, useBlockJtJ, subsetSolver};
+  o.trustRegionRadius = h->trustRegionRadius;
   const std::vector<uint8_t>* en = h->enabledSet ? &h->enabled : nullptr;
   return DISPATCH(h, solveOne<float>(*h->f, en, o, params, iters, errHistory), solveOne<double>(*h->d, en, o, params, iters, errHistory));
 }

@@ -87,7 +87,7 @@ def oracle_one_ulp_spread(ch, efs, b, theta0_b, p, enabled, opts, draws=8):
             orc.set_enabled_parameters(enabled)
         _, pp, _, _ = orc.solve(theta0_b, min_iterations=opts.min_iterations, max_iterations=opts.max_iterations, threshold=opts.threshold,
                                 regularization=opts.regularization, do_line_search=opts.do_line_search, use_block_jtj=opts.use_block_jtj,
-                                subset_solver=opts.subset_line_search, qr_solver=getattr(opts, "linear_solver", 0) == 1)
+                                subset_solver=opts.subset_line_search, qr_solver=getattr(opts, "linear_solver", 0) == 1, trust_region_qr=getattr(opts, "linear_solver", 0) == 2, trust_region_radius=getattr(opts, "trust_region_radius", 1.0))
         worst = max(worst, float(np.max(np.abs(pp - p)) / max(1.0, np.max(np.abs(p)))))
     return worst
 
@@ -114,7 +114,7 @@ def check_solve(ch, efs, theta0, opts: ms.GaussNewtonSolverOptions, lib_path=Non
             orc.set_enabled_parameters(enabled)
         err, p, it, hist = orc.solve(f32(theta0[b]), min_iterations=opts.min_iterations, max_iterations=opts.max_iterations,
                                      threshold=opts.threshold, regularization=opts.regularization, do_line_search=opts.do_line_search,
-                                     use_block_jtj=opts.use_block_jtj, subset_solver=opts.subset_line_search, qr_solver=getattr(opts, "linear_solver", 0) == 1)
+                                     use_block_jtj=opts.use_block_jtj, subset_solver=opts.subset_line_search, qr_solver=getattr(opts, "linear_solver", 0) == 1, trust_region_qr=getattr(opts, "linear_solver", 0) == 2, trust_region_radius=getattr(opts, "trust_region_radius", 1.0))
         d = np.max(np.abs(out["params"][b] - p)) / max(1.0, np.max(np.abs(p)))
         worst = max(worst, d)
         tol, etol = param_tol, 1e-3 * abs(err) + 1e-7
@@ -131,7 +131,7 @@ def check_solve(ch, efs, theta0, opts: ms.GaussNewtonSolverOptions, lib_path=Non
                 orc64.set_enabled_parameters(enabled)
             err64, p64, _, _ = orc64.solve(f32(theta0[b]), min_iterations=opts.min_iterations, max_iterations=opts.max_iterations,
                                            threshold=opts.threshold, regularization=opts.regularization, do_line_search=opts.do_line_search,
-                                           use_block_jtj=opts.use_block_jtj, subset_solver=opts.subset_line_search, qr_solver=getattr(opts, "linear_solver", 0) == 1)
+                                           use_block_jtj=opts.use_block_jtj, subset_solver=opts.subset_line_search, qr_solver=getattr(opts, "linear_solver", 0) == 1, trust_region_qr=getattr(opts, "linear_solver", 0) == 2, trust_region_radius=getattr(opts, "trust_region_radius", 1.0))
             gap = np.max(np.abs(p - p64)) / max(1.0, np.max(np.abs(p)))
             # The float-vs-double gap is ONE draw of the reference's rounding noise on this instance (an instance can land close to the
             # double answer by luck: cfg2 instance 91 has gap 1.2e-5, yet the float oracle moves by up to 8.9e-5 when its targets are

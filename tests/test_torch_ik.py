@@ -47,7 +47,7 @@ def test_solve_ik_forward_matches_the_oracle_and_stays_on_the_device():
 
 def test_solve_ik_qr_linear_solver_is_the_reference_default_path():
     """LinearSolverType.QR = GaussNewtonSolverQRT with its line search (tensor_ik.cpp:153-158, the reference's default) against the
-    oracle's restatement of that solver; TrustRegionQR is rejected loudly (not built on the device)."""
+    oracle's restatement of that solver; LinearSolverType.TrustRegionQR likewise."""
     from momentum_b200 import character as mc
     from momentum_b200 import torch_ik as ti
     from oracle.binding import OracleFunction
@@ -67,8 +67,16 @@ def test_solve_ik_qr_linear_solver_is_the_reference_default_path():
         err, p, it, _ = orc.solve(np.zeros(n), min_iterations=4, max_iterations=12, threshold=10.0, regularization=0.01, do_line_search=True, qr_solver=True)
         d = np.max(np.abs(out[b].cpu().numpy() - p)) / max(1.0, np.max(np.abs(p)))
         assert d <= 5e-4, (b, d)
-    with pytest.raises(NotImplementedError, match="TrustRegionQR"):
-        ti.solve_ik(ch, active, torch.zeros(B, n, device=dev), [ti.ErrorFunctionType.Position], efw, ti.SolverOptions(linear_solver_type=ti.LinearSolverType.TrustRegionQR), **kw)
+    # LinearSolverType.TrustRegionQR = TrustRegionQRT (tensor_ik.cpp:149-152) against the oracle's restatement
+    opts_tr = ti.SolverOptions(linear_solver_type=ti.LinearSolverType.TrustRegionQR, min_iter=4, max_iter=12, threshold=10.0)
+    out = ti.solve_ik(ch, active, torch.zeros(B, n, device=dev), [ti.ErrorFunctionType.Position], efw, opts_tr, **kw)
+    for b in range(B):
+        efs = [mc.PositionErrorFunction(parents, offsets, np.ones(len(parents)), targets, weight=1.0)]
+        orc = OracleFunction(ch, efs, "float32", instance=b)
+        orc.set_enabled_parameters(active)
+        err, p, it, _ = orc.solve(np.zeros(n), min_iterations=4, max_iterations=12, threshold=10.0, trust_region_qr=True)
+        d = np.max(np.abs(out[b].cpu().numpy() - p)) / max(1.0, np.max(np.abs(p)))
+        assert d <= 1e-3, (b, d)
 
 
 def _ift_reference(ch, parents, offsets, weights, targets_b, active, theta_b, gout_b):
