@@ -86,7 +86,7 @@ typedef enum mb2_rotation_error_type {
 typedef enum mb2_jtj_mode {
   MB2_JTJ_AUTO = 0,      /* tile-sparse Gram (mma.sync, three-term TF32 split: fp32-class, not bit-exact fp32) with the tile-scheduled Cholesky; else tcgen05 3xTF32 where the shape allows, else FP32 SIMT */
   MB2_JTJ_FP32_SIMT = 1, /* CUDA-core fp32 (validation path) */
-  MB2_JTJ_TF32X3 = 2,    /* tcgen05 kind::tf32, 3-term split, fp32 accumulate in TMEM (fp32-class accuracy) */
+  MB2_JTJ_TF32X3 = 2,    /* tcgen05 kind::tf32, 3-term split, fp32 accumulate in TMEM (fp32-class accuracy); up to 511 Jacobian columns */
   MB2_JTJ_TF32 = 3,      /* tcgen05 kind::tf32 single pass (~1e-3 relative; changes the GN path, not the fixed point) */
   MB2_JTJ_SPARSE_TILES = 4 /* tensor cores (mma.sync m16n8k8, hi*hi + hi*lo + lo*hi TF32 split, the lo*lo term is dropped: ~2^-21 relative) over the non-zero
                               strips of J only, straight into the Cholesky tile layout (tile-scheduled Cholesky only) */

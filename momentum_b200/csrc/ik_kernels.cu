@@ -467,7 +467,7 @@ cudaError_t launchCholesky(const CholArgs& a, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------------
 // K2s: tile-sparse Gram. A skeleton Jacobian is mostly structural zeros (a row only touches the parameters of one
 // root-to-constraint chain), so the stored 16x16 tiles of J^T J are accumulated from the non-zero 4-row x 16-column strips only
-// (GramPlan): ~20x fewer multiply-adds than the dense product, exact fp32. One CTA per instance: every strip arrives as one
+// (GramPlan): ~20x fewer multiply-adds than the dense product, fp32-class accuracy (three-term TF32 split on mma.sync, the lo*lo term dropped: ~2^-21 relative). One CTA per instance: every strip arrives as one
 // TMA box of the K-major Jacobian, a warp owns a tile at a time, the output is already in the Cholesky kernel's tile layout.
 // ------------------------------------------------------------------------------------------------
 constexpr int kGramThreads = 32 * kGramWarps;
