@@ -169,6 +169,11 @@ struct mb2_solver {
   cudaEvent_t fusedStart{nullptr}, fusedStop{nullptr};
   double fusedMs{0};
   int* hActiveCount{nullptr}; // pinned
+  // pinned staging of the per-instance results of an asynchronous host solve: [B] errors (double) | [B] iterations | [B] status, filled by
+  // copies enqueued behind the solve so that mb2_solver_wait needs one stream synchronisation and no further device round trip
+  char* hResults{nullptr};
+  size_t hResultsBytes{0};
+  bool resultsStaged{false};
   uint64_t totalIterations{0}, kernelLaunches{0};
   bool profiling{false};
   bool inKernelProfile{false}; // profiling level 2: the instrumented kernel instantiations (clock64 per phase; slower)
@@ -178,6 +183,7 @@ struct mb2_solver {
   size_t historyStride{0};
   ~mb2_solver() {
     if (hActiveCount) cudaFreeHost(hActiveCount);
+    if (hResults) cudaFreeHost(hResults);
     if (fusedStart) cudaEventDestroy(fusedStart);
     if (fusedStop) cudaEventDestroy(fusedStop);
     for (auto& e : events) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }
@@ -1395,6 +1401,20 @@ int mb2_solver_solve_device(mb2_solver* s, float* theta, void* cudaStream) {
   return MB2_OK;
 }
 
+static void collectProfile(mb2_solver* s) {
+  if (s->profiling && s->lastFused && s->fusedStart) {
+    float ms = 0.f;
+    s->fusedMs = cudaEventElapsedTime(&ms, s->fusedStart, s->fusedStop) == cudaSuccess ? double(ms) : 0.0;
+  }
+  if (s->profiling) {
+    for (int k = 0; k < 4; ++k) { s->phaseMs[k] = 0; s->phaseLaunches[k] = 0; }
+    for (auto& e : s->events) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, e.start, e.stop) == cudaSuccess) { s->phaseMs[e.phase] += ms; s->phaseLaunches[e.phase]++; }
+    }
+  }
+}
+
 int mb2_solver_get_results(mb2_solver* s, double* errors, int32_t* iterations, int32_t* status) {
   MB2_CHECK(s != nullptr, "null solver");
   mb2_solver_function* f = s->fn;
@@ -1408,17 +1428,7 @@ int mb2_solver_get_results(mb2_solver* s, double* errors, int32_t* iterations, i
   for (int v : its) s->totalIterations += uint64_t(v);
   if (iterations) std::copy(its.begin(), its.end(), iterations);
   if (status) MB2_CUDA(cudaMemcpy(status, s->dStatus.p, size_t(B) * sizeof(int32_t), cudaMemcpyDeviceToHost));
-  if (s->profiling && s->lastFused && s->fusedStart) {
-    float ms = 0.f;
-    s->fusedMs = cudaEventElapsedTime(&ms, s->fusedStart, s->fusedStop) == cudaSuccess ? double(ms) : 0.0;
-  }
-  if (s->profiling) {
-    for (int k = 0; k < 4; ++k) { s->phaseMs[k] = 0; s->phaseLaunches[k] = 0; }
-    for (auto& e : s->events) {
-      float ms = 0.f;
-      if (cudaEventElapsedTime(&ms, e.start, e.stop) == cudaSuccess) { s->phaseMs[e.phase] += ms; s->phaseLaunches[e.phase]++; }
-    }
-  }
+  collectProfile(s);
   return MB2_OK;
 }
 
@@ -1426,12 +1436,27 @@ int mb2_solver_solve_async(mb2_solver* s, float* params) {
   MB2_CHECK(s != nullptr && params != nullptr, "null argument");
   mb2_solver_function* f = s->fn;
   MB2_DEVICE_GUARD(f->ch->device);
-  const size_t bytes = size_t(f->B) * f->ch->host.numParams * sizeof(float);
-  MB2_CUDA(s->dThetaStage.resize(size_t(f->B) * f->ch->host.numParams));
+  const size_t B = size_t(f->B);
+  const size_t bytes = B * f->ch->host.numParams * sizeof(float);
+  MB2_CUDA(s->dThetaStage.resize(B * f->ch->host.numParams));
   MB2_CUDA(cudaMemcpyAsync(s->dThetaStage.p, params, bytes, cudaMemcpyHostToDevice, f->stream));
+  s->resultsStaged = false;
   int rc = mb2_solver_solve_device(s, s->dThetaStage.p, f->stream);
   if (rc != MB2_OK) return rc;
   MB2_CUDA(cudaMemcpyAsync(params, s->dThetaStage.p, bytes, cudaMemcpyDeviceToHost, f->stream));
+  // the per-instance results follow the parameters on the same stream into pinned staging (one synchronisation in mb2_solver_wait)
+  const size_t need = B * (sizeof(double) + 2 * sizeof(int32_t));
+  if (s->hResultsBytes < need) {
+    if (s->hResults) cudaFreeHost(s->hResults);
+    s->hResults = nullptr;
+    s->hResultsBytes = 0;
+    MB2_CUDA(cudaMallocHost(reinterpret_cast<void**>(&s->hResults), need));
+    s->hResultsBytes = need;
+  }
+  MB2_CUDA(cudaMemcpyAsync(s->hResults, f->dErrors.p, B * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+  MB2_CUDA(cudaMemcpyAsync(s->hResults + B * sizeof(double), s->dIterations.p, B * sizeof(int32_t), cudaMemcpyDeviceToHost, f->stream));
+  MB2_CUDA(cudaMemcpyAsync(s->hResults + B * (sizeof(double) + sizeof(int32_t)), s->dStatus.p, B * sizeof(int32_t), cudaMemcpyDeviceToHost, f->stream));
+  s->resultsStaged = true;
   return MB2_OK;
 }
 
@@ -1439,7 +1464,17 @@ int mb2_solver_wait(mb2_solver* s, double* errors, int32_t* iterations, int32_t*
   MB2_CHECK(s != nullptr, "null solver");
   MB2_DEVICE_GUARD(s->fn->ch->device);
   MB2_CUDA(cudaStreamSynchronize(s->fn->stream));
-  return mb2_solver_get_results(s, errors, iterations, status);
+  if (!s->resultsStaged) return mb2_solver_get_results(s, errors, iterations, status);
+  const size_t B = size_t(s->fn->B);
+  const int32_t* its = reinterpret_cast<const int32_t*>(s->hResults + B * sizeof(double));
+  if (errors) std::memcpy(errors, s->hResults, B * sizeof(double));
+  s->totalIterations = 0;
+  for (size_t b = 0; b < B; ++b) s->totalIterations += uint64_t(its[b]);
+  if (iterations) std::memcpy(iterations, its, B * sizeof(int32_t));
+  if (status) std::memcpy(status, s->hResults + B * (sizeof(double) + sizeof(int32_t)), B * sizeof(int32_t));
+  s->resultsStaged = false;
+  collectProfile(s);
+  return MB2_OK;
 }
 
 int mb2_solver_solve(mb2_solver* s, float* params, double* errors, int32_t* iterations, int32_t* status) {

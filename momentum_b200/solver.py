@@ -434,9 +434,16 @@ class GaussNewtonSolver(_Base):
                                              st.ctypes.data_as(_ip)))
         return {"params": p, "errors": err, "iterations": it, "status": st}
 
-    def solve_host_pointer(self, host_ptr: int):
-        """Same through a raw (e.g. pinned) host pointer; results via get_results()."""
-        self._check(self._L.mb2_solver_solve(self._h, C.c_void_p(host_ptr), None, None, None))
+    def solve_host_pointer(self, host_ptr: int, results: bool = False):
+        """Same through a raw (e.g. pinned) host pointer; per-instance results returned when ``results`` (one mb2_solver_solve call),
+        else via get_results()."""
+        if not results:
+            self._check(self._L.mb2_solver_solve(self._h, C.c_void_p(host_ptr), None, None, None))
+            return None
+        B = self.fn.batch
+        err = np.zeros(B, np.float64); it = np.zeros(B, np.int32); st = np.zeros(B, np.int32)
+        self._check(self._L.mb2_solver_solve(self._h, C.c_void_p(host_ptr), err.ctypes.data_as(_dp), it.ctypes.data_as(_ip), st.ctypes.data_as(_ip)))
+        return {"errors": err, "iterations": it, "status": st}
 
     def solve_host_pointer_async(self, host_ptr: int):
         """mb2_solver_solve_async: H2D of the parameters, the solve and the D2H of the result are enqueued on the handle's stream; the
