@@ -72,7 +72,7 @@ __device__ __forceinline__ void stageTable(const E*& table, size_t count, uint32
 // table pointer is PROVABLY a shared-memory address: with `if (a.stageTables)` the pointers could be either and all 273 table loads
 // of the kernel were generic LD instructions (address-space check on every hop of the dependent chains cell -> unit -> record ->
 // contributions; 43 % of the warp-state samples were long-scoreboard waits on them, profiles/r02k).
-constexpr int kSweepMaxWarps = 24; // one warp per instance: up to 24 instances in flight per SM (85 registers per thread)
+constexpr int kSweepMaxWarps = 24; // up to 24 warps per CTA (85 registers per thread)
 template <bool kJacobian, int W, int kStage>
 __global__ void __launch_bounds__(32 * kSweepMaxWarps) sweepKernel(const SweepArgs a) {
   extern __shared__ __align__(16) float smem[];
@@ -175,13 +175,18 @@ cudaError_t launchSweep(const SweepArgs& a0, bool jacobian, cudaStream_t stream)
   const int groupsOneWarp = int((budget - tableBytes) / sweepSmemPerInstance(a.T, 1)); // (no joint-parameter array)
   int W = 1;
   if (groupsOneWarp >= 16) {
-    groups = groupsOneWarp;
-    groups = std::min(groups, kSweepMaxWarps);
-    // the instances of an SM are dealt to its warps round by round: keep the number of rounds the widest CTA gives and use the fewest
-    // warps that still finish in that many (8192 instances on 148 SMs: 24 warps -> 3 rounds, and 19 warps are enough for 3)
+    // The instances of an SM are dealt to its warps round by round, and from about a dozen warps on the kernel is throughput bound
+    // (measured on the cfg3 shard: 0.049 / 0.059 / 0.095 ms per round with 16 / 19 / 28 warps): the time is rounds x warps, i.e. the
+    // padded instance count. Pick the warp count that wastes the fewest slots (8192 instances on 148 SMs: 19 warps x 3 rounds = 8436
+    // slots; 4096 instances: 14 warps x 2 rounds = 4144); a 28-warp variant (73 registers) spilled and lost more than its two rounds won.
     const int sms = std::max(g_numSms, 1);
-    const int rounds = (a.batch + sms * groups - 1) / (sms * groups);
-    groups = std::max(std::min(groups, (a.batch + sms * rounds - 1) / (sms * rounds)), std::min(groups, 16));
+    const int maxG = std::min(groupsOneWarp, kSweepMaxWarps), minG = std::min(12, maxG);
+    long best = -1;
+    if (a.batch < sms * minG) { groups = std::max(1, (a.batch + sms - 1) / sms); best = 0; } // a small batch: spread it over the SMs
+    for (int gcand = maxG; gcand >= minG && best != 0; --gcand) {
+      const long rounds = (a.batch + long(sms) * gcand - 1) / (long(sms) * gcand);
+      if (best < 0 || rounds * gcand < best) { best = rounds * gcand; groups = gcand; }
+    }
   } else {
     if (groups > 15) groups = 15; // named barriers 1..15
     while (W < 8 && groups * W * 2 <= kSweepMaxWarps) W *= 2; // these instances wait on L1 / L2 and on each other's barriers: as many warps as fit
