@@ -571,6 +571,12 @@ MB2_HD void jacobianCell(const FunctionTables& T, int ci, const float* js, const
       const float ds = rc[3];
       F3 acc = f3(0.f, 0.f, 0.f);
       for (int k = 0; k < c.contribCount; ++k) acc = acc + (pointDerivative(T, js, cb[k].joint, cb[k].dof, v) * ds) * cb[k].coef;
+#if defined(__CUDA_ARCH__)
+      // strip layout, unit on a quad boundary (every multi-row unit owns whole quads: its fourth row is a structural zero): the three
+      // rows of this column are ONE 16-byte store instead of three scattered 4-byte ones (the global stores were a third of the sweep's
+      // LSU wavefronts, its busiest pipe)
+      if (T.stripMode && rowShift == 0) { *reinterpret_cast<float4*>(out) = make_float4(acc.x, acc.y, acc.z, 0.f); break; }
+#endif
       out[MB2_ROW(0)] = acc.x; out[MB2_ROW(1)] = acc.y; out[MB2_ROW(2)] = acc.z;
       break;
     }
@@ -596,6 +602,14 @@ MB2_HD void jacobianCell(const FunctionTables& T, int ci, const float* js, const
           acc[3 * jv] += (ds * d.x) * cb[k].coef; acc[3 * jv + 1] += (ds * d.y) * cb[k].coef; acc[3 * jv + 2] += (ds * d.z) * cb[k].coef;
         }
       }
+#if defined(__CUDA_ARCH__)
+      if (T.stripMode && rowShift == 0) { // nine rows = three quads of this column (the last one holds row 8 and three structural zeros)
+        *reinterpret_cast<float4*>(out) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(out + quadFloats) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        *reinterpret_cast<float4*>(out + 2 * quadFloats) = make_float4(acc[8], 0.f, 0.f, 0.f);
+        break;
+      }
+#endif
       for (int k = 0; k < 9; ++k) out[MB2_ROW(k)] = acc[k];
       break;
     }
