@@ -433,10 +433,14 @@ std::string buildPlan(const HostCharacter& ch, const std::vector<HostErrorFuncti
   if (out.units.size() > 65535) return "too many constraints in one solver function (limit 65535 units)";
   out.numRows = row;
   out.recStride = std::max(rec, 1);
-  // group cells so neighbouring lanes run the same code path and touch the same Jacobian column
+  // Group cells so that neighbouring lanes run the same code path and store next to each other. K-major matrix: same column, consecutive
+  // units = consecutive rows of that column. Strip layout (alignRowGroups): same unit, consecutive device columns = consecutive 16-byte
+  // pieces of the unit's strip (a row quad x 16 columns is 256 contiguous bytes), so a warp's stores fill whole sectors and lines, and
+  // the unit / record reads of a warp are broadcasts.
   std::stable_sort(out.cells.begin(), out.cells.end(), [&](const CellDesc& a, const CellDesc& b) {
     const int ka = out.units[a.unit].kind, kb = out.units[b.unit].kind;
     if (ka != kb) return ka < kb;
+    if (alignRowGroups) return a.unit != b.unit ? a.unit < b.unit : a.col < b.col;
     if (a.col != b.col) return a.col < b.col;
     return a.unit < b.unit;
   });
