@@ -436,38 +436,60 @@ MB2_HD void cholVectorTask(const float* tiles, float* y, const CholSchedDev& S, 
   y[S.vtaskRow[vtask] * 16 + hl] -= (s0 + s1) + (s2 + s3);
 }
 
-// ---- backward substitution for one tile column K: y_K <- L(K,K)^-T (y_K - sum_I L(I,K)^T y_I) ----
-MB2_HD void cholBackwardColumn(const float* tiles, float* y, const CholSchedDev& S, int K, int hl, unsigned hmask) {
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  for (int p = S.colPanelStart[K]; p < S.colPanelStart[K + 1]; ++p) {
-    const float* T = tiles + size_t(S.colPanelTile[p]) * 256; // column hl of L(I,K)
-    const float* yi = y + S.colPanelRow[p] * 16;
-#pragma unroll
-    for (int r = 0; r < 16; r += 4) {
-      s0 += T[tileIdx(r, hl)] * yi[r]; s1 += T[tileIdx(r + 1, hl)] * yi[r + 1]; s2 += T[tileIdx(r + 2, hl)] * yi[r + 2]; s3 += T[tileIdx(r + 3, hl)] * yi[r + 3];
-    }
-  }
-  const float s = y[K * 16 + hl] - ((s0 + s1) + (s2 + s3));
-  // x_K = W^T s with W = L(K,K)^-1 stored by phase A: lane c accumulates column c of W
-  const float* W = tiles + size_t(S.diagTile[K]) * 256;
+// ---- backward substitution for one tile column K: y_K <- L(K,K)^-T (y_K - sum_I L(I,K)^T y_I); ONE WARP per column ----
+// Both parts are "column sums of a tile against a vector": sum_r X(r, c) v[r]. A lane reads its own fragment of the tile (two
+// conflict-free LDS.128: rows g, g + 8 x columns 2t, 2t + 1, 8 + 2t, 9 + 2t), multiplies by v[g], v[g + 8] and keeps four partial
+// column sums over all panel tiles of the column; ONE butterfly over the eight lanes that share t finishes them. (The first version,
+// a half-warp per column with lane c reading X(r, c) scalar by scalar, made 18 % of the fused kernel's shared-memory wavefronts, most
+// of them bank-conflict replays: a row of the fragment layout is not a conflict-free 4-byte access.)
+MB2_HD void cholBackwardColumn(const float* tiles, float* y, const CholSchedDev& S, int K, int lane) {
 #if defined(__CUDA_ARCH__)
-  float x0 = 0.f, x1 = 0.f;
-#pragma unroll
-  for (int r = 0; r < 16; r += 2) {
-    x0 += W[tileIdx(r, hl)] * __shfl_sync(hmask, s, r, 16);
-    x1 += W[tileIdx(r + 1, hl)] * __shfl_sync(hmask, s, r + 1, 16);
+  const int g = lane >> 2, t = lane & 3, so = tileSlotOffset(lane);
+  float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+  for (int p = S.colPanelStart[K]; p < S.colPanelStart[K + 1]; ++p) {
+    const float* T = tiles + size_t(S.colPanelTile[p]) * 256;
+    const float* yi = y + S.colPanelRow[p] * 16;
+    const float4 v0 = *reinterpret_cast<const float4*>(T + so), v1 = *reinterpret_cast<const float4*>(T + 128 + so);
+    const float ya = yi[g], yb = yi[g + 8];
+    c0 = fmaf(v0.x, ya, fmaf(v0.z, yb, c0)); c1 = fmaf(v0.y, ya, fmaf(v0.w, yb, c1));
+    c2 = fmaf(v1.x, ya, fmaf(v1.z, yb, c2)); c3 = fmaf(v1.y, ya, fmaf(v1.w, yb, c3));
   }
-  y[K * 16 + hl] = x0 + x1;
+#pragma unroll
+  for (int o = 4; o < 32; o <<= 1) {
+    c0 += __shfl_xor_sync(0xffffffffu, c0, o); c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+    c2 += __shfl_xor_sync(0xffffffffu, c2, o); c3 += __shfl_xor_sync(0xffffffffu, c3, o);
+  }
+  float* yk = y + K * 16;
+  if (g == 0) { yk[2 * t] -= c0; yk[2 * t + 1] -= c1; yk[8 + 2 * t] -= c2; yk[9 + 2 * t] -= c3; } // s = y_K - sums
+  __syncwarp();
+  // x_K = W^T s with W = L(K,K)^-1 stored by phase A
+  const float* W = tiles + size_t(S.diagTile[K]) * 256;
+  const float4 w0 = *reinterpret_cast<const float4*>(W + so), w1 = *reinterpret_cast<const float4*>(W + 128 + so);
+  const float sa = yk[g], sb = yk[g + 8];
+  float x0 = fmaf(w0.x, sa, w0.z * sb), x1 = fmaf(w0.y, sa, w0.w * sb), x2 = fmaf(w1.x, sa, w1.z * sb), x3 = fmaf(w1.y, sa, w1.w * sb);
+#pragma unroll
+  for (int o = 4; o < 32; o <<= 1) {
+    x0 += __shfl_xor_sync(0xffffffffu, x0, o); x1 += __shfl_xor_sync(0xffffffffu, x1, o);
+    x2 += __shfl_xor_sync(0xffffffffu, x2, o); x3 += __shfl_xor_sync(0xffffffffu, x3, o);
+  }
+  __syncwarp(); // every lane has read s before it is overwritten
+  if (g == 0) { yk[2 * t] = x0; yk[2 * t + 1] = x1; yk[8 + 2 * t] = x2; yk[9 + 2 * t] = x3; }
 #else
-  // host emulation: lanes run one after the other, so stage the sums, then lane 15 (last) finishes the block
-  y[K * 16 + hl] = s;
-  if (hl != 15) return;
-  float sv[16];
-  for (int r = 0; r < 16; ++r) sv[r] = y[K * 16 + r];
+  if (lane != 0) return; // host emulation: one caller plays the warp
+  float s[16];
+  for (int c = 0; c < 16; ++c) s[c] = 0.f;
+  for (int p = S.colPanelStart[K]; p < S.colPanelStart[K + 1]; ++p) {
+    const float* T = tiles + size_t(S.colPanelTile[p]) * 256;
+    const float* yi = y + S.colPanelRow[p] * 16;
+    for (int c = 0; c < 16; ++c) for (int r = 0; r < 16; ++r) s[c] += T[tileIdx(r, c)] * yi[r];
+  }
+  float* yk = y + K * 16;
+  for (int c = 0; c < 16; ++c) s[c] = yk[c] - s[c];
+  const float* W = tiles + size_t(S.diagTile[K]) * 256;
   for (int c = 0; c < 16; ++c) {
-    float x0 = 0.f, x1 = 0.f;
-    for (int r = 0; r < 16; r += 2) { x0 += W[tileIdx(r, c)] * sv[r]; x1 += W[tileIdx(r + 1, c)] * sv[r + 1]; }
-    y[K * 16 + c] = x0 + x1;
+    float x = 0.f;
+    for (int r = 0; r < 16; ++r) x += W[tileIdx(r, c)] * s[r];
+    yk[c] = x;
   }
 #endif
 }

@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(kFusedGroupThreads* kGroups, 1) fusedSolveKern
         MB2_PH(kPhUpdate)
       }
       for (int Lv = S.numLevels - 1; Lv >= 0; --Lv) {
-        for (int ci = S.levelColStart[Lv] + hw; ci < S.levelColStart[Lv + 1]; ci += kFusedGroupThreads / 16) cholBackwardColumn(tiles, y, S, S.levelCols[ci], hl, hmask);
+        for (int ci = S.levelColStart[Lv] + warp; ci < S.levelColStart[Lv + 1]; ci += kFusedGroupThreads / 32) cholBackwardColumn(tiles, y, S, S.levelCols[ci], lane);
         groupSync();
       }
       MB2_PH(kPhBackward)

@@ -648,7 +648,7 @@ __global__ void __launch_bounds__(kSchedThreads, kSchedThreads == 256 ? 3 : 1) c
     MB2_PROF(3)
   }
   for (int L = S.numLevels - 1; L >= 0; --L) {
-    for (int ci = S.levelColStart[L] + hw; ci < S.levelColStart[L + 1]; ci += kSchedThreads / 16) cholBackwardColumn(tiles, y, S, S.levelCols[ci], hl, hmask);
+    for (int ci = S.levelColStart[L] + warp; ci < S.levelColStart[L + 1]; ci += kSchedThreads / 32) cholBackwardColumn(tiles, y, S, S.levelCols[ci], lane);
     __syncthreads();
   }
   MB2_PROF(4)
@@ -812,7 +812,7 @@ __global__ void __launch_bounds__(kGramThreads, 4) gramCholeskyKernel(const Gram
     MB2_GC(5)
   }
   for (int L = S.numLevels - 1; L >= 0; --L) {
-    for (int ci = S.levelColStart[L] + hw; ci < S.levelColStart[L + 1]; ci += kGramThreads / 16) cholBackwardColumn(tiles, y, S, S.levelCols[ci], hl, hmask);
+    for (int ci = S.levelColStart[L] + warp; ci < S.levelColStart[L + 1]; ci += kGramThreads / 32) cholBackwardColumn(tiles, y, S, S.levelCols[ci], lane);
     __syncthreads();
   }
   MB2_GC(6)

@@ -267,7 +267,7 @@ static int cholScheduledOne(const CholSchedDev& S, const float* Hs, int ldH, int
   }
   for (int L = S.numLevels - 1; L >= 0; --L)
     for (int ci = S.levelColStart[L]; ci < S.levelColStart[L + 1]; ++ci)
-      for (int hl = 0; hl < 16; ++hl) cholBackwardColumn(tl, y, S, S.levelCols[ci], hl, 0xFFFFu);
+      for (int lane = 0; lane < 32; ++lane) cholBackwardColumn(tl, y, S, S.levelCols[ci], lane);
   float gd = 0.f;
   for (int i = 0; i < S.nPad; ++i) { const int p = S.perm[i]; if (p >= 0) { delta[p] = y[i]; gd += gsub[p] * y[i]; } }
   *gdd = gd;
