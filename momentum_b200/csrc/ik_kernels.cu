@@ -63,7 +63,17 @@ __device__ __forceinline__ void stageTable(const E*& table, size_t count, uint32
   static_assert(sizeof(E) % 4 == 0, "tables are staged word by word");
   const uint32_t* src = reinterpret_cast<const uint32_t*>(table);
   const size_t words = count * (sizeof(E) / 4);
-  for (size_t i = threadIdx.x; i < words; i += blockDim.x) cursor[i] = src[i];
+  // eight loads in flight per thread (a word-by-word loop is a chain of global-load latencies: 23 of them for the 40 KB of cfg3)
+  const int nt = int(blockDim.x);
+  size_t i = threadIdx.x;
+  for (; i + 7 * size_t(nt) < words; i += 8 * size_t(nt)) {
+    uint32_t v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = src[i + size_t(k) * nt];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cursor[i + size_t(k) * nt] = v[k];
+  }
+  for (; i < words; i += nt) cursor[i] = src[i];
   table = reinterpret_cast<const E*>(cursor);
   cursor += tableWords(count, sizeof(E));
 }
@@ -112,6 +122,10 @@ __global__ void __launch_bounds__(32 * kSweepMaxWarps) sweepKernel(const SweepAr
     const float* theta = a.theta + size_t(b) * a.ldTheta;
     for (int i = gl; i < T.numParams; i += gs) th[i] = theta[i];
     groupSync();
+    if (W == 1) { // touch the next instance's parameters now: by the time this one is done they sit in L1 / L2 (one warp = one 880-byte row)
+      const int bn = b + gridDim.x * groupsPerCta;
+      if (bn < a.batch) { const float* tn = a.theta + size_t(bn) * a.ldTheta; for (int i = gl * 8; i < T.numParams; i += gs * 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(tn + i)); }
+    }
     // SkeletonState::set in three data-parallel passes (ik_device.cuh): every joint's local part at once (its seven joint parameters
     // come straight from theta: ParameterTransform::apply row by row), ~50 dependent flops per tree level, then the derivative axes
     // (one warp per instance: three rounds of lanes = joints, each walking its seven rows; several warps per instance: lanes = rows first)
