@@ -493,7 +493,10 @@ constexpr int kGramThreads = 32 * kGramWarps;
 
 size_t gramTilesSmemBytes(size_t stripStride, int blobInts) { return 128 + sizeof(float) * (stripStride + 64) + 16 + sizeof(int32_t) * size_t((blobInts + 3) & ~3); }
 
-__global__ void __launch_bounds__(kGramThreads) gramTilesKernel(const GramArgs a) {
+// kThreads = 256 (eight warps, the width the tile-order table is dealt for), or 512 when the strips of an instance leave room for only
+// one CTA per SM anyway (bodyhands300: 155 KB): the sixteen warps then walk the same table two rounds at a time.
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads) gramTilesKernel(const GramArgs a) {
   extern __shared__ __align__(16) float gramSmem[];
   const int b = blockIdx.x;
   if (a.active != nullptr && a.active[b] == 0) return;
@@ -515,13 +518,13 @@ __global__ void __launch_bounds__(kGramThreads) gramTilesKernel(const GramArgs a
   }
   // the plan tables are read in dependent chains (tile -> pair range -> strips): stage them in shared memory while the copy is in flight
   int32_t* tab = reinterpret_cast<int32_t*>(bar + 2);
-  for (int i = tid; i < a.blobInts; i += kGramThreads) tab[i] = __ldg(a.blob + i);
+  for (int i = tid; i < a.blobInts; i += kThreads) tab[i] = __ldg(a.blob + i);
   __syncthreads();
   mbarWaitRelaxed(barAddr, 0);
   const int32_t* tileOrder = tab + a.offTileOrder, *tileQuadStart = tab + a.offTilePairStart, *quads = tab + a.offPairA; // (blob tables are 16-byte aligned)
   const int32_t* colStripStart = tab + a.offColStripStart, *colStrip = tab + a.offColStrip, *stripRow = tab + a.offStripRow, *tileInfo = tab + a.offTileInfo;
   float* out = a.out + size_t(b) * a.outStride;
-  for (int ti = warp; ti < a.numOrder; ti += kGramThreads / 32) {
+  for (int ti = warp; ti < a.numOrder; ti += kThreads / 32) { // ([rounds][8] table: warp w + 8 takes the odd rounds of warp w's list)
     const int t = tileOrder[ti];
     if (t < 0) continue;
     float acc[2][4];
@@ -533,16 +536,19 @@ __global__ void __launch_bounds__(kGramThreads) gramTilesKernel(const GramArgs a
     gramTileStore(out + size_t(t) * 256, acc, tileInfo[t], a.regularization, lane);
   }
   float* y = out + size_t(a.numTiles) * 256;
-  for (int K = hw; K < a.numTileCols; K += kGramThreads / 16)
+  for (int K = hw; K < a.numTileCols; K += kThreads / 16)
     y[16 * K + hl] = gramVectorEntry(strips, resid, colStrip, stripRow, colStripStart[K], colStripStart[K + 1], hl);
 }
 
 cudaError_t launchGramTiles(const GramArgs& a, cudaStream_t stream) {
   const size_t smem = gramTilesSmemBytes(a.stripStride, a.blobInts);
   if (smem > size_t(g_maxSmemOptin) || (a.stripStride & 3) != 0) return cudaErrorInvalidConfiguration;
-  cudaError_t e = cudaFuncSetAttribute(gramTilesKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  const bool wide = 2 * (smem + 1024) > size_t(g_maxSmemPerSm); // one CTA per SM anyway: give it 16 warps
+  cudaError_t e = wide ? cudaFuncSetAttribute(gramTilesKernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))
+                       : cudaFuncSetAttribute(gramTilesKernel<kGramThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
-  gramTilesKernel<<<a.batch, kGramThreads, smem, stream>>>(a);
+  if (wide) gramTilesKernel<512><<<a.batch, 512, smem, stream>>>(a);
+  else gramTilesKernel<kGramThreads><<<a.batch, kGramThreads, smem, stream>>>(a);
   return cudaGetLastError();
 }
 
