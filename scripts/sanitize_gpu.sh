@@ -22,6 +22,14 @@ for kw in (dict(fused_mode=ms.FUSED_OFF), dict(fused_mode=ms.FUSED_GRAM_CHOLESKY
 ch, efs, theta0, _ = chain_problem(J=6, B=3, seed=21)
 fn = parity.build_function(ch, efs, 3)
 print(fn.get_error(theta0)[:2], ms.GaussNewtonSolver(ms.GaussNewtonSolverOptions(max_iterations=2), fn).solve(theta0)["errors"][:2])
+# round-2 additions: the trust-region QR iteration, the wide (n = 424) tcgen05 JtJ with far items + the 16-warp Gram / Cholesky kernels of cfg4
+print("trust region", ms.GaussNewtonSolver(ms.GaussNewtonSolverOptions(min_iterations=2, max_iterations=2, linear_solver=ms.LINEAR_SOLVER_TRUST_REGION_QR), fn).solve(theta0)["errors"][:2])
+from momentum_b200.problems import bodyhands_problem
+ch, efs, theta0, _ = bodyhands_problem(2)
+fn = parity.build_function(ch, efs, 2)
+for kw in (dict(), dict(jtj_mode=ms.JTJ_TF32X3, cholesky_mode=ms.CHOLESKY_TILES_SPARSE, fused_mode=ms.FUSED_OFF)):
+    out = ms.GaussNewtonSolver(ms.GaussNewtonSolverOptions(min_iterations=1, max_iterations=1, regularization=0.05, **kw), fn).solve(theta0)
+    print("bodyhands", kw, "status", out["status"].tolist(), "err0", float(out["errors"][0]))
 PY
 for tool in memcheck racecheck synccheck; do
   timeout 900 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san_driver.py > $OUT/${TAG}_san_${tool}.log 2>&1
