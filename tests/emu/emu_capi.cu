@@ -768,6 +768,61 @@ extern "C" int emu_plan_figures(mb2_solver_function* f, int64_t out[10]) {
   return MB2_OK;
 }
 
+// What the sweep kernel's 16-byte strip stores rely on (ik_device.cuh jacobianCell): in the solver (strip) layout every Position /
+// Orientation unit starts on a row quad and owns whole quads (the rows up to the next multiple of four belong to no other unit), its
+// cells sit at 16-byte aligned strip offsets, and cells are ordered by (kind, unit, device column).
+// out: [0] units starting off a quad boundary, [1] units whose padding rows overlap another unit, [2] cells at unaligned strip offsets,
+//      [3] cells out of (kind, unit, column) order, [4] multi-row units, [5] cells
+extern "C" int emu_store_invariants(mb2_solver_function* f, int64_t out[6]) {
+  int64_t fig[10];
+  if (emu_plan_figures(f, fig) != MB2_OK) return MB2_ERR_INVALID_ARGUMENT; // leaves f->plan in the solver layout (aligned row groups)
+  const Plan& p = f->plan;
+  std::vector<int> owner(size_t(p.numRows) + 8, -1);
+  int64_t offQuad = 0, overlap = 0, multi = 0;
+  for (size_t u = 0; u < p.units.size(); ++u) {
+    const UnitDesc& d = p.units[u];
+    const bool joint = d.kind == kUnitPosition || d.kind == kUnitOrientation || d.kind == kUnitOrientationRotDiff;
+    if (joint) { ++multi; if ((d.row0 & 3) != 0) ++offQuad; }
+    const int end = joint ? ((d.row0 + d.numRows + 3) & ~3) : d.row0 + d.numRows; // a joint unit claims its padding rows too
+    for (int r = d.row0; r < end; ++r) { if (owner[size_t(r)] >= 0) ++overlap; owner[size_t(r)] = int(u); }
+  }
+  // strip offsets of the cells: the Gram plan of the same layout (as emu_plan_figures builds it)
+  CholSchedule s;
+  std::vector<std::vector<int>> cliques(p.units.size());
+  for (const CellDesc& c : p.cells) cliques[c.unit].push_back(int(c.col));
+  std::vector<int32_t> cr0, crn, cc;
+  for (const CellDesc& c : p.cells) { cr0.push_back(p.units[c.unit].row0); crn.push_back(p.units[c.unit].numRows); cc.push_back(int32_t(c.col)); }
+  GramPlan g;
+  {
+    // the schedule must be the one the plan's device columns were laid out for: rebuild it from the natural-order plan
+    mb2_solver_function tmp = *f; // (plain copy of the host description; device-free harness)
+    std::string e = plan(&tmp, true);
+    if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
+    std::vector<std::vector<int>> cl(tmp.plan.units.size());
+    for (const CellDesc& c : tmp.plan.cells) cl[c.unit].push_back(int(c.col));
+    const std::vector<int> prio = columnDepthPriority(f->ch->host, tmp.plan.enabledList);
+    e = buildCholSchedule(tmp.plan.numCols, cl, false, s, &prio);
+    if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
+    std::vector<int32_t> colOrder;
+    layoutDeviceColumns(s, colOrder);
+    e = buildGramPlan(s, cr0, crn, cc, p.numRows, g);
+    if (!e.empty()) return fail(MB2_ERR_INVALID_ARGUMENT, e);
+  }
+  int64_t unaligned = 0, disorder = 0;
+  for (size_t i = 0; i < p.cells.size(); ++i) {
+    const CellDesc& c = p.cells[i];
+    if ((g.cellStripOff[i] & 3u) != 0) ++unaligned;
+    if (i > 0) {
+      const CellDesc& a = p.cells[i - 1];
+      const int ka = p.units[a.unit].kind, kb = p.units[c.unit].kind;
+      const bool ok = ka < kb || (ka == kb && (a.unit < c.unit || (a.unit == c.unit && a.col < c.col)));
+      if (!ok) ++disorder;
+    }
+  }
+  out[0] = offQuad; out[1] = overlap; out[2] = unaligned; out[3] = disorder; out[4] = multi; out[5] = int64_t(p.cells.size());
+  return MB2_OK;
+}
+
 // table sizes of the solver plan (bytes): what a kernel that stages every table in shared memory has to hold
 extern "C" int emu_table_sizes(mb2_solver_function* f, int64_t out[12]) {
   int64_t fig[10];

@@ -206,3 +206,9 @@ def test_solver_plan_figures_humanoid_and_bodyhands():
         assert odd == 0         # pair lists are consumed two at a time
         assert outside == 0     # every Jacobian cell lands inside the strip of its (row quad, tile column)
         assert strips > 0 and pairs >= strips
+        # what the sweep kernel's 16-byte strip stores rely on: joint units start on a row quad and own their padding rows, cells sit at
+        # 16-byte aligned strip offsets in (kind, unit, device column) order
+        inv = (C.c_int64 * 6)()
+        assert fn._L.emu_store_invariants(fn._h, inv) == 0
+        off_quad, overlap, unaligned, disorder, multi, cells = list(inv)
+        assert multi > 0 and cells > 0 and off_quad == 0 and overlap == 0 and unaligned == 0 and disorder == 0, list(inv)
