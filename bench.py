@@ -309,7 +309,7 @@ def kernel_report(m, peaks, workload):
     else:
         k2_bytes = 4.0 * (m_rows * (st["jacobian_columns"] + 1) + (st["normal_parameters"] + 1) * (st["normal_parameters"] + 2) / 2)
         ach = jtj_flops * B / (jtj_ms * 1e-3) / 1e12 if jtj_ms > 0 else 0.0
-        dense = st["jacobian_columns"] + 1 <= 512 and args_jtj_is_tensor(m)
+        dense = st["jacobian_columns"] + 1 <= 512
         kernels.append({"kernel": "jtjTensorKernel (JtJ/Jtr, tcgen05 3xTF32)" if dense else "jtjSimtKernel", "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
                         "frac": ach / tf32_peak, "peak_source": f"0.5 x {peaks['src']} bf16 cuBLAS burst ({peaks['bf16']} TF/s) = TF32 dense", "traffic": traffic.get("jtj_jtr"),
                         "ms_per_launch": jtj_ms, "algorithmic_flops_per_instance": jtj_flops, "algorithmic_bytes_per_instance": k2_bytes})
@@ -326,10 +326,6 @@ def kernel_report(m, peaks, workload):
                           "tf32_peak": tf32_peak, "note": "credit = m n (n + 1) per instance-iteration (SURVEY 8d); executed = the multiply-adds of the non-zero 4x16 strips only; "
                                                          "mma.sync (HMMA) path, not tcgen05: see profiles/sass_r02.txt"})
     return kernels, jtj_phase, {"fk_residual_jacobian": sweep_ms, "jtj_jtr": jtj_ms, "cholesky_update": chol_ms}, st
-
-
-def args_jtj_is_tensor(m):
-    return True
 
 
 def extra_workloads(ms, torch, args, rank, local_rank, flush, barrier, peaks):
