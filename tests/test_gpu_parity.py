@@ -268,7 +268,7 @@ def test_cfg2_cfg3_humanoid_converged_parameters(orientation):
     # cfg2 (24 Position, m=72) / cfg3 (+6 Orientation, m=126) at a size the oracle finishes in seconds
     # Every one of the 96 instances is compared at the stated 1e-4 against the FLOAT oracle. These under-determined problems (m < n)
     # are still creeping along their weakly constrained directions after 50 damped iterations, and on a few of them float rounding
-    # alone moves the reference by ~1e-4 (scripts/parity_survey.py, profiles/r02_parity_survey.txt): such an instance must be as close to
+    # alone moves the reference by ~1e-4 (scripts/parity_survey.py, profiles/r02s_parity_survey.txt): such an instance must be as close to
     # the DOUBLE oracle as the reference's float build is, and at most 8 of the 96 may need that second look (measured: 2 / 6).
     B = 96
     ch, efs, theta0, _ = humanoid_problem(B, orientation=orientation)
