@@ -628,6 +628,14 @@ class CudaGaussNewtonSolver : public momentum::SolverT<float> {
     momentum::SolverT<float>::setEnabledParameters(parameters);
     step_.reset();
   }
+  // Which of momentum's solver classes the device iteration reproduces: MB2_LINEAR_SOLVER_CHOLESKY = GaussNewtonSolverT / SubsetGaussNewtonSolverT
+  // (default), MB2_LINEAR_SOLVER_QR = GaussNewtonSolverQRT (gauss_newton_solver_qr.h), MB2_LINEAR_SOLVER_TRUST_REGION_QR = TrustRegionQRT with
+  // TrustRegionQROptions::trustRegionRadius_ (trust_region_qr.h:23)
+  void setLinearSolver(mb2_linear_solver solver, float trustRegionRadius = 1.0f) {
+    opt_.linearSolver = solver;
+    opt_.trustRegionRadius = trustRegionRadius;
+    step_.reset();
+  }
   // the whole SolverT loop in one C-ABI call (iterations, stopping rule and error history on the device)
   double solveOnDevice(Eigen::VectorX<float>& params) {
     if (size_t(params.size()) != this->numParameters_) throw std::runtime_error("params.size() == numParameters_"); // solver.cpp:77

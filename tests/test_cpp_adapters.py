@@ -162,6 +162,8 @@ def _part2_source(ch, efs, b, theta0, iterations, regularization):
     L += ["    { GaussNewtonSolverT<float> stock(o, &fn); VectorXf p = p0; const double e = stock.solve(p); show(\"stock\", e, p); }   // momentum's solver loop, device getJtJR",
           "    { momentum_b200::CudaGaussNewtonSolver cuda(o, &fn); VectorXf p = p0; const double e = cuda.solve(p); show(\"solvert\", e, p);  // SolverT::solve, device doIteration",
           "      VectorXf q = p0; const double e2 = cuda.solveOnDevice(q); show(\"device\", e2, q); }                                            // whole loop on the device",
+          "    { momentum_b200::CudaGaussNewtonSolver cuda(o, &fn); cuda.setLinearSolver(MB2_LINEAR_SOLVER_QR); VectorXf q = p0; const double e = cuda.solveOnDevice(q); show(\"qr\", e, q);  // GaussNewtonSolverQRT's step",
+          "      cuda.setLinearSolver(MB2_LINEAR_SOLVER_TRUST_REGION_QR, 1.0f); VectorXf r = p0; const double e2 = cuda.solveOnDevice(r); show(\"trustregion\", e2, r); }                        // TrustRegionQRT's iteration",
           "    { VectorXf g; const double e = fn.getGradient(p0, g); show(\"gradient\", e, g); }",
           "    struct Other : SkeletonErrorFunctionT<float> { using SkeletonErrorFunctionT<float>::SkeletonErrorFunctionT; };",
           "    try { fn.addErrorFunction(std::make_shared<Other>(ch.skeleton, ch.parameterTransform)); std::printf(\"unsupported accepted\\n\"); } catch (const std::runtime_error&) { std::printf(\"unsupported rejected\\n\"); }",
@@ -209,7 +211,7 @@ def test_adapter_part2_momentum_objects_solve_on_the_gpu_and_match_the_oracle():
     its, reg, b = 5, 0.05, 1
     p = _build_and_run_part2(_part2_source(ch, efs, b, theta0[b], its, reg))
     assert p.returncode == 0, p.stdout + p.stderr
-    got = {ln.split()[0]: np.array(ln.split()[1:], np.float64) for ln in p.stdout.splitlines() if ln and ln.split()[0] in ("stock", "solvert", "device", "gradient")}
+    got = {ln.split()[0]: np.array(ln.split()[1:], np.float64) for ln in p.stdout.splitlines() if ln and ln.split()[0] in ("stock", "solvert", "device", "gradient", "qr", "trustregion")}
     assert "unsupported rejected" in p.stdout
     orc = OracleFunction(ch, efs, "float32", instance=b)
     err, ref, _, _ = orc.solve(theta0[b].astype(np.float64), min_iterations=its, max_iterations=its, threshold=1.0, regularization=reg, use_block_jtj=True)
@@ -217,6 +219,12 @@ def test_adapter_part2_momentum_objects_solve_on_the_gpu_and_match_the_oracle():
         e, q = got[route][0], got[route][1:]
         assert np.max(np.abs(q - ref)) / max(1.0, np.max(np.abs(ref))) <= 2e-4, (route, np.max(np.abs(q - ref)))
         assert abs(e - err) <= 1e-3 * abs(err) + 1e-7, (route, e, err)
+    # the other two solver classes through setLinearSolver, each against the oracle's restatement of that class
+    for route, kw in (("qr", dict(regularization=reg, qr_solver=True)), ("trustregion", dict(trust_region_qr=True))):
+        err_r, ref_r, _, _ = orc.solve(theta0[b].astype(np.float64), min_iterations=its, max_iterations=its, threshold=1.0, **kw)
+        e, q = got[route][0], got[route][1:]
+        assert np.max(np.abs(q - ref_r)) / max(1.0, np.max(np.abs(ref_r))) <= 5e-4, (route, np.max(np.abs(q - ref_r)))
+        assert abs(e - err_r) <= 1e-3 * abs(err_r) + 1e-7, (route, e, err_r)
     _, Ho, go = orc.get_jtjr(theta0[b].astype(np.float64))
     g = got["gradient"][1:]
     assert g.shape[0] == ch.num_params and np.max(np.abs(g - 2 * go)) <= 2e-5 * max(1.0, np.abs(go).max())
